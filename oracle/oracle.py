@@ -1,0 +1,200 @@
+"""ctypes loader for the CPU ORACLE (test infrastructure -- see oracle/ssfm_oracle.hpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  `load()` returns the restated oracle (oracle/liboracle.so, built on demand
+with g++); `load_ref()` returns oracle/_ref/libssfm_ref.so, whose RANSAC driver loops are the
+reference's own RansacLib headers compiled from /root/reference (prebuilt; travels to the GPU box).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+class OrcOptions(C.Structure):
+    _fields_ = [
+        ("min_num_iterations", C.c_uint32), ("max_num_iterations", C.c_uint32),
+        ("success_probability", C.c_double), ("squared_inlier_threshold", C.c_double),
+        ("random_seed", C.c_uint32), ("num_lo_steps", C.c_int32),
+        ("threshold_multiplier", C.c_double), ("num_lsq_iterations", C.c_int32),
+        ("min_sample_multiplicator", C.c_int32), ("non_min_sample_multiplier", C.c_int32),
+        ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
+        ("solver_kind", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
+        ("legacy_budget", C.c_int32), ("legacy_prob_success", C.c_double),
+    ]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [
+        ("E", C.c_double * 9), ("r", C.c_double * 3), ("t", C.c_double * 3),
+        ("num_iterations", C.c_uint32), ("best_num_inliers", C.c_int32),
+        ("best_model_score", C.c_double), ("inlier_ratio", C.c_double),
+        ("number_lo_iterations", C.c_int32), ("status", C.c_int32), ("evals", C.c_int64),
+    ]
+
+
+def default_options(**kw):
+    """RansacLib defaults (include/RansacLib/ransac.h:49-73)."""
+    o = OrcOptions(100, 10000, 0.9999, 1.0, 0, 10, 2.0 ** 0.5, 4, 7, 3, 50, 0, 0, 0, 0, 512, 0.999)
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def pipeline_options(thr2, **kw):
+    """estimate_pairwise's options (examples/spherical_sfm_tools.cpp:314-318)."""
+    return default_options(squared_inlier_threshold=thr2, num_lo_steps=0, num_lsq_iterations=0,
+                           final_least_squares=1, **kw)
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Oracle:
+    def __init__(self, path):
+        self.path = path
+        L = self.lib = C.CDLL(path)
+        L.orc_is_reference.restype = C.c_int
+        L.orc_estimate_batch.restype = C.c_double
+        L.orc_score_batch.restype = C.c_double
+        L.orc_estimate_pair.restype = C.c_int
+        L.orc_solve.restype = C.c_int
+        self.is_reference = bool(L.orc_is_reference())
+
+    def philox_sample(self, seed, pair, it, k, n):
+        idx = np.zeros(k, np.int32)
+        self.lib.orc_philox_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(it), k, n, _ip(idx))
+        return idx
+
+    def solve(self, rays, sample, kind=0):
+        rays = np.ascontiguousarray(rays, np.float64)
+        sample = np.ascontiguousarray(sample, np.int32)
+        models = np.zeros((4, 6))
+        nm = self.lib.orc_solve(_dp(rays), _ip(sample), len(sample), kind, _dp(models))
+        return nm, models
+
+    def sampson(self, E, rays):
+        rays = np.ascontiguousarray(rays, np.float64)
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        out = np.zeros(len(rays))
+        self.lib.orc_sampson(_dp(E), _dp(rays), len(rays), _dp(out))
+        return out
+
+    def score(self, E, rays, thr2):
+        rays = np.ascontiguousarray(rays, np.float64)
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        s = C.c_double()
+        n = C.c_int()
+        self.lib.orc_score(_dp(E), _dp(rays), len(rays), C.c_double(thr2), C.byref(s), C.byref(n))
+        return s.value, n.value
+
+    def decompose(self, E, inward=False):
+        E = np.ascontiguousarray(E, np.float64).reshape(9)
+        r = np.zeros(3)
+        t = np.zeros(3)
+        self.lib.orc_decompose(_dp(E), int(inward), _dp(r), _dp(t))
+        return r, t
+
+    def make_E(self, r, inward=False):
+        r = np.ascontiguousarray(r, np.float64)
+        E = np.zeros(9)
+        self.lib.orc_make_E(_dp(r), int(inward), _dp(E))
+        return E.reshape(3, 3)
+
+    def lm_refit(self, rays, sample, E, inward=False):
+        rays = np.ascontiguousarray(rays, np.float64)
+        sample = np.ascontiguousarray(sample, np.int32)
+        E = np.array(E, np.float64).reshape(9).copy()
+        it = C.c_int()
+        term = C.c_int()
+        costs = np.zeros(2)
+        self.lib.orc_lm_refit(_dp(rays), _ip(sample), len(sample), int(inward), _dp(E), C.byref(it), C.byref(term),
+                              _dp(costs))
+        return E.reshape(3, 3), it.value, term.value, costs
+
+    def lo_shuffle(self, seed, sizes, targets):
+        sizes = np.ascontiguousarray(sizes, np.int32)
+        targets = np.ascontiguousarray(targets, np.int32)
+        out = np.zeros(int(targets.sum()), np.int32)
+        self.lib.orc_lo_shuffle(C.c_uint32(seed), len(sizes), _ip(sizes), _ip(targets), _ip(out))
+        return out
+
+    def estimate_pair(self, rays, opt, pair_id=0):
+        rays = np.ascontiguousarray(rays, np.float64)
+        res = OrcResult()
+        inl = np.zeros(max(len(rays), 1), np.int32)
+        n = self.lib.orc_estimate_pair(_dp(rays), len(rays), C.byref(opt), C.c_uint32(pair_id), C.byref(res), _ip(inl))
+        return res, inl[:max(n, 0)].copy()
+
+    def estimate_batch(self, rays, offsets, opt, first_pair_id=0, nthreads=0):
+        rays = np.ascontiguousarray(rays, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        P = len(offsets) - 1
+        res = (OrcResult * P)()
+        secs = self.lib.orc_estimate_batch(_dp(rays), offsets.ctypes.data_as(C.POINTER(C.c_int64)), P, C.byref(opt),
+                                           C.c_uint32(first_pair_id), nthreads, res)
+        return res, secs
+
+    def score_batch(self, models6, rays, thr2, nthreads=0):
+        models6 = np.ascontiguousarray(models6, np.float64)
+        rays = np.ascontiguousarray(rays, np.float64)
+        M = len(models6)
+        scores = np.zeros(M)
+        ninl = np.zeros(M, np.int32)
+        secs = self.lib.orc_score_batch(_dp(models6), M, _dp(rays), len(rays), C.c_double(thr2), nthreads, _dp(scores),
+                                        _ip(ninl))
+        return scores, ninl, secs
+
+
+def _compiler():
+    for c in ("/usr/bin/g++", "g++"):
+        if os.path.exists(c) or c == "g++":
+            return c
+
+
+def build(ref=True, force=False):
+    """Compile liboracle.so and (when /root/reference is present) _ref/libssfm_ref.so."""
+    srcs = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "oracle_capi.h", "ssfm_oracle.hpp", "lomsac.hpp")]
+    newest = max(os.path.getmtime(s) for s in srcs)
+    flags = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-shared"]
+    out = os.path.join(_DIR, "liboracle.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < newest:
+        subprocess.check_call([_compiler()] + flags + ["-o", out, srcs[0]])
+    refroot = os.environ.get("SSFM_REFERENCE_ROOT", "/root/reference")
+    if ref and os.path.isdir(os.path.join(refroot, "include", "RansacLib")):
+        os.makedirs(os.path.join(_DIR, "_ref"), exist_ok=True)
+        rout = os.path.join(_DIR, "_ref", "libssfm_ref.so")
+        if force or not os.path.exists(rout) or os.path.getmtime(rout) < newest:
+            subprocess.check_call([_compiler()] + flags + ["-DSSFM_USE_REFERENCE_RANSACLIB",
+                                                         "-I" + os.path.join(refroot, "include"),
+                                                         "-I" + os.path.join(refroot, "evaluation"),
+                                                         "-o", rout, srcs[0]])
+
+
+_cache = {}
+
+
+def load():
+    if "o" not in _cache:
+        build(ref=False)
+        _cache["o"] = Oracle(os.path.join(_DIR, "liboracle.so"))
+    return _cache["o"]
+
+
+def load_ref():
+    """The reference-RansacLib-driven oracle, or None when it was never built (no /root/reference)."""
+    if "r" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_ref.so")
+        _cache["r"] = Oracle(p) if os.path.exists(p) else None
+    return _cache["r"]

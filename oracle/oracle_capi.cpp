@@ -1,0 +1,262 @@
+// oracle_capi.cpp -- extern "C" surface of the CPU ORACLE (test infrastructure; see ssfm_oracle.hpp).
+//
+// Built two ways by oracle/Makefile:
+//   liboracle.so            : driver loops = the restatement in lomsac.hpp (source-only, travels)
+//   _ref/libssfm_ref.so     : -DSSFM_USE_REFERENCE_RANSACLIB, driver loops = the reference's OWN
+//                             headers, compiled where they lie:
+//                               /root/reference/include/RansacLib/{ransac,sampling,utils}.h
+//                               /root/reference/evaluation/vanilla_ransac.h
+//                             (header-only, <random> only -> builds without Eigen/Ceres).
+//                             The estimator plugged into them is the restated SphericalEstimator
+//                             (the reference's own src/*.cpp need Eigen + Ceres: not buildable here).
+#include "oracle_capi.h"
+
+#include <chrono>
+#include <cstring>
+
+#include "lomsac.hpp"
+#include "ssfm_oracle.hpp"
+
+#include <atomic>
+#include <thread>
+
+#ifdef SSFM_USE_REFERENCE_RANSACLIB
+#include <RansacLib/ransac.h>
+#include <vanilla_ransac.h>
+#endif
+
+using namespace ssfm_oracle;
+
+namespace {
+
+// Dynamic-schedule parallel for over [0, n) on `nthreads` host threads (the role of
+// `#pragma omp parallel for` at examples/spherical_sfm_tools.cpp:332; std::thread so the oracle
+// builds without libgomp).
+template <class F>
+void parallel_for(int n, int nthreads, F f) {
+  if (nthreads <= 0) nthreads = (int)std::thread::hardware_concurrency();
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > n) nthreads = n > 0 ? n : 1;
+  if (nthreads == 1) {
+    for (int i = 0; i < n; ++i) f(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nthreads; ++t)
+    pool.emplace_back([&]() {
+      for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) f(i);
+    });
+  for (auto& th : pool) th.join();
+}
+
+Options to_options(const OrcOptions& o) {
+  Options p;
+  p.min_num_iterations = o.min_num_iterations;
+  p.max_num_iterations = o.max_num_iterations;
+  p.success_probability = o.success_probability;
+  p.squared_inlier_threshold = o.squared_inlier_threshold;
+  p.random_seed = o.random_seed;
+  p.num_lo_steps = o.num_lo_steps;
+  p.threshold_multiplier = o.threshold_multiplier;
+  p.num_lsq_iterations = o.num_lsq_iterations;
+  p.min_sample_multiplicator = o.min_sample_multiplicator;
+  p.non_min_sample_multiplier = o.non_min_sample_multiplier;
+  p.lo_starting_iterations = o.lo_starting_iterations;
+  p.final_least_squares = o.final_least_squares != 0;
+  return p;
+}
+
+int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_id, OrcResult* out, int* inlier_idx) {
+  SphericalEstimator est(corr, n, (SolverKind)o.solver_kind, o.inward != 0, pair_id);
+  Mat3 E;
+  for (int i = 0; i < 9; ++i) E.m[i] = 0.0;
+  Statistics st;
+  const Options opt = to_options(o);
+  typedef PhiloxSampling<SphericalEstimator> Sampler;
+#ifdef SSFM_USE_REFERENCE_RANSACLIB
+  if (o.driver == 0 || o.driver == 1) {
+    ransac_lib::LORansacOptions ro;
+    ro.min_num_iterations_ = o.min_num_iterations;
+    ro.max_num_iterations_ = o.max_num_iterations;
+    ro.success_probability_ = o.success_probability;
+    ro.squared_inlier_threshold_ = o.squared_inlier_threshold;
+    ro.random_seed_ = o.random_seed;
+    ro.num_lo_steps_ = o.num_lo_steps;
+    ro.threshold_multiplier_ = o.threshold_multiplier;
+    ro.num_lsq_iterations_ = o.num_lsq_iterations;
+    ro.min_sample_multiplicator_ = o.min_sample_multiplicator;
+    ro.non_min_sample_multiplier_ = o.non_min_sample_multiplier;
+    ro.lo_starting_iterations_ = o.lo_starting_iterations;
+    ro.final_least_squares_ = o.final_least_squares != 0;
+    ransac_lib::RansacStatistics rs;
+    if (o.driver == 0) {
+      ransac_lib::LocallyOptimizedMSAC<Mat3, std::vector<Mat3>, SphericalEstimator, Sampler> ransac;
+      ransac.EstimateModel(ro, est, &E, &rs);
+    } else {
+      ransac_lib::VanillaMSAC<Mat3, std::vector<Mat3>, SphericalEstimator, Sampler> ransac;
+      ransac.EstimateModel(ro, est, &E, &rs);
+    }
+    st.num_iterations = rs.num_iterations;
+    st.best_num_inliers = rs.best_num_inliers;
+    st.best_model_score = rs.best_model_score;
+    st.inlier_ratio = rs.inlier_ratio;
+    st.inlier_indices = rs.inlier_indices;
+    st.number_lo_iterations = rs.number_lo_iterations;
+  } else {
+    legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
+  }
+#else
+  if (o.driver == 0)
+    lo_msac<SphericalEstimator, Sampler>(opt, est, &E, &st);
+  else if (o.driver == 1)
+    vanilla_msac<SphericalEstimator, Sampler>(opt, est, &E, &st);
+  else
+    legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
+#endif
+  std::memcpy(out->E, E.m, sizeof(E.m));
+  out->num_iterations = st.num_iterations;
+  out->best_num_inliers = st.best_num_inliers;
+  out->best_model_score = st.best_model_score;
+  out->inlier_ratio = st.inlier_ratio;
+  out->number_lo_iterations = st.number_lo_iterations;
+  out->evals = est.evals_;
+  for (int i = 0; i < 3; ++i) out->r[i] = out->t[i] = 0.0;
+  if (n < 3) {
+    out->status = 1;
+  } else if (!(st.best_model_score < std::numeric_limits<double>::max())) {
+    out->status = 2;
+  } else {
+    out->status = 0;
+    decompose_spherical_essential_matrix(E, o.inward != 0, out->r, out->t);
+  }
+  if (inlier_idx) {
+    for (size_t i = 0; i < st.inlier_indices.size(); ++i) inlier_idx[i] = st.inlier_indices[i];
+  }
+  return st.best_num_inliers;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_is_reference(void) {
+#ifdef SSFM_USE_REFERENCE_RANSACLIB
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx) {
+  philox_sample(seed, pair, iter, k, n, idx);
+}
+
+int orc_solve(const double* rays, const int* sample, int n, int kind, double* models) {
+  double m[4][6];
+  for (int k = 0; k < 4; ++k)
+    for (int i = 0; i < 6; ++i) m[k][i] = std::numeric_limits<double>::quiet_NaN();
+  const int nm = solve_spherical(reinterpret_cast<const RayPair*>(rays), sample, n, (SolverKind)kind, m);
+  std::memcpy(models, m, sizeof(m));
+  return nm;
+}
+
+void orc_sampson(const double* E9, const double* rays, int n, double* out) {
+  Mat3 E;
+  std::memcpy(E.m, E9, sizeof(E.m));
+  const RayPair* c = reinterpret_cast<const RayPair*>(rays);
+  for (int i = 0; i < n; ++i) out[i] = sampson_sq(E, c[i]);
+}
+
+void orc_score(const double* E9, const double* rays, int n, double thr, double* score, int* ninl) {
+  Mat3 E;
+  std::memcpy(E.m, E9, sizeof(E.m));
+  const RayPair* c = reinterpret_cast<const RayPair*>(rays);
+  double s = 0.0;
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    const double e = sampson_sq(E, c[i]);
+    s += std::min(e, thr);
+    cnt += (e < thr);
+  }
+  *score = s;
+  *ninl = cnt;
+}
+
+void orc_decompose(const double* E9, int inward, double* r, double* t) {
+  Mat3 E;
+  std::memcpy(E.m, E9, sizeof(E.m));
+  decompose_spherical_essential_matrix(E, inward != 0, r, t);
+}
+
+void orc_make_E(const double* r, int inward, double* E9) {
+  const Mat3 E = make_spherical_essential_matrix(so3exp(r), inward != 0);
+  std::memcpy(E9, E.m, sizeof(E.m));
+}
+
+void orc_lm_refit(const double* rays, const int* sample, int n, int inward, double* E9, int* iters, int* term,
+                  double* costs) {
+  Mat3 E;
+  std::memcpy(E.m, E9, sizeof(E.m));
+  double r[3], t[3];
+  decompose_spherical_essential_matrix(E, inward != 0, r, t);
+  double x[6] = {r[0], r[1], r[2], 0, 0, inward ? 1.0 : -1.0};
+  const LMSummary s = lm_refit(reinterpret_cast<const RayPair*>(rays), sample, n, inward != 0, x);
+  E = make_spherical_essential_matrix(so3exp(x), inward != 0);
+  std::memcpy(E9, E.m, sizeof(E.m));
+  if (iters) *iters = s.iterations;
+  if (term) *term = s.termination;
+  if (costs) { costs[0] = s.initial_cost; costs[1] = s.final_cost; }
+}
+
+// The LO generator's draw sequence: ncalls consecutive shuffle_and_resize() calls on iota
+// vectors of the given sizes, one std::mt19937 seeded once (ransac.h:143-144, utils.h:34-52).
+void orc_lo_shuffle(uint32_t seed, int ncalls, const int* sizes, const int* targets, int* out) {
+  std::mt19937 rng;
+  rng.seed(seed);
+  int o = 0;
+  for (int c = 0; c < ncalls; ++c) {
+    std::vector<int> v(sizes[c]);
+    for (int i = 0; i < sizes[c]; ++i) v[i] = i;
+    shuffle_and_resize(targets[c], &rng, &v);
+    for (int i = 0; i < targets[c]; ++i) out[o++] = v[i];
+  }
+}
+
+int orc_estimate_pair(const double* rays, int n, const OrcOptions* opt, uint32_t pair_id, OrcResult* out,
+                      int* inlier_idx) {
+  return estimate_one(reinterpret_cast<const RayPair*>(rays), n, *opt, pair_id, out, inlier_idx);
+}
+
+double orc_estimate_batch(const double* rays, const int64_t* offsets, int npairs, const OrcOptions* opt,
+                          uint32_t first_pair_id, int nthreads, OrcResult* out) {
+  const RayPair* c = reinterpret_cast<const RayPair*>(rays);
+  const auto t0 = std::chrono::steady_clock::now();
+  parallel_for(npairs, nthreads, [&](int p) {
+    estimate_one(c + offsets[p], (int)(offsets[p + 1] - offsets[p]), *opt, first_pair_id + (uint32_t)p, &out[p], nullptr);
+  });
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+double orc_score_batch(const double* models6, int nmodels, const double* rays, int n, double thr, int nthreads,
+                       double* scores, int* ninl) {
+  const RayPair* c = reinterpret_cast<const RayPair*>(rays);
+  const auto t0 = std::chrono::steady_clock::now();
+  parallel_for(nmodels, nthreads, [&](int m) {
+    const Mat3 E = mat_from_p(models6 + 6 * (size_t)m);
+    double s = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < n; ++i) {
+      const double e = sampson_sq(E, c[i]);
+      s += std::min(e, thr);
+      cnt += (e < thr);
+    }
+    scores[m] = s;
+    ninl[m] = cnt;
+  });
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

@@ -1,0 +1,1261 @@
+// ssfm_oracle.hpp -- CPU float64 ORACLE for the spherical relative-pose hot path.
+//
+// THIS IS TEST INFRASTRUCTURE, NOT THE PRODUCT.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may build, link or call it.
+// The product path (spherical-sfm_b200/csrc, libssfm_b200.so) never includes this file.
+//
+// It is a plain C++17 restatement (no Eigen / Ceres / PoseLib -- none are installed here)
+// of the reference's algorithm, each function citing the reference file:line it follows
+// (paths relative to /root/reference).  Parity status:
+//   * control flow (LO-MSAC / VanillaMSAC): PINNED -- checked bit-for-bit against the
+//     reference's own RansacLib headers compiled in oracle/_ref (see ref_ransaclib.cpp).
+//   * 3-point solvers: pinned by the generator's ground truth (noise-free best-of-4
+//     Frobenius error ~1e-14, evaluation/scripts/run_stability_experiment.py:11,68-83) and
+//     by an independent LAPACK (numpy) solve of the same polynomial system in tests/.
+//     Models that come from COMPLEX roots are implementation-defined in the reference
+//     (real part of an Eigen eigenvector whose phase depends on Eigen's QR iteration
+//     history, src/spherical_solvers.cpp:294-297); here they are the major axis of the
+//     complex solution line (basis independent).  "parity unpinned" for those.
+//   * Ceres LM refit: restated from Ceres 2.2.0 defaults (docker/Dockerfile:50); Ceres is
+//     not installed -> "parity unpinned" beyond the 0.01 deg pose tolerance.
+//   * Sturm root bracketing (jonathanventura/polynomial, unpinned HEAD) -> "parity unpinned".
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <vector>
+
+namespace ssfm_oracle {
+
+// ---------------------------------------------------------------------------------------
+// Data: one correspondence = (u, v) = two 3-vectors, memory-identical to
+// sphericalsfm::RayPair = std::pair<Eigen::Vector3d,Eigen::Vector3d> (include/sphericalsfm/ray.h:8-10).
+// Epipolar convention v^T E u = 0 (src/spherical_solvers.cpp:119).
+// ---------------------------------------------------------------------------------------
+struct RayPair {
+  double u[3];
+  double v[3];
+};
+
+enum SolverKind { ACTION_MATRIX = 0, POLYNOMIAL = 1, FAST_STURM = 2 };
+
+// A spherical essential matrix has the 6-parameter structure (src/spherical_solvers.cpp:299-303)
+//   E = | p0  p1  p2 |
+//       | p1 -p0  p3 |
+//       | p4  p5   0 |
+struct Mat3 {
+  double m[9];  // row-major
+  double& operator()(int r, int c) { return m[3 * r + c]; }
+  double operator()(int r, int c) const { return m[3 * r + c]; }
+};
+
+inline Mat3 mat_from_p(const double p[6]) {
+  Mat3 E;
+  E.m[0] = p[0]; E.m[1] = p[1];  E.m[2] = p[2];
+  E.m[3] = p[1]; E.m[4] = -p[0]; E.m[5] = p[3];
+  E.m[6] = p[4]; E.m[7] = p[5];  E.m[8] = 0.0;
+  return E;
+}
+
+// ---------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11).  This replaces the
+// reference's std::mt19937 minimal-sample stream (include/RansacLib/sampling.h:47-135) so
+// that the sample of iteration k of pair p is a pure function of (seed, p, k).
+// The product has its own implementation (csrc/philox.cuh); tests compare the two.
+// ---------------------------------------------------------------------------------------
+struct Philox4x32 {
+  static inline void round(uint32_t c[4], const uint32_t k[2]) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0];
+    const uint32_t n1 = lo1;
+    const uint32_t n2 = hi0 ^ c[3] ^ k[1];
+    const uint32_t n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  static inline void generate(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    uint32_t k[2] = {key[0], key[1]};
+    for (int r = 0; r < 10; ++r) {
+      round(c, k);
+      k[0] += 0x9E3779B9u;
+      k[1] += 0xBB67AE85u;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// Minimal sample of iteration `iter` of pair `pair`: k distinct indices in [0,N).
+// Same draw-with-rejection scheme as UniformSampling::DrawSample (sampling.h:81-97), with
+// the j-th raw draw = word (j%4) of Philox(counter=(iter, j/4, 0, 0), key=(seed, pair)),
+// mapped to [0,N) by the multiply-shift (x*N)>>32.
+inline void philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int N, int* idx) {
+  const uint32_t key[2] = {seed, pair};
+  uint32_t words[4];
+  uint32_t block = 0;
+  int used = 4;
+  for (int i = 0; i < k; ++i) {
+    bool dup = true;
+    while (dup) {
+      if (used == 4) {
+        const uint32_t ctr[4] = {iter, block++, 0u, 0u};
+        Philox4x32::generate(ctr, key, words);
+        used = 0;
+      }
+      idx[i] = (int)(((uint64_t)words[used++] * (uint64_t)(uint32_t)N) >> 32);
+      dup = false;
+      for (int j = 0; j < i; ++j)
+        if (idx[j] == idx[i]) { dup = true; break; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small dense linear algebra.
+// ---------------------------------------------------------------------------------------
+
+// Null-space basis used by all three solvers: B = last three columns of the Householder Q of
+// the column-pivoted QR of A^T (6 x n)  (src/spherical_solvers.cpp:124-125).  Pivot = largest
+// remaining column norm (Eigen::ColPivHouseholderQR), norms recomputed each step.
+// For n == 3 this is the 3-D null space of A; for n > 3 it is the orthogonal complement of
+// the three pivot rows (which is what the reference's "non-minimal" solve amounts to).
+inline void nullspace_colpiv_qr(const double* A /* n x 6 row-major */, int n, double B[6][3]) {
+  std::vector<double> M(6 * (size_t)n);  // M = A^T, 6 x n, M[r*n + c]
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < 6; ++j) M[(size_t)j * n + i] = A[(size_t)i * 6 + j];
+  const int steps = std::min(6, n);
+  double vs[6][6];
+  double taus[6];
+  for (int k = 0; k < steps; ++k) {
+    // pivot
+    int piv = k;
+    double best = -1.0;
+    for (int c = k; c < n; ++c) {
+      double s = 0.0;
+      for (int r = k; r < 6; ++r) s += M[(size_t)r * n + c] * M[(size_t)r * n + c];
+      if (s > best) { best = s; piv = c; }
+    }
+    if (piv != k)
+      for (int r = 0; r < 6; ++r) std::swap(M[(size_t)r * n + k], M[(size_t)r * n + piv]);
+    // Householder (Eigen makeHouseholder convention)
+    const double c0 = M[(size_t)k * n + k];
+    double tail2 = 0.0;
+    for (int r = k + 1; r < 6; ++r) tail2 += M[(size_t)r * n + k] * M[(size_t)r * n + k];
+    double tau, beta;
+    double v[6] = {0, 0, 0, 0, 0, 0};
+    v[k] = 1.0;
+    if (tail2 <= std::numeric_limits<double>::min()) {
+      tau = 0.0;
+      beta = c0;
+    } else {
+      beta = std::sqrt(c0 * c0 + tail2);
+      if (c0 >= 0.0) beta = -beta;
+      for (int r = k + 1; r < 6; ++r) v[r] = M[(size_t)r * n + k] / (c0 - beta);
+      tau = (beta - c0) / beta;
+    }
+    // apply H = I - tau v v^T to trailing columns
+    for (int c = k; c < n; ++c) {
+      double d = 0.0;
+      for (int r = k; r < 6; ++r) d += v[r] * M[(size_t)r * n + c];
+      d *= tau;
+      for (int r = k; r < 6; ++r) M[(size_t)r * n + c] -= d * v[r];
+    }
+    for (int r = 0; r < 6; ++r) vs[k][r] = v[r];
+    taus[k] = tau;
+  }
+  // Q = H0 H1 ... H_{steps-1};  columns 3..5 of Q = Q e_j
+  for (int j = 0; j < 3; ++j) {
+    double q[6] = {0, 0, 0, 0, 0, 0};
+    q[3 + j] = 1.0;
+    for (int k = steps - 1; k >= 0; --k) {
+      double d = 0.0;
+      for (int r = 0; r < 6; ++r) d += vs[k][r] * q[r];
+      d *= taus[k];
+      for (int r = 0; r < 6; ++r) q[r] -= d * vs[k][r];
+    }
+    for (int r = 0; r < 6; ++r) B[r][j] = q[r];
+  }
+}
+
+// G = C[:,0:6]^-1 C[:,6:10] by partial-pivot LU (Eigen PartialPivLU; spherical_solvers.cpp:279).
+inline bool lu_solve_6x6_4(const double C[6][10], double G[6][4]) {
+  double a[6][10];
+  std::memcpy(a, C, sizeof(a));
+  for (int k = 0; k < 6; ++k) {
+    int piv = k;
+    double best = std::fabs(a[k][k]);
+    for (int r = k + 1; r < 6; ++r)
+      if (std::fabs(a[r][k]) > best) { best = std::fabs(a[r][k]); piv = r; }
+    if (piv != k)
+      for (int c = 0; c < 10; ++c) std::swap(a[k][c], a[piv][c]);
+    const double d = a[k][k];
+    for (int r = k + 1; r < 6; ++r) {
+      const double f = a[r][k] / d;
+      for (int c = k; c < 10; ++c) a[r][c] -= f * a[k][c];
+    }
+  }
+  for (int j = 0; j < 4; ++j)
+    for (int r = 5; r >= 0; --r) {
+      double s = a[r][6 + j];
+      for (int c = r + 1; c < 6; ++c) s -= a[r][c] * G[c][j];
+      G[r][j] = s / a[r][r];
+    }
+  bool ok = true;
+  for (int r = 0; r < 6; ++r)
+    for (int j = 0; j < 4; ++j) ok = ok && std::isfinite(G[r][j]);
+  return ok;
+}
+
+// Eigenvalues of a real 4x4 matrix: Hessenberg reduction + Francis double-shift QR
+// (the EISPACK hqr algorithm, which Eigen::EigenSolver / RealSchur derive from;
+// used at src/spherical_solvers.cpp:287).  Returns false if it does not converge.
+inline bool eigenvalues_4x4(const double Min[4][4], double wr[4], double wi[4]) {
+  const int n = 4;
+  double a[4][4];
+  std::memcpy(a, Min, sizeof(a));
+  // --- reduce to Hessenberg form by stabilised elementary similarity (elmhes)
+  for (int m = 1; m < n - 1; ++m) {
+    double x = 0.0;
+    int i = m;
+    for (int j = m; j < n; ++j)
+      if (std::fabs(a[j][m - 1]) > std::fabs(x)) { x = a[j][m - 1]; i = j; }
+    if (i != m) {
+      for (int j = m - 1; j < n; ++j) std::swap(a[i][j], a[m][j]);
+      for (int j = 0; j < n; ++j) std::swap(a[j][i], a[j][m]);
+    }
+    if (x != 0.0) {
+      for (i = m + 1; i < n; ++i) {
+        double y = a[i][m - 1];
+        if (y != 0.0) {
+          y /= x;
+          a[i][m - 1] = y;
+          for (int j = m; j < n; ++j) a[i][j] -= y * a[m][j];
+          for (int j = 0; j < n; ++j) a[j][m] += y * a[j][i];
+        }
+      }
+    }
+  }
+  for (int i = 2; i < n; ++i)
+    for (int j = 0; j < i - 1; ++j) a[i][j] = 0.0;
+  // --- hqr
+  int nn = n - 1, its, l, m, k, mmin;
+  double z, y, x, w, v, u, t = 0.0, s, r = 0, q = 0, p = 0, anorm = 0.0;
+  for (int i = 0; i < n; ++i)
+    for (int j = std::max(i - 1, 0); j < n; ++j) anorm += std::fabs(a[i][j]);
+  while (nn >= 0) {
+    its = 0;
+    do {
+      for (l = nn; l >= 1; --l) {
+        s = std::fabs(a[l - 1][l - 1]) + std::fabs(a[l][l]);
+        if (s == 0.0) s = anorm;
+        if (std::fabs(a[l][l - 1]) + s == s) { a[l][l - 1] = 0.0; break; }
+      }
+      x = a[nn][nn];
+      if (l == nn) {
+        wr[nn] = x + t; wi[nn--] = 0.0;
+      } else {
+        y = a[nn - 1][nn - 1];
+        w = a[nn][nn - 1] * a[nn - 1][nn];
+        if (l == nn - 1) {
+          p = 0.5 * (y - x);
+          q = p * p + w;
+          z = std::sqrt(std::fabs(q));
+          x += t;
+          if (q >= 0.0) {
+            z = p + (p >= 0.0 ? std::fabs(z) : -std::fabs(z));
+            wr[nn - 1] = wr[nn] = x + z;
+            if (z != 0.0) wr[nn] = x - w / z;
+            wi[nn - 1] = wi[nn] = 0.0;
+          } else {
+            wr[nn - 1] = wr[nn] = x + p;
+            wi[nn - 1] = -(wi[nn] = z);
+          }
+          nn -= 2;
+        } else {
+          if (its == 60) return false;
+          if (its == 10 || its == 20) {
+            t += x;
+            for (int i = 0; i <= nn; ++i) a[i][i] -= x;
+            s = std::fabs(a[nn][nn - 1]) + std::fabs(a[nn - 1][nn - 2]);
+            y = x = 0.75 * s;
+            w = -0.4375 * s * s;
+          }
+          ++its;
+          for (m = nn - 2; m >= l; --m) {
+            z = a[m][m];
+            r = x - z;
+            s = y - z;
+            p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
+            q = a[m + 1][m + 1] - z - r - s;
+            r = a[m + 2][m + 1];
+            s = std::fabs(p) + std::fabs(q) + std::fabs(r);
+            p /= s; q /= s; r /= s;
+            if (m == l) break;
+            u = std::fabs(a[m][m - 1]) * (std::fabs(q) + std::fabs(r));
+            v = std::fabs(p) * (std::fabs(a[m - 1][m - 1]) + std::fabs(z) + std::fabs(a[m + 1][m + 1]));
+            if (u + v == v) break;
+          }
+          for (int i = m + 2; i <= nn; ++i) {
+            a[i][i - 2] = 0.0;
+            if (i != m + 2) a[i][i - 3] = 0.0;
+          }
+          for (k = m; k <= nn - 1; ++k) {
+            if (k != m) {
+              p = a[k][k - 1];
+              q = a[k + 1][k - 1];
+              r = 0.0;
+              if (k != nn - 1) r = a[k + 2][k - 1];
+              if ((x = std::fabs(p) + std::fabs(q) + std::fabs(r)) != 0.0) { p /= x; q /= x; r /= x; }
+            }
+            const double sg = std::sqrt(p * p + q * q + r * r);
+            if ((s = (p >= 0.0 ? sg : -sg)) != 0.0) {
+              if (k == m) {
+                if (l != m) a[k][k - 1] = -a[k][k - 1];
+              } else {
+                a[k][k - 1] = -s * x;
+              }
+              p += s;
+              x = p / s; y = q / s; z = r / s;
+              q /= p; r /= p;
+              for (int j = k; j <= nn; ++j) {
+                p = a[k][j] + q * a[k + 1][j];
+                if (k != nn - 1) { p += r * a[k + 2][j]; a[k + 2][j] -= p * z; }
+                a[k + 1][j] -= p * y;
+                a[k][j] -= p * x;
+              }
+              mmin = nn < k + 3 ? nn : k + 3;
+              for (int i = l; i <= mmin; ++i) {
+                p = x * a[i][k] + y * a[i][k + 1];
+                if (k != nn - 1) { p += z * a[i][k + 2]; a[i][k + 2] -= p * r; }
+                a[i][k + 1] -= p * q;
+                a[i][k] -= p;
+              }
+            }
+          }
+        }
+      }
+    } while (l < nn - 1);
+  }
+  return true;
+}
+
+// Null vector of a (nearly) singular complex 4x4 matrix by Gaussian elimination with
+// complete pivoting: after 3 elimination steps the remaining pivot is ~0; back-substitute
+// with the free unknown = 1.
+inline void null_vector_c4(std::complex<double> a[4][4], std::complex<double> x[4]) {
+  int colperm[4] = {0, 1, 2, 3};
+  for (int k = 0; k < 3; ++k) {
+    int pr = k, pc = k;
+    double best = -1.0;
+    for (int r = k; r < 4; ++r)
+      for (int c = k; c < 4; ++c) {
+        const double m = std::abs(a[r][c]);
+        if (m > best) { best = m; pr = r; pc = c; }
+      }
+    if (pr != k)
+      for (int c = 0; c < 4; ++c) std::swap(a[k][c], a[pr][c]);
+    if (pc != k) {
+      for (int r = 0; r < 4; ++r) std::swap(a[r][k], a[r][pc]);
+      std::swap(colperm[k], colperm[pc]);
+    }
+    for (int r = k + 1; r < 4; ++r) {
+      const std::complex<double> f = a[r][k] / a[k][k];
+      for (int c = k; c < 4; ++c) a[r][c] -= f * a[k][c];
+    }
+  }
+  std::complex<double> y[4];
+  y[3] = 1.0;
+  for (int r = 2; r >= 0; --r) {
+    std::complex<double> s = 0.0;
+    for (int c = r + 1; c < 4; ++c) s -= a[r][c] * y[c];
+    y[r] = s / a[r][r];
+  }
+  for (int i = 0; i < 4; ++i) x[colperm[i]] = y[i];
+}
+
+// Canonical real representative of a projective complex 6-vector pc = a + i b:
+// the unit vector along the major axis of { Re(e^{i th} pc) }.  For a real solution (b = 0)
+// this is a/|a|.  Basis independent; a conjugate pair maps to the same model (twice), which
+// mirrors the reference returning Re(eigenvector) for both members of a pair.
+inline void canonical_real_p(const std::complex<double> pc[6], double p[6]) {
+  double aa = 0, bb = 0, ab = 0;
+  for (int i = 0; i < 6; ++i) {
+    aa += pc[i].real() * pc[i].real();
+    bb += pc[i].imag() * pc[i].imag();
+    ab += pc[i].real() * pc[i].imag();
+  }
+  double c = 1.0, s = 0.0;
+  if (bb > 0.0) {
+    const double th = 0.5 * std::atan2(-2.0 * ab, aa - bb);
+    c = std::cos(th);
+    s = std::sin(th);
+  }
+  double nrm = 0.0;
+  for (int i = 0; i < 6; ++i) {
+    p[i] = pc[i].real() * c - pc[i].imag() * s;
+    nrm += p[i] * p[i];
+  }
+  // ||E||_F^2 = 2 p0^2 + 2 p1^2 + p2^2 + p3^2 + p4^2 + p5^2  (Esoln /= Esoln.norm(), :305)
+  const double f2 = nrm + p[0] * p[0] + p[1] * p[1];
+  const double inv = 1.0 / std::sqrt(f2);
+  for (int i = 0; i < 6; ++i) p[i] *= inv;
+}
+
+// ---------------------------------------------------------------------------------------
+// The polynomial system.  p = x B0 + y B1 + z B2; the six cubic constraints are rows
+// [T10, T20, T00, T21, T12, T22] of T = 2 E E^T E - tr(E E^T) E on the structured E
+// (src/spherical_solvers.cpp:271-277 builds the same 6x10 matrix by a
+// hand-expanded CSE).  Here they are built by polynomial arithmetic on linear forms.
+// Canonical monomial orders:
+//   quadratic: xx xy xz yy yz zz          cubic: xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+// ---------------------------------------------------------------------------------------
+struct Lin { double c[3]; };
+struct Quad { double c[6]; };
+struct Cub { double c[10]; };
+
+inline Quad qmul(const Lin& l, const Lin& m) {
+  Quad q;
+  q.c[0] = l.c[0] * m.c[0];
+  q.c[1] = l.c[0] * m.c[1] + l.c[1] * m.c[0];
+  q.c[2] = l.c[0] * m.c[2] + l.c[2] * m.c[0];
+  q.c[3] = l.c[1] * m.c[1];
+  q.c[4] = l.c[1] * m.c[2] + l.c[2] * m.c[1];
+  q.c[5] = l.c[2] * m.c[2];
+  return q;
+}
+inline Quad qlin(double a, const Quad& A, double b, const Quad& B, double c, const Quad& C, double d,
+                 const Quad& D) {
+  Quad q;
+  for (int i = 0; i < 6; ++i) q.c[i] = a * A.c[i] + b * B.c[i] + c * C.c[i] + d * D.c[i];
+  return q;
+}
+inline Quad qlin2(double a, const Quad& A, double b, const Quad& B) {
+  Quad q;
+  for (int i = 0; i < 6; ++i) q.c[i] = a * A.c[i] + b * B.c[i];
+  return q;
+}
+inline Cub cmul(const Lin& l, const Quad& q) {
+  Cub r;
+  const double lx = l.c[0], ly = l.c[1], lz = l.c[2];
+  r.c[0] = lx * q.c[0];
+  r.c[1] = lx * q.c[1] + ly * q.c[0];
+  r.c[2] = lx * q.c[2] + lz * q.c[0];
+  r.c[3] = lx * q.c[3] + ly * q.c[1];
+  r.c[4] = lx * q.c[4] + ly * q.c[2] + lz * q.c[1];
+  r.c[5] = lx * q.c[5] + lz * q.c[2];
+  r.c[6] = ly * q.c[3];
+  r.c[7] = ly * q.c[4] + lz * q.c[3];
+  r.c[8] = ly * q.c[5] + lz * q.c[4];
+  r.c[9] = lz * q.c[5];
+  return r;
+}
+inline Cub cadd(const Cub& a, const Cub& b, double sb = 1.0) {
+  Cub r;
+  for (int i = 0; i < 10; ++i) r.c[i] = a.c[i] + sb * b.c[i];
+  return r;
+}
+
+// Column (monomial) order of the 6x10 coefficient matrix per solver variant, as indices into
+// the canonical cubic order:
+//   action matrix: x3 x2y xy2 y3 x2z xyz | y2z xz2 yz2 z3   (spherical_solvers.cpp:271-279)
+//   polynomial   : x3 x2y xy2 x2z xyz xz2 | y3 y2z yz2 z3   (:559-621)
+//   fast (Sturm) : x3 x2y xy2 y3 y2z yz2 | x2z xyz xz2 z3   (spherical_fast_estimator.cpp:207-215)
+inline const int* column_order(SolverKind kind) {
+  static const int am[10] = {0, 1, 3, 6, 2, 4, 7, 5, 8, 9};
+  static const int po[10] = {0, 1, 3, 2, 4, 5, 6, 7, 8, 9};
+  static const int fa[10] = {0, 1, 3, 6, 7, 8, 2, 4, 5, 9};
+  return kind == ACTION_MATRIX ? am : (kind == POLYNOMIAL ? po : fa);
+}
+
+inline void build_constraints(const double B[6][3], SolverKind kind, double C[6][10]) {
+  Lin e[6];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 3; ++j) e[i].c[j] = B[i][j];
+  const Quad q22 = qmul(e[2], e[2]), q33 = qmul(e[3], e[3]), q44 = qmul(e[4], e[4]), q55 = qmul(e[5], e[5]);
+  const Quad q23 = qmul(e[2], e[3]), q45 = qmul(e[4], e[5]);
+  const Quad q24 = qmul(e[2], e[4]), q35 = qmul(e[3], e[5]), q25 = qmul(e[2], e[5]), q34 = qmul(e[3], e[4]);
+  const Quad S1 = qlin(-1, q22, -1, q33, 1, q44, 1, q55);  // -e2^2 - e3^2 + e4^2 + e5^2
+  const Quad S2 = qlin(1, q22, -1, q33, 1, q44, -1, q55);
+  const Quad S3 = qlin2(2, q23, 2, q45);
+  const Quad S4 = qlin2(2, q23, -2, q45);
+  const Quad S5 = qlin(-1, q22, 1, q33, 1, q44, -1, q55);
+  const Quad S6 = qlin2(2, q24, -2, q35);
+  const Quad S7 = qlin2(2, q25, 2, q34);
+  Cub rows[6];
+  rows[0] = cadd(cmul(e[0], S4), cmul(e[1], S5));  // T10
+  rows[1] = cmul(e[4], S1);                        // T20
+  rows[2] = cadd(cmul(e[0], S2), cmul(e[1], S3));  // T00
+  rows[3] = cmul(e[5], S1);                        // T21
+  rows[4] = cmul(e[3], S1);                        // T12 = -e3*S1
+  for (int i = 0; i < 10; ++i) rows[4].c[i] = -rows[4].c[i];
+  rows[5] = cadd(cmul(e[0], S6), cmul(e[1], S7));  // T22 = 2 det E
+  const int* ord = column_order(kind);
+  const double scale = (kind == POLYNOMIAL) ? 0.5 : 1.0;  // the polynomial variant's rows are halved
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 10; ++c) C[r][c] = scale * rows[r].c[ord[c]];
+}
+
+// Ferrari quartic in complex arithmetic, the Theia routine the reference vendors
+// (src/spherical_solvers.cpp:15-69).
+inline int solve_quartic_ferrari(double a, double b, double c, double d, double e, std::complex<double>* roots) {
+  const double a_pw2 = a * a, b_pw2 = b * b, a_pw3 = a_pw2 * a, b_pw3 = b_pw2 * b, a_pw4 = a_pw3 * a,
+               b_pw4 = b_pw3 * b;
+  const double alpha = -3.0 * b_pw2 / (8.0 * a_pw2) + c / a;
+  const double beta = b_pw3 / (8.0 * a_pw3) - b * c / (2.0 * a_pw2) + d / a;
+  const double gamma = -3.0 * b_pw4 / (256.0 * a_pw4) + b_pw2 * c / (16.0 * a_pw3) - b * d / (4.0 * a_pw2) + e / a;
+  const double alpha_pw2 = alpha * alpha, alpha_pw3 = alpha_pw2 * alpha;
+  const std::complex<double> P(-alpha_pw2 / 12.0 - gamma, 0);
+  const std::complex<double> Q(-alpha_pw3 / 108.0 + alpha * gamma / 3.0 - std::pow(beta, 2.0) / 8.0, 0);
+  const std::complex<double> R = -Q / 2.0 + std::sqrt(std::pow(Q, 2.0) / 4.0 + std::pow(P, 3.0) / 27.0);
+  const std::complex<double> U = std::pow(R, (1.0 / 3.0));
+  std::complex<double> y;
+  const double kEpsilon = 1e-8;
+  if (std::abs(U.real()) < kEpsilon) {
+    y = -5.0 * alpha / 6.0 - std::pow(Q, (1.0 / 3.0));
+  } else {
+    y = -5.0 * alpha / 6.0 - P / (3.0 * U) + U;
+  }
+  const std::complex<double> w = std::sqrt(alpha + 2.0 * y);
+  roots[0] = -b / (4.0 * a) + 0.5 * (w + std::sqrt(-(3.0 * alpha + 2.0 * y + 2.0 * beta / w)));
+  roots[1] = -b / (4.0 * a) + 0.5 * (w - std::sqrt(-(3.0 * alpha + 2.0 * y + 2.0 * beta / w)));
+  roots[2] = -b / (4.0 * a) + 0.5 * (-w + std::sqrt(-(3.0 * alpha + 2.0 * y - 2.0 * beta / w)));
+  roots[3] = -b / (4.0 * a) + 0.5 * (-w - std::sqrt(-(3.0 * alpha + 2.0 * y - 2.0 * beta / w)));
+  return 4;
+}
+
+// Real roots of a quartic (coefficients highest degree first) in [lo, hi] by a Sturm chain +
+// bisection, the role of Polynomial<4>::realRootsSturm(-10,10,.) at
+// src/spherical_fast_estimator.cpp:220-223 (library un-vendored -> parity unpinned).
+inline int sturm_real_roots(const double coef_hi_first[5], double lo, double hi, double* roots) {
+  // chain[i] stored lowest degree first
+  double ch[5][5] = {};
+  int deg[5];
+  for (int i = 0; i <= 4; ++i) ch[0][i] = coef_hi_first[4 - i];
+  deg[0] = 4;
+  while (deg[0] > 0 && ch[0][deg[0]] == 0.0) --deg[0];
+  if (deg[0] == 0) return 0;
+  for (int i = 1; i <= deg[0]; ++i) ch[1][i - 1] = i * ch[0][i];
+  deg[1] = deg[0] - 1;
+  int nch = 2;
+  while (deg[nch - 1] > 0 && nch < 5) {
+    // remainder of ch[nch-2] / ch[nch-1], negated
+    double rem[5];
+    std::memcpy(rem, ch[nch - 2], sizeof(rem));
+    const int dd = deg[nch - 1];
+    for (int k = deg[nch - 2]; k >= dd; --k) {
+      const double f = rem[k] / ch[nch - 1][dd];
+      for (int j = 0; j <= dd; ++j) rem[k - dd + j] -= f * ch[nch - 1][j];
+      rem[k] = 0.0;
+    }
+    int dr = dd - 1;
+    while (dr >= 0 && rem[dr] == 0.0) --dr;
+    if (dr < 0) break;
+    for (int j = 0; j <= dr; ++j) ch[nch][j] = -rem[j];
+    deg[nch] = dr;
+    ++nch;
+  }
+  auto changes = [&](double x) {
+    int cnt = 0, last = 0;
+    for (int i = 0; i < nch; ++i) {
+      double v = 0.0;
+      for (int j = deg[i]; j >= 0; --j) v = v * x + ch[i][j];
+      const int sg = (v > 0) - (v < 0);
+      if (sg != 0) {
+        if (last != 0 && sg != last) ++cnt;
+        last = sg;
+      }
+    }
+    return cnt;
+  };
+  auto evalp = [&](double x) {
+    double v = 0.0;
+    for (int j = deg[0]; j >= 0; --j) v = v * x + ch[0][j];
+    return v;
+  };
+  int nroots = 0;
+  struct Iv { double a, b; int ca, cb; };
+  std::vector<Iv> stack;
+  stack.push_back({lo, hi, changes(lo), changes(hi)});
+  std::vector<double> found;
+  while (!stack.empty()) {
+    Iv iv = stack.back();
+    stack.pop_back();
+    const int nr = iv.ca - iv.cb;
+    if (nr <= 0) continue;
+    if (nr == 1) {
+      // bisection on the sign of p to full precision
+      double a = iv.a, b = iv.b;
+      double fa = evalp(a);
+      if (fa == 0.0) { found.push_back(a); continue; }
+      for (int it = 0; it < 200; ++it) {
+        const double mid = 0.5 * (a + b);
+        if (mid == a || mid == b) break;
+        const double fm = evalp(mid);
+        if (fm == 0.0) { a = b = mid; break; }
+        if ((fm > 0) == (fa > 0)) { a = mid; fa = fm; } else { b = mid; }
+      }
+      found.push_back(0.5 * (a + b));
+      continue;
+    }
+    const double mid = 0.5 * (iv.a + iv.b);
+    if (mid == iv.a || mid == iv.b || (iv.b - iv.a) < 1e-14) {  // (numerically) multiple root
+      for (int i = 0; i < nr; ++i) found.push_back(mid);
+      continue;
+    }
+    const int cm = changes(mid);
+    stack.push_back({mid, iv.b, cm, iv.cb});
+    stack.push_back({iv.a, mid, iv.ca, cm});
+  }
+  std::sort(found.begin(), found.end());
+  for (double r : found)
+    if (nroots < 4) roots[nroots++] = r;
+  return nroots;
+}
+
+// ---------------------------------------------------------------------------------------
+// The three 3-point (N >= 3) minimal solvers.  Output: up to 4 models as 6-vectors p with
+// ||E||_F = 1.  Returns the number of models.
+//   ACTION_MATRIX  spherical_solver_action_matrix   src/spherical_solvers.cpp:102-311
+//   POLYNOMIAL     spherical_solver_polynomial      src/spherical_solvers.cpp:313-660
+//   FAST_STURM     SphericalFastEstimator::compute  src/spherical_fast_estimator.cpp:44-257
+// ---------------------------------------------------------------------------------------
+inline void epipolar_row(const RayPair& c, double a[6]) {
+  const double* u = c.u;
+  const double* v = c.v;
+  a[0] = u[0] * v[0] - u[1] * v[1];
+  a[1] = u[0] * v[1] + u[1] * v[0];
+  a[2] = u[2] * v[0];
+  a[3] = u[2] * v[1];
+  a[4] = u[0] * v[2];
+  a[5] = u[1] * v[2];
+}
+
+inline void p_from_b(const double B[6][3], const std::complex<double> b[3], double p[6]) {
+  std::complex<double> pc[6];
+  for (int i = 0; i < 6; ++i) pc[i] = B[i][0] * b[0] + B[i][1] * b[1] + B[i][2] * b[2];
+  canonical_real_p(pc, p);
+}
+
+inline int solve_spherical(const RayPair* corr, const int* sample, int n, SolverKind kind, double models[4][6]) {
+  if (n < 3) return 0;  // "bad sample size" (src/spherical_solvers.cpp:105-109)
+  std::vector<double> A(6 * (size_t)n);
+  for (int i = 0; i < n; ++i) epipolar_row(corr[sample[i]], &A[(size_t)6 * i]);
+  double B[6][3];
+  nullspace_colpiv_qr(A.data(), n, B);
+  double C[6][10], G[6][4];
+  build_constraints(B, kind, C);
+  if (!lu_solve_6x6_4(C, G)) {
+    // The reference would emit NaN matrices (never selected: NaN scores fail every '<').
+    for (int k = 0; k < 4; ++k)
+      for (int i = 0; i < 6; ++i) models[k][i] = std::numeric_limits<double>::quiet_NaN();
+    return kind == FAST_STURM ? 0 : 4;
+  }
+  if (kind == ACTION_MATRIX) {
+    // multiplication-by-x on the basis [y^2, x, y, 1] (:281-285)
+    double M[4][4] = {};
+    for (int j = 0; j < 4; ++j) {
+      M[0][j] = -G[2][j];
+      M[1][j] = -G[4][j];
+      M[2][j] = -G[5][j];
+    }
+    M[3][1] = 1.0;
+    double wr[4], wi[4];
+    if (!eigenvalues_4x4(M, wr, wi)) {
+      for (int k = 0; k < 4; ++k)
+        for (int i = 0; i < 6; ++i) models[k][i] = std::numeric_limits<double>::quiet_NaN();
+      return 4;
+    }
+    for (int k = 0; k < 4; ++k) {
+      std::complex<double> a[4][4], v[4];
+      for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) a[r][c] = M[r][c];
+      for (int r = 0; r < 4; ++r) a[r][r] -= std::complex<double>(wr[k], wi[k]);
+      null_vector_c4(a, v);
+      const std::complex<double> b[3] = {v[1], v[2], v[3]};  // (x, y, 1) up to scale (:296)
+      p_from_b(B, b, models[k]);
+    }
+    return 4;
+  }
+  if (kind == POLYNOMIAL) {
+    // quartic in y (:623-627), x from row 5 (:633-640)
+    const double qa = -G[5][0], qb = G[4][0] - G[5][1], qc = G[4][1] - G[5][2], qd = G[4][2] - G[5][3],
+                 qe = G[4][3];
+    std::complex<double> yr[4];
+    solve_quartic_ferrari(qa, qb, qc, qd, qe, yr);
+    for (int k = 0; k < 4; ++k) {
+      const std::complex<double> y = yr[k];
+      const std::complex<double> x = -(G[5][0] * y * y * y + G[5][1] * y * y + G[5][2] * y + G[5][3]);
+      const std::complex<double> b[3] = {x, y, 1.0};
+      p_from_b(B, b, models[k]);
+    }
+    return 4;
+  }
+  // FAST_STURM: quartic det N(y) (:219), real roots in [-10, 10] (:223), x by Cramer (:239)
+  const double c4 = G[4][0] * G[5][1] - G[4][1] * G[5][0];
+  const double c3 = G[3][1] * G[5][0] - G[3][0] * G[5][1] + G[4][0] * G[5][2] - G[4][2] * G[5][0];
+  const double c2 = G[3][2] * G[5][0] - G[3][1] * G[4][0] + G[3][0] * (G[4][1] - G[5][2]);
+  const double c1 = G[3][0] * (G[4][2] + G[4][1] * G[5][3] - G[4][3] * G[5][1]) +
+                    G[3][3] * (G[4][0] * G[5][1] - G[4][1] * G[5][0]) -
+                    G[3][1] * (G[4][0] * G[5][3] - G[4][3] * G[5][0]) - G[3][2] * G[4][0];
+  const double c0 = G[3][3] * (G[4][0] * G[5][2] - G[4][2] * G[5][0]) -
+                    G[3][2] * (G[4][0] * G[5][3] - G[4][3] * G[5][0]) +
+                    G[3][0] * (G[4][2] * G[5][3] - G[4][3] * G[5][2]);
+  const double coef[5] = {c4, c3, c2, c1, c0};
+  double ys[4];
+  const int nr = sturm_real_roots(coef, -10.0, 10.0, ys);
+  int nm = 0;
+  for (int k = 0; k < nr; ++k) {
+    const double y = ys[k];
+    const double N00 = G[3][0], N01 = G[3][2] + G[3][1] * y, N02 = G[3][3] + y * y * y;
+    const double N10 = G[4][0], N11 = G[4][2] + G[4][1] * y, N12 = G[4][3] + y * y;
+    const double x = (N02 * N10 - N00 * N12) / (N00 * N11 - N01 * N10);
+    if (std::isnan(x)) continue;
+    const std::complex<double> b[3] = {x, y, 1.0};
+    p_from_b(B, b, models[nm++]);
+  }
+  return nm;
+}
+
+// ---------------------------------------------------------------------------------------
+// Scoring: squared Sampson distance, SphericalEstimator::EvaluateModelOnPoint
+// (src/spherical_estimator.cpp:67-78).  Evaluation order mirrors Eigen's fixed-size
+// products: row . column accumulated left to right.
+// ---------------------------------------------------------------------------------------
+inline double sampson_sq(const Mat3& E, const RayPair& c) {
+  const double* u = c.u;
+  const double* v = c.v;
+  const double Eu0 = E.m[0] * u[0] + E.m[1] * u[1] + E.m[2] * u[2];
+  const double Eu1 = E.m[3] * u[0] + E.m[4] * u[1] + E.m[5] * u[2];
+  const double Eu2 = E.m[6] * u[0] + E.m[7] * u[1] + E.m[8] * u[2];
+  const double Etv0 = E.m[0] * v[0] + E.m[3] * v[1] + E.m[6] * v[2];
+  const double Etv1 = E.m[1] * v[0] + E.m[4] * v[1] + E.m[7] * v[2];
+  const double d = v[0] * Eu0 + v[1] * Eu1 + v[2] * Eu2;
+  return (d * d) / ((Eu0 * Eu0 + Eu1 * Eu1) + (Etv0 * Etv0 + Etv1 * Etv1));
+}
+
+// ---------------------------------------------------------------------------------------
+// so(3) helpers and the spherical essential matrix  (src/so3.cpp:6-70, src/spherical_utils.cpp:9-66)
+// ---------------------------------------------------------------------------------------
+inline Mat3 matmul(const Mat3& a, const Mat3& b) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+  return r;
+}
+inline Mat3 transpose(const Mat3& a) {
+  Mat3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[3 * i + j] = a.m[3 * j + i];
+  return r;
+}
+inline double det3(const Mat3& a) {
+  return a.m[0] * (a.m[4] * a.m[8] - a.m[5] * a.m[7]) - a.m[1] * (a.m[3] * a.m[8] - a.m[5] * a.m[6]) +
+         a.m[2] * (a.m[3] * a.m[7] - a.m[4] * a.m[6]);
+}
+inline Mat3 skew3(const double v[3]) {  // so3.cpp:6-14
+  Mat3 s;
+  s.m[0] = 0; s.m[1] = -v[2]; s.m[2] = v[1];
+  s.m[3] = v[2]; s.m[4] = 0; s.m[5] = -v[0];
+  s.m[6] = -v[1]; s.m[7] = v[0]; s.m[8] = 0;
+  return s;
+}
+inline Mat3 so3exp(const double r[3]) {  // so3.cpp:16-23
+  const double theta = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  Mat3 R;
+  for (int i = 0; i < 9; ++i) R.m[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  if (theta < 1e-10) return R;
+  const double k[3] = {r[0] / theta, r[1] / theta, r[2] / theta};
+  const Mat3 K = skew3(k);
+  const Mat3 KK = matmul(K, K);
+  const double s = std::sin(theta), c = 1.0 - std::cos(theta);
+  for (int i = 0; i < 9; ++i) R.m[i] += s * K.m[i] + c * KK.m[i];
+  return R;
+}
+inline void so3ln(const Mat3& R, double result[3]) {  // so3.cpp:25-69
+  const double cos_angle = (R(0, 0) + R(1, 1) + R(2, 2) - 1.0) * 0.5;
+  result[0] = (R(2, 1) - R(1, 2)) / 2;
+  result[1] = (R(0, 2) - R(2, 0)) / 2;
+  result[2] = (R(1, 0) - R(0, 1)) / 2;
+  const double sin_angle_abs = std::sqrt(result[0] * result[0] + result[1] * result[1] + result[2] * result[2]);
+  if (cos_angle > M_SQRT1_2) {
+    if (sin_angle_abs > 0) {
+      const double f = std::asin(sin_angle_abs) / sin_angle_abs;
+      for (int i = 0; i < 3; ++i) result[i] *= f;
+    }
+  } else if (cos_angle > -M_SQRT1_2) {
+    const double f = std::acos(cos_angle) / sin_angle_abs;
+    for (int i = 0; i < 3; ++i) result[i] *= f;
+  } else {
+    const double angle = M_PI - std::asin(sin_angle_abs);
+    const double d0 = R(0, 0) - cos_angle, d1 = R(1, 1) - cos_angle, d2 = R(2, 2) - cos_angle;
+    double r2[3];
+    if (std::fabs(d0) > std::fabs(d1) && std::fabs(d0) > std::fabs(d2)) {
+      r2[0] = d0; r2[1] = (R(1, 0) + R(0, 1)) / 2; r2[2] = (R(0, 2) + R(2, 0)) / 2;
+    } else if (std::fabs(d1) > std::fabs(d2)) {
+      r2[0] = (R(1, 0) + R(0, 1)) / 2; r2[1] = d1; r2[2] = (R(2, 1) + R(1, 2)) / 2;
+    } else {
+      r2[0] = (R(0, 2) + R(2, 0)) / 2; r2[1] = (R(2, 1) + R(1, 2)) / 2; r2[2] = d2;
+    }
+    if (r2[0] * result[0] + r2[1] * result[1] + r2[2] * result[2] < 0)
+      for (int i = 0; i < 3; ++i) r2[i] = -r2[i];
+    const double n = std::sqrt(r2[0] * r2[0] + r2[1] * r2[1] + r2[2] * r2[2]);
+    for (int i = 0; i < 3; ++i) result[i] = angle * r2[i] / n;
+  }
+}
+inline Mat3 make_spherical_essential_matrix(const Mat3& R, bool inward) {  // spherical_utils.cpp:9-14
+  double t[3] = {R(0, 2), R(1, 2), R(2, 2) - 1};
+  if (inward)
+    for (int i = 0; i < 3; ++i) t[i] = -t[i];
+  return matmul(skew3(t), R);
+}
+
+// 3x3 SVD by one-sided Jacobi (Hestenes): A = U diag(s) V^T, s sorted descending
+// (the role of Eigen::JacobiSVD at spherical_utils.cpp:18).  A zero singular value gets its
+// left vector completed by a cross product.
+inline void svd3(const Mat3& A, Mat3& U, double s[3], Mat3& V) {
+  double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) a[i][j] = A.m[3 * i + j];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; ++i) {
+          alpha += a[i][p] * a[i][p];
+          beta += a[i][q] * a[i][q];
+          gamma += a[i][p] * a[i][q];
+        }
+        if (gamma == 0.0) continue;
+        off = std::max(off, std::fabs(gamma) / std::sqrt(std::max(alpha * beta, 1e-300)));
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+        for (int i = 0; i < 3; ++i) {
+          const double ap = a[i][p], aq = a[i][q];
+          a[i][p] = c * ap - sn * aq;
+          a[i][q] = sn * ap + c * aq;
+          const double vp = v[i][p], vq = v[i][q];
+          v[i][p] = c * vp - sn * vq;
+          v[i][q] = sn * vp + c * vq;
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  double sv[3];
+  for (int j = 0; j < 3; ++j) sv[j] = std::sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+  int ord[3] = {0, 1, 2};
+  std::sort(ord, ord + 3, [&](int x, int y) { return sv[x] > sv[y]; });
+  double u[3][3];
+  for (int k = 0; k < 3; ++k) {
+    const int j = ord[k];
+    s[k] = sv[j];
+    for (int i = 0; i < 3; ++i) {
+      V.m[3 * i + k] = v[i][j];
+      u[i][k] = sv[j] > 0 ? a[i][j] / sv[j] : 0.0;
+    }
+  }
+  // complete U where singular values are (numerically) zero
+  if (s[2] <= 1e-14 * s[0]) {
+    if (s[1] <= 1e-14 * s[0]) {
+      // rank <= 1: pick any orthonormal completion
+      double e[3] = {0, 0, 0};
+      int mn = 0;
+      for (int i = 1; i < 3; ++i)
+        if (std::fabs(u[i][0]) < std::fabs(u[mn][0])) mn = i;
+      e[mn] = 1.0;
+      double w[3] = {u[1][0] * e[2] - u[2][0] * e[1], u[2][0] * e[0] - u[0][0] * e[2], u[0][0] * e[1] - u[1][0] * e[0]};
+      const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+      for (int i = 0; i < 3; ++i) u[i][1] = w[i] / n;
+    }
+    u[0][2] = u[1][0] * u[2][1] - u[2][0] * u[1][1];
+    u[1][2] = u[2][0] * u[0][1] - u[0][0] * u[2][1];
+    u[2][2] = u[0][0] * u[1][1] - u[1][0] * u[0][1];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) U.m[3 * i + k] = u[i][k];
+}
+
+// decompose_spherical_essential_matrix (src/spherical_utils.cpp:16-66)
+inline void decompose_spherical_essential_matrix(const Mat3& E, bool inward, double r[3], double t[3]) {
+  Mat3 U, V;
+  double s[3];
+  svd3(E, U, s, V);
+  if (det3(U) < 0)
+    for (int i = 0; i < 9; ++i) U.m[i] = -U.m[i];
+  if (det3(V) < 0)
+    for (int i = 0; i < 9; ++i) V.m[i] = -V.m[i];
+  Mat3 D, DT;
+  const double d[9] = {0, 1, 0, -1, 0, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) D.m[i] = d[i];
+  DT = transpose(D);
+  const Mat3 VT = transpose(V);
+  const double tu[3] = {U(0, 2), U(1, 2), U(2, 2)};
+  const Mat3 R1 = matmul(matmul(U, D), VT);
+  const Mat3 R2 = matmul(matmul(U, DT), VT);
+  double t1[3] = {R1(0, 2), R1(1, 2), R1(2, 2) - 1};
+  double t2[3] = {R2(0, 2), R2(1, 2), R2(2, 2) - 1};
+  if (inward)
+    for (int i = 0; i < 3; ++i) { t1[i] = -t1[i]; t2[i] = -t2[i]; }
+  const double n1 = std::sqrt(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+  const double n2 = std::sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+  double r1[3], r2[3];
+  so3ln(R1, r1);
+  so3ln(R2, r2);
+  const double score1 = std::fabs((t1[0] * tu[0] + t1[1] * tu[1] + t1[2] * tu[2]) / n1);
+  const double score2 = std::fabs((t2[0] * tu[0] + t2[1] * tu[1] + t2[2] * tu[2]) / n2);
+  if (score1 > score2) {
+    for (int i = 0; i < 3; ++i) { r[i] = r1[i]; t[i] = t1[i]; }
+  } else {
+    for (int i = 0; i < 3; ++i) { r[i] = r2[i]; t[i] = t2[i]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Least-squares refit: SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157)
+// = Ceres 2.2.0 TRUST_REGION / LEVENBERG_MARQUARDT / DENSE_NORMAL_CHOLESKY on the autodiff'd
+// SampsonError functor (:23-65), free blocks r1 (3) and t1 (3), residual = the squared
+// Sampson value itself.  The Ceres minimiser loop is restated from its documented defaults.
+// ---------------------------------------------------------------------------------------
+template <int N>
+struct Jet {
+  double a;
+  double v[N];
+  Jet() : a(0) { for (int i = 0; i < N; ++i) v[i] = 0; }
+  Jet(double x) : a(x) { for (int i = 0; i < N; ++i) v[i] = 0; }
+  Jet(double x, int k) : a(x) { for (int i = 0; i < N; ++i) v[i] = 0; v[k] = 1.0; }
+};
+template <int N> inline Jet<N> operator+(const Jet<N>& x, const Jet<N>& y) { Jet<N> r; r.a = x.a + y.a; for (int i = 0; i < N; ++i) r.v[i] = x.v[i] + y.v[i]; return r; }
+template <int N> inline Jet<N> operator-(const Jet<N>& x, const Jet<N>& y) { Jet<N> r; r.a = x.a - y.a; for (int i = 0; i < N; ++i) r.v[i] = x.v[i] - y.v[i]; return r; }
+template <int N> inline Jet<N> operator-(const Jet<N>& x) { Jet<N> r; r.a = -x.a; for (int i = 0; i < N; ++i) r.v[i] = -x.v[i]; return r; }
+template <int N> inline Jet<N> operator*(const Jet<N>& x, const Jet<N>& y) { Jet<N> r; r.a = x.a * y.a; for (int i = 0; i < N; ++i) r.v[i] = x.a * y.v[i] + x.v[i] * y.a; return r; }
+template <int N> inline Jet<N> operator/(const Jet<N>& x, const Jet<N>& y) { Jet<N> r; const double inv = 1.0 / y.a; r.a = x.a * inv; for (int i = 0; i < N; ++i) r.v[i] = (x.v[i] - r.a * y.v[i]) * inv; return r; }
+template <int N> inline Jet<N> sqrt(const Jet<N>& x) { Jet<N> r; r.a = std::sqrt(x.a); const double f = 0.5 / r.a; for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * f; return r; }
+template <int N> inline Jet<N> sin(const Jet<N>& x) { Jet<N> r; r.a = std::sin(x.a); const double c = std::cos(x.a); for (int i = 0; i < N; ++i) r.v[i] = c * x.v[i]; return r; }
+template <int N> inline Jet<N> cos(const Jet<N>& x) { Jet<N> r; r.a = std::cos(x.a); const double s = -std::sin(x.a); for (int i = 0; i < N; ++i) r.v[i] = s * x.v[i]; return r; }
+inline double value_of(double x) { return x; }
+template <int N> inline double value_of(const Jet<N>& x) { return x.a; }
+
+// ceres::AngleAxisToRotationMatrix (ceres/rotation.h), output row-major R[3*r+c].
+template <typename T>
+inline void angle_axis_to_rotation(const T aa[3], T R[9]) {
+  using std::sqrt; using std::sin; using std::cos;
+  const T theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  const T kOne = T(1.0);
+  if (value_of(theta2) > std::numeric_limits<double>::epsilon()) {
+    const T theta = sqrt(theta2);
+    const T wx = aa[0] / theta, wy = aa[1] / theta, wz = aa[2] / theta;
+    const T costheta = cos(theta), sintheta = sin(theta);
+    R[0] = costheta + wx * wx * (kOne - costheta);
+    R[3] = wz * sintheta + wx * wy * (kOne - costheta);
+    R[6] = -wy * sintheta + wx * wz * (kOne - costheta);
+    R[1] = wx * wy * (kOne - costheta) - wz * sintheta;
+    R[4] = costheta + wy * wy * (kOne - costheta);
+    R[7] = wx * sintheta + wy * wz * (kOne - costheta);
+    R[2] = wy * sintheta + wx * wz * (kOne - costheta);
+    R[5] = -wx * sintheta + wy * wz * (kOne - costheta);
+    R[8] = costheta + wz * wz * (kOne - costheta);
+  } else {
+    R[0] = kOne; R[3] = aa[2]; R[6] = -aa[1];
+    R[1] = -aa[2]; R[4] = kOne; R[7] = aa[0];
+    R[2] = aa[1]; R[5] = -aa[0]; R[8] = kOne;
+  }
+}
+
+// SampsonError::operator() with r0 = 0 (so Ri = I), t0 constant  (spherical_estimator.cpp:25-64):
+//   R = Rj,  t = Rj (-t0) + t1,  E = [t]x R,  residual = d^2 / (|Eu|_xy^2 + |E^T v|_xy^2)
+template <typename T>
+inline T sampson_residual(const T r1[3], const T t1[3], const double t0[3], const double u[3], const double v[3]) {
+  T R[9];
+  angle_axis_to_rotation(r1, R);
+  T t[3];
+  for (int i = 0; i < 3; ++i) t[i] = R[3 * i] * T(-t0[0]) + R[3 * i + 1] * T(-t0[1]) + R[3 * i + 2] * T(-t0[2]) + t1[i];
+  // E = skew(t) * R
+  T E[9];
+  for (int j = 0; j < 3; ++j) {
+    E[0 + j] = t[1] * R[6 + j] - t[2] * R[3 + j];
+    E[3 + j] = t[2] * R[0 + j] - t[0] * R[6 + j];
+    E[6 + j] = t[0] * R[3 + j] - t[1] * R[0 + j];
+  }
+  const T Eu0 = E[0] * T(u[0]) + E[1] * T(u[1]) + E[2] * T(u[2]);
+  const T Eu1 = E[3] * T(u[0]) + E[4] * T(u[1]) + E[5] * T(u[2]);
+  const T Eu2 = E[6] * T(u[0]) + E[7] * T(u[1]) + E[8] * T(u[2]);
+  const T Etv0 = E[0] * T(v[0]) + E[3] * T(v[1]) + E[6] * T(v[2]);
+  const T Etv1 = E[1] * T(v[0]) + E[4] * T(v[1]) + E[7] * T(v[2]);
+  const T d = T(v[0]) * Eu0 + T(v[1]) * Eu1 + T(v[2]) * Eu2;
+  return (d * d) / (Eu0 * Eu0 + Eu1 * Eu1 + Etv0 * Etv0 + Etv1 * Etv1);
+}
+
+struct LMSummary {
+  int iterations = 0;
+  int termination = 0;  // 1 gradient tol, 2 parameter tol, 3 function tol, 4 max iters, 5 invalid steps, 6 min radius
+  double initial_cost = 0, final_cost = 0;
+};
+
+// Cholesky solve of a 6x6 SPD system; returns false if not positive definite.
+inline bool cholesky_solve6(const double Ain[6][6], const double b[6], double x[6]) {
+  double L[6][6] = {};
+  for (int j = 0; j < 6; ++j) {
+    double d = Ain[j][j];
+    for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+    if (!(d > 0.0)) return false;
+    L[j][j] = std::sqrt(d);
+    for (int i = j + 1; i < 6; ++i) {
+      double s = Ain[i][j];
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      L[i][j] = s / L[j][j];
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+    for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
+    y[i] = s / L[i][i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
+    x[i] = s / L[i][i];
+  }
+  for (int i = 0; i < 6; ++i)
+    if (!std::isfinite(x[i])) return false;
+  return true;
+}
+
+// Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy with Solver::Options defaults
+// (function_tolerance 1e-6, gradient_tolerance 1e-10, parameter_tolerance 1e-8,
+//  initial_trust_region_radius 1e4, max 1e16, min 1e-32, min_relative_decrease 1e-3,
+//  min/max_lm_diagonal 1e-6/1e32, jacobi_scaling on, monotonic steps) and the reference's
+//  max_num_iterations 200, max_num_consecutive_invalid_steps 10 (spherical_estimator.cpp:146-152).
+inline LMSummary lm_refit(const RayPair* corr, const int* sample, int n, bool inward, double x[6]) {
+  LMSummary sum;
+  const double t0[3] = {0, 0, inward ? 1.0 : -1.0};
+  typedef Jet<6> J6;
+  std::vector<double> res(n), cand_res(n);
+  std::vector<double> jac((size_t)n * 6);  // scaled Jacobian
+  double scale[6];
+  auto eval_cost = [&](const double* xx, std::vector<double>& r) {
+    double c = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const RayPair& cp = corr[sample[i]];
+      r[i] = sampson_residual<double>(xx, xx + 3, t0, cp.u, cp.v);
+      c += r[i] * r[i];
+    }
+    return 0.5 * c;
+  };
+  double gradient[6];
+  double gmax = 0.0;
+  auto eval_jac = [&](const double* xx, bool first) {
+    double c = 0.0;
+    for (int k = 0; k < 6; ++k) gradient[k] = 0.0;
+    for (int i = 0; i < n; ++i) {
+      const RayPair& cp = corr[sample[i]];
+      J6 r1[3] = {J6(xx[0], 0), J6(xx[1], 1), J6(xx[2], 2)};
+      J6 t1[3] = {J6(xx[3], 3), J6(xx[4], 4), J6(xx[5], 5)};
+      const J6 r = sampson_residual<J6>(r1, t1, t0, cp.u, cp.v);
+      res[i] = r.a;
+      c += r.a * r.a;
+      for (int k = 0; k < 6; ++k) {
+        jac[(size_t)i * 6 + k] = r.v[k];
+        gradient[k] += r.v[k] * r.a;
+      }
+    }
+    if (first) {
+      for (int k = 0; k < 6; ++k) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += jac[(size_t)i * 6 + k] * jac[(size_t)i * 6 + k];
+        scale[k] = 1.0 / (1.0 + std::sqrt(s));
+      }
+    }
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 6; ++k) jac[(size_t)i * 6 + k] *= scale[k];
+    gmax = 0.0;
+    for (int k = 0; k < 6; ++k) gmax = std::max(gmax, std::fabs(gradient[k]));
+    return 0.5 * c;
+  };
+
+  double x_cost = eval_jac(x, true);
+  sum.initial_cost = sum.final_cost = x_cost;
+  if (!std::isfinite(x_cost)) { sum.termination = 5; return sum; }
+  double radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  double diagonal[6];
+  int num_consecutive_invalid = 0;
+  int iteration = 0;
+  const double gradient_tolerance = 1e-10, parameter_tolerance = 1e-8, function_tolerance = 1e-6;
+  const double min_relative_decrease = 1e-3;
+  while (true) {
+    // FinalizeIterationAndCheckIfMinimizerCanContinue
+    if (iteration >= 200) { sum.termination = 4; break; }
+    if (gmax <= gradient_tolerance) { sum.termination = 1; break; }
+    if (radius < 1e-32) { sum.termination = 6; break; }
+    ++iteration;
+    // LevenbergMarquardtStrategy::ComputeStep
+    if (!reuse_diagonal) {
+      for (int k = 0; k < 6; ++k) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += jac[(size_t)i * 6 + k] * jac[(size_t)i * 6 + k];
+        diagonal[k] = std::min(std::max(s, 1e-6), 1e32);
+      }
+    }
+    double H[6][6], g[6], step[6];
+    for (int a = 0; a < 6; ++a) {
+      g[a] = 0.0;
+      for (int b = 0; b < 6; ++b) H[a][b] = 0.0;
+    }
+    for (int i = 0; i < n; ++i) {
+      const double* ji = &jac[(size_t)i * 6];
+      for (int a = 0; a < 6; ++a) {
+        g[a] += ji[a] * res[i];
+        for (int b = 0; b <= a; ++b) H[a][b] += ji[a] * ji[b];
+      }
+    }
+    for (int a = 0; a < 6; ++a) {
+      for (int b = 0; b < a; ++b) H[b][a] = H[a][b];
+      H[a][a] += diagonal[a] / radius;  // D^T D with D = sqrt(diagonal / radius)
+    }
+    bool valid = cholesky_solve6(H, g, step);
+    reuse_diagonal = true;
+    double model_cost_change = 0.0;
+    if (valid) {
+      for (int k = 0; k < 6; ++k) step[k] = -step[k];
+      // model_cost_change = -(J s) . (r + J s / 2)
+      for (int i = 0; i < n; ++i) {
+        double m = 0.0;
+        for (int k = 0; k < 6; ++k) m += jac[(size_t)i * 6 + k] * step[k];
+        model_cost_change -= m * (res[i] + m / 2.0);
+      }
+      if (!(model_cost_change > 0.0)) valid = false;
+    }
+    if (!valid) {
+      if (++num_consecutive_invalid >= 10) { sum.termination = 5; break; }
+      radius = radius / decrease_factor;  // StepIsInvalid -> StepRejected(0)
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+      continue;
+    }
+    num_consecutive_invalid = 0;
+    double delta[6], cand[6];
+    double step_norm = 0.0, x_norm = 0.0;
+    for (int k = 0; k < 6; ++k) {
+      delta[k] = step[k] * scale[k];
+      cand[k] = x[k] + delta[k];
+      step_norm += delta[k] * delta[k];
+      x_norm += x[k] * x[k];
+    }
+    step_norm = std::sqrt(step_norm);
+    x_norm = std::sqrt(x_norm);
+    double cand_cost = eval_cost(cand, cand_res);
+    if (!std::isfinite(cand_cost)) cand_cost = std::numeric_limits<double>::max();
+    // ParameterToleranceReached
+    if (step_norm <= parameter_tolerance * (x_norm + parameter_tolerance)) { sum.termination = 2; break; }
+    // FunctionToleranceReached
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= function_tolerance * x_cost) { sum.termination = 3; break; }
+    const double relative_decrease = cost_change / model_cost_change;
+    if (relative_decrease > min_relative_decrease) {
+      for (int k = 0; k < 6; ++k) x[k] = cand[k];
+      x_cost = eval_jac(x, false);
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+      radius = std::min(1e16, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+    } else {
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+    }
+  }
+  sum.iterations = iteration;
+  sum.final_cost = x_cost;
+  return sum;
+}
+
+// ---------------------------------------------------------------------------------------
+// SphericalEstimator: the RansacLib estimator concept (include/sphericalsfm/estimator.h:6-29,
+// include/sphericalsfm/spherical_estimator.h:8-33, src/spherical_estimator.cpp:67-164).
+// ---------------------------------------------------------------------------------------
+class SphericalEstimator {
+ public:
+  typedef Mat3 Model;
+  typedef std::vector<Mat3> ModelVector;
+  SphericalEstimator(const RayPair* corr, int n, SolverKind kind, bool inward, uint32_t pair_id = 0)
+      : corr_(corr), n_(n), kind_(kind), inward_(inward), pair_id_(pair_id) {}
+  uint32_t pair_id() const { return pair_id_; }
+  int min_sample_size() const { return 3; }
+  int non_minimal_sample_size() const { return 4; }
+  int num_data() const { return n_; }
+  int MinimalSolver(const std::vector<int>& sample, std::vector<Mat3>* Es) const {
+    double models[4][6];
+    const int nm = solve_spherical(corr_, sample.data(), (int)sample.size(), kind_, models);
+    Es->clear();
+    for (int k = 0; k < nm; ++k) Es->push_back(mat_from_p(models[k]));
+    return nm;
+  }
+  int NonMinimalSolver(const std::vector<int>& sample, Mat3* E) const {  // :86-108
+    double models[4][6];
+    const int nm = solve_spherical(corr_, sample.data(), (int)sample.size(), ACTION_MATRIX, models);
+    if (nm == 0) return 0;
+    double best_score = INFINITY;
+    int best_ind = 0;
+    for (int i = 0; i < nm; ++i) {
+      const Mat3 Ei = mat_from_p(models[i]);
+      double score = 0;
+      for (size_t j = 0; j < sample.size(); ++j) score += EvaluateModelOnPoint(Ei, sample[j]);
+      if (score < best_score) { best_score = score; best_ind = i; }
+    }
+    *E = mat_from_p(models[best_ind]);
+    return 1;
+  }
+  double EvaluateModelOnPoint(const Mat3& E, int i) const {
+    ++evals_;
+    return sampson_sq(E, corr_[i]);
+  }
+  void LeastSquares(const std::vector<int>& sample, Mat3* E) const {  // :110-157
+    double r[3], t[3];
+    decompose_spherical_essential_matrix(*E, inward_, r, t);
+    double x[6] = {r[0], r[1], r[2], 0, 0, inward_ ? 1.0 : -1.0};
+    lm_refit(corr_, sample.data(), (int)sample.size(), inward_, x);
+    *E = make_spherical_essential_matrix(so3exp(x), inward_);
+  }
+  void Decompose(const Mat3& E, double R[9], double t[3]) const {  // :159-164
+    double r[3];
+    decompose_spherical_essential_matrix(E, inward_, r, t);
+    const Mat3 Rm = so3exp(r);
+    std::memcpy(R, Rm.m, sizeof(Rm.m));
+  }
+  mutable long long evals_ = 0;  // correspondence-hypothesis evaluations (the bench metric)
+
+ private:
+  const RayPair* corr_;
+  int n_;
+  SolverKind kind_;
+  bool inward_;
+  uint32_t pair_id_;
+};
+
+// Sampler satisfying RansacLib's Sampler template parameter (ransac.h:119-120), Philox-backed.
+template <class Solver>
+class PhiloxSampling {
+ public:
+  PhiloxSampling(const unsigned int random_seed, const Solver& solver)
+      : seed_(random_seed), pair_(solver.pair_id()), num_data_(solver.num_data()),
+        sample_size_(solver.min_sample_size()) {}
+  void Sample(std::vector<int>* random_sample) {
+    random_sample->resize(sample_size_);
+    philox_sample(seed_, pair_, iter_++, sample_size_, num_data_, random_sample->data());
+  }
+
+ private:
+  uint32_t seed_, pair_;
+  uint32_t iter_ = 0;
+  int num_data_, sample_size_;
+};
+
+}  // namespace ssfm_oracle
