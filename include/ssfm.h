@@ -1,0 +1,184 @@
+/* ssfm.h -- C ABI of the B200 batched spherical relative-pose engine (libssfm_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of jonathanventura/spherical-sfm: robust
+ * relative pose (RANSAC / LO-RANSAC with the spherical 3-point solvers, Sampson scoring and the
+ * least-squares refit) over many image pairs at once.  Plain pointers and sizes only; no C++
+ * or torch types.  Every entry point cites the reference interface it replaces (paths relative
+ * to the reference root).  There is NO CPU fallback: every compute entry fails with
+ * SSFM_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Conventions (reference): one correspondence = RayPair = two 3-vectors (u in image 0, v in
+ * image 1), 6 contiguous doubles, epipolar constraint v^T E u = 0
+ * (include/sphericalsfm/ray.h:8-10, src/spherical_solvers.cpp:119).  E is row-major 3x3.
+ */
+#ifndef SSFM_H_
+#define SSFM_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSFM_ABI_VERSION 1
+
+typedef struct ssfm_engine* ssfm_handle;
+
+/* Return codes of every entry point (the reference's convention is "return 0 / print";
+ * include/RansacLib/ransac.h:137-139, src/spherical_solvers.cpp:105-109). */
+enum {
+  SSFM_OK = 0,
+  SSFM_ERR_INVALID = 1,   /* bad argument */
+  SSFM_ERR_NO_DEVICE = 2, /* no CUDA device / wrong architecture: the engine never falls back to the CPU */
+  SSFM_ERR_CUDA = 3,      /* a CUDA call failed; ssfm_last_error() has the text */
+  SSFM_ERR_OOM = 4
+};
+
+/* Per-pair status. */
+enum { SSFM_PAIR_OK = 0, SSFM_PAIR_TOO_FEW_POINTS = 1, SSFM_PAIR_NO_MODEL = 2 };
+
+/* Minimal solver (SphericalEstimator's use_poly_solver flag, include/sphericalsfm/spherical_estimator.h:13-15;
+ * SphericalFastEstimator, include/sphericalsfm/spherical_fast_estimator.h). */
+enum {
+  SSFM_SOLVER_ACTION_MATRIX = 0, /* spherical_solver_action_matrix, src/spherical_solvers.cpp:102-311 */
+  SSFM_SOLVER_POLYNOMIAL = 1,    /* spherical_solver_polynomial,    src/spherical_solvers.cpp:313-660 */
+  SSFM_SOLVER_FAST_STURM = 2     /* SphericalFastEstimator::compute, src/spherical_fast_estimator.cpp:44-257 */
+};
+
+/* RANSAC driver. */
+enum {
+  SSFM_DRIVER_LO_MSAC = 0,      /* ransac_lib::LocallyOptimizedMSAC::EstimateModel, include/RansacLib/ransac.h:128-275 */
+  SSFM_DRIVER_VANILLA_MSAC = 1, /* ransac_lib::VanillaMSAC::EstimateModel,          evaluation/vanilla_ransac.h:23-99 */
+  SSFM_DRIVER_MSAC_FIXED = 2    /* sphericalsfm::MSAC::compute (fixed hypothesis budget, '<=' inlier test),
+                                   include/sphericalsfm/msac.h:67-131 */
+};
+
+/* RansacOptions + LORansacOptions, field for field (include/RansacLib/ransac.h:47-92), plus the
+ * estimator's constructor arguments and the Philox key.  ssfm_default_options() fills the
+ * reference defaults (ransac.h:49-73). */
+typedef struct SsfmOptions {
+  uint32_t min_num_iterations;      /* 100 */
+  uint32_t max_num_iterations;      /* 10000 */
+  double success_probability;       /* 0.9999 */
+  double squared_inlier_threshold;  /* 1.0 */
+  uint32_t random_seed;             /* 0; Philox key word 0, and the seed of the LO shuffle generator */
+  int32_t num_lo_steps;             /* 10 (estimate_pairwise sets 0, examples/spherical_sfm_tools.cpp:316) */
+  double threshold_multiplier;      /* sqrt(2) */
+  int32_t num_lsq_iterations;       /* 4  (estimate_pairwise sets 0, :317) */
+  int32_t min_sample_multiplicator; /* 7 */
+  int32_t non_min_sample_multiplier;/* 3 */
+  uint32_t lo_starting_iterations;  /* 50 */
+  int32_t final_least_squares;      /* 0  (estimate_pairwise sets 1, :318) */
+  int32_t solver;                   /* SSFM_SOLVER_* */
+  int32_t driver;                   /* SSFM_DRIVER_* */
+  int32_t inward;                   /* SphericalEstimator(.., inward) */
+  int32_t fixed_budget;             /* MSAC_FIXED: estimators.size() (msac.h:77) */
+  double fixed_prob_success;        /* MSAC_FIXED: 0.999 (msac.h:36) */
+  uint32_t first_pair_id;           /* pair p of a batch draws from Philox key (random_seed, first_pair_id + p) */
+} SsfmOptions;
+
+/* A batch of image pairs in CSR form: pair p owns correspondences [offsets[p], offsets[p+1]).
+ * `rays` is the caller's RayPairList memory (6 doubles per correspondence).  The engine never
+ * keeps caller pointers after a call returns (ownership as in spherical_estimator.h:11,15). */
+typedef struct SsfmBatch {
+  int32_t num_pairs;
+  const int64_t* offsets; /* host, num_pairs + 1 entries */
+  const double* rays;     /* host pointer, or device pointer if rays_on_device != 0 */
+  int32_t rays_on_device;
+} SsfmBatch;
+
+/* Per-pair output: the best model + RansacStatistics (include/RansacLib/ransac.h:94-101) + the
+ * pose the callers extract afterwards with decompose_spherical_essential_matrix
+ * (examples/spherical_sfm_tools.cpp:414-418; src/spherical_utils.cpp:16-66). */
+typedef struct SsfmPairResult {
+  double E[9];
+  double r[3]; /* so3ln(R) */
+  double t[3];
+  double best_model_score;
+  double inlier_ratio;
+  uint32_t num_iterations;
+  int32_t best_num_inliers;
+  int32_t number_lo_iterations;
+  int32_t status; /* SSFM_PAIR_* */
+  int64_t evals;  /* minimal-model corr-hypothesis evaluations the reference loop would have made:
+                     num_iterations * models * N */
+} SsfmPairResult;
+
+/* Device-side timing/accounting of the last ssfm_run (CUDA events on the engine's stream). */
+typedef struct SsfmRunStats {
+  double total_ms;
+  double pack_ms, solve_ms, score_ms, chain_ms;
+  int32_t rounds;
+  int32_t kernel_launches;
+  int64_t evals_useful;   /* sum of SsfmPairResult.evals */
+  int64_t evals_executed; /* f32 scoring evaluations actually executed (includes discarded look-ahead) */
+  int64_t evals_exact;    /* f64 evaluations in the certification / LO stage */
+  int64_t score_launches;
+  int64_t h2d_bytes, d2h_bytes;
+} SsfmRunStats;
+
+int ssfm_abi_version(void);
+const char* ssfm_last_error(void);
+void ssfm_default_options(SsfmOptions* opt);
+
+/* Engine lifetime.  One handle = one device + one stream; use one handle per host thread / GPU. */
+int ssfm_create(int device, ssfm_handle* out);
+void ssfm_destroy(ssfm_handle h);
+
+/* Replaces the whole `#pragma omp parallel for` body of estimate_pairwise
+ * (examples/spherical_sfm_tools.cpp:332-420): one LocallyOptimizedMSAC::EstimateModel per pair
+ * (:380-387), the caller's inlier-mask pass (:388-392) and the pose extraction (:414-418).
+ * `results`: host, num_pairs entries.  `inlier_flags`: host, one byte per correspondence of the
+ * batch (1 = err < thr^2), or NULL. */
+int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions* opt, SsfmPairResult* results,
+                        uint8_t* inlier_flags);
+
+/* The same call split into its three stages, so inputs can stay resident in HBM:
+ * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */
+int ssfm_upload(ssfm_handle h, const SsfmBatch* batch);
+int ssfm_run(ssfm_handle h, const SsfmOptions* opt);
+int ssfm_download(ssfm_handle h, SsfmPairResult* results, uint8_t* inlier_flags);
+int ssfm_get_stats(ssfm_handle h, SsfmRunStats* stats);
+/* Device pointer to the result table of the last run (num_pairs x SsfmPairResult), e.g. for an
+ * NCCL all-gather without a host round trip. */
+int ssfm_device_results(ssfm_handle h, void** dev_ptr, int32_t* num_pairs);
+
+/* ---- replay hooks (parity tests drive the reference-shaped pieces one at a time) ---- */
+
+/* The minimal sample of iteration `iter` of pair `pair`: replaces UniformSampling::Sample
+ * (include/RansacLib/sampling.h:58-64).  Host function; the device code uses the same routine. */
+int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t n, int32_t* idx);
+
+/* SphericalEstimator::MinimalSolver (src/spherical_estimator.cpp:80-84) for `num_samples`
+ * samples of 3 indices into `rays` (n correspondences, host).  models: num_samples x 4 x 6 doubles
+ * (p0..p5 of E = [p0 p1 p2; p1 -p0 p3; p4 p5 0], ||E||_F = 1; NaN when absent); num_models: per sample. */
+int ssfm_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t num_samples,
+                       int32_t solver, double* models, int32_t* num_models);
+
+/* ScoreModel + GetInliers count for many models against one pair (include/RansacLib/ransac.h:295-336,
+ * EvaluateModelOnPoint src/spherical_estimator.cpp:67-78): the FP32 scoring kernel.
+ * models6: num_models x 6 doubles (host).  scores: MSAC cost (float), counts: err < thr^2. */
+int ssfm_score(ssfm_handle h, const double* models6, int32_t num_models, const double* rays, int32_t n,
+               double squared_threshold, float* scores, int32_t* counts, float* kernel_ms);
+/* Same quantities from the FP64 certification path (bit-compatible with the reference's arithmetic). */
+int ssfm_score_exact(ssfm_handle h, const double* E9, int32_t num_models, const double* rays, int32_t n,
+                     double squared_threshold, double* scores, int32_t* counts);
+
+/* SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157) for `num_problems`
+ * index sets over one pair.  sample_offsets: num_problems + 1.  E9: in/out, 9 doubles each. */
+int ssfm_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
+                       const int32_t* sample_offsets, int32_t num_problems, int32_t inward, double* E9);
+
+/* decompose_spherical_essential_matrix (src/spherical_utils.cpp:16-66), batched. */
+int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward, double* r3, double* t3);
+
+/* The LO generator: `ncalls` consecutive RandomShuffleAndResize calls (include/RansacLib/utils.h:48-52)
+ * on iota vectors, one std::mt19937(seed) stream (ransac.h:143-144), executed on the device. */
+int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t* sizes, const int32_t* targets,
+                    int32_t* out);
+
+/* Peak-FP32 microbenchmark (FFMA chains on every SM) used as the roofline denominator. */
+int ssfm_measure_fp32_peak(ssfm_handle h, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSFM_H_ */

@@ -1,0 +1,300 @@
+"""spherical-sfm_b200 -- host-side Python mirror of the C ABI in include/ssfm.h.
+
+The product is libssfm_b200.so (hand-written sm_100a CUDA + a thin extern "C" layer, built from
+csrc/ by `build_extension()`); this module only binds it with ctypes so tests, bench.py and
+Python callers can drive the batched relative-pose engine.  There is no CPU fallback: loading
+fails loudly when the library is missing, and every compute call raises SsfmError when CUDA is
+unavailable.
+
+Import name: `spherical_sfm_b200` (see spherical_sfm_b200.py at the repo root; the directory
+name carries the reference's hyphen).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_DIR)
+LIB_PATH = os.path.join(_DIR, "libssfm_b200.so")
+_SOURCES = [os.path.join(_DIR, "csrc", f) for f in
+            ("ssfm_engine.cu", "ssfm_kernels.cuh", "ssfm_chain.cuh", "ssfm_math.cuh")] + [
+                os.path.join(_ROOT, "include", "ssfm.h")]
+
+SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_NO_DEVICE, SSFM_ERR_CUDA, SSFM_ERR_OOM = 0, 1, 2, 3, 4
+PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL = 0, 1, 2
+SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM = 0, 1, 2
+DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED = 0, 1, 2
+
+
+class SsfmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("ssfm error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SsfmOptions(C.Structure):
+    """RansacOptions + LORansacOptions (include/RansacLib/ransac.h:47-92) + estimator arguments."""
+    _fields_ = [
+        ("min_num_iterations", C.c_uint32), ("max_num_iterations", C.c_uint32),
+        ("success_probability", C.c_double), ("squared_inlier_threshold", C.c_double),
+        ("random_seed", C.c_uint32), ("num_lo_steps", C.c_int32),
+        ("threshold_multiplier", C.c_double), ("num_lsq_iterations", C.c_int32),
+        ("min_sample_multiplicator", C.c_int32), ("non_min_sample_multiplier", C.c_int32),
+        ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
+        ("solver", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
+        ("fixed_budget", C.c_int32), ("fixed_prob_success", C.c_double), ("first_pair_id", C.c_uint32),
+    ]
+
+
+class SsfmBatch(C.Structure):
+    _fields_ = [("num_pairs", C.c_int32), ("offsets", C.POINTER(C.c_int64)), ("rays", C.c_void_p),
+                ("rays_on_device", C.c_int32)]
+
+
+class SsfmPairResult(C.Structure):
+    """Best model + RansacStatistics (ransac.h:94-101) + pose."""
+    _fields_ = [
+        ("E", C.c_double * 9), ("r", C.c_double * 3), ("t", C.c_double * 3),
+        ("best_model_score", C.c_double), ("inlier_ratio", C.c_double),
+        ("num_iterations", C.c_uint32), ("best_num_inliers", C.c_int32),
+        ("number_lo_iterations", C.c_int32), ("status", C.c_int32), ("evals", C.c_int64),
+    ]
+
+
+class SsfmRunStats(C.Structure):
+    _fields_ = [
+        ("total_ms", C.c_double), ("pack_ms", C.c_double), ("solve_ms", C.c_double), ("score_ms", C.c_double),
+        ("chain_ms", C.c_double), ("rounds", C.c_int32), ("kernel_launches", C.c_int32),
+        ("evals_useful", C.c_int64), ("evals_executed", C.c_int64), ("evals_exact", C.c_int64),
+        ("score_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+
+RESULT_DTYPE = np.dtype([
+    ("E", np.float64, (9,)), ("r", np.float64, (3,)), ("t", np.float64, (3,)),
+    ("best_model_score", np.float64), ("inlier_ratio", np.float64),
+    ("num_iterations", np.uint32), ("best_num_inliers", np.int32),
+    ("number_lo_iterations", np.int32), ("status", np.int32), ("evals", np.int64)], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(SsfmPairResult)
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+              "-Xcompiler", "-fPIC"]
+
+
+def build_extension(force=False, verbose=False):
+    """Compile csrc/ into libssfm_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    newest = max(os.path.getmtime(s) for s in _SOURCES)
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _SOURCES[0]]
+    subprocess.check_call(cmd, cwd=_DIR)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C ABI.  Raises if libssfm_b200.so has not been built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libssfm_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is the product; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.ssfm_last_error.restype = C.c_char_p
+        L.ssfm_abi_version.restype = C.c_int
+        for name in EXPORTED_SYMBOLS:
+            getattr(L, name)
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
+    "ssfm_estimate_pairs", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
+    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_decompose",
+    "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
+]
+
+
+def _check(rc):
+    if rc != SSFM_OK:
+        raise SsfmError(rc, lib().ssfm_last_error().decode())
+
+
+def default_options(**kw):
+    """RansacLib defaults (ransac.h:49-73)."""
+    o = SsfmOptions()
+    lib().ssfm_default_options(C.byref(o))
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def pipeline_options(squared_inlier_threshold, **kw):
+    """The options estimate_pairwise uses (examples/spherical_sfm_tools.cpp:314-318)."""
+    return default_options(squared_inlier_threshold=squared_inlier_threshold, num_lo_steps=0, num_lsq_iterations=0,
+                           final_least_squares=1, **kw)
+
+
+def sample(seed, pair, it, k, n):
+    idx = np.zeros(k, np.int32)
+    _check(lib().ssfm_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(it), k, n,
+                             idx.ctypes.data_as(C.POINTER(C.c_int32))))
+    return idx
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Engine:
+    """One handle = one GPU + one stream (include/ssfm.h)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().ssfm_create(int(device), C.byref(self._h)))
+        self.device = device
+        self._num_pairs = 0
+        self._num_corr = 0
+
+    def close(self):
+        if self._h:
+            lib().ssfm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the batched entry point --------------------------------------------------------
+    def upload(self, rays, offsets, device_ptr=None):
+        """rays: (M, 6) float64 host array (RayPair memory), or device_ptr=int for rays already in HBM."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        b = SsfmBatch()
+        b.num_pairs = len(offsets) - 1
+        b.offsets = _p(offsets, C.c_int64)
+        if device_ptr is not None:
+            b.rays = C.c_void_p(int(device_ptr))
+            b.rays_on_device = 1
+        else:
+            rays = np.ascontiguousarray(rays, np.float64)
+            assert rays.size == 6 * int(offsets[-1])
+            self._keep = rays
+            b.rays = C.c_void_p(rays.ctypes.data)
+            b.rays_on_device = 0
+        _check(lib().ssfm_upload(self._h, C.byref(b)))
+        self._num_pairs = b.num_pairs
+        self._num_corr = int(offsets[-1])
+        self._keep = None
+
+    def run(self, opt):
+        _check(lib().ssfm_run(self._h, C.byref(opt)))
+
+    def download(self, want_flags=True):
+        res = np.zeros(self._num_pairs, RESULT_DTYPE)
+        flags = np.zeros(self._num_corr, np.uint8) if want_flags else None
+        _check(lib().ssfm_download(self._h, C.c_void_p(res.ctypes.data),
+                                   C.c_void_p(flags.ctypes.data) if want_flags and self._num_corr else None))
+        return res, flags
+
+    def estimate_pairs(self, rays, offsets, opt, want_flags=True):
+        """ssfm_estimate_pairs: upload + run + download in one call (host buffers in, host buffers out)."""
+        rays = np.ascontiguousarray(rays, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0)
+        res = np.zeros(b.num_pairs, RESULT_DTYPE)
+        flags = np.zeros(int(offsets[-1]), np.uint8) if want_flags else None
+        _check(lib().ssfm_estimate_pairs(self._h, C.byref(b), C.byref(opt), C.c_void_p(res.ctypes.data),
+                                         C.c_void_p(flags.ctypes.data) if want_flags and len(flags) else None))
+        self._num_pairs = b.num_pairs
+        self._num_corr = int(offsets[-1])
+        return res, flags
+
+    def stats(self):
+        s = SsfmRunStats()
+        _check(lib().ssfm_get_stats(self._h, C.byref(s)))
+        return s
+
+    def device_results(self):
+        ptr = C.c_void_p()
+        n = C.c_int32()
+        _check(lib().ssfm_device_results(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    # ---- replay hooks -------------------------------------------------------------------
+    def minimal_solve(self, rays, samples, solver=SOLVER_ACTION_MATRIX):
+        rays = np.ascontiguousarray(rays, np.float64)
+        samples = np.ascontiguousarray(samples, np.int32).reshape(-1, 3)
+        ns = len(samples)
+        models = np.zeros((ns, 4, 6))
+        nm = np.zeros(ns, np.int32)
+        _check(lib().ssfm_minimal_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns, solver,
+                                        _p(models, C.c_double), _p(nm, C.c_int32)))
+        return models, nm
+
+    def score(self, models6, rays, thr2):
+        models6 = np.ascontiguousarray(models6, np.float64).reshape(-1, 6)
+        rays = np.ascontiguousarray(rays, np.float64)
+        M = len(models6)
+        scores = np.zeros(M, np.float32)
+        counts = np.zeros(M, np.int32)
+        ms = C.c_float()
+        _check(lib().ssfm_score(self._h, _p(models6, C.c_double), M, _p(rays, C.c_double), len(rays), C.c_double(thr2),
+                                _p(scores, C.c_float), _p(counts, C.c_int32), C.byref(ms)))
+        return scores, counts, ms.value
+
+    def score_exact(self, E9, rays, thr2):
+        E9 = np.ascontiguousarray(E9, np.float64).reshape(-1, 9)
+        rays = np.ascontiguousarray(rays, np.float64)
+        M = len(E9)
+        scores = np.zeros(M)
+        counts = np.zeros(M, np.int32)
+        _check(lib().ssfm_score_exact(self._h, _p(E9, C.c_double), M, _p(rays, C.c_double), len(rays), C.c_double(thr2),
+                                      _p(scores, C.c_double), _p(counts, C.c_int32)))
+        return scores, counts
+
+    def least_squares(self, rays, samples, E9, inward=False):
+        """samples: list of index arrays; E9: (len(samples), 9) initial models.  Returns refined (.., 9)."""
+        rays = np.ascontiguousarray(rays, np.float64)
+        offs = np.zeros(len(samples) + 1, np.int32)
+        offs[1:] = np.cumsum([len(s) for s in samples])
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in samples]) if len(samples) else
+                                   np.zeros(0, np.int32), np.int32)
+        if idx.size == 0:
+            idx = np.zeros(1, np.int32)
+        E = np.array(E9, np.float64).reshape(-1, 9).copy()
+        _check(lib().ssfm_least_squares(self._h, _p(rays, C.c_double), len(rays), _p(idx, C.c_int32), _p(offs, C.c_int32),
+                                        len(samples), int(inward), _p(E, C.c_double)))
+        return E
+
+    def decompose(self, E9, inward=False):
+        E = np.ascontiguousarray(E9, np.float64).reshape(-1, 9)
+        r = np.zeros((len(E), 3))
+        t = np.zeros((len(E), 3))
+        _check(lib().ssfm_decompose(self._h, _p(E, C.c_double), len(E), int(inward), _p(r, C.c_double), _p(t, C.c_double)))
+        return r, t
+
+    def lo_shuffle(self, seed, sizes, targets):
+        sizes = np.ascontiguousarray(sizes, np.int32)
+        targets = np.ascontiguousarray(targets, np.int32)
+        out = np.zeros(max(int(targets.sum()), 1), np.int32)
+        _check(lib().ssfm_lo_shuffle(self._h, C.c_uint32(seed), len(sizes), _p(sizes, C.c_int32), _p(targets, C.c_int32),
+                                     _p(out, C.c_int32)))
+        return out[:int(targets.sum())]
+
+    def measure_fp32_peak(self):
+        t = C.c_double()
+        _check(lib().ssfm_measure_fp32_peak(self._h, C.byref(t)))
+        return t.value
+
+
+from . import problems  # noqa: E402,F401
+from . import sharding  # noqa: E402,F401

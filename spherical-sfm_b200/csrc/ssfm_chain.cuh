@@ -1,0 +1,613 @@
+// ssfm_chain.cuh -- the float64 "certification" stage: everything in the reference's RANSAC loop
+// that is sequential per pair, written once over an execution context Ctx:
+//   WarpCtx   (ssfm_kernels.cu): one warp per image pair, lanes stride over correspondences,
+//             sums by xor-butterfly shuffles (bit-identical on every lane -> uniform control flow)
+//   SerialCtx (tests/hostshim): one host thread, sequential sums -> the reference's summation order;
+//             TEST-ONLY, never part of libssfm_b200.so.
+//
+// Reference being restated (include/RansacLib/ransac.h): EstimateModel :128-275, ScoreModel :295-303,
+// GetInliers :311-336, LocalOptimization :341-407, LeastSquaresFit :409-420, UpdateBestModel :422-428;
+// VanillaMSAC (evaluation/vanilla_ransac.h:23-99); legacy MSAC (include/sphericalsfm/msac.h:67-131);
+// SphericalEstimator::LeastSquares / NonMinimalSolver (src/spherical_estimator.cpp:86-157).
+#pragma once
+#include "ssfm_math.cuh"
+
+namespace ssfm {
+
+struct Params {
+  uint32_t min_iters, max_iters;
+  double eta;   // 1 - success_probability
+  double thr2;  // squared_inlier_threshold
+  uint32_t seed;
+  int num_lo_steps;
+  double thr_mult;
+  int num_lsq_iters;
+  int min_sample_mult;
+  int non_min_mult;
+  uint32_t lo_start;
+  int final_lsq;
+  int solver, driver, inward;
+  int fixed_budget;
+  double fixed_prob;
+  uint32_t first_pair_id;
+  float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
+};
+
+// Per-pair RANSAC state carried across rounds (RansacStatistics + the loop's locals).
+struct PairState {
+  double E_best[9];     // *best_model
+  double E_bestmin[9];  // best_minimal_model
+  double best_model_score;
+  double best_min_score;
+  double inlier_ratio;
+  double legacy_num_iter;  // MSAC_FIXED: num_iter (msac.h:77)
+  long long evals_exact;
+  uint32_t it;         // stats.num_iterations
+  uint32_t max_iters;  // max_num_iterations (adaptive)
+  int best_num_inliers;
+  int num_lo;
+  int done;
+  float runmin32;  // running minimum of the FP32 per-iteration scores
+};
+
+struct SerialCtx {
+  SSFM_HD int lane() const { return 0; }
+  SSFM_HD int width() const { return 1; }
+  SSFM_HD double sum(double x) const { return x; }
+  SSFM_HD int sum_i(int x) const { return x; }
+  SSFM_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
+  SSFM_HD float prefix_min_excl(float x, float init) const { (void)x; return init; }
+  SSFM_HD float min_f(float x) const { return x; }
+  SSFM_HD void sync() const {}
+};
+
+template <class Ctx>
+SSFM_HD_NOINLINE double msac_score_exact(const Ctx& cx, const double* E, const double* rays, int n, double thr, long long* evals) {
+  double s = 0.0;
+  for (int i = cx.lane(); i < n; i += cx.width()) {
+    const double e = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
+    s += (thr < e) ? thr : e;  // std::min(e, thr) incl. its NaN behaviour (ransac.h:306-309)
+  }
+  *evals += n;
+  return cx.sum(s);
+}
+
+// GetInliers: count (and optionally list, in index order) the points with err < thr
+// (or <= thr for the legacy driver, msac.h:60).
+template <class Ctx>
+SSFM_HD_NOINLINE int collect_inliers(const Ctx& cx, const double* E, const double* rays, int n, double thr, bool inclusive,
+                            int* list, unsigned char* flags, long long* evals) {
+  int count = 0;
+  for (int base = 0; base < n; base += cx.width()) {
+    const int i = base + cx.lane();
+    bool in = false;
+    if (i < n) {
+      const double e = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
+      in = inclusive ? (e <= thr) : (e < thr);
+      if (flags) flags[i] = in ? 1 : 0;
+    }
+    const unsigned m = cx.ballot(in);
+    if (list && in) {
+      const unsigned below = cx.width() == 1 ? 0u : (m & ((1u << cx.lane()) - 1u));
+#if defined(__CUDA_ARCH__)
+      list[count + __popc(below)] = i;
+#else
+      list[count + __builtin_popcount(below)] = i;
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    count += __popc(m);
+#else
+    count += __builtin_popcount(m);
+#endif
+  }
+  *evals += n;
+  cx.sync();
+  return count;
+}
+
+// RandomShuffleAndResize (include/RansacLib/utils.h:34-52) with the LO generator.  Serial: one
+// lane walks the whole Fisher-Yates so the generator consumes exactly the reference's draws.
+template <class Ctx>
+SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list, int n) {
+  if (cx.lane() == 0) {
+    for (int i = 0; i < n - 1; ++i) {
+      const int j = uniform_int_libstdcxx(mt, i, n - 1);
+      const int tmp = list[i];
+      list[i] = list[j];
+      list[j] = tmp;
+    }
+  }
+  cx.sync();
+}
+
+// SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157): Ceres 2.2 trust-region
+// LM (dense normal Cholesky, Jacobi scaling, default tolerances, <= 200 iterations) over the
+// residuals listed in `sample`; E is rebuilt from the optimised rotation only (:156).
+template <class Ctx>
+SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int* sample, int n, bool inward, double* E) {
+  double x[6];
+  {
+    double r[3], t[3];
+    decompose_spherical_E(E, inward, r, t);
+    x[0] = r[0]; x[1] = r[1]; x[2] = r[2];
+    x[3] = 0.0; x[4] = 0.0; x[5] = inward ? 1.0 : -1.0;
+  }
+  const double t0z = inward ? 1.0 : -1.0;
+  double H[21], g[6], scale[6], diagonal[6];
+  double x_cost = 0.0, gmax = 0.0;
+  bool have_scale = false;
+
+  // evaluate cost, gradient and J^T J at x (jets), apply Jacobi scaling
+  auto eval_jac = [&](const double* xx) {
+    double Hl[21], gl[6], c = 0.0;
+    for (int a = 0; a < 21; ++a) Hl[a] = 0.0;
+    for (int a = 0; a < 6; ++a) gl[a] = 0.0;
+    for (int i = cx.lane(); i < n; i += cx.width()) {
+      const double* ry = rays + 6 * (size_t)sample[i];
+      Jet6 r1[3] = {jvar(xx[0], 0), jvar(xx[1], 1), jvar(xx[2], 2)};
+      Jet6 t1[3] = {jvar(xx[3], 3), jvar(xx[4], 4), jvar(xx[5], 5)};
+      const Jet6 r = sampson_residual<Jet6>(r1, t1, t0z, ry, ry + 3);
+      c += r.a * r.a;
+      int k = 0;
+      for (int a = 0; a < 6; ++a) {
+        gl[a] += r.v[a] * r.a;
+        for (int b = 0; b <= a; ++b) Hl[k++] += r.v[a] * r.v[b];
+      }
+    }
+    for (int a = 0; a < 21; ++a) H[a] = cx.sum(Hl[a]);
+    for (int a = 0; a < 6; ++a) g[a] = cx.sum(gl[a]);
+    c = cx.sum(c);
+    gmax = 0.0;
+    for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(g[a]));  // gradient of the UNSCALED problem
+    if (!have_scale) {
+      for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(H[a * (a + 1) / 2 + a]));
+      have_scale = true;
+    }
+    int k = 0;
+    for (int a = 0; a < 6; ++a) {
+      g[a] *= scale[a];
+      for (int b = 0; b <= a; ++b) H[k++] *= scale[a] * scale[b];
+    }
+    return 0.5 * c;
+  };
+  auto eval_cost = [&](const double* xx) {
+    double c = 0.0;
+    for (int i = cx.lane(); i < n; i += cx.width()) {
+      const double* ry = rays + 6 * (size_t)sample[i];
+      const double r = sampson_residual<double>(xx, xx + 3, t0z, ry, ry + 3);
+      c += r * r;
+    }
+    return 0.5 * cx.sum(c);
+  };
+
+  x_cost = eval_jac(x);
+  if (isfinite(x_cost)) {
+    double radius = 1e4, decrease_factor = 2.0;
+    bool reuse_diagonal = false;
+    int invalid = 0;
+    for (int iteration = 0;;) {
+      if (iteration >= 200) break;
+      if (gmax <= 1e-10) break;
+      if (radius < 1e-32) break;
+      ++iteration;
+      if (!reuse_diagonal)
+        for (int a = 0; a < 6; ++a) diagonal[a] = fmin(fmax(H[a * (a + 1) / 2 + a], 1e-6), 1e32);
+      double Hd[21], step[6];
+      for (int a = 0; a < 21; ++a) Hd[a] = H[a];
+      for (int a = 0; a < 6; ++a) Hd[a * (a + 1) / 2 + a] += diagonal[a] / radius;
+      bool valid = cholesky_solve6(Hd, g, step);
+      reuse_diagonal = true;
+      double model_cost_change = 0.0;
+      if (valid) {
+        // model_cost_change = -(J s).(r + J s / 2) = -(s.g + s^T H s / 2)
+        double sg = 0.0, sHs = 0.0;
+        int k = 0;
+        for (int a = 0; a < 6; ++a) {
+          step[a] = -step[a];
+          sg += step[a] * g[a];
+        }
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b <= a; ++b) sHs += (a == b ? 1.0 : 2.0) * H[k++] * step[a] * step[b];
+        model_cost_change = -(sg + 0.5 * sHs);
+        if (!(model_cost_change > 0.0)) valid = false;
+      }
+      if (!valid) {
+        if (++invalid >= 10) break;
+        radius /= decrease_factor;
+        decrease_factor *= 2.0;
+        continue;
+      }
+      invalid = 0;
+      double cand[6], step_norm = 0.0, x_norm = 0.0;
+      for (int a = 0; a < 6; ++a) {
+        const double d = step[a] * scale[a];
+        cand[a] = x[a] + d;
+        step_norm += d * d;
+        x_norm += x[a] * x[a];
+      }
+      step_norm = sqrt(step_norm);
+      x_norm = sqrt(x_norm);
+      double cand_cost = eval_cost(cand);
+      if (!isfinite(cand_cost)) cand_cost = kDblMax;
+      if (step_norm <= 1e-8 * (x_norm + 1e-8)) break;               // parameter tolerance
+      const double cost_change = x_cost - cand_cost;
+      if (fabs(cost_change) <= 1e-6 * x_cost) break;                // function tolerance
+      const double rho = cost_change / model_cost_change;
+      if (rho > 1e-3) {
+        for (int a = 0; a < 6; ++a) x[a] = cand[a];
+        x_cost = eval_jac(x);
+        const double tt = 2.0 * rho - 1.0;
+        radius = radius / fmax(1.0 / 3.0, 1.0 - tt * tt * tt);
+        radius = fmin(1e16, radius);
+        decrease_factor = 2.0;
+        reuse_diagonal = false;
+      } else {
+        radius /= decrease_factor;
+        decrease_factor *= 2.0;
+        reuse_diagonal = true;
+      }
+    }
+  }
+  double R[9];
+  so3exp(x, R);
+  make_spherical_E(R, inward, E);
+}
+
+struct Scratch {
+  int* list_a;   // n ints
+  int* list_b;   // n ints
+  uint32_t* mt;  // 625 words
+};
+
+struct PairView {
+  const double* rays;  // 6 doubles per correspondence
+  int n;
+};
+
+template <class Ctx>
+SSFM_HD_NOINLINE void lsq_fit(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, double thresh, double* E,
+                     long long* evals) {  // LeastSquaresFit, ransac.h:409-420
+  const int cap = P.min_sample_mult * 3;
+  const int n = collect_inliers(cx, E, pv.rays, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals);
+  if (n < 3) return;
+  shuffle_and_resize(cx, sc.mt, sc.list_a, n);
+  least_squares(cx, pv.rays, sc.list_a, n < cap ? n : cap, P.inward != 0, E);
+}
+
+SSFM_HD void keep_better(double s, const double* m, double* sb, double* mb) {  // UpdateBestModel :422-428
+  if (s < *sb) {
+    *sb = s;
+    for (int i = 0; i < 9; ++i) mb[i] = m[i];
+  }
+}
+
+// SphericalEstimator::NonMinimalSolver (src/spherical_estimator.cpp:86-108).  The reference runs
+// the action-matrix solver on the whole sample; with its pivoted QR that is the minimal solve on
+// the three greedily pivoted correspondences (largest remaining epipolar-row norm), see
+// nullspace_colpiv.  Picks the model with the smallest summed Sampson error over the sample.
+template <class Ctx>
+SSFM_HD_NOINLINE bool non_minimal_solver(const Ctx& cx, const PairView& pv, const int* sample, int ns, double* E) {
+  if (ns < 3) return false;
+  // greedy pivoting by modified Gram-Schmidt on the epipolar rows (ns <= 64 handled serially & uniformly)
+  int pick[3] = {-1, -1, -1};
+  double q[3][6];
+  for (int k = 0; k < 3; ++k) {
+    double best = -1.0;
+    int bi = -1;
+    for (int i = 0; i < ns; ++i) {
+      if (i == pick[0] || i == pick[1]) continue;
+      double a[6];
+      const double* ry = pv.rays + 6 * (size_t)sample[i];
+      epipolar_row(ry, ry + 3, a);
+      for (int j = 0; j < k; ++j) {
+        double d = 0.0;
+        for (int r = 0; r < 6; ++r) d += q[j][r] * a[r];
+        for (int r = 0; r < 6; ++r) a[r] -= d * q[j][r];
+      }
+      double s = 0.0;
+      for (int r = 0; r < 6; ++r) s += a[r] * a[r];
+      if (s > best) { best = s; bi = i; }
+    }
+    pick[k] = bi;
+    double a[6];
+    const double* ry = pv.rays + 6 * (size_t)sample[bi];
+    epipolar_row(ry, ry + 3, a);
+    for (int j = 0; j < k; ++j) {
+      double d = 0.0;
+      for (int r = 0; r < 6; ++r) d += q[j][r] * a[r];
+      for (int r = 0; r < 6; ++r) a[r] -= d * q[j][r];
+    }
+    double s = 0.0;
+    for (int r = 0; r < 6; ++r) s += a[r] * a[r];
+    s = 1.0 / sqrt(s);
+    for (int r = 0; r < 6; ++r) q[k][r] = a[r] * s;
+  }
+  double models[4][6];
+  const double* c0 = pv.rays + 6 * (size_t)sample[pick[0]];
+  const double* c1 = pv.rays + 6 * (size_t)sample[pick[1]];
+  const double* c2 = pv.rays + 6 * (size_t)sample[pick[2]];
+  solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, models);
+  double best_score = INFINITY;
+  int best_ind = 0;
+  for (int m = 0; m < 4; ++m) {
+    double Em[9];
+    E_from_p(models[m], Em);
+    double score = 0.0;
+    for (int j = 0; j < ns; ++j) {
+      const double* ry = pv.rays + 6 * (size_t)sample[j];
+      score += sampson_exact(Em, ry, ry + 3);
+    }
+    if (score < best_score) { best_score = score; best_ind = m; }
+  }
+  E_from_p(models[best_ind], E);
+  (void)cx;
+  return true;
+}
+
+template <class Ctx>
+SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, double* E_best,
+                                double* score_best, long long* evals) {  // ransac.h:341-407
+  if (4 > pv.n) return;  // non_minimal_sample_size() == 4
+  const double thr = P.thr2, mult = P.thr_mult;
+  double m_init[9];
+  for (int i = 0; i < 9; ++i) m_init[i] = E_best[i];
+  lsq_fit(cx, P, pv, sc, thr * mult, m_init, evals);
+  double score = msac_score_exact(cx, m_init, pv.rays, pv.n, thr, evals);
+  keep_better(score, m_init, score_best, E_best);
+  if (P.num_lo_steps <= 0) return;  // inliers_base is only used by the steps below
+  const int nbase = collect_inliers(cx, m_init, pv.rays, pv.n, thr * mult, false, sc.list_b, (unsigned char*)0, evals);
+  int non_min = 3 * P.non_min_mult;
+  if (nbase / 2 < non_min) non_min = nbase / 2;
+  if (non_min < 4) non_min = 4;
+  for (int r = 0; r < P.num_lo_steps; ++r) {
+    // sample = inliers_base; RandomShuffleAndResize(non_min)   (:380-381)
+    for (int i = cx.lane(); i < nbase; i += cx.width()) sc.list_a[i] = sc.list_b[i];
+    cx.sync();
+    shuffle_and_resize(cx, sc.mt, sc.list_a, nbase);
+    // std::vector::resize(target) grows with zeros when target > size (non_min > nbase)
+    const int ns = non_min;
+    if (ns > nbase) {
+      if (cx.lane() == 0)
+        for (int i = nbase; i < ns; ++i) sc.list_a[i] = 0;
+      cx.sync();
+    }
+    double m[9];
+    if (!non_minimal_solver(cx, pv, sc.list_a, ns, m)) continue;
+    score = msac_score_exact(cx, m, pv.rays, pv.n, thr, evals);
+    keep_better(score, m, score_best, E_best);
+    lsq_fit(cx, P, pv, sc, thr, m, evals);
+    double th = mult * thr;
+    const double dth = (mult - 1.0) * thr / (double)(int)(P.num_lsq_iters - 1);
+    for (int i = 0; i < P.num_lsq_iters; ++i) {
+      lsq_fit(cx, P, pv, sc, th, m, evals);
+      score = msac_score_exact(cx, m, pv.rays, pv.n, thr, evals);
+      keep_better(score, m, score_best, E_best);
+      th -= dth;
+    }
+  }
+}
+
+// GetInliers on *best_model + inlier ratio + NumRequiredIterations (ransac.h:231-238)
+template <class Ctx>
+SSFM_HD_NOINLINE void refresh(const Ctx& cx, const Params& P, const PairView& pv, PairState& st, bool update_max) {
+  st.best_num_inliers = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, (int*)0, (unsigned char*)0, &st.evals_exact);
+  st.inlier_ratio = (double)st.best_num_inliers / (double)pv.n;
+  if (update_max) st.max_iters = required_iterations(st.inlier_ratio, P.eta, 3, P.min_iters, P.max_iters);
+}
+
+SSFM_HD void init_state(const Params& P, int n, PairState& st) {
+  for (int i = 0; i < 9; ++i) { st.E_best[i] = 0.0; st.E_bestmin[i] = 0.0; }
+  st.best_model_score = kDblMax;
+  st.best_min_score = P.driver == 2 ? INFINITY : kDblMax;
+  st.inlier_ratio = 0.0;
+  st.legacy_num_iter = (double)P.fixed_budget;
+  st.evals_exact = 0;
+  st.it = 0;
+  st.max_iters = P.max_iters > P.min_iters ? P.max_iters : P.min_iters;
+  if (P.driver == 2) st.max_iters = (uint32_t)(P.fixed_budget > 0 ? P.fixed_budget : 0);
+  st.best_num_inliers = 0;
+  st.num_lo = 0;
+  st.done = n < 3 ? 1 : 0;  // kMinSampleSize > kNumData -> return 0 (ransac.h:137-139)
+  st.runmin32 = INFINITY;
+}
+
+// Number of minimal-sample iterations the pair still wants (for the next look-ahead round).
+SSFM_HD uint32_t iterations_wanted(const Params& P, const PairState& st) {
+  if (st.done) return 0;
+  uint32_t lim = st.max_iters;
+  if (P.driver == 2) {
+    const double ni = st.legacy_num_iter;
+    const uint32_t c = ni >= (double)P.fixed_budget ? (uint32_t)P.fixed_budget : (uint32_t)ceil(ni > 0 ? ni : 0);
+    lim = c < lim ? c : lim;
+  }
+  return lim > st.it ? lim - st.it : 0;
+}
+
+// Consume one look-ahead round: iterations [st.it, st.it + navail) of this pair were sampled,
+// solved (models: navail x 4 x 6 doubles, NaN = absent) and scored in FP32 (s32[j] = the best of the
+// four FP32 MSAC costs of iteration j).  An iteration can only matter to the reference loop if
+// its float64 score beats the best so far, so only iterations whose FP32 score is within
+// cand_margin of the running FP32 minimum are re-scored here in float64 (bit-compatible
+// arithmetic); everything the reference does at such an iteration -- best-model bookkeeping,
+// local optimisation, inlier refresh, adaptive termination -- then runs exactly.
+template <class Ctx>
+SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, PairState& st,
+                           const double* models, int mstride, const float* s32, int navail) {
+  // model (slot j, root m, parameter i) lives at models[(m * 6 + i) * mstride + j]
+  const bool lo_driver = P.driver == 0;
+  const bool legacy = P.driver == 2;
+  int j = 0;
+  while (!st.done) {
+    // loop condition of the reference's for/while
+    if (legacy) {
+      if (!((double)st.it < st.legacy_num_iter && (int)st.it < P.fixed_budget)) { st.done = 1; break; }
+    } else {
+      if (st.it >= st.max_iters) { st.done = 1; break; }
+    }
+    if (j >= navail) break;  // need another look-ahead round
+    // ---- find the next iteration in this round that can matter
+    int jn = navail;  // first candidate / special index >= j
+    {
+      float run = st.runmin32;
+      int base = j;
+      while (base < navail && jn == navail) {
+        const int jj = base + cx.lane();
+        const float s = jj < navail ? s32[jj] : INFINITY;
+        const float before = cx.prefix_min_excl(s, run);
+        const bool cand = s < INFINITY && s <= before * (1.0f + P.cand_margin);
+        const bool special = lo_driver && jj < navail && (st.it + (uint32_t)(jj - j)) == P.lo_start;
+        const unsigned m = cx.ballot(cand || special);
+        if (m) {
+#if defined(__CUDA_ARCH__)
+          jn = base + (__ffs(m) - 1);
+#else
+          jn = base + (__builtin_ffs(m) - 1);
+#endif
+        }
+        // the running minimum covers every iteration consumed so far (<= jn)
+        run = fminf(run, cx.min_f(jj <= jn ? s : INFINITY));
+        base += cx.width();
+      }
+      st.runmin32 = run;
+    }
+    // iterations j .. jn-1 cannot matter: skip them, honouring the termination test
+    {
+      const uint32_t skip = (uint32_t)(jn - j);
+      uint32_t lim = st.max_iters;
+      if (legacy) {
+        const double ni = st.legacy_num_iter;
+        const uint32_t c = ni >= (double)P.fixed_budget ? (uint32_t)P.fixed_budget : (uint32_t)ceil(ni > 0 ? ni : 0);
+        lim = c;
+      }
+      if (st.it + skip >= lim) {
+        // the loop ends inside the skipped stretch (or exactly at its end)
+        if (lim > st.it) st.it = lim;
+        st.done = 1;
+        break;
+      }
+      st.it += skip;
+      j = jn;
+    }
+    if (j >= navail) break;
+    // ---- iteration st.it (slot j) is a candidate and/or the lo_start iteration
+    if (lo_driver && st.it == P.lo_start && st.best_min_score < kDblMax) {  // ransac.h:163-178
+      ++st.num_lo;
+      local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.evals_exact);
+      refresh(cx, P, pv, st, true);
+    }
+    // exact re-scoring of the iteration's models (GetBestEstimatedModelId, :278-293)
+    double local_best = legacy ? INFINITY : kDblMax;
+    int local_id = -1;
+    int nvalid = 0;
+    for (int m = 0; m < 4; ++m) {
+      double p[6];
+      for (int i = 0; i < 6; ++i) p[i] = models[(size_t)(m * 6 + i) * mstride + j];
+      if (p[0] != p[0]) continue;  // absent (or NaN) model: can never win a '<'
+      ++nvalid;
+      double Em[9];
+      E_from_p(p, Em);
+      const double s = msac_score_exact(cx, Em, pv.rays, pv.n, P.thr2, &st.evals_exact);
+      if (legacy) {
+        if (s < st.best_min_score && s < local_best) { local_best = s; local_id = m; }
+      } else if (s < local_best) {
+        local_best = s;
+        local_id = m;
+      }
+    }
+    // MinimalSolver returned <= 0 models -> `continue` (ransac.h:185).  The action-matrix and
+    // polynomial solvers always return 4 (possibly NaN) matrices; the Sturm variant returns the
+    // number of real roots it kept.
+    const bool has_models = P.solver != 2 || nvalid > 0;
+    if (legacy) {
+      if (local_id >= 0) {  // msac.h:103-110 (running best over all models in order)
+        double p[6], Em[9];
+        for (int i = 0; i < 6; ++i) p[i] = models[(size_t)(local_id * 6 + i) * mstride + j];
+        E_from_p(p, Em);
+        st.best_min_score = local_best;
+        st.best_model_score = local_best;
+        for (int i = 0; i < 9; ++i) st.E_best[i] = Em[i];
+        st.best_num_inliers = collect_inliers(cx, Em, pv.rays, pv.n, P.thr2, true, (int*)0, (unsigned char*)0, &st.evals_exact);
+        st.inlier_ratio = (double)st.best_num_inliers / (double)pv.n;
+        const double outlier_ratio = (pv.n - st.best_num_inliers) / (double)pv.n;
+        if (outlier_ratio < 1.0) {  // msac.h:119-126
+          double ni = log(1. - P.fixed_prob) / log(1. - pow(1. - outlier_ratio, 3.0));
+          if (ni > P.fixed_budget) ni = P.fixed_budget;
+          st.legacy_num_iter = ni;
+        }
+      }
+    } else if (has_models) {
+      const bool is_best = local_id >= 0 && local_best < st.best_min_score;
+      const bool at_lo_start = lo_driver && st.it == P.lo_start;
+      if (is_best || at_lo_start) {  // ransac.h:195-239
+        if (is_best) {
+          double p[6], Em[9];
+          for (int i = 0; i < 6; ++i) p[i] = models[(size_t)(local_id * 6 + i) * mstride + j];
+          E_from_p(p, Em);
+          st.best_min_score = local_best;
+          for (int i = 0; i < 9; ++i) st.E_bestmin[i] = Em[i];
+          keep_better(st.best_min_score, st.E_bestmin, &st.best_model_score, st.E_best);
+        }
+        const bool run_lo = lo_driver && st.it >= P.lo_start && st.best_min_score < kDblMax;
+        if (is_best || run_lo) {
+          if (run_lo) {
+            ++st.num_lo;
+            double score = st.best_min_score;
+            local_optimization(cx, P, pv, sc, st.E_bestmin, &score, &st.evals_exact);
+            keep_better(score, st.E_bestmin, &st.best_model_score, st.E_best);
+          }
+          refresh(cx, P, pv, st, true);
+        }
+      }
+    }
+    ++st.it;
+    ++j;
+  }
+}
+
+// After the loop: the late LO (:245-255), the final least squares (:257-272), and what the
+// callers do next: the inlier mask (examples/spherical_sfm_tools.cpp:388-392) and the pose
+// (:414-418).  Writes r, t; returns the per-pair status.
+template <class Ctx>
+SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, PairState& st, double* r,
+                          double* t, unsigned char* flags) {
+  r[0] = r[1] = r[2] = 0.0;
+  t[0] = t[1] = t[2] = 0.0;
+  if (pv.n < 3) {
+    if (flags)
+      for (int i = cx.lane(); i < pv.n; i += cx.width()) flags[i] = 0;
+    return 1;
+  }
+  if (P.driver == 0) {
+    if (st.it <= P.lo_start && st.best_model_score < kDblMax) {
+      ++st.num_lo;
+      local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.evals_exact);
+      refresh(cx, P, pv, st, false);
+    }
+    if (P.final_lsq) {
+      // LeastSquares on ALL current inliers of best_model (stats.inlier_indices)
+      double refined[9];
+      for (int i = 0; i < 9; ++i) refined[i] = st.E_best[i];
+      const int ni = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, &st.evals_exact);
+      least_squares(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined);
+      const double score = msac_score_exact(cx, refined, pv.rays, pv.n, P.thr2, &st.evals_exact);
+      if (score < st.best_model_score) {
+        st.best_model_score = score;
+        for (int i = 0; i < 9; ++i) st.E_best[i] = refined[i];
+        refresh(cx, P, pv, st, false);
+      }
+    }
+  }
+  const bool have = P.driver == 2 ? (st.best_min_score < INFINITY) : (st.best_model_score < kDblMax);
+  if (!have) {
+    if (P.driver == 2) st.best_model_score = INFINITY;
+    if (flags)
+      for (int i = cx.lane(); i < pv.n; i += cx.width()) flags[i] = 0;
+    return 2;
+  }
+  if (flags) collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, P.driver == 2, (int*)0, flags, &st.evals_exact);
+  decompose_spherical_E(st.E_best, P.inward != 0, r, t);
+  return 0;
+}
+
+}  // namespace ssfm

@@ -1,0 +1,625 @@
+// ssfm_engine.cu -- host side of libssfm_b200.so: the extern "C" layer declared in include/ssfm.h,
+// device-memory management and the round scheduler that drives the kernels in ssfm_kernels.cuh.
+//
+// Execution model (one handle = one GPU, one stream):
+//   upload : H2D of the caller's RayPair memory (float64 AoS) + k_pack into float4 SoA planes
+//   run    : for each pass of <= kMaxPassPairs pairs
+//              k_init_pairs, k_finish_trivial
+//              repeat until no pair is active ("look-ahead rounds"):
+//                k_sample_solve  : every active pair speculates its next <= cap iterations
+//                k_score_rounds  : FP32 scoring of all those hypotheses (the hot kernel)
+//                k_chain         : FP64 certification + sequential LO-MSAC logic, termination,
+//                                  compaction of the still-active pairs
+//              (one 4-byte D2H per round: the number of active pairs)
+//   download: D2H of the per-pair result table (+ optional inlier flags)
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ssfm_kernels.cuh"
+
+using namespace ssfm;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define SSFM_CK(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      return fail(e__ == cudaErrorMemoryAllocation ? SSFM_ERR_OOM : SSFM_ERR_CUDA,             \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                        \
+    }                                                                                          \
+  } while (0)
+
+constexpr int kMaxPassPairs = 131072;
+constexpr int kRoundCap = 256;
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct ssfm_engine {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  // resident batch
+  int P = 0;
+  long long M = 0;
+  std::vector<long long> h_offsets;
+  const double* d_rays = nullptr;  // either rays_own.p or the caller's device pointer
+  DevBuf<double> rays_own;
+  DevBuf<float4> u4, v4;
+  DevBuf<long long> offsets;
+  bool resident = false;
+  // run buffers
+  DevBuf<PairState> states;
+  DevBuf<uint32_t> mt;
+  DevBuf<int> active0, active1, navail, list_a, list_b, counts;
+  DevBuf<double> models;
+  DevBuf<float> s32;
+  DevBuf<unsigned long long> counters;
+  DevBuf<SsfmPairResult> results;
+  DevBuf<unsigned char> flags;
+  bool have_results = false;
+  SsfmRunStats stats = {};
+  int* h_count = nullptr;  // pinned
+};
+
+namespace {
+
+Params make_params(const SsfmOptions& o) {
+  Params P;
+  P.min_iters = o.min_num_iterations;
+  P.max_iters = o.max_num_iterations;
+  P.eta = 1.0 - o.success_probability;
+  P.thr2 = o.squared_inlier_threshold;
+  P.seed = o.random_seed;
+  P.num_lo_steps = o.num_lo_steps;
+  P.thr_mult = o.threshold_multiplier;
+  P.num_lsq_iters = o.num_lsq_iterations;
+  P.min_sample_mult = o.min_sample_multiplicator;
+  P.non_min_mult = o.non_min_sample_multiplier;
+  P.lo_start = o.lo_starting_iterations;
+  P.final_lsq = o.final_least_squares;
+  P.solver = o.solver;
+  P.driver = o.driver;
+  P.inward = o.inward;
+  P.fixed_budget = o.fixed_budget;
+  P.fixed_prob = o.fixed_prob_success;
+  P.first_pair_id = o.first_pair_id;
+  P.cand_margin = 2e-3f;
+  if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
+  return P;
+}
+
+int check_options(const SsfmOptions* o) {
+  if (!o) return fail(SSFM_ERR_INVALID, "options is NULL");
+  if (o->solver < 0 || o->solver > 2) return fail(SSFM_ERR_INVALID, "unknown solver kind");
+  if (o->driver < 0 || o->driver > 2) return fail(SSFM_ERR_INVALID, "unknown driver kind");
+  if (!(o->squared_inlier_threshold > 0.0)) return fail(SSFM_ERR_INVALID, "squared_inlier_threshold must be > 0");
+  if (o->driver == SSFM_DRIVER_MSAC_FIXED && o->fixed_budget <= 0)
+    return fail(SSFM_ERR_INVALID, "fixed_budget must be > 0 for the fixed-budget MSAC driver");
+  return SSFM_OK;
+}
+
+template <int KIND>
+void launch_solve(ssfm_engine* h, const Params& P, int pair0, const int* active, int count, int cap, int R) {
+  dim3 grid(count, (cap + 63) / 64);
+  k_sample_solve<KIND><<<grid, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, active, h->navail.p, h->states.p, R,
+                                                   h->models.p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
+
+const char* ssfm_last_error(void) { return g_last_error.c_str(); }
+
+void ssfm_default_options(SsfmOptions* o) {
+  if (!o) return;
+  o->min_num_iterations = 100u;
+  o->max_num_iterations = 10000u;
+  o->success_probability = 0.9999;
+  o->squared_inlier_threshold = 1.0;
+  o->random_seed = 0u;
+  o->num_lo_steps = 10;
+  o->threshold_multiplier = 1.4142135623730951;
+  o->num_lsq_iterations = 4;
+  o->min_sample_multiplicator = 7;
+  o->non_min_sample_multiplier = 3;
+  o->lo_starting_iterations = 50u;
+  o->final_least_squares = 0;
+  o->solver = SSFM_SOLVER_ACTION_MATRIX;
+  o->driver = SSFM_DRIVER_LO_MSAC;
+  o->inward = 0;
+  o->fixed_budget = 512;
+  o->fixed_prob_success = 0.999;
+  o->first_pair_id = 0u;
+}
+
+int ssfm_create(int device, ssfm_handle* out) {
+  if (!out) return fail(SSFM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SSFM_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                        " (this engine has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SSFM_ERR_INVALID, "device index out of range");
+  SSFM_CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SSFM_CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(SSFM_ERR_NO_DEVICE, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                        "; libssfm_b200 is built for sm_100a only");
+  ssfm_engine* h = new ssfm_engine();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  SSFM_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  for (auto& ev : h->ev) SSFM_CK(cudaEventCreate(&ev));
+  SSFM_CK(cudaMallocHost(&h->h_count, 64));
+  *out = h;
+  return SSFM_OK;
+}
+
+void ssfm_destroy(ssfm_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->rays_own.release(); h->u4.release(); h->v4.release(); h->offsets.release();
+  h->states.release(); h->mt.release(); h->active0.release(); h->active1.release(); h->navail.release();
+  h->list_a.release(); h->list_b.release(); h->counts.release(); h->models.release(); h->s32.release();
+  h->counters.release(); h->results.release(); h->flags.release();
+  for (auto& ev : h->ev) cudaEventDestroy(ev);
+  if (h->h_count) cudaFreeHost(h->h_count);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
+  if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
+  if (b->num_pairs < 0 || (b->num_pairs > 0 && (!b->offsets || !b->rays))) return fail(SSFM_ERR_INVALID, "bad batch");
+  SSFM_CK(cudaSetDevice(h->device));
+  h->resident = false;
+  h->have_results = false;
+  h->P = b->num_pairs;
+  h->h_offsets.assign(b->offsets, b->offsets + b->num_pairs + 1);
+  if (b->num_pairs == 0) h->h_offsets.assign(1, 0);
+  for (int p = 0; p < h->P; ++p)
+    if (h->h_offsets[p + 1] < h->h_offsets[p] || h->h_offsets[p + 1] - h->h_offsets[p] > 0x7fffffffLL)
+      return fail(SSFM_ERR_INVALID, "offsets must be non-decreasing (and each pair < 2^31 correspondences)");
+  if (h->h_offsets[0] != 0) return fail(SSFM_ERR_INVALID, "offsets[0] must be 0");
+  h->M = h->h_offsets[h->P];
+  h->stats = SsfmRunStats();
+  SSFM_CK(h->offsets.ensure(h->P + 1));
+  SSFM_CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), sizeof(long long) * (h->P + 1), cudaMemcpyHostToDevice, h->stream));
+  const size_t m = (size_t)std::max<long long>(h->M, 1);
+  SSFM_CK(h->u4.ensure(m));
+  SSFM_CK(h->v4.ensure(m));
+  SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
+  if (b->rays_on_device) {
+    h->d_rays = b->rays;
+  } else {
+    SSFM_CK(h->rays_own.ensure(m * 6));
+    if (h->M > 0)
+      SSFM_CK(cudaMemcpyAsync(h->rays_own.p, b->rays, sizeof(double) * 6 * (size_t)h->M, cudaMemcpyHostToDevice, h->stream));
+    h->d_rays = h->rays_own.p;
+    h->stats.h2d_bytes = (long long)(sizeof(double) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
+  }
+  if (h->M > 0) {
+    const int threads = 256;
+    const long long blocks = (h->M + threads - 1) / threads;
+    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->u4.p, h->v4.p);
+    SSFM_CK(cudaGetLastError());
+  }
+  SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));  // the caller's buffer may go away after we return
+  float ms = 0.f;
+  SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+  h->stats.pack_ms = ms;
+  h->resident = true;
+  return SSFM_OK;
+}
+
+int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
+  if (!h) return fail(SSFM_ERR_INVALID, "NULL handle");
+  if (int rc = check_options(opt)) return rc;
+  if (!h->resident) return fail(SSFM_ERR_INVALID, "ssfm_run without a resident batch (call ssfm_upload first)");
+  SSFM_CK(cudaSetDevice(h->device));
+  const Params P = make_params(*opt);
+  const double pack_ms = h->stats.pack_ms;
+  const long long h2d = h->stats.h2d_bytes;
+  h->stats = SsfmRunStats();
+  h->stats.pack_ms = pack_ms;
+  h->stats.h2d_bytes = h2d;
+  h->have_results = false;
+  SSFM_CK(h->results.ensure(std::max(h->P, 1)));
+  SSFM_CK(h->flags.ensure((size_t)std::max<long long>(h->M, 1)));
+  SSFM_CK(h->counters.ensure(4));
+  SSFM_CK(h->counts.ensure(4));
+  SSFM_CK(cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
+
+  int first_cap, round_cap;
+  if (P.driver == SSFM_DRIVER_MSAC_FIXED) {
+    first_cap = 32;
+    round_cap = 64;
+  } else {
+    first_cap = (int)std::min<uint32_t>(std::max<uint32_t>(P.min_iters, 32u), 1024u);
+    round_cap = kRoundCap;
+  }
+  if (const char* e = getenv("SSFM_ROUND_CAP")) round_cap = std::max(32, atoi(e));
+  if (const char* e = getenv("SSFM_FIRST_CAP")) first_cap = std::max(32, atoi(e));
+  const int R = std::max(first_cap, round_cap);
+  const float thr32 = (float)P.thr2;
+
+  cudaEvent_t evA = h->ev[0], evB = h->ev[1], evC = h->ev[2], evD = h->ev[3];
+  SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
+  int launches = 0;
+  for (int pair0 = 0; pair0 < h->P; pair0 += kMaxPassPairs) {
+    const int np = std::min(kMaxPassPairs, h->P - pair0);
+    const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
+    const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
+    SSFM_CK(h->states.ensure(np));
+    SSFM_CK(h->active0.ensure(np));
+    SSFM_CK(h->active1.ensure(np));
+    SSFM_CK(h->navail.ensure(np));
+    SSFM_CK(h->models.ensure((size_t)np * 24 * R));
+    SSFM_CK(h->s32.ensure((size_t)np * R));
+    SSFM_CK(h->list_a.ensure(mpass + 16));
+    SSFM_CK(h->list_b.ensure(P.num_lo_steps > 0 ? mpass + 16 : 16));
+    SSFM_CK(h->mt.ensure(P.driver == SSFM_DRIVER_LO_MSAC ? (size_t)np * 625 : 625));
+
+    k_init_pairs<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->mt.p, h->active0.p,
+                                                          h->navail.p, first_cap);
+    SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 4 * sizeof(int), h->stream));
+    k_finish_trivial<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->flags.p, 0,
+                                                              h->results.p + pair0, h->active0.p, h->counts.p);
+    launches += 2;
+    SSFM_CK(cudaMemcpyAsync(h->h_count, h->counts.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    SSFM_CK(cudaStreamSynchronize(h->stream));
+    int count = h->h_count[0];
+    int* act = h->active0.p;
+    int* act_next = h->active1.p;
+    int round = 0;
+    while (count > 0) {
+      const int cap = round == 0 ? first_cap : round_cap;
+      SSFM_CK(cudaEventRecord(evA, h->stream));
+      if (P.solver == 0) launch_solve<0>(h, P, pair0, act, count, cap, R);
+      else if (P.solver == 1) launch_solve<1>(h, P, pair0, act, count, cap, R);
+      else launch_solve<2>(h, P, pair0, act, count, cap, R);
+      SSFM_CK(cudaGetLastError());
+      SSFM_CK(cudaEventRecord(evB, h->stream));
+      {
+        dim3 grid(count, (cap + kScoreThreads - 1) / kScoreThreads);
+        k_score_rounds<<<grid, kScoreThreads, 0, h->stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, h->navail.p, R,
+                                                              h->models.p, thr32, h->s32.p);
+        SSFM_CK(cudaGetLastError());
+      }
+      SSFM_CK(cudaEventRecord(evC, h->stream));
+      SSFM_CK(cudaMemsetAsync(h->counts.p + 1, 0, sizeof(int), h->stream));
+      k_chain<<<(count + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(
+          P, h->d_rays, h->offsets.p, pair0, act, count, h->navail.p, h->states.p, R, h->models.p, h->s32.p, h->list_a.p,
+          h->list_b.p, h->mt.p, c0, h->flags.p + c0, h->results.p + pair0, act_next, h->counts.p + 1, round_cap,
+          h->counters.p);
+      SSFM_CK(cudaGetLastError());
+      SSFM_CK(cudaEventRecord(evD, h->stream));
+      SSFM_CK(cudaMemcpyAsync(h->h_count, h->counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      SSFM_CK(cudaStreamSynchronize(h->stream));
+      float t1 = 0, t2 = 0, t3 = 0;
+      cudaEventElapsedTime(&t1, evA, evB);
+      cudaEventElapsedTime(&t2, evB, evC);
+      cudaEventElapsedTime(&t3, evC, evD);
+      h->stats.solve_ms += t1;
+      h->stats.score_ms += t2;
+      h->stats.chain_ms += t3;
+      h->stats.score_launches += 1;
+      launches += 3;
+      count = h->h_count[0];
+      std::swap(act, act_next);
+      ++round;
+    }
+    h->stats.rounds += round;
+  }
+  SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
+  unsigned long long hc[4] = {0, 0, 0, 0};
+  SSFM_CK(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+  h->stats.total_ms = ms;
+  h->stats.kernel_launches = launches;
+  h->stats.evals_executed = (long long)hc[0];
+  h->stats.evals_exact = (long long)hc[1];
+  h->have_results = true;
+  return SSFM_OK;
+}
+
+int ssfm_download(ssfm_handle h, SsfmPairResult* results, uint8_t* inlier_flags) {
+  if (!h) return fail(SSFM_ERR_INVALID, "NULL handle");
+  if (!h->have_results) return fail(SSFM_ERR_INVALID, "no results to download (call ssfm_run first)");
+  SSFM_CK(cudaSetDevice(h->device));
+  long long bytes = 0;
+  if (results && h->P > 0) {
+    SSFM_CK(cudaMemcpyAsync(results, h->results.p, sizeof(SsfmPairResult) * (size_t)h->P, cudaMemcpyDeviceToHost, h->stream));
+    bytes += (long long)sizeof(SsfmPairResult) * h->P;
+  }
+  if (inlier_flags && h->M > 0) {
+    SSFM_CK(cudaMemcpyAsync(inlier_flags, h->flags.p, (size_t)h->M, cudaMemcpyDeviceToHost, h->stream));
+    bytes += h->M;
+  }
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  h->stats.d2h_bytes = bytes;
+  if (results) {
+    long long useful = 0;
+    for (int p = 0; p < h->P; ++p) useful += results[p].evals;
+    h->stats.evals_useful = useful;
+  }
+  return SSFM_OK;
+}
+
+int ssfm_get_stats(ssfm_handle h, SsfmRunStats* s) {
+  if (!h || !s) return fail(SSFM_ERR_INVALID, "NULL argument");
+  *s = h->stats;
+  return SSFM_OK;
+}
+
+int ssfm_device_results(ssfm_handle h, void** dev_ptr, int32_t* num_pairs) {
+  if (!h || !dev_ptr) return fail(SSFM_ERR_INVALID, "NULL argument");
+  if (!h->have_results) return fail(SSFM_ERR_INVALID, "no results (call ssfm_run first)");
+  *dev_ptr = h->results.p;
+  if (num_pairs) *num_pairs = h->P;
+  return SSFM_OK;
+}
+
+int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions* opt, SsfmPairResult* results,
+                        uint8_t* inlier_flags) {
+  if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
+  if (int rc = check_options(opt)) return rc;
+  if (int rc = ssfm_upload(h, batch)) return rc;
+  if (int rc = ssfm_run(h, opt)) return rc;
+  if (int rc = ssfm_download(h, results, inlier_flags)) return rc;
+  if (batch->rays_on_device) { h->resident = false; h->d_rays = nullptr; }  // never keep a caller pointer
+  return SSFM_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// replay hooks
+// ----------------------------------------------------------------------------------------------
+int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t n, int32_t* idx) {
+  if (!idx || k <= 0 || k > 8 || n < k) return fail(SSFM_ERR_INVALID, "ssfm_sample: need 0 < k <= 8 and n >= k");
+  philox_sample<8>(seed, pair, iter, k, n, idx);
+  return SSFM_OK;
+}
+
+#define SSFM_TMP(T, name, count)                                  \
+  DevBuf<T> name;                                                 \
+  {                                                               \
+    cudaError_t e__ = name.ensure(std::max<size_t>((count), 1));  \
+    if (e__ != cudaSuccess) return fail(SSFM_ERR_OOM, "cudaMalloc failed in hook"); \
+  }
+struct TmpGuard {
+  std::vector<void*> ptrs;
+  ~TmpGuard() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+#define SSFM_KEEP(guard, buf) \
+  guard.ptrs.push_back(buf.p); \
+  buf.cap = 0;
+
+int ssfm_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t ns, int32_t solver,
+                       double* models, int32_t* num_models) {
+  if (!h || !rays || !samples || !models || !num_models || n < 3 || ns < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (solver < 0 || solver > 2) return fail(SSFM_ERR_INVALID, "unknown solver kind");
+  for (int i = 0; i < 3 * ns; ++i)
+    if (samples[i] < 0 || samples[i] >= n) return fail(SSFM_ERR_INVALID, "sample index out of range");
+  if (ns == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, d_rays, (size_t)n * 6) SSFM_KEEP(g, d_rays)
+  SSFM_TMP(int, d_s, (size_t)ns * 3) SSFM_KEEP(g, d_s)
+  SSFM_TMP(double, d_m, (size_t)ns * 24) SSFM_KEEP(g, d_m)
+  SSFM_TMP(int, d_nm, (size_t)ns) SSFM_KEEP(g, d_nm)
+  double* dr = (double*)g.ptrs[0]; int* ds = (int*)g.ptrs[1]; double* dm = (double*)g.ptrs[2]; int* dn = (int*)g.ptrs[3];
+  SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(ds, samples, sizeof(int) * 3 * ns, cudaMemcpyHostToDevice, h->stream));
+  const int blocks = (ns + 63) / 64;
+  if (solver == 0) k_solve_samples<0><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
+  else if (solver == 1) k_solve_samples<1><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
+  else k_solve_samples<2><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(models, dm, sizeof(double) * 24 * ns, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(num_models, dn, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_score(ssfm_handle h, const double* models6, int32_t M, const double* rays, int32_t n, double thr2, float* scores,
+               int32_t* counts, float* kernel_ms) {
+  if (!h || !models6 || !rays || !scores || !counts || M < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (M == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
+  SSFM_TMP(float4, b_u, (size_t)n) SSFM_KEEP(g, b_u)
+  SSFM_TMP(float4, b_v, (size_t)n) SSFM_KEEP(g, b_v)
+  SSFM_TMP(double, b_m, (size_t)M * 6) SSFM_KEEP(g, b_m)
+  double* dr = (double*)g.ptrs[0]; float4* du = (float4*)g.ptrs[1]; float4* dv = (float4*)g.ptrs[2]; double* dm = (double*)g.ptrs[3];
+  const int gx = (M + 4 * kScoreThreads - 1) / (4 * kScoreThreads);
+  const int max_chunks = std::max(1, (n + kTile - 1) / kTile);
+  int nchunks = std::min(max_chunks, std::max(1, (4 * h->num_sms * 2 + gx - 1) / gx));
+  int chunk = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
+  if (chunk <= 0) chunk = kTile;
+  nchunks = std::max(1, (n + chunk - 1) / chunk);
+  SSFM_TMP(float, b_ps, (size_t)nchunks * M) SSFM_KEEP(g, b_ps)
+  SSFM_TMP(int, b_pc, (size_t)nchunks * M) SSFM_KEEP(g, b_pc)
+  SSFM_TMP(float, b_s, (size_t)M) SSFM_KEEP(g, b_s)
+  SSFM_TMP(int, b_c, (size_t)M) SSFM_KEEP(g, b_c)
+  float* ps = (float*)g.ptrs[4]; int* pc = (int*)g.ptrs[5]; float* ds = (float*)g.ptrs[6]; int* dc = (int*)g.ptrs[7];
+  if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(dr, n, du, dv);
+  // warm-up launch (untimed), then the timed one
+  for (int rep = 0; rep < 2; ++rep) {
+    if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
+    dim3 grid(gx, nchunks);
+    k_score_models<<<grid, kScoreThreads, 0, h->stream>>>(du, dv, n, chunk, dm, M, (float)thr2, ps, pc);
+    k_reduce_parts<<<(M + 255) / 256, 256, 0, h->stream>>>(ps, pc, nchunks, M, ds, dc);
+    if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
+  }
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(scores, ds, sizeof(float) * M, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(counts, dc, sizeof(int) * M, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  if (kernel_ms) SSFM_CK(cudaEventElapsedTime(kernel_ms, h->ev[0], h->ev[1]));
+  return SSFM_OK;
+}
+
+int ssfm_score_exact(ssfm_handle h, const double* E9, int32_t M, const double* rays, int32_t n, double thr2, double* scores,
+                     int32_t* counts) {
+  if (!h || !E9 || !rays || !scores || !counts || M < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (M == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
+  SSFM_TMP(double, b_e, (size_t)M * 9) SSFM_KEEP(g, b_e)
+  SSFM_TMP(double, b_s, (size_t)M) SSFM_KEEP(g, b_s)
+  SSFM_TMP(int, b_c, (size_t)M) SSFM_KEEP(g, b_c)
+  double* dr = (double*)g.ptrs[0]; double* de = (double*)g.ptrs[1]; double* ds = (double*)g.ptrs[2]; int* dc = (int*)g.ptrs[3];
+  if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(de, E9, sizeof(double) * 9 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  k_score_exact<<<(M + 3) / 4, 128, 0, h->stream>>>(de, M, dr, n, thr2, ds, dc);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(scores, ds, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(counts, dc, sizeof(int) * M, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx, const int32_t* sample_offsets,
+                       int32_t nprob, int32_t inward, double* E9) {
+  if (!h || !rays || !sample_idx || !sample_offsets || !E9 || nprob < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (nprob == 0) return SSFM_OK;
+  const int total = sample_offsets[nprob];
+  for (int i = 0; i < total; ++i)
+    if (sample_idx[i] < 0 || sample_idx[i] >= n) return fail(SSFM_ERR_INVALID, "sample index out of range");
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
+  SSFM_TMP(int, b_i, (size_t)total) SSFM_KEEP(g, b_i)
+  SSFM_TMP(int, b_o, (size_t)nprob + 1) SSFM_KEEP(g, b_o)
+  SSFM_TMP(double, b_e, (size_t)nprob * 9) SSFM_KEEP(g, b_e)
+  double* dr = (double*)g.ptrs[0]; int* di = (int*)g.ptrs[1]; int* dof = (int*)g.ptrs[2]; double* de = (double*)g.ptrs[3];
+  if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  if (total > 0) SSFM_CK(cudaMemcpyAsync(di, sample_idx, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dof, sample_offsets, sizeof(int) * ((size_t)nprob + 1), cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(de, E9, sizeof(double) * 9 * (size_t)nprob, cudaMemcpyHostToDevice, h->stream));
+  k_least_squares<<<(nprob + 3) / 4, 128, 0, h->stream>>>(dr, di, dof, nprob, inward, de);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(E9, de, sizeof(double) * 9 * (size_t)nprob, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward, double* r3, double* t3) {
+  if (!h || !E9 || !r3 || !t3 || num < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (num == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_e, (size_t)num * 9) SSFM_KEEP(g, b_e)
+  SSFM_TMP(double, b_r, (size_t)num * 3) SSFM_KEEP(g, b_r)
+  SSFM_TMP(double, b_t, (size_t)num * 3) SSFM_KEEP(g, b_t)
+  double* de = (double*)g.ptrs[0]; double* dr = (double*)g.ptrs[1]; double* dt = (double*)g.ptrs[2];
+  SSFM_CK(cudaMemcpyAsync(de, E9, sizeof(double) * 9 * (size_t)num, cudaMemcpyHostToDevice, h->stream));
+  k_decompose<<<(num + 127) / 128, 128, 0, h->stream>>>(de, num, inward, dr, dt);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(r3, dr, sizeof(double) * 3 * (size_t)num, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(t3, dt, sizeof(double) * 3 * (size_t)num, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t* sizes, const int32_t* targets, int32_t* out) {
+  if (!h || !sizes || !targets || !out || ncalls < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (ncalls == 0) return SSFM_OK;
+  int maxsz = 1, total = 0;
+  for (int i = 0; i < ncalls; ++i) {
+    if (sizes[i] < 0 || targets[i] < 0 || targets[i] > sizes[i]) return fail(SSFM_ERR_INVALID, "need 0 <= target <= size");
+    maxsz = std::max(maxsz, sizes[i]);
+    total += targets[i];
+  }
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(int, b_sz, (size_t)ncalls) SSFM_KEEP(g, b_sz)
+  SSFM_TMP(int, b_tg, (size_t)ncalls) SSFM_KEEP(g, b_tg)
+  SSFM_TMP(uint32_t, b_mt, 625) SSFM_KEEP(g, b_mt)
+  SSFM_TMP(int, b_w, (size_t)maxsz) SSFM_KEEP(g, b_w)
+  SSFM_TMP(int, b_o, (size_t)total) SSFM_KEEP(g, b_o)
+  int* dsz = (int*)g.ptrs[0]; int* dtg = (int*)g.ptrs[1]; uint32_t* dmt = (uint32_t*)g.ptrs[2]; int* dw = (int*)g.ptrs[3]; int* dout = (int*)g.ptrs[4];
+  SSFM_CK(cudaMemcpyAsync(dsz, sizes, sizeof(int) * ncalls, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dtg, targets, sizeof(int) * ncalls, cudaMemcpyHostToDevice, h->stream));
+  k_lo_shuffle<<<1, 32, 0, h->stream>>>(seed, ncalls, dsz, dtg, dmt, dw, dout);
+  SSFM_CK(cudaGetLastError());
+  if (total > 0) SSFM_CK(cudaMemcpyAsync(out, dout, sizeof(int) * total, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_measure_fp32_peak(ssfm_handle h, double* tflops) {
+  if (!h || !tflops) return fail(SSFM_ERR_INVALID, "bad argument");
+  SSFM_CK(cudaSetDevice(h->device));
+  const int threads = 256, blocks = h->num_sms * 8, iters = 4096;
+  TmpGuard g;
+  SSFM_TMP(float, b_o, (size_t)threads * blocks) SSFM_KEEP(g, b_o)
+  float* d = (float*)g.ptrs[0];
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
+    k_fma_peak<<<blocks, threads, 0, h->stream>>>(d, iters, 1.000001f, 1e-7f);
+    SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
+    SSFM_CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    SSFM_CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    const double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  SSFM_CK(cudaGetLastError());
+  *tflops = best;
+  return SSFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// hostshim.cpp -- TEST-ONLY host build of the engine's __host__ __device__ arithmetic
+// (spherical-sfm_b200/csrc/ssfm_math.cuh, ssfm_chain.cuh) so that `pytest -m "not gpu"` can
+// check the product's solver / refit / chain logic against the oracle on a machine without a GPU.
+// It is NOT part of libssfm_b200.so, is never loaded by the package, and is not a CPU fallback:
+// the product entry points fail with SSFM_ERR_NO_DEVICE when CUDA is unavailable.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../spherical-sfm_b200/csrc/ssfm_chain.cuh"
+
+using namespace ssfm;
+
+namespace {
+// plain-float emulation of the FP32 scoring kernel's per-iteration output
+float score_iteration_f32(const double* models4x6, const double* rays, int n, float thr) {
+  float best = INFINITY;
+  for (int m = 0; m < 4; ++m) {
+    float p[6];
+    for (int i = 0; i < 6; ++i) p[i] = (float)models4x6[6 * m + i];
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const float u0 = (float)rays[6 * i], u1 = (float)rays[6 * i + 1], u2 = (float)rays[6 * i + 2];
+      const float v0 = (float)rays[6 * i + 3], v1 = (float)rays[6 * i + 4], v2 = (float)rays[6 * i + 5];
+      const float Eu0 = p[0] * u0 + p[1] * u1 + p[2] * u2;
+      const float Eu1 = p[1] * u0 - p[0] * u1 + p[3] * u2;
+      const float Eu2 = p[4] * u0 + p[5] * u1;
+      const float Etv0 = p[0] * v0 + p[1] * v1 + p[4] * v2;
+      const float Etv1 = p[1] * v0 - p[0] * v1 + p[5] * v2;
+      const float d = v0 * Eu0 + v1 * Eu1 + v2 * Eu2;
+      const float e = d * d / (Eu0 * Eu0 + Eu1 * Eu1 + Etv0 * Etv0 + Etv1 * Etv1);
+      acc += fminf(e, thr);
+    }
+    if (acc < best) best = acc;
+  }
+  return best;
+}
+}  // namespace
+
+extern "C" {
+
+struct HsParams {
+  uint32_t min_iters, max_iters;
+  double success_probability, thr2;
+  uint32_t seed;
+  int32_t num_lo_steps;
+  double thr_mult;
+  int32_t num_lsq_iters, min_sample_mult, non_min_mult;
+  uint32_t lo_start;
+  int32_t final_lsq, solver, driver, inward, fixed_budget;
+  double fixed_prob;
+  float cand_margin;
+  int32_t first_round, round_cap;
+};
+
+struct HsResult {
+  double E[9], r[3], t[3];
+  double best_model_score, inlier_ratio;
+  uint32_t num_iterations;
+  int32_t best_num_inliers, num_lo, status;
+  int64_t evals_exact;
+  int32_t rounds, candidates;
+};
+
+void hs_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx) {
+  philox_sample<8>(seed, pair, iter, k, n, idx);
+}
+
+int hs_solve(const double* rays, const int* sample, int kind, double* models) {
+  double m[4][6];
+  const double* c0 = rays + 6 * (size_t)sample[0];
+  const double* c1 = rays + 6 * (size_t)sample[1];
+  const double* c2 = rays + 6 * (size_t)sample[2];
+  int nm;
+  if (kind == 0) nm = solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+  else if (kind == 1) nm = solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+  else nm = solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+  std::memcpy(models, m, sizeof(m));
+  return nm;
+}
+
+void hs_quartic(const double* c, double* re, double* im) {
+  Cplx r[4];
+  quartic_roots(c[0], c[1], c[2], c[3], c[4], r);
+  for (int i = 0; i < 4; ++i) { re[i] = r[i].re; im[i] = r[i].im; }
+}
+
+void hs_decompose(const double* E, int inward, double* r, double* t) { decompose_spherical_E(E, inward != 0, r, t); }
+
+void hs_sampson(const double* E, const double* rays, int n, double* out) {
+  for (int i = 0; i < n; ++i) out[i] = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
+}
+
+void hs_least_squares(const double* rays, const int* sample, int n, int inward, double* E) {
+  SerialCtx cx;
+  least_squares(cx, rays, sample, n, inward != 0, E);
+}
+
+void hs_lo_shuffle(uint32_t seed, int ncalls, const int* sizes, const int* targets, int* out) {
+  std::vector<uint32_t> mt(625);
+  mt19937_seed(mt.data(), seed);
+  SerialCtx cx;
+  int o = 0;
+  for (int c = 0; c < ncalls; ++c) {
+    std::vector<int> v(sizes[c]);
+    for (int i = 0; i < sizes[c]; ++i) v[i] = i;
+    shuffle_and_resize(cx, mt.data(), v.data(), sizes[c]);
+    for (int i = 0; i < targets[c]; ++i) out[o++] = v[i];
+  }
+}
+
+uint32_t hs_required_iterations(double w, double eta, int k, uint32_t lo, uint32_t hi) {
+  return required_iterations(w, eta, k, lo, hi);
+}
+
+// The engine's round structure, emulated serially for one pair.
+void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pair_id, HsResult* out,
+                      unsigned char* flags) {
+  Params P;
+  P.min_iters = hp->min_iters; P.max_iters = hp->max_iters;
+  P.eta = 1.0 - hp->success_probability; P.thr2 = hp->thr2; P.seed = hp->seed;
+  P.num_lo_steps = hp->num_lo_steps; P.thr_mult = hp->thr_mult; P.num_lsq_iters = hp->num_lsq_iters;
+  P.min_sample_mult = hp->min_sample_mult; P.non_min_mult = hp->non_min_mult; P.lo_start = hp->lo_start;
+  P.final_lsq = hp->final_lsq; P.solver = hp->solver; P.driver = hp->driver; P.inward = hp->inward;
+  P.fixed_budget = hp->fixed_budget; P.fixed_prob = hp->fixed_prob; P.first_pair_id = 0;
+  P.cand_margin = hp->cand_margin;
+  PairState st;
+  init_state(P, n, st);
+  std::vector<int> la(n + 16), lb(n + 16);
+  std::vector<uint32_t> mt(625);
+  mt19937_seed(mt.data(), P.seed);
+  Scratch sc{la.data(), lb.data(), mt.data()};
+  PairView pv{rays, n};
+  SerialCtx cx;
+  int rounds = 0, candidates = 0;
+  std::vector<double> models;
+  std::vector<float> s32;
+  while (!st.done) {
+    const uint32_t want = iterations_wanted(P, st);
+    if (want == 0) { st.done = 1; break; }
+    const int cap = rounds == 0 ? hp->first_round : hp->round_cap;
+    const int na = (int)(want < (uint32_t)cap ? want : (uint32_t)cap);
+    models.assign((size_t)na * 24, 0.0);
+    s32.assign(na, 0.f);
+    for (int j = 0; j < na; ++j) {
+      int idx[3];
+      philox_sample<3>(P.seed, pair_id, st.it + j, 3, n, idx);
+      double m[4][6];
+      const double* c0 = rays + 6 * (size_t)idx[0];
+      const double* c1 = rays + 6 * (size_t)idx[1];
+      const double* c2 = rays + 6 * (size_t)idx[2];
+      if (P.solver == 0) solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+      else if (P.solver == 1) solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+      else solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+      for (int k = 0; k < 24; ++k) models[(size_t)k * na + j] = (&m[0][0])[k];
+      s32[j] = score_iteration_f32(&m[0][0], rays, n, (float)P.thr2);
+    }
+    const long long before = st.evals_exact;
+    process_round(cx, P, pv, sc, st, models.data(), na, s32.data(), na);
+    candidates += (int)((st.evals_exact - before) / (n > 0 ? n : 1));
+    ++rounds;
+  }
+  out->status = finalize_pair(cx, P, pv, sc, st, out->r, out->t, flags);
+  std::memcpy(out->E, st.E_best, sizeof(st.E_best));
+  out->best_model_score = st.best_model_score;
+  out->inlier_ratio = st.inlier_ratio;
+  out->num_iterations = st.it;
+  out->best_num_inliers = st.best_num_inliers;
+  out->num_lo = st.num_lo;
+  out->evals_exact = st.evals_exact;
+  out->rounds = rounds;
+  out->candidates = candidates;
+}
+
+}  // extern "C"
