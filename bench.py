@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched spherical relative-pose engine.
+
+Metric (BASELINE.json): correspondence-hypothesis evaluations / second (and image pairs / second),
+at 1/2/4/8 B200, beside the host RansacLib path.
+
+Workload at N=1 (config.workload = "C3"): BASELINE.json configs[2], the largest configuration that
+exercises the whole path -- loop-closure exhaustive, 500 frames = 124 750 image pairs, 1500
+correspondences per pair, 70 % outliers, LO-RANSAC with the pipeline's options
+(examples/spherical_sfm_tools.cpp:314-318), action-matrix 3-point solver.  Synthetic data
+(evaluation/problem_generator conventions + injected outliers).  One "step" = one full pass of the hot
+path over that batch.  With --gpus N every rank processes its own C3-sized shard (weak scaling); the
+per-pair result tables are all-gathered with NCCL.
+
+  value : useful evaluations (num_iterations x 4 models x N per pair, i.e. what the reference loop
+          computes) / device time, inputs resident in HBM (ssfm_run only)
+  e2e   : the same through ssfm_estimate_pairs with pinned HOST buffers: H2D of the RayPair memory,
+          all kernels, D2H of the result table and inlier flags inside the timed region
+  --impl reference : the CPU path (reference RansacLib driver loops from oracle/_ref when present,
+          else the restated oracle) on all host threads, on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+THR2 = (2.0 / 600.0) ** 2
+FLOP_PER_EVAL = 42.0  # generic 3x3 E Sampson evaluation
+C3_PAIRS, C3_CORR, C3_OUTLIERS = 124750, 1500, 0.7
+
+
+def make_batch_torch(P, N, outlier_frac, seed, device, max_angle_deg=20.0, noise=1.0 / 600.0, chunk=8192):
+    """Synthetic spherical two-view problems on `device` (evaluation/problem_generator conventions:
+    t = R e3 - e3, u = (N(0,1), N(0,1), 1), depth U[4,8], noise on both images' xy); an exact number of
+    outliers per pair gets a fresh random v.xy; points that fall behind the second camera are turned
+    into outliers instead of redrawing the whole problem.  Returns (rays (P*N, 6) float64 device tensor,
+    offsets int64 numpy, R_gt (P,3,3))."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    rays = torch.empty((P * N, 6), dtype=torch.float64, device=device)
+    Rall = torch.empty((P, 3, 3), dtype=torch.float64, device=device)
+    n_out = int(round(outlier_frac * N))
+    for p0 in range(0, P, chunk):
+        p1 = min(P, p0 + chunk)
+        n = p1 - p0
+        axis = torch.randn((n, 3), generator=g, device=device, dtype=torch.float64)
+        axis = axis / axis.norm(dim=1, keepdim=True)
+        ang = (torch.rand((n,), generator=g, device=device, dtype=torch.float64) * 2 - 1) * np.deg2rad(max_angle_deg)
+        K = torch.zeros((n, 3, 3), dtype=torch.float64, device=device)
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+        K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+        eye = torch.eye(3, dtype=torch.float64, device=device).expand(n, 3, 3)
+        R = eye + torch.sin(ang)[:, None, None] * K + (1 - torch.cos(ang))[:, None, None] * (K @ K)
+        t = R[:, :, 2].clone()
+        t[:, 2] -= 1.0
+        u = torch.ones((n, N, 3), dtype=torch.float64, device=device)
+        u[:, :, :2] = torch.randn((n, N, 2), generator=g, device=device, dtype=torch.float64)
+        depth = torch.rand((n, N, 1), generator=g, device=device, dtype=torch.float64) * 4 + 4
+        X = u * depth
+        P2 = X @ R.transpose(1, 2) + t[:, None, :]
+        bad = P2[:, :, 2] <= 0.1
+        v = torch.ones((n, N, 3), dtype=torch.float64, device=device)
+        v[:, :, :2] = P2[:, :, :2] / P2[:, :, 2:3].clamp_min(0.1)
+        u[:, :, :2] += noise * torch.randn((n, N, 2), generator=g, device=device, dtype=torch.float64)
+        v[:, :, :2] += noise * torch.randn((n, N, 2), generator=g, device=device, dtype=torch.float64)
+        rank = torch.rand((n, N), generator=g, device=device).argsort(dim=1).argsort(dim=1)
+        out = (rank < n_out) | bad
+        rnd = torch.randn((n, N, 2), generator=g, device=device, dtype=torch.float64)
+        v[:, :, :2] = torch.where(out[:, :, None], rnd, v[:, :, :2])
+        rays[p0 * N:p1 * N, :3] = u.reshape(-1, 3)
+        rays[p0 * N:p1 * N, 3:] = v.reshape(-1, 3)
+        Rall[p0:p1] = R
+    offsets = np.arange(P + 1, dtype=np.int64) * N
+    return rays, offsets, Rall
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        # under load = the upper half of the samples
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(pairs_rays, N, seconds_target, threads=0):
+    """Times the CPU path on a bounded sample.  Only this function (and the tests / smoke) touches oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    impl = O.load_ref() if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libssfm_ref.so")) else None
+    uses_ref_driver = impl is not None
+    if impl is None:
+        impl = O.load()
+    opt = O.pipeline_options(THR2)
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    npairs_avail = len(pairs_rays) // N
+    probe = min(npairs_avail, max(8, cores))
+    offs = np.arange(probe + 1, dtype=np.int64) * N
+    res, secs = impl.estimate_batch(pairs_rays[:probe * N], offs, opt, 0, cores)
+    rate = probe / max(secs, 1e-6)
+    n = int(min(npairs_avail, max(probe, rate * seconds_target)))
+    offs = np.arange(n + 1, dtype=np.int64) * N
+    res, secs = impl.estimate_batch(pairs_rays[:n * N], offs, opt, 0, cores)
+    evals = sum(int(r.num_iterations) * 4 * N for r in res)
+    total_evals = sum(int(r.evals) for r in res)
+    return {
+        "value": evals / secs, "unit": "evals/s", "cores": cores, "kind": "port",
+        "sample": "%d C3 pairs (%d corr, 70%% outliers, LO-MSAC pipeline options) in %.1f s; float64 C++ restatement of the "
+                  "spherical estimator%s; all EvaluateModelOnPoint calls incl. LO: %.3e/s; %.1f pairs/s" % (
+                      n, N, secs, " driven by the reference's own RansacLib headers (oracle/_ref)" if uses_ref_driver
+                      else " and of the RansacLib loop (oracle/)", total_evals / secs, n / secs),
+        "pairs_per_s": n / secs, "seconds": secs, "pairs": n,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=C3_PAIRS)
+    ap.add_argument("--corr", type=int, default=C3_CORR)
+    ap.add_argument("--outliers", type=float, default=C3_OUTLIERS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    P, N = args.pairs, args.corr
+    config = {"workload": "C3", "pairs_per_gpu": P, "corr_per_pair": N, "outlier_frac": args.outliers,
+              "driver": "LO-MSAC (pipeline options: lo_steps 0, lsq_iters 0, final_least_squares)",
+              "solver": "action_matrix", "l2": "inputs_larger_than_l2", "parallelism": "pairs sharded x%d" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import spherical_sfm_b200 as S
+        npairs = 4096
+        import torch
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        rays_t, offsets, _ = make_batch_torch(npairs, N, args.outliers, 1234, dev)
+        rays = rays_t.cpu().numpy()
+        best = None
+        for it in range(args.warmup + args.steps):
+            r = cpu_leg(rays, N, args.cpu_seconds / max(1, args.steps))
+            if it >= args.warmup and (best is None or r["value"] > best["value"]):
+                best = r
+        line = {"metric": "corr_hypothesis_evals_per_sec", "value": best["value"], "unit": "evals/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["seconds"] * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "impl": "reference", "cpu_baseline": best, "pairs_per_sec": best["pairs_per_s"],
+                "e2e": {"value": best["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import spherical_sfm_b200 as S
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # ---- synthetic inputs: generated on the GPU, then moved to pinned host memory ----
+    rays_dev, offsets, _ = make_batch_torch(P, N, args.outliers, 1234 + rank, "cuda")
+    rays_host = torch.empty(rays_dev.shape, dtype=torch.float64, pin_memory=True)
+    rays_host.copy_(rays_dev)
+    del rays_dev
+    torch.cuda.empty_cache()
+    rays_np = rays_host.numpy()
+
+    eng = S.Engine(local_rank)
+    opt = S.pipeline_options(THR2, first_pair_id=rank * P)
+    fp32_peak = eng.measure_fp32_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    class _Dev:  # wraps the engine's device result table for torch (zero copy)
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    def gather_tables():
+        if dist is None:
+            return
+        ptr, n = eng.device_results()
+        t = torch.as_tensor(_Dev(ptr, n * S.RESULT_DTYPE.itemsize), device="cuda")
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+
+    # ---- resident-in-HBM throughput (value) ----
+    eng.upload(rays_np, offsets)
+    for _ in range(args.warmup):
+        eng.run(opt)
+        gather_tables()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, wall0 = 0.0, time.perf_counter()
+    agg = {"solve_ms": 0.0, "score_ms": 0.0, "chain_ms": 0.0, "launches": 0, "rounds": 0, "score_launches": 0,
+           "evals_executed": 0, "evals_exact": 0}
+    for _ in range(args.steps):
+        eng.run(opt)
+        gather_tables()
+        st = eng.stats()
+        dev_ms += st.total_ms
+        for k, v in (("solve_ms", st.solve_ms), ("score_ms", st.score_ms), ("chain_ms", st.chain_ms),
+                     ("launches", st.kernel_launches), ("rounds", st.rounds), ("score_launches", st.score_launches),
+                     ("evals_executed", st.evals_executed), ("evals_exact", st.evals_exact)):
+            agg[k] += v
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    res, _ = eng.download(want_flags=False)
+    useful = int(res["evals"].sum())
+    step_ms = wall_s * 1e3 / args.steps  # wall clock around device-synchronised steps (includes round syncs)
+    dev_step_ms = dev_ms / args.steps
+
+    # ---- end to end through the C ABI with host buffers (e2e) ----
+    eng.estimate_pairs(rays_np, offsets, opt)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e, flags = eng.estimate_pairs(rays_np, offsets, opt)
+        gather_tables()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    st = eng.stats()
+
+    t_step = torch.tensor([step_ms, e2e_s * 1e3, float(useful), dev_step_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t_step.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t_step.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        step_ms, e2e_ms, dev_step_ms = float(tmax[0]), float(tmax[1]), float(tmax[3])
+        useful_total = float(tsum[2])
+    else:
+        e2e_ms, useful_total = e2e_s * 1e3, float(useful)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = useful_total / (step_ms * 1e-3)
+    score_ms_per_launch = agg["score_ms"] / max(1, agg["score_launches"])
+    evals_per_launch = agg["evals_executed"] / max(1, agg["score_launches"])
+    achieved_tflops = evals_per_launch * FLOP_PER_EVAL / (score_ms_per_launch * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "corr_hypothesis_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 scoring + f64 solver/certification", "data": "synthetic", "config": config,
+        "pairs_per_sec": world * P / (step_ms * 1e-3),
+        "device_ms_per_step": dev_step_ms,
+        "stage_ms_per_step": {"solve": agg["solve_ms"] / args.steps, "score": agg["score_ms"] / args.steps,
+                              "chain": agg["chain_ms"] / args.steps, "rounds": agg["rounds"] / args.steps},
+        "evals": {"useful_per_step": useful_total / world, "executed_fp32_per_step": agg["evals_executed"] / args.steps,
+                  "exact_fp64_per_step": agg["evals_exact"] / args.steps},
+        "e2e": {"value": useful_total / (e2e_ms * 1e-3), "unit": "evals/s", "pairs_per_sec": world * P / (e2e_ms * 1e-3),
+                "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes)},
+        "gpu_launches": int(agg["launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "fp32", "kernel": "k_score_rounds", "achieved": achieved_tflops, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak, "traffic": traffic,
+                     "peak_source": "FFMA-chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure; "
+                                    "theoretical 148 SM x 128 x 2 x 1.965 GHz = 74.5)",
+                     "flop_per_eval": FLOP_PER_EVAL, "evals_per_launch": evals_per_launch,
+                     "ms_per_launch": score_ms_per_launch,
+                     "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3)},
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_leg(rays_np[:4096 * N], N, args.cpu_seconds)
+    print(json.dumps(line))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,11 @@ int ssfm_score_exact(ssfm_handle h, const double* E9, int32_t num_models, const 
 int ssfm_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
                        const int32_t* sample_offsets, int32_t num_problems, int32_t inward, double* E9);
 
+/* SphericalEstimator::NonMinimalSolver (src/spherical_estimator.cpp:86-108) for `num_problems` index
+ * sets over one pair.  E9: out, 9 doubles each; ok: out, 1 if a model was produced. */
+int ssfm_non_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
+                           const int32_t* sample_offsets, int32_t num_problems, double* E9, int32_t* ok);
+
 /* decompose_spherical_essential_matrix (src/spherical_utils.cpp:16-66), batched. */
 int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward, double* r3, double* t3);
 

@@ -1,0 +1,295 @@
+// ssfm_ransaclib.hpp -- header-only C++ adapters over the C ABI (ssfm.h) that keep RansacLib's
+// estimator concept and driver signature, so the reference pipeline can call the B200 engine as a
+// drop-in for this path:
+//
+//   reference type                                            replacement here
+//   sphericalsfm::SphericalEstimator                          ssfm_b200::GpuSphericalEstimator<Matrix3>
+//     (include/sphericalsfm/spherical_estimator.h:8-33)
+//   ransac_lib::LocallyOptimizedMSAC<M,MV,Solver>::EstimateModel   ssfm_b200::LocallyOptimizedMSAC<M,MV,Solver>::EstimateModel
+//     (include/RansacLib/ransac.h:128-129)                           (same signature; one GPU call per pair)
+//   ransac_lib::VanillaMSAC (evaluation/vanilla_ransac.h:23)   ssfm_b200::VanillaMSAC
+//   the `#pragma omp parallel for` over pairs                  ssfm_b200::EstimatePairs (ONE call for all pairs)
+//     (examples/spherical_sfm_tools.cpp:332-420)
+//
+// Matrix3 is any 3x3 type with `double& operator()(int,int)` (Eigen::Matrix3d works unchanged);
+// RayPairList is any contiguous container of {Vector3d first, second} (48 bytes per element), i.e.
+// sphericalsfm::RayPairList (include/sphericalsfm/ray.h:8-10).  Options / statistics types are duck
+// typed on RansacLib's field names, so ransac_lib::LORansacOptions / RansacStatistics can be passed
+// as they are; POD mirrors are provided for builds without RansacLib.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ssfm.h"
+
+namespace ssfm_b200 {
+
+struct Mat3d {  // stand-in for Eigen::Matrix3d where Eigen is absent (row-major)
+  double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double& operator()(int r, int c) { return m[3 * r + c]; }
+  double operator()(int r, int c) const { return m[3 * r + c]; }
+};
+
+struct RansacOptions {  // include/RansacLib/ransac.h:47-60
+  uint32_t min_num_iterations_ = 100u;
+  uint32_t max_num_iterations_ = 10000u;
+  double success_probability_ = 0.9999;
+  double squared_inlier_threshold_ = 1.0;
+  unsigned int random_seed_ = 0u;
+};
+struct LORansacOptions : public RansacOptions {  // ransac.h:64-92
+  int num_lo_steps_ = 10;
+  double threshold_multiplier_ = std::sqrt(2.0);
+  int num_lsq_iterations_ = 4;
+  int min_sample_multiplicator_ = 7;
+  int non_min_sample_multiplier_ = 3;
+  uint32_t lo_starting_iterations_ = 50u;
+  bool final_least_squares_ = false;
+};
+struct RansacStatistics {  // ransac.h:94-101
+  uint32_t num_iterations = 0;
+  int best_num_inliers = 0;
+  double best_model_score = std::numeric_limits<double>::max();
+  double inlier_ratio = 0.0;
+  std::vector<int> inlier_indices;
+  int number_lo_iterations = 0;
+};
+
+class Error : public std::runtime_error {
+ public:
+  Error(int code, const char* what) : std::runtime_error(std::string("ssfm: ") + what), code_(code) {}
+  int code() const { return code_; }
+
+ private:
+  int code_;
+};
+inline void check(int rc) {
+  if (rc != SSFM_OK) throw Error(rc, ssfm_last_error());
+}
+
+// RAII handle: one GPU, one stream.
+class Engine {
+ public:
+  explicit Engine(int device = 0) { check(ssfm_create(device, &h_)); }
+  ~Engine() { ssfm_destroy(h_); }
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+  ssfm_handle get() const { return h_; }
+
+ private:
+  ssfm_handle h_ = nullptr;
+};
+
+namespace detail {
+template <class Matrix3>
+inline void to_rowmajor(const Matrix3& E, double* out) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out[3 * r + c] = E(r, c);
+}
+template <class Matrix3>
+inline void from_rowmajor(const double* in, Matrix3* E) {
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) (*E)(r, c) = in[3 * r + c];
+}
+template <class Options>
+inline auto lo_fields(const Options& o, SsfmOptions* s, int) -> decltype(o.num_lo_steps_, void()) {
+  s->num_lo_steps = o.num_lo_steps_;
+  s->threshold_multiplier = o.threshold_multiplier_;
+  s->num_lsq_iterations = o.num_lsq_iterations_;
+  s->min_sample_multiplicator = o.min_sample_multiplicator_;
+  s->non_min_sample_multiplier = o.non_min_sample_multiplier_;
+  s->lo_starting_iterations = o.lo_starting_iterations_;
+  s->final_least_squares = o.final_least_squares_ ? 1 : 0;
+}
+template <class Options>
+inline void lo_fields(const Options&, SsfmOptions*, long) {}
+template <class Options>
+inline SsfmOptions to_c_options(const Options& o) {
+  SsfmOptions s;
+  ssfm_default_options(&s);
+  s.min_num_iterations = o.min_num_iterations_;
+  s.max_num_iterations = o.max_num_iterations_;
+  s.success_probability = o.success_probability_;
+  s.squared_inlier_threshold = o.squared_inlier_threshold_;
+  s.random_seed = o.random_seed_;
+  lo_fields(o, &s, 0);
+  return s;
+}
+}  // namespace detail
+
+// The RansacLib estimator concept (include/sphericalsfm/estimator.h:6-29) on the GPU engine.  Each
+// member forwards to the engine with a batch of one, so any RansacLib-style driver still works;
+// the intended fast path is the batched driver below.
+template <class Matrix3 = Mat3d>
+class GpuSphericalEstimator {
+ public:
+  // rays: n x 6 doubles = RayPairList memory; held by reference like the original (spherical_estimator.h:11,15).
+  GpuSphericalEstimator(const Engine& eng, const double* rays, int n, bool use_poly_solver, bool inward,
+                        uint32_t pair_id = 0)
+      : h_(eng.get()), rays_(rays), n_(n), poly_(use_poly_solver), inward_(inward), pair_id_(pair_id) {}
+  template <class RayPairList>
+  GpuSphericalEstimator(const Engine& eng, const RayPairList& correspondences, bool use_poly_solver, bool inward,
+                        uint32_t pair_id = 0)
+      : GpuSphericalEstimator(eng, correspondences.empty() ? nullptr : reinterpret_cast<const double*>(&correspondences[0]),
+                              (int)correspondences.size(), use_poly_solver, inward, pair_id) {
+    static_assert(sizeof(correspondences[0]) == 48, "RayPair must be two packed 3-vectors of double");
+  }
+  inline int min_sample_size() const { return 3; }
+  inline int non_minimal_sample_size() const { return 4; }
+  inline int num_data() const { return n_; }
+  const double* rays() const { return rays_; }
+  bool inward() const { return inward_; }
+  bool use_poly_solver() const { return poly_; }
+  uint32_t pair_id() const { return pair_id_; }
+  ssfm_handle handle() const { return h_; }
+
+  int MinimalSolver(const std::vector<int>& sample, std::vector<Matrix3>* Es) const {  // spherical_estimator.cpp:80-84
+    Es->clear();
+    if (sample.size() != 3) return 0;
+    double models[24];
+    int nm = 0;
+    check(ssfm_minimal_solve(h_, rays_, n_, sample.data(), 1, poly_ ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX,
+                             models, &nm));
+    for (int k = 0; k < nm; ++k) {
+      const double* p = models + 6 * k;
+      const double E[9] = {p[0], p[1], p[2], p[1], -p[0], p[3], p[4], p[5], 0.0};
+      Matrix3 M;
+      detail::from_rowmajor(E, &M);
+      Es->push_back(M);
+    }
+    return nm;
+  }
+  int NonMinimalSolver(const std::vector<int>& sample, Matrix3* E) const {  // spherical_estimator.cpp:86-108
+    const int offs[2] = {0, (int)sample.size()};
+    double out[9];
+    int ok = 0;
+    check(ssfm_non_minimal_solve(h_, rays_, n_, sample.data(), offs, 1, out, &ok));
+    if (ok) detail::from_rowmajor(out, E);
+    return ok;
+  }
+  double EvaluateModelOnPoint(const Matrix3& E, int i) const {  // spherical_estimator.cpp:67-78
+    double e9[9], score = 0.0;
+    int cnt = 0;
+    detail::to_rowmajor(E, e9);
+    check(ssfm_score_exact(h_, e9, 1, rays_ + 6 * (size_t)i, 1, std::numeric_limits<double>::max(), &score, &cnt));
+    return score;  // min(err, DBL_MAX) summed over one point
+  }
+  void LeastSquares(const std::vector<int>& sample, Matrix3* E) const {  // spherical_estimator.cpp:110-157
+    const int offs[2] = {0, (int)sample.size()};
+    double e9[9];
+    detail::to_rowmajor(*E, e9);
+    check(ssfm_least_squares(h_, rays_, n_, sample.data(), offs, 1, inward_ ? 1 : 0, e9));
+    detail::from_rowmajor(e9, E);
+  }
+  template <class Vector3>
+  void Decompose(const Matrix3& E, const std::vector<int>& /*inliers*/, Matrix3* R, Vector3* t) const {  // :159-164
+    double e9[9], r[3], tt[3];
+    detail::to_rowmajor(E, e9);
+    check(ssfm_decompose(h_, e9, 1, inward_ ? 1 : 0, r, tt));
+    const double th = std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    double Rm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (th >= 1e-10) {  // so3exp, src/so3.cpp:16-23
+      const double k[3] = {r[0] / th, r[1] / th, r[2] / th};
+      const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double kk = 0;
+          for (int l = 0; l < 3; ++l) kk += K[3 * i + l] * K[3 * l + j];
+          Rm[3 * i + j] += std::sin(th) * K[3 * i + j] + (1 - std::cos(th)) * kk;
+        }
+    }
+    detail::from_rowmajor(Rm, R);
+    for (int i = 0; i < 3; ++i) (*t)[i] = tt[i];
+  }
+
+ private:
+  ssfm_handle h_;
+  const double* rays_;
+  int n_;
+  bool poly_, inward_;
+  uint32_t pair_id_;
+};
+
+namespace detail {
+template <class Options, class Solver, class Model, class Statistics>
+int estimate_one(int driver, const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) {
+  SsfmOptions o = to_c_options(options);
+  o.driver = driver;
+  o.solver = solver.use_poly_solver() ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX;
+  o.inward = solver.inward() ? 1 : 0;
+  o.first_pair_id = solver.pair_id();
+  const int n = solver.num_data();
+  const int64_t offsets[2] = {0, n};
+  SsfmBatch b;
+  b.num_pairs = 1;
+  b.offsets = offsets;
+  b.rays = solver.rays();
+  b.rays_on_device = 0;
+  SsfmPairResult r;
+  std::vector<uint8_t> flags(n > 0 ? n : 1);
+  check(ssfm_estimate_pairs(solver.handle(), &b, &o, &r, flags.data()));
+  from_rowmajor(r.E, best_model);
+  statistics->num_iterations = r.num_iterations;
+  statistics->best_num_inliers = r.best_num_inliers;
+  statistics->best_model_score = r.best_model_score;
+  statistics->inlier_ratio = r.inlier_ratio;
+  statistics->number_lo_iterations = r.number_lo_iterations;
+  statistics->inlier_indices.clear();
+  for (int i = 0; i < n; ++i)
+    if (flags[i]) statistics->inlier_indices.push_back(i);
+  return r.best_num_inliers;
+}
+}  // namespace detail
+
+// Same template parameters and EstimateModel signature as ransac_lib::LocallyOptimizedMSAC
+// (include/RansacLib/ransac.h:119-129), so examples/spherical_sfm_tools.cpp:380-387 compiles after
+// swapping the namespace.  Sampling is the engine's Philox stream (the Sampler parameter is ignored).
+template <class Model, class ModelVector, class Solver, class Sampler = void>
+class LocallyOptimizedMSAC {
+ public:
+  template <class Options, class Statistics>
+  int EstimateModel(const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) const {
+    return detail::estimate_one(SSFM_DRIVER_LO_MSAC, options, solver, best_model, statistics);
+  }
+};
+template <class Model, class ModelVector, class Solver, class Sampler = void>
+class VanillaMSAC {  // evaluation/vanilla_ransac.h:17-23
+ public:
+  template <class Options, class Statistics>
+  int EstimateModel(const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) const {
+    return detail::estimate_one(SSFM_DRIVER_VANILLA_MSAC, options, solver, best_model, statistics);
+  }
+};
+
+// The new batched-pairs entry point: one call for all pairs (replaces the OpenMP loop).
+// pair_lists: one RayPairList per image pair.  results: one SsfmPairResult per pair;
+// inlier_flags (optional): concatenated 0/1 flags in pair order.
+template <class Options, class RayPairList>
+inline void EstimatePairs(const Engine& eng, const Options& options, const std::vector<RayPairList>& pair_lists,
+                          bool use_poly_solver, bool inward, std::vector<SsfmPairResult>* results,
+                          std::vector<uint8_t>* inlier_flags = nullptr) {
+  SsfmOptions o = detail::to_c_options(options);
+  o.solver = use_poly_solver ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX;
+  o.inward = inward ? 1 : 0;
+  std::vector<int64_t> offsets(pair_lists.size() + 1, 0);
+  for (size_t p = 0; p < pair_lists.size(); ++p) offsets[p + 1] = offsets[p] + (int64_t)pair_lists[p].size();
+  std::vector<double> rays((size_t)offsets.back() * 6);
+  for (size_t p = 0; p < pair_lists.size(); ++p)
+    if (!pair_lists[p].empty())
+      std::memcpy(rays.data() + 6 * (size_t)offsets[p], &pair_lists[p][0], 48 * pair_lists[p].size());
+  SsfmBatch b;
+  b.num_pairs = (int32_t)pair_lists.size();
+  b.offsets = offsets.data();
+  b.rays = rays.data();
+  b.rays_on_device = 0;
+  results->resize(pair_lists.size());
+  if (inlier_flags) inlier_flags->assign((size_t)offsets.back(), 0);
+  check(ssfm_estimate_pairs(eng.get(), &b, &o, results->data(), inlier_flags ? inlier_flags->data() : nullptr));
+}
+
+}  // namespace ssfm_b200

@@ -115,7 +115,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_decompose",
+    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -274,6 +274,17 @@ class Engine:
         _check(lib().ssfm_least_squares(self._h, _p(rays, C.c_double), len(rays), _p(idx, C.c_int32), _p(offs, C.c_int32),
                                         len(samples), int(inward), _p(E, C.c_double)))
         return E
+
+    def non_minimal_solve(self, rays, samples):
+        rays = np.ascontiguousarray(rays, np.float64)
+        offs = np.zeros(len(samples) + 1, np.int32)
+        offs[1:] = np.cumsum([len(s) for s in samples])
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in samples]), np.int32)
+        E = np.zeros((len(samples), 9))
+        ok = np.zeros(len(samples), np.int32)
+        _check(lib().ssfm_non_minimal_solve(self._h, _p(rays, C.c_double), len(rays), _p(idx, C.c_int32),
+                                            _p(offs, C.c_int32), len(samples), _p(E, C.c_double), _p(ok, C.c_int32)))
+        return E, ok
 
     def decompose(self, E9, inward=False):
         E = np.ascontiguousarray(E9, np.float64).reshape(-1, 9)

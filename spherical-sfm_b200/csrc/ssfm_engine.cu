@@ -555,6 +555,32 @@ int ssfm_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32
   return SSFM_OK;
 }
 
+int ssfm_non_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
+                           const int32_t* sample_offsets, int32_t nprob, double* E9, int32_t* ok) {
+  if (!h || !rays || !sample_idx || !sample_offsets || !E9 || !ok || nprob < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (nprob == 0) return SSFM_OK;
+  const int total = sample_offsets[nprob];
+  for (int i = 0; i < total; ++i)
+    if (sample_idx[i] < 0 || sample_idx[i] >= n) return fail(SSFM_ERR_INVALID, "sample index out of range");
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
+  SSFM_TMP(int, b_i, (size_t)total) SSFM_KEEP(g, b_i)
+  SSFM_TMP(int, b_o, (size_t)nprob + 1) SSFM_KEEP(g, b_o)
+  SSFM_TMP(double, b_e, (size_t)nprob * 9) SSFM_KEEP(g, b_e)
+  SSFM_TMP(int, b_k, (size_t)nprob) SSFM_KEEP(g, b_k)
+  double* dr = (double*)g.ptrs[0]; int* di = (int*)g.ptrs[1]; int* dof = (int*)g.ptrs[2]; double* de = (double*)g.ptrs[3]; int* dk = (int*)g.ptrs[4];
+  if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  if (total > 0) SSFM_CK(cudaMemcpyAsync(di, sample_idx, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dof, sample_offsets, sizeof(int) * ((size_t)nprob + 1), cudaMemcpyHostToDevice, h->stream));
+  k_non_minimal<<<(nprob + 3) / 4, 128, 0, h->stream>>>(dr, n, di, dof, nprob, de, dk);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(E9, de, sizeof(double) * 9 * (size_t)nprob, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(ok, dk, sizeof(int) * (size_t)nprob, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
 int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward, double* r3, double* t3) {
   if (!h || !E9 || !r3 || !t3 || num < 0) return fail(SSFM_ERR_INVALID, "bad argument");
   if (num == 0) return SSFM_OK;

@@ -455,6 +455,20 @@ __global__ void k_least_squares(const double* __restrict__ rays, const int* __re
     for (int i = 0; i < 9; ++i) E9[(size_t)w * 9 + i] = E[i];
 }
 
+__global__ void k_non_minimal(const double* __restrict__ rays, int n, const int* __restrict__ idx,
+                              const int* __restrict__ sample_offsets, int nprob, double* E9, int* ok) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nprob) return;
+  WarpCtx cx{(int)(threadIdx.x & 31)};
+  PairView pv{rays, n};
+  double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool good = non_minimal_solver(cx, pv, idx + sample_offsets[w], sample_offsets[w + 1] - sample_offsets[w], E);
+  if (cx.lane() == 0) {
+    for (int i = 0; i < 9; ++i) E9[(size_t)w * 9 + i] = E[i];
+    ok[w] = good ? 1 : 0;
+  }
+}
+
 __global__ void k_decompose(const double* __restrict__ E9, int num, int inward, double* r3, double* t3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= num) return;

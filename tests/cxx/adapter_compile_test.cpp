@@ -1,0 +1,70 @@
+// Compiles the RansacLib-concept adapters against a reference-shaped call site (the body of
+// estimate_pairwise, examples/spherical_sfm_tools.cpp:378-392) with stand-in Eigen-like types.
+// Exit codes: 0 ok (GPU present), 3 engine reported "no device" (CPU-only box), 1 wrong result.
+#include <array>
+#include <cstdio>
+#include <random>
+#include <utility>
+#include <vector>
+
+#include "ssfm_ransaclib.hpp"
+
+struct Vec3 {  // stand-in for Eigen::Vector3d (3 packed doubles)
+  double d[3];
+  double& operator[](int i) { return d[i]; }
+  double operator[](int i) const { return d[i]; }
+};
+typedef std::pair<Vec3, Vec3> RayPair;
+typedef std::vector<RayPair> RayPairList;
+
+int main() {
+  using namespace ssfm_b200;
+  // a small synthetic pair: rotation about y, t = R e3 - e3, noise-free, 20% gross outliers
+  const double a = 0.1, c = std::cos(a), s = std::sin(a);
+  const double R[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+  const double t[3] = {R[2], R[5], R[8] - 1};
+  std::mt19937 g(1);
+  std::normal_distribution<double> nd;
+  std::uniform_real_distribution<double> ud(4, 8);
+  RayPairList rays(200);
+  for (size_t i = 0; i < rays.size(); ++i) {
+    Vec3 u{{nd(g) * 0.3, nd(g) * 0.3, 1.0}};
+    const double dep = ud(g);
+    double X[3] = {u[0] * dep, u[1] * dep, dep}, Y[3];
+    for (int r = 0; r < 3; ++r) Y[r] = R[3 * r] * X[0] + R[3 * r + 1] * X[1] + R[3 * r + 2] * X[2] + t[r];
+    Vec3 v{{Y[0] / Y[2], Y[1] / Y[2], 1.0}};
+    if (i % 5 == 0) { v[0] = nd(g); v[1] = nd(g); }
+    rays[i] = std::make_pair(u, v);
+  }
+  try {
+    Engine eng(0);
+    LORansacOptions options;
+    options.squared_inlier_threshold_ = 1e-6;
+    options.num_lo_steps_ = 0;
+    options.num_lsq_iterations_ = 0;
+    options.final_least_squares_ = true;
+    GpuSphericalEstimator<Mat3d> estimator(eng, rays, false, false);
+    LocallyOptimizedMSAC<Mat3d, std::vector<Mat3d>, GpuSphericalEstimator<Mat3d>> ransac;
+    RansacStatistics stats;
+    Mat3d E;
+    const int ninliers = ransac.EstimateModel(options, estimator, &E, &stats);
+    int recount = 0;
+    for (size_t i = 0; i < rays.size(); ++i)
+      recount += estimator.EvaluateModelOnPoint(E, (int)i) < options.squared_inlier_threshold_;
+    std::vector<Mat3d> Es;
+    const int nm = estimator.MinimalSolver({1, 2, 3}, &Es);
+    Mat3d Rm;
+    Vec3 tt;
+    estimator.Decompose(E, stats.inlier_indices, &Rm, &tt);
+    std::vector<SsfmPairResult> res;
+    EstimatePairs(eng, options, std::vector<RayPairList>{rays, rays}, false, false, &res);
+    std::printf("inliers %d recount %d models %d R02 %.6f (want %.6f) batched %d %d\n", ninliers, recount, nm, Rm(0, 2), s,
+                res[0].best_num_inliers, res[1].best_num_inliers);
+    const bool ok = ninliers == 160 && recount == ninliers && nm == 4 && std::fabs(Rm(0, 2) - s) < 1e-6 &&
+                    res[0].best_num_inliers == 160;
+    return ok ? 0 : 1;
+  } catch (const Error& e) {
+    std::printf("engine error %d: %s\n", e.code(), e.what());
+    return e.code() == SSFM_ERR_NO_DEVICE ? 3 : 2;
+  }
+}
