@@ -113,6 +113,7 @@ typedef struct SsfmRunStats {
   int64_t evals_exact;    /* f64 evaluations in the certification / LO stage */
   int64_t score_launches;
   int64_t h2d_bytes, d2h_bytes;
+  int64_t refit_waves; /* walk/refit alternations of the deferred least-squares protocol */
 } SsfmRunStats;
 
 int ssfm_abi_version(void);

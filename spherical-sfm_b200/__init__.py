@@ -17,7 +17,7 @@ import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
-LIB_PATH = os.path.join(_DIR, "libssfm_b200.so")
+LIB_PATH = os.environ.get("SSFM_LIB_PATH", os.path.join(_DIR, "libssfm_b200.so"))  # override: profiling builds
 _SOURCES = [os.path.join(_DIR, "csrc", f) for f in
             ("ssfm_engine.cu", "ssfm_kernels.cuh", "ssfm_chain.cuh", "ssfm_math.cuh")] + [
                 os.path.join(_ROOT, "include", "ssfm.h")]
@@ -68,7 +68,7 @@ class SsfmRunStats(C.Structure):
         ("total_ms", C.c_double), ("pack_ms", C.c_double), ("solve_ms", C.c_double), ("score_ms", C.c_double),
         ("chain_ms", C.c_double), ("rounds", C.c_int32), ("kernel_launches", C.c_int32),
         ("evals_useful", C.c_int64), ("evals_executed", C.c_int64), ("evals_exact", C.c_int64),
-        ("score_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+        ("score_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("refit_waves", C.c_int64),
     ]
 
 

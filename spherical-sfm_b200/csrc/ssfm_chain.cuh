@@ -45,10 +45,24 @@ struct PairState {
   uint32_t it;         // stats.num_iterations
   uint32_t max_iters;  // max_num_iterations (adaptive)
   int best_num_inliers;
+  int cnt_best;     // inliers (err < thr2) of E_best, known from the pass that scored it
+  int cnt_bestmin;  // same for E_bestmin
   int num_lo;
   int done;
+  int phase;    // PHASE_*: a deferred least-squares refit is outstanding for this pair
+  int walk_j;   // slot of the current round at which process_round resumes
+  int lm_n;     // number of residuals of the outstanding refit (indices in Scratch::list_a)
   float runmin32;  // running minimum of the FP32 per-iteration scores
 };
+
+// Deferred-refit protocol (pipeline options, num_lo_steps == 0).  Every LocalOptimization is then
+// exactly: LeastSquaresFit (inliers at thr*mult -> shuffle -> <= 21 residuals -> LM) + one
+// ScoreModel + UpdateBestModel (ransac.h:360-366).  The warp that walks a pair does the inlier
+// collection and the shuffle, parks the pair with its refit described in (list_a, lm_n, lm_E),
+// and a separate kernel solves ALL parked refits -- one thread per small problem -- before the
+// walk resumes.  A single warp iterating one 6-parameter LM is latency bound (~10^5 cycles per
+// refit); thousands of independent refits, one per lane, are not.
+enum { PHASE_NONE = 0, PHASE_LO_START = 1, PHASE_LO_BEST = 2, PHASE_LO_LATE = 3, PHASE_FINAL_LSQ = 4 };
 
 struct SerialCtx {
   SSFM_HD int lane() const { return 0; }
@@ -61,14 +75,22 @@ struct SerialCtx {
   SSFM_HD void sync() const {}
 };
 
+// ScoreModel (ransac.h:295-303) fused with the inlier count GetInliers would return for the same
+// model and threshold (:311-336): one pass yields both, so the reference's "GetInliers(best_model)"
+// refresh needs no second pass over the data.
 template <class Ctx>
-SSFM_HD_NOINLINE double msac_score_exact(const Ctx& cx, const double* E, const double* rays, int n, double thr, long long* evals) {
+SSFM_HD_NOINLINE double msac_score_exact(const Ctx& cx, const double* E, const double* rays, int n, double thr, int* count,
+                                         long long* evals) {
   double s = 0.0;
+  int c = 0;
+#pragma unroll 2
   for (int i = cx.lane(); i < n; i += cx.width()) {
     const double e = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
     s += (thr < e) ? thr : e;  // std::min(e, thr) incl. its NaN behaviour (ransac.h:306-309)
+    c += (e < thr) ? 1 : 0;
   }
   *evals += n;
+  *count = cx.sum_i(c);
   return cx.sum(s);
 }
 
@@ -106,12 +128,18 @@ SSFM_HD_NOINLINE int collect_inliers(const Ctx& cx, const double* E, const doubl
   return count;
 }
 
-// RandomShuffleAndResize (include/RansacLib/utils.h:34-52) with the LO generator.  Serial: one
-// lane walks the whole Fisher-Yates so the generator consumes exactly the reference's draws.
+// RandomShuffleAndResize (include/RansacLib/utils.h:34-52) with the LO generator: Fisher-Yates over all
+// n entries, then truncation to `keep`.  Swaps at positions i >= keep only touch entries that are
+// thrown away, so only the first `keep` swaps are materialised (one lane, serial -- they are data
+// dependent); the remaining n-1-keep draws are just CONSUMED so that the generator ends in exactly
+// the state the reference's would: lanes test 32 draws at a time for Lemire's rejection condition
+// (probability ~range/2^32 each) and fall back to the serial walk for a chunk only if one triggers.
 template <class Ctx>
-SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list, int n) {
+SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list, int n, int keep) {
+  int i = 0;
   if (cx.lane() == 0) {
-    for (int i = 0; i < n - 1; ++i) {
+    const int lim = keep < n - 1 ? keep : n - 1;
+    for (; i < lim; ++i) {
       const int j = uniform_int_libstdcxx(mt, i, n - 1);
       const int tmp = list[i];
       list[i] = list[j];
@@ -119,6 +147,45 @@ SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list,
     }
   }
   cx.sync();
+  i = keep < n - 1 ? keep : (n - 1 > 0 ? n - 1 : 0);
+  const int W = cx.width();
+  while (i < n - 1) {
+    uint32_t pos = mt[624];
+    if (pos >= 624) {
+      if (cx.lane() == 0) mt19937_twist(mt);
+      cx.sync();
+      pos = 0;
+    }
+    int chunk = n - 1 - i;
+    if (chunk > W) chunk = W;
+    if ((int)(624 - pos) < chunk) chunk = (int)(624 - pos);
+    bool reject = false;
+    if (W > 1) {
+      const int l = cx.lane();
+      if (l < chunk) {
+        uint32_t y = mt[pos + l];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        const uint32_t range = (uint32_t)(n - 1 - (i + l)) + 1u;  // hi - lo + 1 with lo = i + l, hi = n - 1
+        const uint32_t low = (uint32_t)((uint64_t)y * (uint64_t)range);
+        reject = low < range && low < ((0u - range) % range);
+      }
+    }
+    if (W > 1 && cx.ballot(reject) == 0u) {
+      cx.sync();
+      if (cx.lane() == 0) mt[624] = pos + (uint32_t)chunk;
+      cx.sync();
+      i += chunk;
+    } else {
+      // serial walk over this chunk (always taken by the single-lane test context)
+      if (cx.lane() == 0)
+        for (int k = 0; k < chunk; ++k) (void)uniform_int_libstdcxx(mt, i + k, n - 1);
+      cx.sync();
+      i += chunk;
+    }
+  }
 }
 
 // SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157): Ceres 2.2 trust-region
@@ -138,21 +205,29 @@ SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int
   double x_cost = 0.0, gmax = 0.0;
   bool have_scale = false;
 
-  // evaluate cost, gradient and J^T J at x (jets), apply Jacobi scaling
+  // evaluate cost, gradient and J^T J at x, apply Jacobi scaling.  E(x) and dE/dx are uniform
+  // across the warp (computed once per call as jets); each residual then costs ~200 flops.
   auto eval_jac = [&](const double* xx) {
+    Jet6 Ej[9];
+    {
+      const Jet6 r1[3] = {jvar(xx[0], 0), jvar(xx[1], 1), jvar(xx[2], 2)};
+      const Jet6 t1[3] = {jvar(xx[3], 3), jvar(xx[4], 4), jvar(xx[5], 5)};
+      spherical_E_of_params<Jet6>(r1, t1, t0z, Ej);
+    }
     double Hl[21], gl[6], c = 0.0;
     for (int a = 0; a < 21; ++a) Hl[a] = 0.0;
     for (int a = 0; a < 6; ++a) gl[a] = 0.0;
     for (int i = cx.lane(); i < n; i += cx.width()) {
       const double* ry = rays + 6 * (size_t)sample[i];
-      Jet6 r1[3] = {jvar(xx[0], 0), jvar(xx[1], 1), jvar(xx[2], 2)};
-      Jet6 t1[3] = {jvar(xx[3], 3), jvar(xx[4], 4), jvar(xx[5], 5)};
-      const Jet6 r = sampson_residual<Jet6>(r1, t1, t0z, ry, ry + 3);
-      c += r.a * r.a;
+      double r, jr[6];
+      sampson_value_grad(Ej, ry, ry + 3, r, jr);
+      c += r * r;
       int k = 0;
+#pragma unroll
       for (int a = 0; a < 6; ++a) {
-        gl[a] += r.v[a] * r.a;
-        for (int b = 0; b <= a; ++b) Hl[k++] += r.v[a] * r.v[b];
+        gl[a] += jr[a] * r;
+#pragma unroll
+        for (int b = 0; b <= a; ++b) Hl[k++] += jr[a] * jr[b];
       }
     }
     for (int a = 0; a < 21; ++a) H[a] = cx.sum(Hl[a]);
@@ -172,10 +247,12 @@ SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int
     return 0.5 * c;
   };
   auto eval_cost = [&](const double* xx) {
+    double Ev[9];
+    spherical_E_of_params<double>(xx, xx + 3, t0z, Ev);
     double c = 0.0;
     for (int i = cx.lane(); i < n; i += cx.width()) {
       const double* ry = rays + 6 * (size_t)sample[i];
-      const double r = sampson_residual<double>(xx, xx + 3, t0z, ry, ry + 3);
+      const double r = sampson_value(Ev, ry, ry + 3);
       c += r * r;
     }
     return 0.5 * cx.sum(c);
@@ -258,7 +335,19 @@ struct Scratch {
   int* list_a;   // n ints
   int* list_b;   // n ints
   uint32_t* mt;  // 625 words
+  unsigned long long* prof;  // optional per-phase cycle counters (profiling builds only)
+  double* lm_E;  // 9 doubles: model handed to / returned by a deferred refit
 };
+
+// Phase timers for profiling builds (-DSSFM_PROFILE_CHAIN): cycles spent per phase, summed over warps.
+#if defined(SSFM_PROFILE_CHAIN) && defined(__CUDA_ARCH__)
+#define SSFM_TIC long long tic__ = clock64();
+#define SSFM_TOC(sc, k) if ((sc).prof && cx.lane() == 0) atomicAdd(&(sc).prof[k], (unsigned long long)(clock64() - tic__));
+#else
+#define SSFM_TIC
+#define SSFM_TOC(sc, k)
+#endif
+enum { PH_SCAN = 8, PH_RESCORE, PH_LO_COLLECT, PH_LO_SHUFFLE, PH_LO_LM, PH_LO_SCORE, PH_FINAL_LM, PH_FINAL_REST, PH_TOTAL };
 
 struct PairView {
   const double* rays;  // 6 doubles per correspondence
@@ -269,15 +358,17 @@ template <class Ctx>
 SSFM_HD_NOINLINE void lsq_fit(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, double thresh, double* E,
                      long long* evals) {  // LeastSquaresFit, ransac.h:409-420
   const int cap = P.min_sample_mult * 3;
-  const int n = collect_inliers(cx, E, pv.rays, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals);
+  int n;
+  { SSFM_TIC n = collect_inliers(cx, E, pv.rays, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
   if (n < 3) return;
-  shuffle_and_resize(cx, sc.mt, sc.list_a, n);
-  least_squares(cx, pv.rays, sc.list_a, n < cap ? n : cap, P.inward != 0, E);
+  { SSFM_TIC shuffle_and_resize(cx, sc.mt, sc.list_a, n, n < cap ? n : cap); SSFM_TOC(sc, PH_LO_SHUFFLE) }
+  { SSFM_TIC least_squares(cx, pv.rays, sc.list_a, n < cap ? n : cap, P.inward != 0, E); SSFM_TOC(sc, PH_LO_LM) }
 }
 
-SSFM_HD void keep_better(double s, const double* m, double* sb, double* mb) {  // UpdateBestModel :422-428
+SSFM_HD void keep_better(double s, const double* m, int c, double* sb, double* mb, int* cb) {  // UpdateBestModel :422-428
   if (s < *sb) {
     *sb = s;
+    *cb = c;
     for (int i = 0; i < 9; ++i) mb[i] = m[i];
   }
 }
@@ -347,14 +438,16 @@ SSFM_HD_NOINLINE bool non_minimal_solver(const Ctx& cx, const PairView& pv, cons
 
 template <class Ctx>
 SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, double* E_best,
-                                double* score_best, long long* evals) {  // ransac.h:341-407
+                                         double* score_best, int* cnt_best, long long* evals) {  // ransac.h:341-407
   if (4 > pv.n) return;  // non_minimal_sample_size() == 4
   const double thr = P.thr2, mult = P.thr_mult;
   double m_init[9];
   for (int i = 0; i < 9; ++i) m_init[i] = E_best[i];
   lsq_fit(cx, P, pv, sc, thr * mult, m_init, evals);
-  double score = msac_score_exact(cx, m_init, pv.rays, pv.n, thr, evals);
-  keep_better(score, m_init, score_best, E_best);
+  int cnt = 0;
+  double score;
+  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.rays, pv.n, thr, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
+  keep_better(score, m_init, cnt, score_best, E_best, cnt_best);
   if (P.num_lo_steps <= 0) return;  // inliers_base is only used by the steps below
   const int nbase = collect_inliers(cx, m_init, pv.rays, pv.n, thr * mult, false, sc.list_b, (unsigned char*)0, evals);
   int non_min = 3 * P.non_min_mult;
@@ -364,7 +457,7 @@ SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const P
     // sample = inliers_base; RandomShuffleAndResize(non_min)   (:380-381)
     for (int i = cx.lane(); i < nbase; i += cx.width()) sc.list_a[i] = sc.list_b[i];
     cx.sync();
-    shuffle_and_resize(cx, sc.mt, sc.list_a, nbase);
+    shuffle_and_resize(cx, sc.mt, sc.list_a, nbase, non_min);
     // std::vector::resize(target) grows with zeros when target > size (non_min > nbase)
     const int ns = non_min;
     if (ns > nbase) {
@@ -374,24 +467,48 @@ SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const P
     }
     double m[9];
     if (!non_minimal_solver(cx, pv, sc.list_a, ns, m)) continue;
-    score = msac_score_exact(cx, m, pv.rays, pv.n, thr, evals);
-    keep_better(score, m, score_best, E_best);
+    score = msac_score_exact(cx, m, pv.rays, pv.n, thr, &cnt, evals);
+    keep_better(score, m, cnt, score_best, E_best, cnt_best);
     lsq_fit(cx, P, pv, sc, thr, m, evals);
     double th = mult * thr;
     const double dth = (mult - 1.0) * thr / (double)(int)(P.num_lsq_iters - 1);
     for (int i = 0; i < P.num_lsq_iters; ++i) {
       lsq_fit(cx, P, pv, sc, th, m, evals);
-      score = msac_score_exact(cx, m, pv.rays, pv.n, thr, evals);
-      keep_better(score, m, score_best, E_best);
+      score = msac_score_exact(cx, m, pv.rays, pv.n, thr, &cnt, evals);
+      keep_better(score, m, cnt, score_best, E_best, cnt_best);
       th -= dth;
     }
   }
 }
 
-// GetInliers on *best_model + inlier ratio + NumRequiredIterations (ransac.h:231-238)
+// LocalOptimization for num_lo_steps == 0, first half: the inlier collection and shuffle of
+// LeastSquaresFit (ransac.h:361 -> :409-418).  Returns the number of residuals of the refit
+// (0: fewer than min_sample_size inliers, no refit; < 0: LocalOptimization returns at :350).
 template <class Ctx>
-SSFM_HD_NOINLINE void refresh(const Ctx& cx, const Params& P, const PairView& pv, PairState& st, bool update_max) {
-  st.best_num_inliers = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, (int*)0, (unsigned char*)0, &st.evals_exact);
+SSFM_HD_NOINLINE int lo_begin(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, const double* E,
+                              long long* evals) {
+  if (4 > pv.n) return -1;
+  const int cap = P.min_sample_mult * 3;
+  int n;
+  { SSFM_TIC n = collect_inliers(cx, E, pv.rays, pv.n, P.thr2 * P.thr_mult, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
+  if (n < 3) return 0;
+  { SSFM_TIC shuffle_and_resize(cx, sc.mt, sc.list_a, n, n < cap ? n : cap); SSFM_TOC(sc, PH_LO_SHUFFLE) }
+  return n < cap ? n : cap;
+}
+// second half (ransac.h:363-366): score the refitted model, keep it if it is better.
+template <class Ctx>
+SSFM_HD_NOINLINE void lo_end(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, const double* m_init,
+                             double* E_target, double* score_target, int* cnt_target, long long* evals) {
+  int cnt = 0;
+  double score;
+  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.rays, pv.n, P.thr2, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
+  keep_better(score, m_init, cnt, score_target, E_target, cnt_target);
+}
+
+// GetInliers on *best_model + inlier ratio + NumRequiredIterations (ransac.h:231-238).  The count is
+// the one recorded when *best_model was scored (same model, same threshold, same arithmetic).
+SSFM_HD void refresh(const Params& P, const PairView& pv, PairState& st, bool update_max) {
+  st.best_num_inliers = st.cnt_best;
   st.inlier_ratio = (double)st.best_num_inliers / (double)pv.n;
   if (update_max) st.max_iters = required_iterations(st.inlier_ratio, P.eta, 3, P.min_iters, P.max_iters);
 }
@@ -407,8 +524,13 @@ SSFM_HD void init_state(const Params& P, int n, PairState& st) {
   st.max_iters = P.max_iters > P.min_iters ? P.max_iters : P.min_iters;
   if (P.driver == 2) st.max_iters = (uint32_t)(P.fixed_budget > 0 ? P.fixed_budget : 0);
   st.best_num_inliers = 0;
+  st.cnt_best = 0;
+  st.cnt_bestmin = 0;
   st.num_lo = 0;
   st.done = n < 3 ? 1 : 0;  // kMinSampleSize > kNumData -> return 0 (ransac.h:137-139)
+  st.phase = PHASE_NONE;
+  st.walk_j = 0;
+  st.lm_n = 0;
   st.runmin32 = INFINITY;
 }
 
@@ -431,14 +553,34 @@ SSFM_HD uint32_t iterations_wanted(const Params& P, const PairState& st) {
 // cand_margin of the running FP32 minimum are re-scored here in float64 (bit-compatible
 // arithmetic); everything the reference does at such an iteration -- best-model bookkeeping,
 // local optimisation, inlier refresh, adaptive termination -- then runs exactly.
-template <class Ctx>
+// With DEFER (only valid for num_lo_steps == 0) the function returns early with st.phase != 0
+// whenever a refit is needed; calling it again after the refit was solved resumes at that point.
+template <class Ctx, bool DEFER>
 SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, PairState& st,
-                           const double* models, int mstride, const float* s32, int navail) {
-  // model (slot j, root m, parameter i) lives at models[(m * 6 + i) * mstride + j]
+                           const double* models, int mstride, const float* s32, const float* s32m, int navail) {
+  // model (slot j, root m, parameter i) lives at models[(m * 6 + i) * mstride + j];
+  // s32[j] = min over the four roots of the FP32 cost, s32m[m * mstride + j] = the four costs.
   const bool lo_driver = P.driver == 0;
   const bool legacy = P.driver == 2;
   int j = 0;
+  bool skip_top = false;
+  if (DEFER && st.phase == PHASE_LO_START) {  // the refit of the LO at lo_start came back (ransac.h:166-177)
+    lo_end(cx, P, pv, sc, sc.lm_E, st.E_best, &st.best_model_score, &st.cnt_best, &st.evals_exact);
+    refresh(P, pv, st, true);
+    st.phase = PHASE_NONE;
+    j = st.walk_j;
+    skip_top = true;
+  } else if (DEFER && st.phase == PHASE_LO_BEST) {  // the refit of a new best minimal model came back (:223-238)
+    double score = st.best_min_score;
+    lo_end(cx, P, pv, sc, sc.lm_E, st.E_bestmin, &score, &st.cnt_bestmin, &st.evals_exact);
+    keep_better(score, st.E_bestmin, st.cnt_bestmin, &st.best_model_score, st.E_best, &st.cnt_best);
+    refresh(P, pv, st, true);
+    st.phase = PHASE_NONE;
+    j = st.walk_j + 1;
+    ++st.it;
+  }
   while (!st.done) {
+   if (!skip_top) {
     // loop condition of the reference's for/while
     if (legacy) {
       if (!((double)st.it < st.legacy_num_iter && (int)st.it < P.fixed_budget)) { st.done = 1; break; }
@@ -449,6 +591,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
     // ---- find the next iteration in this round that can matter
     int jn = navail;  // first candidate / special index >= j
     {
+      SSFM_TIC
       float run = st.runmin32;
       int base = j;
       while (base < navail && jn == navail) {
@@ -470,6 +613,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
         base += cx.width();
       }
       st.runmin32 = run;
+      SSFM_TOC(sc, PH_SCAN)
     }
     // iterations j .. jn-1 cannot matter: skip them, honouring the termination test
     {
@@ -493,28 +637,51 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
     // ---- iteration st.it (slot j) is a candidate and/or the lo_start iteration
     if (lo_driver && st.it == P.lo_start && st.best_min_score < kDblMax) {  // ransac.h:163-178
       ++st.num_lo;
-      local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.evals_exact);
-      refresh(cx, P, pv, st, true);
+      if (DEFER) {
+        const int nr = lo_begin(cx, P, pv, sc, st.E_best, &st.evals_exact);
+        if (nr > 0) {
+          if (cx.lane() == 0)
+            for (int i = 0; i < 9; ++i) sc.lm_E[i] = st.E_best[i];
+          st.lm_n = nr;
+          st.phase = PHASE_LO_START;
+          st.walk_j = j;
+          return;
+        }
+      } else {
+        local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.cnt_best, &st.evals_exact);
+      }
+      refresh(P, pv, st, true);
     }
+   }
+    skip_top = false;
     // exact re-scoring of the iteration's models (GetBestEstimatedModelId, :278-293)
+    // Only roots whose FP32 cost is within the pre-filter slack of the iteration's FP32 minimum can
+    // be the float64 argmin; the others are skipped.
     double local_best = legacy ? INFINITY : kDblMax;
-    int local_id = -1;
+    int local_id = -1, local_cnt = 0;
     int nvalid = 0;
+    const float smin = s32[j];
+    SSFM_TIC
     for (int m = 0; m < 4; ++m) {
       double p[6];
       for (int i = 0; i < 6; ++i) p[i] = models[(size_t)(m * 6 + i) * mstride + j];
       if (p[0] != p[0]) continue;  // absent (or NaN) model: can never win a '<'
       ++nvalid;
+      const float sm = s32m[(size_t)m * mstride + j];
+      if (!(sm <= smin * (1.0f + P.cand_margin))) continue;
       double Em[9];
       E_from_p(p, Em);
-      const double s = msac_score_exact(cx, Em, pv.rays, pv.n, P.thr2, &st.evals_exact);
+      int cnt = 0;
+      const double s = msac_score_exact(cx, Em, pv.rays, pv.n, P.thr2, &cnt, &st.evals_exact);
       if (legacy) {
-        if (s < st.best_min_score && s < local_best) { local_best = s; local_id = m; }
+        if (s < st.best_min_score && s < local_best) { local_best = s; local_id = m; local_cnt = cnt; }
       } else if (s < local_best) {
         local_best = s;
         local_id = m;
+        local_cnt = cnt;
       }
     }
+    SSFM_TOC(sc, PH_RESCORE)
     // MinimalSolver returned <= 0 models -> `continue` (ransac.h:185).  The action-matrix and
     // polynomial solvers always return 4 (possibly NaN) matrices; the Sturm variant returns the
     // number of real roots it kept.
@@ -545,18 +712,31 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
           for (int i = 0; i < 6; ++i) p[i] = models[(size_t)(local_id * 6 + i) * mstride + j];
           E_from_p(p, Em);
           st.best_min_score = local_best;
+          st.cnt_bestmin = local_cnt;
           for (int i = 0; i < 9; ++i) st.E_bestmin[i] = Em[i];
-          keep_better(st.best_min_score, st.E_bestmin, &st.best_model_score, st.E_best);
+          keep_better(st.best_min_score, st.E_bestmin, st.cnt_bestmin, &st.best_model_score, st.E_best, &st.cnt_best);
         }
         const bool run_lo = lo_driver && st.it >= P.lo_start && st.best_min_score < kDblMax;
         if (is_best || run_lo) {
           if (run_lo) {
             ++st.num_lo;
-            double score = st.best_min_score;
-            local_optimization(cx, P, pv, sc, st.E_bestmin, &score, &st.evals_exact);
-            keep_better(score, st.E_bestmin, &st.best_model_score, st.E_best);
+            if (DEFER) {
+              const int nr = lo_begin(cx, P, pv, sc, st.E_bestmin, &st.evals_exact);
+              if (nr > 0) {
+                if (cx.lane() == 0)
+                  for (int i = 0; i < 9; ++i) sc.lm_E[i] = st.E_bestmin[i];
+                st.lm_n = nr;
+                st.phase = PHASE_LO_BEST;
+                st.walk_j = j;
+                return;
+              }
+            } else {
+              double score = st.best_min_score;
+              local_optimization(cx, P, pv, sc, st.E_bestmin, &score, &st.cnt_bestmin, &st.evals_exact);
+              keep_better(score, st.E_bestmin, st.cnt_bestmin, &st.best_model_score, st.E_best, &st.cnt_best);
+            }
           }
-          refresh(cx, P, pv, st, true);
+          refresh(P, pv, st, true);
         }
       }
     }
@@ -568,7 +748,8 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
 // After the loop: the late LO (:245-255), the final least squares (:257-272), and what the
 // callers do next: the inlier mask (examples/spherical_sfm_tools.cpp:388-392) and the pose
 // (:414-418).  Writes r, t; returns the per-pair status.
-template <class Ctx>
+// Returns -1 (with st.phase != 0) when DEFER parked a refit.
+template <class Ctx, bool DEFER>
 SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairView& pv, const Scratch& sc, PairState& st, double* r,
                           double* t, unsigned char* flags) {
   r[0] = r[1] = r[2] = 0.0;
@@ -579,22 +760,56 @@ SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairVie
     return 1;
   }
   if (P.driver == 0) {
-    if (st.it <= P.lo_start && st.best_model_score < kDblMax) {
-      ++st.num_lo;
-      local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.evals_exact);
-      refresh(cx, P, pv, st, false);
+    int stage = 0;  // 0 from the top, 1 late LO done, 2 final refit done
+    if (DEFER && st.phase == PHASE_LO_LATE) {
+      lo_end(cx, P, pv, sc, sc.lm_E, st.E_best, &st.best_model_score, &st.cnt_best, &st.evals_exact);
+      refresh(P, pv, st, false);
+      st.phase = PHASE_NONE;
+      stage = 1;
+    } else if (DEFER && st.phase == PHASE_FINAL_LSQ) {
+      st.phase = PHASE_NONE;
+      stage = 2;
     }
-    if (P.final_lsq) {
+    if (stage == 0 && st.it <= P.lo_start && st.best_model_score < kDblMax) {  // ransac.h:245-255
+      ++st.num_lo;
+      if (DEFER) {
+        const int nr = lo_begin(cx, P, pv, sc, st.E_best, &st.evals_exact);
+        if (nr > 0) {
+          if (cx.lane() == 0)
+            for (int i = 0; i < 9; ++i) sc.lm_E[i] = st.E_best[i];
+          st.lm_n = nr;
+          st.phase = PHASE_LO_LATE;
+          return -1;
+        }
+      } else {
+        local_optimization(cx, P, pv, sc, st.E_best, &st.best_model_score, &st.cnt_best, &st.evals_exact);
+      }
+      refresh(P, pv, st, false);
+    }
+    if (P.final_lsq) {  // ransac.h:257-272
       // LeastSquares on ALL current inliers of best_model (stats.inlier_indices)
       double refined[9];
-      for (int i = 0; i < 9; ++i) refined[i] = st.E_best[i];
-      const int ni = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, &st.evals_exact);
-      least_squares(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined);
-      const double score = msac_score_exact(cx, refined, pv.rays, pv.n, P.thr2, &st.evals_exact);
+      if (stage < 2) {
+        const int ni = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, &st.evals_exact);
+        if (DEFER) {
+          if (cx.lane() == 0)
+            for (int i = 0; i < 9; ++i) sc.lm_E[i] = st.E_best[i];
+          st.lm_n = ni;
+          st.phase = PHASE_FINAL_LSQ;
+          return -1;
+        }
+        for (int i = 0; i < 9; ++i) refined[i] = st.E_best[i];
+        { SSFM_TIC least_squares(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined); SSFM_TOC(sc, PH_FINAL_LM) }
+      } else {
+        for (int i = 0; i < 9; ++i) refined[i] = sc.lm_E[i];
+      }
+      int cnt = 0;
+      const double score = msac_score_exact(cx, refined, pv.rays, pv.n, P.thr2, &cnt, &st.evals_exact);
       if (score < st.best_model_score) {
         st.best_model_score = score;
+        st.cnt_best = cnt;
         for (int i = 0; i < 9; ++i) st.E_best[i] = refined[i];
-        refresh(cx, P, pv, st, false);
+        refresh(P, pv, st, false);
       }
     }
   }

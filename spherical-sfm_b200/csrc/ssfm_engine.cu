@@ -80,15 +80,17 @@ struct ssfm_engine {
   std::vector<long long> h_offsets;
   const double* d_rays = nullptr;  // either rays_own.p or the caller's device pointer
   DevBuf<double> rays_own;
-  DevBuf<float4> u4, v4;
+  DevBuf<float4> u4, v4, uv4;
+  bool unit_z = false;
   DevBuf<long long> offsets;
   bool resident = false;
   // run buffers
   DevBuf<PairState> states;
   DevBuf<uint32_t> mt;
-  DevBuf<int> active0, active1, navail, list_a, list_b, counts;
+  DevBuf<int> active0, active1, navail, list_a, list_b, counts, parked0, parked1;
+  DevBuf<double> lm_E;
   DevBuf<double> models;
-  DevBuf<float> s32;
+  DevBuf<float> s32, s32m;
   DevBuf<unsigned long long> counters;
   DevBuf<SsfmPairResult> results;
   DevBuf<unsigned char> flags;
@@ -119,7 +121,7 @@ Params make_params(const SsfmOptions& o) {
   P.fixed_budget = o.fixed_budget;
   P.fixed_prob = o.fixed_prob_success;
   P.first_pair_id = o.first_pair_id;
-  P.cand_margin = 2e-3f;
+  P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
   return P;
 }
@@ -200,10 +202,10 @@ void ssfm_destroy(ssfm_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->rays_own.release(); h->u4.release(); h->v4.release(); h->offsets.release();
+  h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release(); h->s32m.release();
   h->states.release(); h->mt.release(); h->active0.release(); h->active1.release(); h->navail.release();
   h->list_a.release(); h->list_b.release(); h->counts.release(); h->models.release(); h->s32.release();
-  h->counters.release(); h->results.release(); h->flags.release();
+  h->counters.release(); h->results.release(); h->flags.release(); h->parked0.release(); h->parked1.release(); h->lm_E.release();
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   if (h->h_count) cudaFreeHost(h->h_count);
   cudaStreamDestroy(h->stream);
@@ -230,6 +232,9 @@ int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
   const size_t m = (size_t)std::max<long long>(h->M, 1);
   SSFM_CK(h->u4.ensure(m));
   SSFM_CK(h->v4.ensure(m));
+  SSFM_CK(h->uv4.ensure(m));
+  SSFM_CK(h->counts.ensure(8));
+  SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), h->stream));
   SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
   if (b->rays_on_device) {
     h->d_rays = b->rays;
@@ -243,11 +248,13 @@ int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
   if (h->M > 0) {
     const int threads = 256;
     const long long blocks = (h->M + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->u4.p, h->v4.p);
+    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->u4.p, h->v4.p, h->uv4.p, h->counts.p + 2);
     SSFM_CK(cudaGetLastError());
   }
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
+  SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));  // the caller's buffer may go away after we return
+  h->unit_z = h->h_count[2] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
   float ms = 0.f;
   SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
   h->stats.pack_ms = ms;
@@ -269,9 +276,9 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   h->have_results = false;
   SSFM_CK(h->results.ensure(std::max(h->P, 1)));
   SSFM_CK(h->flags.ensure((size_t)std::max<long long>(h->M, 1)));
-  SSFM_CK(h->counters.ensure(4));
-  SSFM_CK(h->counts.ensure(4));
-  SSFM_CK(cudaMemsetAsync(h->counters.p, 0, 4 * sizeof(unsigned long long), h->stream));
+  SSFM_CK(h->counters.ensure(32));
+  SSFM_CK(h->counts.ensure(8));
+  SSFM_CK(cudaMemsetAsync(h->counters.p, 0, 32 * sizeof(unsigned long long), h->stream));
 
   int first_cap, round_cap;
   if (P.driver == SSFM_DRIVER_MSAC_FIXED) {
@@ -284,6 +291,7 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (const char* e = getenv("SSFM_ROUND_CAP")) round_cap = std::max(32, atoi(e));
   if (const char* e = getenv("SSFM_FIRST_CAP")) first_cap = std::max(32, atoi(e));
   const int R = std::max(first_cap, round_cap);
+  const bool defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
   const float thr32 = (float)P.thr2;
 
   cudaEvent_t evA = h->ev[0], evB = h->ev[1], evC = h->ev[2], evD = h->ev[3];
@@ -299,13 +307,17 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     SSFM_CK(h->navail.ensure(np));
     SSFM_CK(h->models.ensure((size_t)np * 24 * R));
     SSFM_CK(h->s32.ensure((size_t)np * R));
+    SSFM_CK(h->s32m.ensure((size_t)np * R * 4));
     SSFM_CK(h->list_a.ensure(mpass + 16));
     SSFM_CK(h->list_b.ensure(P.num_lo_steps > 0 ? mpass + 16 : 16));
     SSFM_CK(h->mt.ensure(P.driver == SSFM_DRIVER_LO_MSAC ? (size_t)np * 625 : 625));
+    SSFM_CK(h->parked0.ensure(np));
+    SSFM_CK(h->parked1.ensure(np));
+    SSFM_CK(h->lm_E.ensure((size_t)np * 9));
 
     k_init_pairs<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->mt.p, h->active0.p,
                                                           h->navail.p, first_cap);
-    SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 4 * sizeof(int), h->stream));
+    SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int), h->stream));
     k_finish_trivial<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->flags.p, 0,
                                                               h->results.p + pair0, h->active0.p, h->counts.p);
     launches += 2;
@@ -325,17 +337,63 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
       SSFM_CK(cudaEventRecord(evB, h->stream));
       {
         dim3 grid(count, (cap + kScoreThreads - 1) / kScoreThreads);
-        k_score_rounds<<<grid, kScoreThreads, 0, h->stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, h->navail.p, R,
-                                                              h->models.p, thr32, h->s32.p);
+        if (h->unit_z)
+          k_score_rounds<true><<<grid, kScoreThreads, 0, h->stream>>>(h->uv4.p, nullptr, h->offsets.p, pair0, act, h->navail.p,
+                                                                      R, h->models.p, thr32, h->s32.p, h->s32m.p);
+        else
+          k_score_rounds<false><<<grid, kScoreThreads, 0, h->stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, h->navail.p,
+                                                                       R, h->models.p, thr32, h->s32.p, h->s32m.p);
         SSFM_CK(cudaGetLastError());
       }
       SSFM_CK(cudaEventRecord(evC, h->stream));
       SSFM_CK(cudaMemsetAsync(h->counts.p + 1, 0, sizeof(int), h->stream));
-      k_chain<<<(count + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(
-          P, h->d_rays, h->offsets.p, pair0, act, count, h->navail.p, h->states.p, R, h->models.p, h->s32.p, h->list_a.p,
-          h->list_b.p, h->mt.p, c0, h->flags.p + c0, h->results.p + pair0, act_next, h->counts.p + 1, round_cap,
-          h->counters.p);
-      SSFM_CK(cudaGetLastError());
+      {
+        ChainArgs A;
+        A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = pair0;
+        A.navail = h->navail.p; A.states = h->states.p; A.R = R; A.models = h->models.p; A.s32 = h->s32.p; A.s32m = h->s32m.p;
+        A.list_a = h->list_a.p; A.list_b = h->list_b.p; A.mt = h->mt.p; A.lm_E = h->lm_E.p; A.list_base = c0;
+        A.flags = h->flags.p + c0; A.results = h->results.p + pair0; A.next_active = act_next; A.next_count = h->counts.p + 1;
+        A.next_cap = round_cap; A.parked_small = h->counts.p + 4; A.parked_big = h->counts.p + 5; A.counters = h->counters.p;
+        A.cap = np;
+        if (!defer) {
+          A.list = act; A.nlist = count; A.mode = 0; A.n_front = 0; A.parked = h->parked0.p;
+          k_chain<false><<<(count + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(P, A);
+          SSFM_CK(cudaGetLastError());
+          launches += 1;
+        } else {
+          // waves: walk -> solve the parked refits -> resume, until no pair of this round is parked
+          const int* cur = act;
+          int ncur = count, mode = 0, nfront = 0;
+          int* out = h->parked0.p;
+          int* other = h->parked1.p;
+          for (int wave = 0;; ++wave) {
+            if (wave > R + 8) return fail(SSFM_ERR_CUDA, "internal error: refit waves did not drain");
+            SSFM_CK(cudaMemsetAsync(h->counts.p + 4, 0, 2 * sizeof(int), h->stream));
+            A.list = cur; A.nlist = ncur; A.mode = mode; A.n_front = nfront; A.parked = out;
+            k_chain<true><<<(ncur + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(P, A);
+            SSFM_CK(cudaGetLastError());
+            launches += 1;
+            SSFM_CK(cudaMemcpyAsync(h->h_count + 4, h->counts.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            SSFM_CK(cudaStreamSynchronize(h->stream));
+            const int ns = h->h_count[4], nb = h->h_count[5];
+            if (ns + nb == 0) break;
+            if (ns > 0) {
+              k_refit_small<<<(ns + 63) / 64, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, h->states.p,
+                                                                  h->list_a.p, c0, h->lm_E.p);
+              launches += 1;
+            }
+            if (nb > 0) {
+              k_refit_big<<<(nb + 3) / 4, 128, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, np, nb, h->states.p,
+                                                               h->list_a.p, c0, h->lm_E.p);
+              launches += 1;
+            }
+            SSFM_CK(cudaGetLastError());
+            cur = out; ncur = ns + nb; mode = 1; nfront = ns;
+            std::swap(out, other);
+            h->stats.refit_waves += 1;
+          }
+        }
+      }
       SSFM_CK(cudaEventRecord(evD, h->stream));
       SSFM_CK(cudaMemcpyAsync(h->h_count, h->counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       SSFM_CK(cudaStreamSynchronize(h->stream));
@@ -347,7 +405,7 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
       h->stats.score_ms += t2;
       h->stats.chain_ms += t3;
       h->stats.score_launches += 1;
-      launches += 3;
+      launches += 2;
       count = h->h_count[0];
       std::swap(act, act_next);
       ++round;
@@ -355,9 +413,17 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     h->stats.rounds += round;
   }
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
-  unsigned long long hc[4] = {0, 0, 0, 0};
+  unsigned long long hc[32] = {};
   SSFM_CK(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
+#if defined(SSFM_PROFILE_CHAIN)
+  {
+    const char* names[] = {"scan", "rescore", "lo_collect", "lo_shuffle", "lo_lm", "lo_score", "final_lm", "final_rest", "total"};
+    fprintf(stderr, "[chain profile, warp-cycles]");
+    for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%.3e", names[k], (double)hc[8 + k]);
+    fprintf(stderr, "\n");
+  }
+#endif
   float ms = 0.f;
   SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
   h->stats.total_ms = ms;
@@ -479,6 +545,9 @@ int ssfm_score(ssfm_handle h, const double* models6, int32_t M, const double* ra
   SSFM_TMP(float4, b_v, (size_t)n) SSFM_KEEP(g, b_v)
   SSFM_TMP(double, b_m, (size_t)M * 6) SSFM_KEEP(g, b_m)
   double* dr = (double*)g.ptrs[0]; float4* du = (float4*)g.ptrs[1]; float4* dv = (float4*)g.ptrs[2]; double* dm = (double*)g.ptrs[3];
+  SSFM_TMP(float4, b_uv, (size_t)n) SSFM_KEEP(g, b_uv)
+  SSFM_TMP(int, b_flag, 1) SSFM_KEEP(g, b_flag)
+  float4* duv = (float4*)g.ptrs[4]; int* dflag = (int*)g.ptrs[5];
   const int gx = (M + 4 * kScoreThreads - 1) / (4 * kScoreThreads);
   const int max_chunks = std::max(1, (n + kTile - 1) / kTile);
   int nchunks = std::min(max_chunks, std::max(1, (4 * h->num_sms * 2 + gx - 1) / gx));
@@ -489,15 +558,20 @@ int ssfm_score(ssfm_handle h, const double* models6, int32_t M, const double* ra
   SSFM_TMP(int, b_pc, (size_t)nchunks * M) SSFM_KEEP(g, b_pc)
   SSFM_TMP(float, b_s, (size_t)M) SSFM_KEEP(g, b_s)
   SSFM_TMP(int, b_c, (size_t)M) SSFM_KEEP(g, b_c)
-  float* ps = (float*)g.ptrs[4]; int* pc = (int*)g.ptrs[5]; float* ds = (float*)g.ptrs[6]; int* dc = (int*)g.ptrs[7];
+  float* ps = (float*)g.ptrs[6]; int* pc = (int*)g.ptrs[7]; float* ds = (float*)g.ptrs[8]; int* dc = (int*)g.ptrs[9];
   if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
-  if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(dr, n, du, dv);
+  SSFM_CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
+  if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(dr, n, du, dv, duv, dflag);
+  SSFM_CK(cudaMemcpyAsync(h->h_count + 3, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  const bool unit_z = h->h_count[3] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
   // warm-up launch (untimed), then the timed one
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
     dim3 grid(gx, nchunks);
-    k_score_models<<<grid, kScoreThreads, 0, h->stream>>>(du, dv, n, chunk, dm, M, (float)thr2, ps, pc);
+    if (unit_z) k_score_models<true><<<grid, kScoreThreads, 0, h->stream>>>(duv, nullptr, n, chunk, dm, M, (float)thr2, ps, pc);
+    else k_score_models<false><<<grid, kScoreThreads, 0, h->stream>>>(du, dv, n, chunk, dm, M, (float)thr2, ps, pc);
     k_reduce_parts<<<(M + 255) / 256, 256, 0, h->stream>>>(ps, pc, nchunks, M, ds, dc);
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
   }

@@ -81,13 +81,17 @@ struct WarpCtx {
 // ------------------------------------------------------------------------------------------
 // k_pack
 // ------------------------------------------------------------------------------------------
-__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ u4, float4* __restrict__ v4) {
+__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ u4, float4* __restrict__ v4,
+                       float4* __restrict__ uv4, int* __restrict__ not_unit_z) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const double2* src = reinterpret_cast<const double2*>(rays + 6 * i);  // 48-byte records, 16-byte aligned
   const double2 a = src[0], b = src[1], c = src[2];
   u4[i] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
   v4[i] = make_float4((float)b.y, (float)c.x, (float)c.y, 0.f);
+  uv4[i] = make_float4((float)a.x, (float)a.y, (float)b.y, (float)c.x);
+  // pipeline rays are K^-1 (x, y, 1) (examples/spherical_sfm_tools.cpp:364-373): z == 1 exactly
+  if (b.x != 1.0 || c.y != 1.0) *not_unit_z = 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -149,12 +153,16 @@ __global__ void __launch_bounds__(64) k_sample_solve(Params P, const double* __r
 // FP32 scoring core.
 // ------------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 128;  // one look-ahead iteration (4 roots) per thread
-constexpr int kTile = 512;          // correspondences per shared-memory stage (2 x 8 KB)
+constexpr int kTile = 512;          // correspondences per shared-memory stage
 constexpr int kStages = 2;
 
+// UNITZ = every ray of the batch has z == 1 exactly (the pipeline's K^-1 (x,y,1) rays and the
+// reference's generator): one float4 (u0,u1,v0,v1) per correspondence and 19 FMA-pipe ops per
+// evaluation; otherwise two float4 (u.xyz, v.xyz) and 24.
+template <bool UNITZ>
 struct ScoreSmem {
-  float4 u[kStages][kTile];
-  float4 v[kStages][kTile];
+  float4 a[kStages][kTile];
+  float4 b[UNITZ ? 1 : kStages][UNITZ ? 1 : kTile];
   unsigned long long bar[kStages];
 };
 
@@ -185,9 +193,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // One correspondence against one structured model p (E = [p0 p1 p2; p1 -p0 p3; p4 p5 0]):
-// squared Sampson distance, 22 FMA-pipe ops + 1 MUFU.RCP (src/spherical_estimator.cpp:67-78).
+// squared Sampson distance (src/spherical_estimator.cpp:67-78).
 __device__ __forceinline__ float sampson_f32(const float (&p)[6], const float4 u, const float4 v) {
   const float Eu0 = fmaf(p[2], u.z, fmaf(p[1], u.y, p[0] * u.x));
   const float Eu1 = fmaf(p[3], u.z, fmaf(-p[0], u.y, p[1] * u.x));
@@ -196,15 +209,28 @@ __device__ __forceinline__ float sampson_f32(const float (&p)[6], const float4 u
   const float Et1 = fmaf(p[5], v.z, fmaf(-p[0], v.y, p[1] * v.x));
   const float d = fmaf(v.z, Eu2, fmaf(v.y, Eu1, v.x * Eu0));
   const float den = fmaf(Et1, Et1, fmaf(Et0, Et0, fmaf(Eu1, Eu1, Eu0 * Eu0)));
-  return __fdividef(d * d, den);
+  return (d * d) * rcp_ftz(den);
+}
+// Same with u = (x, y, 1), v = (z, w, 1) packed as one float4.
+__device__ __forceinline__ float sampson_f32_unitz(const float (&p)[6], const float4 c) {
+  const float Eu0 = fmaf(p[1], c.y, fmaf(p[0], c.x, p[2]));
+  const float Eu1 = fmaf(-p[0], c.y, fmaf(p[1], c.x, p[3]));
+  const float Eu2 = fmaf(p[5], c.y, p[4] * c.x);
+  const float Et0 = fmaf(p[1], c.w, fmaf(p[0], c.z, p[4]));
+  const float Et1 = fmaf(-p[0], c.w, fmaf(p[1], c.z, p[5]));
+  const float d = fmaf(c.w, Eu1, fmaf(c.z, Eu0, Eu2));
+  const float den = fmaf(Et1, Et1, fmaf(Et0, Et0, fmaf(Eu1, Eu1, Eu0 * Eu0)));
+  return (d * d) * rcp_ftz(den);
 }
 
 // Streams correspondences [c0, c1) of one pair through shared memory and accumulates the MSAC
-// cost (and optionally the inlier count) of the calling thread's four models.
-template <bool COUNT>
-__device__ __forceinline__ void score_stream(ScoreSmem& sm, const float4* __restrict__ u4, const float4* __restrict__ v4,
-                                             long long c0, long long c1, const float (&p)[4][6], float thr, float (&acc)[4],
-                                             int (&cnt)[4]) {
+// cost (and optionally the inlier count) of the calling thread's four models.  Warps whose lanes
+// are all idle (`active` false) only take part in the barriers.  Partial sums are folded per tile
+// so the FP32 accumulation error stays ~(kTile + ntiles) ulp.
+template <bool UNITZ, bool COUNT>
+__device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4* __restrict__ pa, const float4* __restrict__ pb,
+                                             long long c0, long long c1, const float (&p)[4][6], float thr, bool active,
+                                             float (&acc)[4], int (&cnt)[4]) {
   const int ntiles = (int)((c1 - c0 + kTile - 1) / kTile);
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -216,29 +242,35 @@ __device__ __forceinline__ void score_stream(ScoreSmem& sm, const float4* __rest
     const int s = t % kStages;
     const long long b = c0 + (long long)t * kTile;
     const uint32_t n = (uint32_t)((c1 - b) < kTile ? (c1 - b) : kTile);
-    mbar_expect_tx(&sm.bar[s], n * 32u);
-    tma_load_1d(&sm.u[s][0], u4 + b, n * 16u, &sm.bar[s]);
-    tma_load_1d(&sm.v[s][0], v4 + b, n * 16u, &sm.bar[s]);
+    mbar_expect_tx(&sm.bar[s], UNITZ ? n * 16u : n * 32u);
+    tma_load_1d(&sm.a[s][0], pa + b, n * 16u, &sm.bar[s]);
+    if (!UNITZ) tma_load_1d(&sm.b[UNITZ ? 0 : s][0], pb + b, n * 16u, &sm.bar[s]);
   };
   if (threadIdx.x == 0)
     for (int t = 0; t < kStages && t < ntiles; ++t) issue(t);
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kStages;
     mbar_wait(&sm.bar[s], (uint32_t)((t / kStages) & 1));
-    const long long b = c0 + (long long)t * kTile;
-    const int n = (int)((c1 - b) < kTile ? (c1 - b) : kTile);
-    const float4* su = sm.u[s];
-    const float4* sv = sm.v[s];
+    if (active) {
+      const long long b = c0 + (long long)t * kTile;
+      const int n = (int)((c1 - b) < kTile ? (c1 - b) : kTile);
+      const float4* sa = sm.a[s];
+      const float4* sb = sm.b[UNITZ ? 0 : s];
+      float tacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
-    for (int i = 0; i < n; ++i) {
-      const float4 u = su[i];
-      const float4 v = sv[i];
+      for (int i = 0; i < n; ++i) {
+        const float4 ca = sa[i];
+        float4 cb;
+        if (!UNITZ) cb = sb[i];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const float e = sampson_f32(p[m], u, v);
-        acc[m] += fminf(e, thr);
-        if (COUNT) cnt[m] += (e < thr) ? 1 : 0;
+        for (int m = 0; m < 4; ++m) {
+          const float e = UNITZ ? sampson_f32_unitz(p[m], ca) : sampson_f32(p[m], ca, cb);
+          tacc[m] += fminf(e, thr);
+          if (COUNT) cnt[m] += (e < thr) ? 1 : 0;
+        }
       }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc[m] += tacc[m];
     }
     __syncthreads();  // everyone is done with stage s before it is refilled
     if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);
@@ -246,19 +278,22 @@ __device__ __forceinline__ void score_stream(ScoreSmem& sm, const float4* __rest
 }
 
 // grid.x = active pairs, grid.y = ceil(R / kScoreThreads)
-__global__ void __launch_bounds__(kScoreThreads) k_score_rounds(const float4* __restrict__ u4, const float4* __restrict__ v4,
+// s32 [a][R]: min over the four roots; s32m [a][4][R]: the four costs.
+template <bool UNITZ>
+__global__ void __launch_bounds__(kScoreThreads) k_score_rounds(const float4* __restrict__ pa, const float4* __restrict__ pb,
                                                                 const long long* __restrict__ offsets, int pair0,
                                                                 const int* __restrict__ active,
                                                                 const int* __restrict__ navail, int R,
                                                                 const double* __restrict__ models, float thr,
-                                                                float* __restrict__ s32) {
-  __shared__ __align__(128) ScoreSmem sm;
+                                                                float* __restrict__ s32, float* __restrict__ s32m) {
+  __shared__ __align__(128) ScoreSmem<UNITZ> sm;
   const int a = active[blockIdx.x];
   const int na = navail[a];
   const int j0 = blockIdx.y * kScoreThreads;
   if (j0 >= na) return;  // uniform for the CTA
   const int j = j0 + threadIdx.x;
   const bool live = j < na;
+  const bool warp_live = (j0 + (int)(threadIdx.x & ~31u)) < na;
   const int pair = pair0 + a;
   float p[4][6];
   const double* src = models + (size_t)a * 24 * R + (live ? j : j0);
@@ -268,12 +303,13 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_rounds(const float4* __
     for (int i = 0; i < 6; ++i) p[m][i] = (float)src[(size_t)(m * 6 + i) * R];
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int cnt[4] = {0, 0, 0, 0};
-  score_stream<false>(sm, u4, v4, offsets[pair], offsets[pair + 1], p, thr, acc, cnt);
+  score_stream<UNITZ, false>(sm, pa, pb, offsets[pair], offsets[pair + 1], p, thr, warp_live, acc, cnt);
   if (live) {
     float best = INFINITY;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const float s = (p[m][0] == p[m][0]) ? acc[m] : INFINITY;  // absent / NaN model
+      s32m[((size_t)a * 4 + m) * R + j] = s;
       if (s < best) best = s;
     }
     s32[(size_t)a * R + j] = best;
@@ -282,11 +318,12 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_rounds(const float4* __
 
 // Arbitrary models x one pair.  grid.x = ceil(M / (4 * kScoreThreads)), grid.y = correspondence chunks.
 // part_score / part_cnt: [chunk][M]
-__global__ void __launch_bounds__(kScoreThreads) k_score_models(const float4* __restrict__ u4, const float4* __restrict__ v4,
+template <bool UNITZ>
+__global__ void __launch_bounds__(kScoreThreads) k_score_models(const float4* __restrict__ pa, const float4* __restrict__ pb,
                                                                 long long n, int chunk, const double* __restrict__ models6,
                                                                 int M, float thr, float* __restrict__ part_score,
                                                                 int* __restrict__ part_cnt) {
-  __shared__ __align__(128) ScoreSmem sm;
+  __shared__ __align__(128) ScoreSmem<UNITZ> sm;
   const int m0 = (blockIdx.x * kScoreThreads + threadIdx.x) * 4;
   float p[4][6];
 #pragma unroll
@@ -297,7 +334,8 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_models(const float4* __
   int cnt[4] = {0, 0, 0, 0};
   const long long c0 = (long long)blockIdx.y * chunk;
   const long long c1 = (c0 + chunk) < n ? (c0 + chunk) : n;
-  score_stream<true>(sm, u4, v4, c0, c1, p, thr, acc, cnt);
+  const bool warp_live = (int)((blockIdx.x * kScoreThreads + (threadIdx.x & ~31u)) * 4) < M;
+  score_stream<UNITZ, true>(sm, pa, pb, c0, c1, p, thr, warp_live, acc, cnt);
 #pragma unroll
   for (int m = 0; m < 4; ++m)
     if (m0 + m < M) {
@@ -321,63 +359,147 @@ __global__ void k_reduce_parts(const float* __restrict__ part_score, const int* 
 }
 
 // ------------------------------------------------------------------------------------------
-// k_chain: one warp per active pair.
+// k_chain: one warp per listed pair.
+//   DEFER = false: everything inline (used when num_lo_steps > 0: RansacLib's full LO schedule).
+//   DEFER = true : refits are parked as tasks (see ssfm_chain.cuh); the host alternates
+//                  k_chain<true> / k_refit_small + k_refit_big until no pair of the round is parked.
+// list addressing: mode 0 = list[w]; mode 1 = the parked list of the previous wave: small tasks were
+// appended from the front (list[0..n_front)), big ones from the back (list[cap-1-k]).
 // ------------------------------------------------------------------------------------------
 constexpr int kChainWarps = 4;
+constexpr int kSmallRefit = 32;  // refits with at most this many residuals get one thread each
 
-__global__ void __launch_bounds__(kChainWarps * 32) k_chain(Params P, const double* __restrict__ rays,
-                                                             const long long* __restrict__ offsets, int pair0,
-                                                             const int* __restrict__ active, int nactive,
-                                                             int* __restrict__ navail, PairState* states, int R,
-                                                             const double* __restrict__ models, const float* __restrict__ s32,
-                                                             int* list_a, int* list_b, uint32_t* mt, long long list_base,
-                                                             unsigned char* flags, SsfmPairResult* results,
-                                                             int* __restrict__ next_active, int* next_count, int next_cap,
-                                                             unsigned long long* counters) {
+struct ChainArgs {
+  const double* rays;
+  const long long* offsets;
+  int pair0;
+  const int* list;
+  int nlist, mode, n_front, cap;
+  int* navail;
+  PairState* states;
+  int R;
+  const double* models;
+  const float* s32;
+  const float* s32m;
+  int* list_a;
+  int* list_b;
+  uint32_t* mt;
+  double* lm_E;
+  long long list_base;
+  unsigned char* flags;
+  SsfmPairResult* results;
+  int* next_active;
+  int* next_count;
+  int next_cap;
+  int* parked;        // output task list (front: small, back: big)
+  int* parked_small;  // counters
+  int* parked_big;
+  unsigned long long* counters;
+};
+
+template <bool DEFER>
+__global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Params P, ChainArgs A) {
   const int w = blockIdx.x * kChainWarps + (threadIdx.x >> 5);
-  if (w >= nactive) return;
+  if (w >= A.nlist) return;
   WarpCtx cx{(int)(threadIdx.x & 31)};
-  const int a = active[w];
-  const int pair = pair0 + a;
-  const long long off = offsets[pair];
-  const int n = (int)(offsets[pair + 1] - off);
-  PairView pv{rays + 6 * off, n};
-  Scratch sc{list_a + (off - list_base), list_b + (off - list_base), mt + (size_t)a * 625};
-  PairState st = states[a];
-  const int na = navail[a];
-  const uint32_t it_before = st.it;
-  process_round(cx, P, pv, sc, st, models + (size_t)a * 24 * R, R, s32 + (size_t)a * R, na);
-  uint32_t want = iterations_wanted(P, st);
-  if (!st.done && want == 0) st.done = 1;
-  if (cx.lane() == 0) {
-    // accounting: look-ahead hypotheses executed this round vs. the ones the reference loop used
-    atomicAdd(&counters[0], (unsigned long long)na * 4ull * (unsigned long long)n);
-    (void)it_before;
+  const int a = A.mode == 0 ? A.list[w] : (w < A.n_front ? A.list[w] : A.list[A.cap - 1 - (w - A.n_front)]);
+  const int pair = A.pair0 + a;
+  const long long off = A.offsets[pair];
+  const int n = (int)(A.offsets[pair + 1] - off);
+  PairView pv{A.rays + 6 * off, n};
+  Scratch sc{A.list_a + (off - A.list_base), A.list_b + (off - A.list_base), A.mt + (size_t)a * 625, A.counters,
+             A.lm_E + (size_t)a * 9};
+#if defined(SSFM_PROFILE_CHAIN)
+  const long long t_start = clock64();
+#endif
+  PairState st = A.states[a];
+  const int na = A.navail[a];
+  const bool fresh = st.phase == PHASE_NONE;  // first visit of this pair in this round
+  bool parked = false;
+  if (!(DEFER && (st.phase == PHASE_LO_LATE || st.phase == PHASE_FINAL_LSQ))) {  // those resume inside finalize_pair
+    process_round<WarpCtx, DEFER>(cx, P, pv, sc, st, A.models + (size_t)a * 24 * A.R, A.R, A.s32 + (size_t)a * A.R,
+                                  A.s32m + (size_t)a * 4 * A.R, na);
+    parked = DEFER && st.phase != PHASE_NONE;
   }
-  if (st.done) {
-    double r[3], t[3];
-    const int status = finalize_pair(cx, P, pv, sc, st, r, t, flags ? flags + (off - list_base) : (unsigned char*)0);
-    if (cx.lane() == 0) {
-      SsfmPairResult& o = results[a];
-      for (int i = 0; i < 9; ++i) o.E[i] = st.E_best[i];
-      for (int i = 0; i < 3; ++i) { o.r[i] = r[i]; o.t[i] = t[i]; }
-      o.best_model_score = st.best_model_score;
-      o.inlier_ratio = st.inlier_ratio;
-      o.num_iterations = st.it;
-      o.best_num_inliers = st.best_num_inliers;
-      o.number_lo_iterations = st.num_lo;
-      o.status = status;
-      o.evals = (long long)st.it * 4ll * (long long)n;
-      atomicAdd(&counters[1], (unsigned long long)st.evals_exact);
-      navail[a] = 0;
-      states[a] = st;
+  if (fresh && cx.lane() == 0) atomicAdd(&A.counters[0], (unsigned long long)na * 4ull * (unsigned long long)n);
+  uint32_t want = 0;
+  if (!parked) {
+    want = iterations_wanted(P, st);
+    if (!st.done && want == 0) st.done = 1;
+    if (st.done) {
+      double r[3], t[3];
+      const int status = finalize_pair<WarpCtx, DEFER>(cx, P, pv, sc, st, r, t, A.flags ? A.flags + (off - A.list_base) : (unsigned char*)0);
+      if (status < 0) {
+        parked = true;
+      } else if (cx.lane() == 0) {
+        SsfmPairResult& o = A.results[a];
+        for (int i = 0; i < 9; ++i) o.E[i] = st.E_best[i];
+        for (int i = 0; i < 3; ++i) { o.r[i] = r[i]; o.t[i] = t[i]; }
+        o.best_model_score = st.best_model_score;
+        o.inlier_ratio = st.inlier_ratio;
+        o.num_iterations = st.it;
+        o.best_num_inliers = st.best_num_inliers;
+        o.number_lo_iterations = st.num_lo;
+        o.status = status;
+        o.evals = (long long)st.it * 4ll * (long long)n;
+        atomicAdd(&A.counters[1], (unsigned long long)st.evals_exact);
+        A.navail[a] = 0;
+      }
     }
-  } else if (cx.lane() == 0) {
-    states[a] = st;
-    navail[a] = (int)(want < (uint32_t)next_cap ? want : (uint32_t)next_cap);
-    const int pos = atomicAdd(next_count, 1);
-    next_active[pos] = a;
   }
+  if (cx.lane() == 0) {
+    A.states[a] = st;
+    if (parked) {
+      if (st.lm_n <= kSmallRefit) A.parked[atomicAdd(A.parked_small, 1)] = a;
+      else A.parked[A.cap - 1 - atomicAdd(A.parked_big, 1)] = a;
+    } else if (!st.done) {
+      A.navail[a] = (int)(want < (uint32_t)A.next_cap ? want : (uint32_t)A.next_cap);
+      A.next_active[atomicAdd(A.next_count, 1)] = a;
+    }
+#if defined(SSFM_PROFILE_CHAIN)
+    atomicAdd(&A.counters[PH_TOTAL], (unsigned long long)(clock64() - t_start));
+#endif
+  }
+}
+
+// Parked refits, SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157).
+// small: one THREAD per refit (<= kSmallRefit residuals), 32 independent LMs per warp.
+__global__ void __launch_bounds__(64) k_refit_small(Params P, const double* __restrict__ rays,
+                                                    const long long* __restrict__ offsets, int pair0,
+                                                    const int* __restrict__ parked, int ntasks,
+                                                    const PairState* __restrict__ states, const int* __restrict__ list_a,
+                                                    long long list_base, double* lm_E) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ntasks) return;
+  const int a = parked[t];
+  const long long off = offsets[pair0 + a];
+  SerialCtx cx;
+  double E[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) E[i] = lm_E[(size_t)a * 9 + i];
+  least_squares(cx, rays + 6 * off, list_a + (off - list_base), states[a].lm_n, P.inward != 0, E);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
+}
+// big: one WARP per refit (the final least squares over all inliers).
+__global__ void __launch_bounds__(128) k_refit_big(Params P, const double* __restrict__ rays,
+                                                   const long long* __restrict__ offsets, int pair0,
+                                                   const int* __restrict__ parked, int cap, int ntasks,
+                                                   const PairState* __restrict__ states, const int* __restrict__ list_a,
+                                                   long long list_base, double* lm_E) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= ntasks) return;
+  WarpCtx cx{(int)(threadIdx.x & 31)};
+  const int a = parked[cap - 1 - w];
+  const long long off = offsets[pair0 + a];
+  double E[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) E[i] = lm_E[(size_t)a * 9 + i];
+  cx.sync();
+  least_squares(cx, rays + 6 * off, list_a + (off - list_base), states[a].lm_n, P.inward != 0, E);
+  if (cx.lane() == 0)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
 }
 
 // Pairs that are finished before any round (n < 3): write their records.
@@ -438,8 +560,8 @@ __global__ void k_score_exact(const double* __restrict__ E9, int M, const double
   long long ev = 0;
   double E[9];
   for (int i = 0; i < 9; ++i) E[i] = E9[(size_t)w * 9 + i];
-  const double s = msac_score_exact(cx, E, rays, n, thr, &ev);
-  const int c = collect_inliers(cx, E, rays, n, thr, false, (int*)0, (unsigned char*)0, &ev);
+  int c = 0;
+  const double s = msac_score_exact(cx, E, rays, n, thr, &c, &ev);
   if (cx.lane() == 0) { scores[w] = s; counts[w] = c; }
 }
 
@@ -487,7 +609,7 @@ __global__ void k_lo_shuffle(uint32_t seed, int ncalls, const int* __restrict__ 
   for (int c = 0; c < ncalls; ++c) {
     for (int i = cx.lane(); i < sizes[c]; i += 32) work[i] = i;
     cx.sync();
-    shuffle_and_resize(cx, mt, work, sizes[c]);
+    shuffle_and_resize(cx, mt, work, sizes[c], targets[c]);
     for (int i = cx.lane(); i < targets[c]; i += 32) out[o + i] = work[i];
     cx.sync();
     o += targets[c];

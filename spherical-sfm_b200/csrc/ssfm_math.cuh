@@ -848,9 +848,12 @@ SSFM_HD double jval(const Jet6& x) { return x.a; }
 SSFM_HD double jlift(double x, double*) { return x; }
 SSFM_HD Jet6 jlift(double x, Jet6*) { return jconst(x); }
 
-// residual = squared Sampson value of E = [t]x R with R = exp(r1), t = -R t0 + t1.
+// E = [t]x R with R = exp(r1) (ceres::AngleAxisToRotationMatrix), t = -R t0 + t1, t0 = (0,0,t0z): the
+// model part of the reference's SampsonError functor (src/spherical_estimator.cpp:34-53).  It does not
+// depend on the correspondence, so the refit evaluates it ONCE per LM iteration (as jets: E[i].a is
+// the matrix, E[i].v[k] its derivative w.r.t. parameter k) instead of once per residual.
 template <typename T>
-SSFM_HD T sampson_residual(const T* r1, const T* t1, double t0z, const double* u, const double* v) {
+SSFM_HD void spherical_E_of_params(const T* r1, const T* t1, double t0z, T* E) {
   T R[9];
   const T theta2 = r1[0] * r1[0] + r1[1] * r1[1] + r1[2] * r1[2];
   const T one = jlift(1.0, (T*)0);
@@ -874,24 +877,51 @@ SSFM_HD T sampson_residual(const T* r1, const T* t1, double t0z, const double* u
     R[1] = -r1[2]; R[4] = one; R[7] = r1[0];
     R[2] = r1[1]; R[5] = -r1[0]; R[8] = one;
   }
-  // t = R * (-t0) + t1 with t0 = (0, 0, t0z)
   T t[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) t[i] = R[3 * i + 2] * (-t0z) + t1[i];
-  T E[9];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     E[0 + j] = t[1] * R[6 + j] - t[2] * R[3 + j];
     E[3 + j] = t[2] * R[0 + j] - t[0] * R[6 + j];
     E[6 + j] = t[0] * R[3 + j] - t[1] * R[0 + j];
   }
-  const T Eu0 = E[0] * u[0] + E[1] * u[1] + E[2] * u[2];
-  const T Eu1 = E[3] * u[0] + E[4] * u[1] + E[5] * u[2];
-  const T Eu2 = E[6] * u[0] + E[7] * u[1] + E[8] * u[2];
-  const T Etv0 = E[0] * v[0] + E[3] * v[1] + E[6] * v[2];
-  const T Etv1 = E[1] * v[0] + E[4] * v[1] + E[7] * v[2];
-  const T d = Eu0 * v[0] + Eu1 * v[1] + Eu2 * v[2];
-  return (d * d) / (Eu0 * Eu0 + Eu1 * Eu1 + Etv0 * Etv0 + Etv1 * Etv1);
+}
+
+// residual r = d^2 / den of one correspondence (value only)
+SSFM_HD double sampson_value(const double* E, const double* u, const double* v) {
+  const double Eu0 = E[0] * u[0] + E[1] * u[1] + E[2] * u[2];
+  const double Eu1 = E[3] * u[0] + E[4] * u[1] + E[5] * u[2];
+  const double Eu2 = E[6] * u[0] + E[7] * u[1] + E[8] * u[2];
+  const double Et0 = E[0] * v[0] + E[3] * v[1] + E[6] * v[2];
+  const double Et1 = E[1] * v[0] + E[4] * v[1] + E[7] * v[2];
+  const double d = Eu0 * v[0] + Eu1 * v[1] + Eu2 * v[2];
+  return (d * d) / (Eu0 * Eu0 + Eu1 * Eu1 + Et0 * Et0 + Et1 * Et1);
+}
+
+// residual and its gradient w.r.t. the 6 parameters, given E as jets (chain rule of the same
+// expression tree the reference autodiffs, src/spherical_estimator.cpp:55-61).
+SSFM_HD void sampson_value_grad(const Jet6* E, const double* u, const double* v, double& r, double* g) {
+  const double Eu0 = E[0].a * u[0] + E[1].a * u[1] + E[2].a * u[2];
+  const double Eu1 = E[3].a * u[0] + E[4].a * u[1] + E[5].a * u[2];
+  const double Eu2 = E[6].a * u[0] + E[7].a * u[1] + E[8].a * u[2];
+  const double Et0 = E[0].a * v[0] + E[3].a * v[1] + E[6].a * v[2];
+  const double Et1 = E[1].a * v[0] + E[4].a * v[1] + E[7].a * v[2];
+  const double d = Eu0 * v[0] + Eu1 * v[1] + Eu2 * v[2];
+  const double den = Eu0 * Eu0 + Eu1 * Eu1 + Et0 * Et0 + Et1 * Et1;
+  const double inv = 1.0 / den;
+  r = (d * d) * inv;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double dEu0 = E[0].v[k] * u[0] + E[1].v[k] * u[1] + E[2].v[k] * u[2];
+    const double dEu1 = E[3].v[k] * u[0] + E[4].v[k] * u[1] + E[5].v[k] * u[2];
+    const double dEu2 = E[6].v[k] * u[0] + E[7].v[k] * u[1] + E[8].v[k] * u[2];
+    const double dEt0 = E[0].v[k] * v[0] + E[3].v[k] * v[1] + E[6].v[k] * v[2];
+    const double dEt1 = E[1].v[k] * v[0] + E[4].v[k] * v[1] + E[7].v[k] * v[2];
+    const double dd = dEu0 * v[0] + dEu1 * v[1] + dEu2 * v[2];
+    const double dden = 2.0 * (Eu0 * dEu0 + Eu1 * dEu1 + Et0 * dEt0 + Et1 * dEt1);
+    g[k] = (2.0 * d * dd - r * dden) * inv;
+  }
 }
 
 // 6x6 SPD solve (DENSE_NORMAL_CHOLESKY, src/spherical_estimator.cpp:148).  H is the lower

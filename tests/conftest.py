@@ -78,7 +78,7 @@ class HsParams(C.Structure):
                 ('num_lsq_iters', C.c_int32), ('min_sample_mult', C.c_int32), ('non_min_mult', C.c_int32),
                 ('lo_start', C.c_uint32), ('final_lsq', C.c_int32), ('solver', C.c_int32), ('driver', C.c_int32),
                 ('inward', C.c_int32), ('fixed_budget', C.c_int32), ('fixed_prob', C.c_double),
-                ('cand_margin', C.c_float), ('first_round', C.c_int32), ('round_cap', C.c_int32)]
+                ('cand_margin', C.c_float), ('first_round', C.c_int32), ('round_cap', C.c_int32), ('defer', C.c_int32)]
 
 
 class HsResult(C.Structure):
@@ -112,14 +112,14 @@ class HostShim:
         nm = self.lib.hs_solve(self.dp(rays), self.ip(s), kind, self.dp(models))
         return nm, models
 
-    def estimate_pair(self, rays, opt, pair_id, margin=2e-3, first=128, cap=256):
+    def estimate_pair(self, rays, opt, pair_id, margin=2e-4, first=128, cap=256, defer=1):
         rays = np.ascontiguousarray(rays, np.float64)
         n = len(rays)
         hp = HsParams(opt.min_num_iterations, opt.max_num_iterations, opt.success_probability,
                       opt.squared_inlier_threshold, opt.random_seed, opt.num_lo_steps, opt.threshold_multiplier,
                       opt.num_lsq_iterations, opt.min_sample_multiplicator, opt.non_min_sample_multiplier,
                       opt.lo_starting_iterations, opt.final_least_squares, opt.solver_kind, opt.driver, opt.inward,
-                      opt.legacy_budget, opt.legacy_prob_success, margin, first, cap)
+                      opt.legacy_budget, opt.legacy_prob_success, margin, first, cap, defer)
         res = HsResult()
         flags = np.zeros(max(n, 1), np.uint8)
         self.lib.hs_estimate_pair(self.dp(rays), n, C.byref(hp), C.c_uint32(pair_id), C.byref(res),

@@ -13,7 +13,7 @@ using namespace ssfm;
 
 namespace {
 // plain-float emulation of the FP32 scoring kernel's per-iteration output
-float score_iteration_f32(const double* models4x6, const double* rays, int n, float thr) {
+float score_iteration_f32(const double* models4x6, const double* rays, int n, float thr, float* per_model) {
   float best = INFINITY;
   for (int m = 0; m < 4; ++m) {
     float p[6];
@@ -31,6 +31,8 @@ float score_iteration_f32(const double* models4x6, const double* rays, int n, fl
       const float e = d * d / (Eu0 * Eu0 + Eu1 * Eu1 + Etv0 * Etv0 + Etv1 * Etv1);
       acc += fminf(e, thr);
     }
+    if (!(models4x6[6 * m] == models4x6[6 * m])) acc = INFINITY;
+    per_model[m] = acc;
     if (acc < best) best = acc;
   }
   return best;
@@ -51,6 +53,7 @@ struct HsParams {
   double fixed_prob;
   float cand_margin;
   int32_t first_round, round_cap;
+  int32_t defer;  // 1: use the deferred-refit protocol (requires num_lo_steps == 0)
 };
 
 struct HsResult {
@@ -104,7 +107,7 @@ void hs_lo_shuffle(uint32_t seed, int ncalls, const int* sizes, const int* targe
   for (int c = 0; c < ncalls; ++c) {
     std::vector<int> v(sizes[c]);
     for (int i = 0; i < sizes[c]; ++i) v[i] = i;
-    shuffle_and_resize(cx, mt.data(), v.data(), sizes[c]);
+    shuffle_and_resize(cx, mt.data(), v.data(), sizes[c], targets[c]);
     for (int i = 0; i < targets[c]; ++i) out[o++] = v[i];
   }
 }
@@ -129,12 +132,14 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
   std::vector<int> la(n + 16), lb(n + 16);
   std::vector<uint32_t> mt(625);
   mt19937_seed(mt.data(), P.seed);
-  Scratch sc{la.data(), lb.data(), mt.data()};
+  double lmE[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  Scratch sc{la.data(), lb.data(), mt.data(), nullptr, lmE};
+  const bool defer = hp->defer != 0 && P.num_lo_steps == 0;
   PairView pv{rays, n};
   SerialCtx cx;
   int rounds = 0, candidates = 0;
   std::vector<double> models;
-  std::vector<float> s32;
+  std::vector<float> s32, s32m;
   while (!st.done) {
     const uint32_t want = iterations_wanted(P, st);
     if (want == 0) { st.done = 1; break; }
@@ -142,6 +147,7 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
     const int na = (int)(want < (uint32_t)cap ? want : (uint32_t)cap);
     models.assign((size_t)na * 24, 0.0);
     s32.assign(na, 0.f);
+    s32m.assign((size_t)na * 4, 0.f);
     for (int j = 0; j < na; ++j) {
       int idx[3];
       philox_sample<3>(P.seed, pair_id, st.it + j, 3, n, idx);
@@ -153,14 +159,32 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
       else if (P.solver == 1) solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
       else solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
       for (int k = 0; k < 24; ++k) models[(size_t)k * na + j] = (&m[0][0])[k];
-      s32[j] = score_iteration_f32(&m[0][0], rays, n, (float)P.thr2);
+      float pm[4];
+      s32[j] = score_iteration_f32(&m[0][0], rays, n, (float)P.thr2, pm);
+      for (int k = 0; k < 4; ++k) s32m[(size_t)k * na + j] = pm[k];
     }
     const long long before = st.evals_exact;
-    process_round(cx, P, pv, sc, st, models.data(), na, s32.data(), na);
+    if (defer) {
+      for (;;) {
+        process_round<SerialCtx, true>(cx, P, pv, sc, st, models.data(), na, s32.data(), s32m.data(), na);
+        if (st.phase == PHASE_NONE) break;
+        least_squares(cx, rays, sc.list_a, st.lm_n, P.inward != 0, sc.lm_E);  // what the refit kernel does
+      }
+    } else {
+      process_round<SerialCtx, false>(cx, P, pv, sc, st, models.data(), na, s32.data(), s32m.data(), na);
+    }
     candidates += (int)((st.evals_exact - before) / (n > 0 ? n : 1));
     ++rounds;
   }
-  out->status = finalize_pair(cx, P, pv, sc, st, out->r, out->t, flags);
+  if (defer) {
+    for (;;) {
+      out->status = finalize_pair<SerialCtx, true>(cx, P, pv, sc, st, out->r, out->t, flags);
+      if (out->status >= 0) break;
+      least_squares(cx, rays, sc.list_a, st.lm_n, P.inward != 0, sc.lm_E);
+    }
+  } else {
+    out->status = finalize_pair<SerialCtx, false>(cx, P, pv, sc, st, out->r, out->t, flags);
+  }
   std::memcpy(out->E, st.E_best, sizeof(st.E_best));
   out->best_model_score = st.best_model_score;
   out->inlier_ratio = st.inlier_ratio;

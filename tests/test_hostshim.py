@@ -136,7 +136,7 @@ def test_chain_logic_reproduces_reference_loop(S, O, orc, shim, name, kw, n, out
     for p in range(trials):
         pr = S.problems.make_problem(S.problems.make_rng(7, p), n, inward, None, 1 / 600, int(outl * n), 20.0)
         a, ia = orc.estimate_pair(pr.rays, opt, p)
-        res, fl = shim.estimate_pair(pr.rays, opt, p)
+        res, fl = shim.estimate_pair(pr.rays, opt, p, defer=p % 2)  # both the inline and the deferred-refit protocol
         fa = np.zeros(n, np.uint8)
         fa[ia] = 1
         assert a.status == res.status
