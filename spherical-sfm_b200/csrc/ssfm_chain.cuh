@@ -128,32 +128,76 @@ SSFM_HD_NOINLINE int collect_inliers(const Ctx& cx, const double* E, const doubl
   return count;
 }
 
+// mt19937 state regeneration, collectively: 32 elements at a time, reads before writes, which
+// preserves the in-place sequential recurrence (element i needs old i, old i+1 and element
+// (i+397) mod 624, which is old for i < 227 and already regenerated otherwise).
+template <class Ctx>
+SSFM_HD void mt_twist_ctx(const Ctx& cx, uint32_t* mt) {
+  if (cx.width() == 1) {
+    mt19937_twist(mt);
+    return;
+  }
+  for (int base = 0; base < 624; base += 32) {
+    const int i = base + cx.lane();
+    uint32_t v = 0;
+    if (i < 624) {
+      const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+      v = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    cx.sync();
+    if (i < 624) mt[i] = v;
+    cx.sync();
+  }
+}
+SSFM_HD uint32_t mt_temper(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y;
+}
+
 // RandomShuffleAndResize (include/RansacLib/utils.h:34-52) with the LO generator: Fisher-Yates over all
 // n entries, then truncation to `keep`.  Swaps at positions i >= keep only touch entries that are
-// thrown away, so only the first `keep` swaps are materialised (one lane, serial -- they are data
-// dependent); the remaining n-1-keep draws are just CONSUMED so that the generator ends in exactly
-// the state the reference's would: lanes test 32 draws at a time for Lemire's rejection condition
-// (probability ~range/2^32 each) and fall back to the serial walk for a chunk only if one triggers.
+// thrown away, so only the first `keep` swaps are materialised (every lane computes the same draw,
+// lane 0 swaps); the remaining n-1-keep draws are just CONSUMED so that the generator ends in
+// exactly the state the reference's would: lanes test 32 draws at a time for Lemire's rejection
+// condition (probability ~range/2^32 each) and replay a chunk serially only if one triggers.
 template <class Ctx>
 SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list, int n, int keep) {
-  int i = 0;
-  if (cx.lane() == 0) {
-    const int lim = keep < n - 1 ? keep : n - 1;
-    for (; i < lim; ++i) {
-      const int j = uniform_int_libstdcxx(mt, i, n - 1);
+  if (n < 2) return;
+  uint32_t pos = mt[624];
+  const int lim = keep < n - 1 ? keep : n - 1;
+  // uniform_int_distribution<int>(i, n-1)(mt19937): libstdc++ (GCC >= 11), Lemire's method
+  auto draw = [&](int i) -> int {
+    const uint32_t range = (uint32_t)(n - 1 - i) + 1u;
+    uint64_t product;
+    for (;;) {
+      if (pos >= 624) {
+        mt_twist_ctx(cx, mt);
+        pos = 0;
+      }
+      product = (uint64_t)mt_temper(mt[pos++]) * (uint64_t)range;
+      const uint32_t low = (uint32_t)product;
+      if (low >= range) break;
+      if (low >= (0u - range) % range) break;
+    }
+    return i + (int)(uint32_t)(product >> 32);
+  };
+  for (int i = 0; i < lim; ++i) {
+    const int j = draw(i);
+    if (cx.lane() == 0) {
       const int tmp = list[i];
       list[i] = list[j];
       list[j] = tmp;
     }
   }
   cx.sync();
-  i = keep < n - 1 ? keep : (n - 1 > 0 ? n - 1 : 0);
+  int i = lim;
   const int W = cx.width();
   while (i < n - 1) {
-    uint32_t pos = mt[624];
     if (pos >= 624) {
-      if (cx.lane() == 0) mt19937_twist(mt);
-      cx.sync();
+      mt_twist_ctx(cx, mt);
       pos = 0;
     }
     int chunk = n - 1 - i;
@@ -163,172 +207,190 @@ SSFM_HD_NOINLINE void shuffle_and_resize(const Ctx& cx, uint32_t* mt, int* list,
     if (W > 1) {
       const int l = cx.lane();
       if (l < chunk) {
-        uint32_t y = mt[pos + l];
-        y ^= (y >> 11);
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= (y >> 18);
-        const uint32_t range = (uint32_t)(n - 1 - (i + l)) + 1u;  // hi - lo + 1 with lo = i + l, hi = n - 1
+        const uint32_t y = mt_temper(mt[pos + l]);
+        const uint32_t range = (uint32_t)(n - 1 - (i + l)) + 1u;
         const uint32_t low = (uint32_t)((uint64_t)y * (uint64_t)range);
         reject = low < range && low < ((0u - range) % range);
       }
     }
     if (W > 1 && cx.ballot(reject) == 0u) {
-      cx.sync();
-      if (cx.lane() == 0) mt[624] = pos + (uint32_t)chunk;
-      cx.sync();
-      i += chunk;
+      pos += (uint32_t)chunk;
     } else {
-      // serial walk over this chunk (always taken by the single-lane test context)
-      if (cx.lane() == 0)
-        for (int k = 0; k < chunk; ++k) (void)uniform_int_libstdcxx(mt, i + k, n - 1);
-      cx.sync();
-      i += chunk;
+      for (int k = 0; k < chunk; ++k) (void)draw(i + k);
     }
+    i += chunk;
   }
+  cx.sync();
+  if (cx.lane() == 0) mt[624] = pos;
+  cx.sync();
 }
 
 // SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157): Ceres 2.2 trust-region
 // LM (dense normal Cholesky, Jacobi scaling, default tolerances, <= 200 iterations) over the
 // residuals listed in `sample`; E is rebuilt from the optimised rotation only (:156).
+// Written as init / step / finish so that a kernel can interleave many refits per warp (a lane
+// that converges picks up the next task while its neighbours keep iterating).
+struct LMState {
+  double x[6], H[21], g[6], scale[6], diagonal[6];
+  double x_cost, gmax, radius, decrease_factor, t0z;
+  int iteration, invalid;
+  bool reuse_diagonal, have_scale;
+};
+
+// cost, gradient and J^T J at S.x with Jacobi scaling.  E(x) and dE/dx are uniform across the
+// context (computed once per call as jets); each residual then costs ~200 flops.
 template <class Ctx>
-SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int* sample, int n, bool inward, double* E) {
-  double x[6];
+SSFM_HD double lm_eval_jac(const Ctx& cx, const double* rays, const int* sample, int n, LMState& S) {
+  Jet6 Ej[9];
+  {
+    const Jet6 r1[3] = {jvar(S.x[0], 0), jvar(S.x[1], 1), jvar(S.x[2], 2)};
+    const Jet6 t1[3] = {jvar(S.x[3], 3), jvar(S.x[4], 4), jvar(S.x[5], 5)};
+    spherical_E_of_params<Jet6>(r1, t1, S.t0z, Ej);
+  }
+  double Hl[21], gl[6], c = 0.0;
+  for (int a = 0; a < 21; ++a) Hl[a] = 0.0;
+  for (int a = 0; a < 6; ++a) gl[a] = 0.0;
+  for (int i = cx.lane(); i < n; i += cx.width()) {
+    const double* ry = rays + 6 * (size_t)sample[i];
+    double r, jr[6];
+    sampson_value_grad(Ej, ry, ry + 3, r, jr);
+    c += r * r;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      gl[a] += jr[a] * r;
+#pragma unroll
+      for (int b = 0; b <= a; ++b) Hl[k++] += jr[a] * jr[b];
+    }
+  }
+  for (int a = 0; a < 21; ++a) S.H[a] = cx.sum(Hl[a]);
+  for (int a = 0; a < 6; ++a) S.g[a] = cx.sum(gl[a]);
+  c = cx.sum(c);
+  S.gmax = 0.0;
+  for (int a = 0; a < 6; ++a) S.gmax = fmax(S.gmax, fabs(S.g[a]));  // gradient of the UNSCALED problem
+  if (!S.have_scale) {
+    for (int a = 0; a < 6; ++a) S.scale[a] = 1.0 / (1.0 + sqrt(S.H[a * (a + 1) / 2 + a]));
+    S.have_scale = true;
+  }
+  int k = 0;
+  for (int a = 0; a < 6; ++a) {
+    S.g[a] *= S.scale[a];
+    for (int b = 0; b <= a; ++b) S.H[k++] *= S.scale[a] * S.scale[b];
+  }
+  return 0.5 * c;
+}
+template <class Ctx>
+SSFM_HD double lm_eval_cost(const Ctx& cx, const double* rays, const int* sample, int n, double t0z, const double* xx) {
+  double Ev[9];
+  spherical_E_of_params<double>(xx, xx + 3, t0z, Ev);
+  double c = 0.0;
+  for (int i = cx.lane(); i < n; i += cx.width()) {
+    const double* ry = rays + 6 * (size_t)sample[i];
+    const double r = sampson_value(Ev, ry, ry + 3);
+    c += r * r;
+  }
+  return 0.5 * cx.sum(c);
+}
+
+template <class Ctx>
+SSFM_HD_NOINLINE void lm_init(const Ctx& cx, const double* rays, const int* sample, int n, bool inward, const double* E,
+                              LMState& S) {
   {
     double r[3], t[3];
     decompose_spherical_E(E, inward, r, t);
-    x[0] = r[0]; x[1] = r[1]; x[2] = r[2];
-    x[3] = 0.0; x[4] = 0.0; x[5] = inward ? 1.0 : -1.0;
+    S.x[0] = r[0]; S.x[1] = r[1]; S.x[2] = r[2];
+    S.x[3] = 0.0; S.x[4] = 0.0; S.x[5] = inward ? 1.0 : -1.0;
   }
-  const double t0z = inward ? 1.0 : -1.0;
-  double H[21], g[6], scale[6], diagonal[6];
-  double x_cost = 0.0, gmax = 0.0;
-  bool have_scale = false;
+  S.t0z = inward ? 1.0 : -1.0;
+  S.have_scale = false;
+  S.radius = 1e4;
+  S.decrease_factor = 2.0;
+  S.reuse_diagonal = false;
+  S.invalid = 0;
+  S.iteration = 0;
+  S.x_cost = lm_eval_jac(cx, rays, sample, n, S);
+}
 
-  // evaluate cost, gradient and J^T J at x, apply Jacobi scaling.  E(x) and dE/dx are uniform
-  // across the warp (computed once per call as jets); each residual then costs ~200 flops.
-  auto eval_jac = [&](const double* xx) {
-    Jet6 Ej[9];
-    {
-      const Jet6 r1[3] = {jvar(xx[0], 0), jvar(xx[1], 1), jvar(xx[2], 2)};
-      const Jet6 t1[3] = {jvar(xx[3], 3), jvar(xx[4], 4), jvar(xx[5], 5)};
-      spherical_E_of_params<Jet6>(r1, t1, t0z, Ej);
-    }
-    double Hl[21], gl[6], c = 0.0;
-    for (int a = 0; a < 21; ++a) Hl[a] = 0.0;
-    for (int a = 0; a < 6; ++a) gl[a] = 0.0;
-    for (int i = cx.lane(); i < n; i += cx.width()) {
-      const double* ry = rays + 6 * (size_t)sample[i];
-      double r, jr[6];
-      sampson_value_grad(Ej, ry, ry + 3, r, jr);
-      c += r * r;
-      int k = 0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        gl[a] += jr[a] * r;
-#pragma unroll
-        for (int b = 0; b <= a; ++b) Hl[k++] += jr[a] * jr[b];
-      }
-    }
-    for (int a = 0; a < 21; ++a) H[a] = cx.sum(Hl[a]);
-    for (int a = 0; a < 6; ++a) g[a] = cx.sum(gl[a]);
-    c = cx.sum(c);
-    gmax = 0.0;
-    for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(g[a]));  // gradient of the UNSCALED problem
-    if (!have_scale) {
-      for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(H[a * (a + 1) / 2 + a]));
-      have_scale = true;
-    }
+// One trust-region iteration.  Returns true when the minimiser terminates.
+template <class Ctx>
+SSFM_HD_NOINLINE bool lm_step(const Ctx& cx, const double* rays, const int* sample, int n, LMState& S) {
+  if (!isfinite(S.x_cost)) return true;
+  if (S.iteration >= 200) return true;
+  if (S.gmax <= 1e-10) return true;       // gradient tolerance
+  if (S.radius < 1e-32) return true;
+  ++S.iteration;
+  if (!S.reuse_diagonal)
+    for (int a = 0; a < 6; ++a) S.diagonal[a] = fmin(fmax(S.H[a * (a + 1) / 2 + a], 1e-6), 1e32);
+  double Hd[21], step[6];
+  for (int a = 0; a < 21; ++a) Hd[a] = S.H[a];
+  for (int a = 0; a < 6; ++a) Hd[a * (a + 1) / 2 + a] += S.diagonal[a] / S.radius;
+  bool valid = cholesky_solve6(Hd, S.g, step);
+  S.reuse_diagonal = true;
+  double model_cost_change = 0.0;
+  if (valid) {
+    // model_cost_change = -(J s).(r + J s / 2) = -(s.g + s^T H s / 2)
+    double sg = 0.0, sHs = 0.0;
     int k = 0;
     for (int a = 0; a < 6; ++a) {
-      g[a] *= scale[a];
-      for (int b = 0; b <= a; ++b) H[k++] *= scale[a] * scale[b];
+      step[a] = -step[a];
+      sg += step[a] * S.g[a];
     }
-    return 0.5 * c;
-  };
-  auto eval_cost = [&](const double* xx) {
-    double Ev[9];
-    spherical_E_of_params<double>(xx, xx + 3, t0z, Ev);
-    double c = 0.0;
-    for (int i = cx.lane(); i < n; i += cx.width()) {
-      const double* ry = rays + 6 * (size_t)sample[i];
-      const double r = sampson_value(Ev, ry, ry + 3);
-      c += r * r;
-    }
-    return 0.5 * cx.sum(c);
-  };
-
-  x_cost = eval_jac(x);
-  if (isfinite(x_cost)) {
-    double radius = 1e4, decrease_factor = 2.0;
-    bool reuse_diagonal = false;
-    int invalid = 0;
-    for (int iteration = 0;;) {
-      if (iteration >= 200) break;
-      if (gmax <= 1e-10) break;
-      if (radius < 1e-32) break;
-      ++iteration;
-      if (!reuse_diagonal)
-        for (int a = 0; a < 6; ++a) diagonal[a] = fmin(fmax(H[a * (a + 1) / 2 + a], 1e-6), 1e32);
-      double Hd[21], step[6];
-      for (int a = 0; a < 21; ++a) Hd[a] = H[a];
-      for (int a = 0; a < 6; ++a) Hd[a * (a + 1) / 2 + a] += diagonal[a] / radius;
-      bool valid = cholesky_solve6(Hd, g, step);
-      reuse_diagonal = true;
-      double model_cost_change = 0.0;
-      if (valid) {
-        // model_cost_change = -(J s).(r + J s / 2) = -(s.g + s^T H s / 2)
-        double sg = 0.0, sHs = 0.0;
-        int k = 0;
-        for (int a = 0; a < 6; ++a) {
-          step[a] = -step[a];
-          sg += step[a] * g[a];
-        }
-        for (int a = 0; a < 6; ++a)
-          for (int b = 0; b <= a; ++b) sHs += (a == b ? 1.0 : 2.0) * H[k++] * step[a] * step[b];
-        model_cost_change = -(sg + 0.5 * sHs);
-        if (!(model_cost_change > 0.0)) valid = false;
-      }
-      if (!valid) {
-        if (++invalid >= 10) break;
-        radius /= decrease_factor;
-        decrease_factor *= 2.0;
-        continue;
-      }
-      invalid = 0;
-      double cand[6], step_norm = 0.0, x_norm = 0.0;
-      for (int a = 0; a < 6; ++a) {
-        const double d = step[a] * scale[a];
-        cand[a] = x[a] + d;
-        step_norm += d * d;
-        x_norm += x[a] * x[a];
-      }
-      step_norm = sqrt(step_norm);
-      x_norm = sqrt(x_norm);
-      double cand_cost = eval_cost(cand);
-      if (!isfinite(cand_cost)) cand_cost = kDblMax;
-      if (step_norm <= 1e-8 * (x_norm + 1e-8)) break;               // parameter tolerance
-      const double cost_change = x_cost - cand_cost;
-      if (fabs(cost_change) <= 1e-6 * x_cost) break;                // function tolerance
-      const double rho = cost_change / model_cost_change;
-      if (rho > 1e-3) {
-        for (int a = 0; a < 6; ++a) x[a] = cand[a];
-        x_cost = eval_jac(x);
-        const double tt = 2.0 * rho - 1.0;
-        radius = radius / fmax(1.0 / 3.0, 1.0 - tt * tt * tt);
-        radius = fmin(1e16, radius);
-        decrease_factor = 2.0;
-        reuse_diagonal = false;
-      } else {
-        radius /= decrease_factor;
-        decrease_factor *= 2.0;
-        reuse_diagonal = true;
-      }
-    }
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b <= a; ++b) sHs += (a == b ? 1.0 : 2.0) * S.H[k++] * step[a] * step[b];
+    model_cost_change = -(sg + 0.5 * sHs);
+    if (!(model_cost_change > 0.0)) valid = false;
   }
+  if (!valid) {
+    if (++S.invalid >= 10) return true;
+    S.radius /= S.decrease_factor;
+    S.decrease_factor *= 2.0;
+    return false;
+  }
+  S.invalid = 0;
+  double cand[6], step_norm = 0.0, x_norm = 0.0;
+  for (int a = 0; a < 6; ++a) {
+    const double d = step[a] * S.scale[a];
+    cand[a] = S.x[a] + d;
+    step_norm += d * d;
+    x_norm += S.x[a] * S.x[a];
+  }
+  step_norm = sqrt(step_norm);
+  x_norm = sqrt(x_norm);
+  double cand_cost = lm_eval_cost(cx, rays, sample, n, S.t0z, cand);
+  if (!isfinite(cand_cost)) cand_cost = kDblMax;
+  if (step_norm <= 1e-8 * (x_norm + 1e-8)) return true;   // parameter tolerance
+  const double cost_change = S.x_cost - cand_cost;
+  if (fabs(cost_change) <= 1e-6 * S.x_cost) return true;  // function tolerance
+  const double rho = cost_change / model_cost_change;
+  if (rho > 1e-3) {
+    for (int a = 0; a < 6; ++a) S.x[a] = cand[a];
+    S.x_cost = lm_eval_jac(cx, rays, sample, n, S);
+    const double tt = 2.0 * rho - 1.0;
+    S.radius = S.radius / fmax(1.0 / 3.0, 1.0 - tt * tt * tt);
+    S.radius = fmin(1e16, S.radius);
+    S.decrease_factor = 2.0;
+    S.reuse_diagonal = false;
+  } else {
+    S.radius /= S.decrease_factor;
+    S.decrease_factor *= 2.0;
+    S.reuse_diagonal = true;
+  }
+  return false;
+}
+
+SSFM_HD void lm_finish(const LMState& S, bool inward, double* E) {
   double R[9];
-  so3exp(x, R);
+  so3exp(S.x, R);
   make_spherical_E(R, inward, E);
+}
+
+template <class Ctx>
+SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int* sample, int n, bool inward, double* E) {
+  LMState S;
+  lm_init(cx, rays, sample, n, inward, E, S);
+  while (!lm_step(cx, rays, sample, n, S)) {
+  }
+  lm_finish(S, inward, E);
 }
 
 struct Scratch {

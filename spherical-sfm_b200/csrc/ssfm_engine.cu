@@ -285,11 +285,11 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     first_cap = 32;
     round_cap = 64;
   } else {
-    first_cap = (int)std::min<uint32_t>(std::max<uint32_t>(P.min_iters, 32u), 1024u);
+    first_cap = (int)std::min<uint32_t>((std::max<uint32_t>(P.min_iters, 32u) + 31u) & ~31u, 1024u);
     round_cap = kRoundCap;
   }
-  if (const char* e = getenv("SSFM_ROUND_CAP")) round_cap = std::max(32, atoi(e));
-  if (const char* e = getenv("SSFM_FIRST_CAP")) first_cap = std::max(32, atoi(e));
+  if (const char* e = getenv("SSFM_ROUND_CAP")) round_cap = (std::max(32, atoi(e)) + 31) & ~31;
+  if (const char* e = getenv("SSFM_FIRST_CAP")) first_cap = (std::max(32, atoi(e)) + 31) & ~31;
   const int R = std::max(first_cap, round_cap);
   const bool defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
   const float thr32 = (float)P.thr2;
@@ -378,8 +378,11 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
             const int ns = h->h_count[4], nb = h->h_count[5];
             if (ns + nb == 0) break;
             if (ns > 0) {
-              k_refit_small<<<(ns + 63) / 64, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, h->states.p,
-                                                                  h->list_a.p, c0, h->lm_E.p);
+              // persistent lanes pulling from a queue: enough warps to fill the machine, not one per task
+              SSFM_CK(cudaMemsetAsync(h->counts.p + 6, 0, sizeof(int), h->stream));
+              const int blocks = std::min((ns + 63) / 64, h->num_sms * 8);
+              k_refit_small<<<blocks, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, h->counts.p + 6,
+                                                          h->states.p, h->list_a.p, c0, h->lm_E.p);
               launches += 1;
             }
             if (nb > 0) {

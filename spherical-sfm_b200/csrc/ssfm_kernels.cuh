@@ -78,6 +78,15 @@ struct WarpCtx {
   }
 };
 
+// Look-ahead of the next round: the iterations the pair still wants, rounded up to a whole warp of
+// scoring lanes (the extra lanes would idle otherwise; slots past max_iters are simply never consumed),
+// capped by the round size (a multiple of 32).
+__host__ __device__ inline int lookahead(uint32_t want, int cap) {
+  if (want == 0) return 0;
+  const uint32_t r = (want + 31u) & ~31u;
+  return (int)(r < (uint32_t)cap ? r : (uint32_t)cap);
+}
+
 // ------------------------------------------------------------------------------------------
 // k_pack
 // ------------------------------------------------------------------------------------------
@@ -109,7 +118,7 @@ __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, in
   if (want == 0) st.done = 1;
   states[a] = st;
   active[a] = a;
-  navail[a] = (int)(want < (uint32_t)first_cap ? want : (uint32_t)first_cap);
+  navail[a] = lookahead(want, first_cap);
   if (P.driver == 0) mt19937_seed(mt + (size_t)a * 625, P.seed);
 }
 
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Param
       if (st.lm_n <= kSmallRefit) A.parked[atomicAdd(A.parked_small, 1)] = a;
       else A.parked[A.cap - 1 - atomicAdd(A.parked_big, 1)] = a;
     } else if (!st.done) {
-      A.navail[a] = (int)(want < (uint32_t)A.next_cap ? want : (uint32_t)A.next_cap);
+      A.navail[a] = lookahead(want, A.next_cap);
       A.next_active[atomicAdd(A.next_count, 1)] = a;
     }
 #if defined(SSFM_PROFILE_CHAIN)
@@ -463,23 +472,46 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Param
 }
 
 // Parked refits, SphericalEstimator::LeastSquares (src/spherical_estimator.cpp:110-157).
-// small: one THREAD per refit (<= kSmallRefit residuals), 32 independent LMs per warp.
+// small: one THREAD per refit (<= kSmallRefit residuals), 32 independent LMs per warp.  Iteration
+// counts vary from ~6 to 200 between problems, so lanes pull tasks from a queue: a lane whose LM
+// terminates fetches the next task while its neighbours keep iterating.
 __global__ void __launch_bounds__(64) k_refit_small(Params P, const double* __restrict__ rays,
                                                     const long long* __restrict__ offsets, int pair0,
-                                                    const int* __restrict__ parked, int ntasks,
+                                                    const int* __restrict__ parked, int ntasks, int* queue_head,
                                                     const PairState* __restrict__ states, const int* __restrict__ list_a,
                                                     long long list_base, double* lm_E) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= ntasks) return;
-  const int a = parked[t];
-  const long long off = offsets[pair0 + a];
   SerialCtx cx;
-  double E[9];
+  const bool inward = P.inward != 0;
+  int task = ntasks, a = 0, n = 0;
+  bool have = false;
+  const double* ry = rays;
+  const int* smp = list_a;
+  LMState S;
+  for (;;) {
+    if (!have) {
+      task = atomicAdd(queue_head, 1);
+      if (task < ntasks) {
+        a = parked[task];
+        const long long off = offsets[pair0 + a];
+        ry = rays + 6 * off;
+        smp = list_a + (off - list_base);
+        n = states[a].lm_n;
+        double E[9];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) E[i] = lm_E[(size_t)a * 9 + i];
-  least_squares(cx, rays + 6 * off, list_a + (off - list_base), states[a].lm_n, P.inward != 0, E);
+        for (int i = 0; i < 9; ++i) E[i] = lm_E[(size_t)a * 9 + i];
+        lm_init(cx, ry, smp, n, inward, E, S);
+        have = true;
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have && lm_step(cx, ry, smp, n, S)) {
+      double E[9];
+      lm_finish(S, inward, E);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
+      for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
+      have = false;
+    }
+  }
 }
 // big: one WARP per refit (the final least squares over all inliers).
 __global__ void __launch_bounds__(128) k_refit_big(Params P, const double* __restrict__ rays,
