@@ -104,8 +104,8 @@ typedef struct SsfmPairResult {
 
 /* Device-side timing/accounting of the last ssfm_run (CUDA events on the engine's stream). */
 typedef struct SsfmRunStats {
-  double total_ms;
-  double pack_ms, solve_ms, score_ms, chain_ms;
+  double total_ms; /* host wall clock of ssfm_run (all streams drained) */
+  double pack_ms, solve_ms, score_ms, chain_ms; /* CUDA-event time on the launching streams */
   int32_t rounds;
   int32_t kernel_launches;
   int64_t evals_useful;   /* sum of SsfmPairResult.evals */
@@ -114,6 +114,7 @@ typedef struct SsfmRunStats {
   int64_t score_launches;
   int64_t h2d_bytes, d2h_bytes;
   int64_t refit_waves; /* walk/refit alternations of the deferred least-squares protocol */
+  int32_t workers;     /* concurrent streams the pair list was split over; stage times are summed over them */
 } SsfmRunStats;
 
 int ssfm_abi_version(void);

@@ -68,7 +68,7 @@ class SsfmRunStats(C.Structure):
         ("total_ms", C.c_double), ("pack_ms", C.c_double), ("solve_ms", C.c_double), ("score_ms", C.c_double),
         ("chain_ms", C.c_double), ("rounds", C.c_int32), ("kernel_launches", C.c_int32),
         ("evals_useful", C.c_int64), ("evals_executed", C.c_int64), ("evals_exact", C.c_int64),
-        ("score_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("refit_waves", C.c_int64),
+        ("score_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("refit_waves", C.c_int64), ("workers", C.c_int32),
     ]
 
 

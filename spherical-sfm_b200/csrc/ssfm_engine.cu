@@ -19,7 +19,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ssfm_kernels.cuh"
@@ -69,6 +71,7 @@ struct DevBuf {
 
 }  // namespace
 
+struct Worker;
 struct ssfm_engine {
   int device = 0;
   int num_sms = 0;
@@ -84,22 +87,49 @@ struct ssfm_engine {
   bool unit_z = false;
   DevBuf<long long> offsets;
   bool resident = false;
-  // run buffers
-  DevBuf<PairState> states;
-  DevBuf<uint32_t> mt;
-  DevBuf<int> active0, active1, navail, list_a, list_b, counts, parked0, parked1;
-  DevBuf<double> lm_E;
-  DevBuf<double> models;
-  DevBuf<float> s32, s32m;
-  DevBuf<unsigned long long> counters;
+  // run buffers live in the workers (one stream each; see ssfm_run)
+  DevBuf<int> counts;  // upload-time flags
   DevBuf<SsfmPairResult> results;
   DevBuf<unsigned char> flags;
+  struct Worker* workers = nullptr;
+  int num_workers = 0;
   bool have_results = false;
   SsfmRunStats stats = {};
   int* h_count = nullptr;  // pinned
 };
 
+// One worker = one stream + its own scratch.  ssfm_run splits the pair list between the workers and
+// drives them from separate host threads, so one worker's latency-bound FP64 chain/refit kernels
+// overlap the other worker's FP32-bound scoring kernel on the same GPU.
+struct Worker {
+  cudaStream_t stream = nullptr;     // sampling/solving and FP32 scoring (bulk, normal priority)
+  cudaStream_t stream_hi = nullptr;  // FP64 chain + refit waves (small latency-bound grids, high priority:
+                                     // they slip in between another worker's scoring CTAs)
+  cudaEvent_t ev[4] = {};
+  int* h_count = nullptr;  // pinned
+  DevBuf<PairState> states;
+  DevBuf<uint32_t> mt;
+  DevBuf<int> active0, active1, navail, list_a, list_b, counts, parked0, parked1;
+  DevBuf<double> models, lm_E;
+  DevBuf<float> s32, s32m;
+  DevBuf<unsigned long long> counters;
+  // outputs of the last run
+  double solve_ms = 0, score_ms = 0, chain_ms = 0;
+  int rounds = 0, launches = 0;
+  long long score_launches = 0, refit_waves = 0;
+  unsigned long long hc[32] = {};
+  int rc = SSFM_OK;
+  std::string err;
+  void release() {
+    states.release(); mt.release(); active0.release(); active1.release(); navail.release(); list_a.release();
+    list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
+    s32.release(); s32m.release(); counters.release();
+  }
+};
+
 namespace {
+
+constexpr int kMaxWorkers = 4;
 
 Params make_params(const SsfmOptions& o) {
   Params P;
@@ -137,10 +167,171 @@ int check_options(const SsfmOptions* o) {
 }
 
 template <int KIND>
-void launch_solve(ssfm_engine* h, const Params& P, int pair0, const int* active, int count, int cap, int R) {
+void launch_solve(ssfm_engine* h, Worker& w, const Params& P, int pair0, const int* active, int count, int cap, int R) {
   dim3 grid(count, (cap + 63) / 64);
-  k_sample_solve<KIND><<<grid, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, active, h->navail.p, h->states.p, R,
-                                                   h->models.p);
+  k_sample_solve<KIND><<<grid, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, active, w.navail.p, w.states.p, R,
+                                                  w.models.p);
+}
+
+struct RunCfg {
+  int first_cap, round_cap, R;
+  int small_refit_threads_min;  // waves with more small refits than this use one thread per refit
+  bool defer;
+  float thr32;
+};
+
+#define SSFM_WCK(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      w.err = std::string(#call) + ": " + cudaGetErrorString(e__);                             \
+      return e__ == cudaErrorMemoryAllocation ? SSFM_ERR_OOM : SSFM_ERR_CUDA;                  \
+    }                                                                                          \
+  } while (0)
+
+// All rounds for pairs [pbegin, pend) on worker w's stream.
+int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, int pbegin, int pend) {
+  SSFM_WCK(cudaSetDevice(h->device));
+  const int first_cap = cfg.first_cap, round_cap = cfg.round_cap, R = cfg.R;
+  const bool defer = cfg.defer;
+  const float thr32 = cfg.thr32;
+  w.solve_ms = w.score_ms = w.chain_ms = 0;
+  w.rounds = w.launches = 0;
+  w.score_launches = w.refit_waves = 0;
+  SSFM_WCK(w.counters.ensure(32));
+  SSFM_WCK(w.counts.ensure(8));
+  SSFM_WCK(cudaMemsetAsync(w.counters.p, 0, 32 * sizeof(unsigned long long), w.stream));
+  cudaEvent_t evA = w.ev[0], evB = w.ev[1], evC = w.ev[2], evD = w.ev[3];
+  int launches = 0;
+  for (int pair0 = pbegin; pair0 < pend; pair0 += kMaxPassPairs) {
+    const int np = std::min(kMaxPassPairs, pend - pair0);
+    const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
+    const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
+    SSFM_WCK(w.states.ensure(np));
+    SSFM_WCK(w.active0.ensure(np));
+    SSFM_WCK(w.active1.ensure(np));
+    SSFM_WCK(w.navail.ensure(np));
+    SSFM_WCK(w.models.ensure((size_t)np * 24 * R));
+    SSFM_WCK(w.s32.ensure((size_t)np * R));
+    SSFM_WCK(w.s32m.ensure((size_t)np * R * 4));
+    SSFM_WCK(w.list_a.ensure(mpass + 16));
+    SSFM_WCK(w.list_b.ensure(P.num_lo_steps > 0 ? mpass + 16 : 16));
+    SSFM_WCK(w.mt.ensure(P.driver == SSFM_DRIVER_LO_MSAC ? (size_t)np * 625 : 625));
+    SSFM_WCK(w.parked0.ensure(np));
+    SSFM_WCK(w.parked1.ensure(np));
+    SSFM_WCK(w.lm_E.ensure((size_t)np * 9));
+
+    k_init_pairs<<<(np + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, pair0, np, w.states.p, w.mt.p, w.active0.p,
+                                                         w.navail.p, first_cap);
+    SSFM_WCK(cudaMemsetAsync(w.counts.p, 0, 2 * sizeof(int), w.stream));
+    k_finish_trivial<<<(np + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, pair0, np, w.states.p, h->flags.p, 0,
+                                                             h->results.p + pair0, w.active0.p, w.counts.p);
+    launches += 2;
+    SSFM_WCK(cudaMemcpyAsync(w.h_count, w.counts.p, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+    SSFM_WCK(cudaStreamSynchronize(w.stream));
+    int count = w.h_count[0];
+    int* act = w.active0.p;
+    int* act_next = w.active1.p;
+    int round = 0;
+    while (count > 0) {
+      const int cap = round == 0 ? first_cap : round_cap;
+      SSFM_WCK(cudaEventRecord(evA, w.stream));
+      if (P.solver == 0) launch_solve<0>(h, w, P, pair0, act, count, cap, R);
+      else if (P.solver == 1) launch_solve<1>(h, w, P, pair0, act, count, cap, R);
+      else launch_solve<2>(h, w, P, pair0, act, count, cap, R);
+      SSFM_WCK(cudaGetLastError());
+      SSFM_WCK(cudaEventRecord(evB, w.stream));
+      {
+        dim3 grid(count, (cap + kScoreThreads - 1) / kScoreThreads);
+        if (h->unit_z)
+          k_score_rounds<true><<<grid, kScoreThreads, 0, w.stream>>>(h->uv4.p, nullptr, h->offsets.p, pair0, act, w.navail.p,
+                                                                     R, w.models.p, thr32, w.s32.p, w.s32m.p);
+        else
+          k_score_rounds<false><<<grid, kScoreThreads, 0, w.stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, w.navail.p,
+                                                                      R, w.models.p, thr32, w.s32.p, w.s32m.p);
+        SSFM_WCK(cudaGetLastError());
+      }
+      SSFM_WCK(cudaEventRecord(evC, w.stream));
+      cudaStream_t hs = w.stream_hi;  // everything below runs at high priority, after the scoring kernel
+      SSFM_WCK(cudaStreamWaitEvent(hs, evC, 0));
+      SSFM_WCK(cudaMemsetAsync(w.counts.p + 1, 0, sizeof(int), hs));
+      {
+        ChainArgs A;
+        A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = pair0;
+        A.navail = w.navail.p; A.states = w.states.p; A.R = R; A.models = w.models.p; A.s32 = w.s32.p; A.s32m = w.s32m.p;
+        A.list_a = w.list_a.p; A.list_b = w.list_b.p; A.mt = w.mt.p; A.lm_E = w.lm_E.p; A.list_base = c0;
+        A.flags = h->flags.p + c0; A.results = h->results.p + pair0; A.next_active = act_next; A.next_count = w.counts.p + 1;
+        A.next_cap = round_cap; A.parked_small = w.counts.p + 4; A.parked_big = w.counts.p + 5; A.counters = w.counters.p;
+        A.cap = np;
+        if (!defer) {
+          A.list = act; A.nlist = count; A.mode = 0; A.n_front = 0; A.parked = w.parked0.p;
+          k_chain<false><<<(count + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, hs>>>(P, A);
+          SSFM_WCK(cudaGetLastError());
+          launches += 1;
+        } else {
+          // waves: walk -> solve the parked refits -> resume, until no pair of this round is parked
+          const int* cur = act;
+          int ncur = count, mode = 0, nfront = 0;
+          int* out = w.parked0.p;
+          int* other = w.parked1.p;
+          for (int wave = 0;; ++wave) {
+            if (wave > R + 8) { w.err = "internal error: refit waves did not drain"; return SSFM_ERR_CUDA; }
+            SSFM_WCK(cudaMemsetAsync(w.counts.p + 4, 0, 2 * sizeof(int), hs));
+            A.list = cur; A.nlist = ncur; A.mode = mode; A.n_front = nfront; A.parked = out;
+            k_chain<true><<<(ncur + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, hs>>>(P, A);
+            SSFM_WCK(cudaGetLastError());
+            launches += 1;
+            SSFM_WCK(cudaMemcpyAsync(w.h_count + 4, w.counts.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, hs));
+            SSFM_WCK(cudaStreamSynchronize(hs));
+            const int ns = w.h_count[4], nb = w.h_count[5];
+            if (ns + nb == 0) break;
+            if (ns > cfg.small_refit_threads_min) {
+              // persistent lanes pulling from a queue: enough warps to fill the machine, not one per task
+              SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, sizeof(int), hs));
+              const int blocks = std::min((ns + 63) / 64, h->num_sms * 8);
+              k_refit_small<<<blocks, 64, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, w.counts.p + 6, w.states.p,
+                                                   w.list_a.p, c0, w.lm_E.p);
+              launches += 1;
+            } else if (ns > 0) {
+              // too few to fill the machine one thread each: one warp per refit (lower latency; this is tail)
+              k_refit_big<<<(ns + 3) / 4, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, ns, 1, w.states.p,
+                                                        w.list_a.p, c0, w.lm_E.p);
+              launches += 1;
+            }
+            if (nb > 0) {
+              k_refit_big<<<(nb + 3) / 4, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, nb, 0, w.states.p,
+                                                        w.list_a.p, c0, w.lm_E.p);
+              launches += 1;
+            }
+            SSFM_WCK(cudaGetLastError());
+            cur = out; ncur = ns + nb; mode = 1; nfront = ns;
+            std::swap(out, other);
+            w.refit_waves += 1;
+          }
+        }
+      }
+      SSFM_WCK(cudaEventRecord(evD, hs));
+      SSFM_WCK(cudaMemcpyAsync(w.h_count, w.counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, hs));
+      SSFM_WCK(cudaStreamSynchronize(hs));
+      float t1 = 0, t2 = 0, t3 = 0;
+      cudaEventElapsedTime(&t1, evA, evB);
+      cudaEventElapsedTime(&t2, evB, evC);
+      cudaEventElapsedTime(&t3, evC, evD);
+      w.solve_ms += t1;
+      w.score_ms += t2;
+      w.chain_ms += t3;
+      w.score_launches += 1;
+      launches += 2;
+      count = w.h_count[0];
+      std::swap(act, act_next);
+      ++round;
+    }
+    w.rounds += round;
+  }
+  SSFM_WCK(cudaMemcpyAsync(w.hc, w.counters.p, sizeof(w.hc), cudaMemcpyDeviceToHost, w.stream));
+  SSFM_WCK(cudaStreamSynchronize(w.stream));
+  w.launches = launches;
+  return SSFM_OK;
 }
 
 }  // namespace
@@ -194,6 +385,17 @@ int ssfm_create(int device, ssfm_handle* out) {
   SSFM_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) SSFM_CK(cudaEventCreate(&ev));
   SSFM_CK(cudaMallocHost(&h->h_count, 64));
+  h->num_workers = kMaxWorkers;
+  h->workers = new Worker[kMaxWorkers];
+  for (int k = 0; k < kMaxWorkers; ++k) {
+    Worker& w = h->workers[k];
+    int prio_lo = 0, prio_hi = 0;
+    SSFM_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SSFM_CK(cudaStreamCreateWithPriority(&w.stream, cudaStreamNonBlocking, prio_lo));
+    SSFM_CK(cudaStreamCreateWithPriority(&w.stream_hi, cudaStreamNonBlocking, prio_hi));
+    for (auto& ev : w.ev) SSFM_CK(cudaEventCreate(&ev));
+    SSFM_CK(cudaMallocHost(&w.h_count, 64));
+  }
   *out = h;
   return SSFM_OK;
 }
@@ -202,10 +404,19 @@ void ssfm_destroy(ssfm_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release(); h->s32m.release();
-  h->states.release(); h->mt.release(); h->active0.release(); h->active1.release(); h->navail.release();
-  h->list_a.release(); h->list_b.release(); h->counts.release(); h->models.release(); h->s32.release();
-  h->counters.release(); h->results.release(); h->flags.release(); h->parked0.release(); h->parked1.release(); h->lm_E.release();
+  h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release();
+  h->counts.release(); h->results.release(); h->flags.release();
+  for (int k = 0; k < h->num_workers; ++k) {
+    Worker& w = h->workers[k];
+    cudaStreamSynchronize(w.stream);
+    cudaStreamSynchronize(w.stream_hi);
+    w.release();
+    for (auto& ev : w.ev) cudaEventDestroy(ev);
+    if (w.h_count) cudaFreeHost(w.h_count);
+    cudaStreamDestroy(w.stream);
+    cudaStreamDestroy(w.stream_hi);
+  }
+  delete[] h->workers;
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   if (h->h_count) cudaFreeHost(h->h_count);
   cudaStreamDestroy(h->stream);
@@ -276,149 +487,58 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   h->have_results = false;
   SSFM_CK(h->results.ensure(std::max(h->P, 1)));
   SSFM_CK(h->flags.ensure((size_t)std::max<long long>(h->M, 1)));
-  SSFM_CK(h->counters.ensure(32));
-  SSFM_CK(h->counts.ensure(8));
-  SSFM_CK(cudaMemsetAsync(h->counters.p, 0, 32 * sizeof(unsigned long long), h->stream));
 
-  int first_cap, round_cap;
+  RunCfg cfg;
   if (P.driver == SSFM_DRIVER_MSAC_FIXED) {
-    first_cap = 32;
-    round_cap = 64;
+    cfg.first_cap = 32;
+    cfg.round_cap = 64;
   } else {
-    first_cap = (int)std::min<uint32_t>((std::max<uint32_t>(P.min_iters, 32u) + 31u) & ~31u, 1024u);
-    round_cap = kRoundCap;
+    cfg.first_cap = (int)std::min<uint32_t>((std::max<uint32_t>(P.min_iters, 32u) + 31u) & ~31u, 1024u);
+    cfg.round_cap = kRoundCap;
   }
-  if (const char* e = getenv("SSFM_ROUND_CAP")) round_cap = (std::max(32, atoi(e)) + 31) & ~31;
-  if (const char* e = getenv("SSFM_FIRST_CAP")) first_cap = (std::max(32, atoi(e)) + 31) & ~31;
-  const int R = std::max(first_cap, round_cap);
-  const bool defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
-  const float thr32 = (float)P.thr2;
+  if (const char* e = getenv("SSFM_ROUND_CAP")) cfg.round_cap = (std::max(32, atoi(e)) + 31) & ~31;
+  if (const char* e = getenv("SSFM_FIRST_CAP")) cfg.first_cap = (std::max(32, atoi(e)) + 31) & ~31;
+  cfg.R = std::max(cfg.first_cap, cfg.round_cap);
+  cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
+  cfg.thr32 = (float)P.thr2;
+  cfg.small_refit_threads_min = 8192;
+  if (const char* e = getenv("SSFM_REFIT_THREADS_MIN")) cfg.small_refit_threads_min = atoi(e);
 
-  cudaEvent_t evA = h->ev[0], evB = h->ev[1], evC = h->ev[2], evD = h->ev[3];
-  SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
-  int launches = 0;
-  for (int pair0 = 0; pair0 < h->P; pair0 += kMaxPassPairs) {
-    const int np = std::min(kMaxPassPairs, h->P - pair0);
-    const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
-    const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
-    SSFM_CK(h->states.ensure(np));
-    SSFM_CK(h->active0.ensure(np));
-    SSFM_CK(h->active1.ensure(np));
-    SSFM_CK(h->navail.ensure(np));
-    SSFM_CK(h->models.ensure((size_t)np * 24 * R));
-    SSFM_CK(h->s32.ensure((size_t)np * R));
-    SSFM_CK(h->s32m.ensure((size_t)np * R * 4));
-    SSFM_CK(h->list_a.ensure(mpass + 16));
-    SSFM_CK(h->list_b.ensure(P.num_lo_steps > 0 ? mpass + 16 : 16));
-    SSFM_CK(h->mt.ensure(P.driver == SSFM_DRIVER_LO_MSAC ? (size_t)np * 625 : 625));
-    SSFM_CK(h->parked0.ensure(np));
-    SSFM_CK(h->parked1.ensure(np));
-    SSFM_CK(h->lm_E.ensure((size_t)np * 9));
-
-    k_init_pairs<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->mt.p, h->active0.p,
-                                                          h->navail.p, first_cap);
-    SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 2 * sizeof(int), h->stream));
-    k_finish_trivial<<<(np + 127) / 128, 128, 0, h->stream>>>(P, h->offsets.p, pair0, np, h->states.p, h->flags.p, 0,
-                                                              h->results.p + pair0, h->active0.p, h->counts.p);
-    launches += 2;
-    SSFM_CK(cudaMemcpyAsync(h->h_count, h->counts.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    SSFM_CK(cudaStreamSynchronize(h->stream));
-    int count = h->h_count[0];
-    int* act = h->active0.p;
-    int* act_next = h->active1.p;
-    int round = 0;
-    while (count > 0) {
-      const int cap = round == 0 ? first_cap : round_cap;
-      SSFM_CK(cudaEventRecord(evA, h->stream));
-      if (P.solver == 0) launch_solve<0>(h, P, pair0, act, count, cap, R);
-      else if (P.solver == 1) launch_solve<1>(h, P, pair0, act, count, cap, R);
-      else launch_solve<2>(h, P, pair0, act, count, cap, R);
-      SSFM_CK(cudaGetLastError());
-      SSFM_CK(cudaEventRecord(evB, h->stream));
-      {
-        dim3 grid(count, (cap + kScoreThreads - 1) / kScoreThreads);
-        if (h->unit_z)
-          k_score_rounds<true><<<grid, kScoreThreads, 0, h->stream>>>(h->uv4.p, nullptr, h->offsets.p, pair0, act, h->navail.p,
-                                                                      R, h->models.p, thr32, h->s32.p, h->s32m.p);
-        else
-          k_score_rounds<false><<<grid, kScoreThreads, 0, h->stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, h->navail.p,
-                                                                       R, h->models.p, thr32, h->s32.p, h->s32m.p);
-        SSFM_CK(cudaGetLastError());
-      }
-      SSFM_CK(cudaEventRecord(evC, h->stream));
-      SSFM_CK(cudaMemsetAsync(h->counts.p + 1, 0, sizeof(int), h->stream));
-      {
-        ChainArgs A;
-        A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = pair0;
-        A.navail = h->navail.p; A.states = h->states.p; A.R = R; A.models = h->models.p; A.s32 = h->s32.p; A.s32m = h->s32m.p;
-        A.list_a = h->list_a.p; A.list_b = h->list_b.p; A.mt = h->mt.p; A.lm_E = h->lm_E.p; A.list_base = c0;
-        A.flags = h->flags.p + c0; A.results = h->results.p + pair0; A.next_active = act_next; A.next_count = h->counts.p + 1;
-        A.next_cap = round_cap; A.parked_small = h->counts.p + 4; A.parked_big = h->counts.p + 5; A.counters = h->counters.p;
-        A.cap = np;
-        if (!defer) {
-          A.list = act; A.nlist = count; A.mode = 0; A.n_front = 0; A.parked = h->parked0.p;
-          k_chain<false><<<(count + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(P, A);
-          SSFM_CK(cudaGetLastError());
-          launches += 1;
-        } else {
-          // waves: walk -> solve the parked refits -> resume, until no pair of this round is parked
-          const int* cur = act;
-          int ncur = count, mode = 0, nfront = 0;
-          int* out = h->parked0.p;
-          int* other = h->parked1.p;
-          for (int wave = 0;; ++wave) {
-            if (wave > R + 8) return fail(SSFM_ERR_CUDA, "internal error: refit waves did not drain");
-            SSFM_CK(cudaMemsetAsync(h->counts.p + 4, 0, 2 * sizeof(int), h->stream));
-            A.list = cur; A.nlist = ncur; A.mode = mode; A.n_front = nfront; A.parked = out;
-            k_chain<true><<<(ncur + kChainWarps - 1) / kChainWarps, kChainWarps * 32, 0, h->stream>>>(P, A);
-            SSFM_CK(cudaGetLastError());
-            launches += 1;
-            SSFM_CK(cudaMemcpyAsync(h->h_count + 4, h->counts.p + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-            SSFM_CK(cudaStreamSynchronize(h->stream));
-            const int ns = h->h_count[4], nb = h->h_count[5];
-            if (ns + nb == 0) break;
-            if (ns > 0) {
-              // persistent lanes pulling from a queue: enough warps to fill the machine, not one per task
-              SSFM_CK(cudaMemsetAsync(h->counts.p + 6, 0, sizeof(int), h->stream));
-              const int blocks = std::min((ns + 63) / 64, h->num_sms * 8);
-              k_refit_small<<<blocks, 64, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, h->counts.p + 6,
-                                                          h->states.p, h->list_a.p, c0, h->lm_E.p);
-              launches += 1;
-            }
-            if (nb > 0) {
-              k_refit_big<<<(nb + 3) / 4, 128, 0, h->stream>>>(P, h->d_rays, h->offsets.p, pair0, out, np, nb, h->states.p,
-                                                               h->list_a.p, c0, h->lm_E.p);
-              launches += 1;
-            }
-            SSFM_CK(cudaGetLastError());
-            cur = out; ncur = ns + nb; mode = 1; nfront = ns;
-            std::swap(out, other);
-            h->stats.refit_waves += 1;
-          }
-        }
-      }
-      SSFM_CK(cudaEventRecord(evD, h->stream));
-      SSFM_CK(cudaMemcpyAsync(h->h_count, h->counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      SSFM_CK(cudaStreamSynchronize(h->stream));
-      float t1 = 0, t2 = 0, t3 = 0;
-      cudaEventElapsedTime(&t1, evA, evB);
-      cudaEventElapsedTime(&t2, evB, evC);
-      cudaEventElapsedTime(&t3, evC, evD);
-      h->stats.solve_ms += t1;
-      h->stats.score_ms += t2;
-      h->stats.chain_ms += t3;
-      h->stats.score_launches += 1;
-      launches += 2;
-      count = h->h_count[0];
-      std::swap(act, act_next);
-      ++round;
-    }
-    h->stats.rounds += round;
+  // Split the pairs between workers by correspondence count.  Small batches use one worker.
+  int nw = h->P >= 2048 ? 2 : 1;
+  if (const char* e = getenv("SSFM_WORKERS")) nw = std::max(1, std::min(kMaxWorkers, atoi(e)));
+  nw = std::max(1, std::min(nw, std::max(h->P, 1)));
+  std::vector<int> bounds(nw + 1, 0);
+  bounds[nw] = h->P;
+  for (int k = 1; k < nw; ++k) {
+    const long long target = h->M * k / nw;
+    int b = (int)(std::lower_bound(h->h_offsets.begin(), h->h_offsets.end(), target) - h->h_offsets.begin());
+    bounds[k] = std::max(bounds[k - 1], std::min(b, h->P));
   }
-  SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
-  unsigned long long hc[32] = {};
-  SSFM_CK(cudaMemcpyAsync(hc, h->counters.p, sizeof(hc), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> threads;
+  for (int k = 1; k < nw; ++k) {
+    Worker* w = &h->workers[k];
+    const int b0 = bounds[k], b1 = bounds[k + 1];
+    threads.emplace_back([h, w, &P, &cfg, b0, b1]() { w->rc = run_range(h, *w, P, cfg, b0, b1); });
+  }
+  h->workers[0].rc = run_range(h, h->workers[0], P, cfg, bounds[0], bounds[1]);
+  for (auto& t : threads) t.join();
+  const auto t1 = std::chrono::steady_clock::now();
+  unsigned long long hc[32] = {};
+  for (int k = 0; k < nw; ++k) {
+    Worker& w = h->workers[k];
+    if (w.rc != SSFM_OK) return fail(w.rc, w.err);
+    h->stats.solve_ms += w.solve_ms;
+    h->stats.score_ms += w.score_ms;
+    h->stats.chain_ms += w.chain_ms;
+    h->stats.rounds = std::max(h->stats.rounds, w.rounds);
+    h->stats.kernel_launches += w.launches;
+    h->stats.score_launches += w.score_launches;
+    h->stats.refit_waves += w.refit_waves;
+    for (int i = 0; i < 32; ++i) hc[i] += w.hc[i];
+  }
 #if defined(SSFM_PROFILE_CHAIN)
   {
     const char* names[] = {"scan", "rescore", "lo_collect", "lo_shuffle", "lo_lm", "lo_score", "final_lm", "final_rest", "total"};
@@ -427,10 +547,8 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     fprintf(stderr, "\n");
   }
 #endif
-  float ms = 0.f;
-  SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
-  h->stats.total_ms = ms;
-  h->stats.kernel_launches = launches;
+  h->stats.total_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  h->stats.workers = nw;
   h->stats.evals_executed = (long long)hc[0];
   h->stats.evals_exact = (long long)hc[1];
   h->have_results = true;

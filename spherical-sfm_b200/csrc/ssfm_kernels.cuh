@@ -514,15 +514,17 @@ __global__ void __launch_bounds__(64) k_refit_small(Params P, const double* __re
   }
 }
 // big: one WARP per refit (the final least squares over all inliers).
+// Also used for the SMALL refits of a wave that has too few of them to fill the machine with one
+// thread each (from_front = 1): a warp per refit has ~3x lower latency, and those waves are pure tail.
 __global__ void __launch_bounds__(128) k_refit_big(Params P, const double* __restrict__ rays,
                                                    const long long* __restrict__ offsets, int pair0,
-                                                   const int* __restrict__ parked, int cap, int ntasks,
+                                                   const int* __restrict__ parked, int cap, int ntasks, int from_front,
                                                    const PairState* __restrict__ states, const int* __restrict__ list_a,
                                                    long long list_base, double* lm_E) {
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= ntasks) return;
   WarpCtx cx{(int)(threadIdx.x & 31)};
-  const int a = parked[cap - 1 - w];
+  const int a = from_front ? parked[w] : parked[cap - 1 - w];
   const long long off = offsets[pair0 + a];
   double E[9];
 #pragma unroll

@@ -899,8 +899,9 @@ SSFM_HD double sampson_value(const double* E, const double* u, const double* v) 
   return (d * d) / (Eu0 * Eu0 + Eu1 * Eu1 + Et0 * Et0 + Et1 * Et1);
 }
 
-// residual and its gradient w.r.t. the 6 parameters, given E as jets (chain rule of the same
-// expression tree the reference autodiffs, src/spherical_estimator.cpp:55-61).
+// residual and its gradient w.r.t. the 6 parameters, given E as jets: de/dE (9 closed-form entries)
+// contracted with dE/dx (chain rule of the expression tree the reference autodiffs,
+// src/spherical_estimator.cpp:55-61).
 SSFM_HD void sampson_value_grad(const Jet6* E, const double* u, const double* v, double& r, double* g) {
   const double Eu0 = E[0].a * u[0] + E[1].a * u[1] + E[2].a * u[2];
   const double Eu1 = E[3].a * u[0] + E[4].a * u[1] + E[5].a * u[2];
@@ -911,23 +912,31 @@ SSFM_HD void sampson_value_grad(const Jet6* E, const double* u, const double* v,
   const double den = Eu0 * Eu0 + Eu1 * Eu1 + Et0 * Et0 + Et1 * Et1;
   const double inv = 1.0 / den;
   r = (d * d) * inv;
+  // de/dE_ij = (2 d v_i u_j - r * dden/dE_ij) / den,  dden/dE_ij = 2 (Eu_i u_j [i<2] + Et_j v_i [j<2])
+  const double a2 = 2.0 * d * inv, b2 = 2.0 * r * inv;
+  double w[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double dd = 0.0;
+      if (i < 2) dd += (i == 0 ? Eu0 : Eu1) * u[j];
+      if (j < 2) dd += (j == 0 ? Et0 : Et1) * v[i];
+      w[3 * i + j] = a2 * v[i] * u[j] - b2 * dd;
+    }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double dEu0 = E[0].v[k] * u[0] + E[1].v[k] * u[1] + E[2].v[k] * u[2];
-    const double dEu1 = E[3].v[k] * u[0] + E[4].v[k] * u[1] + E[5].v[k] * u[2];
-    const double dEu2 = E[6].v[k] * u[0] + E[7].v[k] * u[1] + E[8].v[k] * u[2];
-    const double dEt0 = E[0].v[k] * v[0] + E[3].v[k] * v[1] + E[6].v[k] * v[2];
-    const double dEt1 = E[1].v[k] * v[0] + E[4].v[k] * v[1] + E[7].v[k] * v[2];
-    const double dd = dEu0 * v[0] + dEu1 * v[1] + dEu2 * v[2];
-    const double dden = 2.0 * (Eu0 * dEu0 + Eu1 * dEu1 + Et0 * dEt0 + Et1 * dEt1);
-    g[k] = (2.0 * d * dd - r * dden) * inv;
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 9; ++q) s += w[q] * E[q].v[k];
+    g[k] = s;
   }
 }
 
 // 6x6 SPD solve (DENSE_NORMAL_CHOLESKY, src/spherical_estimator.cpp:148).  H is the lower
 // triangle packed row-wise (21 entries).  Returns false if not positive definite.
 SSFM_HD bool cholesky_solve6(const double* Hp, const double* b, double* x) {
-  double L[21];
+  double L[21], inv[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
     double d = Hp[j * (j + 1) / 2 + j];
@@ -936,12 +945,13 @@ SSFM_HD bool cholesky_solve6(const double* Hp, const double* b, double* x) {
     if (!(d > 0.0)) return false;
     const double ljj = sqrt(d);
     L[j * (j + 1) / 2 + j] = ljj;
+    inv[j] = 1.0 / ljj;
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double s = Hp[i * (i + 1) / 2 + j];
 #pragma unroll
       for (int k = 0; k < j; ++k) s -= L[i * (i + 1) / 2 + k] * L[j * (j + 1) / 2 + k];
-      L[i * (i + 1) / 2 + j] = s / ljj;
+      L[i * (i + 1) / 2 + j] = s * inv[j];
     }
   }
   double y[6];
@@ -950,7 +960,7 @@ SSFM_HD bool cholesky_solve6(const double* Hp, const double* b, double* x) {
     double s = b[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i * (i + 1) / 2 + k] * y[k];
-    y[i] = s / L[i * (i + 1) / 2 + i];
+    y[i] = s * inv[i];
   }
   bool ok = true;
 #pragma unroll
@@ -958,7 +968,7 @@ SSFM_HD bool cholesky_solve6(const double* Hp, const double* b, double* x) {
     double s = y[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k * (k + 1) / 2 + i] * x[k];
-    x[i] = s / L[i * (i + 1) / 2 + i];
+    x[i] = s * inv[i];
     ok = ok && isfinite(x[i]);
   }
   return ok;
