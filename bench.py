@@ -273,11 +273,15 @@ def main():
     dev_step_ms = dev_ms / args.steps
 
     # ---- end to end through the C ABI with host buffers (e2e) ----
-    eng.estimate_pairs(rays_np, offsets, opt)  # warm
+    out_res_t = torch.empty(P * S.RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)  # pinned host outputs
+    out_flags_t = torch.empty(P * N, dtype=torch.uint8, pin_memory=True)
+    out_res = out_res_t.numpy().view(S.RESULT_DTYPE)
+    out_flags = out_flags_t.numpy()
+    eng.estimate_pairs(rays_np, offsets, opt, out_results=out_res, out_flags=out_flags)  # warm
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res_e2e, flags = eng.estimate_pairs(rays_np, offsets, opt)
+        res_e2e, flags = eng.estimate_pairs(rays_np, offsets, opt, out_results=out_res, out_flags=out_flags)
         gather_tables()
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps

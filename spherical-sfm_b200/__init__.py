@@ -205,13 +205,15 @@ class Engine:
                                    C.c_void_p(flags.ctypes.data) if want_flags and self._num_corr else None))
         return res, flags
 
-    def estimate_pairs(self, rays, offsets, opt, want_flags=True):
-        """ssfm_estimate_pairs: upload + run + download in one call (host buffers in, host buffers out)."""
+    def estimate_pairs(self, rays, offsets, opt, want_flags=True, out_results=None, out_flags=None):
+        """ssfm_estimate_pairs: upload + run + download in one call (host buffers in, host buffers out).
+        out_results / out_flags: optional preallocated (e.g. pinned) output arrays."""
         rays = np.ascontiguousarray(rays, np.float64)
         offsets = np.ascontiguousarray(offsets, np.int64)
         b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0)
-        res = np.zeros(b.num_pairs, RESULT_DTYPE)
-        flags = np.zeros(int(offsets[-1]), np.uint8) if want_flags else None
+        res = out_results if out_results is not None else np.zeros(b.num_pairs, RESULT_DTYPE)
+        assert res.dtype == RESULT_DTYPE and len(res) == b.num_pairs
+        flags = (out_flags if out_flags is not None else np.zeros(int(offsets[-1]), np.uint8)) if want_flags else None
         _check(lib().ssfm_estimate_pairs(self._h, C.byref(b), C.byref(opt), C.c_void_p(res.ctypes.data),
                                          C.c_void_p(flags.ctypes.data) if want_flags and len(flags) else None))
         self._num_pairs = b.num_pairs

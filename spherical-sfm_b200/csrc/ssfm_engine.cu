@@ -47,6 +47,8 @@ int fail(int code, const std::string& msg) {
   } while (0)
 
 constexpr int kMaxPassPairs = 131072;
+constexpr int kPipelinePassPairs = 16384;  // pass size when the upload is pipelined with the compute
+constexpr int kMaxUploadChunks = 4096;
 constexpr int kRoundCap = 256;
 
 template <class T>
@@ -87,6 +89,11 @@ struct ssfm_engine {
   bool unit_z = false;
   DevBuf<long long> offsets;
   bool resident = false;
+  // pipelined upload (ssfm_estimate_pairs): one event + one unit-z flag per pass of pairs
+  std::vector<cudaEvent_t> up_ev;
+  std::vector<int> up_bounds;  // pair bounds of the upload chunks (empty: not pipelined)
+  DevBuf<int> up_flags;
+  int* h_up_flags = nullptr;  // pinned
   // run buffers live in the workers (one stream each; see ssfm_run)
   DevBuf<int> counts;  // upload-time flags
   DevBuf<SsfmPairResult> results;
@@ -109,7 +116,7 @@ struct Worker {
   int* h_count = nullptr;  // pinned
   DevBuf<PairState> states;
   DevBuf<uint32_t> mt;
-  DevBuf<int> active0, active1, navail, list_a, list_b, counts, parked0, parked1;
+  DevBuf<int> active0, active1, ident, navail, list_a, list_b, counts, parked0, parked1;
   DevBuf<double> models, lm_E;
   DevBuf<float> s32, s32m;
   DevBuf<unsigned long long> counters;
@@ -121,7 +128,7 @@ struct Worker {
   int rc = SSFM_OK;
   std::string err;
   void release() {
-    states.release(); mt.release(); active0.release(); active1.release(); navail.release(); list_a.release();
+    states.release(); mt.release(); active0.release(); active1.release(); ident.release(); navail.release(); list_a.release();
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release();
   }
@@ -189,8 +196,13 @@ struct RunCfg {
     }                                                                                          \
   } while (0)
 
-// All rounds for pairs [pbegin, pend) on worker w's stream.
-int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, int pbegin, int pend) {
+struct PassDesc {
+  int pair0, np;
+  int pipelined;  // 1: the upload is still in flight; round 0 is launched chunk by chunk as the rays arrive
+};
+
+// All rounds of the given passes on worker w's streams.
+int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, const std::vector<PassDesc>& passes) {
   SSFM_WCK(cudaSetDevice(h->device));
   const int first_cap = cfg.first_cap, round_cap = cfg.round_cap, R = cfg.R;
   const bool defer = cfg.defer;
@@ -203,13 +215,15 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, int
   SSFM_WCK(cudaMemsetAsync(w.counters.p, 0, 32 * sizeof(unsigned long long), w.stream));
   cudaEvent_t evA = w.ev[0], evB = w.ev[1], evC = w.ev[2], evD = w.ev[3];
   int launches = 0;
-  for (int pair0 = pbegin; pair0 < pend; pair0 += kMaxPassPairs) {
-    const int np = std::min(kMaxPassPairs, pend - pair0);
+  for (const PassDesc& pd : passes) {
+    const int pair0 = pd.pair0, np = pd.np;
+    bool unit_z = h->unit_z;
     const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
     const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
     SSFM_WCK(w.states.ensure(np));
     SSFM_WCK(w.active0.ensure(np));
     SSFM_WCK(w.active1.ensure(np));
+    SSFM_WCK(w.ident.ensure(np));
     SSFM_WCK(w.navail.ensure(np));
     SSFM_WCK(w.models.ensure((size_t)np * 24 * R));
     SSFM_WCK(w.s32.ensure((size_t)np * R));
@@ -222,7 +236,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, int
     SSFM_WCK(w.lm_E.ensure((size_t)np * 9));
 
     k_init_pairs<<<(np + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, pair0, np, w.states.p, w.mt.p, w.active0.p,
-                                                         w.navail.p, first_cap);
+                                                         w.ident.p, w.navail.p, first_cap);
     SSFM_WCK(cudaMemsetAsync(w.counts.p, 0, 2 * sizeof(int), w.stream));
     k_finish_trivial<<<(np + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, pair0, np, w.states.p, h->flags.p, 0,
                                                              h->results.p + pair0, w.active0.p, w.counts.p);
@@ -236,20 +250,39 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, int
     while (count > 0) {
       const int cap = round == 0 ? first_cap : round_cap;
       SSFM_WCK(cudaEventRecord(evA, w.stream));
-      if (P.solver == 0) launch_solve<0>(h, w, P, pair0, act, count, cap, R);
-      else if (P.solver == 1) launch_solve<1>(h, w, P, pair0, act, count, cap, R);
-      else launch_solve<2>(h, w, P, pair0, act, count, cap, R);
-      SSFM_WCK(cudaGetLastError());
-      SSFM_WCK(cudaEventRecord(evB, w.stream));
-      {
-        dim3 grid(count, (cap + kScoreThreads - 1) / kScoreThreads);
-        if (h->unit_z)
-          k_score_rounds<true><<<grid, kScoreThreads, 0, w.stream>>>(h->uv4.p, nullptr, h->offsets.p, pair0, act, w.navail.p,
-                                                                     R, w.models.p, thr32, w.s32.p, w.s32m.p);
+      auto launch_round = [&](const int* list, int n, bool uz, bool mark) -> cudaError_t {
+        if (P.solver == 0) launch_solve<0>(h, w, P, pair0, list, n, cap, R);
+        else if (P.solver == 1) launch_solve<1>(h, w, P, pair0, list, n, cap, R);
+        else launch_solve<2>(h, w, P, pair0, list, n, cap, R);
+        if (mark) cudaEventRecord(evB, w.stream);  // solve | score boundary for the stage timers
+        dim3 grid(n, (cap + kScoreThreads - 1) / kScoreThreads);
+        if (uz)
+          k_score_rounds<true><<<grid, kScoreThreads, 0, w.stream>>>(h->uv4.p, nullptr, h->offsets.p, pair0, list, w.navail.p, R,
+                                                                     w.models.p, thr32, w.s32.p, w.s32m.p);
         else
-          k_score_rounds<false><<<grid, kScoreThreads, 0, w.stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, act, w.navail.p,
+          k_score_rounds<false><<<grid, kScoreThreads, 0, w.stream>>>(h->u4.p, h->v4.p, h->offsets.p, pair0, list, w.navail.p,
                                                                       R, w.models.p, thr32, w.s32.p, w.s32m.p);
-        SSFM_WCK(cudaGetLastError());
+        return cudaGetLastError();
+      };
+      if (round == 0 && pd.pipelined) {
+        // The upload is still streaming in: sample/solve/score each chunk of pairs as soon as its rays
+        // are in HBM (identity list slice; pairs with nothing to do exit at once), so the H2D copy of
+        // later chunks overlaps the first round's kernels.
+        SSFM_WCK(cudaEventRecord(evB, w.stream));  // chunked round: everything is booked under 'score'
+        bool all_unit = true;
+        for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) {
+          const int q0 = std::max(h->up_bounds[k], pair0), q1 = std::min(h->up_bounds[k + 1], pair0 + np);
+          if (q1 <= q0) continue;
+          SSFM_WCK(cudaEventSynchronize(h->up_ev[k]));
+          const bool uz = h->h_up_flags[k] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+          all_unit = all_unit && uz;
+          SSFM_WCK(launch_round(w.ident.p + (q0 - pair0), q1 - q0, uz, false));
+          launches += 2;
+        }
+        unit_z = all_unit;
+        launches -= 2;
+      } else {
+        SSFM_WCK(launch_round(act, count, unit_z, true));
       }
       SSFM_WCK(cudaEventRecord(evC, w.stream));
       cudaStream_t hs = w.stream_hi;  // everything below runs at high priority, after the scoring kernel
@@ -385,6 +418,7 @@ int ssfm_create(int device, ssfm_handle* out) {
   SSFM_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) SSFM_CK(cudaEventCreate(&ev));
   SSFM_CK(cudaMallocHost(&h->h_count, 64));
+  SSFM_CK(cudaMallocHost(&h->h_up_flags, sizeof(int) * kMaxUploadChunks));
   h->num_workers = kMaxWorkers;
   h->workers = new Worker[kMaxWorkers];
   for (int k = 0; k < kMaxWorkers; ++k) {
@@ -419,11 +453,14 @@ void ssfm_destroy(ssfm_handle h) {
   delete[] h->workers;
   for (auto& ev : h->ev) cudaEventDestroy(ev);
   if (h->h_count) cudaFreeHost(h->h_count);
+  if (h->h_up_flags) cudaFreeHost(h->h_up_flags);
+  for (auto& e : h->up_ev) cudaEventDestroy(e);
+  h->up_flags.release();
   cudaStreamDestroy(h->stream);
   delete h;
 }
 
-int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
+static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
   if (b->num_pairs < 0 || (b->num_pairs > 0 && (!b->offsets || !b->rays))) return fail(SSFM_ERR_INVALID, "bad batch");
   SSFM_CK(cudaSetDevice(h->device));
@@ -446,6 +483,40 @@ int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
   SSFM_CK(h->uv4.ensure(m));
   SSFM_CK(h->counts.ensure(8));
   SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), h->stream));
+  h->up_bounds.clear();
+  if (pipelined && !b->rays_on_device && h->P > 2 * kPipelinePassPairs && (h->P / kPipelinePassPairs) < kMaxUploadChunks - 1) {
+    // Chunked, asynchronous upload: chunk k = pairs [k*16384, (k+1)*16384); H2D + pack on the copy
+    // stream, an event per chunk.  ssfm_run's passes wait on the events, so the copy of chunk k+1
+    // overlaps the kernels of chunk k.  (The caller's buffer is only read until ssfm_run returns.)
+    SSFM_CK(h->rays_own.ensure(m * 6));
+    h->d_rays = h->rays_own.p;
+    for (int p0 = 0; p0 < h->P; p0 += kPipelinePassPairs) h->up_bounds.push_back(p0);
+    h->up_bounds.push_back(h->P);
+    const int nchunks = (int)h->up_bounds.size() - 1;
+    SSFM_CK(h->up_flags.ensure(nchunks));
+    SSFM_CK(cudaMemsetAsync(h->up_flags.p, 0, sizeof(int) * nchunks, h->stream));
+    while ((int)h->up_ev.size() < nchunks) {
+      cudaEvent_t e;
+      SSFM_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->up_ev.push_back(e);
+    }
+    for (int k = 0; k < nchunks; ++k) {
+      const long long c0 = h->h_offsets[h->up_bounds[k]], c1 = h->h_offsets[h->up_bounds[k + 1]];
+      if (c1 > c0) {
+        SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
+                                cudaMemcpyHostToDevice, h->stream));
+        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream>>>(h->rays_own.p + 6 * c0, c1 - c0, h->u4.p + c0,
+                                                                         h->v4.p + c0, h->uv4.p + c0, h->up_flags.p + k);
+        SSFM_CK(cudaGetLastError());
+      }
+      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      SSFM_CK(cudaEventRecord(h->up_ev[k], h->stream));
+    }
+    h->stats.h2d_bytes = (long long)(sizeof(double) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
+    h->unit_z = false;  // decided per chunk
+    h->resident = true;
+    return SSFM_OK;
+  }
   SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
   if (b->rays_on_device) {
     h->d_rays = b->rays;
@@ -472,6 +543,8 @@ int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
   h->resident = true;
   return SSFM_OK;
 }
+
+int ssfm_upload(ssfm_handle h, const SsfmBatch* b) { return upload_impl(h, b, false); }
 
 int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (!h) return fail(SSFM_ERR_INVALID, "NULL handle");
@@ -504,26 +577,33 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   cfg.small_refit_threads_min = 8192;
   if (const char* e = getenv("SSFM_REFIT_THREADS_MIN")) cfg.small_refit_threads_min = atoi(e);
 
-  // Split the pairs between workers by correspondence count.  Small batches use one worker.
-  int nw = h->P >= 2048 ? 2 : 1;
+  // Pass lists per worker: contiguous ranges balanced by correspondence count.
+  int nw = 1;
   if (const char* e = getenv("SSFM_WORKERS")) nw = std::max(1, std::min(kMaxWorkers, atoi(e)));
   nw = std::max(1, std::min(nw, std::max(h->P, 1)));
-  std::vector<int> bounds(nw + 1, 0);
-  bounds[nw] = h->P;
-  for (int k = 1; k < nw; ++k) {
-    const long long target = h->M * k / nw;
-    int b = (int)(std::lower_bound(h->h_offsets.begin(), h->h_offsets.end(), target) - h->h_offsets.begin());
-    bounds[k] = std::max(bounds[k - 1], std::min(b, h->P));
+  std::vector<std::vector<PassDesc>> plan(nw);
+  {
+    const int pipelined = h->up_bounds.empty() ? 0 : 1;
+    std::vector<int> bounds(nw + 1, 0);
+    bounds[nw] = h->P;
+    for (int k = 1; k < nw; ++k) {
+      const long long target = h->M * k / nw;
+      int b = (int)(std::lower_bound(h->h_offsets.begin(), h->h_offsets.end(), target) - h->h_offsets.begin());
+      bounds[k] = std::max(bounds[k - 1], std::min(b, h->P));
+    }
+    for (int k = 0; k < nw; ++k)
+      for (int p0 = bounds[k]; p0 < bounds[k + 1]; p0 += kMaxPassPairs)
+        plan[k].push_back(PassDesc{p0, std::min(kMaxPassPairs, bounds[k + 1] - p0), pipelined});
+    if (!pipelined) SSFM_CK(cudaStreamSynchronize(h->stream));
   }
-  SSFM_CK(cudaStreamSynchronize(h->stream));
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<std::thread> threads;
   for (int k = 1; k < nw; ++k) {
     Worker* w = &h->workers[k];
-    const int b0 = bounds[k], b1 = bounds[k + 1];
-    threads.emplace_back([h, w, &P, &cfg, b0, b1]() { w->rc = run_range(h, *w, P, cfg, b0, b1); });
+    const std::vector<PassDesc>* pl = &plan[k];
+    threads.emplace_back([h, w, &P, &cfg, pl]() { w->rc = run_range(h, *w, P, cfg, *pl); });
   }
-  h->workers[0].rc = run_range(h, h->workers[0], P, cfg, bounds[0], bounds[1]);
+  h->workers[0].rc = run_range(h, h->workers[0], P, cfg, plan[0]);
   for (auto& t : threads) t.join();
   const auto t1 = std::chrono::steady_clock::now();
   unsigned long long hc[32] = {};
@@ -596,8 +676,15 @@ int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions
                         uint8_t* inlier_flags) {
   if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
   if (int rc = check_options(opt)) return rc;
-  if (int rc = ssfm_upload(h, batch)) return rc;
+  if (int rc = upload_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return rc;
   if (int rc = ssfm_run(h, opt)) return rc;
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  if (!h->up_bounds.empty()) {  // the batch is fully resident now; later ssfm_run calls use the plain plan
+    bool all_unit = true;
+    for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) all_unit = all_unit && h->h_up_flags[k] == 0;
+    h->unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    h->up_bounds.clear();
+  }
   if (int rc = ssfm_download(h, results, inlier_flags)) return rc;
   if (batch->rays_on_device) { h->resident = false; h->d_rays = nullptr; }  // never keep a caller pointer
   return SSFM_OK;

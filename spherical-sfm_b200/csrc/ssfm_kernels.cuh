@@ -107,7 +107,7 @@ __global__ void k_pack(const double* __restrict__ rays, long long m, float4* __r
 // k_init_pairs
 // ------------------------------------------------------------------------------------------
 __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, int pair0, int npairs, PairState* states,
-                             uint32_t* mt, int* active, int* navail, int first_cap) {
+                             uint32_t* mt, int* active, int* ident, int* navail, int first_cap) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= npairs) return;
   const int pair = pair0 + a;
@@ -118,6 +118,7 @@ __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, in
   if (want == 0) st.done = 1;
   states[a] = st;
   active[a] = a;
+  ident[a] = a;
   navail[a] = lookahead(want, first_cap);
   if (P.driver == 0) mt19937_seed(mt + (size_t)a * 625, P.seed);
 }
