@@ -1,0 +1,3 @@
+// Stand-in for <ceres/ceres.h>: see ../ssfm_mini_ceres.hpp (test infrastructure, NOT Ceres).
+#pragma once
+#include "../ssfm_mini_ceres.hpp"

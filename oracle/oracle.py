@@ -179,6 +179,18 @@ def build(ref=True, force=False):
                                                          "-I" + os.path.join(refroot, "include"),
                                                          "-I" + os.path.join(refroot, "evaluation"),
                                                          "-o", rout, srcs[0]])
+        # the reference's own sources against the Eigen / Ceres stand-ins (see Makefile `ref`)
+        shim = [os.path.join(_DIR, "eigen_shim", "ssfm_mini_eigen.hpp"), os.path.join(_DIR, "ceres_shim", "ssfm_mini_ceres.hpp")]
+        refsrc = [os.path.join(refroot, "src", f) for f in ("spherical_solvers.cpp", "so3.cpp", "spherical_utils.cpp")]
+        inc = ["-I" + _DIR, "-I" + os.path.join(_DIR, "eigen_shim"), "-I" + os.path.join(_DIR, "ceres_shim"),
+               "-I" + os.path.join(refroot, "include"), "-I" + os.path.join(refroot, "evaluation")]
+        for name, main, extra in (("libssfm_refsolvers.so", "ref_solvers.cpp", []),
+                                  ("libssfm_reffull.so", "ref_full.cpp", [os.path.join(refroot, "src", "spherical_estimator.cpp")])):
+            out2 = os.path.join(_DIR, "_ref", name)
+            dep = max([newest, os.path.getmtime(os.path.join(_DIR, main))] + [os.path.getmtime(x) for x in shim])
+            if force or not os.path.exists(out2) or os.path.getmtime(out2) < dep:
+                subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + inc +
+                                      ["-o", out2, os.path.join(_DIR, main)] + extra + refsrc)
 
 
 _cache = {}
@@ -189,6 +201,16 @@ def load():
         build(ref=False)
         _cache["o"] = Oracle(os.path.join(_DIR, "liboracle.so"))
     return _cache["o"]
+
+
+def load_ref_full():
+    """oracle/_ref/libssfm_reffull.so: the reference's own RansacLib + SphericalEstimator + solver sources,
+    compiled unmodified against the Eigen/Ceres stand-ins.  None when it was never built."""
+    if "f" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_reffull.so")
+        _cache["f"] = Oracle(p) if os.path.exists(p) else None
+    return _cache["f"]
 
 
 def load_ref():

@@ -63,6 +63,13 @@ def ref(O):
 
 
 @pytest.fixture(scope="session")
+def reffull(O):
+    """oracle/_ref/libssfm_reffull.so: the reference's own sources (RansacLib, SphericalEstimator, solvers)
+    compiled unmodified against Eigen/Ceres stand-ins.  None if it was never built."""
+    return O.load_ref_full()
+
+
+@pytest.fixture(scope="session")
 def engine(S):
     import __graft_entry__ as G
     if not os.path.exists(S.LIB_PATH):
