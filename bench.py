@@ -335,6 +335,18 @@ def main():
                      "ms_per_launch": score_ms_per_launch,
                      "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3)},
     }
+    # config C5 (scoring stress: 4096 hypotheses x 200k correspondences, 90 % outliers), scoring kernel only
+    try:
+        n5 = 200000
+        rays5_t, _, _ = make_batch_torch(1, n5, 0.9, 99, "cuda")
+        rays5 = rays5_t.cpu().numpy()
+        samples = np.array([S.sample(3, 0, i, 3, n5) for i in range(1024)], np.int32)
+        m5, _ = eng.minimal_solve(rays5, samples, 0)
+        _, _, ms5 = eng.score(m5.reshape(-1, 6), rays5, THR2)
+        line["c5_scoring"] = {"hypotheses": 4096, "corr": n5, "kernel_ms": ms5, "evals_per_sec": 4096.0 * n5 / (ms5 * 1e-3),
+                              "fp32_frac": 4096.0 * n5 * FLOP_PER_EVAL / (ms5 * 1e-3) / 1e12 / fp32_peak}
+    except Exception as exc:  # the headline line must not die on the side measurement
+        line["c5_scoring"] = {"error": str(exc)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(rays_np[:4096 * N], N, args.cpu_seconds)
     print(json.dumps(line))

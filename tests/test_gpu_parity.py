@@ -278,3 +278,59 @@ def test_full_size_properties_c3_shape(S, engine):
     errs = np.array([np.rad2deg(S.problems.rot_error(Rgt[p], S.problems.so3exp(res["r"][p]))) for p in range(P)])
     assert np.median(errs) < 0.05 and (errs < 0.5).mean() > 0.995
     assert (res["best_num_inliers"] > 0.25 * N).mean() > 0.995
+
+
+def test_engine_follows_reference_sources(S, O, engine, reffull):
+    """The GPU engine against oracle/_ref/libssfm_reffull.so: the reference's own RansacLib +
+    SphericalEstimator + solver sources (compiled unmodified against Eigen/Ceres stand-ins).  Same
+    trajectory -> identical statistics and inlier sets; a trajectory can only differ when a model built from
+    a complex root pair (implementation-defined upstream) wins an early iteration."""
+    if reffull is None:
+        pytest.skip("oracle/_ref/libssfm_reffull.so not present")
+    opt = S.pipeline_options(THR2)
+    P, N = 12, 1000
+    rays, offsets, probs = S.problems.make_batch(1234, P, N, noise=1 / 600, outlier_frac=0.5)
+    res, flags = engine.estimate_pairs(rays, offsets, opt)
+    oopt = to_oracle_options(O, opt)
+    exact = 0
+    for p in range(P):
+        b, ib = reffull.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
+        fl = np.zeros(N, np.uint8)
+        fl[ib] = 1
+        same = (int(res["num_iterations"][p]) == b.num_iterations and int(res["best_num_inliers"][p]) == b.best_num_inliers and
+                int(res["number_lo_iterations"][p]) == b.number_lo_iterations and (flags[offsets[p]:offsets[p + 1]] == fl).all())
+        d = np.rad2deg(S.problems.rot_error(S.problems.so3exp(np.array(b.r)), S.problems.so3exp(res["r"][p])))
+        if same:
+            exact += 1
+            assert d < 0.01
+            assert model_dist(res["E"][p] / np.linalg.norm(res["E"][p]), np.array(b.E) / np.linalg.norm(b.E)) < 1e-6
+        else:
+            assert d < 0.1 and abs(int(res["best_num_inliers"][p]) - b.best_num_inliers) <= 0.02 * N
+    assert exact >= 0.6 * P
+
+
+@pytest.mark.parametrize("n", [10000, 200000])
+def test_config_c5_scoring_stress(S, engine, orc, n):
+    """Config C5: 4096 hypotheses x 10k-200k correspondences, 90 % outliers, scoring kernel only
+    (correspondences split across CTAs, deterministic two-stage reduction)."""
+    pr = S.problems.make_problem(S.problems.make_rng(55, n), n, False, None, 1 / 600, int(0.9 * n), 20.0)
+    samples = np.array([S.sample(3, 0, i, 3, n) for i in range(1024)], np.int32)
+    models, nm = engine.minimal_solve(pr.rays, samples, 0)
+    m6 = models.reshape(-1, 6)
+    assert len(m6) == 4096
+    s32, c32, ms = engine.score(m6, pr.rays, THR2)
+    s32b, c32b, _ = engine.score(m6, pr.rays, THR2)
+    assert (s32 == s32b).all() and (c32 == c32b).all()  # deterministic
+    sub = np.arange(0, 4096, 64 if n > 50000 else 16)
+    so, co, _ = orc.score_batch(m6[sub], pr.rays, THR2)
+    ok = ~np.isnan(so)
+    assert np.max(np.abs(s32[sub][ok] - so[ok]) / so[ok]) < 2e-4
+    for k, j in enumerate(sub[:8]):
+        e = orc.sampson(E_of(m6[j]), pr.rays)
+        band = int((np.abs(e / THR2 - 1) < 1e-3).sum())
+        assert abs(int(c32[j]) - int(co[k])) <= band
+    # the best hypothesis of the FP32 kernel is (one of) the best in float64
+    best = int(np.nanargmin(s32))
+    sb, _ = orc.score(E_of(m6[best]), pr.rays, THR2)
+    assert sb <= np.nanmin(so) * (1 + 1e-3)
+    print("C5 n=%d: %.3f ms -> %.3e evals/s" % (n, ms, 4096.0 * n / (ms * 1e-3)))
