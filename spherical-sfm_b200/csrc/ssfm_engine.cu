@@ -574,7 +574,9 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   cfg.R = std::max(cfg.first_cap, cfg.round_cap);
   cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
   cfg.thr32 = (float)P.thr2;
-  cfg.small_refit_threads_min = 8192;
+  // 0: every small refit is solved one thread per problem.  (A warp-per-refit path for thin waves has lower
+  // latency but sums in a different order, which would make results depend on how many pairs share a wave.)
+  cfg.small_refit_threads_min = 0;
   if (const char* e = getenv("SSFM_REFIT_THREADS_MIN")) cfg.small_refit_threads_min = atoi(e);
 
   // Pass lists per worker: contiguous ranges balanced by correspondence count.

@@ -128,8 +128,11 @@ __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, in
 // models layout: [a][m*6+i][R]  (SoA over the look-ahead slot so both this kernel's stores and the
 // scoring kernel's loads are coalesced)
 // ------------------------------------------------------------------------------------------
+#ifndef SSFM_SOLVE_MINBLOCKS
+#define SSFM_SOLVE_MINBLOCKS 4
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(64) k_sample_solve(Params P, const double* __restrict__ rays,
+__global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Params P, const double* __restrict__ rays,
                                                      const long long* __restrict__ offsets, int pair0,
                                                      const int* __restrict__ active, const int* __restrict__ navail,
                                                      const PairState* __restrict__ states, int R,
@@ -476,7 +479,10 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Param
 // small: one THREAD per refit (<= kSmallRefit residuals), 32 independent LMs per warp.  Iteration
 // counts vary from ~6 to 200 between problems, so lanes pull tasks from a queue: a lane whose LM
 // terminates fetches the next task while its neighbours keep iterating.
-__global__ void __launch_bounds__(64) k_refit_small(Params P, const double* __restrict__ rays,
+#ifndef SSFM_REFIT_MINBLOCKS
+#define SSFM_REFIT_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params P, const double* __restrict__ rays,
                                                     const long long* __restrict__ offsets, int pair0,
                                                     const int* __restrict__ parked, int ntasks, int* queue_head,
                                                     const PairState* __restrict__ states, const int* __restrict__ list_a,

@@ -334,3 +334,53 @@ def test_config_c5_scoring_stress(S, engine, orc, n):
     sb, _ = orc.score(E_of(m6[best]), pr.rays, THR2)
     assert sb <= np.nanmin(so) * (1 + 1e-3)
     print("C5 n=%d: %.3f ms -> %.3e evals/s" % (n, ms, 4096.0 * n / (ms * 1e-3)))
+
+
+def test_large_batches_multi_pass_pipelined_and_multi_stream(S, engine):
+    """Engine plumbing at scale: more pairs than one pass holds (131 072), the pipelined (chunked) upload
+    of ssfm_estimate_pairs, and several concurrent streams must all give bit-identical tables."""
+    import bench
+    P, N = 140000, 48
+    rays_t, offsets, _ = bench.make_batch_torch(P, N, 0.5, 7, "cuda")
+    rays = rays_t.cpu().numpy()
+    opt = S.pipeline_options(THR2)
+    a, fa = engine.estimate_pairs(rays, offsets, opt)  # pipelined upload (P > 2 x 16384), 2 passes
+    os.environ["SSFM_NO_PIPELINE"] = "1"
+    try:
+        b, fb = engine.estimate_pairs(rays, offsets, opt)
+    finally:
+        del os.environ["SSFM_NO_PIPELINE"]
+    assert a.tobytes() == b.tobytes() and (fa == fb).all()
+    os.environ["SSFM_WORKERS"] = "3"
+    try:
+        engine.upload(rays, offsets)
+        engine.run(opt)
+        c, fc = engine.download()
+    finally:
+        del os.environ["SSFM_WORKERS"]
+    assert a.tobytes() == c.tobytes() and (fa == fc).all()
+    assert (a["status"] == 0).mean() > 0.99 and (a["num_iterations"] >= 100).all()
+    # a sub-batch reproduces its rows (results do not depend on batch composition)
+    sl = slice(131000, 131100)
+    opt2 = S.pipeline_options(THR2, first_pair_id=sl.start)
+    d, fd = engine.estimate_pairs(rays[offsets[sl.start]:offsets[sl.stop]], offsets[sl.start:sl.stop + 1] - offsets[sl.start], opt2)
+    assert d.tobytes() == a[sl].tobytes()
+
+
+def test_general_rays_use_general_kernel(S, O, engine, orc):
+    """Rays that are not (x, y, 1): unit-norm bearing vectors (examples/test_spherical_relpose.cpp:426-429)
+    go through the general FP32 kernel and must match the oracle just the same."""
+    rays, offsets, probs = S.problems.make_batch(31, 8, 700, noise=1 / 600, outlier_frac=0.5)
+    rays = rays.copy()
+    rays[:, :3] /= np.linalg.norm(rays[:, :3], axis=1, keepdims=True)
+    rays[:, 3:] /= np.linalg.norm(rays[:, 3:], axis=1, keepdims=True)
+    opt = S.pipeline_options(THR2 / 4)
+    res, flags = engine.estimate_pairs(rays, offsets, opt)
+    oopt = to_oracle_options(O, opt)
+    for p in range(8):
+        ref, inl = orc.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
+        fl = np.zeros(700, np.uint8)
+        fl[inl] = 1
+        assert int(res["num_iterations"][p]) == ref.num_iterations
+        assert int(res["best_num_inliers"][p]) == ref.best_num_inliers
+        assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
