@@ -186,7 +186,7 @@ def main():
         if rank != 0:
             return
         import spherical_sfm_b200 as S
-        npairs = 4096
+        npairs = 24576
         import torch
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         rays_t, offsets, _ = make_batch_torch(npairs, N, args.outliers, 1234, dev)
@@ -348,7 +348,7 @@ def main():
     except Exception as exc:  # the headline line must not die on the side measurement
         line["c5_scoring"] = {"error": str(exc)}
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_leg(rays_np[:4096 * N], N, args.cpu_seconds)
+        line["cpu_baseline"] = cpu_leg(rays_np[:min(P, 32768) * N], N, args.cpu_seconds)
     print(json.dumps(line))
     eng.close()
     if dist is not None:
