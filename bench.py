@@ -335,6 +335,37 @@ def main():
                      "ms_per_launch": score_ms_per_launch,
                      "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3)},
     }
+    # the caller-side variant: keypoints + matches + Kinv in, rays built on the device (8 B per match over PCIe)
+    try:
+        fpx = 600.0
+        kp_all = torch.empty((2 * P * N, 2), dtype=torch.float32, pin_memory=True)
+        rt = torch.from_numpy(rays_np)
+        kp_all[:P * N] = (rt[:, 0:2] * fpx).to(torch.float32)
+        kp_all[P * N:] = (rt[:, 3:5] * fpx).to(torch.float32)
+        idx = torch.arange(P * N, dtype=torch.int32)
+        mt_all = torch.stack([idx % N, idx % N], dim=1).contiguous()
+        kp_pairs = torch.empty((P, 2), dtype=torch.int32)
+        kp_pairs[:, 0] = torch.arange(P, dtype=torch.int32)
+        kp_pairs[:, 1] = torch.arange(P, dtype=torch.int32) + P
+        kp_off = np.arange(2 * P + 1, dtype=np.int64) * N
+        Kinv = np.array([[1 / fpx, 0, 0], [0, 1 / fpx, 0], [0, 0, 1.0]])
+        mt_pin = torch.empty(mt_all.shape, dtype=torch.int32, pin_memory=True)
+        mt_pin.copy_(mt_all)
+        args_m = (kp_all.numpy(), kp_off, kp_pairs.numpy(), mt_pin.numpy(), offsets, Kinv, opt)
+        eng.estimate_pairs_from_matches(*args_m, out_results=out_res, out_flags=out_flags)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rm, _ = eng.estimate_pairs_from_matches(*args_m, out_results=out_res, out_flags=out_flags)
+        barrier()
+        ms_m = (time.perf_counter() - t0) * 1e3 / args.steps
+        stm = eng.stats()
+        line["e2e_from_matches"] = {"value": float(rm["evals"].sum()) * world / (ms_m * 1e-3), "unit": "evals/s", "ms_per_step": ms_m,
+                                    "pairs_per_sec": world * P / (ms_m * 1e-3), "h2d_bytes_per_step": int(stm.h2d_bytes),
+                                    "note": "rank-0 time; keypoints are float32 pixels, so inputs differ from the RayPair runs by rounding"}
+        del kp_all, mt_all, mt_pin, rt
+    except Exception as exc:
+        line["e2e_from_matches"] = {"error": str(exc)}
     # config C5 (scoring stress: 4096 hypotheses x 200k correspondences, 90 % outliers), scoring kernel only
     try:
         n5 = 200000

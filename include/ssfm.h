@@ -33,7 +33,12 @@ enum {
 };
 
 /* Per-pair status. */
-enum { SSFM_PAIR_OK = 0, SSFM_PAIR_TOO_FEW_POINTS = 1, SSFM_PAIR_NO_MODEL = 2 };
+enum {
+  SSFM_PAIR_OK = 0,
+  SSFM_PAIR_TOO_FEW_POINTS = 1, /* fewer correspondences than the minimal sample (ransac.h:137-139) */
+  SSFM_PAIR_NO_MODEL = 2,
+  SSFM_PAIR_SKIPPED = 3         /* fewer correspondences than SsfmOptions.min_num_points (spherical_sfm_tools.cpp:351) */
+};
 
 /* Minimal solver (SphericalEstimator's use_poly_solver flag, include/sphericalsfm/spherical_estimator.h:13-15;
  * SphericalFastEstimator, include/sphericalsfm/spherical_fast_estimator.h). */
@@ -73,6 +78,8 @@ typedef struct SsfmOptions {
   int32_t fixed_budget;             /* MSAC_FIXED: estimators.size() (msac.h:77) */
   double fixed_prob_success;        /* MSAC_FIXED: 0.999 (msac.h:36) */
   uint32_t first_pair_id;           /* pair p of a batch draws from Philox key (random_seed, first_pair_id + p) */
+  int32_t min_num_points;           /* 0; pairs with fewer correspondences are skipped, like `m01.size() < min_num_inliers`
+                                       in estimate_pairwise (examples/spherical_sfm_tools.cpp:351) */
 } SsfmOptions;
 
 /* A batch of image pairs in CSR form: pair p owns correspondences [offsets[p], offsets[p+1]).
@@ -132,6 +139,25 @@ void ssfm_destroy(ssfm_handle h);
  * batch (1 = err < thr^2), or NULL. */
 int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions* opt, SsfmPairResult* results,
                         uint8_t* inlier_flags);
+
+/* The caller side of the path: estimate_pairwise builds every ray pair on the host as
+ * Kinv * (x, y, 1) from the two images' keypoints and the pair's matches (examples/spherical_sfm_tools.cpp:
+ * 357-376).  This entry takes the keypoints / matches / Kinv as they are and builds the rays on the device
+ * (float64, same operation order), so 8 bytes per match cross PCIe instead of 48. */
+typedef struct SsfmMatchBatch {
+  int32_t num_images;
+  const int64_t* keypoint_offsets; /* host, num_images + 1 */
+  const float* keypoints_xy;       /* host, 2 floats per keypoint (cv::Point2f, Features::points) */
+  int32_t num_pairs;
+  const int32_t* pair_images;      /* host, 2 per pair: index0, index1 (ImageMatch) */
+  const int64_t* match_offsets;    /* host, num_pairs + 1 */
+  const int32_t* matches;          /* host, 2 per match: keypoint index in image index0, in image index1, in the
+                                      iteration order of the Matches map */
+  double Kinv[9];                  /* Intrinsics::getKinv(), row-major */
+} SsfmMatchBatch;
+int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* batch);
+int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch, const SsfmOptions* opt,
+                                     SsfmPairResult* results, uint8_t* inlier_flags);
 
 /* The same call split into its three stages, so inputs can stay resident in HBM:
  * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */

@@ -23,7 +23,7 @@ _SOURCES = [os.path.join(_DIR, "csrc", f) for f in
                 os.path.join(_ROOT, "include", "ssfm.h")]
 
 SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_NO_DEVICE, SSFM_ERR_CUDA, SSFM_ERR_OOM = 0, 1, 2, 3, 4
-PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL = 0, 1, 2
+PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL, PAIR_SKIPPED = 0, 1, 2, 3
 SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM = 0, 1, 2
 DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED = 0, 1, 2
 
@@ -45,12 +45,20 @@ class SsfmOptions(C.Structure):
         ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
         ("solver", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("fixed_budget", C.c_int32), ("fixed_prob_success", C.c_double), ("first_pair_id", C.c_uint32),
+        ("min_num_points", C.c_int32),
     ]
 
 
 class SsfmBatch(C.Structure):
     _fields_ = [("num_pairs", C.c_int32), ("offsets", C.POINTER(C.c_int64)), ("rays", C.c_void_p),
                 ("rays_on_device", C.c_int32)]
+
+
+class SsfmMatchBatch(C.Structure):
+    """Keypoints + matches + Kinv, as estimate_pairwise holds them (examples/spherical_sfm_tools.cpp:335-376)."""
+    _fields_ = [("num_images", C.c_int32), ("keypoint_offsets", C.POINTER(C.c_int64)), ("keypoints_xy", C.POINTER(C.c_float)),
+                ("num_pairs", C.c_int32), ("pair_images", C.POINTER(C.c_int32)), ("match_offsets", C.POINTER(C.c_int64)),
+                ("matches", C.POINTER(C.c_int32)), ("Kinv", C.c_double * 9)]
 
 
 class SsfmPairResult(C.Structure):
@@ -114,7 +122,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
-    "ssfm_estimate_pairs", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
+    "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
     "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
@@ -218,6 +226,31 @@ class Engine:
                                          C.c_void_p(flags.ctypes.data) if want_flags and len(flags) else None))
         self._num_pairs = b.num_pairs
         self._num_corr = int(offsets[-1])
+        return res, flags
+
+    def estimate_pairs_from_matches(self, keypoints_xy, keypoint_offsets, pair_images, matches, match_offsets, Kinv, opt,
+                                    want_flags=True, out_results=None, out_flags=None):
+        """ssfm_estimate_pairs_from_matches: rays are built on the device from keypoints, matches and Kinv."""
+        kp = np.ascontiguousarray(keypoints_xy, np.float32).reshape(-1, 2)
+        kpo = np.ascontiguousarray(keypoint_offsets, np.int64)
+        pi = np.ascontiguousarray(pair_images, np.int32).reshape(-1, 2)
+        mt = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+        mo = np.ascontiguousarray(match_offsets, np.int64)
+        b = SsfmMatchBatch()
+        b.num_images = len(kpo) - 1
+        b.keypoint_offsets = _p(kpo, C.c_int64)
+        b.keypoints_xy = _p(kp, C.c_float)
+        b.num_pairs = len(pi)
+        b.pair_images = _p(pi, C.c_int32)
+        b.match_offsets = _p(mo, C.c_int64)
+        b.matches = _p(mt, C.c_int32)
+        b.Kinv = (C.c_double * 9)(*np.asarray(Kinv, np.float64).reshape(9))
+        res = out_results if out_results is not None else np.zeros(b.num_pairs, RESULT_DTYPE)
+        flags = (out_flags if out_flags is not None else np.zeros(int(mo[-1]), np.uint8)) if want_flags else None
+        _check(lib().ssfm_estimate_pairs_from_matches(self._h, C.byref(b), C.byref(opt), C.c_void_p(res.ctypes.data),
+                                                      C.c_void_p(flags.ctypes.data) if want_flags and len(flags) else None))
+        self._num_pairs = b.num_pairs
+        self._num_corr = int(mo[-1])
         return res, flags
 
     def stats(self):

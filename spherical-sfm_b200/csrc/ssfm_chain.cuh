@@ -30,6 +30,7 @@ struct Params {
   int fixed_budget;
   double fixed_prob;
   uint32_t first_pair_id;
+  int min_points;  // pairs with fewer correspondences are skipped
   float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
 };
 
@@ -589,7 +590,7 @@ SSFM_HD void init_state(const Params& P, int n, PairState& st) {
   st.cnt_best = 0;
   st.cnt_bestmin = 0;
   st.num_lo = 0;
-  st.done = n < 3 ? 1 : 0;  // kMinSampleSize > kNumData -> return 0 (ransac.h:137-139)
+  st.done = (n < 3 || n < P.min_points) ? 1 : 0;  // kMinSampleSize > kNumData -> return 0 (ransac.h:137-139)
   st.phase = PHASE_NONE;
   st.walk_j = 0;
   st.lm_n = 0;

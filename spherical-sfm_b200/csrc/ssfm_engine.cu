@@ -158,6 +158,7 @@ Params make_params(const SsfmOptions& o) {
   P.fixed_budget = o.fixed_budget;
   P.fixed_prob = o.fixed_prob_success;
   P.first_pair_id = o.first_pair_id;
+  P.min_points = o.min_num_points;
   P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
   return P;
@@ -395,6 +396,7 @@ void ssfm_default_options(SsfmOptions* o) {
   o->fixed_budget = 512;
   o->fixed_prob_success = 0.999;
   o->first_pair_id = 0u;
+  o->min_num_points = 0;
 }
 
 int ssfm_create(int device, ssfm_handle* out) {
@@ -545,6 +547,75 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
 }
 
 int ssfm_upload(ssfm_handle h, const SsfmBatch* b) { return upload_impl(h, b, false); }
+
+int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) {
+  if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
+  if (b->num_pairs < 0 || b->num_images < 0) return fail(SSFM_ERR_INVALID, "bad batch");
+  if (b->num_pairs > 0 && (!b->keypoint_offsets || !b->keypoints_xy || !b->pair_images || !b->match_offsets || !b->matches))
+    return fail(SSFM_ERR_INVALID, "NULL array in match batch");
+  SSFM_CK(cudaSetDevice(h->device));
+  const int P = b->num_pairs;
+  const long long M = P > 0 ? b->match_offsets[P] : 0;
+  const long long NK = b->num_images > 0 ? b->keypoint_offsets[b->num_images] : 0;
+  for (int p = 0; p < P; ++p) {
+    const int i0 = b->pair_images[2 * p], i1 = b->pair_images[2 * p + 1];
+    if (i0 < 0 || i1 < 0 || i0 >= b->num_images || i1 >= b->num_images) return fail(SSFM_ERR_INVALID, "pair image index out of range");
+    if (b->match_offsets[p + 1] < b->match_offsets[p]) return fail(SSFM_ERR_INVALID, "match_offsets must be non-decreasing");
+  }  // (keypoint indices of the individual matches are range-checked by the kernel)
+  DevBuf<float> d_kp;
+  DevBuf<long long> d_kpoff;
+  DevBuf<int> d_pairs, d_matches;
+  DevBuf<double> d_kinv;
+  struct Guard {
+    DevBuf<float>& a; DevBuf<long long>& b; DevBuf<int>& c; DevBuf<int>& d; DevBuf<double>& e;
+    ~Guard() { a.release(); b.release(); c.release(); d.release(); e.release(); }
+  } guard{d_kp, d_kpoff, d_pairs, d_matches, d_kinv};
+  SSFM_CK(d_kp.ensure((size_t)std::max<long long>(2 * NK, 2)));
+  SSFM_CK(d_kpoff.ensure(b->num_images + 1));
+  SSFM_CK(d_pairs.ensure((size_t)std::max(2 * P, 2)));
+  SSFM_CK(d_matches.ensure((size_t)std::max<long long>(2 * M, 2)));
+  SSFM_CK(d_kinv.ensure(9));
+  SSFM_CK(h->rays_own.ensure((size_t)std::max<long long>(6 * M, 6)));
+  SSFM_CK(h->offsets.ensure(P + 1));
+  SSFM_CK(h->counts.ensure(8));
+  SSFM_CK(cudaMemsetAsync(h->counts.p + 3, 0, sizeof(int), h->stream));
+  if (NK > 0) SSFM_CK(cudaMemcpyAsync(d_kp.p, b->keypoints_xy, sizeof(float) * 2 * (size_t)NK, cudaMemcpyHostToDevice, h->stream));
+  if (b->num_images > 0)
+    SSFM_CK(cudaMemcpyAsync(d_kpoff.p, b->keypoint_offsets, sizeof(long long) * (b->num_images + 1), cudaMemcpyHostToDevice, h->stream));
+  if (P > 0) {
+    SSFM_CK(cudaMemcpyAsync(d_pairs.p, b->pair_images, sizeof(int) * 2 * (size_t)P, cudaMemcpyHostToDevice, h->stream));
+    SSFM_CK(cudaMemcpyAsync(h->offsets.p, b->match_offsets, sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (M > 0) SSFM_CK(cudaMemcpyAsync(d_matches.p, b->matches, sizeof(int) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(d_kinv.p, b->Kinv, sizeof(double) * 9, cudaMemcpyHostToDevice, h->stream));
+  if (M > 0) {
+    k_build_rays<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const float2*>(d_kp.p), d_kpoff.p, d_pairs.p,
+                                                                     h->offsets.p, P, reinterpret_cast<const int2*>(d_matches.p), M,
+                                                                     d_kinv.p, h->rays_own.p, h->counts.p + 3);
+    SSFM_CK(cudaGetLastError());
+  }
+  SSFM_CK(cudaMemcpyAsync(h->h_count + 3, h->counts.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  if (h->h_count[3] != 0) return fail(SSFM_ERR_INVALID, "match keypoint index out of range");
+  // from here on it is an ordinary batch whose rays already live in HBM
+  SsfmBatch rb;
+  rb.num_pairs = P;
+  rb.offsets = b->match_offsets;
+  rb.rays = h->rays_own.p;
+  rb.rays_on_device = 1;
+  const int rc = upload_impl(h, &rb, false);
+  h->stats.h2d_bytes = (long long)(8 * NK + 8 * (long long)P + 8 * M + 8 * (P + 1) + 8 * (b->num_images + 1) + 72);
+  return rc;
+}
+
+int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch, const SsfmOptions* opt,
+                                     SsfmPairResult* results, uint8_t* inlier_flags) {
+  if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
+  if (int rc = check_options(opt)) return rc;
+  if (int rc = ssfm_upload_matches(h, batch)) return rc;
+  if (int rc = ssfm_run(h, opt)) return rc;
+  return ssfm_download(h, results, inlier_flags);
+}
 
 int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (!h) return fail(SSFM_ERR_INVALID, "NULL handle");

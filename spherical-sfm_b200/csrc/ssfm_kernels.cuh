@@ -104,6 +104,46 @@ __global__ void k_pack(const double* __restrict__ rays, long long m, float4* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// k_build_rays: the ray construction of estimate_pairwise (examples/spherical_sfm_tools.cpp:357-376) on the
+// device.  One thread per match: loc = Kinv * (x, y, 1) in float64 with Eigen's row.col accumulation order
+// ((k0 x + k1 y) + k2), no FMA contraction, so the rays are bit-identical to the host's.
+// ------------------------------------------------------------------------------------------
+__global__ void k_build_rays(const float2* __restrict__ kp, const long long* __restrict__ kp_off,
+                             const int* __restrict__ pair_images, const long long* __restrict__ match_off, int npairs,
+                             const int2* __restrict__ matches, long long m, const double* __restrict__ Kinv,
+                             double* __restrict__ rays, int* __restrict__ bad_index) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int lo = 0, hi = npairs;  // last pair whose first match is <= i
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (match_off[mid] <= i) lo = mid; else hi = mid;
+  }
+  const int img0 = pair_images[2 * lo], img1 = pair_images[2 * lo + 1];
+  const int2 mt = matches[i];
+  const long long b0 = kp_off[img0], b1 = kp_off[img1];
+  if (mt.x < 0 || mt.y < 0 || mt.x >= kp_off[img0 + 1] - b0 || mt.y >= kp_off[img1 + 1] - b1) {
+    *bad_index = 1;  // reported as SSFM_ERR_INVALID by the host
+    return;
+  }
+  const float2 p0 = kp[b0 + mt.x];
+  const float2 p1 = kp[b1 + mt.y];
+  double k[9];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) k[q] = Kinv[q];
+  double out[6];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    out[r] = add_rn(add_rn(mul_rn(k[3 * r], (double)p0.x), mul_rn(k[3 * r + 1], (double)p0.y)), k[3 * r + 2]);
+    out[3 + r] = add_rn(add_rn(mul_rn(k[3 * r], (double)p1.x), mul_rn(k[3 * r + 1], (double)p1.y)), k[3 * r + 2]);
+  }
+  double2* dst = reinterpret_cast<double2*>(rays + 6 * i);
+  dst[0] = make_double2(out[0], out[1]);
+  dst[1] = make_double2(out[2], out[3]);
+  dst[2] = make_double2(out[4], out[5]);
+}
+
+// ------------------------------------------------------------------------------------------
 // k_init_pairs
 // ------------------------------------------------------------------------------------------
 __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, int pair0, int npairs, PairState* states,
@@ -566,7 +606,7 @@ __global__ void k_finish_trivial(Params P, const long long* __restrict__ offsets
   o.num_iterations = 0;
   o.best_num_inliers = 0;
   o.number_lo_iterations = 0;
-  o.status = n < 3 ? SSFM_PAIR_TOO_FEW_POINTS : SSFM_PAIR_NO_MODEL;
+  o.status = n < 3 ? SSFM_PAIR_TOO_FEW_POINTS : (n < P.min_points ? SSFM_PAIR_SKIPPED : SSFM_PAIR_NO_MODEL);
   o.evals = 0;
   results[a] = o;
   if (flags)

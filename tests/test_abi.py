@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol(S):
     G.build()
     L = S.lib()
     names = declared_functions()
-    assert len(names) >= 20
+    assert len(names) >= 22
     for n in names:
         assert hasattr(L, n), n
     assert sorted(S.EXPORTED_SYMBOLS) == names
@@ -41,7 +41,7 @@ def test_built_for_sm_100a_with_tma(S):
 
 def test_struct_layouts(S):
     assert C.sizeof(S.SsfmPairResult) == 160 and S.RESULT_DTYPE.itemsize == 160
-    assert C.sizeof(S.SsfmOptions) == 96
+    assert C.sizeof(S.SsfmOptions) == 96  # min_num_points fills the tail padding
     assert C.sizeof(S.SsfmBatch) == 32
 
 

@@ -384,3 +384,59 @@ def test_general_rays_use_general_kernel(S, O, engine, orc):
         assert int(res["num_iterations"][p]) == ref.num_iterations
         assert int(res["best_num_inliers"][p]) == ref.best_num_inliers
         assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
+
+
+def test_rays_built_on_device_from_keypoints_and_matches(S, O, engine, orc):
+    """ssfm_estimate_pairs_from_matches: the ray construction of estimate_pairwise
+    (examples/spherical_sfm_tools.cpp:357-376: loc = Kinv * (x, y, 1) per keypoint of each match) done on
+    the device must give exactly the result of building the RayPairList on the host; pairs with fewer matches
+    than min_num_points are skipped like `m01.size() < min_num_inliers` (:351)."""
+    rng = np.random.default_rng(4)
+    f, cx, cy = 600.0, 320.0, 240.0
+    K = np.array([[f, 0, cx], [0, f, cy], [0, 0, 1.0]])
+    Kinv = np.linalg.inv(K)
+    n_img, pairs = 5, [(0, 1), (1, 2), (2, 3), (0, 4), (3, 4)]
+    sizes = [900, 700, 50, 1200, 400]
+    kps = [[] for _ in range(n_img)]
+    matches, moffs = [], [0]
+    for (i0, i1), n in zip(pairs, sizes):
+        pr = S.problems.make_problem(S.problems.make_rng(41, i0 * 10 + i1), n, False, None, 1 / 600, n // 2, 20.0)
+        px0 = (pr.rays[:, :2] * f + [cx, cy]).astype(np.float32)  # cv::Point2f keypoints
+        px1 = (pr.rays[:, 3:5] * f + [cx, cy]).astype(np.float32)
+        b0, b1 = len(kps[i0]), len(kps[i1])
+        kps[i0].extend(px0.tolist())
+        kps[i1].extend(px1.tolist())
+        matches.extend([(b0 + k, b1 + k) for k in range(n)])
+        moffs.append(moffs[-1] + n)
+    kp_off = np.concatenate([[0], np.cumsum([len(k) for k in kps])]).astype(np.int64)
+    kp = np.array([p for k in kps for p in k], np.float32)
+    matches = np.array(matches, np.int32)
+    opt = S.pipeline_options((2.0 * Kinv[0, 0]) ** 2, min_num_points=100)  # spherical_sfm_tools.cpp:315
+    res, flags = engine.estimate_pairs_from_matches(kp, kp_off, np.array(pairs, np.int32), matches, np.array(moffs, np.int64), Kinv, opt)
+    # host-side construction, exactly as the reference does it (float keypoints -> double, Kinv * (x, y, 1))
+    rays = np.zeros((len(matches), 6))
+    for p, (i0, i1) in enumerate(pairs):
+        for i in range(moffs[p], moffs[p + 1]):
+            a = kp[kp_off[i0] + matches[i, 0]].astype(np.float64)
+            b = kp[kp_off[i1] + matches[i, 1]].astype(np.float64)
+            rays[i, :3] = [(Kinv[r, 0] * a[0] + Kinv[r, 1] * a[1]) + Kinv[r, 2] for r in range(3)]
+            rays[i, 3:] = [(Kinv[r, 0] * b[0] + Kinv[r, 1] * b[1]) + Kinv[r, 2] for r in range(3)]
+    res2, flags2 = engine.estimate_pairs(rays, np.array(moffs, np.int64), opt)
+    assert res.tobytes() == res2.tobytes() and (flags == flags2).all()
+    assert res["status"].tolist() == [0, 0, S.PAIR_SKIPPED, 0, 0]
+    oopt = to_oracle_options(O, opt)
+    for p in (0, 1, 3, 4):
+        ref, inl = orc.estimate_pair(rays[moffs[p]:moffs[p + 1]], oopt, p)
+        assert int(res["num_iterations"][p]) == ref.num_iterations and int(res["best_num_inliers"][p]) == ref.best_num_inliers
+
+
+def test_from_matches_rejects_bad_indices(S, engine):
+    kp = np.zeros((10, 2), np.float32)
+    opt = S.pipeline_options(THR2)
+    with pytest.raises(S.SsfmError) as e:
+        engine.estimate_pairs_from_matches(kp, np.array([0, 5, 10], np.int64), np.array([[0, 1]], np.int32),
+                                           np.array([[0, 0], [1, 1], [2, 7]], np.int32), np.array([0, 3], np.int64), np.eye(3), opt)
+    assert e.value.code == S.SSFM_ERR_INVALID
+    with pytest.raises(S.SsfmError):
+        engine.estimate_pairs_from_matches(kp, np.array([0, 5, 10], np.int64), np.array([[0, 2]], np.int32),
+                                           np.array([[0, 0]], np.int32), np.array([0, 1], np.int64), np.eye(3), opt)
