@@ -203,6 +203,13 @@ int ssfm_non_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const i
 /* decompose_spherical_essential_matrix (src/spherical_utils.cpp:16-66), batched. */
 int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward, double* r3, double* t3);
 
+/* The focal search's inner step: for every trial focal f, every pair's E is rescaled
+ * E' = T E T, T = diag(f/f0, f/f0, 1), and decomposed again (transform_image_matches,
+ * examples/spherical_sfm_tools.cpp:1118-1131; 1024 trials x P pairs in find_best_focal_length_random).
+ * scales: num_scales values of f/f0.  r3: num_scales x num x 3 (so3ln of the chosen rotation). */
+int ssfm_decompose_rescaled(ssfm_handle h, const double* E9, int32_t num, const double* scales, int32_t num_scales,
+                            int32_t inward, double* r3);
+
 /* The LO generator: `ncalls` consecutive RandomShuffleAndResize calls (include/RansacLib/utils.h:48-52)
  * on iota vectors, one std::mt19937(seed) stream (ransac.h:143-144), executed on the device. */
 int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t* sizes, const int32_t* targets,

@@ -123,7 +123,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose",
+    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -327,6 +327,15 @@ class Engine:
         t = np.zeros((len(E), 3))
         _check(lib().ssfm_decompose(self._h, _p(E, C.c_double), len(E), int(inward), _p(r, C.c_double), _p(t, C.c_double)))
         return r, t
+
+    def decompose_rescaled(self, E9, scales, inward=False):
+        """transform_image_matches (examples/spherical_sfm_tools.cpp:1118-1131): r of T E T for every scale."""
+        E = np.ascontiguousarray(E9, np.float64).reshape(-1, 9)
+        sc = np.ascontiguousarray(scales, np.float64)
+        r = np.zeros((len(sc), len(E), 3))
+        _check(lib().ssfm_decompose_rescaled(self._h, _p(E, C.c_double), len(E), _p(sc, C.c_double), len(sc), int(inward),
+                                             _p(r, C.c_double)))
+        return r
 
     def lo_shuffle(self, seed, sizes, targets):
         sizes = np.ascontiguousarray(sizes, np.int32)

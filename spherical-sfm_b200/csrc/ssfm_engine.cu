@@ -954,6 +954,26 @@ int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward,
   return SSFM_OK;
 }
 
+int ssfm_decompose_rescaled(ssfm_handle h, const double* E9, int32_t num, const double* scales, int32_t nscales, int32_t inward,
+                            double* r3) {
+  if (!h || !E9 || !scales || !r3 || num < 0 || nscales < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (num == 0 || nscales == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_e, (size_t)num * 9) SSFM_KEEP(g, b_e)
+  SSFM_TMP(double, b_s, (size_t)nscales) SSFM_KEEP(g, b_s)
+  SSFM_TMP(double, b_r, (size_t)num * nscales * 3) SSFM_KEEP(g, b_r)
+  double* de = (double*)g.ptrs[0]; double* dsc = (double*)g.ptrs[1]; double* dr = (double*)g.ptrs[2];
+  SSFM_CK(cudaMemcpyAsync(de, E9, sizeof(double) * 9 * (size_t)num, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dsc, scales, sizeof(double) * (size_t)nscales, cudaMemcpyHostToDevice, h->stream));
+  const long long total = (long long)num * nscales;
+  k_decompose_rescaled<<<(unsigned)((total + 127) / 128), 128, 0, h->stream>>>(de, num, dsc, nscales, inward, dr);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(r3, dr, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
 int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t* sizes, const int32_t* targets, int32_t* out) {
   if (!h || !sizes || !targets || !out || ncalls < 0) return fail(SSFM_ERR_INVALID, "bad argument");
   if (ncalls == 0) return SSFM_OK;

@@ -681,6 +681,23 @@ __global__ void k_decompose(const double* __restrict__ E9, int num, int inward, 
   for (int k = 0; k < 3; ++k) { r3[(size_t)i * 3 + k] = r[k]; t3[(size_t)i * 3 + k] = t[k]; }
 }
 
+// transform_image_matches (examples/spherical_sfm_tools.cpp:1118-1131): E' = T E T, T = diag(s, s, 1), decompose.
+__global__ void k_decompose_rescaled(const double* __restrict__ E9, int num, const double* __restrict__ scales, int nscales,
+                                     int inward, double* __restrict__ r3) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)num * nscales) return;
+  const int pair = (int)(i % num), sc = (int)(i / num);
+  const double s = scales[sc];
+  const double T[3] = {s, s, 1.0};
+  double E[9], r[3], t[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) E[3 * a + b] = (T[a] * E9[(size_t)pair * 9 + 3 * a + b]) * T[b];
+  decompose_spherical_E(E, inward != 0, r, t);
+  for (int k = 0; k < 3; ++k) r3[(size_t)i * 3 + k] = r[k];
+}
+
 __global__ void k_lo_shuffle(uint32_t seed, int ncalls, const int* __restrict__ sizes, const int* __restrict__ targets,
                              uint32_t* mt, int* work, int* out) {
   WarpCtx cx{(int)(threadIdx.x & 31)};

@@ -22,7 +22,7 @@ def test_library_builds_and_exports_every_declared_symbol(S):
     G.build()
     L = S.lib()
     names = declared_functions()
-    assert len(names) >= 22
+    assert len(names) >= 23
     for n in names:
         assert hasattr(L, n), n
     assert sorted(S.EXPORTED_SYMBOLS) == names

@@ -440,3 +440,21 @@ def test_from_matches_rejects_bad_indices(S, engine):
     with pytest.raises(S.SsfmError):
         engine.estimate_pairs_from_matches(kp, np.array([0, 5, 10], np.int64), np.array([[0, 2]], np.int32),
                                            np.array([[0, 0]], np.int32), np.array([0, 1], np.int64), np.eye(3), opt)
+
+
+def test_decompose_rescaled_matches_oracle(S, engine, orc):
+    """Focal-search inner step: E' = T E T with T = diag(f/f0, f/f0, 1), then decompose (1118-1131)."""
+    rng = np.random.default_rng(9)
+    Es = []
+    for _ in range(40):
+        r = rng.standard_normal(3)
+        r *= rng.uniform(0.02, 0.5) / np.linalg.norm(r)
+        Es.append(orc.make_E(r).reshape(9))
+    Es = np.array(Es)
+    scales = np.array([0.5, 0.8, 1.0, 1.25, 2.0])
+    got = engine.decompose_rescaled(Es, scales)
+    for si, s in enumerate(scales):
+        T = np.diag([s, s, 1.0])
+        for k in range(len(Es)):
+            want, _ = orc.decompose(T @ Es[k].reshape(3, 3) @ T)
+            assert np.abs(got[si, k] - want).max() < 1e-9
