@@ -310,7 +310,7 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
       const float4* sa = sm.a[s];
       const float4* sb = sm.b[UNITZ ? 0 : s];
       float tacc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
       for (int i = 0; i < n; ++i) {
         const float4 ca = sa[i];
         float4 cb;
