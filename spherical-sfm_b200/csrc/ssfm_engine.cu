@@ -651,7 +651,9 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (const char* e = getenv("SSFM_REFIT_THREADS_MIN")) cfg.small_refit_threads_min = atoi(e);
 
   // Pass lists per worker: contiguous ranges balanced by correspondence count.
-  int nw = 1;
+  // Resident batch: one stream (a second one gains ~1 %).  While the upload is still streaming in
+  // (ssfm_estimate_pairs), two streams: one's upload waits and thin refit waves hide behind the other's scoring.
+  int nw = (!h->up_bounds.empty() && h->P >= 4096) ? 2 : 1;
   if (const char* e = getenv("SSFM_WORKERS")) nw = std::max(1, std::min(kMaxWorkers, atoi(e)));
   nw = std::max(1, std::min(nw, std::max(h->P, 1)));
   std::vector<std::vector<PassDesc>> plan(nw);
