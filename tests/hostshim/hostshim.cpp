@@ -119,7 +119,8 @@ uint32_t hs_required_iterations(double w, double eta, int k, uint32_t lo, uint32
 // The engine's round structure, emulated serially for one pair.
 void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pair_id, HsResult* out,
                       unsigned char* flags) {
-  Params P;
+  Params P{};
+  P.min_points = 0;
   P.min_iters = hp->min_iters; P.max_iters = hp->max_iters;
   P.eta = 1.0 - hp->success_probability; P.thr2 = hp->thr2; P.seed = hp->seed;
   P.num_lo_steps = hp->num_lo_steps; P.thr_mult = hp->thr_mult; P.num_lsq_iters = hp->num_lsq_iters;
