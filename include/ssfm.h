@@ -52,8 +52,13 @@ enum {
 enum {
   SSFM_DRIVER_LO_MSAC = 0,      /* ransac_lib::LocallyOptimizedMSAC::EstimateModel, include/RansacLib/ransac.h:128-275 */
   SSFM_DRIVER_VANILLA_MSAC = 1, /* ransac_lib::VanillaMSAC::EstimateModel,          evaluation/vanilla_ransac.h:23-99 */
-  SSFM_DRIVER_MSAC_FIXED = 2    /* sphericalsfm::MSAC::compute (fixed hypothesis budget, '<=' inlier test),
+  SSFM_DRIVER_MSAC_FIXED = 2,   /* sphericalsfm::MSAC::compute (fixed hypothesis budget, '<=' inlier test),
                                    include/sphericalsfm/msac.h:67-131 */
+  SSFM_DRIVER_PREEMPTIVE = 3    /* sphericalsfm::PreemptiveRANSAC::compute, include/sphericalsfm/preemptive_ransac.h:46-139:
+                                   fixed_budget hypotheses from selection samples of m+1 correspondences (the extra
+                                   one disambiguates the roots), inlier counting in blocks of preemptive_block
+                                   observations, survivors halved every preemptive_block blocks, '<=' inlier test.
+                                   best_model_score = the winner's legacy MSAC cost (msac.h:56-64). */
 };
 
 /* RansacOptions + LORansacOptions, field for field (include/RansacLib/ransac.h:47-92), plus the
@@ -75,11 +80,13 @@ typedef struct SsfmOptions {
   int32_t solver;                   /* SSFM_SOLVER_* */
   int32_t driver;                   /* SSFM_DRIVER_* */
   int32_t inward;                   /* SphericalEstimator(.., inward) */
-  int32_t fixed_budget;             /* MSAC_FIXED: estimators.size() (msac.h:77) */
+  int32_t fixed_budget;             /* MSAC_FIXED, PREEMPTIVE: estimators.size() (msac.h:77, preemptive_ransac.h:49) */
   double fixed_prob_success;        /* MSAC_FIXED: 0.999 (msac.h:36) */
   uint32_t first_pair_id;           /* pair p of a batch draws from Philox key (random_seed, first_pair_id + p) */
   int32_t min_num_points;           /* 0; pairs with fewer correspondences are skipped, like `m01.size() < min_num_inliers`
                                        in estimate_pairwise (examples/spherical_sfm_tools.cpp:351) */
+  int32_t preemptive_block;         /* 10; PREEMPTIVE: B (preemptive_ransac.h:34,40) */
+  int32_t reserved;
 } SsfmOptions;
 
 /* A batch of image pairs in CSR form: pair p owns correspondences [offsets[p], offsets[p+1]).
@@ -174,6 +181,11 @@ int ssfm_device_results(ssfm_handle h, void** dev_ptr, int32_t* num_pairs);
 /* The minimal sample of iteration `iter` of pair `pair`: replaces UniformSampling::Sample
  * (include/RansacLib/sampling.h:58-64).  Host function; the device code uses the same routine. */
 int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t n, int32_t* idx);
+/* random_sample of the legacy drivers (include/sphericalsfm/preemptive_ransac.h:8-28): Knuth 3.4.2S selection
+ * sampling, k of n_total records in increasing order.  The reference draws from the C library's rand(); here
+ * draw j of hypothesis h is word (j%4) of Philox(counter=(h, j/4, 1, 0), key=(seed, pair)) >> 1.  Host-side,
+ * pure function. */
+int ssfm_selection_sample(uint32_t seed, uint32_t pair, uint32_t hypothesis, int32_t n_total, int32_t k, int32_t* idx);
 
 /* SphericalEstimator::MinimalSolver (src/spherical_estimator.cpp:80-84) for `num_samples`
  * samples of 3 indices into `rays` (n correspondences, host).  models: num_samples x 4 x 6 doubles

@@ -8,6 +8,9 @@
 //   ransac_lib::LocallyOptimizedMSAC<M,MV,Solver>::EstimateModel   ssfm_b200::LocallyOptimizedMSAC<M,MV,Solver>::EstimateModel
 //     (include/RansacLib/ransac.h:128-129)                           (same signature; one GPU call per pair)
 //   ransac_lib::VanillaMSAC (evaluation/vanilla_ransac.h:23)   ssfm_b200::VanillaMSAC
+//   sphericalsfm::MSAC<List,Est>::compute (msac.h:67-131)     ssfm_b200::MSAC<List,Est>::compute            (legacy drivers of the
+//   sphericalsfm::PreemptiveRANSAC<List,Est>::compute         ssfm_b200::PreemptiveRANSAC<List,Est>::compute  Sturm-variant estimator;
+//     (preemptive_ransac.h:46-139)                            + ssfm_b200::GpuSphericalFastEstimator           same signatures)
 //   the `#pragma omp parallel for` over pairs                  ssfm_b200::EstimatePairs (ONE call for all pairs)
 //     (examples/spherical_sfm_tools.cpp:332-420)
 //
@@ -263,6 +266,100 @@ class VanillaMSAC {  // evaluation/vanilla_ransac.h:17-23
   template <class Options, class Statistics>
   int EstimateModel(const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) const {
     return detail::estimate_one(SSFM_DRIVER_VANILLA_MSAC, options, solver, best_model, statistics);
+  }
+};
+
+// ---- the legacy drivers (include/sphericalsfm/msac.h, preemptive_ransac.h) ----------------------------
+// Upstream they take a vector of pre-allocated estimators (one per hypothesis) and return a pointer to the
+// winning one.  Here the hypotheses live on the device: the vector's size is the hypothesis budget, and the
+// winner's model is written into estimators[0], which is what *best_estimator points to on return.
+template <class Matrix3 = Mat3d>
+struct GpuSphericalFastEstimator {  // include/sphericalsfm/spherical_fast_estimator.h:8-24
+  Matrix3 E;
+  double r[3] = {0, 0, 0}, t[3] = {0, 0, 0};  // decomposeE(inward, r, t) of the winner (:290-341), filled by compute()
+  static constexpr int kSolver = SSFM_SOLVER_FAST_STURM;
+  int sampleSize() { return 3; }
+  bool canRefine() { return true; }
+  template <class Vector3>
+  void decomposeE(bool /*inward*/, Vector3& r_out, Vector3& t_out) const {
+    for (int i = 0; i < 3; ++i) { r_out[i] = r[i]; t_out[i] = t[i]; }
+  }
+};
+
+namespace detail {
+template <class It, class EstimatorType>
+int legacy_compute(const Engine& eng, SsfmOptions o, It begin, It end, std::vector<EstimatorType*>& estimators,
+                   EstimatorType** best_estimator, std::vector<bool>& inliers, int* iter) {
+  static_assert(sizeof(*begin) == 48, "RayPair must be two packed 3-vectors of double");
+  const int n = (int)(end - begin);
+  if (estimators.empty()) throw Error(SSFM_ERR_INVALID, "no estimators (the vector's size is the hypothesis budget)");
+  o.solver = EstimatorType::kSolver;
+  o.fixed_budget = (int32_t)estimators.size();
+  const int64_t offsets[2] = {0, n};
+  SsfmBatch b;
+  b.num_pairs = 1;
+  b.offsets = offsets;
+  b.rays = n > 0 ? reinterpret_cast<const double*>(&*begin) : nullptr;
+  b.rays_on_device = 0;
+  SsfmPairResult res;
+  std::vector<uint8_t> flags(n > 0 ? n : 1);
+  check(ssfm_estimate_pairs(eng.get(), &b, &o, &res, flags.data()));
+  inliers.assign(n, false);
+  for (int i = 0; i < n; ++i) inliers[i] = flags[i] != 0;
+  if (iter) *iter = (int)res.num_iterations;
+  if (res.status == SSFM_PAIR_OK) {
+    from_rowmajor(res.E, &estimators[0]->E);
+    for (int i = 0; i < 3; ++i) { estimators[0]->r[i] = res.r[i]; estimators[0]->t[i] = res.t[i]; }
+    *best_estimator = estimators[0];
+  }
+  return res.best_num_inliers;
+}
+}  // namespace detail
+
+template <class ListType, class EstimatorType>
+struct MSAC {  // include/sphericalsfm/msac.h:29-131
+  const Engine& engine;
+  double inlier_threshold = 0.001;
+  double prob_success;
+  double init_outlier_ratio;  // kept for source compatibility; the loop overwrites it before use (msac.h:113)
+  int iter = 0;               // number of iterations performed
+  uint32_t random_seed = 0, pair_id = 0;
+  bool inward = false;
+  explicit MSAC(const Engine& eng, double _prob_success = 0.999, double _init_outlier_ratio = 0.8)
+      : engine(eng), prob_success(_prob_success), init_outlier_ratio(_init_outlier_ratio) {}
+  int compute(typename ListType::iterator begin, typename ListType::iterator end, std::vector<EstimatorType*>& estimators,
+              EstimatorType** best_estimator, std::vector<bool>& inliers) {
+    SsfmOptions o;
+    ssfm_default_options(&o);
+    o.driver = SSFM_DRIVER_MSAC_FIXED;
+    o.squared_inlier_threshold = inlier_threshold * inlier_threshold;
+    o.fixed_prob_success = prob_success;
+    o.random_seed = random_seed;
+    o.first_pair_id = pair_id;
+    o.inward = inward ? 1 : 0;
+    return detail::legacy_compute(engine, o, begin, end, estimators, best_estimator, inliers, &iter);
+  }
+};
+
+template <class ListType, class EstimatorType>
+struct PreemptiveRANSAC {  // include/sphericalsfm/preemptive_ransac.h:30-139
+  const Engine& engine;
+  double inlier_threshold = 0.001;
+  size_t B;  // block size
+  uint32_t random_seed = 0, pair_id = 0;
+  bool inward = false;
+  explicit PreemptiveRANSAC(const Engine& eng, size_t _B = 10) : engine(eng), B(_B) {}
+  int compute(typename ListType::iterator begin, typename ListType::iterator end, std::vector<EstimatorType*>& estimators,
+              EstimatorType** best_estimator, std::vector<bool>& inliers) {
+    SsfmOptions o;
+    ssfm_default_options(&o);
+    o.driver = SSFM_DRIVER_PREEMPTIVE;
+    o.squared_inlier_threshold = inlier_threshold * inlier_threshold;
+    o.preemptive_block = (int32_t)B;
+    o.random_seed = random_seed;
+    o.first_pair_id = pair_id;
+    o.inward = inward ? 1 : 0;
+    return detail::legacy_compute(engine, o, begin, end, estimators, best_estimator, inliers, (int*)nullptr);
   }
 };
 

@@ -6,13 +6,16 @@
 //                        GetInliers :311-336, NumRequiredIterations include/RansacLib/utils.h:110-140)
 //   vanilla_msac() <- ransac_lib::VanillaMSAC::EstimateModel           evaluation/vanilla_ransac.h:23-99
 //   legacy_msac()  <- sphericalsfm::MSAC::compute                      include/sphericalsfm/msac.h:67-131
+//   preemptive_ransac() <- sphericalsfm::PreemptiveRANSAC::compute     include/sphericalsfm/preemptive_ransac.h:46-139
 //
 // Parity: PINNED.  tests/test_oracle_vs_ref.py runs this restatement and the reference's own
 // RansacLib headers (compiled into oracle/_ref from /root/reference/include) on the same
 // problems and demands bit-identical models, statistics and inlier sets.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <limits>
 #include <random>
 #include <vector>
@@ -290,6 +293,92 @@ int legacy_msac(const Options& opt, int budget, double prob_success, const Solve
   if (std::isfinite(best_score))
     for (int i = 0; i < n; ++i)
       if (solver.EvaluateModelOnPoint(*best_model, i) <= thr) st->inlier_indices.push_back(i);
+  return num_inliers;
+}
+
+// Pre-emptive RANSAC (include/sphericalsfm/preemptive_ransac.h:46-139).
+//   1. M hypotheses (= estimators.size()): a selection sample of m+1 correspondences (:66), the
+//      minimal solver on the first m (:69), the extra one picks the solution with the smallest
+//      error, first wins ties (:75-90).  A sample without a solution leaves a hypothesis that
+//      is never an inlier anywhere (upstream leaves its E unset, :72); with exactly one solution
+//      upstream never calls chooseSolution (:75) so E stays unset as well -- here it is that
+//      solution (the evident intent).
+//   2. Observations are visited in blocks of B (:100-107): every surviving hypothesis counts its
+//      inliers ('<=', :105) on the block; after block i the survivors are the
+//      f_i = floor(M 2^-floor(i/B)) best by (count, index) descending (:110-113, std::greater on
+//      pair<int,size_t>); stop at one survivor or at the end of the data (:116-119).
+//   3. The top hypothesis is scored on everything for the inlier mask (:122-137).
+// `Sample4` draws the m+1 indices of hypothesis i: knuth_sample for the reference's scheme.
+template <class Solver, class SampleFn>
+int preemptive_ransac(const Options& opt, int M, int B, const Solver& solver, SampleFn sample_fn,
+                      typename Solver::Model* best_model, Statistics* st) {
+  typedef typename Solver::Model Model;
+  *st = Statistics();
+  const int m = solver.min_sample_size(), N = solver.num_data();
+  if (m + 1 > N || m <= 0 || M <= 0 || B <= 0) return 0;
+  const double thr = opt.squared_inlier_threshold;
+  std::vector<Model> hyp(M);
+  std::vector<char> has(M, 0);
+  std::vector<std::pair<int, size_t> > order(M);
+  std::vector<int> sample(m + 1), minimal(m);
+  typename Solver::ModelVector models;
+  for (int i = 0; i < M; ++i) {
+    order[i].first = 0;
+    order[i].second = (size_t)i;
+    sample_fn((uint32_t)i, N, m + 1, sample.data());
+    for (int k = 0; k < m; ++k) minimal[k] = sample[k];
+    const int nsolns = solver.MinimalSolver(minimal, &models);
+    if (nsolns == 0) continue;
+    int best_index = 0;
+    double best_score = INFINITY;
+    if (nsolns > 1) {
+      for (int j = 0; j < nsolns; ++j) {
+        const double score = solver.EvaluateModelOnPoint(models[j], sample[m]);
+        if (score < best_score) {
+          best_score = score;
+          best_index = j;
+        }
+      }
+    }
+    hyp[i] = models[best_index];
+    has[i] = 1;
+  }
+  int it = 0;
+  size_t f = (size_t)M;
+  for (size_t i = 1; i < (size_t)N; ++i) {
+    const int start = it;
+    for (; it != start + B && it != N; ++it)
+      for (size_t j = 0; j < f; ++j) {
+        const size_t h = order[j].second;
+        if (has[h] && solver.EvaluateModelOnPoint(hyp[h], it) <= thr) order[j].first++;
+      }
+    f = (size_t)std::floor(M * std::pow(2., -std::floor((double)(i / (size_t)B))));
+    std::partial_sort(order.begin(), order.begin() + f, order.end(), std::greater<std::pair<int, size_t> >());
+    if (f <= 1) break;
+    if (it == N) break;
+  }
+  const size_t top = order[0].second;
+  st->num_iterations = (uint32_t)M;
+  if (!has[top]) {
+    st->best_model_score = std::numeric_limits<double>::max();
+    return 0;
+  }
+  *best_model = hyp[top];
+  int num_inliers = 0;
+  double cost = 0.0;  // not part of the reference's output: the legacy MSAC cost of the winner (msac.h:56-64)
+  for (int i = 0; i < N; ++i) {
+    const double score = solver.EvaluateModelOnPoint(*best_model, i);
+    if (score <= thr) {
+      st->inlier_indices.push_back(i);
+      num_inliers++;
+      cost += score;
+    } else {
+      cost += thr;
+    }
+  }
+  st->best_num_inliers = num_inliers;
+  st->best_model_score = cost;
+  st->inlier_ratio = (double)num_inliers / (double)N;
   return num_inliers;
 }
 

@@ -24,6 +24,7 @@ class OrcOptions(C.Structure):
         ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
         ("solver_kind", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("legacy_budget", C.c_int32), ("legacy_prob_success", C.c_double),
+        ("preemptive_block", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -38,7 +39,7 @@ class OrcResult(C.Structure):
 
 def default_options(**kw):
     """RansacLib defaults (include/RansacLib/ransac.h:49-73)."""
-    o = OrcOptions(100, 10000, 0.9999, 1.0, 0, 10, 2.0 ** 0.5, 4, 7, 3, 50, 0, 0, 0, 0, 512, 0.999)
+    o = OrcOptions(100, 10000, 0.9999, 1.0, 0, 10, 2.0 ** 0.5, 4, 7, 3, 50, 0, 0, 0, 0, 512, 0.999, 10, 0)
     for k, v in kw.items():
         if not hasattr(o, k):
             raise KeyError(k)
@@ -74,6 +75,11 @@ class Oracle:
     def philox_sample(self, seed, pair, it, k, n):
         idx = np.zeros(k, np.int32)
         self.lib.orc_philox_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(it), k, n, _ip(idx))
+        return idx
+
+    def knuth_sample(self, seed, pair, hyp, n_total, k):
+        idx = np.zeros(k, np.int32)
+        self.lib.orc_knuth_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(hyp), n_total, k, _ip(idx))
         return idx
 
     def solve(self, rays, sample, kind=0):

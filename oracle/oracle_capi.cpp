@@ -23,6 +23,23 @@
 #ifdef SSFM_USE_REFERENCE_RANSACLIB
 #include <RansacLib/ransac.h>
 #include <vanilla_ransac.h>
+// The reference's pre-emptive driver, compiled where it lies.  Its sampler calls the C library's
+// rand() (preemptive_ransac.h:18); the call expression is redirected -- by a macro, the header is
+// not touched -- to the Philox-backed stream the restatement uses (ssfm_oracle::philox_rand31),
+// so that both draw the same samples and can be compared bit for bit.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+#include <vector>
+namespace pinned_rand {
+thread_local uint32_t seed = 0, pair = 0, hyp = 0, draw = 0;
+inline int next() { return ssfm_oracle::philox_rand31(seed, pair, hyp, draw++); }
+}  // namespace pinned_rand
+#define rand() pinned_rand::next()
+#include <sphericalsfm/preemptive_ransac.h>
+#undef rand
 #endif
 
 using namespace ssfm_oracle;
@@ -67,6 +84,37 @@ Options to_options(const OrcOptions& o) {
   return p;
 }
 
+#ifdef SSFM_USE_REFERENCE_RANSACLIB
+// EstimatorType for the reference's PreemptiveRANSAC template (the interface of
+// include/sphericalsfm/estimator.h:6-23 as that driver uses it): the restated minimal solver
+// behind compute(), the restated Sampson error behind score().
+struct RefPreemptAdapter {
+  SolverKind kind = FAST_STURM;
+  Mat3 Esolns[4];
+  Mat3 E;
+  bool has = false;
+  long long* evals = nullptr;
+  int sampleSize() { return 3; }
+  int compute(std::vector<RayPair>::iterator b, std::vector<RayPair>::iterator e) {
+    pinned_rand::hyp++;  // compute() directly follows each random_sample(): the next draws belong to the next hypothesis
+    pinned_rand::draw = 0;
+    const int idx[3] = {0, 1, 2};
+    double models[4][6];
+    const int nm = solve_spherical(&*b, idx, (int)(e - b), kind, models);
+    for (int k = 0; k < nm; ++k) Esolns[k] = mat_from_p(models[k]);
+    has = nm > 0;
+    if (has) E = Esolns[0];
+    return nm;
+  }
+  void chooseSolution(int j) { E = Esolns[j]; }
+  double score(std::vector<RayPair>::iterator it) {
+    if (!has) return INFINITY;
+    ++*evals;
+    return sampson_sq(E, *it);
+  }
+};
+#endif
+
 int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_id, OrcResult* out, int* inlier_idx) {
   SphericalEstimator est(corr, n, (SolverKind)o.solver_kind, o.inward != 0, pair_id);
   Mat3 E;
@@ -103,6 +151,42 @@ int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_
     st.inlier_ratio = rs.inlier_ratio;
     st.inlier_indices = rs.inlier_indices;
     st.number_lo_iterations = rs.number_lo_iterations;
+  } else if (o.driver == 3) {
+    const int M = o.legacy_budget, B = o.preemptive_block;
+    if (n >= 4 && M > 0 && B > 0) {
+      std::vector<RayPair> list(corr, corr + n);
+      std::vector<RefPreemptAdapter> pool(M);
+      std::vector<RefPreemptAdapter*> ptrs(M);
+      long long evals = 0;
+      for (int i = 0; i < M; ++i) {
+        pool[i].kind = (SolverKind)o.solver_kind;
+        pool[i].evals = &evals;
+        ptrs[i] = &pool[i];
+      }
+      pinned_rand::seed = o.random_seed;
+      pinned_rand::pair = pair_id;
+      pinned_rand::hyp = 0;
+      pinned_rand::draw = 0;
+      sphericalsfm::PreemptiveRANSAC<std::vector<RayPair>, RefPreemptAdapter> pr((size_t)B);
+      pr.inlier_threshold = std::sqrt(o.squared_inlier_threshold);
+      RefPreemptAdapter* best = nullptr;
+      std::vector<bool> inl;
+      const int ninl = pr.compute(list.begin(), list.end(), ptrs, &best, inl);
+      st.num_iterations = (uint32_t)M;
+      if (best && best->has) {
+        E = best->E;
+        double cost = 0.0;
+        for (int i = 0; i < n; ++i) {
+          const double sc = sampson_sq(E, corr[i]);
+          cost += (sc <= o.squared_inlier_threshold) ? sc : o.squared_inlier_threshold;
+          if (inl[i]) st.inlier_indices.push_back(i);
+        }
+        st.best_num_inliers = ninl;
+        st.best_model_score = cost;
+        st.inlier_ratio = (double)ninl / (double)n;
+      }
+      est.evals_ += evals;
+    }
   } else {
     legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
   }
@@ -111,6 +195,9 @@ int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_
     lo_msac<SphericalEstimator, Sampler>(opt, est, &E, &st);
   else if (o.driver == 1)
     vanilla_msac<SphericalEstimator, Sampler>(opt, est, &E, &st);
+  else if (o.driver == 3)
+    preemptive_ransac(opt, o.legacy_budget, o.preemptive_block, est,
+                      [&](uint32_t hyp, int N, int k, int* idx) { knuth_sample(o.random_seed, pair_id, hyp, N, k, idx); }, &E, &st);
   else
     legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
 #endif
@@ -122,7 +209,7 @@ int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_
   out->number_lo_iterations = st.number_lo_iterations;
   out->evals = est.evals_;
   for (int i = 0; i < 3; ++i) out->r[i] = out->t[i] = 0.0;
-  if (n < 3) {
+  if (n < 3 || (o.driver == 3 && n < 4)) {
     out->status = 1;
   } else if (!(st.best_model_score < std::numeric_limits<double>::max())) {
     out->status = 2;
@@ -150,6 +237,9 @@ int orc_is_reference(void) {
 
 void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx) {
   philox_sample(seed, pair, iter, k, n, idx);
+}
+void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* idx) {
+  knuth_sample(seed, pair, hyp, N, n, idx);
 }
 
 int orc_solve(const double* rays, const int* sample, int n, int kind, double* models) {

@@ -24,8 +24,10 @@ typedef struct {
   int32_t solver_kind; /* 0 action matrix, 1 polynomial, 2 fast/Sturm */
   int32_t driver;      /* 0 LO-MSAC, 1 vanilla MSAC, 2 legacy fixed-budget MSAC */
   int32_t inward;
-  int32_t legacy_budget;
+  int32_t legacy_budget;       /* drivers 2, 3: number of hypotheses (estimators.size()) */
   double legacy_prob_success;
+  int32_t preemptive_block;    /* driver 3: B (preemptive_ransac.h:40) */
+  int32_t reserved;
 } OrcOptions;
 
 typedef struct {
@@ -43,6 +45,7 @@ typedef struct {
 
 int orc_is_reference(void); /* 1 in oracle/_ref (driver = the reference's RansacLib) */
 void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx);
+void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* idx);
 int orc_solve(const double* rays, const int* sample, int n, int kind, double* models /* 4x6 */);
 void orc_sampson(const double* E9, const double* rays, int n, double* out);
 void orc_score(const double* E9, const double* rays, int n, double thr, double* score, int* ninl);

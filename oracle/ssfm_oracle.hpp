@@ -116,6 +116,39 @@ inline void philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, in
   }
 }
 
+// rand() of the legacy drivers, as a pure function of (seed, pair, hypothesis, draw): the
+// reference calls the C library's rand() (include/sphericalsfm/preemptive_ransac.h:18); here the
+// j-th call made while drawing the sample of hypothesis `hyp` is word (j%4) of
+// Philox(counter=(hyp, j/4, 1, 0), key=(seed, pair)) >> 1, i.e. uniform on [0, RAND_MAX] with
+// RAND_MAX = 2^31-1 (glibc).  The value RAND_MAX itself is folded onto RAND_MAX-1 so that u < 1
+// strictly (with u == 1 the reference's selection sampling can run past the end of the list).
+inline int philox_rand31(uint32_t seed, uint32_t pair, uint32_t hyp, uint32_t draw) {
+  const uint32_t key[2] = {seed, pair};
+  const uint32_t ctr[4] = {hyp, draw >> 2, 1u, 0u};
+  uint32_t words[4];
+  Philox4x32::generate(ctr, key, words);
+  uint32_t r = words[draw & 3u] >> 1;
+  if (r == 0x7fffffffu) r = 0x7ffffffeu;
+  return (int)r;
+}
+
+// random_sample (include/sphericalsfm/preemptive_ransac.h:8-28): Knuth 3.4.2S selection sampling,
+// n of N records in increasing order.
+inline void knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* out) {
+  int t = 0, m = 0;
+  uint32_t draw = 0;
+  while (m < n) {
+    const double u = philox_rand31(seed, pair, hyp, draw++) / (double)2147483647;
+    if ((N - t) * u >= n - m) {
+      t++;
+    } else {
+      out[m] = t;
+      t++;
+      m++;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Small dense linear algebra.
 // ---------------------------------------------------------------------------------------

@@ -25,7 +25,7 @@ _SOURCES = [os.path.join(_DIR, "csrc", f) for f in
 SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_NO_DEVICE, SSFM_ERR_CUDA, SSFM_ERR_OOM = 0, 1, 2, 3, 4
 PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL, PAIR_SKIPPED = 0, 1, 2, 3
 SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM = 0, 1, 2
-DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED = 0, 1, 2
+DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED, DRIVER_PREEMPTIVE = 0, 1, 2, 3
 
 
 class SsfmError(RuntimeError):
@@ -45,7 +45,7 @@ class SsfmOptions(C.Structure):
         ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
         ("solver", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("fixed_budget", C.c_int32), ("fixed_prob_success", C.c_double), ("first_pair_id", C.c_uint32),
-        ("min_num_points", C.c_int32),
+        ("min_num_points", C.c_int32), ("preemptive_block", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -123,7 +123,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -154,6 +154,14 @@ def sample(seed, pair, it, k, n):
     idx = np.zeros(k, np.int32)
     _check(lib().ssfm_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(it), k, n,
                              idx.ctypes.data_as(C.POINTER(C.c_int32))))
+    return idx
+
+
+def selection_sample(seed, pair, hypothesis, n_total, k):
+    """random_sample of the legacy drivers (preemptive_ransac.h:8-28) on the Philox-backed rand()."""
+    idx = np.zeros(k, np.int32)
+    _check(lib().ssfm_selection_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(hypothesis), n_total, k,
+                                       idx.ctypes.data_as(C.POINTER(C.c_int32))))
     return idx
 
 

@@ -31,6 +31,7 @@ struct Params {
   double fixed_prob;
   uint32_t first_pair_id;
   int min_points;  // pairs with fewer correspondences are skipped
+  int preempt_block;  // pre-emptive driver: B
   float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
 };
 

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "ssfm_kernels.cuh"
+#include "ssfm_preemptive.cuh"
 
 using namespace ssfm;
 
@@ -120,6 +121,7 @@ struct Worker {
   DevBuf<double> models, lm_E;
   DevBuf<float> s32, s32m;
   DevBuf<unsigned long long> counters;
+  DevBuf<unsigned char> has;  // pre-emptive driver: hypothesis-has-a-model flags
   // outputs of the last run
   double solve_ms = 0, score_ms = 0, chain_ms = 0;
   int rounds = 0, launches = 0;
@@ -130,7 +132,7 @@ struct Worker {
   void release() {
     states.release(); mt.release(); active0.release(); active1.release(); ident.release(); navail.release(); list_a.release();
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
-    s32.release(); s32m.release(); counters.release();
+    s32.release(); s32m.release(); counters.release(); has.release();
   }
 };
 
@@ -159,6 +161,7 @@ Params make_params(const SsfmOptions& o) {
   P.fixed_prob = o.fixed_prob_success;
   P.first_pair_id = o.first_pair_id;
   P.min_points = o.min_num_points;
+  P.preempt_block = o.preemptive_block;
   P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
   return P;
@@ -167,7 +170,9 @@ Params make_params(const SsfmOptions& o) {
 int check_options(const SsfmOptions* o) {
   if (!o) return fail(SSFM_ERR_INVALID, "options is NULL");
   if (o->solver < 0 || o->solver > 2) return fail(SSFM_ERR_INVALID, "unknown solver kind");
-  if (o->driver < 0 || o->driver > 2) return fail(SSFM_ERR_INVALID, "unknown driver kind");
+  if (o->driver < 0 || o->driver > 3) return fail(SSFM_ERR_INVALID, "unknown driver kind");
+  if (o->driver == SSFM_DRIVER_PREEMPTIVE && (o->fixed_budget <= 0 || o->fixed_budget > 8192 || o->preemptive_block <= 0))
+    return fail(SSFM_ERR_INVALID, "pre-emptive driver needs 0 < fixed_budget <= 8192 hypotheses and preemptive_block > 0");
   if (!(o->squared_inlier_threshold > 0.0)) return fail(SSFM_ERR_INVALID, "squared_inlier_threshold must be > 0");
   if (o->driver == SSFM_DRIVER_MSAC_FIXED && o->fixed_budget <= 0)
     return fail(SSFM_ERR_INVALID, "fixed_budget must be > 0 for the fixed-budget MSAC driver");
@@ -221,6 +226,39 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
     bool unit_z = h->unit_z;
     const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
     const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
+    if (P.driver == SSFM_DRIVER_PREEMPTIVE) {
+      // No sequential dependence between hypotheses: generate all M per pair, then one CTA per pair runs the
+      // block-wise elimination.  Two launches per pass.
+      const int M = P.fixed_budget;
+      int Mpad = 1;
+      while (Mpad < M) Mpad <<= 1;
+      SSFM_WCK(w.models.ensure((size_t)np * 6 * M));
+      SSFM_WCK(w.has.ensure((size_t)np * M));
+      SSFM_WCK(cudaEventRecord(evA, w.stream));
+      SSFM_WCK(cudaMemsetAsync(w.has.p, 0, (size_t)np * M, w.stream));
+      dim3 grid(np, (M + 63) / 64);
+      if (P.solver == 0) k_preempt_hypotheses<0><<<grid, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, M, w.models.p, w.has.p);
+      else if (P.solver == 1) k_preempt_hypotheses<1><<<grid, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, M, w.models.p, w.has.p);
+      else k_preempt_hypotheses<2><<<grid, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, M, w.models.p, w.has.p);
+      SSFM_WCK(cudaGetLastError());
+      SSFM_WCK(cudaEventRecord(evB, w.stream));
+      const size_t smem = (size_t)Mpad * (sizeof(long long) + sizeof(int));
+      SSFM_WCK(cudaFuncSetAttribute(k_preempt_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k_preempt_select<<<np, kPreemptThreads, smem, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, M, Mpad, P.preempt_block,
+                                                                w.models.p, w.has.p, h->flags.p, h->results.p + pair0,
+                                                                w.counters.p);
+      SSFM_WCK(cudaGetLastError());
+      SSFM_WCK(cudaEventRecord(evC, w.stream));
+      SSFM_WCK(cudaStreamSynchronize(w.stream));
+      float t1 = 0, t2 = 0;
+      cudaEventElapsedTime(&t1, evA, evB);
+      cudaEventElapsedTime(&t2, evB, evC);
+      w.solve_ms += t1;
+      w.chain_ms += t2;
+      w.rounds += 1;
+      launches += 2;
+      continue;
+    }
     SSFM_WCK(w.states.ensure(np));
     SSFM_WCK(w.active0.ensure(np));
     SSFM_WCK(w.active1.ensure(np));
@@ -397,6 +435,8 @@ void ssfm_default_options(SsfmOptions* o) {
   o->fixed_prob_success = 0.999;
   o->first_pair_id = 0u;
   o->min_num_points = 0;
+  o->preemptive_block = 10; /* PreemptiveRANSAC( size_t _B = 10 ), preemptive_ransac.h:40 */
+  o->reserved = 0;
 }
 
 int ssfm_create(int device, ssfm_handle* out) {
@@ -771,6 +811,12 @@ int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions
 int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t n, int32_t* idx) {
   if (!idx || k <= 0 || k > 8 || n < k) return fail(SSFM_ERR_INVALID, "ssfm_sample: need 0 < k <= 8 and n >= k");
   philox_sample<8>(seed, pair, iter, k, n, idx);
+  return SSFM_OK;
+}
+
+int ssfm_selection_sample(uint32_t seed, uint32_t pair, uint32_t hypothesis, int32_t n_total, int32_t k, int32_t* idx) {
+  if (!idx || k <= 0 || n_total < k) return fail(SSFM_ERR_INVALID, "ssfm_selection_sample: need 0 < k <= n_total");
+  knuth_sample(seed, pair, hypothesis, n_total, k, idx);
   return SSFM_OK;
 }
 

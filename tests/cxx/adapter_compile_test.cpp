@@ -58,10 +58,28 @@ int main() {
     estimator.Decompose(E, stats.inlier_indices, &Rm, &tt);
     std::vector<SsfmPairResult> res;
     EstimatePairs(eng, options, std::vector<RayPairList>{rays, rays}, false, false, &res);
-    std::printf("inliers %d recount %d models %d R02 %.6f (want %.6f) batched %d %d\n", ninliers, recount, nm, Rm(0, 2), s,
-                res[0].best_num_inliers, res[1].best_num_inliers);
+    // the legacy drivers with their upstream signatures (msac.h:67, preemptive_ransac.h:46)
+    typedef GpuSphericalFastEstimator<Mat3d> FastEst;
+    std::vector<FastEst> pool(256);
+    std::vector<FastEst*> ptrs;
+    for (auto& e : pool) ptrs.push_back(&e);
+    FastEst* best = nullptr;
+    std::vector<bool> inl;
+    MSAC<RayPairList, FastEst> msac(eng);
+    msac.inlier_threshold = 1e-3;
+    const int n_msac = msac.compute(rays.begin(), rays.end(), ptrs, &best, inl);
+    PreemptiveRANSAC<RayPairList, FastEst> pre(eng, 10);
+    pre.inlier_threshold = 1e-3;
+    FastEst* best2 = nullptr;
+    const int n_pre = pre.compute(rays.begin(), rays.end(), ptrs, &best2, inl);
+    Vec3 rr, tr;
+    if (best2) best2->decomposeE(false, rr, tr);
+    std::printf("inliers %d recount %d models %d R02 %.6f (want %.6f) batched %d %d legacy msac %d (iter %d) preemptive %d ry %.6f\n",
+                ninliers, recount, nm, Rm(0, 2), s, res[0].best_num_inliers, res[1].best_num_inliers, n_msac, msac.iter, n_pre,
+                best2 ? rr[1] : 0.0);
     const bool ok = ninliers == 160 && recount == ninliers && nm == 4 && std::fabs(Rm(0, 2) - s) < 1e-6 &&
-                    res[0].best_num_inliers == 160;
+                    res[0].best_num_inliers == 160 && n_msac == 160 && best != nullptr && n_pre == 160 && best2 != nullptr &&
+                    std::fabs(rr[1] - a) < 1e-6 && (int)inl.size() == 200;
     return ok ? 0 : 1;
   } catch (const Error& e) {
     std::printf("engine error %d: %s\n", e.code(), e.what());

@@ -177,6 +177,57 @@ def test_config_c2_fast_solver_legacy_msac(S, O, engine, orc):
         assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
 
 
+@pytest.mark.parametrize("solver,M,B,N,outl", [(2, 512, 10, 2000, 0.3), (0, 500, 7, 700, 0.5), (1, 64, 3, 300, 0.4),
+                                               (2, 1024, 10, 150, 0.3)])
+def test_preemptive_ransac_driver(S, O, engine, orc, ref, solver, M, B, N, outl):
+    """sphericalsfm::PreemptiveRANSAC::compute (include/sphericalsfm/preemptive_ransac.h:46-139) on the device
+    against the reference header itself (oracle/_ref) or its restatement: same winner (model 1e-7 after
+    normalisation), identical inlier masks and counts, same cost; config C2's solver pairing first."""
+    opt = S.default_options(squared_inlier_threshold=THR2, driver=S.DRIVER_PREEMPTIVE, solver=solver, fixed_budget=M,
+                            preemptive_block=B, random_seed=17, first_pair_id=3)
+    P = 24
+    rays, offsets, probs = S.problems.make_batch(21, P, N, noise=1 / 600, outlier_frac=outl, rotation_deg=1.0 if solver == 2 else None)
+    res, flags = engine.estimate_pairs(rays, offsets, opt)
+    oopt = to_oracle_options(O, opt)
+    impl = ref if ref is not None else orc
+    good = 0
+    for p in range(P):
+        a, inl = impl.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, opt.first_pair_id + p)
+        fl = np.zeros(N, np.uint8)
+        fl[inl] = 1
+        assert int(res["status"][p]) == a.status
+        assert int(res["num_iterations"][p]) == a.num_iterations == M
+        assert int(res["best_num_inliers"][p]) == a.best_num_inliers, p
+        assert (flags[offsets[p]:offsets[p + 1]] == fl).all(), p
+        if a.status == 0:
+            assert model_dist(res["E"][p] / np.linalg.norm(res["E"][p]), np.array(a.E) / np.linalg.norm(a.E)) < 1e-7
+            assert abs(res["best_model_score"][p] - a.best_model_score) <= 1e-9 * a.best_model_score
+            good += np.rad2deg(S.problems.rot_error(probs[p].R, S.problems.so3exp(res["r"][p]))) < 1.0
+    if M >= 500 and N >= 700:
+        assert good >= P - 2
+
+
+def test_preemptive_ransac_edge_cases(S, O, engine, orc):
+    """Ragged / tiny pairs (fewer than m+1 = 4 points -> TOO_FEW), a single hypothesis, data shorter than one block."""
+    sizes = [0, 3, 4, 5, 9, 40, 1, 333]
+    rng = S.problems.make_rng(5, 0)
+    parts = [S.problems.make_problem(S.problems.make_rng(31, i), max(n, 1), False, None, 1 / 600, n // 3, 20.0).rays[:n] for i, n in enumerate(sizes)]
+    rays = np.concatenate(parts)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    for M, B in [(1, 10), (2, 1), (128, 10), (100, 50)]:
+        opt = S.default_options(squared_inlier_threshold=THR2, driver=S.DRIVER_PREEMPTIVE, solver=0, fixed_budget=M, preemptive_block=B)
+        res, flags = engine.estimate_pairs(rays, offsets, opt)
+        oopt = to_oracle_options(O, opt)
+        for p, n in enumerate(sizes):
+            a, inl = orc.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
+            assert int(res["status"][p]) == a.status, (M, B, p)
+            if n >= 4:
+                assert int(res["best_num_inliers"][p]) == a.best_num_inliers, (M, B, p)
+                fl = np.zeros(n, np.uint8)
+                fl[inl] = 1
+                assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
+
+
 def test_ragged_empty_and_tiny_pairs(S, O, engine, orc):
     """Edge cases: empty pairs, fewer points than the minimal sample, exactly minimal, ragged sizes."""
     sizes = [0, 2, 3, 8, 1, 700, 0, 33, 1500, 5]

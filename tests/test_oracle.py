@@ -165,6 +165,52 @@ def test_restated_drivers_equal_reference_ransaclib(S, O, orc, ref, name, kw, n,
         assert (ia == ib).all() and a.evals == b.evals
 
 
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_restated_preemptive_ransac_equals_reference_header(S, O, orc, ref, kind):
+    """oracle/lomsac.hpp::preemptive_ransac against the reference's own include/sphericalsfm/preemptive_ransac.h
+    compiled in oracle/_ref (its rand() call redirected to the same Philox-backed stream): bit-identical winner,
+    inlier mask and count, over ragged sizes, hypothesis budgets and block sizes."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    for p in range(18):
+        n = [4, 5, 30, 200, 1000, 1500][p % 6]
+        pr = S.problems.make_problem(S.problems.make_rng(11, p), n, p % 2 == 1, None, 1 / 600, int(0.4 * n), 20.0)
+        opt = O.default_options(squared_inlier_threshold=THR2, driver=3, solver_kind=kind, legacy_budget=[64, 500, 512][p % 3],
+                                preemptive_block=[10, 7, 3][p % 3], random_seed=5, inward=p % 2)
+        a, ia = orc.estimate_pair(pr.rays, opt, p)
+        b, ib = ref.estimate_pair(pr.rays, opt, p)
+        assert a.status == b.status and list(a.E) == list(b.E)
+        assert (a.num_iterations, a.best_num_inliers, a.best_model_score, a.inlier_ratio, a.evals) == (
+            b.num_iterations, b.best_num_inliers, b.best_model_score, b.inlier_ratio, b.evals)
+        assert (ia == ib).all()
+
+
+def test_preemptive_ransac_recovers_pose(S, O, orc):
+    """The pre-emptive driver with the Sturm solver (its upstream pairing) finds the rotation on C2-like pairs."""
+    opt = O.default_options(squared_inlier_threshold=THR2, driver=3, solver_kind=2, legacy_budget=512, preemptive_block=10)
+    ok = 0
+    for p in range(10):
+        pr = S.problems.make_problem(S.problems.make_rng(12, p), 2000, False, None, 1 / 600, 600, 1.0)
+        a, ia = orc.estimate_pair(pr.rays, opt, p)
+        assert a.status == 0
+        ok += np.rad2deg(S.problems.rot_error(pr.R, S.problems.so3exp(np.array(a.r)))) < 0.5
+    assert ok >= 9
+
+
+def test_selection_sample_properties(S, orc):
+    """random_sample (Knuth 3.4.2S): k distinct indices in increasing order, uniform marginals; the product's host
+    hook reproduces the oracle's stream."""
+    hits = np.zeros(50)
+    for h in range(4000):
+        idx = orc.knuth_sample(3, 9, h, 50, 4)
+        assert (np.diff(idx) > 0).all() and idx[0] >= 0 and idx[-1] < 50
+        hits[idx] += 1
+    assert abs(hits / 4000 - 4 / 50).max() < 0.02
+    for h in range(200):
+        assert (S.selection_sample(3, 9, h, 977, 4) == orc.knuth_sample(3, 9, h, 977, 4)).all()
+    assert (orc.knuth_sample(1, 1, 0, 4, 4) == np.arange(4)).all()
+
+
 def test_oracle_recovers_pose_with_outliers(S, O, orc):
     """Config C1: 1000 correspondences, 50 % outliers, calibrated solver, pipeline options."""
     opt = O.pipeline_options(THR2)
