@@ -45,7 +45,11 @@ enum {
 enum {
   SSFM_SOLVER_ACTION_MATRIX = 0, /* spherical_solver_action_matrix, src/spherical_solvers.cpp:102-311 */
   SSFM_SOLVER_POLYNOMIAL = 1,    /* spherical_solver_polynomial,    src/spherical_solvers.cpp:313-660 */
-  SSFM_SOLVER_FAST_STURM = 2     /* SphericalFastEstimator::compute, src/spherical_fast_estimator.cpp:44-257 */
+  SSFM_SOLVER_FAST_STURM = 2,    /* SphericalFastEstimator::compute, src/spherical_fast_estimator.cpp:44-257 */
+  SSFM_SOLVER_SIXPT_FOCAL = 3    /* SixPointEstimator (examples/six_point_estimator.{h,cpp}): six-point shared-focal
+                                    relative pose, <= 15 models {t, r, focal} per sample, min_sample_size 6.  Rays are
+                                    (x - cx, y - cy, 1) in pixel units.  Drivers: SSFM_DRIVER_VANILLA_MSAC (config C4).
+                                    SsfmPairResult.E is the matrix the estimator scores with, r/t/focal the model. */
 };
 
 /* RANSAC driver. */
@@ -86,7 +90,10 @@ typedef struct SsfmOptions {
   int32_t min_num_points;           /* 0; pairs with fewer correspondences are skipped, like `m01.size() < min_num_inliers`
                                        in estimate_pairwise (examples/spherical_sfm_tools.cpp:351) */
   int32_t preemptive_block;         /* 10; PREEMPTIVE: B (preemptive_ransac.h:34,40) */
-  int32_t reserved;
+  int32_t sixpt_focal_scoring;      /* 0; SIXPT_FOCAL: 0 = score with E = skew3(t) so3exp(r) on the raw rays, exactly as
+                                       SixPointEstimator::EvaluateModelOnPoint does (six_point_estimator.cpp:78-91; the
+                                       focal is not used there); 1 = score with F = Kinv E Kinv, Kinv = diag(1,1,focal),
+                                       the model of the reference's own refit functor (:62-70) */
 } SsfmOptions;
 
 /* A batch of image pairs in CSR form: pair p owns correspondences [offsets[p], offsets[p+1]).
@@ -114,6 +121,7 @@ typedef struct SsfmPairResult {
   int32_t status; /* SSFM_PAIR_* */
   int64_t evals;  /* minimal-model corr-hypothesis evaluations the reference loop would have made:
                      num_iterations * models * N */
+  double focal;   /* SixPointSolution::focal (SSFM_SOLVER_SIXPT_FOCAL), 0 otherwise */
 } SsfmPairResult;
 
 /* Device-side timing/accounting of the last ssfm_run (CUDA events on the engine's stream). */
@@ -221,6 +229,12 @@ int ssfm_decompose(ssfm_handle h, const double* E9, int32_t num, int32_t inward,
  * scales: num_scales values of f/f0.  r3: num_scales x num x 3 (so3ln of the chosen rotation). */
 int ssfm_decompose_rescaled(ssfm_handle h, const double* E9, int32_t num, const double* scales, int32_t num_scales,
                             int32_t inward, double* r3);
+
+/* SixPointEstimator::MinimalSolver (examples/six_point_estimator.cpp:93-119) on explicit samples of six
+ * indices each.  models: num_samples x 15 x 7 doubles (t[3] unit, r[3] = so3ln(R), focal), sorted by focal;
+ * num_models: how many of the 15 are valid for each sample. */
+int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples6, int32_t num_samples,
+                     double* models, int32_t* num_models);
 
 /* The LO generator: `ncalls` consecutive RandomShuffleAndResize calls (include/RansacLib/utils.h:48-52)
  * on iota vectors, one std::mt19937(seed) stream (ransac.h:143-144), executed on the device. */

@@ -1,0 +1,324 @@
+"""CPU ORACLE (test infrastructure only) for the six-point shared-focal estimator.
+
+Follows examples/six_point_estimator.{h,cpp} of the reference:
+  MinimalSolver          six_point_estimator.cpp:93-119  (poselib::relpose_6pt_shared_focal, :104)
+  EvaluateModelOnPoint   :78-91   (E = skew3(t) * so3exp(r); the focal is NOT used, as upstream)
+  SampsonError functor   :25-76   (F = Kinv E Kinv, Kinv = diag(1,1,focal)) -> `focal_scoring=True`
+and evaluation/vanilla_ransac.h:23-99 for the driver (config C4 runs VanillaMSAC).
+
+PARITY UNPINNED: the arithmetic of the minimal solver lives in PoseLib (vlarsson/PoseLib, cloned at an
+unpinned HEAD by docker/Dockerfile:58-62, absent from /root/reference and from this image); the reference has
+no test, golden vector or caller for SixPointEstimator.  What is restated here is the *published* problem
+(Stewenius et al. 2005 / Kukelova, Bujnak, Pajdla BMVC 2008, "Polynomial eigenvalue solutions to the 5-pt and
+6-pt relative pose problems"): with F = x F0 + y F1 + F2 spanning the null space of the six epipolar
+constraints, w = 1/f^2 and Q = diag(1,1,w), all real solutions (x, y, w>0) of
+
+      det F = 0,      2 F Q F^T Q F - trace(F Q F^T Q) F = 0          (10 cubics in x,y; quadratic in w)
+
+each decomposed into (R, t) with PoseLib's cheirality rule (every sample point in front of both cameras,
+|t| = 1).  Solutions are returned sorted by focal length (PoseLib's own order is an artefact of its
+elimination template and is not reproducible without its source).  This oracle solves the quadratic
+eigenvalue problem with LAPACK (scipy.linalg.eig on the companion pencil); the product uses its own
+Hessenberg-QR iteration, so the two are independent implementations.  Pins available: ground truth of
+synthetic problems (focal, rotation, translation direction) and the residual of the polynomial system.
+"""
+import numpy as np
+import scipy.linalg
+
+# monomial order of the 10 cubic monomials in (x, y)
+MONO = [(3, 0), (2, 1), (1, 2), (0, 3), (2, 0), (1, 1), (0, 2), (1, 0), (0, 1), (0, 0)]
+MONO_IDX = {m: i for i, m in enumerate(MONO)}
+
+
+def _pmul(a, b):
+    """product of polynomials in (x, y, w) stored as dense arrays P[i, j, k] = coeff of x^i y^j w^k"""
+    out = np.zeros((a.shape[0] + b.shape[0] - 1, a.shape[1] + b.shape[1] - 1, a.shape[2] + b.shape[2] - 1))
+    for i, j, k in zip(*np.nonzero(a)):
+        out[i:i + b.shape[0], j:j + b.shape[1], k:k + b.shape[2]] += a[i, j, k] * b
+    return out
+
+
+def _padd(a, b):
+    s = tuple(max(p, q) for p, q in zip(a.shape, b.shape))
+    out = np.zeros(s)
+    out[:a.shape[0], :a.shape[1], :a.shape[2]] += a
+    out[:b.shape[0], :b.shape[1], :b.shape[2]] += b
+    return out
+
+
+def nullspace_basis(x1, x2):
+    """three 3x3 matrices spanning {F : x2_i^T F x1_i = 0, i < 6}"""
+    A = np.zeros((6, 9))
+    for i in range(6):
+        A[i] = np.outer(x2[i], x1[i]).reshape(9)
+    _, _, vt = np.linalg.svd(A)
+    return vt[6].reshape(3, 3), vt[7].reshape(3, 3), vt[8].reshape(3, 3)
+
+
+def constraint_matrices(F0, F1, F2):
+    """M0, M1, M2 (10x10): row e of (M0 + w M1 + w^2 M2) . monomials(x,y) is equation e"""
+    def lin(i, j):
+        p = np.zeros((2, 2, 1))
+        p[1, 0, 0] = F0[i, j]
+        p[0, 1, 0] = F1[i, j]
+        p[0, 0, 0] = F2[i, j]
+        return p
+    F = [[lin(i, j) for j in range(3)] for i in range(3)]
+    wpoly = np.zeros((1, 1, 2))
+    wpoly[0, 0, 1] = 1.0
+    q = [np.ones((1, 1, 1)), np.ones((1, 1, 1)), wpoly]  # Q = diag(1, 1, w)
+    # G = F Q F^T
+    G = [[None] * 3 for _ in range(3)]
+    for i in range(3):
+        for j in range(3):
+            acc = np.zeros((1, 1, 1))
+            for k in range(3):
+                acc = _padd(acc, _pmul(_pmul(F[i][k], q[k]), F[j][k]))
+            G[i][j] = acc
+    H = [[_pmul(G[i][j], q[j]) for j in range(3)] for i in range(3)]  # H = G Q
+    tr = _padd(_padd(H[0][0], H[1][1]), H[2][2])
+    eqs = []
+    det = _padd(_padd(_pmul(F[0][0], _padd(_pmul(F[1][1], F[2][2]), -_pmul(F[1][2], F[2][1]))),
+                      -_pmul(F[0][1], _padd(_pmul(F[1][0], F[2][2]), -_pmul(F[1][2], F[2][0])))),
+                _pmul(F[0][2], _padd(_pmul(F[1][0], F[2][1]), -_pmul(F[1][1], F[2][0]))))
+    eqs.append(det)
+    for i in range(3):
+        for j in range(3):
+            acc = -_pmul(tr, F[i][j])
+            for k in range(3):
+                acc = _padd(acc, 2.0 * _pmul(H[i][k], F[k][j]))
+            eqs.append(acc)
+    M = np.zeros((3, 10, 10))
+    for e, p in enumerate(eqs):
+        for i, j, k in zip(*np.nonzero(p)):
+            M[k, e, MONO_IDX[(i, j)]] += p[i, j, k]
+    return M[0], M[1], M[2]
+
+
+def _monomials(x, y):
+    return np.array([x ** a * y ** b for a, b in MONO])
+
+
+def _dmonomials(x, y):
+    dx = np.array([a * x ** max(a - 1, 0) * y ** b if a > 0 else 0.0 for a, b in MONO])
+    dy = np.array([b * x ** a * y ** max(b - 1, 0) if b > 0 else 0.0 for a, b in MONO])
+    return dx, dy
+
+
+def solve_xyw(M0, M1, M2, polish=12):
+    """all real (x, y, w > 0): quadratic eigenvalue problem in w, then Gauss-Newton on the 10 equations"""
+    Z, I = np.zeros((10, 10)), np.eye(10)
+    A = np.block([[Z, I], [-M0, -M1]])
+    B = np.block([[I, Z], [Z, M2]])
+    with np.errstate(all="ignore"):
+        vals, vecs = scipy.linalg.eig(A, B)
+    sols = []
+    for k in range(20):
+        w = vals[k]
+        # nearly real eigenvalues are kept: a close pair of real roots shows up as a conjugate pair with a
+        # small imaginary part; the polish below starts on either side and the residual test decides
+        if not np.isfinite(w) or abs(w.imag) > 1e-4 * max(abs(w.real), 1e-300) or w.real <= 0:
+            continue
+        m = vecs[:10, k]
+        m = (m / m[9]).real if abs(m[9]) > 1e-14 * np.abs(m).max() else None
+        if m is None:
+            continue
+        x, y, w = m[7], m[8], (w.real + w.imag if w.real + w.imag > 0 else w.real)
+        ok = True
+        converged = False
+        for _ in range(polish):
+            mo = _monomials(x, y)
+            dx, dy = _dmonomials(x, y)
+            Mw = M0 + w * M1 + w * w * M2
+            res = Mw @ mo
+            J = np.stack([Mw @ dx, Mw @ dy, (M1 + 2 * w * M2) @ mo], axis=1)
+            step, *_ = np.linalg.lstsq(J, -res, rcond=None)
+            x, y, w = x + step[0], y + step[1], w + step[2]
+            if not np.isfinite([x, y, w]).all():
+                ok = False
+                break
+            # accepted only once the iteration has settled (a start that wanders is a spurious eigenvalue)
+            if (abs(step[0]) <= 1e-12 * (1 + abs(x)) and abs(step[1]) <= 1e-12 * (1 + abs(y))
+                    and abs(step[2]) <= 1e-12 * abs(w)):
+                converged = True
+                break
+        if not ok or not converged or w <= 0:
+            continue
+        mo = _monomials(x, y)
+        Mw = M0 + w * M1 + w * w * M2
+        scale = np.abs(Mw) @ np.abs(mo)
+        if (np.abs(Mw @ mo) > 1e-8 * scale).any():
+            continue
+        if any(abs(x - s[0]) + abs(y - s[1]) < 1e-6 * (1 + abs(x) + abs(y)) and abs(w - s[2]) < 1e-6 * w for s in sols):
+            continue
+        sols.append((x, y, w))
+    return sols
+
+
+def so3exp(r):
+    th = np.linalg.norm(r)
+    if th < 1e-10:
+        return np.eye(3)
+    k = r / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def so3ln(R):
+    """src/so3.cpp:25-69 semantics via a robust axis-angle extraction"""
+    c = (np.trace(R) - 1) / 2
+    c = min(1.0, max(-1.0, c))
+    th = np.arccos(c)
+    if th < 1e-10:
+        return np.zeros(3)
+    if np.pi - th > 1e-6:
+        ax = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / (2 * np.sin(th))
+        return th * ax
+    S = (R + np.eye(3)) / 2
+    i = int(np.argmax(np.diag(S)))
+    ax = S[:, i] / np.sqrt(S[i, i])
+    s = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    if s @ ax < 0:
+        ax = -ax
+    return th * ax
+
+
+def skew(t):
+    return np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+
+
+def _cheirality(R, t, x1, x2):
+    """PoseLib's check_cheirality for unit bearing vectors, all sample points"""
+    for a1, a2 in zip(x1, x2):
+        Rx1 = R @ a1
+        a = -Rx1 @ a2
+        b1 = -Rx1 @ t
+        b2 = a2 @ t
+        if not (b1 - a * b2 > 0 and -a * b1 + b2 > 0):
+            return False
+    return True
+
+
+def minimal_solver(rays6):
+    """rays6: 6 x 6 (u, v) with u, v = (x, y, 1) in pixel units about the principal point.
+    Returns a list of (t[3] unit, r[3], focal), sorted by focal."""
+    u = np.asarray(rays6, float)[:, :3]
+    v = np.asarray(rays6, float)[:, 3:]
+    s = np.sqrt((np.sum(u[:, :2] ** 2) + np.sum(v[:, :2] ** 2)) / 12.0)  # conditioning only: focal is in units of s
+    s = s if s > 0 else 1.0
+    D = np.diag([1 / s, 1 / s, 1.0])
+    x1, x2 = u @ D, v @ D
+    F0, F1, F2 = nullspace_basis(x1, x2)
+    M0, M1, M2 = constraint_matrices(F0, F1, F2)
+    out = []
+    for x, y, w in solve_xyw(M0, M1, M2):
+        f = 1.0 / np.sqrt(w)
+        K = np.diag([f, f, 1.0])
+        E = K @ (x * F0 + y * F1 + F2) @ K
+        U, _, Vt = np.linalg.svd(E)
+        if np.linalg.det(U) < 0:
+            U[:, 2] *= -1
+        if np.linalg.det(Vt) < 0:
+            Vt[2] *= -1
+        W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+        Kinv = np.diag([1 / f, 1 / f, 1.0])
+        b1 = x1 @ Kinv
+        b2 = x2 @ Kinv
+        b1 /= np.linalg.norm(b1, axis=1, keepdims=True)
+        b2 /= np.linalg.norm(b2, axis=1, keepdims=True)
+        for R in (U @ W @ Vt, U @ W.T @ Vt):
+            for t in (U[:, 2], -U[:, 2]):
+                if _cheirality(R, t, b1, b2):
+                    out.append((t.copy(), so3ln(R), f * s))
+    out.sort(key=lambda m: m[2])
+    return out
+
+
+def scoring_matrix(model, focal_scoring=False):
+    t, r, f = model
+    E = skew(t) @ so3exp(r)
+    if focal_scoring:
+        Kinv = np.diag([1.0, 1.0, f])
+        E = Kinv @ E @ Kinv
+    return E
+
+
+def sampson(E, rays):
+    """squared Sampson error in the operation order of the reference (six_point_estimator.cpp:85-90)"""
+    u, v = rays[:, :3], rays[:, 3:]
+    Eu = [(E[i, 0] * u[:, 0] + E[i, 1] * u[:, 1]) + E[i, 2] * u[:, 2] for i in range(3)]
+    Etv = [(E[0, j] * v[:, 0] + E[1, j] * v[:, 1]) + E[2, j] * v[:, 2] for j in range(2)]
+    d = (v[:, 0] * Eu[0] + v[:, 1] * Eu[1]) + v[:, 2] * Eu[2]
+    with np.errstate(all="ignore"):
+        return (d * d) / ((Eu[0] * Eu[0] + Eu[1] * Eu[1]) + (Etv[0] * Etv[0] + Etv[1] * Etv[1]))
+
+
+def required_iterations(w, eta, k, lo, hi):  # include/RansacLib/utils.h:110-140
+    if w <= 0.0:
+        return hi
+    if w >= 1.0:
+        return lo
+    miss = 1.0 - w ** k
+    if miss >= 0.99999999999999:
+        return hi
+    n = np.ceil(np.log(eta) / np.log(miss) + 0.5)
+    return max(lo, min(int(n), hi))
+
+
+def vanilla_msac(rays, sampler, thr2, min_iters=100, max_iters=10000, prob=0.9999, focal_scoring=False,
+                 scoring_of=None):
+    """evaluation/vanilla_ransac.h:23-99 with the six-point estimator.  sampler(iteration) -> 6 indices.
+    scoring_of(model) -> 3x3 lets a test substitute the product's scoring matrix for its own."""
+    n = len(rays)
+    st = dict(num_iterations=0, best_num_inliers=0, best_model_score=np.finfo(float).max, inlier_ratio=0.0,
+              inliers=np.zeros(0, int), model=None, evals=0, status=1 if n < 6 else 2)
+    if n < 6:
+        return st
+    limit = max(max_iters, min_iters)
+    best_min = np.finfo(float).max
+    it = 0
+    while it < limit:
+        models = minimal_solver(rays[sampler(it)])
+        if models:
+            st["evals"] += len(models) * n
+            scores = []
+            for m in models:
+                E = scoring_of(m) if scoring_of else scoring_matrix(m, focal_scoring)
+                scores.append(np.minimum(sampson(E, rays), thr2).sum())  # NaN-propagating like std::min(err, thr)
+            k = int(np.argmin(scores))  # first minimum wins, like the strict '<' scan (ransac.h:278-293)
+            if scores[k] < best_min:
+                best_min = scores[k]
+                st["best_model_score"] = scores[k]
+                st["model"] = models[k]
+                E = scoring_of(models[k]) if scoring_of else scoring_matrix(models[k], focal_scoring)
+                err = sampson(E, rays)
+                st["errors"] = err
+                st["inliers"] = np.nonzero(err < thr2)[0]
+                st["best_num_inliers"] = len(st["inliers"])
+                st["inlier_ratio"] = st["best_num_inliers"] / n
+                limit = required_iterations(st["inlier_ratio"], 1.0 - prob, 6, min_iters, max_iters)
+                st["status"] = 0
+        it += 1
+    st["num_iterations"] = it
+    return st
+
+
+def make_problem(rng, n, focal, outlier_frac=0.0, noise_px=0.0, max_angle_deg=20.0):
+    """synthetic shared-focal pair in pixel units about the principal point (config C4)"""
+    ax = rng.normal(size=3)
+    ax /= np.linalg.norm(ax)
+    ang = np.deg2rad(rng.uniform(-1, 1) * max_angle_deg)
+    R = so3exp(ax * ang)
+    t = rng.normal(size=3)
+    t /= np.linalg.norm(t)
+    X = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(4, 8, n)], axis=1)
+    Y = X @ R.T + t
+    u = np.stack([focal * X[:, 0] / X[:, 2], focal * X[:, 1] / X[:, 2], np.ones(n)], axis=1)
+    v = np.stack([focal * Y[:, 0] / Y[:, 2], focal * Y[:, 1] / Y[:, 2], np.ones(n)], axis=1)
+    u[:, :2] += rng.normal(size=(n, 2)) * noise_px
+    v[:, :2] += rng.normal(size=(n, 2)) * noise_px
+    no = int(round(outlier_frac * n))
+    if no:
+        idx = rng.choice(n, no, replace=False)
+        v[idx, :2] = rng.uniform(-0.5 * focal, 0.5 * focal, size=(no, 2))
+    return np.concatenate([u, v], axis=1), R, t, focal

@@ -24,7 +24,7 @@ _SOURCES = [os.path.join(_DIR, "csrc", f) for f in
 
 SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_NO_DEVICE, SSFM_ERR_CUDA, SSFM_ERR_OOM = 0, 1, 2, 3, 4
 PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL, PAIR_SKIPPED = 0, 1, 2, 3
-SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM = 0, 1, 2
+SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM, SOLVER_SIXPT_FOCAL = 0, 1, 2, 3
 DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED, DRIVER_PREEMPTIVE = 0, 1, 2, 3
 
 
@@ -45,7 +45,7 @@ class SsfmOptions(C.Structure):
         ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
         ("solver", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("fixed_budget", C.c_int32), ("fixed_prob_success", C.c_double), ("first_pair_id", C.c_uint32),
-        ("min_num_points", C.c_int32), ("preemptive_block", C.c_int32), ("reserved", C.c_int32),
+        ("min_num_points", C.c_int32), ("preemptive_block", C.c_int32), ("sixpt_focal_scoring", C.c_int32),
     ]
 
 
@@ -67,7 +67,7 @@ class SsfmPairResult(C.Structure):
         ("E", C.c_double * 9), ("r", C.c_double * 3), ("t", C.c_double * 3),
         ("best_model_score", C.c_double), ("inlier_ratio", C.c_double),
         ("num_iterations", C.c_uint32), ("best_num_inliers", C.c_int32),
-        ("number_lo_iterations", C.c_int32), ("status", C.c_int32), ("evals", C.c_int64),
+        ("number_lo_iterations", C.c_int32), ("status", C.c_int32), ("evals", C.c_int64), ("focal", C.c_double),
     ]
 
 
@@ -84,7 +84,7 @@ RESULT_DTYPE = np.dtype([
     ("E", np.float64, (9,)), ("r", np.float64, (3,)), ("t", np.float64, (3,)),
     ("best_model_score", np.float64), ("inlier_ratio", np.float64),
     ("num_iterations", np.uint32), ("best_num_inliers", np.int32),
-    ("number_lo_iterations", np.int32), ("status", np.int32), ("evals", np.int64)], align=True)
+    ("number_lo_iterations", np.int32), ("status", np.int32), ("evals", np.int64), ("focal", np.float64)], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(SsfmPairResult)
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
@@ -123,7 +123,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_selection_sample", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -281,6 +281,17 @@ class Engine:
         nm = np.zeros(ns, np.int32)
         _check(lib().ssfm_minimal_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns, solver,
                                         _p(models, C.c_double), _p(nm, C.c_int32)))
+        return models, nm
+
+    def sixpt_solve(self, rays, samples6):
+        """SixPointEstimator::MinimalSolver on explicit samples: (models[ns,15,7] = t, r, focal; counts[ns])."""
+        rays = np.ascontiguousarray(rays, np.float64)
+        samples = np.ascontiguousarray(samples6, np.int32).reshape(-1, 6)
+        ns = len(samples)
+        models = np.zeros((ns, 15, 7))
+        nm = np.zeros(ns, np.int32)
+        _check(lib().ssfm_sixpt_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns,
+                                      _p(models, C.c_double), _p(nm, C.c_int32)))
         return models, nm
 
     def score(self, models6, rays, thr2):

@@ -32,6 +32,7 @@ struct Params {
   uint32_t first_pair_id;
   int min_points;  // pairs with fewer correspondences are skipped
   int preempt_block;  // pre-emptive driver: B
+  int sixpt_focal_scoring;  // six-point estimator: score with Kinv E Kinv instead of E
   float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
 };
 

@@ -26,6 +26,7 @@
 
 #include "ssfm_kernels.cuh"
 #include "ssfm_preemptive.cuh"
+#include "ssfm_sixpt_kernels.cuh"
 
 using namespace ssfm;
 
@@ -122,6 +123,9 @@ struct Worker {
   DevBuf<float> s32, s32m;
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned char> has;  // pre-emptive driver: hypothesis-has-a-model flags
+  DevBuf<SixState> six_states;  // six-point estimator
+  DevBuf<int> six_nm, pk_id, pk_count;
+  DevBuf<float> pk_G;
   // outputs of the last run
   double solve_ms = 0, score_ms = 0, chain_ms = 0;
   int rounds = 0, launches = 0;
@@ -133,6 +137,7 @@ struct Worker {
     states.release(); mt.release(); active0.release(); active1.release(); ident.release(); navail.release(); list_a.release();
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release(); has.release();
+    six_states.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
   }
 };
 
@@ -162,6 +167,7 @@ Params make_params(const SsfmOptions& o) {
   P.first_pair_id = o.first_pair_id;
   P.min_points = o.min_num_points;
   P.preempt_block = o.preemptive_block;
+  P.sixpt_focal_scoring = o.sixpt_focal_scoring;
   P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
   return P;
@@ -169,7 +175,9 @@ Params make_params(const SsfmOptions& o) {
 
 int check_options(const SsfmOptions* o) {
   if (!o) return fail(SSFM_ERR_INVALID, "options is NULL");
-  if (o->solver < 0 || o->solver > 2) return fail(SSFM_ERR_INVALID, "unknown solver kind");
+  if (o->solver < 0 || o->solver > 3) return fail(SSFM_ERR_INVALID, "unknown solver kind");
+  if (o->solver == SSFM_SOLVER_SIXPT_FOCAL && o->driver != SSFM_DRIVER_VANILLA_MSAC)
+    return fail(SSFM_ERR_INVALID, "the six-point shared-focal estimator runs under SSFM_DRIVER_VANILLA_MSAC only (its LeastSquares is not built)");
   if (o->driver < 0 || o->driver > 3) return fail(SSFM_ERR_INVALID, "unknown driver kind");
   if (o->driver == SSFM_DRIVER_PREEMPTIVE && (o->fixed_budget <= 0 || o->fixed_budget > 8192 || o->preemptive_block <= 0))
     return fail(SSFM_ERR_INVALID, "pre-emptive driver needs 0 < fixed_budget <= 8192 hypotheses and preemptive_block > 0");
@@ -226,6 +234,86 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
     bool unit_z = h->unit_z;
     const long long c0 = h->h_offsets[pair0], c1 = h->h_offsets[pair0 + np];
     const size_t mpass = (size_t)std::max<long long>(c1 - c0, 1);
+    if (pd.pipelined && (P.solver == SSFM_SOLVER_SIXPT_FOCAL || P.driver == SSFM_DRIVER_PREEMPTIVE)) {
+      // these paths do not launch chunk by chunk: wait for the whole upload of this pass
+      bool all_unit = true;
+      for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) {
+        const int q0 = std::max(h->up_bounds[k], pair0), q1 = std::min(h->up_bounds[k + 1], pair0 + np);
+        if (q1 <= q0) continue;
+        SSFM_WCK(cudaEventSynchronize(h->up_ev[k]));
+        all_unit = all_unit && h->h_up_flags[k] == 0;
+      }
+      unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    }
+    if (P.solver == SSFM_SOLVER_SIXPT_FOCAL) {
+      // Six-point shared-focal estimator under VanillaMSAC: look-ahead rounds like the 3-point path, in
+      // sub-passes bounded by the model table (15 models x 16 doubles per look-ahead slot).
+      const int kSub = 2048;
+      for (int s0 = 0; s0 < np; s0 += kSub) {
+        const int q0 = pair0 + s0, nq = std::min(kSub, np - s0);
+        SSFM_WCK(w.six_states.ensure(nq));
+        SSFM_WCK(w.active0.ensure(nq));
+        SSFM_WCK(w.active1.ensure(nq));
+        SSFM_WCK(w.navail.ensure(nq));
+        SSFM_WCK(w.models.ensure((size_t)nq * R * kSixMaxModels * kSixRecord));
+        SSFM_WCK(w.six_nm.ensure((size_t)nq * R));
+        SSFM_WCK(w.s32m.ensure((size_t)nq * R * kSixSlotModels));
+        SSFM_WCK(w.pk_G.ensure((size_t)nq * R * kSixMaxModels * 9));
+        SSFM_WCK(w.pk_id.ensure((size_t)nq * R * kSixMaxModels));
+        SSFM_WCK(w.pk_count.ensure(nq));
+        SSFM_WCK(cudaMemsetAsync(w.pk_count.p, 0, sizeof(int) * nq, w.stream));
+        k_sixpt_init<<<(nq + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, q0, nq, w.six_states.p, w.active0.p, w.navail.p,
+                                                             first_cap, w.counts.p);
+        launches += 1;
+        int count = nq;
+        int* act = w.active0.p;
+        int* act_next = w.active1.p;
+        int round = 0;
+        while (count > 0) {
+          const int cap = round == 0 ? first_cap : round_cap;
+          SSFM_WCK(cudaEventRecord(evA, w.stream));
+          dim3 gs(count, (cap + 63) / 64);
+          k_sixpt_sample_solve<<<gs, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, q0, act, w.navail.p, w.six_states.p, R,
+                                                        w.models.p, w.six_nm.p, w.pk_G.p, w.pk_id.p, w.pk_count.p, w.s32m.p);
+          SSFM_WCK(cudaGetLastError());
+          SSFM_WCK(cudaEventRecord(evB, w.stream));
+          dim3 gc(count, (cap * kSixMaxModels + 127) / 128);
+          if (unit_z)
+            k_sixpt_score<true><<<gc, 128, 0, w.stream>>>(h->uv4.p, nullptr, h->offsets.p, q0, act, R, w.pk_G.p, w.pk_id.p,
+                                                          w.pk_count.p, thr32, w.s32m.p, w.counters.p);
+          else
+            k_sixpt_score<false><<<gc, 128, 0, w.stream>>>(h->u4.p, h->v4.p, h->offsets.p, q0, act, R, w.pk_G.p, w.pk_id.p,
+                                                           w.pk_count.p, thr32, w.s32m.p, w.counters.p);
+          SSFM_WCK(cudaGetLastError());
+          SSFM_WCK(cudaEventRecord(evC, w.stream));
+          SSFM_WCK(cudaMemsetAsync(w.counts.p + 1, 0, sizeof(int), w.stream));
+          SixChainArgs A;
+          A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = q0; A.list = act; A.nlist = count; A.navail = w.navail.p;
+          A.states = w.six_states.p; A.R = R; A.models = w.models.p; A.nmodels = w.six_nm.p; A.s32m = w.s32m.p;
+          A.flags = h->flags.p; A.results = h->results.p + q0; A.next_active = act_next; A.next_count = w.counts.p + 1;
+          A.next_cap = round_cap; A.pk_count = w.pk_count.p; A.counters = w.counters.p;
+          k_sixpt_chain<<<(count + kSixChainWarps - 1) / kSixChainWarps, kSixChainWarps * 32, 0, w.stream>>>(P, A);
+          SSFM_WCK(cudaGetLastError());
+          SSFM_WCK(cudaEventRecord(evD, w.stream));
+          SSFM_WCK(cudaMemcpyAsync(w.h_count, w.counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+          SSFM_WCK(cudaStreamSynchronize(w.stream));
+          float t1 = 0, t2 = 0, t3 = 0;
+          cudaEventElapsedTime(&t1, evA, evB);
+          cudaEventElapsedTime(&t2, evB, evC);
+          cudaEventElapsedTime(&t3, evC, evD);
+          w.solve_ms += t1;
+          w.score_ms += t2;
+          w.chain_ms += t3;
+          w.score_launches += 1;
+          launches += 3;
+          count = w.h_count[0];
+          std::swap(act, act_next);
+          ++round;
+        }
+        w.rounds = std::max(w.rounds, round);
+      }
+      continue;
+    }
     if (P.driver == SSFM_DRIVER_PREEMPTIVE) {
       // No sequential dependence between hypotheses: generate all M per pair, then one CTA per pair runs the
       // block-wise elimination.  Two launches per pass.
@@ -436,7 +524,7 @@ void ssfm_default_options(SsfmOptions* o) {
   o->first_pair_id = 0u;
   o->min_num_points = 0;
   o->preemptive_block = 10; /* PreemptiveRANSAC( size_t _B = 10 ), preemptive_ransac.h:40 */
-  o->reserved = 0;
+  o->sixpt_focal_scoring = 0;
 }
 
 int ssfm_create(int device, ssfm_handle* out) {
@@ -811,6 +899,32 @@ int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions
 int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t n, int32_t* idx) {
   if (!idx || k <= 0 || k > 8 || n < k) return fail(SSFM_ERR_INVALID, "ssfm_sample: need 0 < k <= 8 and n >= k");
   philox_sample<8>(seed, pair, iter, k, n, idx);
+  return SSFM_OK;
+}
+
+int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples6, int32_t num_samples,
+                     double* models, int32_t* num_models) {
+  if (!h || !rays || !samples6 || !models || !num_models || n < 6 || num_samples < 0)
+    return fail(SSFM_ERR_INVALID, "ssfm_sixpt_solve: bad argument");
+  for (int i = 0; i < 6 * num_samples; ++i)
+    if (samples6[i] < 0 || samples6[i] >= n) return fail(SSFM_ERR_INVALID, "ssfm_sixpt_solve: sample index out of range");
+  if (num_samples == 0) return SSFM_OK;
+  SSFM_CK(cudaSetDevice(h->device));
+  DevBuf<double> d_rays, d_models;
+  DevBuf<int> d_samples, d_nm;
+  SSFM_CK(d_rays.ensure((size_t)n * 6));
+  SSFM_CK(d_models.ensure((size_t)num_samples * kSixMaxModels * 7));
+  SSFM_CK(d_samples.ensure((size_t)num_samples * 6));
+  SSFM_CK(d_nm.ensure(num_samples));
+  SSFM_CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(d_samples.p, samples6, sizeof(int) * 6 * num_samples, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemsetAsync(d_models.p, 0, sizeof(double) * num_samples * kSixMaxModels * 7, h->stream));
+  k_sixpt_solve_samples<<<(num_samples + 63) / 64, 64, 0, h->stream>>>(d_rays.p, d_samples.p, num_samples, d_models.p, d_nm.p);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(models, d_models.p, sizeof(double) * num_samples * kSixMaxModels * 7, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(num_models, d_nm.p, sizeof(int) * num_samples, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  d_rays.release(); d_models.release(); d_samples.release(); d_nm.release();
   return SSFM_OK;
 }
 

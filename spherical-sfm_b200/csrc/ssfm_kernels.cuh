@@ -495,6 +495,7 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Param
         o.number_lo_iterations = st.num_lo;
         o.status = status;
         o.evals = (long long)st.it * 4ll * (long long)n;
+        o.focal = 0.0;
         atomicAdd(&A.counters[1], (unsigned long long)st.evals_exact);
         A.navail[a] = 0;
       }
@@ -608,6 +609,7 @@ __global__ void k_finish_trivial(Params P, const long long* __restrict__ offsets
   o.number_lo_iterations = 0;
   o.status = n < 3 ? SSFM_PAIR_TOO_FEW_POINTS : (n < P.min_points ? SSFM_PAIR_SKIPPED : SSFM_PAIR_NO_MODEL);
   o.evals = 0;
+  o.focal = 0.0;
   results[a] = o;
   if (flags)
     for (int i = 0; i < n; ++i) flags[off - list_base + i] = 0;

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(kPreemptThreads)
       o.number_lo_iterations = 0;
       o.status = N < 4 ? SSFM_PAIR_TOO_FEW_POINTS : SSFM_PAIR_SKIPPED;
       o.evals = 0;
+      o.focal = 0.0;
       results[a] = o;
     }
     return;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(kPreemptThreads)
     o.num_iterations = (uint32_t)M;
     o.number_lo_iterations = 0;
     o.evals = Ev;
+    o.focal = 0.0;
     if (have) {
       o.best_model_score = S;
       o.best_num_inliers = Cn;

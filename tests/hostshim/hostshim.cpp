@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../spherical-sfm_b200/csrc/ssfm_chain.cuh"
+#include "../../spherical-sfm_b200/csrc/ssfm_sixpt.cuh"
 
 using namespace ssfm;
 
@@ -195,6 +196,20 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
   out->evals_exact = st.evals_exact;
   out->rounds = rounds;
   out->candidates = candidates;
+}
+
+// six-point shared-focal minimal solver (csrc/ssfm_sixpt.cuh) on the host, for tests without a GPU
+int hs_sixpt_solve(const double* rays36, double* models /* 15 x 7: t, r, f */, double* G /* 15 x 9 */, int focal_scoring) {
+  double c[6][6];
+  for (int i = 0; i < 36; ++i) c[i / 6][i % 6] = rays36[i];
+  SixPointModel out[kSixMaxModels];
+  const int n = solve_sixpt_focal(c, out);
+  for (int k = 0; k < n; ++k) {
+    for (int d = 0; d < 3; ++d) { models[7 * k + d] = out[k].t[d]; models[7 * k + 3 + d] = out[k].r[d]; }
+    models[7 * k + 6] = out[k].f;
+    sixpt_scoring_matrix(out[k], focal_scoring, G + 9 * k);
+  }
+  return n;
 }
 
 }  // extern "C"

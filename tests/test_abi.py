@@ -40,7 +40,7 @@ def test_built_for_sm_100a_with_tma(S):
 
 
 def test_struct_layouts(S):
-    assert C.sizeof(S.SsfmPairResult) == 160 and S.RESULT_DTYPE.itemsize == 160
+    assert C.sizeof(S.SsfmPairResult) == 168 and S.RESULT_DTYPE.itemsize == 168
     assert C.sizeof(S.SsfmOptions) == 104
     assert C.sizeof(S.SsfmBatch) == 32
 

@@ -1,0 +1,166 @@
+"""Six-point shared-focal estimator: numpy oracle (oracle/sixpt_oracle.py,
+LAPACK eigen-solver) vs the product's own solver (Hessenberg-QR; host build in tests/hostshim without a GPU, the
+device build through the C ABI with one).  PoseLib's arithmetic is absent from the reference tree, so the pins are
+the ground truth of synthetic problems and the agreement of two independent implementations."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import sixpt_oracle as X  # noqa: E402
+
+
+def _host_solve(shim_lib, rays, focal_scoring=0):
+    rays = np.ascontiguousarray(rays, np.float64)
+    m = np.zeros((15, 7))
+    G = np.zeros((15, 9))
+    dp = C.POINTER(C.c_double)
+    n = shim_lib.hs_sixpt_solve(rays.ctypes.data_as(dp), m.ctypes.data_as(dp), G.ctypes.data_as(dp), focal_scoring)
+    return m[:n], G[:n]
+
+
+def _model_diff(a, b):
+    """a: 7-vector (t, r, f); b: oracle tuple"""
+    t, r, f = b
+    return max(np.abs(a[:3] - t).max(), np.abs(a[3:6] - r).max(), abs(a[6] - f) / f)
+
+
+def test_oracle_solver_recovers_ground_truth():
+    rng = np.random.default_rng(1)
+    for k in range(60):
+        rays, R, t, f = X.make_problem(rng, 6, rng.uniform(400, 1200))
+        sols = X.minimal_solver(rays)
+        assert 1 <= len(sols) <= 15
+        best = min(max(np.linalg.norm(X.so3exp(r) - R), np.linalg.norm(tt - t), abs(ff - f) / f) for tt, r, ff in sols)
+        assert best < 1e-6
+        # every solution satisfies the six epipolar constraints with its own focal
+        for m in sols:
+            F = X.scoring_matrix(m, focal_scoring=True)
+            assert np.abs(X.sampson(F, rays)).max() < 1e-12 * f * f
+
+
+def test_product_solver_matches_oracle_on_host(shim):
+    """csrc/ssfm_sixpt.cuh compiled for the host (tests only): same number of solutions, same models to 1e-9
+    (north_star bar: 1e-5 after root matching), noise-free and noisy samples, and the scoring matrices."""
+    rng = np.random.default_rng(2)
+    nsol = 0
+    for k in range(200):
+        rays, R, t, f = X.make_problem(rng, 6, rng.uniform(400, 1200), noise_px=0.0 if k < 100 else 1.0)
+        a, G = _host_solve(shim.lib, rays, focal_scoring=k % 2)
+        b = X.minimal_solver(rays)
+        assert len(a) == len(b), k
+        nsol += len(a)
+        for i, mb in enumerate(b):
+            assert _model_diff(a[i], mb) < 1e-9, (k, i)
+            Go = X.scoring_matrix(mb, focal_scoring=bool(k % 2))
+            assert np.abs(G[i].reshape(3, 3) - Go).max() < 1e-8 * np.abs(Go).max()
+    assert nsol > 200
+
+
+def test_oracle_vanilla_msac_recovers_focal_and_rotation():
+    """Config C4 shape at reduced size: pixel-unit rays, unknown shared focal, 30 % outliers."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    orc = O.load()
+    rng = np.random.default_rng(3)
+    for p in range(2):
+        f = rng.uniform(400, 1200)
+        rays, R, t, f = X.make_problem(rng, 300, f, outlier_frac=0.3, noise_px=0.5)
+        st = X.vanilla_msac(rays, lambda it: orc.philox_sample(7, p, it, 6, len(rays)), 4.0, focal_scoring=True)
+        assert st["status"] == 0 and st["best_num_inliers"] >= 0.6 * 300
+        tt, r, ff = st["model"]
+        # a minimal-sample model without refit: the focal is only weakly constrained by the Sampson error
+        assert 0.5 < ff / f < 2.0
+        assert np.rad2deg(np.linalg.norm(X.so3ln(X.so3exp(r).T @ R))) < 10.0
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_device_solver_matches_oracle(S, engine):
+    rng = np.random.default_rng(4)
+    rays_all, samples = [], []
+    for k in range(64):
+        rays, R, t, f = X.make_problem(rng, 6, rng.uniform(400, 1200), noise_px=0.0 if k < 32 else 1.0)
+        samples.append(np.arange(6) + 6 * k)
+        rays_all.append(rays)
+    rays_all = np.concatenate(rays_all)
+    models, nm = engine.sixpt_solve(rays_all, np.array(samples))
+    for k in range(64):
+        b = X.minimal_solver(rays_all[6 * k:6 * k + 6])
+        assert nm[k] == len(b), k
+        for i, mb in enumerate(b):
+            assert _model_diff(models[k, i], mb) < 1e-9
+
+
+def _run_c4(S, engine, orc, P, N, outl, focal_scoring, seed):
+    rng = np.random.default_rng(seed)
+    parts, truth = [], []
+    for p in range(P):
+        rays, R, t, f = X.make_problem(rng, N, rng.uniform(400, 1200), outlier_frac=outl, noise_px=0.5)
+        parts.append(rays)
+        truth.append((R, t, f))
+    rays = np.concatenate(parts)
+    offsets = (np.arange(P + 1) * N).astype(np.int64)
+    thr2 = 4.0 if focal_scoring else 1e-3
+    opt = S.default_options(squared_inlier_threshold=thr2, driver=S.DRIVER_VANILLA_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
+                            sixpt_focal_scoring=focal_scoring, random_seed=7, first_pair_id=11)
+    res, flags = engine.estimate_pairs(rays, offsets, opt)
+    for p in range(P):
+        pr = rays[offsets[p]:offsets[p + 1]]
+        st = X.vanilla_msac(pr, lambda it: orc.philox_sample(7, 11 + p, it, 6, N), thr2, focal_scoring=bool(focal_scoring))
+        assert int(res["status"][p]) == st["status"]
+        assert int(res["num_iterations"][p]) == st["num_iterations"], p
+        # two independent eigen-solvers may disagree on a near-double root once in ~10^4 samples
+        assert abs(int(res["evals"][p]) - st["evals"]) <= 2 * N, p
+        if st["status"] != 0:
+            continue
+        tt, r, ff = st["model"]
+        assert max(np.abs(res["t"][p] - tt).max(), np.abs(res["r"][p] - r).max(), abs(res["focal"][p] - ff) / ff) < 1e-7
+        assert abs(res["best_model_score"][p] - st["best_model_score"]) <= 1e-9 * st["best_model_score"]
+        # inlier masks: identical except for points within 1e-6 (relative) of the threshold (north_star)
+        fl = np.zeros(N, np.uint8)
+        fl[st["inliers"]] = 1
+        diff = np.nonzero(flags[offsets[p]:offsets[p + 1]] != fl)[0]
+        assert (np.abs(st["errors"][diff] - thr2) <= 1e-6 * thr2).all()
+        assert abs(int(res["best_num_inliers"][p]) - st["best_num_inliers"]) <= len(diff)
+    return res, truth
+
+
+@pytest.mark.gpu
+def test_config_c4_six_point_vanilla_msac(S, engine, orc):
+    """Config C4 (1000 correspondences, 50 % outliers, shared focal U[400,1200], VanillaMSAC) on the device vs the
+    numpy oracle loop: same iteration counts, models, costs, inlier masks; and the focal / rotation are right."""
+    res, truth = _run_c4(S, engine, orc, 3, 1000, 0.5, 1, 5)
+    for p, (R, t, f) in enumerate(truth):
+        assert 0.5 < res["focal"][p] / f < 2.0  # minimal-sample model, no refit: focal weakly constrained
+        assert np.rad2deg(np.linalg.norm(X.so3ln(X.so3exp(res["r"][p]).T @ R))) < 10.0
+        assert res["best_num_inliers"][p] >= 0.45 * 1000
+
+
+@pytest.mark.gpu
+def test_six_point_reference_literal_scoring_and_small_pairs(S, engine, orc):
+    """focal_scoring = 0 is SixPointEstimator::EvaluateModelOnPoint as written upstream (E on the raw rays)."""
+    _run_c4(S, engine, orc, 2, 200, 0.3, 0, 6)
+    _run_c4(S, engine, orc, 4, 120, 0.2, 1, 8)
+
+
+@pytest.mark.gpu
+def test_six_point_edge_cases_and_driver_check(S, engine):
+    rng = np.random.default_rng(9)
+    sizes = [0, 5, 6, 40]
+    parts = [X.make_problem(rng, max(n, 1), 700.0, noise_px=0.2)[0][:n] for n in sizes]
+    rays = np.concatenate(parts)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    opt = S.default_options(squared_inlier_threshold=4.0, driver=S.DRIVER_VANILLA_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
+                            sixpt_focal_scoring=1)
+    res, flags = engine.estimate_pairs(rays, offsets, opt)
+    assert list(res["status"][:2]) == [1, 1]
+    assert res["status"][3] == 0 and res["best_num_inliers"][3] >= 30 and 350 < res["focal"][3] < 1400
+    assert res["num_iterations"][2] == 10000 or res["status"][2] == 0  # six points: every sample is the same set
+    opt.driver = S.DRIVER_LO_MSAC
+    with pytest.raises(S.SsfmError):
+        engine.estimate_pairs(rays, offsets, opt)
