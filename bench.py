@@ -378,6 +378,27 @@ def main():
                               "fp32_frac": 4096.0 * n5 * FLOP_PER_EVAL / (ms5 * 1e-3) / 1e12 / fp32_peak}
     except Exception as exc:  # the headline line must not die on the side measurement
         line["c5_scoring"] = {"error": str(exc)}
+    # config C4 (six-point shared-focal estimator under VanillaMSAC, 1000 corr/pair, 50 % outliers): a 2000-pair
+    # slice of the 20 000-pair configuration, inputs resident
+    try:
+        P4 = 2000
+        rays4, offs4, f4, _, _ = S.problems.make_sixpt_batch(4, P4, 1000)
+        opt4 = S.default_options(squared_inlier_threshold=4.0, driver=S.DRIVER_VANILLA_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
+                                 sixpt_focal_scoring=1, random_seed=1234)
+        eng.upload(rays4, offs4)
+        eng.run(opt4)
+        t0 = time.perf_counter()
+        eng.run(opt4)
+        ms4 = (time.perf_counter() - t0) * 1e3
+        st4 = eng.stats()
+        r4, _ = eng.download(want_flags=False)
+        line["c4_sixpt"] = {"pairs": P4, "corr": 1000, "ms": ms4, "pairs_per_sec": P4 / (ms4 * 1e-3),
+                            "evals_per_sec": float(r4["evals"].sum()) / (ms4 * 1e-3), "mean_iterations": float(r4["num_iterations"].mean()),
+                            "solve_ms": st4.solve_ms, "score_ms": st4.score_ms, "chain_ms": st4.chain_ms,
+                            "focal_within_50pct": float((np.abs(r4["focal"] / f4 - 1) < 0.5).mean())}
+        del rays4
+    except Exception as exc:
+        line["c4_sixpt"] = {"error": str(exc)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(rays_np[:min(P, 32768) * N], N, args.cpu_seconds)
     print(json.dumps(line))

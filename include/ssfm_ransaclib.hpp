@@ -11,6 +11,8 @@
 //   sphericalsfm::MSAC<List,Est>::compute (msac.h:67-131)     ssfm_b200::MSAC<List,Est>::compute            (legacy drivers of the
 //   sphericalsfm::PreemptiveRANSAC<List,Est>::compute         ssfm_b200::PreemptiveRANSAC<List,Est>::compute  Sturm-variant estimator;
 //     (preemptive_ransac.h:46-139)                            + ssfm_b200::GpuSphericalFastEstimator           same signatures)
+//   sphericalsfmtools::SixPointEstimator / SixPointSolution    ssfm_b200::GpuSixPointEstimator / SixPointSolution
+//     (examples/six_point_estimator.h:9-37)                      (VanillaMSAC<SixPointSolution, ..., GpuSixPointEstimator>)
 //   the `#pragma omp parallel for` over pairs                  ssfm_b200::EstimatePairs (ONE call for all pairs)
 //     (examples/spherical_sfm_tools.cpp:332-420)
 //
@@ -219,11 +221,29 @@ class GpuSphericalEstimator {
 };
 
 namespace detail {
+template <class Solver>
+inline auto solver_fields(const Solver& s, SsfmOptions* o, int) -> decltype(s.use_poly_solver(), void()) {
+  o->solver = s.use_poly_solver() ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX;
+}
+template <class Solver>
+inline void solver_fields(const Solver& s, SsfmOptions* o, long) {  // GpuSixPointEstimator
+  o->solver = Solver::kSolver;
+  o->sixpt_focal_scoring = s.focal_scoring() ? 1 : 0;
+}
+template <class Matrix3>
+inline auto store_model(const SsfmPairResult& r, Matrix3* m, int) -> decltype((*m)(0, 0), void()) {
+  from_rowmajor(r.E, m);
+}
+template <class Solution>
+inline void store_model(const SsfmPairResult& r, Solution* m, long) {  // SixPointSolution
+  for (int d = 0; d < 3; ++d) { m->t[d] = r.t[d]; m->r[d] = r.r[d]; }
+  m->focal = r.focal;
+}
 template <class Options, class Solver, class Model, class Statistics>
 int estimate_one(int driver, const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) {
   SsfmOptions o = to_c_options(options);
   o.driver = driver;
-  o.solver = solver.use_poly_solver() ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX;
+  solver_fields(solver, &o, 0);
   o.inward = solver.inward() ? 1 : 0;
   o.first_pair_id = solver.pair_id();
   const int n = solver.num_data();
@@ -236,7 +256,7 @@ int estimate_one(int driver, const Options& options, const Solver& solver, Model
   SsfmPairResult r;
   std::vector<uint8_t> flags(n > 0 ? n : 1);
   check(ssfm_estimate_pairs(solver.handle(), &b, &o, &r, flags.data()));
-  from_rowmajor(r.E, best_model);
+  store_model(r, best_model, 0);
   statistics->num_iterations = r.num_iterations;
   statistics->best_num_inliers = r.best_num_inliers;
   statistics->best_model_score = r.best_model_score;
@@ -267,6 +287,100 @@ class VanillaMSAC {  // evaluation/vanilla_ransac.h:17-23
   int EstimateModel(const Options& options, const Solver& solver, Model* best_model, Statistics* statistics) const {
     return detail::estimate_one(SSFM_DRIVER_VANILLA_MSAC, options, solver, best_model, statistics);
   }
+};
+
+// ---- the six-point shared-focal estimator (examples/six_point_estimator.h:9-37) ------------------------
+struct SixPointSolution {  // :9-13 (sphericalsfm::Pose reduced to its t and r members)
+  double t[3] = {0, 0, 0};
+  double r[3] = {0, 0, 0};
+  double focal = 0.0;
+};
+
+class GpuSixPointEstimator {
+ public:
+  static constexpr int kSolver = SSFM_SOLVER_SIXPT_FOCAL;
+  // focal_scoring = false reproduces EvaluateModelOnPoint as written upstream (E on the raw rays, :78-91)
+  GpuSixPointEstimator(const Engine& eng, const double* rays, int n, bool focal_scoring = false, uint32_t pair_id = 0)
+      : h_(eng.get()), rays_(rays), n_(n), focal_scoring_(focal_scoring), pair_id_(pair_id) {}
+  template <class RayPairList>
+  GpuSixPointEstimator(const Engine& eng, const RayPairList& correspondences, bool focal_scoring = false, uint32_t pair_id = 0)
+      : GpuSixPointEstimator(eng, correspondences.empty() ? nullptr : reinterpret_cast<const double*>(&correspondences[0]),
+                             (int)correspondences.size(), focal_scoring, pair_id) {
+    static_assert(sizeof(correspondences[0]) == 48, "RayPair must be two packed 3-vectors of double");
+  }
+  inline int min_sample_size() const { return 6; }
+  inline int non_minimal_sample_size() const { return 7; }
+  inline int num_data() const { return n_; }
+  const double* rays() const { return rays_; }
+  bool inward() const { return false; }
+  bool focal_scoring() const { return focal_scoring_; }
+  uint32_t pair_id() const { return pair_id_; }
+  ssfm_handle handle() const { return h_; }
+
+  int MinimalSolver(const std::vector<int>& sample, std::vector<SixPointSolution>* solns) const {  // .cpp:93-119
+    solns->clear();
+    if (sample.size() < 6) return 0;
+    double models[15 * 7];
+    int nm = 0;
+    check(ssfm_sixpt_solve(h_, rays_, n_, sample.data(), 1, models, &nm));
+    for (int k = 0; k < nm; ++k) {
+      SixPointSolution s;
+      for (int d = 0; d < 3; ++d) { s.t[d] = models[7 * k + d]; s.r[d] = models[7 * k + 3 + d]; }
+      s.focal = models[7 * k + 6];
+      solns->push_back(s);
+    }
+    return nm;
+  }
+  int NonMinimalSolver(const std::vector<int>& sample, SixPointSolution* soln) const {  // .cpp:121-144
+    std::vector<SixPointSolution> solns;
+    const int nsols = MinimalSolver(sample, &solns);
+    if (nsols == 0) return 0;
+    double best_score = INFINITY;
+    int best_ind = 0;
+    for (int i = 0; i < nsols; ++i) {
+      double score = 0;
+      for (size_t j = 0; j < sample.size(); ++j) score += EvaluateModelOnPoint(solns[i], sample[j]);
+      if (score < best_score) { best_score = score; best_ind = i; }
+    }
+    *soln = solns[best_ind];
+    return 1;
+  }
+  // The 3x3 matrix the estimator scores with: skew3(t) * so3exp(r)  (.cpp:85), optionally Kinv . Kinv.
+  void ScoringMatrix(const SixPointSolution& s, double* G) const {
+    const double th = std::sqrt(s.r[0] * s.r[0] + s.r[1] * s.r[1] + s.r[2] * s.r[2]);
+    double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (th >= 1e-10) {
+      const double k[3] = {s.r[0] / th, s.r[1] / th, s.r[2] / th};
+      const double K[9] = {0, -k[2], k[1], k[2], 0, -k[0], -k[1], k[0], 0};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double kk = 0;
+          for (int l = 0; l < 3; ++l) kk += K[3 * i + l] * K[3 * l + j];
+          R[3 * i + j] += std::sin(th) * K[3 * i + j] + (1 - std::cos(th)) * kk;
+        }
+    }
+    const double S[9] = {0, -s.t[2], s.t[1], s.t[2], 0, -s.t[0], -s.t[1], s.t[0], 0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) G[3 * i + j] = S[3 * i] * R[j] + S[3 * i + 1] * R[3 + j] + S[3 * i + 2] * R[6 + j];
+    if (focal_scoring_) { G[2] *= s.focal; G[5] *= s.focal; G[6] *= s.focal; G[7] *= s.focal; G[8] *= s.focal * s.focal; }
+  }
+  double EvaluateModelOnPoint(const SixPointSolution& soln, int i) const {  // .cpp:78-91
+    double G[9], score = 0.0;
+    int cnt = 0;
+    ScoringMatrix(soln, G);
+    check(ssfm_score_exact(h_, G, 1, rays_ + 6 * (size_t)i, 1, std::numeric_limits<double>::max(), &score, &cnt));
+    return score;
+  }
+  void LeastSquares(const std::vector<int>&, SixPointSolution*) const {  // .cpp:146-192
+    throw Error(SSFM_ERR_INVALID, "SixPointEstimator::LeastSquares (sphere-manifold LM over r, t, focal) is not built");
+  }
+
+ private:
+  ssfm_handle h_;
+  const double* rays_;
+  int n_;
+  bool focal_scoring_;
+  uint32_t pair_id_;
 };
 
 // ---- the legacy drivers (include/sphericalsfm/msac.h, preemptive_ransac.h) ----------------------------

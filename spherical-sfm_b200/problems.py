@@ -111,3 +111,30 @@ def trans_error(t_gt, t):
     b = t / np.linalg.norm(t)
     d = np.clip(a @ b, -1, 1)
     return float(min(np.arccos(d), np.arccos(-d)))
+
+
+def make_sixpt_batch(seed, num_pairs, num_corr, outlier_frac=0.5, noise_px=0.5, focal_range=(400.0, 1200.0), max_angle_deg=20.0):
+    """Config C4 inputs: general (non-spherical) two-view problems with an unknown shared focal; rays are
+    (x - cx, y - cy, 1) in pixel units.  Returns rays (P*N, 6), offsets, focal (P,), R (P,3,3), t (P,3)."""
+    rng = np.random.default_rng(seed)
+    P, N = num_pairs, num_corr
+    f = rng.uniform(focal_range[0], focal_range[1], P)
+    ax = rng.normal(size=(P, 3))
+    ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+    ang = np.deg2rad(rng.uniform(-max_angle_deg, max_angle_deg, P))
+    K = np.zeros((P, 3, 3))
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -ax[:, 2], ax[:, 1], ax[:, 2]
+    K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 0], -ax[:, 1], ax[:, 0]
+    R = np.eye(3)[None] + np.sin(ang)[:, None, None] * K + (1 - np.cos(ang))[:, None, None] * (K @ K)
+    t = rng.normal(size=(P, 3))
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    X = np.stack([rng.uniform(-2, 2, (P, N)), rng.uniform(-2, 2, (P, N)), rng.uniform(4, 8, (P, N))], axis=2)
+    Y = np.einsum("pij,pnj->pni", R, X) + t[:, None, :]
+    rays = np.ones((P, N, 6))
+    rays[:, :, 0:2] = f[:, None, None] * X[:, :, :2] / X[:, :, 2:3] + rng.normal(size=(P, N, 2)) * noise_px
+    rays[:, :, 3:5] = f[:, None, None] * Y[:, :, :2] / Y[:, :, 2:3] + rng.normal(size=(P, N, 2)) * noise_px
+    out = rng.random((P, N)) < outlier_frac
+    v = rays[:, :, 3:5]
+    v[out] = rng.uniform(-0.5, 0.5, (int(out.sum()), 2)) * np.repeat(f[:, None], N, 1)[out][:, None]
+    rays[:, :, 3:5] = v
+    return rays.reshape(P * N, 6), (np.arange(P + 1) * N).astype(np.int64), f, R, t

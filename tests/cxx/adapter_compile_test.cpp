@@ -74,12 +74,23 @@ int main() {
     const int n_pre = pre.compute(rays.begin(), rays.end(), ptrs, &best2, inl);
     Vec3 rr, tr;
     if (best2) best2->decomposeE(false, rr, tr);
+    // the six-point shared-focal estimator under VanillaMSAC (examples/six_point_estimator.h); the rays above are
+    // calibrated (focal 1), so the recovered focal must be ~1
+    GpuSixPointEstimator six(eng, rays, /*focal_scoring=*/true);
+    VanillaMSAC<SixPointSolution, std::vector<SixPointSolution>, GpuSixPointEstimator> ransac6;
+    RansacStatistics stats6;
+    SixPointSolution sol6;
+    const int n_six = ransac6.EstimateModel(options, six, &sol6, &stats6);
+    std::vector<SixPointSolution> sols6;
+    const int nm6 = six.MinimalSolver({1, 2, 3, 4, 6, 7}, &sols6);
+    std::printf("six-point: inliers %d focal %.6f minimal models %d\n", n_six, sol6.focal, nm6);
     std::printf("inliers %d recount %d models %d R02 %.6f (want %.6f) batched %d %d legacy msac %d (iter %d) preemptive %d ry %.6f\n",
                 ninliers, recount, nm, Rm(0, 2), s, res[0].best_num_inliers, res[1].best_num_inliers, n_msac, msac.iter, n_pre,
                 best2 ? rr[1] : 0.0);
     const bool ok = ninliers == 160 && recount == ninliers && nm == 4 && std::fabs(Rm(0, 2) - s) < 1e-6 &&
                     res[0].best_num_inliers == 160 && n_msac == 160 && best != nullptr && n_pre == 160 && best2 != nullptr &&
-                    std::fabs(rr[1] - a) < 1e-6 && (int)inl.size() == 200;
+                    std::fabs(rr[1] - a) < 1e-6 && (int)inl.size() == 200 && n_six == 160 &&
+                    std::fabs(sol6.focal - 1.0) < 1e-6 && nm6 >= 1;
     return ok ? 0 : 1;
   } catch (const Error& e) {
     std::printf("engine error %d: %s\n", e.code(), e.what());
