@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--outliers", type=float, default=C3_OUTLIERS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (from_matches, C5, C4); sweeps only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -335,6 +336,12 @@ def main():
                      "ms_per_launch": score_ms_per_launch,
                      "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3)},
     }
+    if args.no_extras:
+        print(json.dumps(line))
+        eng.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     # the caller-side variant: keypoints + matches + Kinv in, rays built on the device (8 B per match over PCIe)
     try:
         fpx = 600.0

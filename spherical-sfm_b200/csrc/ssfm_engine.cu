@@ -124,6 +124,8 @@ struct Worker {
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned char> has;  // pre-emptive driver: hypothesis-has-a-model flags
   DevBuf<SixState> six_states;  // six-point estimator
+  DevBuf<LMState> lm_states;    // stragglers handed from k_refit_small to k_refit_long
+  DevBuf<int> long_list;
   DevBuf<int> six_nm, pk_id, pk_count;
   DevBuf<float> pk_G;
   // outputs of the last run
@@ -137,6 +139,7 @@ struct Worker {
     states.release(); mt.release(); active0.release(); active1.release(); ident.release(); navail.release(); list_a.release();
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release(); has.release();
+    lm_states.release(); long_list.release();
     six_states.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
   }
 };
@@ -198,6 +201,8 @@ struct RunCfg {
   int first_cap, round_cap, R;
   int small_refit_threads_min;  // waves with more small refits than this use one thread per refit
   bool defer;
+  bool handover;  // stragglers of the one-thread-per-refit kernel continue on a warp
+  int handover_at;
   float thr32;
 };
 
@@ -361,6 +366,8 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
     SSFM_WCK(w.parked0.ensure(np));
     SSFM_WCK(w.parked1.ensure(np));
     SSFM_WCK(w.lm_E.ensure((size_t)np * 9));
+    SSFM_WCK(w.lm_states.ensure(defer ? np : 1));
+    SSFM_WCK(w.long_list.ensure(defer ? np : 1));
 
     k_init_pairs<<<(np + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, pair0, np, w.states.p, w.mt.p, w.active0.p,
                                                          w.ident.p, w.navail.p, first_cap);
@@ -447,11 +454,19 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
             if (ns + nb == 0) break;
             if (ns > cfg.small_refit_threads_min) {
               // persistent lanes pulling from a queue: enough warps to fill the machine, not one per task
-              SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, sizeof(int), hs));
+              SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, 2 * sizeof(int), hs));  // task queue head, straggler count
               const int blocks = std::min((ns + 63) / 64, h->num_sms * 8);
+              const bool handover = cfg.handover;
               k_refit_small<<<blocks, 64, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, w.counts.p + 6, w.states.p,
-                                                   w.list_a.p, c0, w.lm_E.p);
+                                                   w.list_a.p, c0, w.lm_E.p, w.lm_states.p, handover ? w.long_list.p : nullptr,
+                                                   w.counts.p + 7, cfg.handover_at);
               launches += 1;
+              if (handover) {
+                SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, sizeof(int), hs));
+                k_refit_long<<<h->num_sms * 2, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, w.long_list.p, w.counts.p + 7,
+                                                            w.counts.p + 6, w.states.p, w.list_a.p, c0, w.lm_E.p, w.lm_states.p);
+                launches += 1;
+              }
             } else if (ns > 0) {
               // too few to fill the machine one thread each: one warp per refit (lower latency; this is tail)
               k_refit_big<<<(ns + 3) / 4, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, ns, 1, w.states.p,
@@ -773,6 +788,9 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   cfg.R = std::max(cfg.first_cap, cfg.round_cap);
   cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
   cfg.thr32 = (float)P.thr2;
+  cfg.handover = getenv("SSFM_NO_HANDOVER") == nullptr;
+  cfg.handover_at = kHandover;
+  if (const char* e = getenv("SSFM_HANDOVER")) cfg.handover_at = std::max(1, atoi(e));
   // 0: every small refit is solved one thread per problem.  (A warp-per-refit path for thin waves has lower
   // latency but sums in a different order, which would make results depend on how many pairs share a wave.)
   cfg.small_refit_threads_min = 0;

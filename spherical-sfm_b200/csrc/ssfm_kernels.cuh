@@ -523,11 +523,18 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Param
 #ifndef SSFM_REFIT_MINBLOCKS
 #define SSFM_REFIT_MINBLOCKS 4
 #endif
+// A refit that has not converged after kHandover trust-region iterations is a straggler (the median needs 11,
+// 1 % need more than 40, the cap is 200 -- and the slowest refit of a wave sets the wave's duration): its LMState
+// is written out and k_refit_long continues it with a whole warp (residuals across lanes).  The switch depends
+// only on the refit's own iteration count, so results do not depend on what else is in the batch.
+constexpr int kHandover = 24;  // default; SSFM_HANDOVER overrides for sweeps
+
 __global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params P, const double* __restrict__ rays,
                                                     const long long* __restrict__ offsets, int pair0,
                                                     const int* __restrict__ parked, int ntasks, int* queue_head,
                                                     const PairState* __restrict__ states, const int* __restrict__ list_a,
-                                                    long long list_base, double* lm_E) {
+                                                    long long list_base, double* lm_E, LMState* __restrict__ lm_states,
+                                                    int* __restrict__ long_list, int* long_count, int handover_at) {
   SerialCtx cx;
   const bool inward = P.inward != 0;
   int task = ntasks, a = 0, n = 0;
@@ -552,13 +559,50 @@ __global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params
       }
     }
     if (!__any_sync(0xffffffffu, have)) break;
-    if (have && lm_step(cx, ry, smp, n, S)) {
-      double E[9];
-      lm_finish(S, inward, E);
+    if (have) {
+      if (lm_step(cx, ry, smp, n, S)) {
+        double E[9];
+        lm_finish(S, inward, E);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
+        have = false;
+      } else if (S.iteration >= handover_at && long_list != nullptr) {
+        lm_states[a] = S;
+        long_list[atomicAdd(long_count, 1)] = a;
+        have = false;
+      }
+    }
+  }
+}
+
+// Stragglers handed over by k_refit_small: persistent warps pull them from the list.
+__global__ void __launch_bounds__(128) k_refit_long(Params P, const double* __restrict__ rays,
+                                                    const long long* __restrict__ offsets, int pair0,
+                                                    const int* __restrict__ long_list, const int* __restrict__ long_count,
+                                                    int* queue_head, const PairState* __restrict__ states,
+                                                    const int* __restrict__ list_a, long long list_base, double* lm_E,
+                                                    const LMState* __restrict__ lm_states) {
+  WarpCtx cx{(int)(threadIdx.x & 31)};
+  const int ntasks = *long_count;
+  const bool inward = P.inward != 0;
+  for (;;) {
+    int task = 0;
+    if (cx.lane() == 0) task = atomicAdd(queue_head, 1);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= ntasks) break;
+    const int a = long_list[task];
+    const long long off = offsets[pair0 + a];
+    const double* ry = rays + 6 * off;
+    const int* smp = list_a + (off - list_base);
+    const int n = states[a].lm_n;
+    LMState S = lm_states[a];
+    while (!lm_step(cx, ry, smp, n, S)) {
+    }
+    double E[9];
+    lm_finish(S, inward, E);
+    if (cx.lane() == 0)
 #pragma unroll
       for (int i = 0; i < 9; ++i) lm_E[(size_t)a * 9 + i] = E[i];
-      have = false;
-    }
   }
 }
 // big: one WARP per refit (the final least squares over all inliers).
