@@ -404,11 +404,11 @@ SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out)
   // companion matrix of (M2 + mu M1 + mu^2 M0) m = 0:  T = [0 I; -M0^-1 M2, -M0^-1 M1]
   double T[kN][kN];
   {
-    double L[10][10], X[10][20];
+    // rows 10..19 of T serve as the right-hand sides X = [-M2 | -M1] and are solved in place
+    double L[10][10];
     int ok = 1;
-    for (int i = 0; i < 10; ++i) {
-      for (int j = 0; j < 10; ++j) { L[i][j] = M[0][i][j]; X[i][j] = -M[2][i][j]; X[i][10 + j] = -M[1][i][j]; }
-    }
+    for (int i = 0; i < 10; ++i)
+      for (int j = 0; j < 10; ++j) { L[i][j] = M[0][i][j]; T[10 + i][j] = -M[2][i][j]; T[10 + i][10 + j] = -M[1][i][j]; }
     for (int k = 0; k < 10; ++k) {  // Gaussian elimination with partial pivoting on [L | X]
       int piv = k;
       double best = fabs(L[k][k]);
@@ -417,29 +417,26 @@ SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out)
       if (!(best > 1e-300)) { ok = 0; break; }
       if (piv != k) {
         for (int j = 0; j < 10; ++j) { const double tt = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = tt; }
-        for (int j = 0; j < 20; ++j) { const double tt = X[k][j]; X[k][j] = X[piv][j]; X[piv][j] = tt; }
+        for (int j = 0; j < kN; ++j) { const double tt = T[10 + k][j]; T[10 + k][j] = T[10 + piv][j]; T[10 + piv][j] = tt; }
       }
       const double inv = 1.0 / L[k][k];
       for (int i = k + 1; i < 10; ++i) {
         const double f = L[i][k] * inv;
         if (f != 0.0) {
           for (int j = k + 1; j < 10; ++j) L[i][j] -= f * L[k][j];
-          for (int j = 0; j < 20; ++j) X[i][j] -= f * X[k][j];
+          for (int j = 0; j < kN; ++j) T[10 + i][j] -= f * T[10 + k][j];
         }
       }
     }
     if (!ok) return 0;
-    for (int j = 0; j < 20; ++j)
+    for (int j = 0; j < kN; ++j)
       for (int i = 9; i >= 0; --i) {
-        double v = X[i][j];
-        for (int q = i + 1; q < 10; ++q) v -= L[i][q] * X[q][j];
-        X[i][j] = v / L[i][i];
+        double v = T[10 + i][j];
+        for (int q = i + 1; q < 10; ++q) v -= L[i][q] * T[10 + q][j];
+        T[10 + i][j] = v / L[i][i];
       }
     for (int i = 0; i < 10; ++i)
-      for (int j = 0; j < kN; ++j) {
-        T[i][j] = (j == 10 + i) ? 1.0 : 0.0;
-        T[10 + i][j] = X[i][j];
-      }
+      for (int j = 0; j < kN; ++j) T[i][j] = (j == 10 + i) ? 1.0 : 0.0;
   }
   for (int i = 0; i < kN; ++i)
     for (int j = 0; j < kN; ++j)

@@ -59,7 +59,10 @@ __global__ void k_sixpt_init(Params P, const long long* __restrict__ offsets, in
 }
 
 // grid (active pairs, ceil(cap / 64)), 64 threads
-__global__ void __launch_bounds__(64)
+#ifndef SSFM_SIXPT_MINBLOCKS
+#define SSFM_SIXPT_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, SSFM_SIXPT_MINBLOCKS)
     k_sixpt_sample_solve(Params P, const double* __restrict__ rays, const long long* __restrict__ offsets, int pair0,
                          const int* __restrict__ active, const int* __restrict__ navail, const SixState* __restrict__ states,
                          int R, double* __restrict__ models, int* __restrict__ nmodels, float* __restrict__ pk_G,
