@@ -174,6 +174,27 @@ int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* batch);
 int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch, const SsfmOptions* opt,
                                      SsfmPairResult* results, uint8_t* inlier_flags);
 
+/* SfM::Retriangulate (src/sfm.cpp:156-192): one LocallyOptimizedMSAC with
+ * sphericalsfm::TriangulationEstimator (src/triangulation_estimator.cpp:46-127) per 3-D point over its observations,
+ * all points in one call (replaces the cv::parallel_for_ over points).  Cameras are the SfM's poses (t, r);
+ * observations are pixel coordinates with the principal point removed; one focal for all (intrinsics.focal).
+ * `opt` = the options Retriangulate builds (:176-178): ssfm_default_options + squared_inlier_threshold = 4,
+ * final_least_squares = 1; solver/driver fields are ignored.  Outputs (host, caller-allocated): points_xyz
+ * num_points x 3 (zero unless status == SSFM_PAIR_OK, like SetPoint(j, Zero) at :172), num_inliers, status
+ * (SSFM_PAIR_SKIPPED: fewer than 3 observations, :173; SSFM_PAIR_NO_MODEL: fewer than 3 inliers, :186),
+ * num_iterations (may be NULL). */
+typedef struct SsfmTrackBatch {
+  int32_t num_cameras;
+  const double* camera_tr;     /* host, num_cameras x 6: Pose::t, Pose::r */
+  int32_t num_points;
+  const int64_t* obs_offsets;  /* host, num_points + 1 */
+  const int32_t* obs_camera;   /* host, camera index of each observation */
+  const double* obs_xy;        /* host, 2 per observation */
+  double focal;
+} SsfmTrackBatch;
+int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* tracks, const SsfmOptions* opt, double* points_xyz,
+                       int32_t* num_inliers, int32_t* status, uint32_t* num_iterations);
+
 /* The same call split into its three stages, so inputs can stay resident in HBM:
  * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */
 int ssfm_upload(ssfm_handle h, const SsfmBatch* batch);

@@ -77,6 +77,16 @@ class Oracle:
         self.lib.orc_philox_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(it), k, n, _ip(idx))
         return idx
 
+    def triangulate(self, cam_tr, obs_xy, focal, opt, point_id=0):
+        """SfM::Retriangulate for one point: cam_tr (n,6) = t, r of each observation's camera; obs_xy (n,2)."""
+        cam_tr = np.ascontiguousarray(cam_tr, np.float64)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float64)
+        res = OrcResult()
+        inl = np.zeros(max(len(obs_xy), 1), np.int32)
+        n = self.lib.orc_triangulate(_dp(cam_tr), _dp(obs_xy), len(obs_xy), C.c_double(focal), C.byref(opt), C.c_uint32(point_id),
+                                     C.byref(res), _ip(inl))
+        return res, inl[:max(n, 0)].copy()
+
     def knuth_sample(self, seed, pair, hyp, n_total, k):
         idx = np.zeros(k, np.int32)
         self.lib.orc_knuth_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(hyp), n_total, k, _ip(idx))

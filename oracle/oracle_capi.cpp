@@ -16,6 +16,7 @@
 
 #include "lomsac.hpp"
 #include "ssfm_oracle.hpp"
+#include "tri_oracle.hpp"
 
 #include <atomic>
 #include <thread>
@@ -238,6 +239,56 @@ int orc_is_reference(void) {
 void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx) {
   philox_sample(seed, pair, iter, k, n, idx);
 }
+// SfM::Retriangulate for one point (src/sfm.cpp:156-192).  cam_tr: per OBSERVATION t[3], r[3] of its camera pose.
+int orc_triangulate(const double* cam_tr, const double* obs_xy, int n, double focal, const OrcOptions* o, uint32_t point_id,
+                    OrcResult* out, int* inlier_idx) {
+  std::vector<TriObservation> obs(n > 0 ? n : 0);
+  for (int i = 0; i < n; ++i) obs[i] = make_tri_observation(cam_tr + 6 * i, cam_tr + 6 * i + 3, obs_xy + 2 * i, focal);
+  TriangulationEstimator est(obs.data(), n, point_id);
+  Point3 X;
+  Statistics st;
+  for (int i = 0; i < 9; ++i) out->E[i] = 0.0;
+  for (int i = 0; i < 3; ++i) out->r[i] = out->t[i] = 0.0;
+  out->status = 3;  // fewer than 3 observations: the point stays at zero (sfm.cpp:172-173)
+  out->num_iterations = 0; out->best_num_inliers = 0; out->best_model_score = std::numeric_limits<double>::max();
+  out->inlier_ratio = 0; out->number_lo_iterations = 0; out->evals = 0;
+  if (n < 3) return 0;
+  const Options opt = to_options(*o);
+#ifdef SSFM_USE_REFERENCE_RANSACLIB
+  {
+    ransac_lib::LORansacOptions ro;
+    ro.min_num_iterations_ = o->min_num_iterations; ro.max_num_iterations_ = o->max_num_iterations;
+    ro.success_probability_ = o->success_probability; ro.squared_inlier_threshold_ = o->squared_inlier_threshold;
+    ro.random_seed_ = o->random_seed; ro.num_lo_steps_ = o->num_lo_steps; ro.threshold_multiplier_ = o->threshold_multiplier;
+    ro.num_lsq_iterations_ = o->num_lsq_iterations; ro.min_sample_multiplicator_ = o->min_sample_multiplicator;
+    ro.non_min_sample_multiplier_ = o->non_min_sample_multiplier; ro.lo_starting_iterations_ = o->lo_starting_iterations;
+    ro.final_least_squares_ = o->final_least_squares != 0;
+    ransac_lib::RansacStatistics rs;
+    ransac_lib::LocallyOptimizedMSAC<Point3, std::vector<Point3>, TriangulationEstimator, PhiloxSampling<TriangulationEstimator> > ransac;
+    ransac.EstimateModel(ro, est, &X, &rs);
+    st.num_iterations = rs.num_iterations; st.best_num_inliers = rs.best_num_inliers; st.best_model_score = rs.best_model_score;
+    st.inlier_ratio = rs.inlier_ratio; st.inlier_indices = rs.inlier_indices; st.number_lo_iterations = rs.number_lo_iterations;
+  }
+#else
+  lo_msac<TriangulationEstimator, PhiloxSampling<TriangulationEstimator> >(opt, est, &X, &st);
+#endif
+  out->num_iterations = st.num_iterations;
+  out->best_num_inliers = st.best_num_inliers;
+  out->best_model_score = st.best_model_score;
+  out->inlier_ratio = st.inlier_ratio;
+  out->number_lo_iterations = st.number_lo_iterations;
+  out->evals = est.evals_;
+  if (st.best_num_inliers < 3) {  // sfm.cpp:186
+    out->status = 2;
+  } else {
+    out->status = 0;
+    for (int i = 0; i < 3; ++i) out->E[i] = X.v[i];
+  }
+  if (inlier_idx)
+    for (size_t i = 0; i < st.inlier_indices.size(); ++i) inlier_idx[i] = st.inlier_indices[i];
+  return st.best_num_inliers;
+}
+
 void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* idx) {
   knuth_sample(seed, pair, hyp, N, n, idx);
 }

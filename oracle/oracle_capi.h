@@ -45,6 +45,8 @@ typedef struct {
 
 int orc_is_reference(void); /* 1 in oracle/_ref (driver = the reference's RansacLib) */
 void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* idx);
+int orc_triangulate(const double* cam_tr, const double* obs_xy, int n, double focal, const OrcOptions* opt, uint32_t point_id,
+                    OrcResult* out, int* inlier_idx);
 void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* idx);
 int orc_solve(const double* rays, const int* sample, int n, int kind, double* models /* 4x6 */);
 void orc_sampson(const double* E9, const double* rays, int n, double* out);

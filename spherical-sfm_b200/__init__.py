@@ -71,6 +71,14 @@ class SsfmPairResult(C.Structure):
     ]
 
 
+class SsfmTrackBatch(C.Structure):
+    _fields_ = [
+        ("num_cameras", C.c_int32), ("camera_tr", C.POINTER(C.c_double)), ("num_points", C.c_int32),
+        ("obs_offsets", C.POINTER(C.c_int64)), ("obs_camera", C.POINTER(C.c_int32)), ("obs_xy", C.POINTER(C.c_double)),
+        ("focal", C.c_double),
+    ]
+
+
 class SsfmRunStats(C.Structure):
     _fields_ = [
         ("total_ms", C.c_double), ("pack_ms", C.c_double), ("solve_ms", C.c_double), ("score_ms", C.c_double),
@@ -123,7 +131,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -282,6 +290,22 @@ class Engine:
         _check(lib().ssfm_minimal_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns, solver,
                                         _p(models, C.c_double), _p(nm, C.c_int32)))
         return models, nm
+
+    def retriangulate(self, camera_tr, obs_offsets, obs_camera, obs_xy, focal, opt):
+        """ssfm_retriangulate: SfM::Retriangulate for all points.  Returns (points[P,3], num_inliers, status, iterations)."""
+        cam = np.ascontiguousarray(camera_tr, np.float64).reshape(-1, 6)
+        offs = np.ascontiguousarray(obs_offsets, np.int64)
+        oc = np.ascontiguousarray(obs_camera, np.int32)
+        oxy = np.ascontiguousarray(obs_xy, np.float64).reshape(-1, 2)
+        P = len(offs) - 1
+        b = SsfmTrackBatch(len(cam), _p(cam, C.c_double), P, _p(offs, C.c_int64), _p(oc, C.c_int32), _p(oxy, C.c_double), float(focal))
+        pts = np.zeros((max(P, 1), 3))
+        ninl = np.zeros(max(P, 1), np.int32)
+        status = np.zeros(max(P, 1), np.int32)
+        iters = np.zeros(max(P, 1), np.uint32)
+        _check(lib().ssfm_retriangulate(self._h, C.byref(b), C.byref(opt), _p(pts, C.c_double), _p(ninl, C.c_int32),
+                                        _p(status, C.c_int32), _p(iters, C.c_uint32)))
+        return pts[:P], ninl[:P], status[:P], iters[:P]
 
     def sixpt_solve(self, rays, samples6):
         """SixPointEstimator::MinimalSolver on explicit samples: (models[ns,15,7] = t, r, focal; counts[ns])."""

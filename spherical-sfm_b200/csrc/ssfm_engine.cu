@@ -939,6 +939,77 @@ int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t 
   return SSFM_OK;
 }
 
+int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* b, const SsfmOptions* opt, double* points_xyz, int32_t* num_inliers,
+                       int32_t* status, uint32_t* num_iterations) {
+  if (!h || !b || !opt || !points_xyz || !num_inliers || !status) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: NULL argument");
+  if (b->num_points < 0 || b->num_cameras < 0 || !(b->focal > 0.0)) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: bad sizes or focal");
+  if (b->num_points == 0) return SSFM_OK;
+  if (!b->obs_offsets || !b->camera_tr) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: NULL table");
+  const long long M = b->obs_offsets[b->num_points];
+  for (int p = 0; p < b->num_points; ++p)
+    if (b->obs_offsets[p + 1] < b->obs_offsets[p]) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: offsets not monotone");
+  if (b->obs_offsets[0] != 0 || (M > 0 && (!b->obs_camera || !b->obs_xy))) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: bad observation tables");
+  for (long long i = 0; i < M; ++i)
+    if (b->obs_camera[i] < 0 || b->obs_camera[i] >= b->num_cameras) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: camera index out of range");
+  SSFM_CK(cudaSetDevice(h->device));
+  Params P = make_params(*opt);
+  DevBuf<tri::Cam> cams;
+  DevBuf<double> d_tr, d_xy, d_pts;
+  DevBuf<long long> d_off;
+  DevBuf<int> d_cam, d_scratch, d_ninl, d_status;
+  DevBuf<unsigned int> d_iters;
+  DevBuf<uint32_t> d_mt;
+  const int NP = b->num_points;
+  const int kPass = 262144;
+  auto release = [&]() {
+    cams.release(); d_tr.release(); d_xy.release(); d_pts.release(); d_off.release(); d_cam.release(); d_scratch.release();
+    d_ninl.release(); d_status.release(); d_iters.release(); d_mt.release();
+  };
+#define SSFM_RT(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) {                                                                           \
+      release();                                                                                        \
+      return fail(e__ == cudaErrorMemoryAllocation ? SSFM_ERR_OOM : SSFM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                                   \
+  } while (0)
+  SSFM_RT(cams.ensure(std::max(b->num_cameras, 1)));
+  SSFM_RT(d_tr.ensure((size_t)std::max(b->num_cameras, 1) * 6));
+  SSFM_RT(d_xy.ensure((size_t)std::max<long long>(M, 1) * 2));
+  SSFM_RT(d_cam.ensure((size_t)std::max<long long>(M, 1)));
+  SSFM_RT(d_off.ensure((size_t)NP + 1));
+  SSFM_RT(d_pts.ensure((size_t)NP * 3));
+  SSFM_RT(d_ninl.ensure(NP));
+  SSFM_RT(d_status.ensure(NP));
+  SSFM_RT(d_iters.ensure(NP));
+  SSFM_RT(d_mt.ensure((size_t)std::min(NP, kPass) * 625));
+  cudaStream_t st = h->stream;
+  if (b->num_cameras > 0) SSFM_RT(cudaMemcpyAsync(d_tr.p, b->camera_tr, sizeof(double) * 6 * b->num_cameras, cudaMemcpyHostToDevice, st));
+  if (M > 0) {
+    SSFM_RT(cudaMemcpyAsync(d_xy.p, b->obs_xy, sizeof(double) * 2 * M, cudaMemcpyHostToDevice, st));
+    SSFM_RT(cudaMemcpyAsync(d_cam.p, b->obs_camera, sizeof(int) * M, cudaMemcpyHostToDevice, st));
+  }
+  SSFM_RT(cudaMemcpyAsync(d_off.p, b->obs_offsets, sizeof(long long) * ((size_t)NP + 1), cudaMemcpyHostToDevice, st));
+  if (b->num_cameras > 0) k_tri_cameras<<<(b->num_cameras + 127) / 128, 128, 0, st>>>(d_tr.p, b->num_cameras, cams.p);
+  for (int p0 = 0; p0 < NP; p0 += kPass) {
+    const int np = std::min(kPass, NP - p0);
+    const long long c0 = b->obs_offsets[p0], c1 = b->obs_offsets[p0 + np];
+    SSFM_RT(d_scratch.ensure((size_t)std::max<long long>(4 * (c1 - c0), 1)));
+    k_retriangulate<<<(np + 63) / 64, 64, 0, st>>>(P, cams.p, d_off.p, d_cam.p, d_xy.p, b->focal, p0, np, d_scratch.p, c0, d_mt.p,
+                                                   d_pts.p, d_ninl.p, d_status.p, d_iters.p);
+    SSFM_RT(cudaGetLastError());
+    SSFM_RT(cudaStreamSynchronize(st));  // the scratch buffers are reused by the next pass
+  }
+  SSFM_RT(cudaMemcpyAsync(points_xyz, d_pts.p, sizeof(double) * 3 * NP, cudaMemcpyDeviceToHost, st));
+  SSFM_RT(cudaMemcpyAsync(num_inliers, d_ninl.p, sizeof(int) * NP, cudaMemcpyDeviceToHost, st));
+  SSFM_RT(cudaMemcpyAsync(status, d_status.p, sizeof(int) * NP, cudaMemcpyDeviceToHost, st));
+  if (num_iterations) SSFM_RT(cudaMemcpyAsync(num_iterations, d_iters.p, sizeof(unsigned int) * NP, cudaMemcpyDeviceToHost, st));
+  SSFM_RT(cudaStreamSynchronize(st));
+#undef SSFM_RT
+  release();
+  return SSFM_OK;
+}
+
 int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples6, int32_t num_samples,
                      double* models, int32_t* num_models) {
   if (!h || !rays || !samples6 || !models || !num_models || n < 6 || num_samples < 0)

@@ -17,6 +17,7 @@
 
 #include "../../include/ssfm.h"
 #include "ssfm_chain.cuh"
+#include "ssfm_triangulate.cuh"
 
 namespace ssfm {
 
@@ -657,6 +658,51 @@ __global__ void k_finish_trivial(Params P, const long long* __restrict__ offsets
   results[a] = o;
   if (flags)
     for (int i = 0; i < n; ++i) flags[off - list_base + i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Retriangulate (ssfm_triangulate.cuh): camera table, then one thread per point.
+// ------------------------------------------------------------------------------------------
+__global__ void k_tri_cameras(const double* __restrict__ cam_tr, int nc, tri::Cam* __restrict__ cams) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nc) return;
+  tri::Cam c;
+  for (int k = 0; k < 3; ++k) { c.t[k] = cam_tr[6 * i + k]; c.r[k] = cam_tr[6 * i + 3 + k]; }
+  so3exp(c.r, c.R);  // Pose::Pose (src/sfm_types.cpp:14-19)
+  cams[i] = c;
+}
+
+__global__ void __launch_bounds__(64) k_retriangulate(Params P, const tri::Cam* __restrict__ cams,
+                                                      const long long* __restrict__ offsets, const int* __restrict__ obs_cam,
+                                                      const double* __restrict__ obs_xy, double focal, int point0, int npoints,
+                                                      int* __restrict__ scratch, long long scratch_base, uint32_t* __restrict__ mt,
+                                                      double* __restrict__ points, int* __restrict__ num_inliers,
+                                                      int* __restrict__ status, unsigned int* __restrict__ iterations) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= npoints) return;
+  const int pt = point0 + a;
+  const long long off = offsets[pt];
+  const int n = (int)(offsets[pt + 1] - off);
+  double X[3] = {0.0, 0.0, 0.0};  // SetPoint(j, Zero) (src/sfm.cpp:172)
+  tri::Stats st;
+  st.num_iterations = 0; st.best_num_inliers = 0;
+  int code = SSFM_PAIR_SKIPPED;
+  if (n >= 3) {  // :173
+    tri::View v{cams, obs_cam + off, obs_xy + 2 * off, n, focal};
+    int* sc = scratch + 4 * (off - scratch_base);
+    tri::Lists L{sc, sc + n, sc + 2 * n, sc + 3 * n, mt + (size_t)a * 625};
+    const int ninl = tri::lo_msac(P, v, L, P.first_pair_id + (uint32_t)pt, X, st);
+    if (ninl < 3) {  // :186
+      X[0] = X[1] = X[2] = 0.0;
+      code = SSFM_PAIR_NO_MODEL;
+    } else {
+      code = SSFM_PAIR_OK;
+    }
+  }
+  points[3 * (size_t)pt] = X[0]; points[3 * (size_t)pt + 1] = X[1]; points[3 * (size_t)pt + 2] = X[2];
+  num_inliers[pt] = st.best_num_inliers;
+  status[pt] = code;
+  if (iterations) iterations[pt] = st.num_iterations;
 }
 
 // ------------------------------------------------------------------------------------------

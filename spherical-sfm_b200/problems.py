@@ -138,3 +138,41 @@ def make_sixpt_batch(seed, num_pairs, num_corr, outlier_frac=0.5, noise_px=0.5, 
     v[out] = rng.uniform(-0.5, 0.5, (int(out.sum()), 2)) * np.repeat(f[:, None], N, 1)[out][:, None]
     rays[:, :, 3:5] = v
     return rays.reshape(P * N, 6), (np.arange(P + 1) * N).astype(np.int64), f, R, t
+
+
+def make_tracks(seed, num_cameras, num_points, obs_range=(3, 24), focal=600.0, noise_px=0.5, outlier_frac=0.2):
+    """Inputs of SfM::Retriangulate (src/sfm.cpp:156-192): cameras on the unit sphere looking outward (spherical
+    motion: t = R e3 - e3 composed along a circle), 3-D points in front of them, ragged tracks with pixel noise and
+    gross outliers.  Returns camera_tr (C,6: t, r), obs_offsets (P+1), obs_camera, obs_xy, focal, X_true (P,3)."""
+    rng = np.random.default_rng(seed)
+    ang = np.linspace(0, 2 * np.pi, num_cameras, endpoint=False)
+    cam = np.zeros((num_cameras, 6))
+    for i, a in enumerate(ang):
+        r = np.array([0.0, a, 0.0]) + rng.normal(size=3) * 0.01
+        R = so3exp(r)
+        cam[i, :3] = R[:, 2] - np.array([0, 0, 1.0])  # t = R e3 - e3 (src/spherical_utils.cpp:9-14)
+        cam[i, 3:] = r
+    offs = [0]
+    oc, oxy, Xs = [], [], []
+    for p in range(num_points):
+        n = int(rng.integers(obs_range[0], obs_range[1] + 1))
+        c0 = int(rng.integers(0, num_cameras))
+        cams = (c0 + np.arange(n)) % num_cameras
+        R0 = so3exp(cam[c0 + 0 if n == 0 else cams[n // 2], 3:])
+        t0 = cam[cams[n // 2], :3]
+        Xc = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(4, 8)])  # in the middle camera's frame
+        X = R0.T @ (Xc - t0)
+        for c in cams:
+            R = so3exp(cam[c, 3:])
+            PX = R @ X + cam[c, :3]
+            if PX[2] < 1.0 or np.abs(PX[:2] / PX[2]).max() > 1.5:  # not visible from this camera
+                continue
+            xy = focal * PX[:2] / PX[2] + rng.normal(size=2) * noise_px
+            if rng.random() < outlier_frac:
+                xy = rng.uniform(-300, 300, 2)
+            oc.append(c)
+            oxy.append(xy)
+        offs.append(len(oc))
+        Xs.append(X)
+    return (cam, np.array(offs, np.int64), np.array(oc, np.int32), np.array(oxy, np.float64).reshape(-1, 2), focal,
+            np.array(Xs))

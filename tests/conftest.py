@@ -134,6 +134,22 @@ class HostShim:
         return res, flags[:n]
 
 
+    def triangulate(self, cam_tr, obs_xy, focal, opt, point_id):
+        """csrc/ssfm_triangulate.cuh on the host: (X, num_inliers, iterations, num_lo)."""
+        cam_tr = np.ascontiguousarray(cam_tr, np.float64)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float64)
+        hp = HsParams(opt.min_num_iterations, opt.max_num_iterations, opt.success_probability,
+                      opt.squared_inlier_threshold, opt.random_seed, opt.num_lo_steps, opt.threshold_multiplier,
+                      opt.num_lsq_iterations, opt.min_sample_multiplicator, opt.non_min_sample_multiplier,
+                      opt.lo_starting_iterations, opt.final_least_squares, 0, 0, 0, 0, 0.0, 0.0, 0, 0, 0)
+        X = np.zeros(3)
+        it = C.c_uint32()
+        nlo = C.c_int()
+        n = self.lib.hs_triangulate(self.dp(cam_tr), self.dp(obs_xy), len(obs_xy), C.c_double(focal), C.byref(hp),
+                                    C.c_uint32(point_id), self.dp(X), C.byref(it), C.byref(nlo))
+        return X, n, it.value, nlo.value
+
+
 @pytest.fixture(scope="session")
 def shim():
     return HostShim()

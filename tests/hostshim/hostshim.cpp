@@ -9,6 +9,7 @@
 
 #include "../../spherical-sfm_b200/csrc/ssfm_chain.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_sixpt.cuh"
+#include "../../spherical-sfm_b200/csrc/ssfm_triangulate.cuh"
 
 using namespace ssfm;
 
@@ -196,6 +197,33 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
   out->evals_exact = st.evals_exact;
   out->rounds = rounds;
   out->candidates = candidates;
+}
+
+// Retriangulate for one point (csrc/ssfm_triangulate.cuh) on the host, for tests without a GPU.
+// cam_tr: per OBSERVATION t[3], r[3]; returns best_num_inliers.
+int hs_triangulate(const double* cam_tr, const double* obs_xy, int n, double focal, const HsParams* hp, uint32_t point_id,
+                   double* X, uint32_t* iterations, int* num_lo) {
+  Params P{};
+  P.min_iters = hp->min_iters; P.max_iters = hp->max_iters; P.eta = 1.0 - hp->success_probability; P.thr2 = hp->thr2;
+  P.seed = hp->seed; P.num_lo_steps = hp->num_lo_steps; P.thr_mult = hp->thr_mult; P.num_lsq_iters = hp->num_lsq_iters;
+  P.min_sample_mult = hp->min_sample_mult; P.non_min_mult = hp->non_min_mult; P.lo_start = hp->lo_start;
+  P.final_lsq = hp->final_lsq;
+  std::vector<tri::Cam> cams(n > 0 ? n : 1);
+  std::vector<int> oc(n > 0 ? n : 1);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < 3; ++k) { cams[i].t[k] = cam_tr[6 * i + k]; cams[i].r[k] = cam_tr[6 * i + 3 + k]; }
+    so3exp(cams[i].r, cams[i].R);
+    oc[i] = i;
+  }
+  std::vector<int> scratch(4 * (size_t)(n > 0 ? n : 1) + 16);
+  std::vector<uint32_t> mt(625);
+  tri::View v{cams.data(), oc.data(), obs_xy, n, focal};
+  tri::Lists L{scratch.data(), scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 3 * n, mt.data()};
+  tri::Stats st;
+  const int ninl = tri::lo_msac(P, v, L, point_id, X, st);
+  *iterations = st.num_iterations;
+  *num_lo = st.num_lo;
+  return ninl;
 }
 
 // six-point shared-focal minimal solver (csrc/ssfm_sixpt.cuh) on the host, for tests without a GPU
