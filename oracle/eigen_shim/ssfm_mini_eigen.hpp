@@ -19,6 +19,10 @@
 
 #include "../ssfm_oracle.hpp"
 
+#ifndef EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#endif
+
 namespace Eigen {
 
 const int Dynamic = -1;
@@ -149,6 +153,7 @@ typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 3> Matrix3d;
 typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<double, 4, 1> Vector4d;
 typedef Matrix<double, Dynamic, Dynamic> MatrixXd;
 typedef Matrix<double, Dynamic, 1> VectorXd;
 
@@ -187,6 +192,16 @@ struct BlockRef {
   typename Matrix<T, Dynamic, Dynamic>::PartialLU lu() const;
   T squaredNorm() const { return eval().squaredNorm(); }
   T norm() const { return eval().norm(); }
+  Matrix<T, Dynamic, Dynamic> operator/(T s) const {
+    Matrix<T, Dynamic, Dynamic> m = eval();
+    for (T& v : m.d) v /= s;
+    return m;
+  }
+  Matrix<T, Dynamic, Dynamic> operator*(T s) const {
+    Matrix<T, Dynamic, Dynamic> m = eval();
+    for (T& v : m.d) v *= s;
+    return m;
+  }
 };
 
 template <class T, int R, int C>
@@ -356,6 +371,11 @@ struct Matrix<T, R, C>::PartialLU {
     }
     return x;
   }
+  Matrix<T, Dynamic, Dynamic> inverse() const {
+    Matrix<T, Dynamic, Dynamic> id(a.r, a.r);
+    for (int i = 0; i < a.r; ++i) id(i, i) = T(1);
+    return solve(id);
+  }
 };
 template <class T, int R, int C>
 typename Matrix<T, R, C>::PartialLU Matrix<T, R, C>::lu() const {
@@ -411,6 +431,55 @@ class JacobiSVD {
   JacobiSVD(const M& m, unsigned int opts = 0) : f(m.jacobiSvd(opts)) {}
   const Matrix<double, 3, 3>& matrixU() const { return f.U; }
   const Matrix<double, 3, 3>& matrixV() const { return f.V; }
+};
+
+// JacobiSVD of a tall dynamic matrix (src/triangulation_estimator.cpp:81: the 2N x 4 DLT matrix, ComputeFullV):
+// one-sided Jacobi (Hestenes) on the columns of A; singular values descending, V orthogonal.
+template <>
+class JacobiSVD<MatrixXd> {
+ public:
+  MatrixXd V;
+  VectorXd S;
+  JacobiSVD(const MatrixXd& A_in, unsigned int = 0) {
+    MatrixXd A(A_in);
+    const int m = A.rows(), n = A.cols();
+    V = MatrixXd(n, n);
+    for (int i = 0; i < n; ++i) V(i, i) = 1.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+      bool rotated = false;
+      for (int p = 0; p < n - 1; ++p)
+        for (int q = p + 1; q < n; ++q) {
+          double alpha = 0, beta = 0, gamma = 0;
+          for (int i = 0; i < m; ++i) { alpha += A(i, p) * A(i, p); beta += A(i, q) * A(i, q); gamma += A(i, p) * A(i, q); }
+          if (gamma == 0.0 || std::fabs(gamma) <= 1e-16 * std::sqrt(alpha * beta)) continue;
+          rotated = true;
+          const double zeta = (beta - alpha) / (2.0 * gamma);
+          const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+          for (int i = 0; i < m; ++i) { const double a = A(i, p), b = A(i, q); A(i, p) = c * a - s * b; A(i, q) = s * a + c * b; }
+          for (int i = 0; i < n; ++i) { const double a = V(i, p), b = V(i, q); V(i, p) = c * a - s * b; V(i, q) = s * a + c * b; }
+        }
+      if (!rotated) break;
+    }
+    std::vector<double> sv(n);
+    std::vector<int> order(n);
+    for (int j = 0; j < n; ++j) {
+      double s = 0;
+      for (int i = 0; i < m; ++i) s += A(i, j) * A(i, j);
+      sv[j] = std::sqrt(s);
+      order[j] = j;
+    }
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return sv[a] > sv[b]; });
+    MatrixXd Vs(n, n);
+    S = VectorXd(n, 1);
+    for (int j = 0; j < n; ++j) {
+      S(j) = sv[order[j]];
+      for (int i = 0; i < n; ++i) Vs(i, j) = V(i, order[j]);
+    }
+    V = Vs;
+  }
+  const MatrixXd& matrixV() const { return V; }
+  const VectorXd& singularValues() const { return S; }
 };
 
 // ---- EigenSolver (real 4x4): eigenvalues by Hessenberg-QR, unit-norm eigenvectors ----

@@ -180,7 +180,7 @@ def _compiler():
 
 def build(ref=True, force=False):
     """Compile liboracle.so and (when /root/reference is present) _ref/libssfm_ref.so."""
-    srcs = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "oracle_capi.h", "ssfm_oracle.hpp", "lomsac.hpp")]
+    srcs = [os.path.join(_DIR, f) for f in ("oracle_capi.cpp", "oracle_capi.h", "ssfm_oracle.hpp", "lomsac.hpp", "tri_oracle.hpp")]
     newest = max(os.path.getmtime(s) for s in srcs)
     flags = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-shared"]
     out = os.path.join(_DIR, "liboracle.so")
@@ -207,6 +207,13 @@ def build(ref=True, force=False):
             if force or not os.path.exists(out2) or os.path.getmtime(out2) < dep:
                 subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + inc +
                                       ["-o", out2, os.path.join(_DIR, main)] + extra + refsrc)
+        # the reference's triangulation path (src/triangulation_estimator.cpp, sfm_types.cpp, so3.cpp + RansacLib)
+        out3 = os.path.join(_DIR, "_ref", "libssfm_reftri.so")
+        dep = max([newest, os.path.getmtime(os.path.join(_DIR, "ref_tri.cpp"))] + [os.path.getmtime(x) for x in shim])
+        if force or not os.path.exists(out3) or os.path.getmtime(out3) < dep:
+            subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + inc +
+                                  ["-o", out3, os.path.join(_DIR, "ref_tri.cpp")] +
+                                  [os.path.join(refroot, "src", f) for f in ("triangulation_estimator.cpp", "sfm_types.cpp", "so3.cpp")])
 
 
 _cache = {}
@@ -217,6 +224,24 @@ def load():
         build(ref=False)
         _cache["o"] = Oracle(os.path.join(_DIR, "liboracle.so"))
     return _cache["o"]
+
+
+class TriReference:
+    """oracle/_ref/libssfm_reftri.so: only orc_triangulate (the reference's TriangulationEstimator + RansacLib)."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.lib.orc_triangulate.restype = C.c_int
+
+    triangulate = Oracle.triangulate
+
+
+def load_ref_tri():
+    if "t" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_reftri.so")
+        _cache["t"] = TriReference(p) if os.path.exists(p) else None
+    return _cache["t"]
 
 
 def load_ref_full():
