@@ -406,6 +406,25 @@ def main():
         del rays4
     except Exception as exc:
         line["c4_sixpt"] = {"error": str(exc)}
+    # SfM::Retriangulate: 200 000 points, ragged tracks of 3..30 observations, 20 % outliers,
+    # RansacLib's default LO schedule; host buffers in, host buffers out
+    try:
+        base = S.problems.make_tracks(7, 200, 2000, obs_range=(3, 30), noise_px=0.5, outlier_frac=0.2)
+        cam_t, offs0, oc0, oxy0, f_t, _ = base
+        reps_t = 100
+        oc_t = np.tile(oc0, reps_t)
+        oxy_t = np.tile(oxy0, (reps_t, 1))
+        offs_t = np.concatenate([[0], np.cumsum(np.tile(np.diff(offs0), reps_t))]).astype(np.int64)
+        opt_t = S.default_options(squared_inlier_threshold=4.0, final_least_squares=1)
+        eng.retriangulate(cam_t, offs_t, oc_t, oxy_t, f_t, opt_t)
+        t0 = time.perf_counter()
+        _, _, st_t, it_t = eng.retriangulate(cam_t, offs_t, oc_t, oxy_t, f_t, opt_t)
+        ms_t = (time.perf_counter() - t0) * 1e3
+        line["retriangulate"] = {"points": int(len(offs_t) - 1), "observations": int(offs_t[-1]), "ms": ms_t,
+                                 "points_per_sec": (len(offs_t) - 1) / (ms_t * 1e-3), "ok_fraction": float((st_t == 0).mean()),
+                                 "mean_iterations": float(it_t.mean())}
+    except Exception as exc:
+        line["retriangulate"] = {"error": str(exc)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(rays_np[:min(P, 32768) * N], N, args.cpu_seconds)
     print(json.dumps(line))

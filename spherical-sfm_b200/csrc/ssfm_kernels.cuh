@@ -667,8 +667,7 @@ __global__ void k_tri_cameras(const double* __restrict__ cam_tr, int nc, tri::Ca
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nc) return;
   tri::Cam c;
-  for (int k = 0; k < 3; ++k) { c.t[k] = cam_tr[6 * i + k]; c.r[k] = cam_tr[6 * i + 3 + k]; }
-  so3exp(c.r, c.R);  // Pose::Pose (src/sfm_types.cpp:14-19)
+  tri::make_camera(cam_tr + 6 * i, cam_tr + 6 * i + 3, c);  // Pose::Pose (src/sfm_types.cpp:14-19)
   cams[i] = c;
 }
 

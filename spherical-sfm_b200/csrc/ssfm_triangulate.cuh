@@ -16,7 +16,27 @@ namespace tri {
 
 struct Cam {  // sphericalsfm::Pose (src/sfm_types.cpp:14-19): t, r and the rotation block of P = [so3exp(r) | t]
   double t[3], r[3], R[9];
+  double Rc[9];  // the rotation ceres::AngleAxisRotatePoint(r, .) applies (the refit's model of the same pose)
 };
+
+// Fill R (so3exp, as Pose's constructor does) and Rc (ceres/rotation.h's angle-axis formula) from t, r.
+SSFM_HD void make_camera(const double* t, const double* r, Cam& c) {
+  for (int k = 0; k < 3; ++k) { c.t[k] = t[k]; c.r[k] = r[k]; }
+  so3exp(c.r, c.R);
+  double* Rc = c.Rc;
+  const double th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+  if (th2 > 2.220446049250313e-16) {
+    const double th = sqrt(th2), ct = cos(th), st = sin(th), ti = 1.0 / th;
+    const double wx = r[0] * ti, wy = r[1] * ti, wz = r[2] * ti, oc = 1.0 - ct;
+    Rc[0] = ct + wx * wx * oc;       Rc[1] = wx * wy * oc - wz * st;  Rc[2] = wy * st + wx * wz * oc;
+    Rc[3] = wz * st + wx * wy * oc;  Rc[4] = ct + wy * wy * oc;       Rc[5] = -wx * st + wy * wz * oc;
+    Rc[6] = -wy * st + wx * wz * oc; Rc[7] = wx * st + wy * wz * oc;  Rc[8] = ct + wz * wz * oc;
+  } else {
+    Rc[0] = 1; Rc[1] = -r[2]; Rc[2] = r[1];
+    Rc[3] = r[2]; Rc[4] = 1; Rc[5] = -r[0];
+    Rc[6] = -r[1]; Rc[7] = r[0]; Rc[8] = 1;
+  }
+}
 
 struct View {  // the TriangulationObservationList of one point
   const Cam* cams;
@@ -102,19 +122,7 @@ SSFM_HD_NOINLINE void non_minimal(const View& v, const int* sample, int ns, doub
 // ceres::AngleAxisRotatePoint applies).
 SSFM_HD void residual_jac(const View& v, int i, const double* X, double* res, double (*J)[3]) {
   const Cam& c = v.cams[v.obs_cam[i]];
-  double Rc[9];
-  const double th2 = c.r[0] * c.r[0] + c.r[1] * c.r[1] + c.r[2] * c.r[2];
-  if (th2 > 2.220446049250313e-16) {
-    const double th = sqrt(th2), ct = cos(th), st = sin(th), ti = 1.0 / th;
-    const double wx = c.r[0] * ti, wy = c.r[1] * ti, wz = c.r[2] * ti, oc = 1.0 - ct;
-    Rc[0] = ct + wx * wx * oc;      Rc[1] = wx * wy * oc - wz * st; Rc[2] = wy * st + wx * wz * oc;
-    Rc[3] = wz * st + wx * wy * oc; Rc[4] = ct + wy * wy * oc;      Rc[5] = -wx * st + wy * wz * oc;
-    Rc[6] = -wy * st + wx * wz * oc; Rc[7] = wx * st + wy * wz * oc; Rc[8] = ct + wz * wz * oc;
-  } else {
-    Rc[0] = 1; Rc[1] = -c.r[2]; Rc[2] = c.r[1];
-    Rc[3] = c.r[2]; Rc[4] = 1; Rc[5] = -c.r[0];
-    Rc[6] = -c.r[1]; Rc[7] = c.r[0]; Rc[8] = 1;
-  }
+  const double* Rc = c.Rc;
   const double PX0 = Rc[0] * X[0] + Rc[1] * X[1] + Rc[2] * X[2] + c.t[0];
   const double PX1 = Rc[3] * X[0] + Rc[4] * X[1] + Rc[5] * X[2] + c.t[1];
   const double PX2 = Rc[6] * X[0] + Rc[7] * X[1] + Rc[8] * X[2] + c.t[2];

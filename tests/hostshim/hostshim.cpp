@@ -211,8 +211,7 @@ int hs_triangulate(const double* cam_tr, const double* obs_xy, int n, double foc
   std::vector<tri::Cam> cams(n > 0 ? n : 1);
   std::vector<int> oc(n > 0 ? n : 1);
   for (int i = 0; i < n; ++i) {
-    for (int k = 0; k < 3; ++k) { cams[i].t[k] = cam_tr[6 * i + k]; cams[i].r[k] = cam_tr[6 * i + 3 + k]; }
-    so3exp(cams[i].r, cams[i].R);
+    tri::make_camera(cam_tr + 6 * i, cam_tr + 6 * i + 3, cams[i]);
     oc[i] = i;
   }
   std::vector<int> scratch(4 * (size_t)(n > 0 ? n : 1) + 16);
