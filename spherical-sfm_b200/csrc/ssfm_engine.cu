@@ -956,14 +956,16 @@ int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* b, const SsfmOptions
   DevBuf<tri::Cam> cams;
   DevBuf<double> d_tr, d_xy, d_pts;
   DevBuf<long long> d_off;
-  DevBuf<int> d_cam, d_scratch, d_ninl, d_status;
+  DevBuf<int> d_cam, d_scratch, d_ninl, d_status, d_order, d_list0, d_list1, d_cnt;
+  DevBuf<tri::LoState> d_states;
   DevBuf<unsigned int> d_iters;
   DevBuf<uint32_t> d_mt;
   const int NP = b->num_points;
   const int kPass = 262144;
   auto release = [&]() {
     cams.release(); d_tr.release(); d_xy.release(); d_pts.release(); d_off.release(); d_cam.release(); d_scratch.release();
-    d_ninl.release(); d_status.release(); d_iters.release(); d_mt.release();
+    d_ninl.release(); d_status.release(); d_iters.release(); d_mt.release(); d_order.release();
+    d_list0.release(); d_list1.release(); d_cnt.release(); d_states.release();
   };
 #define SSFM_RT(call)                                                                                   \
   do {                                                                                                  \
@@ -991,14 +993,43 @@ int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* b, const SsfmOptions
   }
   SSFM_RT(cudaMemcpyAsync(d_off.p, b->obs_offsets, sizeof(long long) * ((size_t)NP + 1), cudaMemcpyHostToDevice, st));
   if (b->num_cameras > 0) k_tri_cameras<<<(b->num_cameras + 127) / 128, 128, 0, st>>>(d_tr.p, b->num_cameras, cams.p);
+  // process the points in order of track length (stable counting sort on the host)
+  std::vector<int> order(NP);
+  {
+    std::vector<std::pair<int, int>> key(NP);
+    for (int p = 0; p < NP; ++p) key[p] = std::make_pair((int)(b->obs_offsets[p + 1] - b->obs_offsets[p]), p);
+    std::stable_sort(key.begin(), key.end());
+    for (int p = 0; p < NP; ++p) order[p] = key[p].second;
+  }
+  SSFM_RT(d_order.ensure(NP));
+  SSFM_RT(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int) * NP, cudaMemcpyHostToDevice, st));
+  SSFM_RT(d_scratch.ensure((size_t)std::max<long long>(4 * M, 1)));
+  SSFM_RT(d_list0.ensure(std::min(NP, kPass)));
+  SSFM_RT(d_list1.ensure(std::min(NP, kPass)));
+  SSFM_RT(d_states.ensure(std::min(NP, kPass)));
+  SSFM_RT(d_cnt.ensure(1));
   for (int p0 = 0; p0 < NP; p0 += kPass) {
     const int np = std::min(kPass, NP - p0);
-    const long long c0 = b->obs_offsets[p0], c1 = b->obs_offsets[p0 + np];
-    SSFM_RT(d_scratch.ensure((size_t)std::max<long long>(4 * (c1 - c0), 1)));
-    k_retriangulate<<<(np + 63) / 64, 64, 0, st>>>(P, cams.p, d_off.p, d_cam.p, d_xy.p, b->focal, p0, np, d_scratch.p, c0, d_mt.p,
-                                                   d_pts.p, d_ninl.p, d_status.p, d_iters.p);
-    SSFM_RT(cudaGetLastError());
-    SSFM_RT(cudaStreamSynchronize(st));  // the scratch buffers are reused by the next pass
+    // phases: every point runs up to stop_at iterations; the unfinished ones are compacted and continued together
+    // (iteration counts range from min_num_iterations to max_num_iterations: one launch would leave most lanes idle)
+    int count = np;
+    int* cur = nullptr;
+    int* nxt = d_list0.p;
+    unsigned int stop = 256;
+    for (int phase = 0; count > 0; ++phase) {
+      SSFM_RT(cudaMemsetAsync(d_cnt.p, 0, sizeof(int), st));
+      k_retriangulate<<<(count + 63) / 64, 64, 0, st>>>(P, cams.p, d_off.p, d_cam.p, d_xy.p, b->focal, p0, count, d_order.p, cur, nxt,
+                                                        d_cnt.p, stop, d_states.p, d_scratch.p, d_mt.p, d_pts.p, d_ninl.p,
+                                                        d_status.p, d_iters.p);
+      SSFM_RT(cudaGetLastError());
+      int left = 0;
+      SSFM_RT(cudaMemcpyAsync(&left, d_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SSFM_RT(cudaStreamSynchronize(st));
+      count = left;
+      cur = nxt;
+      nxt = (nxt == d_list0.p) ? d_list1.p : d_list0.p;
+      stop = stop >= 0x40000000u ? 0xFFFFFFFFu : stop * 4;
+    }
   }
   SSFM_RT(cudaMemcpyAsync(points_xyz, d_pts.p, sizeof(double) * 3 * NP, cudaMemcpyDeviceToHost, st));
   SSFM_RT(cudaMemcpyAsync(num_inliers, d_ninl.p, sizeof(int) * NP, cudaMemcpyDeviceToHost, st));

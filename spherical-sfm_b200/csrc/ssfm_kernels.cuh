@@ -671,37 +671,55 @@ __global__ void k_tri_cameras(const double* __restrict__ cam_tr, int nc, tri::Ca
   cams[i] = c;
 }
 
+// list == nullptr: the points order[point0 .. point0+npoints) (first phase); otherwise the compacted list of points
+// left unfinished by the previous phase.  A point that reaches `stop_at` iterations without finishing is appended
+// to next_list, its loop state saved, and continued by the next launch among points of similar length.
 __global__ void __launch_bounds__(64) k_retriangulate(Params P, const tri::Cam* __restrict__ cams,
                                                       const long long* __restrict__ offsets, const int* __restrict__ obs_cam,
                                                       const double* __restrict__ obs_xy, double focal, int point0, int npoints,
-                                                      int* __restrict__ scratch, long long scratch_base, uint32_t* __restrict__ mt,
+                                                      const int* __restrict__ order, const int* __restrict__ list,
+                                                      int* __restrict__ next_list, int* __restrict__ next_count,
+                                                      unsigned int stop_at, tri::LoState* __restrict__ states,
+                                                      int* __restrict__ scratch, uint32_t* __restrict__ mt,
                                                       double* __restrict__ points, int* __restrict__ num_inliers,
                                                       int* __restrict__ status, unsigned int* __restrict__ iterations) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= npoints) return;
-  const int pt = point0 + a;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool exists = w < npoints;  // every lane of a warp takes part in lo_msac_run's votes: no early return
+  const int a = exists ? (list ? list[w] : w) : 0;  // slot of this point within the pass (state / mt index)
+  const int pt = order[point0 + a];                 // points sorted by track length: the lanes of a warp loop over similar n
   const long long off = offsets[pt];
-  const int n = (int)(offsets[pt + 1] - off);
+  const int n = exists ? (int)(offsets[pt + 1] - off) : 0;
+  const bool active = exists && n >= 3;  // src/sfm.cpp:173
+  tri::View v{cams, obs_cam + off, obs_xy + 2 * off, active ? n : 0, focal};
+  int* sc = scratch + 4 * off;
+  tri::Lists L{sc, sc + n, sc + 2 * n, sc + 3 * n, mt + (size_t)a * 625};
+  tri::LoState S;
+  S.started = 0;
+  if (active && list) S = states[a];
+  const bool finished = tri::lo_msac_run(P, v, L, P.first_pair_id + (uint32_t)pt, S, stop_at, active);
+  if (!exists) return;
+  if (active && !finished) {
+    states[a] = S;
+    next_list[atomicAdd(next_count, 1)] = a;
+    return;
+  }
+  int code = SSFM_PAIR_SKIPPED, ninl = 0;
+  unsigned int iters = 0;
   double X[3] = {0.0, 0.0, 0.0};  // SetPoint(j, Zero) (src/sfm.cpp:172)
-  tri::Stats st;
-  st.num_iterations = 0; st.best_num_inliers = 0;
-  int code = SSFM_PAIR_SKIPPED;
-  if (n >= 3) {  // :173
-    tri::View v{cams, obs_cam + off, obs_xy + 2 * off, n, focal};
-    int* sc = scratch + 4 * (off - scratch_base);
-    tri::Lists L{sc, sc + n, sc + 2 * n, sc + 3 * n, mt + (size_t)a * 625};
-    const int ninl = tri::lo_msac(P, v, L, P.first_pair_id + (uint32_t)pt, X, st);
+  if (active) {
+    ninl = S.st.best_num_inliers;
+    iters = S.st.num_iterations;
     if (ninl < 3) {  // :186
-      X[0] = X[1] = X[2] = 0.0;
       code = SSFM_PAIR_NO_MODEL;
     } else {
       code = SSFM_PAIR_OK;
+      X[0] = S.X[0]; X[1] = S.X[1]; X[2] = S.X[2];
     }
   }
   points[3 * (size_t)pt] = X[0]; points[3 * (size_t)pt + 1] = X[1]; points[3 * (size_t)pt + 2] = X[2];
-  num_inliers[pt] = st.best_num_inliers;
+  num_inliers[pt] = ninl;
   status[pt] = code;
-  if (iterations) iterations[pt] = st.num_iterations;
+  if (iterations) iterations[pt] = iters;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -340,48 +340,100 @@ SSFM_HD void refresh(const Params& P, const View& v, const Lists& L, const doubl
   if (max_iters) *max_iters = required_iterations(st.inlier_ratio, P.eta, 2, P.min_iters, P.max_iters);
 }
 
-// LocallyOptimizedMSAC::EstimateModel (ransac.h:128-275) with TriangulationEstimator.  Returns best_num_inliers.
-SSFM_HD_NOINLINE int lo_msac(const Params& P, const View& v, const Lists& L, uint32_t point_id, double* X, Stats& st) {
-  st.num_iterations = 0; st.best_num_inliers = 0; st.num_lo = 0; st.best_model_score = kDblMax; st.inlier_ratio = 0.0; st.evals = 0;
-  X[0] = X[1] = X[2] = 0.0;
+// Loop state carried across launches: the kernel runs the points in phases (a point that needs many more
+// iterations than its neighbours is continued in a later, densely packed launch instead of keeping its warp alive).
+struct LoState {
+  double X[3], best_min_model[3], best_min_score;
+  Stats st;
+  uint32_t max_iters;
+  int started;
+};
+
+#if defined(__CUDA_ARCH__)
+#define SSFM_TRI_ALL(p) __all_sync(0xffffffffu, (p))
+#else
+#define SSFM_TRI_ALL(p) (p)
+#endif
+
+// LocallyOptimizedMSAC::EstimateModel (ransac.h:128-275) with TriangulationEstimator, resumable: runs iterations
+// until the loop ends or stats.num_iterations reaches stop_at.  Returns true when the estimate is complete
+// (S.X, S.st final).
+//
+// Warp-synchronous form.  The expensive part of the loop is LocalOptimization (51 least-squares fits), which each
+// point triggers at its own iterations; executed where it stands, one lane would refit while 31 wait.  So a lane
+// that reaches a LocalOptimization call PAUSES there, the warp keeps running the cheap sample/solve/score
+// iterations of the other lanes until all of them are paused (or finished), and then all pending
+// LocalOptimizations run together.  Per point nothing changes: same calls, same order, same generator draws.
+// ALL 32 lanes of a warp must call this function together (dummy lanes pass active = false).
+SSFM_HD_NOINLINE bool lo_msac_run(const Params& P, const View& v, const Lists& L, uint32_t point_id, LoState& S, uint32_t stop_at,
+                                  bool active = true) {
+  Stats& st = S.st;
+  double* X = S.X;
   const int n = v.n;
-  if (2 > n) return 0;
-  mt19937_seed(L.mt, P.seed);
-  uint32_t max_iters = P.max_iters > P.min_iters ? P.max_iters : P.min_iters;
+  if (active && !S.started) {
+    S.started = 1;
+    st.num_iterations = 0; st.best_num_inliers = 0; st.num_lo = 0; st.best_model_score = kDblMax; st.inlier_ratio = 0.0; st.evals = 0;
+    X[0] = X[1] = X[2] = 0.0;
+    S.best_min_model[0] = S.best_min_model[1] = S.best_min_model[2] = 0.0;
+    S.best_min_score = kDblMax;
+    S.max_iters = P.max_iters > P.min_iters ? P.max_iters : P.min_iters;
+    if (n >= 2) mt19937_seed(L.mt, P.seed);
+  }
+  if (n < 2) active = false;  // ransac.h:137-139
   const double thr = P.thr2;
-  double best_min_model[3] = {0, 0, 0}, best_min_score = kDblMax;
-  for (st.num_iterations = 0u; st.num_iterations < max_iters; ++st.num_iterations) {
-    const uint32_t it = st.num_iterations;
-    if (it == P.lo_start && best_min_score < kDblMax) {  // :163-178
+  enum { RUN = 0, LO_TOP = 1, LO_BEST = 2, END = 3, STOP = 4 };
+  int pending = active ? RUN : END;
+  bool sampled = false;  // the LO at the top of iteration lo_start has run; continue that iteration with its sample
+  for (;;) {
+    // ---- cheap section: iterate until a LocalOptimization is due, the loop ends or the phase limit is reached
+    while (pending == RUN) {
+      const uint32_t it = st.num_iterations;
+      if (!sampled) {
+        if (it >= S.max_iters) { pending = END; break; }
+        if (it >= stop_at) { pending = STOP; break; }
+        if (it == P.lo_start && S.best_min_score < kDblMax) { pending = LO_TOP; break; }  // :163-178
+      }
+      sampled = false;
+      int sample[2];
+      philox_sample<2>(P.seed, point_id, it, 2, n, sample);
+      double m[3];
+      non_minimal(v, sample, 2, m);  // MinimalSolver = NonMinimalSolver on the sample, always one model (:56-63)
+      const double s = msac_score(v, m, thr, &st.evals);
+      double local_best = kDblMax;
+      if (s < local_best) local_best = s;  // GetBestEstimatedModelId over one model; a NaN score leaves DBL_MAX
+      if (local_best < S.best_min_score || it == P.lo_start) {  // :195-239
+        const bool is_best = local_best < S.best_min_score;
+        if (is_best) {
+          S.best_min_score = local_best;
+          S.best_min_model[0] = m[0]; S.best_min_model[1] = m[1]; S.best_min_model[2] = m[2];
+          keep(S.best_min_score, S.best_min_model, &st.best_model_score, X);
+        }
+        const bool run_lo = it >= P.lo_start && S.best_min_score < kDblMax;
+        if (run_lo) { pending = LO_BEST; break; }
+        if (is_best) refresh(P, v, L, X, st, &S.max_iters);
+      }
+      ++st.num_iterations;
+    }
+    // ---- every lane of the warp is paused or finished: run the pending LocalOptimizations together
+    if (SSFM_TRI_ALL(pending == END || pending == STOP)) break;
+    if (pending == LO_TOP) {
       ++st.num_lo;
       local_optimization(P, v, L, X, &st.best_model_score, &st.evals);
-      refresh(P, v, L, X, st, &max_iters);
-    }
-    int sample[2];
-    philox_sample<2>(P.seed, point_id, it, 2, n, sample);
-    double m[3];
-    non_minimal(v, sample, 2, m);  // MinimalSolver = NonMinimalSolver on the sample, always one model (:56-63)
-    const double s = msac_score(v, m, thr, &st.evals);
-    double local_best = kDblMax;
-    if (s < local_best) local_best = s;  // GetBestEstimatedModelId over one model; a NaN score leaves DBL_MAX
-    if (local_best < best_min_score || it == P.lo_start) {  // :195-239
-      const bool is_best = local_best < best_min_score;
-      if (is_best) {
-        best_min_score = local_best;
-        best_min_model[0] = m[0]; best_min_model[1] = m[1]; best_min_model[2] = m[2];
-        keep(best_min_score, best_min_model, &st.best_model_score, X);
-      }
-      const bool run_lo = it >= P.lo_start && best_min_score < kDblMax;
-      if (!is_best && !run_lo) continue;
-      if (run_lo) {
-        ++st.num_lo;
-        double score = best_min_score;
-        local_optimization(P, v, L, best_min_model, &score, &st.evals);
-        keep(score, best_min_model, &st.best_model_score, X);
-      }
-      refresh(P, v, L, X, st, &max_iters);
+      refresh(P, v, L, X, st, &S.max_iters);
+      sampled = true;  // resume inside iteration lo_start, after the check
+      pending = RUN;
+    } else if (pending == LO_BEST) {
+      ++st.num_lo;
+      double score = S.best_min_score;
+      local_optimization(P, v, L, S.best_min_model, &score, &st.evals);
+      keep(score, S.best_min_model, &st.best_model_score, X);
+      refresh(P, v, L, X, st, &S.max_iters);
+      ++st.num_iterations;
+      pending = RUN;
     }
   }
+  if (pending == STOP) return false;
+  if (!active) return true;
   if (st.num_iterations <= P.lo_start && st.best_model_score < kDblMax) {  // :245-255
     ++st.num_lo;
     local_optimization(P, v, L, X, &st.best_model_score, &st.evals);
@@ -397,6 +449,17 @@ SSFM_HD_NOINLINE int lo_msac(const Params& P, const View& v, const Lists& L, uin
       refresh(P, v, L, X, st, (uint32_t*)0);
     }
   }
+  return true;
+}
+
+// In one go (tests/hostshim; `chunk` > 0 exercises the resumable path).  Returns best_num_inliers.
+SSFM_HD int lo_msac(const Params& P, const View& v, const Lists& L, uint32_t point_id, double* X, Stats& st, uint32_t chunk = 0) {
+  LoState S;
+  S.started = 0;
+  uint32_t stop = chunk ? chunk : 0xFFFFFFFFu;
+  while (!lo_msac_run(P, v, L, point_id, S, stop)) stop += chunk;
+  X[0] = S.X[0]; X[1] = S.X[1]; X[2] = S.X[2];
+  st = S.st;
   return st.best_num_inliers;
 }
 

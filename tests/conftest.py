@@ -134,7 +134,7 @@ class HostShim:
         return res, flags[:n]
 
 
-    def triangulate(self, cam_tr, obs_xy, focal, opt, point_id):
+    def triangulate(self, cam_tr, obs_xy, focal, opt, point_id, chunk=0):
         """csrc/ssfm_triangulate.cuh on the host: (X, num_inliers, iterations, num_lo)."""
         cam_tr = np.ascontiguousarray(cam_tr, np.float64)
         obs_xy = np.ascontiguousarray(obs_xy, np.float64)
@@ -146,7 +146,7 @@ class HostShim:
         it = C.c_uint32()
         nlo = C.c_int()
         n = self.lib.hs_triangulate(self.dp(cam_tr), self.dp(obs_xy), len(obs_xy), C.c_double(focal), C.byref(hp),
-                                    C.c_uint32(point_id), self.dp(X), C.byref(it), C.byref(nlo))
+                                    C.c_uint32(point_id), self.dp(X), C.byref(it), C.byref(nlo), C.c_uint32(chunk))
         return X, n, it.value, nlo.value
 
 

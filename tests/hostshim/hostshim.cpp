@@ -202,7 +202,7 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
 // Retriangulate for one point (csrc/ssfm_triangulate.cuh) on the host, for tests without a GPU.
 // cam_tr: per OBSERVATION t[3], r[3]; returns best_num_inliers.
 int hs_triangulate(const double* cam_tr, const double* obs_xy, int n, double focal, const HsParams* hp, uint32_t point_id,
-                   double* X, uint32_t* iterations, int* num_lo) {
+                   double* X, uint32_t* iterations, int* num_lo, uint32_t chunk) {
   Params P{};
   P.min_iters = hp->min_iters; P.max_iters = hp->max_iters; P.eta = 1.0 - hp->success_probability; P.thr2 = hp->thr2;
   P.seed = hp->seed; P.num_lo_steps = hp->num_lo_steps; P.thr_mult = hp->thr_mult; P.num_lsq_iters = hp->num_lsq_iters;
@@ -219,7 +219,7 @@ int hs_triangulate(const double* cam_tr, const double* obs_xy, int n, double foc
   tri::View v{cams.data(), oc.data(), obs_xy, n, focal};
   tri::Lists L{scratch.data(), scratch.data() + n, scratch.data() + 2 * n, scratch.data() + 3 * n, mt.data()};
   tri::Stats st;
-  const int ninl = tri::lo_msac(P, v, L, point_id, X, st);
+  const int ninl = tri::lo_msac(P, v, L, point_id, X, st, chunk);
   *iterations = st.num_iterations;
   *num_lo = st.num_lo;
   return ninl;
