@@ -311,7 +311,12 @@ def main():
     prof = os.path.join(ROOT, "profiles", "score_kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            # the ncu capture is of a launch over `pairs_in_capture` pairs x 128 look-ahead slots; DRAM bytes of this
+            # kernel are per pair (its correspondence plane + its model table, each read once), so the figure is
+            # scaled to the average launch of this run
+            pairs_per_launch = evals_per_launch / (4.0 * N * 128.0)
+            traffic = tj.get("dram_bytes_per_launch") * pairs_per_launch / float(tj.get("pairs_in_capture", 8192))
         except Exception:
             traffic = None
     line = {
