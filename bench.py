@@ -341,7 +341,7 @@ def main():
                      "ms_per_launch": score_ms_per_launch,
                      "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3)},
     }
-    if args.no_extras:
+    if args.no_extras or world > 1:  # side measurements are single-GPU only (the other ranks have left by now)
         print(json.dumps(line))
         eng.close()
         if dist is not None:
@@ -365,11 +365,11 @@ def main():
         mt_pin.copy_(mt_all)
         args_m = (kp_all.numpy(), kp_off, kp_pairs.numpy(), mt_pin.numpy(), offsets, Kinv, opt)
         eng.estimate_pairs_from_matches(*args_m, out_results=out_res, out_flags=out_flags)
-        barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             rm, _ = eng.estimate_pairs_from_matches(*args_m, out_results=out_res, out_flags=out_flags)
-        barrier()
+        torch.cuda.synchronize()
         ms_m = (time.perf_counter() - t0) * 1e3 / args.steps
         stm = eng.stats()
         line["e2e_from_matches"] = {"value": float(rm["evals"].sum()) * world / (ms_m * 1e-3), "unit": "evals/s", "ms_per_step": ms_m,
