@@ -48,7 +48,9 @@ enum {
   SSFM_SOLVER_FAST_STURM = 2,    /* SphericalFastEstimator::compute, src/spherical_fast_estimator.cpp:44-257 */
   SSFM_SOLVER_SIXPT_FOCAL = 3    /* SixPointEstimator (examples/six_point_estimator.{h,cpp}): six-point shared-focal
                                     relative pose, <= 15 models {t, r, focal} per sample, min_sample_size 6.  Rays are
-                                    (x - cx, y - cy, 1) in pixel units.  Drivers: SSFM_DRIVER_VANILLA_MSAC (config C4).
+                                    (x - cx, y - cy, 1) in pixel units.  Batched driver: SSFM_DRIVER_VANILLA_MSAC (config C4);
+                                    the whole estimator concept is exposed through the hooks ssfm_sixpt_solve,
+                                    ssfm_score_exact and ssfm_sixpt_least_squares.
                                     SsfmPairResult.E is the matrix the estimator scores with, r/t/focal the model. */
 };
 
@@ -256,6 +258,12 @@ int ssfm_decompose_rescaled(ssfm_handle h, const double* E9, int32_t num, const 
  * num_models: how many of the 15 are valid for each sample. */
 int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples6, int32_t num_samples,
                      double* models, int32_t* num_models);
+
+/* SixPointEstimator::LeastSquares (examples/six_point_estimator.cpp:146-192): trust-region LM over r (3), t on the unit
+ * sphere (ceres::SphereManifold<3>) and the focal, residuals = the SampsonError functor (:25-76) on the listed
+ * correspondences.  models7: nprob x 7 (t, r, focal), refined in place. */
+int ssfm_sixpt_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
+                             const int32_t* sample_offsets, int32_t nprob, double* models7);
 
 /* The LO generator: `ncalls` consecutive RandomShuffleAndResize calls (include/RansacLib/utils.h:48-52)
  * on iota vectors, one std::mt19937(seed) stream (ransac.h:143-144), executed on the device. */

@@ -371,8 +371,12 @@ class GpuSixPointEstimator {
     check(ssfm_score_exact(h_, G, 1, rays_ + 6 * (size_t)i, 1, std::numeric_limits<double>::max(), &score, &cnt));
     return score;
   }
-  void LeastSquares(const std::vector<int>&, SixPointSolution*) const {  // .cpp:146-192
-    throw Error(SSFM_ERR_INVALID, "SixPointEstimator::LeastSquares (sphere-manifold LM over r, t, focal) is not built");
+  void LeastSquares(const std::vector<int>& sample, SixPointSolution* soln) const {  // .cpp:146-192
+    const int offs[2] = {0, (int)sample.size()};
+    double m[7] = {soln->t[0], soln->t[1], soln->t[2], soln->r[0], soln->r[1], soln->r[2], soln->focal};
+    check(ssfm_sixpt_least_squares(h_, rays_, n_, sample.data(), offs, 1, m));
+    for (int d = 0; d < 3; ++d) { soln->t[d] = m[d]; soln->r[d] = m[3 + d]; }
+    soln->focal = m[6];
   }
 
  private:

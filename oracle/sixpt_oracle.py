@@ -322,3 +322,194 @@ def make_problem(rng, n, focal, outlier_frac=0.0, noise_px=0.0, max_angle_deg=20
         idx = rng.choice(n, no, replace=False)
         v[idx, :2] = rng.uniform(-0.5 * focal, 0.5 * focal, size=(no, 2))
     return np.concatenate([u, v], axis=1), R, t, focal
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SixPointEstimator::LeastSquares (examples/six_point_estimator.cpp:146-192).  PARITY UNPINNED (Ceres is absent): the
+# trust-region LM with Solver::Options defaults, the autodiff'd SampsonError functor (:25-76) and
+# ceres::SphereManifold<3> (Plus / PlusJacobian in Householder form) are restated from Ceres' documentation.
+# ---------------------------------------------------------------------------------------------------------------
+class _Dual:
+    """forward-mode scalar with a 7-vector of partials (r1, t1, focal) -- the role of ceres::Jet<double, 7>"""
+    __slots__ = ("a", "v")
+
+    def __init__(self, a, v=None):
+        self.a = float(a)
+        self.v = np.zeros(7) if v is None else v
+
+    @staticmethod
+    def var(a, k):
+        v = np.zeros(7)
+        v[k] = 1.0
+        return _Dual(a, v)
+
+    def _c(self, o):
+        return o if isinstance(o, _Dual) else _Dual(o)
+
+    def __add__(self, o):
+        o = self._c(o)
+        return _Dual(self.a + o.a, self.v + o.v)
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        o = self._c(o)
+        return _Dual(self.a - o.a, self.v - o.v)
+
+    def __rsub__(self, o):
+        return self._c(o) - self
+
+    def __neg__(self):
+        return _Dual(-self.a, -self.v)
+
+    def __mul__(self, o):
+        o = self._c(o)
+        return _Dual(self.a * o.a, self.a * o.v + self.v * o.a)
+    __rmul__ = __mul__
+
+    def __truediv__(self, o):
+        o = self._c(o)
+        q = self.a / o.a
+        return _Dual(q, (self.v - q * o.v) / o.a)
+
+
+def _dsqrt(x):
+    r = np.sqrt(x.a)
+    return _Dual(r, x.v * (0.5 / r))
+
+
+def _sampson_functor(x7, u, v):
+    """SampsonError::operator() with r0 = t0 = 0 (Ri = I): returns the residual as a _Dual"""
+    r = [x7[0], x7[1], x7[2]]
+    t = [x7[3], x7[4], x7[5]]
+    f = x7[6]
+    th2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2]
+    if th2.a > np.finfo(float).eps:  # ceres::AngleAxisToRotationMatrix
+        th = _dsqrt(th2)
+        wx, wy, wz = r[0] / th, r[1] / th, r[2] / th
+        ct, st = _Dual(np.cos(th.a), -np.sin(th.a) * th.v), _Dual(np.sin(th.a), np.cos(th.a) * th.v)
+        oc = 1.0 - ct
+        R = [[ct + wx * wx * oc, wx * wy * oc - wz * st, wy * st + wx * wz * oc],
+             [wz * st + wx * wy * oc, ct + wy * wy * oc, wy * wz * oc - wx * st],
+             [wx * wz * oc - wy * st, wx * st + wy * wz * oc, ct + wz * wz * oc]]
+    else:
+        one = _Dual(1.0)
+        R = [[one, -r[2], r[1]], [r[2], one, -r[0]], [-r[1], r[0], one]]
+    sk = [[_Dual(0.0), -t[2], t[1]], [t[2], _Dual(0.0), -t[0]], [-t[1], t[0], _Dual(0.0)]]
+    E = [[sk[i][0] * R[0][j] + sk[i][1] * R[1][j] + sk[i][2] * R[2][j] for j in range(3)] for i in range(3)]
+    k = [_Dual(1.0), _Dual(1.0), f]
+    F = [[k[i] * E[i][j] * k[j] for j in range(3)] for i in range(3)]
+    Fu = [F[i][0] * u[0] + F[i][1] * u[1] + F[i][2] * u[2] for i in range(3)]
+    Ftv = [F[0][j] * v[0] + F[1][j] * v[1] + F[2][j] * v[2] for j in range(3)]
+    d = Fu[0] * v[0] + Fu[1] * v[1] + Fu[2] * v[2]
+    return (d * d) / (Fu[0] * Fu[0] + Fu[1] * Fu[1] + Ftv[0] * Ftv[0] + Ftv[1] * Ftv[1])
+
+
+def _householder3(x):
+    sigma = x[0] * x[0] + x[1] * x[1]
+    v = np.array([x[0], x[1], 1.0])
+    if sigma <= np.finfo(float).eps:
+        return v, (2.0 if x[2] < 0 else 0.0)
+    mu = np.sqrt(x[2] * x[2] + sigma)
+    vp = x[2] - mu if x[2] <= 0 else -sigma / (x[2] + mu)
+    beta = 2.0 * vp * vp / (sigma + vp * vp)
+    v[:2] /= vp
+    return v, beta
+
+
+def sphere_plus(x, d):
+    nd = np.linalg.norm(d)
+    if nd == 0:
+        return np.array(x, float)
+    v, beta = _householder3(x)
+    y = np.array([np.sin(nd) / nd * d[0], np.sin(nd) / nd * d[1], np.cos(nd)])
+    return np.linalg.norm(x) * (y - v * (beta * (v @ y)))
+
+
+def sphere_plus_jacobian(x):
+    v, beta = _householder3(x)
+    return np.linalg.norm(x) * (np.eye(3) - beta * np.outer(v, v))[:, :2]
+
+
+def least_squares(rays, sample, model, max_iters=200):
+    """returns (refined model, iterations, initial cost, final cost)"""
+    t, r, f = model
+    x = np.concatenate([np.asarray(r, float), np.asarray(t, float), [float(f)]])
+    pts = [(rays[i, :3], rays[i, 3:]) for i in sample]
+
+    def eval_full(xx):
+        X = [_Dual.var(xx[k], k) for k in range(7)]
+        res = [_sampson_functor(X, u, v) for u, v in pts]
+        rv = np.array([q.a for q in res])
+        Ja = np.array([q.v for q in res]).reshape(-1, 7)
+        Pt = sphere_plus_jacobian(xx[3:6])
+        Jl = np.concatenate([Ja[:, :3], Ja[:, 3:6] @ Pt, Ja[:, 6:7]], axis=1)
+        return rv, Jl
+
+    def eval_cost(xx):
+        X = [_Dual(xx[k]) for k in range(7)]
+        rv = np.array([_sampson_functor(X, u, v).a for u, v in pts])
+        return 0.5 * float(rv @ rv)
+
+    res, J = eval_full(x)
+    x_cost = 0.5 * float(res @ res)
+    initial = x_cost
+    if not np.isfinite(x_cost):
+        return model, 0, initial, x_cost
+    scale = 1.0 / (1.0 + np.sqrt((J * J).sum(axis=0))) if len(pts) else np.ones(6)
+    J = J * scale
+    grad_max = np.abs((J / scale).T @ res).max() if len(pts) else 0.0
+    radius, decrease, reuse, invalid, it = 1e4, 2.0, False, 0, 0
+    diagonal = np.zeros(6)
+    while True:
+        if it >= max_iters or grad_max <= 1e-10 or radius < 1e-32:
+            break
+        it += 1
+        H = J.T @ J
+        g = J.T @ res
+        if not reuse:
+            diagonal = np.minimum(np.maximum(np.diag(H), 1e-6), 1e32)
+        reuse = True
+        valid = True
+        try:
+            L = np.linalg.cholesky(H + np.diag(diagonal / radius))
+            step = -np.linalg.solve(L.T, np.linalg.solve(L, g))
+            valid = bool(np.isfinite(step).all())
+        except np.linalg.LinAlgError:
+            valid = False
+        mcc = 0.0
+        if valid:
+            m = J @ step
+            mcc = -float(m @ (res + m / 2.0))
+            valid = mcc > 0.0
+        if not valid:
+            invalid += 1
+            if invalid >= 10:
+                break
+            radius /= decrease
+            decrease *= 2.0
+            continue
+        invalid = 0
+        delta = step * scale
+        cand = np.concatenate([x[:3] + delta[:3], sphere_plus(x[3:6], delta[3:5]), [x[6] + delta[5]]])
+        step_norm, x_norm = np.linalg.norm(cand - x), np.linalg.norm(x)
+        cand_cost = eval_cost(cand)
+        if not np.isfinite(cand_cost):
+            cand_cost = np.finfo(float).max
+        if step_norm <= 1e-8 * (x_norm + 1e-8):
+            break
+        change = x_cost - cand_cost
+        if abs(change) <= 1e-6 * x_cost:
+            break
+        rho = change / mcc
+        if rho > 1e-3:
+            x = cand
+            res, J = eval_full(x)
+            x_cost = 0.5 * float(res @ res)
+            grad_max = np.abs(J.T @ res).max()
+            J = J * scale
+            radius = min(1e16, radius / max(1.0 / 3.0, 1.0 - (2.0 * rho - 1.0) ** 3))
+            decrease, reuse = 2.0, False
+        else:
+            radius /= decrease
+            decrease *= 2.0
+    return (x[3:6].copy(), x[:3].copy(), float(x[6])), it, initial, x_cost

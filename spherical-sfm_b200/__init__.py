@@ -131,7 +131,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -317,6 +317,16 @@ class Engine:
         _check(lib().ssfm_sixpt_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns,
                                       _p(models, C.c_double), _p(nm, C.c_int32)))
         return models, nm
+
+    def sixpt_least_squares(self, rays, samples, models7):
+        """SixPointEstimator::LeastSquares on lists of correspondence indices; models7 (n,7) = t, r, focal."""
+        rays = np.ascontiguousarray(rays, np.float64)
+        idx = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in samples]), np.int32)
+        offs = np.concatenate([[0], np.cumsum([len(s) for s in samples])]).astype(np.int32)
+        m = np.ascontiguousarray(models7, np.float64).reshape(-1, 7).copy()
+        _check(lib().ssfm_sixpt_least_squares(self._h, _p(rays, C.c_double), len(rays), _p(idx, C.c_int32), _p(offs, C.c_int32),
+                                              len(samples), _p(m, C.c_double)))
+        return m
 
     def score(self, models6, rays, thr2):
         models6 = np.ascontiguousarray(models6, np.float64).reshape(-1, 6)

@@ -180,7 +180,7 @@ int check_options(const SsfmOptions* o) {
   if (!o) return fail(SSFM_ERR_INVALID, "options is NULL");
   if (o->solver < 0 || o->solver > 3) return fail(SSFM_ERR_INVALID, "unknown solver kind");
   if (o->solver == SSFM_SOLVER_SIXPT_FOCAL && o->driver != SSFM_DRIVER_VANILLA_MSAC)
-    return fail(SSFM_ERR_INVALID, "the six-point shared-focal estimator runs under SSFM_DRIVER_VANILLA_MSAC only (its LeastSquares is not built)");
+    return fail(SSFM_ERR_INVALID, "the batched six-point shared-focal path runs SSFM_DRIVER_VANILLA_MSAC (config C4); for LO-MSAC drive GpuSixPointEstimator through the hooks");
   if (o->driver < 0 || o->driver > 3) return fail(SSFM_ERR_INVALID, "unknown driver kind");
   if (o->driver == SSFM_DRIVER_PREEMPTIVE && (o->fixed_budget <= 0 || o->fixed_budget > 8192 || o->preemptive_block <= 0))
     return fail(SSFM_ERR_INVALID, "pre-emptive driver needs 0 < fixed_budget <= 8192 hypotheses and preemptive_block > 0");
@@ -1207,6 +1207,31 @@ int ssfm_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32
   k_least_squares<<<(nprob + 3) / 4, 128, 0, h->stream>>>(dr, di, dof, nprob, inward, de);
   SSFM_CK(cudaGetLastError());
   SSFM_CK(cudaMemcpyAsync(E9, de, sizeof(double) * 9 * (size_t)nprob, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  return SSFM_OK;
+}
+
+int ssfm_sixpt_least_squares(ssfm_handle h, const double* rays, int32_t n, const int32_t* sample_idx,
+                             const int32_t* sample_offsets, int32_t nprob, double* models7) {
+  if (!h || !rays || !sample_idx || !sample_offsets || !models7 || nprob < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (nprob == 0) return SSFM_OK;
+  const int total = sample_offsets[nprob];
+  for (int i = 0; i < total; ++i)
+    if (sample_idx[i] < 0 || sample_idx[i] >= n) return fail(SSFM_ERR_INVALID, "sample index out of range");
+  SSFM_CK(cudaSetDevice(h->device));
+  TmpGuard g;
+  SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
+  SSFM_TMP(int, b_i, (size_t)total) SSFM_KEEP(g, b_i)
+  SSFM_TMP(int, b_o, (size_t)nprob + 1) SSFM_KEEP(g, b_o)
+  SSFM_TMP(double, b_m, (size_t)nprob * 7) SSFM_KEEP(g, b_m)
+  double* dr = (double*)g.ptrs[0]; int* di = (int*)g.ptrs[1]; int* dof = (int*)g.ptrs[2]; double* dm = (double*)g.ptrs[3];
+  if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  if (total > 0) SSFM_CK(cudaMemcpyAsync(di, sample_idx, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dof, sample_offsets, sizeof(int) * ((size_t)nprob + 1), cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dm, models7, sizeof(double) * 7 * (size_t)nprob, cudaMemcpyHostToDevice, h->stream));
+  k_sixpt_least_squares<<<(nprob + 63) / 64, 64, 0, h->stream>>>(dr, di, dof, nprob, dm);
+  SSFM_CK(cudaGetLastError());
+  SSFM_CK(cudaMemcpyAsync(models7, dm, sizeof(double) * 7 * (size_t)nprob, cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
   return SSFM_OK;
 }

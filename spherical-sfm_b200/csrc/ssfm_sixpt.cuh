@@ -571,4 +571,214 @@ SSFM_HD void sixpt_scoring_matrix(const SixPointModel& m, int focal_scoring, dou
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SixPointEstimator::LeastSquares (examples/six_point_estimator.cpp:146-192): Ceres trust-region LM over
+// r1 (3), t1 on the unit sphere (ceres::SphereManifold<3>, 2 tangent dimensions) and the focal (1), residual =
+// the SampsonError functor (:25-76) with r0 = t0 = 0: E = [t1]x R(r1), F = Kinv E Kinv, Kinv = diag(1,1,focal).
+// Ceres is absent from the reference tree: Solver::Options defaults and the SphereManifold Plus / PlusJacobian
+// (Householder form) are restated from its documentation, as in the 3-point refit.
+// ---------------------------------------------------------------------------------------------
+namespace sixpt {
+
+// Householder vector of ceres::internal::ComputeHouseholderVector for a 3-vector: H = I - beta v v^T maps x to |x| e3.
+SSFM_HD void householder3(const double* x, double* v, double* beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  v[0] = x[0]; v[1] = x[1]; v[2] = 1.0;
+  *beta = 0.0;
+  const double xp = x[2];
+  if (sigma <= 2.220446049250313e-16) {
+    if (xp < 0.0) *beta = 2.0;
+    return;
+  }
+  const double mu = sqrt(xp * xp + sigma);
+  const double vp = xp <= 0.0 ? xp - mu : -sigma / (xp + mu);
+  *beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp; v[1] /= vp;
+}
+// SphereManifold<3>::Plus: x_plus = |x| H [sin(|d|) d / |d| ; cos(|d|)]
+SSFM_HD void sphere_plus(const double* x, const double* d, double* out) {
+  const double nd = sqrt(d[0] * d[0] + d[1] * d[1]);
+  if (nd == 0.0) { out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; return; }
+  double v[3], beta;
+  householder3(x, v, &beta);
+  const double sbd = sin(nd) / nd;
+  const double y[3] = {sbd * d[0], sbd * d[1], cos(nd)};
+  const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  const double vy = beta * (v[0] * y[0] + v[1] * y[1] + v[2] * y[2]);
+  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * vy);
+}
+// SphereManifold<3>::PlusJacobian (3 x 2): |x| times the first two columns of H
+SSFM_HD void sphere_plus_jacobian(const double* x, double (*J)[2]) {
+  double v[3], beta;
+  householder3(x, v, &beta);
+  const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 2; ++j) J[i][j] = nx * ((i == j ? 1.0 : 0.0) - beta * v[i] * v[j]);
+}
+
+}  // namespace sixpt
+
+struct SixLmSummary {
+  int iterations;
+  double initial_cost, final_cost;
+};
+
+// rays: the estimator's correspondences (6 doubles each); sample: indices of the residuals.
+SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const double* rays, const int* sample, int n, SixPointModel& model) {
+  using namespace sixpt;
+  double x[7] = {model.r[0], model.r[1], model.r[2], model.t[0], model.t[1], model.t[2], model.f};
+  double H[21], g[6], scale[6], diagonal[6] = {0, 0, 0, 0, 0, 0}, gmax = 0.0;
+  bool have_scale = false;
+  // residuals (the functor returns d^2/den itself as the residual, :72) and the local Jacobian at xx
+  auto evaluate = [&](const double* xx, bool with_jac) -> double {
+    double c = 0.0;
+    Jet6 Ej[9];
+    double Pt[3][2];
+    if (with_jac) {
+      const Jet6 r1[3] = {jvar(xx[0], 0), jvar(xx[1], 1), jvar(xx[2], 2)};
+      const Jet6 t1[3] = {jvar(xx[3], 3), jvar(xx[4], 4), jvar(xx[5], 5)};
+      spherical_E_of_params<Jet6>(r1, t1, 0.0, Ej);
+      sphere_plus_jacobian(xx + 3, Pt);
+      for (int a = 0; a < 21; ++a) H[a] = 0.0;
+      for (int a = 0; a < 6; ++a) g[a] = 0.0;
+    } else {
+      double Ed[9];
+      spherical_E_of_params<double>(xx, xx + 3, 0.0, Ed);
+      for (int q = 0; q < 9; ++q) Ej[q].a = Ed[q];
+    }
+    const double f = xx[6];
+    const double S[9] = {1, 1, f, 1, 1, f, f, f, f * f}, dS[9] = {0, 0, 1, 0, 0, 1, 1, 1, 2 * f};
+    double F[9];
+    for (int q = 0; q < 9; ++q) F[q] = Ej[q].a * S[q];
+    for (int k = 0; k < n; ++k) {
+      const double* u = rays + 6 * (size_t)sample[k];
+      const double* v = u + 3;
+      const double Fu0 = F[0] * u[0] + F[1] * u[1] + F[2] * u[2];
+      const double Fu1 = F[3] * u[0] + F[4] * u[1] + F[5] * u[2];
+      const double Fu2 = F[6] * u[0] + F[7] * u[1] + F[8] * u[2];
+      const double Ft0 = F[0] * v[0] + F[3] * v[1] + F[6] * v[2];
+      const double Ft1 = F[1] * v[0] + F[4] * v[1] + F[7] * v[2];
+      const double d = v[0] * Fu0 + v[1] * Fu1 + v[2] * Fu2;
+      const double den = Fu0 * Fu0 + Fu1 * Fu1 + Ft0 * Ft0 + Ft1 * Ft1;
+      const double inv = 1.0 / den;
+      const double r = d * d * inv;
+      c += r * r;
+      if (!with_jac) continue;
+      const double a2 = 2.0 * d * inv, b2 = 2.0 * r * inv;
+      double w[9];
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+          double dd = 0.0;
+          if (i < 2) dd += (i == 0 ? Fu0 : Fu1) * u[j];
+          if (j < 2) dd += (j == 0 ? Ft0 : Ft1) * v[i];
+          w[3 * i + j] = a2 * v[i] * u[j] - b2 * dd;  // d residual / d F_ij
+        }
+      double ga[7];
+      for (int p7 = 0; p7 < 6; ++p7) {
+        double sacc = 0.0;
+        for (int q = 0; q < 9; ++q) sacc += w[q] * Ej[q].v[p7] * S[q];
+        ga[p7] = sacc;
+      }
+      ga[6] = 0.0;
+      for (int q = 0; q < 9; ++q) ga[6] += w[q] * Ej[q].a * dS[q];
+      const double jl[6] = {ga[0], ga[1], ga[2], ga[3] * Pt[0][0] + ga[4] * Pt[1][0] + ga[5] * Pt[2][0],
+                            ga[3] * Pt[0][1] + ga[4] * Pt[1][1] + ga[5] * Pt[2][1], ga[6]};
+      int hk = 0;
+      for (int a = 0; a < 6; ++a) {
+        g[a] += jl[a] * r;
+        for (int b = 0; b <= a; ++b) H[hk++] += jl[a] * jl[b];
+      }
+    }
+    if (with_jac) {
+      gmax = 0.0;
+      for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(g[a]));  // gradient of the unscaled problem
+      if (!have_scale) {
+        for (int a = 0; a < 6; ++a) scale[a] = 1.0 / (1.0 + sqrt(H[a * (a + 1) / 2 + a]));
+        have_scale = true;
+      }
+      int hk = 0;
+      for (int a = 0; a < 6; ++a) {
+        g[a] *= scale[a];
+        for (int b = 0; b <= a; ++b) H[hk++] *= scale[a] * scale[b];
+      }
+    }
+    return 0.5 * c;
+  };
+  SixLmSummary sum;
+  double x_cost = evaluate(x, true);
+  sum.iterations = 0;
+  sum.initial_cost = sum.final_cost = x_cost;
+  if (!isfinite(x_cost)) return sum;
+  double radius = 1e4, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  int invalid = 0, iteration = 0;
+  for (;;) {
+    if (iteration >= 200) break;
+    if (gmax <= 1e-10) break;
+    if (radius < 1e-32) break;
+    ++iteration;
+    if (!reuse_diagonal)
+      for (int a = 0; a < 6; ++a) diagonal[a] = fmin(fmax(H[a * (a + 1) / 2 + a], 1e-6), 1e32);
+    double Hd[21], step[6];
+    for (int a = 0; a < 21; ++a) Hd[a] = H[a];
+    for (int a = 0; a < 6; ++a) Hd[a * (a + 1) / 2 + a] += diagonal[a] / radius;
+    bool valid = cholesky_solve6(Hd, g, step);
+    reuse_diagonal = true;
+    double model_cost_change = 0.0;
+    if (valid) {
+      double sg = 0.0, sHs = 0.0;
+      int hk = 0;
+      for (int a = 0; a < 6; ++a) {
+        step[a] = -step[a];
+        sg += step[a] * g[a];
+      }
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b <= a; ++b) sHs += (a == b ? 1.0 : 2.0) * H[hk++] * step[a] * step[b];
+      model_cost_change = -(sg + 0.5 * sHs);
+      if (!(model_cost_change > 0.0)) valid = false;
+    }
+    if (!valid) {
+      if (++invalid >= 10) break;
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+      continue;
+    }
+    invalid = 0;
+    double delta[6], cand[7];
+    for (int a = 0; a < 6; ++a) delta[a] = step[a] * scale[a];
+    cand[0] = x[0] + delta[0]; cand[1] = x[1] + delta[1]; cand[2] = x[2] + delta[2];
+    sphere_plus(x + 3, delta + 3, cand + 3);
+    cand[6] = x[6] + delta[5];
+    double step_norm = 0.0, x_norm = 0.0;
+    for (int a = 0; a < 7; ++a) {
+      step_norm += (cand[a] - x[a]) * (cand[a] - x[a]);
+      x_norm += x[a] * x[a];
+    }
+    step_norm = sqrt(step_norm);
+    x_norm = sqrt(x_norm);
+    double cand_cost = evaluate(cand, false);
+    if (!isfinite(cand_cost)) cand_cost = kDblMax;
+    if (step_norm <= 1e-8 * (x_norm + 1e-8)) break;
+    const double cost_change = x_cost - cand_cost;
+    if (fabs(cost_change) <= 1e-6 * x_cost) break;
+    const double rho = cost_change / model_cost_change;
+    if (rho > 1e-3) {
+      for (int a = 0; a < 7; ++a) x[a] = cand[a];
+      x_cost = evaluate(x, true);
+      const double tt = 2.0 * rho - 1.0;
+      radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - tt * tt * tt));
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+    } else {
+      radius /= decrease_factor;
+      decrease_factor *= 2.0;
+    }
+  }
+  sum.iterations = iteration;
+  sum.final_cost = x_cost;
+  for (int i = 0; i < 3; ++i) { model.r[i] = x[i]; model.t[i] = x[3 + i]; }
+  model.f = x[6];
+  return sum;
+}
+
 }  // namespace ssfm

@@ -300,4 +300,18 @@ __global__ void k_sixpt_solve_samples(const double* __restrict__ rays, const int
   }
 }
 
+// Hook: SixPointEstimator::LeastSquares, one thread per refit.  models: nprob x 7 (t, r, focal), in place.
+__global__ void k_sixpt_least_squares(const double* __restrict__ rays, const int* __restrict__ idx,
+                                      const int* __restrict__ sample_offsets, int nprob, double* __restrict__ models) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nprob) return;
+  SixPointModel m;
+  double* d = models + 7 * (size_t)p;
+  for (int q = 0; q < 3; ++q) { m.t[q] = d[q]; m.r[q] = d[3 + q]; }
+  m.f = d[6];
+  sixpt_least_squares(rays, idx + sample_offsets[p], sample_offsets[p + 1] - sample_offsets[p], m);
+  for (int q = 0; q < 3; ++q) { d[q] = m.t[q]; d[3 + q] = m.r[q]; }
+  d[6] = m.f;
+}
+
 }  // namespace ssfm

@@ -239,4 +239,17 @@ int hs_sixpt_solve(const double* rays36, double* models /* 15 x 7: t, r, f */, d
   return n;
 }
 
+// SixPointEstimator::LeastSquares on the host (tests only): model = t[3], r[3], f; returns LM iterations
+int hs_sixpt_least_squares(const double* rays, const int* sample, int n, double* model7, double* costs2) {
+  SixPointModel m;
+  for (int d = 0; d < 3; ++d) { m.t[d] = model7[d]; m.r[d] = model7[3 + d]; }
+  m.f = model7[6];
+  const SixLmSummary s = sixpt_least_squares(rays, sample, n, m);
+  for (int d = 0; d < 3; ++d) { model7[d] = m.t[d]; model7[3 + d] = m.r[d]; }
+  model7[6] = m.f;
+  costs2[0] = s.initial_cost;
+  costs2[1] = s.final_cost;
+  return s.iterations;
+}
+
 }  // extern "C"

@@ -61,6 +61,47 @@ def test_product_solver_matches_oracle_on_host(shim):
     assert nsol > 200
 
 
+def _host_ls(shim_lib, rays, sample, model):
+    rays = np.ascontiguousarray(rays, np.float64)
+    sample = np.ascontiguousarray(sample, np.int32)
+    m = np.concatenate([model[0], model[1], [model[2]]]).astype(np.float64)
+    costs = np.zeros(2)
+    dp = C.POINTER(C.c_double)
+    it = shim_lib.hs_sixpt_least_squares(rays.ctypes.data_as(dp), sample.ctypes.data_as(C.POINTER(C.c_int)), len(sample),
+                                         m.ctypes.data_as(dp), costs.ctypes.data_as(dp))
+    return m, it, costs
+
+
+def _refit_cases(n_cases, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n_cases:
+        rays, R, t, f = X.make_problem(rng, 60, rng.uniform(400, 1200), noise_px=0.5)
+        sols = X.minimal_solver(rays[:6])
+        if sols:
+            out.append((rays, R, t, f, min(sols, key=lambda m: np.linalg.norm(X.so3exp(m[1]) - R))))
+    return out
+
+
+def test_least_squares_product_matches_oracle_and_improves_the_model(shim):
+    """SixPointEstimator::LeastSquares: the product's LM (analytic chain rule through E-jets, Householder sphere
+    manifold) against the numpy oracle (dual numbers): same iteration counts, same refined model; and the refit moves
+    a minimal-sample model towards the truth while keeping |t| = 1."""
+    better = 0
+    cases = _refit_cases(12, 5)
+    for rays, R, t, f, m0 in cases:
+        sample = np.arange(6, 48)
+        mo, ito, c0, c1 = X.least_squares(rays, sample, m0)
+        mh, ith, costs = _host_ls(shim.lib, rays, sample, m0)
+        assert ito == ith and abs(costs[1] - c1) <= 1e-9 * max(c1, 1e-30)
+        assert max(np.abs(mo[0] - mh[:3]).max(), np.abs(mo[1] - mh[3:6]).max(), abs(mo[2] - mh[6]) / mo[2]) < 1e-6
+        assert abs(np.linalg.norm(mh[:3]) - 1.0) < 1e-12 and c1 <= c0
+        e0 = np.linalg.norm(X.so3ln(X.so3exp(m0[1]).T @ R))
+        e1 = np.linalg.norm(X.so3ln(X.so3exp(mo[1]).T @ R))
+        better += e1 < e0
+    assert better >= 10
+
+
 def test_oracle_vanilla_msac_recovers_focal_and_rotation():
     """Config C4 shape at reduced size: pixel-unit rays, unknown shared focal, 30 % outliers."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -94,6 +135,16 @@ def test_device_solver_matches_oracle(S, engine):
         assert nm[k] == len(b), k
         for i, mb in enumerate(b):
             assert _model_diff(models[k, i], mb) < 1e-9
+
+
+@pytest.mark.gpu
+def test_device_least_squares_matches_oracle(S, engine):
+    cases = _refit_cases(8, 6)
+    for rays, R, t, f, m0 in cases:
+        sample = np.arange(6, 40)
+        mo, ito, c0, c1 = X.least_squares(rays, sample, m0)
+        md = engine.sixpt_least_squares(rays, [sample], np.concatenate([m0[0], m0[1], [m0[2]]])[None])[0]
+        assert max(np.abs(mo[0] - md[:3]).max(), np.abs(mo[1] - md[3:6]).max(), abs(mo[2] - md[6]) / mo[2]) < 1e-6
 
 
 def _run_c4(S, engine, orc, P, N, outl, focal_scoring, seed):
