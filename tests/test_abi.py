@@ -90,17 +90,30 @@ def test_product_does_not_touch_the_oracle():
         assert not re.search(r"oracle/|liboracle|ssfm_oracle|orc_", inc)
 
 
-def test_cxx_adapter_header_compiles():
-    """include/ssfm_ransaclib.hpp: the RansacLib-concept adapters a reference maintainer would use."""
+def _build_and_run_adapter():
     src = os.path.join(ROOT, "tests", "cxx", "adapter_compile_test.cpp")
     out = os.path.join(ROOT, "tests", "cxx", "adapter_compile_test")
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     subprocess.check_call([cxx, "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-o", out, src,
                            "-L" + os.path.join(ROOT, "spherical-sfm_b200"), "-lssfm_b200",
                            "-Wl,-rpath," + os.path.join(ROOT, "spherical-sfm_b200")])
+    return subprocess.run([out], capture_output=True, text=True)
+
+
+def test_cxx_adapter_header_compiles():
+    """include/ssfm_ransaclib.hpp: the RansacLib-concept adapters a reference maintainer would use."""
     import torch
-    r = subprocess.run([out], capture_output=True, text=True)
+    r = _build_and_run_adapter()
     if torch.cuda.is_available():
         assert r.returncode == 0, r.stdout + r.stderr
     else:  # no device: the adapter must report the engine's error, not compute
         assert r.returncode == 3, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cxx_adapters_on_device():
+    """The reference-shaped call sites (LocallyOptimizedMSAC / VanillaMSAC / MSAC / PreemptiveRANSAC adapters, the
+    estimator concepts, EstimatePairs) through the C ABI on the GPU: tests/cxx/adapter_compile_test.cpp checks the
+    inlier counts, rotations and focal it gets back."""
+    r = _build_and_run_adapter()
+    assert r.returncode == 0, r.stdout + r.stderr
