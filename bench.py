@@ -150,7 +150,14 @@ def cpu_leg(pairs_rays, N, seconds_target, threads=0):
     res, secs = impl.estimate_batch(pairs_rays[:n * N], offs, opt, 0, cores)
     evals = sum(int(r.num_iterations) * 4 * N for r in res)
     total_evals = sum(int(r.evals) for r in res)
+    # the same path on ONE host thread, ~3 s
+    n1 = int(max(4, min(n, rate / max(cores, 1) * 3.0)))
+    offs1 = np.arange(n1 + 1, dtype=np.int64) * N
+    res1, secs1 = impl.estimate_batch(pairs_rays[:n1 * N], offs1, opt, 0, 1)
+    evals1 = sum(int(r.num_iterations) * 4 * N for r in res1)
+    single = {"value": evals1 / secs1, "pairs_per_s": n1 / secs1, "pairs": n1, "seconds": secs1}
     return {
+        "one_thread": single,
         "value": evals / secs, "unit": "evals/s", "cores": cores, "kind": "port",
         "sample": "%d C3 pairs (%d corr, 70%% outliers, LO-MSAC pipeline options) in %.1f s; float64 C++ restatement of the "
                   "spherical estimator%s; all EvaluateModelOnPoint calls incl. LO: %.3e/s; %.1f pairs/s" % (
