@@ -451,8 +451,11 @@ struct ChainArgs {
   unsigned long long* counters;
 };
 
+#ifndef SSFM_CHAIN_MINBLOCKS
+#define SSFM_CHAIN_MINBLOCKS 8  // 64 registers: this kernel is latency bound, occupancy pays (chain stage 124 -> 117 ms)
+#endif
 template <bool DEFER>
-__global__ void __launch_bounds__(kChainWarps * 32, DEFER ? 6 : 4) k_chain(Params P, ChainArgs A) {
+__global__ void __launch_bounds__(kChainWarps * 32, DEFER ? SSFM_CHAIN_MINBLOCKS : 4) k_chain(Params P, ChainArgs A) {
   const int w = blockIdx.x * kChainWarps + (threadIdx.x >> 5);
   if (w >= A.nlist) return;
   WarpCtx cx{(int)(threadIdx.x & 31)};
@@ -576,8 +579,11 @@ __global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params
   }
 }
 
+#ifndef SSFM_REFITBIG_MINBLOCKS
+#define SSFM_REFITBIG_MINBLOCKS 1
+#endif
 // Stragglers handed over by k_refit_small: persistent warps pull them from the list.
-__global__ void __launch_bounds__(128) k_refit_long(Params P, const double* __restrict__ rays,
+__global__ void __launch_bounds__(128, SSFM_REFITBIG_MINBLOCKS) k_refit_long(Params P, const double* __restrict__ rays,
                                                     const long long* __restrict__ offsets, int pair0,
                                                     const int* __restrict__ long_list, const int* __restrict__ long_count,
                                                     int* queue_head, const PairState* __restrict__ states,
@@ -609,7 +615,7 @@ __global__ void __launch_bounds__(128) k_refit_long(Params P, const double* __re
 // big: one WARP per refit (the final least squares over all inliers).
 // Also used for the SMALL refits of a wave that has too few of them to fill the machine with one
 // thread each (from_front = 1): a warp per refit has ~3x lower latency, and those waves are pure tail.
-__global__ void __launch_bounds__(128) k_refit_big(Params P, const double* __restrict__ rays,
+__global__ void __launch_bounds__(128, SSFM_REFITBIG_MINBLOCKS) k_refit_big(Params P, const double* __restrict__ rays,
                                                    const long long* __restrict__ offsets, int pair0,
                                                    const int* __restrict__ parked, int cap, int ntasks, int from_front,
                                                    const PairState* __restrict__ states, const int* __restrict__ list_a,
