@@ -680,7 +680,10 @@ __global__ void k_tri_cameras(const double* __restrict__ cam_tr, int nc, tri::Ca
 // list == nullptr: the points order[point0 .. point0+npoints) (first phase); otherwise the compacted list of points
 // left unfinished by the previous phase.  A point that reaches `stop_at` iterations without finishing is appended
 // to next_list, its loop state saved, and continued by the next launch among points of similar length.
-__global__ void __launch_bounds__(64) k_retriangulate(Params P, const tri::Cam* __restrict__ cams,
+#ifndef SSFM_TRI_MINBLOCKS
+#define SSFM_TRI_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, SSFM_TRI_MINBLOCKS) k_retriangulate(Params P, const tri::Cam* __restrict__ cams,
                                                       const long long* __restrict__ offsets, const int* __restrict__ obs_cam,
                                                       const double* __restrict__ obs_xy, double focal, int point0, int npoints,
                                                       const int* __restrict__ order, const int* __restrict__ list,
