@@ -17,7 +17,7 @@ for r in rows[start + 1:]:
     a = agg.setdefault(name, [0, 0.0])
     a[0] += 1
     a[1] += v
-own = {k: v for k, v in agg.items() if k.startswith("ssfm::") and "k_fma_peak" not in k}
+own = {k: v for k, v in agg.items() if (k.startswith("ssfm::") or k.startswith("k_")) and "k_fma_peak" not in k}
 tot = sum(v[1] for v in own.values())
 with open(out, "w") as f:
     f.write("# %s\n\n" % title)
