@@ -13,6 +13,7 @@
 //     (preemptive_ransac.h:46-139)                            + ssfm_b200::GpuSphericalFastEstimator           same signatures)
 //   sphericalsfmtools::SixPointEstimator / SixPointSolution    ssfm_b200::GpuSixPointEstimator / SixPointSolution
 //     (examples/six_point_estimator.h:9-37)                      (VanillaMSAC<SixPointSolution, ..., GpuSixPointEstimator>)
+//   SfM::Retriangulate (src/sfm.cpp:156-192)                  ssfm_b200::Retriangulate (ONE call for all points)
 //   the `#pragma omp parallel for` over pairs                  ssfm_b200::EstimatePairs (ONE call for all pairs)
 //     (examples/spherical_sfm_tools.cpp:332-420)
 //
@@ -505,6 +506,52 @@ inline void EstimatePairs(const Engine& eng, const Options& options, const std::
   results->resize(pair_lists.size());
   if (inlier_flags) inlier_flags->assign((size_t)offsets.back(), 0);
   check(ssfm_estimate_pairs(eng.get(), &b, &o, results->data(), inlier_flags ? inlier_flags->data() : nullptr));
+}
+
+// SfM::Retriangulate (src/sfm.cpp:156-192) for all points in one call.  camera_tr[i] = {t, r} of GetPose(i);
+// tracks[j] = the observations of point j as (camera index, x, y) with the principal point removed; `focal` =
+// intrinsics.focal.  points[j] is zero unless status[j] == SSFM_PAIR_OK, exactly like SetPoint(j, Zero) followed by
+// the conditional SetPoint(j, X).
+struct TrackObservation {
+  int camera;
+  double x, y;
+};
+struct Point3d {
+  double x = 0, y = 0, z = 0;
+};
+inline void Retriangulate(const Engine& eng, const std::vector<double>& camera_tr /* 6 per camera */,
+                          const std::vector<std::vector<TrackObservation>>& tracks, double focal, std::vector<Point3d>* points,
+                          std::vector<int32_t>* num_inliers = nullptr, std::vector<int32_t>* status = nullptr) {
+  std::vector<int64_t> offs(tracks.size() + 1, 0);
+  for (size_t j = 0; j < tracks.size(); ++j) offs[j + 1] = offs[j] + (int64_t)tracks[j].size();
+  std::vector<int32_t> cam((size_t)offs.back());
+  std::vector<double> xy((size_t)offs.back() * 2);
+  for (size_t j = 0; j < tracks.size(); ++j)
+    for (size_t k = 0; k < tracks[j].size(); ++k) {
+      const size_t o = (size_t)offs[j] + k;
+      cam[o] = tracks[j][k].camera;
+      xy[2 * o] = tracks[j][k].x;
+      xy[2 * o + 1] = tracks[j][k].y;
+    }
+  SsfmTrackBatch tb;
+  tb.num_cameras = (int32_t)(camera_tr.size() / 6);
+  tb.camera_tr = camera_tr.data();
+  tb.num_points = (int32_t)tracks.size();
+  tb.obs_offsets = offs.data();
+  tb.obs_camera = cam.data();
+  tb.obs_xy = xy.data();
+  tb.focal = focal;
+  SsfmOptions o;
+  ssfm_default_options(&o);
+  o.squared_inlier_threshold = 4.0;  // src/sfm.cpp:177
+  o.final_least_squares = 1;         // :178
+  std::vector<double> pts(tracks.size() * 3 + 3);
+  std::vector<int32_t> ninl(tracks.size() + 1), st(tracks.size() + 1);
+  check(ssfm_retriangulate(eng.get(), &tb, &o, pts.data(), ninl.data(), st.data(), nullptr));
+  points->resize(tracks.size());
+  for (size_t j = 0; j < tracks.size(); ++j) { (*points)[j].x = pts[3 * j]; (*points)[j].y = pts[3 * j + 1]; (*points)[j].z = pts[3 * j + 2]; }
+  if (num_inliers) num_inliers->assign(ninl.begin(), ninl.begin() + tracks.size());
+  if (status) status->assign(st.begin(), st.begin() + tracks.size());
 }
 
 }  // namespace ssfm_b200

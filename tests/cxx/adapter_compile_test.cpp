@@ -101,6 +101,24 @@ int main() {
     SixPointSolution refit = sol6;
     refit.focal *= 1.05;  // perturb, then LeastSquares must bring it back
     six.LeastSquares(stats6.inlier_indices, &refit);
+    // SfM::Retriangulate: eight cameras translated along x (identity rotations), two points, one gross outlier each
+    std::vector<double> cam_tr;
+    for (int c = 0; c < 8; ++c) { const double tr[6] = {-0.2 * c, 0, 0, 0, 0, 0}; cam_tr.insert(cam_tr.end(), tr, tr + 6); }
+    const double Xs[2][3] = {{0.3, -0.2, 5.0}, {-0.5, 0.4, 7.0}};
+    std::vector<std::vector<TrackObservation>> tracks(2);
+    for (int j = 0; j < 2; ++j)
+      for (int c = 0; c < 8; ++c) {
+        const double px = Xs[j][0] - 0.2 * c, py = Xs[j][1], pz = Xs[j][2];
+        TrackObservation ob{c, 600.0 * px / pz, 600.0 * py / pz};
+        if (c == 3) ob.x += 80.0;
+        tracks[j].push_back(ob);
+      }
+    std::vector<Point3d> pts3;
+    std::vector<int32_t> tri_inl, tri_status;
+    Retriangulate(eng, cam_tr, tracks, 600.0, &pts3, &tri_inl, &tri_status);
+    const bool tri_ok = tri_status[0] == SSFM_PAIR_OK && tri_status[1] == SSFM_PAIR_OK && tri_inl[0] == 7 && tri_inl[1] == 7 &&
+                        std::fabs(pts3[0].z - 5.0) < 1e-6 && std::fabs(pts3[1].x + 0.5) < 1e-6;
+    std::printf("retriangulate: inliers %d %d point0 (%.6f %.6f %.6f)\n", tri_inl[0], tri_inl[1], pts3[0].x, pts3[0].y, pts3[0].z);
     std::printf("six-point: inliers %d focal %.6f minimal models %d refit focal %.6f\n", n_six, sol6.focal, nm6, refit.focal);
     std::printf("inliers %d recount %d models %d R02 %.6f (want %.6f) batched %d %d legacy msac %d (iter %d) preemptive %d ry %.6f\n",
                 ninliers, recount, nm, Rm(0, 2), s, res[0].best_num_inliers, res[1].best_num_inliers, n_msac, msac.iter, n_pre,
@@ -108,7 +126,7 @@ int main() {
     const bool ok = ninliers == 160 && recount == ninliers && nm == 4 && std::fabs(Rm(0, 2) - s) < 1e-6 &&
                     res[0].best_num_inliers == 160 && n_msac == 160 && best != nullptr && n_pre == 160 && best2 != nullptr &&
                     std::fabs(rr[1] - a) < 1e-6 && (int)inl.size() == 200 && n_six == 160 &&
-                    std::fabs(sol6.focal - 1.0) < 1e-6 && nm6 >= 1 && std::fabs(refit.focal - 1.0) < 5e-3;  // the refit stops at Ceres' function tolerance
+                    std::fabs(sol6.focal - 1.0) < 1e-6 && nm6 >= 1 && std::fabs(refit.focal - 1.0) < 5e-3 && tri_ok;  // the refit stops at Ceres' function tolerance
     return ok ? 0 : 1;
   } catch (const Error& e) {
     std::printf("engine error %d: %s\n", e.code(), e.what());
