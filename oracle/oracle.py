@@ -207,6 +207,16 @@ def build(ref=True, force=False):
             if force or not os.path.exists(out2) or os.path.getmtime(out2) < dep:
                 subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + inc +
                                       ["-o", out2, os.path.join(_DIR, main)] + extra + refsrc)
+        # the reference's orphan SphericalFastEstimator (src/spherical_fast_estimator.cpp) with the fast_shim stand-ins
+        out4 = os.path.join(_DIR, "_ref", "libssfm_reffast.so")
+        fast_dep = [os.path.join(_DIR, "ref_fast.cpp"), os.path.join(_DIR, "fast_shim", "sphericalsfm", "estimator.h"),
+                    os.path.join(_DIR, "fast_shim", "Polynomial", "Polynomial.hpp")]
+        dep4 = max([newest] + [os.path.getmtime(x) for x in fast_dep + shim])
+        if force or not os.path.exists(out4) or os.path.getmtime(out4) < dep4:
+            subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + _DIR,
+                                   "-I" + os.path.join(_DIR, "fast_shim"), "-I" + os.path.join(_DIR, "eigen_shim"),
+                                   "-I" + os.path.join(refroot, "include"), "-o", out4, os.path.join(_DIR, "ref_fast.cpp"),
+                                   os.path.join(refroot, "src", "spherical_fast_estimator.cpp"), os.path.join(refroot, "src", "so3.cpp")])
         # the reference's triangulation path (src/triangulation_estimator.cpp, sfm_types.cpp, so3.cpp + RansacLib)
         out3 = os.path.join(_DIR, "_ref", "libssfm_reftri.so")
         dep = max([newest, os.path.getmtime(os.path.join(_DIR, "ref_tri.cpp"))] + [os.path.getmtime(x) for x in shim])
@@ -234,6 +244,39 @@ class TriReference:
         self.lib.orc_triangulate.restype = C.c_int
 
     triangulate = Oracle.triangulate
+
+
+class FastReference:
+    """oracle/_ref/libssfm_reffast.so: the reference's SphericalFastEstimator::compute / score / decomposeE."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+        self.lib.orc_fast_compute.restype = C.c_int
+
+    def compute(self, rays3):
+        r = np.ascontiguousarray(rays3, np.float64).reshape(-1)
+        E = np.zeros(36)
+        n = self.lib.orc_fast_compute(_dp(r), _dp(E))
+        return [E[9 * i:9 * i + 9].reshape(3, 3).copy() for i in range(n)]
+
+    def score(self, E, rays):
+        rays = np.ascontiguousarray(rays, np.float64)
+        out = np.zeros(len(rays))
+        self.lib.orc_fast_score(_dp(np.ascontiguousarray(E, np.float64).reshape(-1)), _dp(rays.reshape(-1)), len(rays), _dp(out))
+        return out
+
+    def decompose(self, E, inward=False):
+        r, t = np.zeros(3), np.zeros(3)
+        self.lib.orc_fast_decompose(_dp(np.ascontiguousarray(E, np.float64).reshape(-1)), int(inward), _dp(r), _dp(t))
+        return r, t
+
+
+def load_ref_fast():
+    if "s" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_reffast.so")
+        _cache["s"] = FastReference(p) if os.path.exists(p) else None
+    return _cache["s"]
 
 
 def load_ref_tri():

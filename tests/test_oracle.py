@@ -211,6 +211,37 @@ def test_selection_sample_properties(S, orc):
     assert (orc.knuth_sample(1, 1, 0, 4, 4) == np.arange(4)).all()
 
 
+def test_restated_sturm_solver_matches_reference_fast_estimator_source(S, O, orc):
+    """The FAST_STURM solver of the oracle (config C2's solver) against the reference's own orphan
+    src/spherical_fast_estimator.cpp, compiled unmodified with stand-ins for the old Estimator base and
+    Polynomial<4>::realRootsSturm (oracle/_ref/libssfm_reffast.so): same number of solutions, same matrices (up to
+    sign) to 1e-8; score() and decomposeE() identical to the oracle's Sampson error and decomposition."""
+    rf = O.load_ref_fast()
+    if rf is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    total = 0
+    for k in range(200):
+        pr = S.problems.make_problem(S.problems.make_rng(21, k), 30, k % 2 == 1, None, (1 / 600 if k % 3 else 0.0), 0,
+                                     20.0 if k % 4 else 180.0)
+        smp = np.array([1, 7, 13], np.int32)
+        nm, models = orc.solve(pr.rays, smp, 2)
+        Er = rf.compute(pr.rays[smp])
+        assert len(Er) == nm, k
+        total += nm
+        for i in range(nm):
+            Eo = E_of(models[i])
+            Eo = Eo / np.linalg.norm(Eo)
+            assert min(min(np.abs(Eo - e).max(), np.abs(Eo + e).max()) for e in Er) < 1e-8
+    assert total > 300
+    pr = S.problems.make_problem(S.problems.make_rng(22, 0), 50, False, None, 1 / 600, 10, 20.0)
+    E = pr.E / np.linalg.norm(pr.E)
+    assert np.abs(rf.score(E, pr.rays) - orc.sampson(E, pr.rays)).max() == 0.0
+    for inward in (False, True):
+        r1, t1 = rf.decompose(E, inward)
+        r2, t2 = orc.decompose(E, inward)
+        assert np.abs(r1 - r2).max() < 1e-12 and np.abs(t1 - t2).max() < 1e-12
+
+
 def test_oracle_recovers_pose_with_outliers(S, O, orc):
     """Config C1: 1000 correspondences, 50 % outliers, calibrated solver, pipeline options."""
     opt = O.pipeline_options(THR2)
