@@ -248,14 +248,14 @@ int vanilla_msac(const Options& opt, const Solver& solver, typename Solver::Mode
 // Legacy fixed-budget MSAC (include/sphericalsfm/msac.h:67-131): hypothesis budget M
 // (= estimators.size()), inlier test '<=' (:60), cost = sum(score if inlier else thr^2),
 // adaptive stop num_iter = log(1-p)/log(1-(1-outlier_ratio)^m) capped at M (:119-126).
-// The reference samples with rand()-driven Knuth 3.4.2S (:6-27); here the sampler is Philox.
-template <class Solver, class Sampler>
-int legacy_msac(const Options& opt, int budget, double prob_success, const Solver& solver,
+// The reference samples with random_sample (:6-27, Knuth 3.4.2S on rand()); `sample_fn(iteration, N, k, idx)` supplies
+// it (knuth_sample on the Philox-backed rand()).
+template <class Solver, class SampleFn>
+int legacy_msac(const Options& opt, int budget, double prob_success, const Solver& solver, SampleFn sample_fn,
                 typename Solver::Model* best_model, Statistics* st) {
   *st = Statistics();
   const int k = solver.min_sample_size(), n = solver.num_data();
   if (k > n || k <= 0) return 0;
-  Sampler sampler(opt.random_seed, solver);
   const double thr = opt.squared_inlier_threshold;
   double num_iter = budget;
   double best_score = INFINITY;
@@ -264,7 +264,7 @@ int legacy_msac(const Options& opt, int budget, double prob_success, const Solve
   typename Solver::ModelVector models;
   int iter = 0;
   while (iter < num_iter && iter < budget) {
-    sampler.Sample(&sample);
+    sample_fn((uint32_t)iter, n, k, sample.data());
     const int nm = solver.MinimalSolver(sample, &models);
     for (int m = 0; m < nm; ++m) {
       double score = 0.0;

@@ -217,6 +217,15 @@ def build(ref=True, force=False):
                                    "-I" + os.path.join(_DIR, "fast_shim"), "-I" + os.path.join(_DIR, "eigen_shim"),
                                    "-I" + os.path.join(refroot, "include"), "-o", out4, os.path.join(_DIR, "ref_fast.cpp"),
                                    os.path.join(refroot, "src", "spherical_fast_estimator.cpp"), os.path.join(refroot, "src", "so3.cpp")])
+        # config C2 as upstream wrote it: msac.h / preemptive_ransac.h around SphericalFastEstimator
+        out5 = os.path.join(_DIR, "_ref", "libssfm_reflegacy.so")
+        leg = [os.path.join(_DIR, f) for f in ("ref_legacy_msac.cpp", "ref_legacy_preemptive.cpp", "ref_legacy_common.hpp", "pinned_rand.hpp")]
+        dep5 = max([newest] + [os.path.getmtime(x) for x in leg + fast_dep + shim])
+        if force or not os.path.exists(out5) or os.path.getmtime(out5) < dep5:
+            subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + _DIR,
+                                   "-I" + os.path.join(_DIR, "fast_shim"), "-I" + os.path.join(_DIR, "eigen_shim"),
+                                   "-I" + os.path.join(refroot, "include"), "-o", out5, leg[0], leg[1],
+                                   os.path.join(refroot, "src", "spherical_fast_estimator.cpp"), os.path.join(refroot, "src", "so3.cpp")])
         # the reference's triangulation path (src/triangulation_estimator.cpp, sfm_types.cpp, so3.cpp + RansacLib)
         out3 = os.path.join(_DIR, "_ref", "libssfm_reftri.so")
         dep = max([newest, os.path.getmtime(os.path.join(_DIR, "ref_tri.cpp"))] + [os.path.getmtime(x) for x in shim])
@@ -269,6 +278,30 @@ class FastReference:
         r, t = np.zeros(3), np.zeros(3)
         self.lib.orc_fast_decompose(_dp(np.ascontiguousarray(E, np.float64).reshape(-1)), int(inward), _dp(r), _dp(t))
         return r, t
+
+
+class LegacyReference:
+    """oracle/_ref/libssfm_reflegacy.so: the reference's MSAC / PreemptiveRANSAC drivers around its SphericalFastEstimator."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+
+    def estimate_pair(self, rays, opt, pair_id=0):
+        rays = np.ascontiguousarray(rays, np.float64)
+        res = OrcResult()
+        inl = np.zeros(max(len(rays), 1), np.int32)
+        fn = self.lib.orc_legacy_msac if opt.driver == 2 else self.lib.orc_legacy_preemptive
+        fn.restype = C.c_int
+        n = fn(_dp(rays), len(rays), C.byref(opt), C.c_uint32(pair_id), C.byref(res), _ip(inl))
+        return res, inl[:max(n, 0)].copy()
+
+
+def load_ref_legacy():
+    if "l" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_reflegacy.so")
+        _cache["l"] = LegacyReference(p) if os.path.exists(p) else None
+    return _cache["l"]
 
 
 def load_ref_fast():

@@ -189,7 +189,8 @@ int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_
       est.evals_ += evals;
     }
   } else {
-    legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
+    legacy_msac(opt, o.legacy_budget, o.legacy_prob_success, est,
+                [&](uint32_t it, int N, int k, int* idx) { knuth_sample(o.random_seed, pair_id, it, N, k, idx); }, &E, &st);
   }
 #else
   if (o.driver == 0)
@@ -200,7 +201,8 @@ int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_
     preemptive_ransac(opt, o.legacy_budget, o.preemptive_block, est,
                       [&](uint32_t hyp, int N, int k, int* idx) { knuth_sample(o.random_seed, pair_id, hyp, N, k, idx); }, &E, &st);
   else
-    legacy_msac<SphericalEstimator, Sampler>(opt, o.legacy_budget, o.legacy_prob_success, est, &E, &st);
+    legacy_msac(opt, o.legacy_budget, o.legacy_prob_success, est,
+                [&](uint32_t it, int N, int k, int* idx) { knuth_sample(o.random_seed, pair_id, it, N, k, idx); }, &E, &st);
 #endif
   std::memcpy(out->E, E.m, sizeof(E.m));
   out->num_iterations = st.num_iterations;

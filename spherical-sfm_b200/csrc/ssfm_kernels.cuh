@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Param
   const int n = (int)(offsets[pair + 1] - off);
   const uint32_t it = states[a].it + (uint32_t)j;
   int idx[3];
-  philox_sample<3>(P.seed, P.first_pair_id + (uint32_t)pair, it, 3, n, idx);
+  if (P.driver == 2)  // msac.h:83 draws with random_sample (selection sampling on rand()), the RansacLib drivers with DrawSample
+    knuth_sample(P.seed, P.first_pair_id + (uint32_t)pair, it, n, 3, idx);
+  else
+    philox_sample<3>(P.seed, P.first_pair_id + (uint32_t)pair, it, 3, n, idx);
   double c[3][6];
 #pragma unroll
   for (int s = 0; s < 3; ++s) {

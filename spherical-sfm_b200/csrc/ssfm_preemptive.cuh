@@ -15,39 +15,6 @@
 
 namespace ssfm {
 
-// rand() of the legacy drivers as a pure function of (seed, pair, hypothesis, draw): word (draw % 4) of
-// Philox(counter = (hyp, draw / 4, 1, 0), key = (seed, pair)) >> 1, RAND_MAX folded onto RAND_MAX - 1 so that
-// u = rand() / RAND_MAX < 1 (with u == 1 upstream's selection sampling can run past the end of the list).
-struct PhiloxRand31 {
-  uint32_t seed, pair, hyp, draw;
-  uint32_t w[4];
-  SSFM_HD int next() {
-    if ((draw & 3u) == 0u) philox4x32_10(hyp, draw >> 2, 1u, 0u, seed, pair, w);
-    const uint32_t k = draw & 3u;
-    uint32_t r = (k == 0 ? w[0] : (k == 1 ? w[1] : (k == 2 ? w[2] : w[3]))) >> 1;
-    ++draw;
-    if (r == 0x7fffffffu) r = 0x7ffffffeu;
-    return (int)r;
-  }
-};
-
-// random_sample (preemptive_ransac.h:8-28): n of N records, in increasing order.
-SSFM_HD void knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* out) {
-  PhiloxRand31 g;
-  g.seed = seed; g.pair = pair; g.hyp = hyp; g.draw = 0;
-  int t = 0, m = 0;
-  while (m < n) {
-    const double u = (double)g.next() / 2147483647.0;
-    if ((double)(N - t) * u >= (double)(n - m)) {
-      t++;
-    } else {
-      out[m] = t;
-      t++;
-      m++;
-    }
-  }
-}
-
 // hyps layout: [pair-in-pass][6][M] (SoA over the hypothesis so stores coalesce); p[0] = NaN marks a
 // hypothesis without a model.  has[pair][M]: 0 = the solver returned no solution (:72).
 template <int KIND>

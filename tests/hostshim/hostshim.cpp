@@ -153,7 +153,8 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
     s32m.assign((size_t)na * 4, 0.f);
     for (int j = 0; j < na; ++j) {
       int idx[3];
-      philox_sample<3>(P.seed, pair_id, st.it + j, 3, n, idx);
+      if (P.driver == 2) knuth_sample(P.seed, pair_id, st.it + j, n, 3, idx);
+      else philox_sample<3>(P.seed, pair_id, st.it + j, 3, n, idx);
       double m[4][6];
       const double* c0 = rays + 6 * (size_t)idx[0];
       const double* c1 = rays + 6 * (size_t)idx[1];

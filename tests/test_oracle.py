@@ -242,6 +242,30 @@ def test_restated_sturm_solver_matches_reference_fast_estimator_source(S, O, orc
         assert np.abs(r1 - r2).max() < 1e-12 and np.abs(t1 - t2).max() < 1e-12
 
 
+@pytest.mark.parametrize("driver", [2, 3])
+def test_restated_legacy_path_matches_reference_sources_end_to_end(S, O, orc, driver):
+    """Config C2 as upstream wrote it -- include/sphericalsfm/msac.h (driver 2) / preemptive_ransac.h (driver 3) around
+    src/spherical_fast_estimator.cpp, all compiled unmodified (oracle/_ref/libssfm_reflegacy.so; rand() redirected to
+    the Philox-backed stream) -- against the restated drivers + restated Sturm solver: same status, iteration counts
+    and inlier sets; the winning matrix to 1e-7 (up to sign)."""
+    rl = O.load_ref_legacy()
+    if rl is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    for p in range(18):
+        n = [2000, 300, 60][p % 3]
+        pr = S.problems.make_problem(S.problems.make_rng(31, p), n, False, 1.0, 1 / 600, int(0.3 * n), 20.0)
+        opt = O.default_options(squared_inlier_threshold=THR2, driver=driver, solver_kind=2, legacy_budget=[512, 200][p % 2],
+                                preemptive_block=[10, 5][p % 2], random_seed=3)
+        a, ia = orc.estimate_pair(pr.rays, opt, p)
+        b, ib = rl.estimate_pair(pr.rays, opt, p)
+        assert (a.status, a.num_iterations, a.best_num_inliers) == (b.status, b.num_iterations, b.best_num_inliers), p
+        assert (ia == ib).all()
+        if a.status == 0:
+            Ea, Eb = np.array(a.E) / np.linalg.norm(a.E), np.array(b.E) / np.linalg.norm(b.E)
+            assert min(np.abs(Ea - Eb).max(), np.abs(Ea + Eb).max()) < 1e-7
+            assert abs(a.best_model_score - b.best_model_score) <= 1e-6 * b.best_model_score  # models differ by ~1e-9
+
+
 def test_oracle_recovers_pose_with_outliers(S, O, orc):
     """Config C1: 1000 correspondences, 50 % outliers, calibrated solver, pipeline options."""
     opt = O.pipeline_options(THR2)
