@@ -162,19 +162,25 @@ def test_polynomial_solver_and_inward(S, O, engine, orc):
 
 
 def test_config_c2_fast_solver_legacy_msac(S, O, engine, orc):
-    """Config C2: Sturm-variant solver under the legacy fixed-budget MSAC driver (msac.h), 2000 corr."""
+    """Config C2: Sturm-variant solver under the legacy fixed-budget MSAC driver (msac.h), 2000 corr -- against the
+    restated oracle and, where oracle/_ref travelled with the snapshot, against the reference's own msac.h +
+    spherical_fast_estimator.cpp (libssfm_reflegacy.so)."""
     opt = S.default_options(squared_inlier_threshold=THR2, driver=S.DRIVER_MSAC_FIXED, solver=S.SOLVER_FAST_STURM,
                             fixed_budget=512)
     rays, offsets, probs = S.problems.make_batch(10, 32, 2000, noise=1 / 600, outlier_frac=0.3, rotation_deg=1.0)
     res, flags = engine.estimate_pairs(rays, offsets, opt)
     oopt = to_oracle_options(O, opt)
-    for p in range(32):
-        ref, inl = orc.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
-        assert int(res["num_iterations"][p]) == ref.num_iterations
-        assert int(res["best_num_inliers"][p]) == ref.best_num_inliers
-        fl = np.zeros(2000, np.uint8)
-        fl[inl] = 1
-        assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
+    impls = [orc] + ([O.load_ref_legacy()] if O.load_ref_legacy() is not None else [])
+    for impl in impls:
+        for p in range(32):
+            ref, inl = impl.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
+            assert int(res["num_iterations"][p]) == ref.num_iterations
+            assert int(res["best_num_inliers"][p]) == ref.best_num_inliers
+            fl = np.zeros(2000, np.uint8)
+            fl[inl] = 1
+            assert (flags[offsets[p]:offsets[p + 1]] == fl).all()
+            d = S.problems.rot_error(S.problems.so3exp(np.array(ref.r)), S.problems.so3exp(res["r"][p]))
+            assert np.rad2deg(d) < 0.01
 
 
 @pytest.mark.parametrize("solver,M,B,N,outl", [(2, 512, 10, 2000, 0.3), (0, 500, 7, 700, 0.5), (1, 64, 3, 300, 0.4),
@@ -190,6 +196,8 @@ def test_preemptive_ransac_driver(S, O, engine, orc, ref, solver, M, B, N, outl)
     res, flags = engine.estimate_pairs(rays, offsets, opt)
     oopt = to_oracle_options(O, opt)
     impl = ref if ref is not None else orc
+    if solver == 2 and O.load_ref_legacy() is not None:  # the reference's own preemptive_ransac.h + spherical_fast_estimator.cpp
+        impl = O.load_ref_legacy()
     good = 0
     for p in range(P):
         a, inl = impl.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, opt.first_pair_id + p)
