@@ -304,6 +304,39 @@ def test_golden_vectors(S, O, engine):
             assert np.rad2deg(d) < 0.01
 
 
+def test_golden_vectors_from_reference_sources(S, O, engine):
+    """tests/golden/refsrc_golden.npz: outputs of the reference's OWN sources (msac.h / preemptive_ransac.h +
+    spherical_fast_estimator.cpp; triangulation_estimator.cpp + RansacLib; spherical_estimator.cpp +
+    spherical_solvers.cpp + RansacLib) generated where /root/reference exists -- checked here against the device."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refsrc_golden.npz"))
+    for k in range(int(g["num_legacy"])):
+        drv, M, B, pid, seed = [int(x) for x in g["lg_cfg_%d" % k]]
+        opt = S.default_options(squared_inlier_threshold=THR2, driver=drv, solver=S.SOLVER_FAST_STURM, fixed_budget=M,
+                                preemptive_block=B, random_seed=seed, first_pair_id=pid)
+        rays = g["lg_rays_%d" % k]
+        res, flags = engine.estimate_pairs(rays, np.array([0, len(rays)], np.int64), opt)
+        assert int(res["num_iterations"][0]) == int(g["lg_iters_%d" % k])
+        assert int(res["best_num_inliers"][0]) == int(g["lg_ninl_%d" % k])
+        assert (np.nonzero(flags)[0] == g["lg_inliers_%d" % k]).all()
+        Eg = g["lg_E_%d" % k]
+        assert model_dist(res["E"][0] / np.linalg.norm(res["E"][0]), Eg / np.linalg.norm(Eg)) < 1e-7
+        d = S.problems.rot_error(S.problems.so3exp(g["lg_r_%d" % k]), S.problems.so3exp(res["r"][0]))
+        assert np.rad2deg(d) < 0.01
+    opt = S.default_options(squared_inlier_threshold=4.0, final_least_squares=1)
+    pts, ninl, status, iters = engine.retriangulate(g["tri_cam"], g["tri_offs"], g["tri_oc"], g["tri_oxy"], float(g["tri_focal"]), opt)
+    assert (status == g["tri_status"]).all() and (ninl == g["tri_ninl"]).all() and (iters == g["tri_iters"]).all()
+    assert np.abs(pts - g["tri_points"]).max() <= 1e-6 * max(1.0, np.abs(g["tri_points"]).max())
+    for k in range(int(g["num_full"])):
+        opt = S.pipeline_options(THR2, first_pair_id=int(g["fu_pid_%d" % k]))
+        rays = g["fu_rays_%d" % k]
+        res, flags = engine.estimate_pairs(rays, np.array([0, len(rays)], np.int64), opt)
+        assert (int(res["num_iterations"][0]), int(res["best_num_inliers"][0]), int(res["number_lo_iterations"][0])) == (
+            int(g["fu_iters_%d" % k]), int(g["fu_ninl_%d" % k]), int(g["fu_nlo_%d" % k]))
+        assert (np.nonzero(flags)[0] == g["fu_inliers_%d" % k]).all()
+        d = S.problems.rot_error(S.problems.so3exp(g["fu_r_%d" % k]), S.problems.so3exp(res["r"][0]))
+        assert np.rad2deg(d) < 0.01
+
+
 def test_determinism_and_pair_id_offset(S, engine):
     """Same inputs -> identical bits; a sub-batch with first_pair_id reproduces the full batch's rows."""
     rays, offsets, _ = S.problems.make_batch(21, 12, 800, noise=1 / 600, outlier_frac=0.6)

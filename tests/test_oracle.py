@@ -266,6 +266,36 @@ def test_restated_legacy_path_matches_reference_sources_end_to_end(S, O, orc, dr
             assert abs(a.best_model_score - b.best_model_score) <= 1e-6 * b.best_model_score  # models differ by ~1e-9
 
 
+def test_golden_vectors_from_reference_sources(S, O, orc):
+    """tests/golden/refsrc_golden.npz (made by make_golden_refsrc.py from the reference's own sources compiled into
+    oracle/_ref) against the restated oracle: legacy drivers + Sturm solver (config C2), Retriangulate, and the
+    3-point pipeline path (estimator + solvers + RansacLib)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refsrc_golden.npz"))
+    for k in range(int(g["num_legacy"])):
+        drv, M, B, pid, seed = [int(x) for x in g["lg_cfg_%d" % k]]
+        opt = O.default_options(squared_inlier_threshold=THR2, driver=drv, solver_kind=2, legacy_budget=M, preemptive_block=B,
+                                random_seed=seed)
+        res, inl = orc.estimate_pair(g["lg_rays_%d" % k], opt, pid)
+        assert res.num_iterations == int(g["lg_iters_%d" % k]) and res.best_num_inliers == int(g["lg_ninl_%d" % k])
+        assert (inl == g["lg_inliers_%d" % k]).all()
+        Ea, Eb = np.array(res.E) / np.linalg.norm(res.E), g["lg_E_%d" % k] / np.linalg.norm(g["lg_E_%d" % k])
+        assert min(np.abs(Ea - Eb).max(), np.abs(Ea + Eb).max()) < 1e-7
+    opt = O.default_options(squared_inlier_threshold=4.0, final_least_squares=1)
+    cam, offs, oc, oxy, f = g["tri_cam"], g["tri_offs"], g["tri_oc"], g["tri_oxy"], float(g["tri_focal"])
+    for p in range(len(offs) - 1):
+        a, b = offs[p], offs[p + 1]
+        res, inl = orc.triangulate(cam[oc[a:b]], oxy[a:b], f, opt, p)
+        assert (res.status, res.num_iterations, res.best_num_inliers) == (int(g["tri_status"][p]), int(g["tri_iters"][p]), int(g["tri_ninl"][p]))
+        assert np.abs(np.array(res.E[:3]) - g["tri_points"][p]).max() <= 1e-6 * max(1.0, np.abs(g["tri_points"][p]).max())
+    for k in range(int(g["num_full"])):
+        res, inl = orc.estimate_pair(g["fu_rays_%d" % k], O.pipeline_options(THR2), int(g["fu_pid_%d" % k]))
+        assert (res.num_iterations, res.best_num_inliers, res.number_lo_iterations) == (
+            int(g["fu_iters_%d" % k]), int(g["fu_ninl_%d" % k]), int(g["fu_nlo_%d" % k]))
+        assert (inl == g["fu_inliers_%d" % k]).all()
+        d = S.problems.rot_error(S.problems.so3exp(g["fu_r_%d" % k]), S.problems.so3exp(np.array(res.r)))
+        assert np.rad2deg(d) < 0.01
+
+
 def test_oracle_recovers_pose_with_outliers(S, O, orc):
     """Config C1: 1000 correspondences, 50 % outliers, calibrated solver, pipeline options."""
     opt = O.pipeline_options(THR2)
