@@ -58,6 +58,7 @@ class Matrix {
   Matrix() : r(R > 0 ? R : 0), c(C > 0 ? C : 0), d((size_t)r * c, T(0)) {}
   Matrix(int rows, int cols) : r(rows), c(cols), d((size_t)rows * cols, T(0)) {}
   Matrix(T a, T b, T cc) : r(3), c(1), d{a, b, cc} {}
+  Matrix(T a, T b) : r(2), c(1), d{a, b} {}  // Vector2d(x, y); integer arguments select (rows, cols) above
   template <int R2, int C2>
   Matrix(const Matrix<T, R2, C2>& o) : r(o.r), c(o.c), d(o.d) {}
   Matrix(const BlockRef<T>& b);
@@ -273,6 +274,10 @@ Matrix<T, R, C> operator-(const Matrix<T, R, C>& a, const Matrix<T, R2, C2>& b) 
   for (size_t i = 0; i < m.d.size(); ++i) m.d[i] -= b.d[i];
   return m;
 }
+template <class T, int R, int C>
+Matrix<T, R, C> operator-(const BlockRef<T>& a, const Matrix<T, R, C>& b) { return Matrix<T, R, C>(a.eval()) - b; }
+template <class T, int R, int C>
+Matrix<T, R, C> operator+(const BlockRef<T>& a, const Matrix<T, R, C>& b) { return Matrix<T, R, C>(a.eval()) + b; }
 template <class T, int R, int C>
 Matrix<T, R, C> operator*(const Matrix<T, R, C>& a, const BlockRef<T>& b) { return a * b.eval(); }
 template <class T, int R, int C>

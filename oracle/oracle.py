@@ -226,6 +226,14 @@ def build(ref=True, force=False):
                                    "-I" + os.path.join(_DIR, "fast_shim"), "-I" + os.path.join(_DIR, "eigen_shim"),
                                    "-I" + os.path.join(refroot, "include"), "-o", out5, leg[0], leg[1],
                                    os.path.join(refroot, "src", "spherical_fast_estimator.cpp"), os.path.join(refroot, "src", "so3.cpp")])
+        # the reference's synthetic-problem generator + error metrics (evaluation/problem_generator)
+        out6 = os.path.join(_DIR, "_ref", "libssfm_refgen.so")
+        dep6 = max([newest, os.path.getmtime(os.path.join(_DIR, "ref_gen.cpp"))] + [os.path.getmtime(x) for x in shim])
+        if force or not os.path.exists(out6) or os.path.getmtime(out6) < dep6:
+            subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w"] + inc +
+                                  ["-o", out6, os.path.join(_DIR, "ref_gen.cpp"),
+                                   os.path.join(refroot, "evaluation", "problem_generator", "problem_generator.cpp"),
+                                   os.path.join(refroot, "src", "so3.cpp"), os.path.join(refroot, "src", "spherical_utils.cpp")])
         # the reference's triangulation path (src/triangulation_estimator.cpp, sfm_types.cpp, so3.cpp + RansacLib)
         out3 = os.path.join(_DIR, "_ref", "libssfm_reftri.so")
         dep = max([newest, os.path.getmtime(os.path.join(_DIR, "ref_tri.cpp"))] + [os.path.getmtime(x) for x in shim])
@@ -278,6 +286,34 @@ class FastReference:
         r, t = np.zeros(3), np.zeros(3)
         self.lib.orc_fast_decompose(_dp(np.ascontiguousarray(E, np.float64).reshape(-1)), int(inward), _dp(r), _dp(t))
         return r, t
+
+
+class GeneratorReference:
+    """oracle/_ref/libssfm_refgen.so: ProblemGenerator::make_random_problem and RelativePoseSolution's error metrics
+    (evaluation/problem_generator/*).  The random engine is process-wide and seeded by default, as upstream."""
+
+    def __init__(self, path):
+        self.lib = C.CDLL(path)
+
+    def make_random_problem(self, num_corr, inward=False, rotation_deg=-1.0, point_noise=0.0):
+        rays, E, R, t = np.zeros((num_corr, 6)), np.zeros(9), np.zeros(9), np.zeros(3)
+        self.lib.orc_make_random_problem(num_corr, int(inward), C.c_double(rotation_deg), C.c_double(point_noise), _dp(rays),
+                                         _dp(E), _dp(R), _dp(t))
+        return rays, E.reshape(3, 3), R.reshape(3, 3), t
+
+    def errors(self, E, R, t, Es, Rs, ts):
+        out = np.zeros(3)
+        a = [np.ascontiguousarray(x, np.float64).reshape(-1) for x in (E, R, t, Es, Rs, ts)]
+        self.lib.orc_solution_errors(*[_dp(x) for x in a], _dp(out))
+        return out  # frob, rot, trans
+
+
+def load_ref_gen():
+    if "g" not in _cache:
+        build(ref=True)
+        p = os.path.join(_DIR, "_ref", "libssfm_refgen.so")
+        _cache["g"] = GeneratorReference(p) if os.path.exists(p) else None
+    return _cache["g"]
 
 
 class LegacyReference:

@@ -337,6 +337,34 @@ def test_golden_vectors_from_reference_sources(S, O, engine):
         assert np.rad2deg(d) < 0.01
 
 
+def test_reference_generator_problems(S, O, engine):
+    """tests/golden/refgen_golden.npz: problems from the reference's own ProblemGenerator and the results of its own
+    estimator sources, against the device -- the flows of evaluation/test_random_problems.cpp (minimal solve on
+    {0,1,2}) and evaluation/test_ransac.cpp (VanillaMSAC), plus the pipeline's LO-MSAC."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "refgen_golden.npz"))
+    for k in range(int(g["num_cases"])):
+        rays, E = g["rays_%d" % k], g["E_%d" % k]
+        inward, noise = bool(g["cfg_%d" % k][0]), float(g["cfg_%d" % k][1])
+        models, nm = engine.minimal_solve(rays, np.array([[0, 1, 2]], np.int32), S.SOLVER_ACTION_MATRIX)
+        best = min(S.problems.frob_error(E, E_of(m)) for m in models[0][:nm[0]] if np.isfinite(m).all())
+        if noise == 0.0:
+            assert best < 1e-9
+        for name, kw in (("van", dict(driver=S.DRIVER_VANILLA_MSAC, max_num_iterations=2 ** 31 - 1)),
+                         ("lo", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1))):
+            opt = S.default_options(squared_inlier_threshold=THR2, inward=int(inward), first_pair_id=100 + k, **kw)
+            res, flags = engine.estimate_pairs(rays, np.array([0, len(rays)], np.int64), opt)
+            st = g["%s_stats_%d" % (name, k)]
+            # (nearly) noise-free data: most minimal models tie at a cost of ~0, so the number of LO runs is decided by
+            # rounding noise between implementations
+            assert (int(res["num_iterations"][0]), int(res["best_num_inliers"][0])) == (int(st[0]), int(st[1])), (name, k)
+            assert noise == 0.0 or abs(int(res["number_lo_iterations"][0]) - int(st[2])) <= 1
+            assert (np.nonzero(flags)[0] == g["%s_inliers_%d" % (name, k)]).all()
+            Eg = g["%s_E_%d" % (name, k)]
+            assert model_dist(res["E"][0] / np.linalg.norm(res["E"][0]), Eg / np.linalg.norm(Eg)) < 1e-6
+            d = S.problems.rot_error(S.problems.so3exp(g["%s_r_%d" % (name, k)]), S.problems.so3exp(res["r"][0]))
+            assert np.rad2deg(d) < 0.01
+
+
 def test_determinism_and_pair_id_offset(S, engine):
     """Same inputs -> identical bits; a sub-batch with first_pair_id reproduces the full batch's rows."""
     rays, offsets, _ = S.problems.make_batch(21, 12, 800, noise=1 / 600, outlier_frac=0.6)
