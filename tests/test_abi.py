@@ -117,3 +117,49 @@ def test_cxx_adapters_on_device():
     inlier counts, rotations and focal it gets back."""
     r = _build_and_run_adapter()
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) prints one JSON line with the
+    contract's keys; it needs no GPU."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-seconds", "1.5"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "corr_hypothesis_evals_per_sec" and line["unit"] == "evals/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["config"]["workload"]
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert cb["one_thread"]["value"] > 0
+
+
+def test_bench_refuses_to_run_the_product_arm_without_a_gpu():
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_bench_product_arm_contract_small():
+    """bench.py's JSON line on a reduced pair count (contract keys only; the numbers that count come from the default run)."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--pairs", "4096", "--steps", "2", "--warmup", "3", "--no-cpu",
+                        "--no-extras"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and 0 < line["e2e"]["value"] < line["value"] * 1.05
+    rf = line["roofline"]
+    assert rf["bound"] == "fp32" and 0.3 < rf["frac"] < 1.0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
