@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define SSFM_ABI_VERSION 1
+#define SSFM_ABI_VERSION 2
 
 typedef struct ssfm_engine* ssfm_handle;
 
@@ -96,7 +96,13 @@ typedef struct SsfmOptions {
                                        SixPointEstimator::EvaluateModelOnPoint does (six_point_estimator.cpp:78-91; the
                                        focal is not used there); 1 = score with F = Kinv E Kinv, Kinv = diag(1,1,focal),
                                        the model of the reference's own refit functor (:62-70) */
+  int32_t complex_root_models;      /* 0; ACTION_MATRIX: what a complex eigenvalue of the action matrix yields.  Upstream keeps the
+                                       real part of Eigen's complex eigenvector (src/spherical_solvers.cpp:294-297, filter commented
+                                       out); its phase is decided by rounding noise, so it cannot be matched.
+                                       SSFM_COMPLEX_CANONICAL (0): the major axis of the complex solution line (deterministic,
+                                       basis independent); SSFM_COMPLEX_SKIP (1): no model, i.e. upstream's filter switched on */
 } SsfmOptions;
+enum { SSFM_COMPLEX_CANONICAL = 0, SSFM_COMPLEX_SKIP = 1 };
 
 /* A batch of image pairs in CSR form: pair p owns correspondences [offsets[p], offsets[p+1]).
  * `rays` is the caller's RayPairList memory (6 doubles per correspondence).  The engine never
@@ -104,7 +110,7 @@ typedef struct SsfmOptions {
 typedef struct SsfmBatch {
   int32_t num_pairs;
   const int64_t* offsets; /* host, num_pairs + 1 entries */
-  const double* rays;     /* host pointer, or device pointer if rays_on_device != 0 */
+  const double* rays;     /* host pointer, or device pointer (16-byte aligned) if rays_on_device != 0 */
   int32_t rays_on_device;
 } SsfmBatch;
 
@@ -223,6 +229,9 @@ int ssfm_selection_sample(uint32_t seed, uint32_t pair, uint32_t hypothesis, int
  * (p0..p5 of E = [p0 p1 p2; p1 -p0 p3; p4 p5 0], ||E||_F = 1; NaN when absent); num_models: per sample. */
 int ssfm_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t num_samples,
                        int32_t solver, double* models, int32_t* num_models);
+/* Same with the solver kind and complex_root_models taken from an options struct. */
+int ssfm_minimal_solve_opt(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t num_samples,
+                           const SsfmOptions* opt, double* models, int32_t* num_models);
 
 /* ScoreModel + GetInliers count for many models against one pair (include/RansacLib/ransac.h:295-336,
  * EvaluateModelOnPoint src/spherical_estimator.cpp:67-78): the FP32 scoring kernel.

@@ -6,9 +6,10 @@
 //
 // What it reproduces faithfully: column-pivoted Householder QR with Eigen's pivot rule and
 // makeHouseholder sign convention (so the null-space basis B, and with it the polynomial variant's
-// root set, follows the reference), partial-pivot LU, a 3x3 SVD.  EigenSolver returns unit-norm
-// eigenvectors; for complex pairs the phase is arbitrary -- as it effectively is in Eigen, where it
-// depends on the QR iteration history (models from complex roots are "parity unpinned").
+// root set, follows the reference), partial-pivot LU, a 3x3 SVD.  EigenSolver is Eigen 3.4's algorithm
+// restated step by step (ssfm_oracle::eigen34_eigensolver_4x4: Householder Hessenberg reduction, Francis
+// QR with Eigen's shift/deflation rules, hqr2 back-substitution, unit-norm complex columns), because the
+// reference keeps the real part of COMPLEX eigenvectors, whose phase is fixed by that iteration history.
 #pragma once
 #include <algorithm>
 #include <cassert>
@@ -495,22 +496,17 @@ class EigenSolver {
   typedef Matrix<std::complex<double>, Dynamic, 1> EigenvalueType;
   explicit EigenSolver(const M& m) : vecs_(4, 4), vals_(4, 1) {
     assert(m.rows() == 4 && m.cols() == 4);
-    double a[4][4], wr[4] = {0, 0, 0, 0}, wi[4] = {0, 0, 0, 0};
+    double a[4][4];
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 4; ++j) a[i][j] = m(i, j);
-    ssfm_oracle::eigenvalues_4x4(a, wr, wi);
+    std::complex<double> ev[4], V[4][4];
+    const bool ok = ssfm_oracle::eigen34_eigensolver_4x4(a, ev, V);
+    const double nanv = std::numeric_limits<double>::quiet_NaN();
+    const bool skip = ssfm_oracle::eigen_shim_skip_complex() != 0;
     for (int k = 0; k < 4; ++k) {
-      std::complex<double> b[4][4], v[4];
-      for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) b[i][j] = a[i][j];
-      const std::complex<double> lam(wr[k], wi[k]);
-      for (int i = 0; i < 4; ++i) b[i][i] -= lam;
-      ssfm_oracle::null_vector_c4(b, v);
-      double n = 0;
-      for (int i = 0; i < 4; ++i) n += std::norm(v[i]);
-      n = std::sqrt(n);
-      for (int i = 0; i < 4; ++i) vecs_(i, k) = v[i] / n;
-      vals_(k) = lam;
+      const bool masked = skip && ok && ev[k].imag() != 0.0;
+      for (int i = 0; i < 4; ++i) vecs_(i, k) = (ok && !masked) ? V[i][k] : std::complex<double>(nanv, nanv);
+      vals_(k) = ok ? ev[k] : std::complex<double>(nanv, nanv);
     }
   }
   const EigenvectorsType& eigenvectors() const { return vecs_; }

@@ -12,6 +12,7 @@ import subprocess
 import numpy as np
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
+COMPLEX_CANONICAL, COMPLEX_EIGEN, COMPLEX_SKIP = 0, 1, 2  # ssfm_oracle.hpp ComplexRootMode
 
 
 class OrcOptions(C.Structure):
@@ -24,7 +25,7 @@ class OrcOptions(C.Structure):
         ("lo_starting_iterations", C.c_uint32), ("final_least_squares", C.c_int32),
         ("solver_kind", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("legacy_budget", C.c_int32), ("legacy_prob_success", C.c_double),
-        ("preemptive_block", C.c_int32), ("reserved", C.c_int32),
+        ("preemptive_block", C.c_int32), ("complex_mode", C.c_int32),
     ]
 
 
@@ -70,6 +71,7 @@ class Oracle:
         L.orc_score_batch.restype = C.c_double
         L.orc_estimate_pair.restype = C.c_int
         L.orc_solve.restype = C.c_int
+        L.orc_solve_mode.restype = C.c_int
         self.is_reference = bool(L.orc_is_reference())
 
     def philox_sample(self, seed, pair, it, k, n):
@@ -92,12 +94,23 @@ class Oracle:
         self.lib.orc_knuth_sample(C.c_uint32(seed), C.c_uint32(pair), C.c_uint32(hyp), n_total, k, _ip(idx))
         return idx
 
-    def solve(self, rays, sample, kind=0):
+    def solve(self, rays, sample, kind=0, complex_mode=COMPLEX_CANONICAL):
+        """The minimal solver on one sample.  complex_mode: what to return for action-matrix models that come from a
+        complex eigenvalue (ssfm_oracle.hpp ComplexRootMode).  Reference-source builds ignore CANONICAL (they always
+        return what the reference returns) and honour SKIP through the mask in the Eigen stand-in."""
         rays = np.ascontiguousarray(rays, np.float64)
         sample = np.ascontiguousarray(sample, np.int32)
         models = np.zeros((4, 6))
-        nm = self.lib.orc_solve(_dp(rays), _ip(sample), len(sample), kind, _dp(models))
+        nm = self.lib.orc_solve_mode(_dp(rays), _ip(sample), len(sample), kind, int(complex_mode), _dp(models))
         return nm, models
+
+    def eigen34(self, M):
+        """Eigen::EigenSolver<Matrix4d>(M) restated: (eigenvalues[4] complex, eigenvectors[4,4] complex, ok)."""
+        M = np.ascontiguousarray(M, np.float64).reshape(16)
+        ev = np.zeros(8)
+        V = np.zeros(32)
+        ok = self.lib.orc_eigen34(_dp(M), _dp(ev), _dp(V))
+        return ev[0::2] + 1j * ev[1::2], (V[0::2] + 1j * V[1::2]).reshape(4, 4), bool(ok)
 
     def sampson(self, E, rays):
         rays = np.ascontiguousarray(rays, np.float64)
@@ -160,6 +173,19 @@ class Oracle:
         secs = self.lib.orc_estimate_batch(_dp(rays), offsets.ctypes.data_as(C.POINTER(C.c_int64)), P, C.byref(opt),
                                            C.c_uint32(first_pair_id), nthreads, res)
         return res, secs
+
+    def estimate_batch_flags(self, rays, offsets, opt, first_pair_id=0, nthreads=0):
+        """estimate_batch + the final inlier set as one byte per correspondence.  Returns (results, flags, seconds)."""
+        rays = np.ascontiguousarray(rays, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        P = len(offsets) - 1
+        res = (OrcResult * P)()
+        flags = np.zeros(max(int(offsets[-1]), 1), np.uint8)
+        self.lib.orc_estimate_batch_flags.restype = C.c_double
+        secs = self.lib.orc_estimate_batch_flags(_dp(rays), offsets.ctypes.data_as(C.POINTER(C.c_int64)), P, C.byref(opt),
+                                                 C.c_uint32(first_pair_id), nthreads, res,
+                                                 flags.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return res, flags[:int(offsets[-1])], secs
 
     def score_batch(self, models6, rays, thr2, nthreads=0):
         models6 = np.ascontiguousarray(models6, np.float64)

@@ -117,7 +117,7 @@ struct RefPreemptAdapter {
 #endif
 
 int estimate_one(const RayPair* corr, int n, const OrcOptions& o, uint32_t pair_id, OrcResult* out, int* inlier_idx) {
-  SphericalEstimator est(corr, n, (SolverKind)o.solver_kind, o.inward != 0, pair_id);
+  SphericalEstimator est(corr, n, (SolverKind)o.solver_kind, o.inward != 0, pair_id, o.complex_mode);
   Mat3 E;
   for (int i = 0; i < 9; ++i) E.m[i] = 0.0;
   Statistics st;
@@ -295,13 +295,33 @@ void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, 
   knuth_sample(seed, pair, hyp, N, n, idx);
 }
 
-int orc_solve(const double* rays, const int* sample, int n, int kind, double* models) {
+int orc_solve_mode(const double* rays, const int* sample, int n, int kind, int complex_mode, double* models) {
   double m[4][6];
   for (int k = 0; k < 4; ++k)
     for (int i = 0; i < 6; ++i) m[k][i] = std::numeric_limits<double>::quiet_NaN();
-  const int nm = solve_spherical(reinterpret_cast<const RayPair*>(rays), sample, n, (SolverKind)kind, m);
+  const int nm = solve_spherical(reinterpret_cast<const RayPair*>(rays), sample, n, (SolverKind)kind, m, complex_mode);
   std::memcpy(models, m, sizeof(m));
   return nm;
+}
+int orc_solve(const double* rays, const int* sample, int n, int kind, double* models) {
+  return orc_solve_mode(rays, sample, n, kind, COMPLEX_CANONICAL, models);
+}
+
+// Eigen::EigenSolver<Matrix4d> restated (ssfm_oracle.hpp): ev = 4 x (re, im); V = 4 x 4 x (re, im), row-major.
+int orc_eigen34(const double* M16, double* ev, double* V) {
+  double M[4][4];
+  std::memcpy(M, M16, sizeof(M));
+  std::complex<double> e[4], v[4][4];
+  const bool ok = eigen34_eigensolver_4x4(M, e, v);
+  for (int k = 0; k < 4; ++k) {
+    ev[2 * k] = e[k].real();
+    ev[2 * k + 1] = e[k].imag();
+    for (int i = 0; i < 4; ++i) {
+      V[2 * (4 * i + k)] = v[i][k].real();
+      V[2 * (4 * i + k) + 1] = v[i][k].imag();
+    }
+  }
+  return ok ? 1 : 0;
 }
 
 void orc_sampson(const double* E9, const double* rays, int n, double* out) {
@@ -377,6 +397,24 @@ double orc_estimate_batch(const double* rays, const int64_t* offsets, int npairs
   const auto t0 = std::chrono::steady_clock::now();
   parallel_for(npairs, nthreads, [&](int p) {
     estimate_one(c + offsets[p], (int)(offsets[p + 1] - offsets[p]), *opt, first_pair_id + (uint32_t)p, &out[p], nullptr);
+  });
+  const auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Same, also returning the final inlier set of every pair as one byte per correspondence (stats.inlier_indices).
+double orc_estimate_batch_flags(const double* rays, const int64_t* offsets, int npairs, const OrcOptions* opt,
+                                uint32_t first_pair_id, int nthreads, OrcResult* out, uint8_t* flags) {
+  const RayPair* c = reinterpret_cast<const RayPair*>(rays);
+  const auto t0 = std::chrono::steady_clock::now();
+  parallel_for(npairs, nthreads, [&](int p) {
+    const int n = (int)(offsets[p + 1] - offsets[p]);
+    std::vector<int> idx(n > 0 ? n : 1);
+    const int ninl = estimate_one(c + offsets[p], n, *opt, first_pair_id + (uint32_t)p, &out[p], idx.data());
+    uint8_t* f = flags + offsets[p];
+    for (int i = 0; i < n; ++i) f[i] = 0;
+    if (out[p].status == 0)
+      for (int i = 0; i < ninl; ++i) f[idx[i]] = 1;
   });
   const auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();

@@ -27,7 +27,8 @@ typedef struct {
   int32_t legacy_budget;       /* drivers 2, 3: number of hypotheses (estimators.size()) */
   double legacy_prob_success;
   int32_t preemptive_block;    /* driver 3: B (preemptive_ransac.h:40) */
-  int32_t reserved;
+  int32_t complex_mode;        /* action-matrix solver, models from complex eigenvalues: 0 canonical, 1 Eigen-restated Re(V), 2 skip (ssfm_oracle.hpp ComplexRootMode);
+                                  reference-source builds: 2 masks them in the Eigen stand-in, anything else is Eigen-restated */
 } OrcOptions;
 
 typedef struct {
@@ -49,6 +50,8 @@ int orc_triangulate(const double* cam_tr, const double* obs_xy, int n, double fo
                     OrcResult* out, int* inlier_idx);
 void orc_knuth_sample(uint32_t seed, uint32_t pair, uint32_t hyp, int N, int n, int* idx);
 int orc_solve(const double* rays, const int* sample, int n, int kind, double* models /* 4x6 */);
+int orc_solve_mode(const double* rays, const int* sample, int n, int kind, int complex_mode, double* models /* 4x6 */);
+int orc_eigen34(const double* M16, double* ev /* 4 x (re,im) */, double* V /* 4x4 x (re,im) */);
 void orc_sampson(const double* E9, const double* rays, int n, double* out);
 void orc_score(const double* E9, const double* rays, int n, double thr, double* score, int* ninl);
 void orc_decompose(const double* E9, int inward, double* r, double* t);
@@ -61,6 +64,8 @@ int orc_estimate_pair(const double* rays, int n, const OrcOptions* opt, uint32_t
 /* host threads over pairs, like the OpenMP loop at examples/spherical_sfm_tools.cpp:332; returns wall seconds. */
 double orc_estimate_batch(const double* rays, const int64_t* offsets, int npairs, const OrcOptions* opt,
                           uint32_t first_pair_id, int nthreads, OrcResult* out);
+double orc_estimate_batch_flags(const double* rays, const int64_t* offsets, int npairs, const OrcOptions* opt,
+                                uint32_t first_pair_id, int nthreads, OrcResult* out, uint8_t* flags /* one byte per correspondence */);
 double orc_score_batch(const double* models6, int nmodels, const double* rays, int n, double thr, int nthreads,
                        double* scores, int* ninl);
 

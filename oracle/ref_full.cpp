@@ -61,6 +61,7 @@ Eigen::Matrix3d to_mat(const double* E9) {
 }
 
 int estimate_one(const double* rays, int n, const OrcOptions& o, uint32_t pair_id, OrcResult* out, int* inlier_idx) {
+  ssfm_oracle::eigen_shim_skip_complex() = o.complex_mode == ssfm_oracle::COMPLEX_SKIP;  // single-threaded harness
   const RayPairList corr = to_list(rays, n);
   CountingEstimator est(corr, o.solver_kind == 1, o.inward != 0, pair_id);
   ransac_lib::LORansacOptions ro;
@@ -119,6 +120,13 @@ void orc_philox_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n
   ssfm_oracle::philox_sample(seed, pair, iter, k, n, idx);
 }
 
+int orc_solve(const double* rays, const int* sample, int n, int kind, double* models);
+int orc_solve_mode(const double* rays, const int* sample, int n, int kind, int complex_mode, double* models) {
+  ssfm_oracle::eigen_shim_skip_complex() = complex_mode == ssfm_oracle::COMPLEX_SKIP;
+  const int nm = orc_solve(rays, sample, n, kind, models);
+  ssfm_oracle::eigen_shim_skip_complex() = 0;
+  return nm;
+}
 int orc_solve(const double* rays, const int* sample, int n, int kind, double* models) {
   int mx = 0;
   for (int i = 0; i < n; ++i) mx = std::max(mx, sample[i]);

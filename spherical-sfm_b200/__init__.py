@@ -18,14 +18,20 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 LIB_PATH = os.environ.get("SSFM_LIB_PATH", os.path.join(_DIR, "libssfm_b200.so"))  # override: profiling builds
-_SOURCES = [os.path.join(_DIR, "csrc", f) for f in
-            ("ssfm_engine.cu", "ssfm_kernels.cuh", "ssfm_chain.cuh", "ssfm_math.cuh")] + [
-                os.path.join(_ROOT, "include", "ssfm.h")]
+_MAIN_SOURCE = os.path.join(_DIR, "csrc", "ssfm_engine.cu")
+
+
+def _sources():
+    """Everything libssfm_b200.so is compiled from (the staleness check looks at all of it)."""
+    import glob
+    return sorted(glob.glob(os.path.join(_DIR, "csrc", "*.cu")) + glob.glob(os.path.join(_DIR, "csrc", "*.cuh")) +
+                  glob.glob(os.path.join(_ROOT, "include", "*.h")))
 
 SSFM_OK, SSFM_ERR_INVALID, SSFM_ERR_NO_DEVICE, SSFM_ERR_CUDA, SSFM_ERR_OOM = 0, 1, 2, 3, 4
 PAIR_OK, PAIR_TOO_FEW_POINTS, PAIR_NO_MODEL, PAIR_SKIPPED = 0, 1, 2, 3
 SOLVER_ACTION_MATRIX, SOLVER_POLYNOMIAL, SOLVER_FAST_STURM, SOLVER_SIXPT_FOCAL = 0, 1, 2, 3
 DRIVER_LO_MSAC, DRIVER_VANILLA_MSAC, DRIVER_MSAC_FIXED, DRIVER_PREEMPTIVE = 0, 1, 2, 3
+COMPLEX_CANONICAL, COMPLEX_SKIP = 0, 1
 
 
 class SsfmError(RuntimeError):
@@ -46,6 +52,7 @@ class SsfmOptions(C.Structure):
         ("solver", C.c_int32), ("driver", C.c_int32), ("inward", C.c_int32),
         ("fixed_budget", C.c_int32), ("fixed_prob_success", C.c_double), ("first_pair_id", C.c_uint32),
         ("min_num_points", C.c_int32), ("preemptive_block", C.c_int32), ("sixpt_focal_scoring", C.c_int32),
+        ("complex_root_models", C.c_int32),
     ]
 
 
@@ -101,10 +108,10 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build_extension(force=False, verbose=False):
     """Compile csrc/ into libssfm_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    newest = max(os.path.getmtime(s) for s in _SOURCES)
+    newest = max(os.path.getmtime(s) for s in _sources())
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _SOURCES[0]]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _MAIN_SOURCE]
     subprocess.check_call(cmd, cwd=_DIR)
     return LIB_PATH
 
@@ -131,7 +138,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
 ]
 
@@ -281,14 +288,15 @@ class Engine:
         return ptr.value, n.value
 
     # ---- replay hooks -------------------------------------------------------------------
-    def minimal_solve(self, rays, samples, solver=SOLVER_ACTION_MATRIX):
+    def minimal_solve(self, rays, samples, solver=SOLVER_ACTION_MATRIX, complex_root_models=COMPLEX_CANONICAL):
         rays = np.ascontiguousarray(rays, np.float64)
         samples = np.ascontiguousarray(samples, np.int32).reshape(-1, 3)
         ns = len(samples)
         models = np.zeros((ns, 4, 6))
         nm = np.zeros(ns, np.int32)
-        _check(lib().ssfm_minimal_solve(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns, solver,
-                                        _p(models, C.c_double), _p(nm, C.c_int32)))
+        opt = default_options(solver=solver, complex_root_models=complex_root_models)
+        _check(lib().ssfm_minimal_solve_opt(self._h, _p(rays, C.c_double), len(rays), _p(samples, C.c_int32), ns, C.byref(opt),
+                                            _p(models, C.c_double), _p(nm, C.c_int32)))
         return models, nm
 
     def retriangulate(self, camera_tr, obs_offsets, obs_camera, obs_xy, focal, opt):

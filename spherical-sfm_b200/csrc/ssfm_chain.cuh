@@ -34,6 +34,7 @@ struct Params {
   int preempt_block;  // pre-emptive driver: B
   int sixpt_focal_scoring;  // six-point estimator: score with Kinv E Kinv instead of E
   float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
+  int skip_complex;   // action-matrix solver: leave out the models of complex eigenvalues (SsfmOptions.complex_root_models)
 };
 
 // Per-pair RANSAC state carried across rounds (RansacStatistics + the loop's locals).
@@ -443,7 +444,8 @@ SSFM_HD void keep_better(double s, const double* m, int c, double* sb, double* m
 // the three greedily pivoted correspondences (largest remaining epipolar-row norm), see
 // nullspace_colpiv.  Picks the model with the smallest summed Sampson error over the sample.
 template <class Ctx>
-SSFM_HD_NOINLINE bool non_minimal_solver(const Ctx& cx, const PairView& pv, const int* sample, int ns, double* E) {
+SSFM_HD_NOINLINE bool non_minimal_solver(const Ctx& cx, const PairView& pv, const int* sample, int ns, double* E,
+                                         bool skip_complex = false) {
   if (ns < 3) return false;
   // greedy pivoting by modified Gram-Schmidt on the epipolar rows (ns <= 64 handled serially & uniformly)
   int pick[3] = {-1, -1, -1};
@@ -483,7 +485,7 @@ SSFM_HD_NOINLINE bool non_minimal_solver(const Ctx& cx, const PairView& pv, cons
   const double* c0 = pv.rays + 6 * (size_t)sample[pick[0]];
   const double* c1 = pv.rays + 6 * (size_t)sample[pick[1]];
   const double* c2 = pv.rays + 6 * (size_t)sample[pick[2]];
-  solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, models);
+  solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, models, skip_complex);
   double best_score = INFINITY;
   int best_ind = 0;
   for (int m = 0; m < 4; ++m) {
@@ -531,7 +533,7 @@ SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const P
       cx.sync();
     }
     double m[9];
-    if (!non_minimal_solver(cx, pv, sc.list_a, ns, m)) continue;
+    if (!non_minimal_solver(cx, pv, sc.list_a, ns, m, P.skip_complex != 0)) continue;
     score = msac_score_exact(cx, m, pv.rays, pv.n, thr, &cnt, evals);
     keep_better(score, m, cnt, score_best, E_best, cnt_best);
     lsq_fit(cx, P, pv, sc, thr, m, evals);

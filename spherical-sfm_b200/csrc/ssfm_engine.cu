@@ -81,6 +81,7 @@ struct ssfm_engine {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[6] = {};
+  cudaEvent_t ev_tables = nullptr;  // offsets (+ upload-time flags) are in HBM: every worker stream waits on it
   // resident batch
   int P = 0;
   long long M = 0;
@@ -171,6 +172,7 @@ Params make_params(const SsfmOptions& o) {
   P.min_points = o.min_num_points;
   P.preempt_block = o.preemptive_block;
   P.sixpt_focal_scoring = o.sixpt_focal_scoring;
+  P.skip_complex = o.complex_root_models == SSFM_COMPLEX_SKIP;
   P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
   return P;
@@ -182,6 +184,8 @@ int check_options(const SsfmOptions* o) {
   if (o->solver == SSFM_SOLVER_SIXPT_FOCAL && o->driver != SSFM_DRIVER_VANILLA_MSAC)
     return fail(SSFM_ERR_INVALID, "the batched six-point shared-focal path runs SSFM_DRIVER_VANILLA_MSAC (config C4); for LO-MSAC drive GpuSixPointEstimator through the hooks");
   if (o->driver < 0 || o->driver > 3) return fail(SSFM_ERR_INVALID, "unknown driver kind");
+  if (o->complex_root_models != SSFM_COMPLEX_CANONICAL && o->complex_root_models != SSFM_COMPLEX_SKIP)
+    return fail(SSFM_ERR_INVALID, "unknown complex_root_models");
   if (o->driver == SSFM_DRIVER_PREEMPTIVE && (o->fixed_budget <= 0 || o->fixed_budget > 8192 || o->preemptive_block <= 0))
     return fail(SSFM_ERR_INVALID, "pre-emptive driver needs 0 < fixed_budget <= 8192 hypotheses and preemptive_block > 0");
   if (!(o->squared_inlier_threshold > 0.0)) return fail(SSFM_ERR_INVALID, "squared_inlier_threshold must be > 0");
@@ -231,6 +235,8 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
   w.score_launches = w.refit_waves = 0;
   SSFM_WCK(w.counters.ensure(32));
   SSFM_WCK(w.counts.ensure(8));
+  SSFM_WCK(cudaStreamWaitEvent(w.stream, h->ev_tables, 0));
+  SSFM_WCK(cudaStreamWaitEvent(w.stream_hi, h->ev_tables, 0));
   SSFM_WCK(cudaMemsetAsync(w.counters.p, 0, 32 * sizeof(unsigned long long), w.stream));
   cudaEvent_t evA = w.ev[0], evB = w.ev[1], evC = w.ev[2], evD = w.ev[3];
   int launches = 0;
@@ -540,7 +546,10 @@ void ssfm_default_options(SsfmOptions* o) {
   o->min_num_points = 0;
   o->preemptive_block = 10; /* PreemptiveRANSAC( size_t _B = 10 ), preemptive_ransac.h:40 */
   o->sixpt_focal_scoring = 0;
+  o->complex_root_models = SSFM_COMPLEX_CANONICAL;
 }
+
+static int create_resources(ssfm_engine* h);
 
 int ssfm_create(int device, ssfm_handle* out) {
   if (!out) return fail(SSFM_ERR_INVALID, "out is NULL");
@@ -560,8 +569,19 @@ int ssfm_create(int device, ssfm_handle* out) {
   ssfm_engine* h = new ssfm_engine();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  const int rc = create_resources(h);
+  if (rc != SSFM_OK) {
+    ssfm_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return SSFM_OK;
+}
+
+static int create_resources(ssfm_engine* h) {
   SSFM_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   for (auto& ev : h->ev) SSFM_CK(cudaEventCreate(&ev));
+  SSFM_CK(cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming));
   SSFM_CK(cudaMallocHost(&h->h_count, 64));
   SSFM_CK(cudaMallocHost(&h->h_up_flags, sizeof(int) * kMaxUploadChunks));
   h->num_workers = kMaxWorkers;
@@ -575,39 +595,43 @@ int ssfm_create(int device, ssfm_handle* out) {
     for (auto& ev : w.ev) SSFM_CK(cudaEventCreate(&ev));
     SSFM_CK(cudaMallocHost(&w.h_count, 64));
   }
-  *out = h;
   return SSFM_OK;
 }
 
 void ssfm_destroy(ssfm_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release();
   h->counts.release(); h->results.release(); h->flags.release();
   for (int k = 0; k < h->num_workers; ++k) {
     Worker& w = h->workers[k];
-    cudaStreamSynchronize(w.stream);
-    cudaStreamSynchronize(w.stream_hi);
+    if (w.stream) cudaStreamSynchronize(w.stream);
+    if (w.stream_hi) cudaStreamSynchronize(w.stream_hi);
     w.release();
-    for (auto& ev : w.ev) cudaEventDestroy(ev);
+    for (auto& ev : w.ev)
+      if (ev) cudaEventDestroy(ev);
     if (w.h_count) cudaFreeHost(w.h_count);
-    cudaStreamDestroy(w.stream);
-    cudaStreamDestroy(w.stream_hi);
+    if (w.stream) cudaStreamDestroy(w.stream);
+    if (w.stream_hi) cudaStreamDestroy(w.stream_hi);
   }
   delete[] h->workers;
-  for (auto& ev : h->ev) cudaEventDestroy(ev);
+  for (auto& ev : h->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (h->ev_tables) cudaEventDestroy(h->ev_tables);
   if (h->h_count) cudaFreeHost(h->h_count);
   if (h->h_up_flags) cudaFreeHost(h->h_up_flags);
   for (auto& e : h->up_ev) cudaEventDestroy(e);
   h->up_flags.release();
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
 static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
   if (b->num_pairs < 0 || (b->num_pairs > 0 && (!b->offsets || !b->rays))) return fail(SSFM_ERR_INVALID, "bad batch");
+  if (b->rays_on_device && (reinterpret_cast<uintptr_t>(b->rays) & 15u) != 0)
+    return fail(SSFM_ERR_INVALID, "device rays must be 16-byte aligned (they are read as double2)");
   SSFM_CK(cudaSetDevice(h->device));
   h->resident = false;
   h->have_results = false;
@@ -628,6 +652,9 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   SSFM_CK(h->uv4.ensure(m));
   SSFM_CK(h->counts.ensure(8));
   SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), h->stream));
+  // Worker streams are non-blocking and start reading `offsets` before any chunk event in the pipelined plan:
+  // they wait on this event first (run_range), so a reused engine never sees the previous batch's table.
+  SSFM_CK(cudaEventRecord(h->ev_tables, h->stream));
   h->up_bounds.clear();
   if (pipelined && !b->rays_on_device && h->P > 2 * kPipelinePassPairs && (h->P / kPipelinePassPairs) < kMaxUploadChunks - 1) {
     // Chunked, asynchronous upload: chunk k = pairs [k*16384, (k+1)*16384); H2D + pack on the copy
@@ -916,8 +943,15 @@ int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions
                         uint8_t* inlier_flags) {
   if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
   if (int rc = check_options(opt)) return rc;
-  if (int rc = upload_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return rc;
-  if (int rc = ssfm_run(h, opt)) return rc;
+  auto abandon = [h](int rc) {  // never leave copies from the caller's buffer in flight, nor a half-uploaded batch resident
+    cudaStreamSynchronize(h->stream);
+    h->up_bounds.clear();
+    h->resident = false;
+    h->have_results = false;
+    return rc;
+  };
+  if (int rc = upload_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return abandon(rc);
+  if (int rc = ssfm_run(h, opt)) return abandon(rc);
   SSFM_CK(cudaStreamSynchronize(h->stream));
   if (!h->up_bounds.empty()) {  // the batch is fully resident now; later ssfm_run calls use the plain plan
     bool all_unit = true;
@@ -942,6 +976,7 @@ int ssfm_sample(uint32_t seed, uint32_t pair, uint32_t iter, int32_t k, int32_t 
 int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* b, const SsfmOptions* opt, double* points_xyz, int32_t* num_inliers,
                        int32_t* status, uint32_t* num_iterations) {
   if (!h || !b || !opt || !points_xyz || !num_inliers || !status) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: NULL argument");
+  if (int rc = check_options(opt)) return rc;
   if (b->num_points < 0 || b->num_cameras < 0 || !(b->focal > 0.0)) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: bad sizes or focal");
   if (b->num_points == 0) return SSFM_OK;
   if (!b->obs_offsets || !b->camera_tr) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: NULL table");
@@ -1089,8 +1124,19 @@ struct TmpGuard {
   guard.ptrs.push_back(buf.p); \
   buf.cap = 0;
 
+static int minimal_solve_impl(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t ns, int32_t solver,
+                              int skip, double* models, int32_t* num_models);
 int ssfm_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t ns, int32_t solver,
                        double* models, int32_t* num_models) {
+  return minimal_solve_impl(h, rays, n, samples, ns, solver, 0, models, num_models);
+}
+int ssfm_minimal_solve_opt(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t ns, const SsfmOptions* opt,
+                           double* models, int32_t* num_models) {
+  if (int rc = check_options(opt)) return rc;
+  return minimal_solve_impl(h, rays, n, samples, ns, opt->solver, opt->complex_root_models == SSFM_COMPLEX_SKIP, models, num_models);
+}
+static int minimal_solve_impl(ssfm_handle h, const double* rays, int32_t n, const int32_t* samples, int32_t ns, int32_t solver,
+                              int skip, double* models, int32_t* num_models) {
   if (!h || !rays || !samples || !models || !num_models || n < 3 || ns < 0) return fail(SSFM_ERR_INVALID, "bad argument");
   if (solver < 0 || solver > 2) return fail(SSFM_ERR_INVALID, "unknown solver kind");
   for (int i = 0; i < 3 * ns; ++i)
@@ -1106,9 +1152,9 @@ int ssfm_minimal_solve(ssfm_handle h, const double* rays, int32_t n, const int32
   SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(ds, samples, sizeof(int) * 3 * ns, cudaMemcpyHostToDevice, h->stream));
   const int blocks = (ns + 63) / 64;
-  if (solver == 0) k_solve_samples<0><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
-  else if (solver == 1) k_solve_samples<1><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
-  else k_solve_samples<2><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, dm, dn);
+  if (solver == 0) k_solve_samples<0><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, skip, dm, dn);
+  else if (solver == 1) k_solve_samples<1><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, skip, dm, dn);
+  else k_solve_samples<2><<<blocks, 64, 0, h->stream>>>(dr, ds, ns, skip, dm, dn);
   SSFM_CK(cudaGetLastError());
   SSFM_CK(cudaMemcpyAsync(models, dm, sizeof(double) * 24 * ns, cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaMemcpyAsync(num_models, dn, sizeof(int) * ns, cudaMemcpyDeviceToHost, h->stream));

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Param
     c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
   }
   double m[4][6];
-  solve_minimal<KIND>(c[0], c[0] + 3, c[1], c[1] + 3, c[2], c[2] + 3, m);
+  solve_minimal<KIND>(c[0], c[0] + 3, c[1], c[1] + 3, c[2], c[2] + 3, m, P.skip_complex != 0);
   double* dst = models + (size_t)a * 24 * R + j;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(64, SSFM_TRI_MINBLOCKS) k_retriangulate(Params
 // Hook kernels (parity tests drive the pieces one at a time).
 // ------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void k_solve_samples(const double* __restrict__ rays, const int* __restrict__ samples, int ns,
+__global__ void k_solve_samples(const double* __restrict__ rays, const int* __restrict__ samples, int ns, int skip_complex,
                                 double* __restrict__ models, int* __restrict__ nmodels) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= ns) return;
@@ -748,7 +748,7 @@ __global__ void k_solve_samples(const double* __restrict__ rays, const int* __re
   double a[3][6];
   for (int i = 0; i < 6; ++i) { a[0][i] = c0[i]; a[1][i] = c1[i]; a[2][i] = c2[i]; }
   double m[4][6];
-  const int nm = solve_minimal<KIND>(a[0], a[0] + 3, a[1], a[1] + 3, a[2], a[2] + 3, m);
+  const int nm = solve_minimal<KIND>(a[0], a[0] + 3, a[1], a[1] + 3, a[2], a[2] + 3, m, skip_complex != 0);
   for (int k = 0; k < 4; ++k)
     for (int i = 0; i < 6; ++i) models[(size_t)s * 24 + k * 6 + i] = m[k][i];
   nmodels[s] = nm;

@@ -8,7 +8,8 @@
 // Reference citations are relative to the reference root.  The numerics are deliberately NOT the
 // reference's (nor the oracle's): null space by pivoted Householder, but roots by a real
 // quadratic factorisation of the characteristic quartic + Bairstow/Newton polish and eigenvectors
-// by 2x2 solves, so that parity tests compare two independent implementations.
+// by 2x2 solves, so that parity tests compare two independent implementations.  What is returned
+// is the reference's: four models per sample, the polynomial variant's Re(y) models included.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -756,9 +757,13 @@ SSFM_HD void roots_action_matrix(const double (&G)[6][4], Cplx* xs, Cplx* ys) {
 
 // Solve one minimal sample.  models: 4 x 6.  Returns the number of models (KIND 0/1: always 4,
 // NaN-filled when the elimination breaks down; KIND 2: real roots with |y| <= 10 only).
+// skip_complex (KIND 0 only): models that come from a complex eigenvalue of the action matrix are left out (NaN)
+// -- upstream's own commented-out filter (src/spherical_solvers.cpp:294).  Otherwise they are the canonical
+// representative (model_from_b): the reference's Re(eigenvector) has a phase fixed by rounding noise in Eigen's QR
+// sweeps, which no second implementation can reproduce.
 template <int KIND>
 SSFM_HD_NOINLINE int solve_minimal(const double* u0, const double* v0, const double* u1, const double* v1, const double* u2,
-                          const double* v2, double (&models)[4][6]) {
+                          const double* v2, double (&models)[4][6], bool skip_complex = false) {
   double m[6][3];
   {
     double a[6];
@@ -787,7 +792,11 @@ SSFM_HD_NOINLINE int solve_minimal(const double* u0, const double* v0, const dou
     Cplx xs[4], ys[4];
     roots_action_matrix(G, xs, ys);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) model_from_b(B, xs[k], ys[k], Cplx{1.0, 0.0}, models[k]);
+    for (int k = 0; k < 4; ++k) {
+      model_from_b(B, xs[k], ys[k], Cplx{1.0, 0.0}, models[k]);
+      if (skip_complex && xs[k].im != 0.0)
+        for (int i = 0; i < 6; ++i) models[k][i] = nanv;
+    }
     return 4;
   } else if (KIND == 1) {
     const bool ok = eliminate_G<4>(C, G);
@@ -801,12 +810,12 @@ SSFM_HD_NOINLINE int solve_minimal(const double* u0, const double* v0, const dou
     quartic_roots(-G[5][0], G[4][0] - G[5][1], G[4][1] - G[5][2], G[4][2] - G[5][3], G[4][3], yr);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const Cplx y = yr[k];
-      const Cplx y2 = cmul(y, y), y3 = cmul(y2, y);
-      Cplx x = cadd(cadd(cscale(G[5][0], y3), cscale(G[5][1], y2)), cscale(G[5][2], y));
-      x.re += G[5][3];
-      x = {-x.re, -x.im};
-      model_from_b(B, x, y, Cplx{1.0, 0.0}, models[k]);
+      // SolveQuarticReals without a tolerance keeps the REAL PART of every Ferrari root (:73-83, call at :631);
+      // x is row 5 evaluated at that real y.  Deterministic upstream, so it is matched (not canonicalised).
+      const double y = yr[k].re;
+      const double y2 = y * y, y3 = y2 * y;
+      const double x = -G[5][0] * y3 - G[5][1] * y2 - G[5][2] * y - G[5][3];
+      model_from_b(B, Cplx{x, 0.0}, Cplx{y, 0.0}, Cplx{1.0, 0.0}, models[k]);
     }
     return 4;
   } else {

@@ -85,7 +85,8 @@ class HsParams(C.Structure):
                 ('num_lsq_iters', C.c_int32), ('min_sample_mult', C.c_int32), ('non_min_mult', C.c_int32),
                 ('lo_start', C.c_uint32), ('final_lsq', C.c_int32), ('solver', C.c_int32), ('driver', C.c_int32),
                 ('inward', C.c_int32), ('fixed_budget', C.c_int32), ('fixed_prob', C.c_double),
-                ('cand_margin', C.c_float), ('first_round', C.c_int32), ('round_cap', C.c_int32), ('defer', C.c_int32)]
+                ('cand_margin', C.c_float), ('first_round', C.c_int32), ('round_cap', C.c_int32), ('defer', C.c_int32),
+                ('skip_complex', C.c_int32)]
 
 
 class HsResult(C.Structure):
@@ -112,11 +113,11 @@ class HostShim:
     def ip(a):
         return a.ctypes.data_as(C.POINTER(C.c_int))
 
-    def solve(self, rays, sample, kind):
+    def solve(self, rays, sample, kind, skip_complex=False):
         rays = np.ascontiguousarray(rays, np.float64)
         s = np.ascontiguousarray(sample, np.int32)
         models = np.full((4, 6), np.nan)
-        nm = self.lib.hs_solve(self.dp(rays), self.ip(s), kind, self.dp(models))
+        nm = self.lib.hs_solve(self.dp(rays), self.ip(s), kind, int(skip_complex), self.dp(models))
         return nm, models
 
     def estimate_pair(self, rays, opt, pair_id, margin=2e-4, first=128, cap=256, defer=1):
@@ -126,7 +127,8 @@ class HostShim:
                       opt.squared_inlier_threshold, opt.random_seed, opt.num_lo_steps, opt.threshold_multiplier,
                       opt.num_lsq_iterations, opt.min_sample_multiplicator, opt.non_min_sample_multiplier,
                       opt.lo_starting_iterations, opt.final_least_squares, opt.solver_kind, opt.driver, opt.inward,
-                      opt.legacy_budget, opt.legacy_prob_success, margin, first, cap, defer)
+                      opt.legacy_budget, opt.legacy_prob_success, margin, first, cap, defer,
+                      int(opt.complex_mode == 2))  # OrcOptions.complex_mode: 0 canonical, 2 skip
         res = HsResult()
         flags = np.zeros(max(n, 1), np.uint8)
         self.lib.hs_estimate_pair(self.dp(rays), n, C.byref(hp), C.c_uint32(pair_id), C.byref(res),
@@ -141,7 +143,7 @@ class HostShim:
         hp = HsParams(opt.min_num_iterations, opt.max_num_iterations, opt.success_probability,
                       opt.squared_inlier_threshold, opt.random_seed, opt.num_lo_steps, opt.threshold_multiplier,
                       opt.num_lsq_iterations, opt.min_sample_multiplicator, opt.non_min_sample_multiplier,
-                      opt.lo_starting_iterations, opt.final_least_squares, 0, 0, 0, 0, 0.0, 0.0, 0, 0, 0)
+                      opt.lo_starting_iterations, opt.final_least_squares, 0, 0, 0, 0, 0.0, 0.0, 0, 0, 0, 0)
         X = np.zeros(3)
         it = C.c_uint32()
         nlo = C.c_int()
@@ -163,4 +165,39 @@ def to_oracle_options(O, opt):
         of = ren.get(f, f)
         if hasattr(o, of):
             setattr(o, of, getattr(opt, f))
+    o.complex_mode = 2 if opt.complex_root_models == 1 else 0  # SSFM_COMPLEX_SKIP -> COMPLEX_SKIP, else canonical
     return o
+
+
+def check_full_path_goldens(S, g, run_case, stride=1):
+    """tests/golden/refsrc_golden.npz, full 3-point path (168 cases made by the reference's own sources in oracle/_ref).
+    run_case(rays, cfg, skip) -> ((status, iterations, inliers, lo_count), r, E, flags) for the implementation under test.
+      * "skip" goldens (complex action-matrix eigenvalues masked upstream): every case identical -- status, iteration
+        count, LO count, inlier flags -- and the pose within 0.01 deg.
+      * "up" goldens (upstream as written): identical exactly on the cases recorded in fu_same_canonical (the others are
+        the ones where a complex-eigenvalue model, whose phase upstream is rounding noise, wins an iteration)."""
+    import hashlib
+    cfgs = g["fu_cfg"]
+    followed, total = 0, 0
+    for k in range(0, len(cfgs), stride):
+        cfg = tuple(int(x) for x in cfgs[k])
+        n, nout, pid, inward, flsq, kind = cfg
+        pr = S.problems.make_problem(S.problems.make_rng(2026, pid), n, bool(inward), None, 1 / 600, nout, 20.0)
+        assert hashlib.sha256(np.ascontiguousarray(pr.rays).tobytes()).hexdigest() == str(g["fu_sha"][k])
+        for mode, skip in (("skip", True), ("up", False)):
+            st, r, E, flags = run_case(pr.rays, cfg, skip)
+            o0, o1 = g["fu_inl_off_" + mode][k], g["fu_inl_off_" + mode][k + 1]
+            gflags = np.unpackbits(g["fu_inl_" + mode][o0:o1])[:n]
+            same = tuple(int(x) for x in g["fu_stats_" + mode][k]) == tuple(int(x) for x in st) and (gflags == flags).all()
+            if mode == "skip":
+                assert same, (k, cfg, st, g["fu_stats_skip"][k])
+            else:
+                total += 1
+                followed += bool(same)
+                assert bool(same) == bool(g["fu_same_canonical"][k]), (k, cfg, st, g["fu_stats_up"][k])
+            if same:
+                d = S.problems.rot_error(S.problems.so3exp(g["fu_r_" + mode][k]), S.problems.so3exp(np.asarray(r)))
+                assert np.rad2deg(d) < 0.01
+                Eg = g["fu_E_" + mode][k]
+                assert model_dist(np.asarray(E) / np.linalg.norm(E), Eg / np.linalg.norm(Eg)) < 1e-5
+    print("full-path goldens: follows upstream-as-written on %d / %d cases, masked upstream on all" % (followed, total))

@@ -56,6 +56,7 @@ struct HsParams {
   float cand_margin;
   int32_t first_round, round_cap;
   int32_t defer;  // 1: use the deferred-refit protocol (requires num_lo_steps == 0)
+  int32_t skip_complex;  // SsfmOptions.complex_root_models == SSFM_COMPLEX_SKIP
 };
 
 struct HsResult {
@@ -71,15 +72,16 @@ void hs_sample(uint32_t seed, uint32_t pair, uint32_t iter, int k, int n, int* i
   philox_sample<8>(seed, pair, iter, k, n, idx);
 }
 
-int hs_solve(const double* rays, const int* sample, int kind, double* models) {
+int hs_solve(const double* rays, const int* sample, int kind, int skip_complex, double* models) {
+  const bool sk = skip_complex != 0;
   double m[4][6];
   const double* c0 = rays + 6 * (size_t)sample[0];
   const double* c1 = rays + 6 * (size_t)sample[1];
   const double* c2 = rays + 6 * (size_t)sample[2];
   int nm;
-  if (kind == 0) nm = solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
-  else if (kind == 1) nm = solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
-  else nm = solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+  if (kind == 0) nm = solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, sk);
+  else if (kind == 1) nm = solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, sk);
+  else nm = solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, sk);
   std::memcpy(models, m, sizeof(m));
   return nm;
 }
@@ -130,6 +132,7 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
   P.final_lsq = hp->final_lsq; P.solver = hp->solver; P.driver = hp->driver; P.inward = hp->inward;
   P.fixed_budget = hp->fixed_budget; P.fixed_prob = hp->fixed_prob; P.first_pair_id = 0;
   P.cand_margin = hp->cand_margin;
+  P.skip_complex = hp->skip_complex;
   PairState st;
   init_state(P, n, st);
   std::vector<int> la(n + 16), lb(n + 16);
@@ -159,9 +162,9 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
       const double* c0 = rays + 6 * (size_t)idx[0];
       const double* c1 = rays + 6 * (size_t)idx[1];
       const double* c2 = rays + 6 * (size_t)idx[2];
-      if (P.solver == 0) solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
-      else if (P.solver == 1) solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
-      else solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m);
+      if (P.solver == 0) solve_minimal<0>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, P.skip_complex != 0);
+      else if (P.solver == 1) solve_minimal<1>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, P.skip_complex != 0);
+      else solve_minimal<2>(c0, c0 + 3, c1, c1 + 3, c2, c2 + 3, m, P.skip_complex != 0);
       for (int k = 0; k < 24; ++k) models[(size_t)k * na + j] = (&m[0][0])[k];
       float pm[4];
       s32[j] = score_iteration_f32(&m[0][0], rays, n, (float)P.thr2, pm);

@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol(S):
     for n in names:
         assert hasattr(L, n), n
     assert sorted(S.EXPORTED_SYMBOLS) == names
-    assert L.ssfm_abi_version() == 1
+    assert L.ssfm_abi_version() == 2
 
 
 def test_built_for_sm_100a_with_tma(S):
@@ -41,7 +41,7 @@ def test_built_for_sm_100a_with_tma(S):
 
 def test_struct_layouts(S):
     assert C.sizeof(S.SsfmPairResult) == 168 and S.RESULT_DTYPE.itemsize == 168
-    assert C.sizeof(S.SsfmOptions) == 104
+    assert C.sizeof(S.SsfmOptions) == 112
     assert C.sizeof(S.SsfmBatch) == 32
 
 

@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import THR2, E_of, match_models, model_dist
+from conftest import THR2, E_of, check_full_path_goldens, match_models, model_dist
 
 
 def numpy_solutions(rays3):
@@ -77,9 +77,11 @@ def test_solver_matches_independent_numpy_solve(S, orc):
         # every real solution found by brute-force Newton is among the oracle's models
         for p in real:
             assert min(model_dist(p, m) for m in models) < 1e-7
-        # the polynomial and action-matrix variants agree on all four canonical models
+        # the polynomial and action-matrix variants agree on the models of real roots (those of complex roots differ by
+        # construction upstream: Re(y) of the Ferrari root vs the real part of a complex eigenvector)
         _, mp = orc.solve(pr.rays, [0, 1, 2], 1)
-        assert match_models(models, mp) < 1e-7 and match_models(mp, models) < 1e-7
+        _, mreal = orc.solve(pr.rays, [0, 1, 2], 0, 2)  # COMPLEX_SKIP: real eigenvalues only
+        assert match_models(mreal, mp) < 1e-7
 
 
 def test_models_satisfy_constraints_and_sample(S, orc):
@@ -287,13 +289,17 @@ def test_golden_vectors_from_reference_sources(S, O, orc):
         res, inl = orc.triangulate(cam[oc[a:b]], oxy[a:b], f, opt, p)
         assert (res.status, res.num_iterations, res.best_num_inliers) == (int(g["tri_status"][p]), int(g["tri_iters"][p]), int(g["tri_ninl"][p]))
         assert np.abs(np.array(res.E[:3]) - g["tri_points"][p]).max() <= 1e-6 * max(1.0, np.abs(g["tri_points"][p]).max())
-    for k in range(int(g["num_full"])):
-        res, inl = orc.estimate_pair(g["fu_rays_%d" % k], O.pipeline_options(THR2), int(g["fu_pid_%d" % k]))
-        assert (res.num_iterations, res.best_num_inliers, res.number_lo_iterations) == (
-            int(g["fu_iters_%d" % k]), int(g["fu_ninl_%d" % k]), int(g["fu_nlo_%d" % k]))
-        assert (inl == g["fu_inliers_%d" % k]).all()
-        d = S.problems.rot_error(S.problems.so3exp(g["fu_r_%d" % k]), S.problems.so3exp(np.array(res.r)))
-        assert np.rad2deg(d) < 0.01
+    check_full_path_goldens(S, g, lambda rays, cfg, skip: _oracle_full_case(O, orc, rays, cfg, skip))
+
+
+def _oracle_full_case(O, orc, rays, cfg, skip):
+    n, nout, pid, inward, flsq, kind = cfg
+    opt = O.default_options(squared_inlier_threshold=THR2, num_lo_steps=0, num_lsq_iterations=0, final_least_squares=flsq,
+                            inward=inward, solver_kind=kind, complex_mode=O.COMPLEX_SKIP if skip else O.COMPLEX_CANONICAL)
+    res, inl = orc.estimate_pair(rays, opt, pid)
+    f = np.zeros(n, np.uint8)
+    f[inl] = 1
+    return (res.status, res.num_iterations, res.best_num_inliers, res.number_lo_iterations), np.array(res.r), np.array(res.E), f
 
 
 def test_reference_generator_problems_and_metrics(S, O, orc):
@@ -382,34 +388,102 @@ def test_golden_vectors(S, O, orc):
 # src/spherical_estimator.cpp, src/spherical_solvers.cpp, src/so3.cpp, src/spherical_utils.cpp compiled
 # unmodified against stand-ins for Eigen and Ceres).
 # ---------------------------------------------------------------------------------------------------
-def _real_root_models(models):
-    """Models that are not duplicated: duplicates are conjugate complex pairs, whose representative
-    is implementation-defined in the reference."""
-    out = []
-    for i in range(4):
-        if np.isnan(models[i]).any():
-            continue
-        if any(j != i and model_dist(models[i], models[j]) < 1e-9 for j in range(4)):
-            continue
-        out.append(models[i])
-    return out
+def _action_matrix(S, rays3):
+    """The 4x4 action matrix M of a minimal sample (src/spherical_solvers.cpp:281-285), built independently in numpy:
+    null space by SVD, the six cubic constraints by fitting, G by a linear solve."""
+    u, v = rays3[:, :3], rays3[:, 3:]
+    A = np.stack([u[:, 0] * v[:, 0] - u[:, 1] * v[:, 1], u[:, 0] * v[:, 1] + u[:, 1] * v[:, 0], u[:, 2] * v[:, 0],
+                  u[:, 2] * v[:, 1], u[:, 0] * v[:, 2], u[:, 1] * v[:, 2]], 1)
+    B = np.linalg.svd(A)[2][3:].T
+
+    def T(b):
+        p = B @ b
+        E = E_of(p)
+        M3 = 2 * E @ E.T @ E - np.trace(E @ E.T) * E
+        return np.array([M3[1, 0], M3[2, 0], M3[0, 0], M3[2, 1], M3[1, 2], M3[2, 2]])
+    mon = lambda b: np.array([b[0] ** 3, b[0] ** 2 * b[1], b[0] * b[1] ** 2, b[1] ** 3, b[0] ** 2 * b[2], b[0] * b[1] * b[2],
+                              b[1] ** 2 * b[2], b[0] * b[2] ** 2, b[1] * b[2] ** 2, b[2] ** 3])
+    rng = np.random.default_rng(0)
+    pts = rng.standard_normal((40, 3))
+    Cm = np.linalg.lstsq(np.array([mon(b) for b in pts]), np.array([T(b) for b in pts]), rcond=None)[0].T
+    G = np.linalg.solve(Cm[:, :6], Cm[:, 6:])
+    M = np.zeros((4, 4))
+    M[0], M[1], M[2] = -G[2], -G[4], -G[5]
+    M[3, 1] = 1
+    return M
+
+
+def test_eigen_restatement_is_an_eigendecomposition(S, orc):
+    """oracle's Eigen::EigenSolver<Matrix4d> restatement against LAPACK: eigenvalues, M v = lambda v, unit columns,
+    conjugate pairs stored as (re + i im, re - i im) from one real column pair."""
+    rng = np.random.default_rng(5)
+    for tr in range(300):
+        M = rng.standard_normal((4, 4)) * rng.choice([1e-3, 1.0, 1e3])
+        if tr % 3 == 0:
+            M[3] = [0, 1, 0, 0]
+        ev, V, ok = orc.eigen34(M)
+        assert ok
+        want = np.linalg.eigvals(M)
+        for lam in ev:
+            assert np.min(np.abs(want - lam)) < 1e-9 * np.abs(want).max()
+        for k in range(4):
+            assert abs(np.linalg.norm(V[:, k]) - 1) < 1e-12
+            assert np.abs(M @ V[:, k] - ev[k] * V[:, k]).max() < 1e-9 * np.abs(M).max()
+            if ev[k].imag > 0:
+                assert ev[k + 1] == np.conj(ev[k]) and (V[:, k + 1] == np.conj(V[:, k])).all()
+
+
+def test_complex_root_models_are_ill_conditioned_upstream(S, orc):
+    """WHY models from complex eigenvalues of the action matrix cannot be pinned.  The reference returns
+    Re(eigenvector) (src/spherical_solvers.cpp:294-297); the phase of Eigen's complex eigenvector is fixed by the last
+    Francis sweeps, which act on a converged (rounding-noise sized) sub-diagonal.  Measured on Eigen 3.4's algorithm
+    restated: perturbing the action matrix by ONE ulp leaves real eigenvectors where they were (< 1e-9) and moves the real
+    part of complex ones by more than 1e-6 in over a quarter of the cases, by more than 1e-2 in some.  So two builds of
+    the reference itself (different compiler, FMA contraction, Eigen vectorisation) disagree on these models."""
+    moved_real, moved_cplx = [], []
+    for tr in range(400):
+        pr = S.problems.make_problem(S.problems.make_rng(33, tr), 6, False, None, 1 / 600, 0, 180.0)
+        M = _action_matrix(S, pr.rays[:3])
+        ev, V, ok = orc.eigen34(M)
+        rng = np.random.default_rng(tr)
+        M2 = M * (1 + rng.integers(-1, 2, (4, 4)) * 2.0 ** -52)
+        ev2, V2, ok2 = orc.eigen34(M2)
+        assert ok and ok2
+        for k in range(4):
+            a, b = V[1:, k].real, V2[1:, k].real
+            d = min(np.abs(a - b).max(), np.abs(a + b).max())
+            (moved_cplx if ev[k].imag != 0 else moved_real).append(d)
+    moved_real, moved_cplx = np.array(moved_real), np.array(moved_cplx)
+    print("1-ulp perturbation: real eigenvectors move by max %.1e (n=%d); Re(complex eigenvector) by median %.1e, "
+          "%.0f %% > 1e-6, %.0f %% > 1e-2 (n=%d)" % (moved_real.max(), len(moved_real), np.median(moved_cplx),
+                                                     100 * (moved_cplx > 1e-6).mean(), 100 * (moved_cplx > 1e-2).mean(), len(moved_cplx)))
+    assert len(moved_cplx) > 200 and len(moved_real) > 200
+    assert np.percentile(moved_real, 99) < 1e-9
+    assert (moved_cplx > 1e-6).mean() > 0.25 and (moved_cplx > 1e-2).mean() > 0.02
 
 
 @pytest.mark.parametrize("kind", [0, 1])
-def test_restated_solvers_match_reference_sources(S, orc, reffull, kind):
+def test_restated_solvers_match_reference_sources(S, O, orc, reffull, kind):
+    """Every model of every sample against src/spherical_solvers.cpp compiled in oracle/_ref.  Polynomial variant: all four
+    models, the Re(y) ones of complex Ferrari roots included (deterministic upstream, :73-83, :631-657).  Action matrix: all
+    models of real eigenvalues; with the complex ones masked on both sides the model sets are identical, NaN pattern included."""
     if reffull is None:
         pytest.skip("oracle/_ref not built")
     rng = S.problems.make_rng(21, kind)
-    worst = []
-    for tr in range(200):
+    worst, ncomplex = [], 0
+    for tr in range(300):
         pr = S.problems.make_problem(rng, 8, bool(tr % 3 == 0), None, 0.0 if tr % 2 == 0 else 1 / 600, 0, 180.0)
-        nmo, mo = orc.solve(pr.rays, [0, 1, 2], kind)
-        nmr, mr = reffull.solve(pr.rays, [0, 1, 2], kind)
+        mode = O.COMPLEX_SKIP if kind == 0 else O.COMPLEX_CANONICAL
+        nmo, mo = orc.solve(pr.rays, [0, 1, 2], kind, mode)
+        nmr, mr = reffull.solve(pr.rays, [0, 1, 2], kind, mode)
         assert nmo == nmr == 4
-        for m in _real_root_models(mo):
-            worst.append(min(model_dist(m, q) for q in mr))
+        no, nr = np.isnan(mo).any(axis=1), np.isnan(mr).any(axis=1)
+        assert no.sum() == nr.sum()
+        ncomplex += int(no.sum())
+        if (~no).any():
+            worst.append(max(match_models(mo, mr), match_models(mr, mo)))
     worst = np.array(worst)
-    assert len(worst) > 300
+    assert kind == 1 or ncomplex > 100
     assert np.median(worst) < 1e-13
     assert worst.max() < (1e-8 if kind == 0 else 1e-5)  # the reference's Ferrari quartic is the less accurate one
 
@@ -437,39 +511,49 @@ def test_restated_scoring_refit_geometry_match_reference_sources(S, orc, reffull
 
 
 REF_CASES = [
-    ("pipeline50", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 1000, 0.5, 8),
-    ("pipeline70", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 1500, 0.7, 4),
+    ("pipeline50", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 1000, 0.5, 24),
+    ("pipeline70", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 1500, 0.7, 16),
+    ("loopclosure70", dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=0), 1500, 0.7, 8),
     ("defaultLO", dict(), 400, 0.5, 4),
     ("vanilla", dict(driver=1), 400, 0.4, 6),
-    ("poly", dict(solver_kind=1, num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 400, 0.5, 4),
+    ("poly", dict(solver_kind=1, num_lo_steps=0, num_lsq_iterations=0, final_least_squares=1), 400, 0.5, 8),
 ]
+
+
+def _same_trajectory(a, ia, b, ib):
+    return (a.status == b.status and a.num_iterations == b.num_iterations and a.best_num_inliers == b.best_num_inliers and
+            a.number_lo_iterations == b.number_lo_iterations and len(ia) == len(ib) and bool((ia == ib).all()))
 
 
 @pytest.mark.parametrize("name,kw,n,outl,trials", REF_CASES)
 def test_restatement_follows_reference_sources_end_to_end(S, O, orc, reffull, name, kw, n, outl, trials):
-    """Whole-path agreement.  Where both follow the same trajectory (always, unless a model built from a
-    complex root pair -- implementation-defined upstream -- wins an early iteration) everything is
-    identical and E agrees to ~1e-15; otherwise the final poses still agree to a few hundredths of a degree."""
+    """Whole-path agreement with the reference's sources, no tolerance on the trajectory: with the models of complex
+    action-matrix eigenvalues masked on both sides (upstream's own commented-out filter; the only ill-posed piece, see
+    test_complex_root_models_are_ill_conditioned_upstream) EVERY pair gives the same iteration count, LO count and inlier
+    set, E to ~1e-15 and the pose within 0.01 deg.  Unmasked, a pair can only differ where such a model wins an iteration;
+    the fraction that does is printed (and pinned case by case in tests/golden/refsrc_golden.npz)."""
     if reffull is None:
         pytest.skip("oracle/_ref not built")
-    opt = O.default_options(squared_inlier_threshold=THR2, **kw)
-    exact = 0
+    followed = 0
     for p in range(trials):
         pr = S.problems.make_problem(S.problems.make_rng(7, p), n, False, None, 1 / 600, int(outl * n), 20.0)
+        opt = O.default_options(squared_inlier_threshold=THR2, complex_mode=O.COMPLEX_SKIP, **kw)
         a, ia = orc.estimate_pair(pr.rays, opt, p)
         b, ib = reffull.estimate_pair(pr.rays, opt, p)
         assert a.status == b.status == 0
-        same = (a.num_iterations == b.num_iterations and a.best_num_inliers == b.best_num_inliers and
-                a.number_lo_iterations == b.number_lo_iterations and len(ia) == len(ib) and (ia == ib).all())
-        if same:
-            exact += 1
-            # LM stops on Ceres' 1e-6 function tolerance, so long refit chains (default LO: 51 LMs per LO)
-            # amplify rounding differences between the two minimiser implementations to ~1e-7
-            assert model_dist(np.array(a.E) / np.linalg.norm(a.E), np.array(b.E) / np.linalg.norm(b.E)) < 1e-5
-            assert abs(a.best_model_score - b.best_model_score) <= 1e-6 * a.best_model_score
-            d = S.problems.rot_error(S.problems.so3exp(np.array(a.r)), S.problems.so3exp(np.array(b.r)))
-            assert np.rad2deg(d) < 0.01
+        assert _same_trajectory(a, ia, b, ib), (name, p)
+        # LM stops on Ceres' 1e-6 function tolerance, so long refit chains (default LO: 51 LMs per LO)
+        # amplify rounding differences between the two minimiser implementations to ~1e-7
+        assert model_dist(np.array(a.E) / np.linalg.norm(a.E), np.array(b.E) / np.linalg.norm(b.E)) < 1e-5
+        assert abs(a.best_model_score - b.best_model_score) <= 1e-6 * a.best_model_score
+        d = S.problems.rot_error(S.problems.so3exp(np.array(a.r)), S.problems.so3exp(np.array(b.r)))
+        assert np.rad2deg(d) < 0.01
+        if kw.get("solver_kind", 0) == 0:
+            opt.complex_mode = O.COMPLEX_CANONICAL
+            a, ia = orc.estimate_pair(pr.rays, opt, p)
+            opt.complex_mode = O.COMPLEX_EIGEN
+            b, ib = reffull.estimate_pair(pr.rays, opt, p)
+            followed += _same_trajectory(a, ia, b, ib)
         else:
-            d = S.problems.rot_error(S.problems.so3exp(np.array(a.r)), S.problems.so3exp(np.array(b.r)))
-            assert np.rad2deg(d) < 0.1 and abs(a.best_num_inliers - b.best_num_inliers) <= 0.02 * n
-    assert exact >= 0.6 * trials
+            followed += 1
+    print("%s: canonical-representative oracle follows upstream-as-written on %d / %d pairs" % (name, followed, trials))
