@@ -130,6 +130,24 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def validate_table(S, res, R_gt, N, sample=4096):
+    """Sanity of a timed result table against the synthetic ground truth: status histogram, rotation error of the
+    recovered poses, inlier counts.  Raises if the run is broken (the bench line is then not printed)."""
+    P = len(res)
+    hist = {int(k): int(v) for k, v in zip(*np.unique(res["status"], return_counts=True))}
+    idx = np.linspace(0, P - 1, min(P, sample)).astype(np.int64)
+    errs = np.array([np.rad2deg(S.problems.rot_error(R_gt[p], S.problems.so3exp(res["r"][p]))) for p in idx if res["status"][p] == 0])
+    out = {"pairs": P, "status_histogram": hist, "pairs_checked_against_ground_truth": int(len(errs)),
+           "median_rotation_error_deg": float(np.median(errs)) if len(errs) else None,
+           "fraction_within_0.5deg": float((errs < 0.5).mean()) if len(errs) else None,
+           "median_inlier_ratio": float(np.median(res["best_num_inliers"] / float(N))),
+           "iterations_min_mean_max": [int(res["num_iterations"].min()), float(res["num_iterations"].mean()), int(res["num_iterations"].max())]}
+    ok = (hist.get(0, 0) >= 0.99 * P and len(errs) > 0 and out["median_rotation_error_deg"] < 0.1 and out["fraction_within_0.5deg"] > 0.98)
+    if not ok:
+        raise SystemExit("bench.py: the timed run produced a broken result table: %s" % json.dumps(out))
+    return out
+
+
 def cpu_leg(pairs_rays, N, seconds_target, threads=0):
     """Times the CPU path on a bounded sample.  Only this function (and the tests / smoke) touches oracle/."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -167,6 +185,182 @@ def cpu_leg(pairs_rays, N, seconds_target, threads=0):
     }
 
 
+def config_block(S, eng, fp32_peak, args):
+    """Per-config measurements (BASELINE.json configs[0,1,3,4]); the headline line is configs[2].  Every entry names its
+    dominant kernel and carries the same path timed on the host (oracle/), on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    orc = O.load()
+    cores = os.cpu_count() or 1
+    out = {}
+
+    def stage_share(st):
+        tot = max(st.solve_ms + st.score_ms + st.chain_ms, 1e-9)
+        parts = {"k_sample_solve": st.solve_ms, "k_score_rounds": st.score_ms, "k_chain+refits": st.chain_ms}
+        k = max(parts, key=parts.get)
+        return {"dominant": k, "dominant_frac_of_device_time": parts[k] / tot, "solve_ms": st.solve_ms, "score_ms": st.score_ms,
+                "chain_ms": st.chain_ms}
+
+    # ---- C1: evaluation/test_random_problems shape -- ONE pair, 1000 corr, 50 % outliers, calibrated solver: latency of a
+    # single EstimateModel through the boundary (what GpuSphericalEstimator + LocallyOptimizedMSAC cost per call)
+    rays1, offs1, _ = S.problems.make_batch(1234, 1, 1000, noise=1 / 600, outlier_frac=0.5, max_angle_deg=20.0)
+    opt1 = S.pipeline_options(THR2)
+    eng.estimate_pairs(rays1, offs1, opt1)
+    lat = []
+    for _ in range(20):
+        t0 = time.perf_counter()
+        r1, _ = eng.estimate_pairs(rays1, offs1, opt1)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        o1, _ = orc.estimate_pair(rays1, O.pipeline_options(THR2), 0)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / reps
+    out["C1"] = {"workload": "1 pair x 1000 corr, 50 % outliers, action-matrix, LO-MSAC pipeline options; host buffers in/out",
+                 "latency_ms_median": float(np.median(lat)), "latency_ms_min": float(np.min(lat)), "iterations": int(r1["num_iterations"][0]),
+                 "evals_per_sec": float(r1["evals"][0]) / (np.median(lat) * 1e-3), **stage_share(eng.stats()),
+                 "cpu": {"latency_ms": cpu_ms, "cores": 1, "kind": "port", "same_iterations": int(o1.num_iterations) == int(r1["num_iterations"][0])},
+                 "note": "latency-bound: one pair cannot fill 148 SMs; the batched entry exists for this reason"}
+
+    # ---- C2: sequential video, 1999 adjacent pairs x 2000 corr, Sturm-variant solver, legacy MSAC with a fixed budget M = 512
+    P2, N2 = 1999, 2000
+    rays2, offs2, _ = S.problems.make_batch(2, P2, N2, noise=1 / 600, outlier_frac=0.3, rotation_deg=1.0)
+    opt2 = S.default_options(squared_inlier_threshold=THR2, driver=S.DRIVER_MSAC_FIXED, solver=S.SOLVER_FAST_STURM, fixed_budget=512)
+    eng.upload(rays2, offs2)
+    eng.run(opt2)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.run(opt2)
+    ms2 = (time.perf_counter() - t0) * 1e3 / 3
+    st2 = eng.stats()
+    r2, _ = eng.download(want_flags=False)
+    t0 = time.perf_counter()
+    eng.estimate_pairs(rays2, offs2, opt2)
+    ms2e = (time.perf_counter() - t0) * 1e3
+    oo = O.default_options(squared_inlier_threshold=THR2, driver=2, solver_kind=2, legacy_budget=512)
+    nc = P2
+    _, secs = orc.estimate_batch(rays2[:nc * N2], offs2[:nc + 1], oo, 0, cores)
+    _, secs = orc.estimate_batch(rays2[:nc * N2], offs2[:nc + 1], oo, 0, cores)
+    out["C2"] = {"workload": "1999 pairs x 2000 corr, 30 % outliers, 1 deg rotation, fast/Sturm solver, MSAC_FIXED M=512",
+                 "ms": ms2, "pairs_per_sec": P2 / (ms2 * 1e-3), "evals_per_sec": float(r2["evals"].sum()) / (ms2 * 1e-3),
+                 "e2e_ms": ms2e, "e2e_pairs_per_sec": P2 / (ms2e * 1e-3), "mean_iterations": float(r2["num_iterations"].mean()),
+                 **stage_share(st2),
+                 "cpu": {"pairs_per_sec": nc / secs, "cores": cores, "kind": "port", "sample": "%d pairs in %.2f s" % (nc, secs)}}
+
+    # ---- C4: full config -- 20 000 pairs x 1000 corr, six-point shared-focal estimator under VanillaMSAC
+    P4 = 20000
+    rays4, offs4, f4, _, _ = S.problems.make_sixpt_batch(4, P4, 1000)
+    opt4 = S.default_options(squared_inlier_threshold=4.0, driver=S.DRIVER_VANILLA_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
+                             sixpt_focal_scoring=1, random_seed=1234)
+    eng.upload(rays4, offs4)
+    eng.run(opt4)
+    t0 = time.perf_counter()
+    eng.run(opt4)
+    ms4 = (time.perf_counter() - t0) * 1e3
+    st4 = eng.stats()
+    r4, _ = eng.download(want_flags=False)
+    c4 = {"workload": "20000 pairs x 1000 corr, 50 % outliers, six-point shared focal, VanillaMSAC", "ms": ms4,
+          "pairs_per_sec": P4 / (ms4 * 1e-3), "evals_per_sec": float(r4["evals"].sum()) / (ms4 * 1e-3),
+          "mean_iterations": float(r4["num_iterations"].mean()), "focal_within_50pct": float((np.abs(r4["focal"] / f4 - 1) < 0.5).mean()),
+          **{k.replace("k_sample_solve", "k_sixpt_sample_solve").replace("k_score_rounds", "k_sixpt_score").replace("k_chain+refits", "k_sixpt_chain"): v
+             for k, v in stage_share(st4).items()}}
+    c4["dominant"] = {"k_sample_solve": "k_sixpt_sample_solve", "k_score_rounds": "k_sixpt_score", "k_chain+refits": "k_sixpt_chain"}[c4["dominant"]]
+    try:
+        import sixpt_oracle as SO
+        t0 = time.perf_counter()
+        npairs_cpu = 0
+        while time.perf_counter() - t0 < 6.0 and npairs_cpu < 8:
+            pid, n4 = npairs_cpu, int(offs4[npairs_cpu + 1] - offs4[npairs_cpu])
+            SO.vanilla_msac(rays4[offs4[pid]:offs4[pid + 1]], lambda it: orc.philox_sample(1234, pid, it, 6, n4), 4.0, focal_scoring=True)
+            npairs_cpu += 1
+        secs = time.perf_counter() - t0
+        c4["cpu"] = {"pairs_per_sec": npairs_cpu / secs, "cores": 1, "kind": "port (numpy + LAPACK restatement; PoseLib itself is absent)",
+                     "sample": "%d pairs in %.1f s" % (npairs_cpu, secs)}
+    except Exception as exc:
+        c4["cpu"] = {"error": repr(exc)}
+    out["C4"] = c4
+    del rays4
+
+    # ---- C5 as specified: 8 pairs x {10k, 20k, 50k, 100k, 200k} corr x 4096 hypotheses, 90 % outliers, scoring kernel only
+    c5 = {"workload": "8 pairs x N corr x 4096 hypotheses (1024 Philox samples x 4 roots), 90 % outliers, k_score_models", "sweep": []}
+    for n5 in (10000, 20000, 50000, 100000, 200000):
+        rays5, offs5, _ = S.problems.make_batch(500, 8, n5, noise=1 / 600, outlier_frac=0.9)
+        m5 = np.zeros((8, 4096, 6))
+        for pr_i in range(8):
+            samples = np.array([S.sample(3, pr_i, i, 3, n5) for i in range(1024)], np.int32)
+            mm, _ = eng.minimal_solve(rays5[offs5[pr_i]:offs5[pr_i + 1]], samples, 0)
+            m5[pr_i] = mm.reshape(-1, 6)
+        _, _, ms5 = eng.score_pairs(m5, rays5, offs5, THR2)  # ONE launch for the 8 pairs
+        ev = 8 * 4096.0 * n5
+        entry = {"corr": n5, "kernel_ms_8_pairs": ms5, "evals_per_sec": ev / (ms5 * 1e-3),
+                 "fp32_frac": ev * FLOP_PER_EVAL / (ms5 * 1e-3) / 1e12 / fp32_peak}
+        if n5 == 200000:
+            sub = m5[7][: 4 * cores]
+            _, _, secs = orc.score_batch(sub, rays5[offs5[7]:], THR2, cores)
+            entry["cpu"] = {"evals_per_sec": len(sub) * float(n5) / secs, "cores": cores, "kind": "port"}
+        c5["sweep"].append(entry)
+    c5["dominant"] = "k_score_models"
+    out["C5"] = c5
+    return out
+
+
+def strong_scaling_leg(S, torch, dist, eng, args, rank, world, table_1gpu, barrier):
+    """Strong scaling: ONE C3 batch (the one rank 0 processed alone in the weak leg: seed 1234) split over the ranks by
+    ssfm_partition_pairs; each rank runs its shard end to end from pinned host memory (H2D inside the timed region), the
+    per-pair records are all-gathered with NCCL, and rank 0 checks that the gathered table is byte-identical to the table
+    it computed on one GPU.  Returns the dict for the bench line (rank 0) or None."""
+    P, N = args.pairs, args.corr
+    rays_dev, offsets, _ = make_batch_torch(P, N, args.outliers, 1234, "cuda")  # same generator state on every rank
+    bounds = S.partition_pairs(offsets, world)
+    p0, p1 = bounds[rank], bounds[rank + 1]
+    c0, c1 = int(offsets[p0]), int(offsets[p1])
+    shard_host = torch.empty((c1 - c0, 6), dtype=torch.float64, pin_memory=True)
+    shard_host.copy_(rays_dev[c0:c1])
+    del rays_dev
+    torch.cuda.empty_cache()
+    shard_np = shard_host.numpy()
+    shard_offs = offsets[p0:p1 + 1] - c0
+    opt = S.pipeline_options(THR2, first_pair_id=p0)
+    maxn = max(bounds[i + 1] - bounds[i] for i in range(world))
+    item = S.RESULT_DTYPE.itemsize
+    out_res = torch.empty(max(p1 - p0, 1) * item, dtype=torch.uint8, pin_memory=True).numpy().view(S.RESULT_DTYPE)[:p1 - p0]
+
+    class _Dev:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    send = torch.zeros(maxn * item, dtype=torch.uint8, device="cuda")
+    outs = [torch.empty_like(send) for _ in range(world)]
+
+    def step():
+        eng.estimate_pairs(shard_np, shard_offs, opt, want_flags=False, out_results=out_res)
+        ptr, n = eng.device_results()
+        send[:n * item].copy_(torch.as_tensor(_Dev(ptr, n * item), device="cuda"))
+        dist.all_gather(outs, send)
+
+    steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank != 0:
+        return None
+    gathered = np.concatenate([outs[r].cpu().numpy()[:(bounds[r + 1] - bounds[r]) * item] for r in range(world)]).view(S.RESULT_DTYPE)
+    same = gathered.tobytes() == table_1gpu.tobytes()
+    useful = float(table_1gpu["evals"].sum())
+    return {"scaling": "strong", "pairs_total": P, "ms_per_step": ms, "pairs_per_sec": P / (ms * 1e-3), "value": useful / (ms * 1e-3),
+            "unit": "evals/s", "steps": steps, "shard_pairs": [bounds[i + 1] - bounds[i] for i in range(world)],
+            "timed_region": "H2D of each rank's shard from pinned host memory + all kernels + D2H of the records + NCCL all-gather",
+            "gathered_table_byte_identical_to_single_gpu": bool(same)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,6 +373,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (from_matches, C5, C4); sweeps only")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -223,7 +418,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- synthetic inputs: generated on the GPU, then moved to pinned host memory ----
-    rays_dev, offsets, _ = make_batch_torch(P, N, args.outliers, 1234 + rank, "cuda")
+    rays_dev, offsets, R_gt = make_batch_torch(P, N, args.outliers, 1234 + rank, "cuda")
+    R_gt = R_gt.cpu().numpy()
     rays_host = torch.empty(rays_dev.shape, dtype=torch.float64, pin_memory=True)
     rays_host.copy_(rays_dev)
     del rays_dev
@@ -244,6 +440,8 @@ def main():
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
+    gathered = {}
+
     def gather_tables():
         if dist is None:
             return
@@ -251,6 +449,7 @@ def main():
         t = torch.as_tensor(_Dev(ptr, n * S.RESULT_DTYPE.itemsize), device="cuda")
         outs = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(outs, t)
+        gathered["tables"] = outs
 
     # ---- resident-in-HBM throughput (value) ----
     eng.upload(rays_np, offsets)
@@ -277,6 +476,7 @@ def main():
     clocks = sampler.stop()
     res, _ = eng.download(want_flags=False)
     useful = int(res["evals"].sum())
+    validation = validate_table(S, res, R_gt, N)  # a silently broken run must not print a number
     step_ms = wall_s * 1e3 / args.steps  # wall clock around device-synchronised steps (includes round syncs)
     dev_step_ms = dev_ms / args.steps
 
@@ -295,6 +495,10 @@ def main():
     e2e_s = (time.perf_counter() - t0) / args.steps
     st = eng.stats()
 
+    strong = None
+    if dist is not None and not args.no_strong:
+        strong = strong_scaling_leg(S, torch, dist, eng, args, rank, world, res if rank == 0 else None, barrier)
+
     t_step = torch.tensor([step_ms, e2e_s * 1e3, float(useful), dev_step_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         tmax = t_step.clone()
@@ -305,10 +509,22 @@ def main():
         useful_total = float(tsum[2])
     else:
         e2e_ms, useful_total = e2e_s * 1e3, float(useful)
+    # the gathered table is checked, not dropped: every rank's block must equal what that rank downloaded itself
+    gather_ok = None
+    if dist is not None:
+        mine = torch.from_numpy(res_e2e.view(np.uint8).reshape(-1).copy()).cuda()
+        blocks = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(blocks, mine)  # reference copy of every rank's own table (not timed)
+        gather_ok = all(bool(torch.equal(gathered["tables"][r], blocks[r])) for r in range(world))
+        flag = torch.tensor([1 if gather_ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    if gather_ok is False:
+        raise SystemExit("bench.py: the all-gathered result tables differ from the ranks' own tables")
 
     value = useful_total / (step_ms * 1e-3)
     score_ms_per_launch = agg["score_ms"] / max(1, agg["score_launches"])
@@ -339,6 +555,9 @@ def main():
         "e2e": {"value": useful_total / (e2e_ms * 1e-3), "unit": "evals/s", "pairs_per_sec": world * P / (e2e_ms * 1e-3),
                 "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(st.h2d_bytes), "d2h_bytes_per_step": int(st.d2h_bytes)},
         "gpu_launches": int(agg["launches"]),
+        "validation": validation,
+        "gathered_tables_verified": gather_ok,
+        "strong_scaling": strong,
         "clocks": clocks,
         "roofline": {"bound": "fp32", "kernel": "k_score_rounds", "achieved": achieved_tflops, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": achieved_tflops / fp32_peak, "traffic": traffic,
@@ -385,39 +604,11 @@ def main():
         del kp_all, mt_all, mt_pin, rt
     except Exception as exc:
         line["e2e_from_matches"] = {"error": str(exc)}
-    # config C5 (scoring stress: 4096 hypotheses x 200k correspondences, 90 % outliers), scoring kernel only
+    # BASELINE.json configs other than the headline one: C1, C2, full C4, C5 as specified -- each with a CPU figure beside it
     try:
-        n5 = 200000
-        rays5_t, _, _ = make_batch_torch(1, n5, 0.9, 99, "cuda")
-        rays5 = rays5_t.cpu().numpy()
-        samples = np.array([S.sample(3, 0, i, 3, n5) for i in range(1024)], np.int32)
-        m5, _ = eng.minimal_solve(rays5, samples, 0)
-        _, _, ms5 = eng.score(m5.reshape(-1, 6), rays5, THR2)
-        line["c5_scoring"] = {"hypotheses": 4096, "corr": n5, "kernel_ms": ms5, "evals_per_sec": 4096.0 * n5 / (ms5 * 1e-3),
-                              "fp32_frac": 4096.0 * n5 * FLOP_PER_EVAL / (ms5 * 1e-3) / 1e12 / fp32_peak}
-    except Exception as exc:  # the headline line must not die on the side measurement
-        line["c5_scoring"] = {"error": str(exc)}
-    # config C4 (six-point shared-focal estimator under VanillaMSAC, 1000 corr/pair, 50 % outliers): a 2000-pair
-    # slice of the 20 000-pair configuration, inputs resident
-    try:
-        P4 = 2000
-        rays4, offs4, f4, _, _ = S.problems.make_sixpt_batch(4, P4, 1000)
-        opt4 = S.default_options(squared_inlier_threshold=4.0, driver=S.DRIVER_VANILLA_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
-                                 sixpt_focal_scoring=1, random_seed=1234)
-        eng.upload(rays4, offs4)
-        eng.run(opt4)
-        t0 = time.perf_counter()
-        eng.run(opt4)
-        ms4 = (time.perf_counter() - t0) * 1e3
-        st4 = eng.stats()
-        r4, _ = eng.download(want_flags=False)
-        line["c4_sixpt"] = {"pairs": P4, "corr": 1000, "ms": ms4, "pairs_per_sec": P4 / (ms4 * 1e-3),
-                            "evals_per_sec": float(r4["evals"].sum()) / (ms4 * 1e-3), "mean_iterations": float(r4["num_iterations"].mean()),
-                            "solve_ms": st4.solve_ms, "score_ms": st4.score_ms, "chain_ms": st4.chain_ms,
-                            "focal_within_50pct": float((np.abs(r4["focal"] / f4 - 1) < 0.5).mean())}
-        del rays4
-    except Exception as exc:
-        line["c4_sixpt"] = {"error": str(exc)}
+        line["configs"] = config_block(S, eng, fp32_peak, args)
+    except Exception as exc:  # the headline line must not die on a side measurement
+        line["configs"] = {"error": repr(exc)}
     # SfM::Retriangulate: 200 000 points, ragged tracks of 3..30 observations, 20 % outliers,
     # RansacLib's default LO schedule; host buffers in, host buffers out
     try:

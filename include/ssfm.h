@@ -203,6 +203,27 @@ typedef struct SsfmTrackBatch {
 int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* tracks, const SsfmOptions* opt, double* points_xyz,
                        int32_t* num_inliers, int32_t* status, uint32_t* num_iterations);
 
+/* ---- one batch, N devices, one process (north_star: "image pairs shard with no cross-pair dependence across the 8 GPUs") ----
+ * The reference caller is a single process whose OpenMP loop walks all i<j pairs (examples/spherical_sfm_tools.cpp:321-332).
+ * ssfm_estimate_pairs_multi is that call fanned out over GPUs: contiguous shards balanced by correspondence count
+ * (ssfm_partition_pairs), one host thread + one engine per device, results written straight into the caller's table.
+ * There is no data-path collective, and the table is byte-identical to the single-device one (pair p keeps Philox key
+ * (random_seed, first_pair_id + p) wherever it runs).  Host rays only. */
+typedef struct ssfm_multi* ssfm_multi_handle;
+int ssfm_multi_create(const int32_t* devices, int32_t num_devices, ssfm_multi_handle* out);
+void ssfm_multi_destroy(ssfm_multi_handle m);
+int32_t ssfm_multi_num_devices(ssfm_multi_handle m);
+/* num_shards + 1 pair bounds: shard r = pairs [bounds[r], bounds[r+1]), equal shares of the correspondences. */
+int ssfm_partition_pairs(const int64_t* offsets, int32_t num_pairs, int32_t num_shards, int32_t* bounds);
+int ssfm_estimate_pairs_multi(ssfm_multi_handle m, const SsfmBatch* batch, const SsfmOptions* opt, SsfmPairResult* results,
+                              uint8_t* inlier_flags);
+/* Stats of device `index` in the last multi call, and the shard it ran (first_pair / num_pairs may be NULL). */
+int ssfm_multi_get_stats(ssfm_multi_handle m, int32_t index, SsfmRunStats* stats, int32_t* first_pair, int32_t* num_pairs);
+/* For device-side consumers of the whole table: all-gather-v of the per-pair records over NVLink/NVSwitch (NCCL, loaded
+ * with dlopen on first use).  dev_tables: num_devices device pointers, each to num_pairs x SsfmPairResult in global pair
+ * order, owned by the handle and valid until the next multi call. */
+int ssfm_multi_allgather_results(ssfm_multi_handle m, void** dev_tables, int32_t* num_pairs);
+
 /* The same call split into its three stages, so inputs can stay resident in HBM:
  * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */
 int ssfm_upload(ssfm_handle h, const SsfmBatch* batch);
@@ -238,6 +259,11 @@ int ssfm_minimal_solve_opt(ssfm_handle h, const double* rays, int32_t n, const i
  * models6: num_models x 6 doubles (host).  scores: MSAC cost (float), counts: err < thr^2. */
 int ssfm_score(ssfm_handle h, const double* models6, int32_t num_models, const double* rays, int32_t n,
                double squared_threshold, float* scores, int32_t* counts, float* kernel_ms);
+/* The same for several pairs in ONE launch (config C5: 8 pairs x 4096 hypotheses x 10k-200k correspondences): pair p owns
+ * correspondences [offsets[p], offsets[p+1]) of `rays` and the models models6[p][num_models][6]; scores / counts are
+ * [num_pairs][num_models].  kernel_ms: device time of the scoring + reduction launches (after a warm-up launch). */
+int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t num_models, const double* rays, const int64_t* offsets,
+                     int32_t num_pairs, double squared_threshold, float* scores, int32_t* counts, float* kernel_ms);
 /* Same quantities from the FP64 certification path (bit-compatible with the reference's arithmetic). */
 int ssfm_score_exact(ssfm_handle h, const double* E9, int32_t num_models, const double* rays, int32_t n,
                      double squared_threshold, double* scores, int32_t* counts);

@@ -91,6 +91,23 @@ class Engine {
   ssfm_handle h_ = nullptr;
 };
 
+// RAII handle over several GPUs of one box (ssfm_multi_create): one engine per device, one batch per call.
+class MultiEngine {
+ public:
+  explicit MultiEngine(const std::vector<int>& devices) {
+    std::vector<int32_t> d(devices.begin(), devices.end());
+    check(ssfm_multi_create(d.data(), (int32_t)d.size(), &h_));
+  }
+  ~MultiEngine() { ssfm_multi_destroy(h_); }
+  MultiEngine(const MultiEngine&) = delete;
+  MultiEngine& operator=(const MultiEngine&) = delete;
+  ssfm_multi_handle get() const { return h_; }
+  int num_devices() const { return ssfm_multi_num_devices(h_); }
+
+ private:
+  ssfm_multi_handle h_ = nullptr;
+};
+
 namespace detail {
 template <class Matrix3>
 inline void to_rowmajor(const Matrix3& E, double* out) {
@@ -485,10 +502,34 @@ struct PreemptiveRANSAC {  // include/sphericalsfm/preemptive_ransac.h:30-139
 // The new batched-pairs entry point: one call for all pairs (replaces the OpenMP loop).
 // pair_lists: one RayPairList per image pair.  results: one SsfmPairResult per pair;
 // inlier_flags (optional): concatenated 0/1 flags in pair order.
+namespace detail {
+template <class Options, class RayPairList, class Call>
+inline void estimate_pairs_impl(const Options& options, const std::vector<RayPairList>& pair_lists, bool use_poly_solver, bool inward,
+                                std::vector<SsfmPairResult>* results, std::vector<uint8_t>* inlier_flags, Call call);
+}
 template <class Options, class RayPairList>
 inline void EstimatePairs(const Engine& eng, const Options& options, const std::vector<RayPairList>& pair_lists,
                           bool use_poly_solver, bool inward, std::vector<SsfmPairResult>* results,
                           std::vector<uint8_t>* inlier_flags = nullptr) {
+  detail::estimate_pairs_impl(options, pair_lists, use_poly_solver, inward, results, inlier_flags,
+                              [&](const SsfmBatch* b, const SsfmOptions* o, SsfmPairResult* r, uint8_t* f) {
+                                return ssfm_estimate_pairs(eng.get(), b, o, r, f);
+                              });
+}
+// The same over all GPUs of the handle: shards of the pair list, one per device; identical table.
+template <class Options, class RayPairList>
+inline void EstimatePairs(const MultiEngine& eng, const Options& options, const std::vector<RayPairList>& pair_lists,
+                          bool use_poly_solver, bool inward, std::vector<SsfmPairResult>* results,
+                          std::vector<uint8_t>* inlier_flags = nullptr) {
+  detail::estimate_pairs_impl(options, pair_lists, use_poly_solver, inward, results, inlier_flags,
+                              [&](const SsfmBatch* b, const SsfmOptions* o, SsfmPairResult* r, uint8_t* f) {
+                                return ssfm_estimate_pairs_multi(eng.get(), b, o, r, f);
+                              });
+}
+template <class Options, class RayPairList, class Call>
+inline void detail::estimate_pairs_impl(const Options& options, const std::vector<RayPairList>& pair_lists, bool use_poly_solver,
+                                        bool inward, std::vector<SsfmPairResult>* results, std::vector<uint8_t>* inlier_flags,
+                                        Call call) {
   SsfmOptions o = detail::to_c_options(options);
   o.solver = use_poly_solver ? SSFM_SOLVER_POLYNOMIAL : SSFM_SOLVER_ACTION_MATRIX;
   o.inward = inward ? 1 : 0;
@@ -505,7 +546,7 @@ inline void EstimatePairs(const Engine& eng, const Options& options, const std::
   b.rays_on_device = 0;
   results->resize(pair_lists.size());
   if (inlier_flags) inlier_flags->assign((size_t)offsets.back(), 0);
-  check(ssfm_estimate_pairs(eng.get(), &b, &o, results->data(), inlier_flags ? inlier_flags->data() : nullptr));
+  check(call(&b, &o, results->data(), inlier_flags ? inlier_flags->data() : nullptr));
 }
 
 // SfM::Retriangulate (src/sfm.cpp:156-192) for all points in one call.  camera_tr[i] = {t, r} of GetPose(i);

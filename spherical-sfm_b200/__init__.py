@@ -18,7 +18,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 LIB_PATH = os.environ.get("SSFM_LIB_PATH", os.path.join(_DIR, "libssfm_b200.so"))  # override: profiling builds
-_MAIN_SOURCE = os.path.join(_DIR, "csrc", "ssfm_engine.cu")
+_UNITS = [os.path.join(_DIR, "csrc", f) for f in ("ssfm_engine.cu", "ssfm_multi.cu")]  # translation units
 
 
 def _sources():
@@ -111,7 +111,7 @@ def build_extension(force=False, verbose=False):
     newest = max(os.path.getmtime(s) for s in _sources())
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, _MAIN_SOURCE]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _UNITS + ["-ldl"]
     subprocess.check_call(cmd, cwd=_DIR)
     return LIB_PATH
 
@@ -138,8 +138,10 @@ def lib():
 EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
-    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
+    "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_pairs", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
+    "ssfm_multi_create", "ssfm_multi_destroy", "ssfm_multi_num_devices", "ssfm_partition_pairs", "ssfm_estimate_pairs_multi",
+    "ssfm_multi_get_stats", "ssfm_multi_allgather_results",
 ]
 
 
@@ -347,6 +349,20 @@ class Engine:
                                 _p(scores, C.c_float), _p(counts, C.c_int32), C.byref(ms)))
         return scores, counts, ms.value
 
+    def score_pairs(self, models6, rays, offsets, thr2):
+        """ssfm_score_pairs: models6 (P, M, 6) against P pairs (CSR offsets) in one launch -> (scores (P, M), counts, ms)."""
+        models6 = np.ascontiguousarray(models6, np.float64)
+        Pn, M = models6.shape[0], models6.shape[1]
+        rays = np.ascontiguousarray(rays, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        assert len(offsets) == Pn + 1
+        scores = np.zeros((Pn, M), np.float32)
+        counts = np.zeros((Pn, M), np.int32)
+        ms = C.c_float()
+        _check(lib().ssfm_score_pairs(self._h, _p(models6, C.c_double), M, _p(rays, C.c_double), _p(offsets, C.c_int64), Pn,
+                                      C.c_double(thr2), _p(scores, C.c_float), _p(counts, C.c_int32), C.byref(ms)))
+        return scores, counts, ms.value
+
     def score_exact(self, E9, rays, thr2):
         E9 = np.ascontiguousarray(E9, np.float64).reshape(-1, 9)
         rays = np.ascontiguousarray(rays, np.float64)
@@ -410,6 +426,58 @@ class Engine:
         t = C.c_double()
         _check(lib().ssfm_measure_fp32_peak(self._h, C.byref(t)))
         return t.value
+
+
+def partition_pairs(offsets, num_shards):
+    """ssfm_partition_pairs: num_shards + 1 pair bounds, equal shares of the correspondences (host function)."""
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    bounds = np.zeros(num_shards + 1, np.int32)
+    _check(lib().ssfm_partition_pairs(_p(offsets, C.c_int64), len(offsets) - 1, int(num_shards), _p(bounds, C.c_int32)))
+    return bounds.tolist()
+
+
+class MultiEngine:
+    """One batch, N devices, one process (ssfm_estimate_pairs_multi)."""
+
+    def __init__(self, devices):
+        devs = np.ascontiguousarray(list(devices), np.int32)
+        self._h = C.c_void_p()
+        self.devices = devs.tolist()
+        _check(lib().ssfm_multi_create(_p(devs, C.c_int32), len(devs), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ssfm_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def estimate_pairs(self, rays, offsets, opt, want_flags=True, out_results=None, out_flags=None):
+        rays = np.ascontiguousarray(rays, np.float64)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0)
+        res = out_results if out_results is not None else np.zeros(b.num_pairs, RESULT_DTYPE)
+        flags = (out_flags if out_flags is not None else np.zeros(int(offsets[-1]), np.uint8)) if want_flags else None
+        _check(lib().ssfm_estimate_pairs_multi(self._h, C.byref(b), C.byref(opt), C.c_void_p(res.ctypes.data),
+                                               C.c_void_p(flags.ctypes.data) if want_flags and len(flags) else None))
+        return res, flags
+
+    def stats(self, index):
+        s = SsfmRunStats()
+        p0, n = C.c_int32(), C.c_int32()
+        _check(lib().ssfm_multi_get_stats(self._h, int(index), C.byref(s), C.byref(p0), C.byref(n)))
+        return s, p0.value, n.value
+
+    def allgather_results(self):
+        """Device pointers (one per device) to the whole result table in global pair order, and the pair count."""
+        ptrs = (C.c_void_p * len(self.devices))()
+        n = C.c_int32()
+        _check(lib().ssfm_multi_allgather_results(self._h, ptrs, C.byref(n)))
+        return [p for p in ptrs], n.value
 
 
 from . import problems  # noqa: E402,F401

@@ -522,6 +522,7 @@ extern "C" {
 int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
 
 const char* ssfm_last_error(void) { return g_last_error.c_str(); }
+void ssfm_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }  // for the library's other translation units
 
 void ssfm_default_options(SsfmOptions* o) {
   if (!o) return;
@@ -1164,48 +1165,66 @@ static int minimal_solve_impl(ssfm_handle h, const double* rays, int32_t n, cons
 
 int ssfm_score(ssfm_handle h, const double* models6, int32_t M, const double* rays, int32_t n, double thr2, float* scores,
                int32_t* counts, float* kernel_ms) {
-  if (!h || !models6 || !rays || !scores || !counts || M < 0 || n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
-  if (M == 0) return SSFM_OK;
+  if (n < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  const int64_t offs[2] = {0, n};
+  return ssfm_score_pairs(h, models6, M, rays, offs, 1, thr2, scores, counts, kernel_ms);
+}
+
+int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const double* rays, const int64_t* offsets, int32_t num_pairs,
+                     double thr2, float* scores, int32_t* counts, float* kernel_ms) {
+  if (!h || !models6 || !rays || !offsets || !scores || !counts || M < 0 || num_pairs < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  if (M == 0 || num_pairs == 0) return SSFM_OK;
+  if (offsets[0] != 0) return fail(SSFM_ERR_INVALID, "offsets[0] must be 0");
+  long long nmax = 0;
+  for (int p = 0; p < num_pairs; ++p) {
+    if (offsets[p + 1] < offsets[p]) return fail(SSFM_ERR_INVALID, "offsets must be non-decreasing");
+    nmax = std::max<long long>(nmax, offsets[p + 1] - offsets[p]);
+  }
+  const long long n = offsets[num_pairs];
+  if (nmax > 0x7fffffffLL) return fail(SSFM_ERR_INVALID, "pair too large");
   SSFM_CK(cudaSetDevice(h->device));
   TmpGuard g;
   SSFM_TMP(double, b_rays, (size_t)n * 6) SSFM_KEEP(g, b_rays)
   SSFM_TMP(float4, b_u, (size_t)n) SSFM_KEEP(g, b_u)
   SSFM_TMP(float4, b_v, (size_t)n) SSFM_KEEP(g, b_v)
-  SSFM_TMP(double, b_m, (size_t)M * 6) SSFM_KEEP(g, b_m)
+  SSFM_TMP(double, b_m, (size_t)num_pairs * M * 6) SSFM_KEEP(g, b_m)
   double* dr = (double*)g.ptrs[0]; float4* du = (float4*)g.ptrs[1]; float4* dv = (float4*)g.ptrs[2]; double* dm = (double*)g.ptrs[3];
   SSFM_TMP(float4, b_uv, (size_t)n) SSFM_KEEP(g, b_uv)
   SSFM_TMP(int, b_flag, 1) SSFM_KEEP(g, b_flag)
-  float4* duv = (float4*)g.ptrs[4]; int* dflag = (int*)g.ptrs[5];
+  SSFM_TMP(long long, b_off, (size_t)num_pairs + 1) SSFM_KEEP(g, b_off)
+  float4* duv = (float4*)g.ptrs[4]; int* dflag = (int*)g.ptrs[5]; long long* doff = (long long*)g.ptrs[6];
+  // correspondences of every pair are split into chunks (multiples of the tile) so that the grid fills the machine
   const int gx = (M + 4 * kScoreThreads - 1) / (4 * kScoreThreads);
-  const int max_chunks = std::max(1, (n + kTile - 1) / kTile);
-  int nchunks = std::min(max_chunks, std::max(1, (4 * h->num_sms * 2 + gx - 1) / gx));
-  int chunk = ((n + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile;
+  const int max_chunks = (int)std::max<long long>(1, (nmax + kTile - 1) / kTile);
+  int nchunks = std::min(max_chunks, std::max(1, (4 * h->num_sms * 2 + gx * num_pairs - 1) / (gx * num_pairs)));
+  int chunk = (int)(((nmax + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile);
   if (chunk <= 0) chunk = kTile;
-  nchunks = std::max(1, (n + chunk - 1) / chunk);
-  SSFM_TMP(float, b_ps, (size_t)nchunks * M) SSFM_KEEP(g, b_ps)
-  SSFM_TMP(int, b_pc, (size_t)nchunks * M) SSFM_KEEP(g, b_pc)
-  SSFM_TMP(float, b_s, (size_t)M) SSFM_KEEP(g, b_s)
-  SSFM_TMP(int, b_c, (size_t)M) SSFM_KEEP(g, b_c)
-  float* ps = (float*)g.ptrs[6]; int* pc = (int*)g.ptrs[7]; float* ds = (float*)g.ptrs[8]; int* dc = (int*)g.ptrs[9];
+  nchunks = (int)std::max<long long>(1, (nmax + chunk - 1) / chunk);
+  SSFM_TMP(float, b_ps, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_ps)
+  SSFM_TMP(int, b_pc, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_pc)
+  SSFM_TMP(float, b_s, (size_t)num_pairs * M) SSFM_KEEP(g, b_s)
+  SSFM_TMP(int, b_c, (size_t)num_pairs * M) SSFM_KEEP(g, b_c)
+  float* ps = (float*)g.ptrs[7]; int* pc = (int*)g.ptrs[8]; float* ds = (float*)g.ptrs[9]; int* dc = (int*)g.ptrs[10];
   if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
-  SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M * num_pairs, cudaMemcpyHostToDevice, h->stream));
+  SSFM_CK(cudaMemcpyAsync(doff, offsets, sizeof(long long) * ((size_t)num_pairs + 1), cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
-  if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, h->stream>>>(dr, n, du, dv, duv, dflag);
+  if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, du, dv, duv, dflag);
   SSFM_CK(cudaMemcpyAsync(h->h_count + 3, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
   const bool unit_z = h->h_count[3] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
   // warm-up launch (untimed), then the timed one
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
-    dim3 grid(gx, nchunks);
-    if (unit_z) k_score_models<true><<<grid, kScoreThreads, 0, h->stream>>>(duv, nullptr, n, chunk, dm, M, (float)thr2, ps, pc);
-    else k_score_models<false><<<grid, kScoreThreads, 0, h->stream>>>(du, dv, n, chunk, dm, M, (float)thr2, ps, pc);
-    k_reduce_parts<<<(M + 255) / 256, 256, 0, h->stream>>>(ps, pc, nchunks, M, ds, dc);
+    dim3 grid(gx, nchunks, num_pairs);
+    if (unit_z) k_score_models<true><<<grid, kScoreThreads, 0, h->stream>>>(duv, nullptr, doff, chunk, dm, M, (float)thr2, ps, pc);
+    else k_score_models<false><<<grid, kScoreThreads, 0, h->stream>>>(du, dv, doff, chunk, dm, M, (float)thr2, ps, pc);
+    k_reduce_parts<<<dim3((M + 255) / 256, num_pairs), 256, 0, h->stream>>>(ps, pc, nchunks, M, ds, dc);
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
   }
   SSFM_CK(cudaGetLastError());
-  SSFM_CK(cudaMemcpyAsync(scores, ds, sizeof(float) * M, cudaMemcpyDeviceToHost, h->stream));
-  SSFM_CK(cudaMemcpyAsync(counts, dc, sizeof(int) * M, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(scores, ds, sizeof(float) * (size_t)M * num_pairs, cudaMemcpyDeviceToHost, h->stream));
+  SSFM_CK(cudaMemcpyAsync(counts, dc, sizeof(int) * (size_t)M * num_pairs, cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
   if (kernel_ms) SSFM_CK(cudaEventElapsedTime(kernel_ms, h->ev[0], h->ev[1]));
   return SSFM_OK;

@@ -373,46 +373,53 @@ __global__ void __launch_bounds__(kScoreThreads) k_score_rounds(const float4* __
   }
 }
 
-// Arbitrary models x one pair.  grid.x = ceil(M / (4 * kScoreThreads)), grid.y = correspondence chunks.
-// part_score / part_cnt: [chunk][M]
+// Arbitrary models x pairs (config C5).  grid.x = ceil(M / (4 * kScoreThreads)), grid.y = correspondence chunks,
+// grid.z = pairs.  Pair z owns correspondences [offsets[z], offsets[z+1]) and the models models6[z][M][6].
+// part_score / part_cnt: [pair][chunk][M]; chunks past the end of a (shorter) pair write zeros.
 template <bool UNITZ>
 __global__ void __launch_bounds__(kScoreThreads) k_score_models(const float4* __restrict__ pa, const float4* __restrict__ pb,
-                                                                long long n, int chunk, const double* __restrict__ models6,
-                                                                int M, float thr, float* __restrict__ part_score,
-                                                                int* __restrict__ part_cnt) {
+                                                                const long long* __restrict__ offsets, int chunk,
+                                                                const double* __restrict__ models6, int M, float thr,
+                                                                float* __restrict__ part_score, int* __restrict__ part_cnt) {
   __shared__ __align__(128) ScoreSmem<UNITZ> sm;
+  const int pair = blockIdx.z;
+  const long long base = offsets[pair], n = offsets[pair + 1] - base;
   const int m0 = (blockIdx.x * kScoreThreads + threadIdx.x) * 4;
   float p[4][6];
+  const double* mp = models6 + (size_t)pair * M * 6;
 #pragma unroll
   for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int i = 0; i < 6; ++i) p[m][i] = (m0 + m < M) ? (float)models6[(size_t)(m0 + m) * 6 + i] : 0.f;
+    for (int i = 0; i < 6; ++i) p[m][i] = (m0 + m < M) ? (float)mp[(size_t)(m0 + m) * 6 + i] : 0.f;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   int cnt[4] = {0, 0, 0, 0};
   const long long c0 = (long long)blockIdx.y * chunk;
   const long long c1 = (c0 + chunk) < n ? (c0 + chunk) : n;
   const bool warp_live = (int)((blockIdx.x * kScoreThreads + (threadIdx.x & ~31u)) * 4) < M;
-  score_stream<UNITZ, true>(sm, pa, pb, c0, c1, p, thr, warp_live, acc, cnt);
+  if (c0 < n) score_stream<UNITZ, true>(sm, pa, pb, base + c0, base + c1, p, thr, warp_live, acc, cnt);  // uniform per CTA
+  const size_t row = ((size_t)pair * gridDim.y + blockIdx.y) * M;
 #pragma unroll
   for (int m = 0; m < 4; ++m)
     if (m0 + m < M) {
-      part_score[(size_t)blockIdx.y * M + m0 + m] = acc[m];
-      part_cnt[(size_t)blockIdx.y * M + m0 + m] = cnt[m];
+      part_score[row + m0 + m] = acc[m];
+      part_cnt[row + m0 + m] = cnt[m];
     }
 }
 
+// scores / counts: [pair][M]
 __global__ void k_reduce_parts(const float* __restrict__ part_score, const int* __restrict__ part_cnt, int nchunks, int M,
                                float* __restrict__ scores, int* __restrict__ counts) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pair = blockIdx.y;
   if (m >= M) return;
   float s = 0.f;
   int c = 0;
   for (int k = 0; k < nchunks; ++k) {  // fixed order -> deterministic
-    s += part_score[(size_t)k * M + m];
-    c += part_cnt[(size_t)k * M + m];
+    s += part_score[((size_t)pair * nchunks + k) * M + m];
+    c += part_cnt[((size_t)pair * nchunks + k) * M + m];
   }
-  scores[m] = s;
-  counts[m] = c;
+  scores[(size_t)pair * M + m] = s;
+  counts[(size_t)pair * M + m] = c;
 }
 
 // ------------------------------------------------------------------------------------------

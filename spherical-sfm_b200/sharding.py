@@ -7,18 +7,10 @@ import numpy as np
 
 def partition_pairs(offsets, world_size):
     """Contiguous block partition of the pair list balanced by correspondence count
-    (cost ~ N_pair x iterations; N_pair is the a-priori proxy).  Returns world_size+1 pair bounds."""
-    offsets = np.asarray(offsets, np.int64)
-    P = len(offsets) - 1
-    total = int(offsets[-1])
-    bounds = [0]
-    for r in range(1, world_size):
-        target = total * r / world_size
-        b = int(np.searchsorted(offsets, target, side="left"))
-        b = min(max(b, bounds[-1]), P)
-        bounds.append(b)
-    bounds.append(P)
-    return bounds
+    (cost ~ N_pair x iterations; N_pair is the a-priori proxy).  Returns world_size+1 pair bounds.
+    One implementation: the library's ssfm_partition_pairs (a host function; ssfm_estimate_pairs_multi uses the same)."""
+    from . import partition_pairs as _pp
+    return _pp(offsets, world_size)
 
 
 def shard(rays, offsets, rank, world_size):

@@ -557,3 +557,27 @@ def test_restatement_follows_reference_sources_end_to_end(S, O, orc, reffull, na
         else:
             followed += 1
     print("%s: canonical-representative oracle follows upstream-as-written on %d / %d pairs" % (name, followed, trials))
+
+
+def test_lm_refit_termination_is_sensitive_upstream(S, O, orc):
+    """tests/golden/lm_sensitive_pair.npz: a C1-shaped pair found by the at-scale GPU parity run (pair 1132 of 2048) on which the
+    engine, the host build of the engine's code and the oracle ended with 480 / 481 / 482 inliers -- same iterations, same LO
+    count.  The oracle alone reproduces all three outcomes when its INPUT rays are changed by one ulp: the final least-squares
+    refit (Ceres trust region, function tolerance 1e-6, on a cost whose residual is the squared Sampson value, so the minimum
+    is degenerate) stops one step earlier or later.  The poses stay within 0.01 deg of each other, which is the bar that
+    applies to refitted models; trajectories of such pairs are not reproducible by any second implementation."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "lm_sensitive_pair.npz"))
+    rays, pid = g["rays"], int(g["pair_id"])
+    opt = O.pipeline_options(THR2)
+    base, _ = orc.estimate_pair(rays, opt, pid)
+    outcomes, worst = set(), 0.0
+    for j in range(1, 9):
+        rng = np.random.default_rng(j)
+        m = np.ones_like(rays)
+        m[:, [0, 1, 3, 4]] = 1 + rng.integers(-1, 2, (len(rays), 4)) * 2.0 ** -52
+        a, _ = orc.estimate_pair(rays * m, opt, pid)
+        assert (a.num_iterations, a.number_lo_iterations) == (base.num_iterations, base.number_lo_iterations)
+        outcomes.add(a.best_num_inliers)
+        worst = max(worst, np.rad2deg(S.problems.rot_error(S.problems.so3exp(np.array(base.r)), S.problems.so3exp(np.array(a.r)))))
+    print("1-ulp input perturbations: inlier counts", sorted(outcomes), "worst pose difference %.4f deg" % worst)
+    assert len(outcomes) >= 2 and worst < 0.01

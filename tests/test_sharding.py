@@ -17,9 +17,12 @@ def test_partition_covers_all_pairs(S):
         assert b[0] == 0 and b[-1] == 1001 and all(b[i] <= b[i + 1] for i in range(w))
         loads = [offs[b[i + 1]] - offs[b[i]] for i in range(w)]
         assert max(loads) - min(loads) <= 2 * 3000
-    # degenerate: fewer pairs than ranks
+    # degenerate: fewer pairs than ranks, empty batch
     b = S.sharding.partition_pairs(np.array([0, 10, 20]), 8)
-    assert b[0] == 0 and b[-1] == 2
+    assert b[0] == 0 and b[-1] == 2 and all(b[i] <= b[i + 1] for i in range(8))
+    assert S.partition_pairs(np.array([0]), 4) == [0, 0, 0, 0, 0]
+    # it is the library's C function (ssfm_partition_pairs, the one ssfm_estimate_pairs_multi shards with)
+    assert S.sharding.partition_pairs(offs, 5) == S.partition_pairs(offs, 5)
 
 
 def _worker(rank, world, port, q):
