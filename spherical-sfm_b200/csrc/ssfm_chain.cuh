@@ -68,16 +68,36 @@ struct PairState {
 // refit); thousands of independent refits, one per lane, are not.
 enum { PHASE_NONE = 0, PHASE_LO_START = 1, PHASE_LO_BEST = 2, PHASE_LO_LATE = 3, PHASE_FINAL_LSQ = 4 };
 
+// Execution contexts.  lane()/width() stride the data-parallel loops over correspondences and sum()/sum_i()/sum_vec()
+// reduce over the whole context (identical result on every thread -> uniform control flow).  slane()/swidth()/ballot()/
+// prefix_min_excl()/min_f() are the scan view used on the short per-round score arrays.
 struct SerialCtx {
   SSFM_HD int lane() const { return 0; }
   SSFM_HD int width() const { return 1; }
+  SSFM_HD int slane() const { return 0; }
+  SSFM_HD int swidth() const { return 1; }
   SSFM_HD double sum(double x) const { return x; }
   SSFM_HD int sum_i(int x) const { return x; }
+  template <int K>
+  SSFM_HD void sum_vec(double (&v)[K]) const { (void)v; }
   SSFM_HD unsigned ballot(bool p) const { return p ? 1u : 0u; }
   SSFM_HD float prefix_min_excl(float x, float init) const { (void)x; return init; }
   SSFM_HD float min_f(float x) const { return x; }
   SSFM_HD void sync() const {}
 };
+
+// One correspondence = 6 doubles at a 16-byte aligned address (48-byte records): three 128-bit loads
+// (LDG.128) instead of six 64-bit ones.
+SSFM_HD void load6(const double* p, double (&c)[6]) {
+#if defined(__CUDA_ARCH__)
+  const double2 a = reinterpret_cast<const double2*>(p)[0];
+  const double2 b = reinterpret_cast<const double2*>(p)[1];
+  const double2 d = reinterpret_cast<const double2*>(p)[2];
+  c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y; c[4] = d.x; c[5] = d.y;
+#else
+  for (int i = 0; i < 6; ++i) c[i] = p[i];
+#endif
+}
 
 // ScoreModel (ransac.h:295-303) fused with the inlier count GetInliers would return for the same
 // model and threshold (:311-336): one pass yields both, so the reference's "GetInliers(best_model)"
@@ -89,7 +109,9 @@ SSFM_HD_NOINLINE double msac_score_exact(const Ctx& cx, const double* E, const d
   int c = 0;
 #pragma unroll 2
   for (int i = cx.lane(); i < n; i += cx.width()) {
-    const double e = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
+    double ry[6];
+    load6(rays + 6 * (size_t)i, ry);
+    const double e = sampson_exact(E, ry, ry + 3);
     s += (thr < e) ? thr : e;  // std::min(e, thr) incl. its NaN behaviour (ransac.h:306-309)
     c += (e < thr) ? 1 : 0;
   }
@@ -108,7 +130,9 @@ SSFM_HD_NOINLINE int collect_inliers(const Ctx& cx, const double* E, const doubl
     const int i = base + cx.lane();
     bool in = false;
     if (i < n) {
-      const double e = sampson_exact(E, rays + 6 * (size_t)i, rays + 6 * (size_t)i + 3);
+      double ry[6];
+      load6(rays + 6 * (size_t)i, ry);
+      const double e = sampson_exact(E, ry, ry + 3);
       in = inclusive ? (e <= thr) : (e < thr);
       if (flags) flags[i] = in ? 1 : 0;
     }
@@ -251,25 +275,26 @@ SSFM_HD double lm_eval_jac(const Ctx& cx, const double* rays, const int* sample,
     const Jet6 t1[3] = {jvar(S.x[3], 3), jvar(S.x[4], 4), jvar(S.x[5], 5)};
     spherical_E_of_params<Jet6>(r1, t1, S.t0z, Ej);
   }
-  double Hl[21], gl[6], c = 0.0;
-  for (int a = 0; a < 21; ++a) Hl[a] = 0.0;
-  for (int a = 0; a < 6; ++a) gl[a] = 0.0;
+  double acc[28];  // [0,21): J^T J (lower triangle), [21,27): J^T r, [27]: r^T r -- reduced over the context in one go
+  for (int a = 0; a < 28; ++a) acc[a] = 0.0;
   for (int i = cx.lane(); i < n; i += cx.width()) {
-    const double* ry = rays + 6 * (size_t)sample[i];
+    double ry[6];
+    load6(rays + 6 * (size_t)sample[i], ry);
     double r, jr[6];
     sampson_value_grad(Ej, ry, ry + 3, r, jr);
-    c += r * r;
+    acc[27] += r * r;
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
-      gl[a] += jr[a] * r;
+      acc[21 + a] += jr[a] * r;
 #pragma unroll
-      for (int b = 0; b <= a; ++b) Hl[k++] += jr[a] * jr[b];
+      for (int b = 0; b <= a; ++b) acc[k++] += jr[a] * jr[b];
     }
   }
-  for (int a = 0; a < 21; ++a) S.H[a] = cx.sum(Hl[a]);
-  for (int a = 0; a < 6; ++a) S.g[a] = cx.sum(gl[a]);
-  c = cx.sum(c);
+  cx.sum_vec(acc);
+  for (int a = 0; a < 21; ++a) S.H[a] = acc[a];
+  for (int a = 0; a < 6; ++a) S.g[a] = acc[21 + a];
+  double c = acc[27];
   S.gmax = 0.0;
   for (int a = 0; a < 6; ++a) S.gmax = fmax(S.gmax, fabs(S.g[a]));  // gradient of the UNSCALED problem
   if (!S.have_scale) {
@@ -289,7 +314,8 @@ SSFM_HD double lm_eval_cost(const Ctx& cx, const double* rays, const int* sample
   spherical_E_of_params<double>(xx, xx + 3, t0z, Ev);
   double c = 0.0;
   for (int i = cx.lane(); i < n; i += cx.width()) {
-    const double* ry = rays + 6 * (size_t)sample[i];
+    double ry[6];
+    load6(rays + 6 * (size_t)sample[i], ry);
     const double r = sampson_value(Ev, ry, ry + 3);
     c += r * r;
   }
@@ -662,7 +688,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
       float run = st.runmin32;
       int base = j;
       while (base < navail && jn == navail) {
-        const int jj = base + cx.lane();
+        const int jj = base + cx.slane();
         const float s = jj < navail ? s32[jj] : INFINITY;
         const float before = cx.prefix_min_excl(s, run);
         const bool cand = s < INFINITY && s <= before * (1.0f + P.cand_margin);
@@ -677,7 +703,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
         }
         // the running minimum covers every iteration consumed so far (<= jn)
         run = fminf(run, cx.min_f(jj <= jn ? s : INFINITY));
-        base += cx.width();
+        base += cx.swidth();
       }
       st.runmin32 = run;
       SSFM_TOC(sc, PH_SCAN)

@@ -42,6 +42,13 @@ struct WarpCtx {
 #endif
     return x;
   }
+  __host__ __device__ int slane() const { return ln; }
+  __host__ __device__ int swidth() const { return 32; }
+  template <int K>
+  __host__ __device__ void sum_vec(double (&v)[K]) const {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = sum(v[k]);
+  }
   __host__ __device__ unsigned ballot(bool p) const {
 #if defined(__CUDA_ARCH__)
     return __ballot_sync(0xffffffffu, p);
@@ -212,6 +219,10 @@ __global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Param
 constexpr int kScoreThreads = 128;  // one look-ahead iteration (4 roots) per thread
 constexpr int kTile = 512;          // correspondences per shared-memory stage
 constexpr int kStages = 2;
+#ifndef SSFM_PACKED_SCORING
+#define SSFM_PACKED_SCORING 1
+#endif
+constexpr bool kPackedScoring = SSFM_PACKED_SCORING != 0;  // unit-z scoring loop on FFMA2 (0: the scalar FFMA loop)
 
 // UNITZ = every ray of the batch has z == 1 exactly (the pipeline's K^-1 (x,y,1) rays and the
 // reference's generator): one float4 (u0,u1,v0,v1) per correspondence and 19 FMA-pipe ops per
@@ -280,6 +291,47 @@ __device__ __forceinline__ float sampson_f32_unitz(const float (&p)[6], const fl
   return (d * d) * rcp_ftz(den);
 }
 
+// ---- packed FP32 (sm_100 fma.rn.f32x2 / mul.rn.f32x2 / add.rn.f32x2 -> SASS FFMA2 / FMUL2 / FADD2) ----
+// One instruction carries two independent FP32 operations, halving the issue slots of the scoring loop (the FMA pipe
+// still retires 128 lanes-FMAs per clock per SM: the gain is that the loop stops being issue-bound).  The two halves
+// of a register pair hold two MODELS (roots) of the calling thread; the correspondence is broadcast to both halves.
+// Every packed operation is the same IEEE operation as its scalar twin, in the same order, so results are bit-identical.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// Two models against one unit-z correspondence: P[0..5] = (p_i of model a, p_i of model b), P[6] = -P[0];
+// X, Y, Z, W = the correspondence's (u.x, u.y, v.x, v.y) broadcast to both halves.  Same expression tree as
+// sampson_f32_unitz; returns d^2 and the denominator (the reciprocal is a scalar MUFU per half).
+__device__ __forceinline__ void sampson2_unitz(const f32x2 (&P)[7], f32x2 X, f32x2 Y, f32x2 Z, f32x2 W, f32x2& d2, f32x2& den) {
+  const f32x2 Eu0 = fma2(P[1], Y, fma2(P[0], X, P[2]));
+  const f32x2 Eu1 = fma2(P[6], Y, fma2(P[1], X, P[3]));
+  const f32x2 Eu2 = fma2(P[5], Y, mul2(P[4], X));
+  const f32x2 Et0 = fma2(P[1], W, fma2(P[0], Z, P[4]));
+  const f32x2 Et1 = fma2(P[6], W, fma2(P[1], Z, P[5]));
+  const f32x2 d = fma2(W, Eu1, fma2(Z, Eu0, Eu2));
+  den = fma2(Et1, Et1, fma2(Et0, Et0, fma2(Eu1, Eu1, mul2(Eu0, Eu0))));
+  d2 = mul2(d, d);
+}
+
 // Streams correspondences [c0, c1) of one pair through shared memory and accumulates the MSAC
 // cost (and optionally the inlier count) of the calling thread's four models.  Warps whose lanes
 // are all idle (`active` false) only take part in the barriers.  Partial sums are folded per tile
@@ -289,6 +341,13 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
                                              long long c0, long long c1, const float (&p)[4][6], float thr, bool active,
                                              float (&acc)[4], int (&cnt)[4]) {
   const int ntiles = (int)((c1 - c0 + kTile - 1) / kTile);
+  f32x2 P2[2][7];  // models (0,1) and (2,3) packed parameter by parameter; [6] = -p0
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) P2[h][i] = pack2(p[2 * h][i], p[2 * h + 1][i]);
+    P2[h][6] = pack2(-p[2 * h][0], -p[2 * h + 1][0]);
+  }
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) mbar_init(&sm.bar[s], 1);
@@ -313,21 +372,52 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
       const int n = (int)((c1 - b) < kTile ? (c1 - b) : kTile);
       const float4* sa = sm.a[s];
       const float4* sb = sm.b[UNITZ ? 0 : s];
-      float tacc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (UNITZ && kPackedScoring) {
+        f32x2 tacc2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
 #pragma unroll 8
-      for (int i = 0; i < n; ++i) {
-        const float4 ca = sa[i];
-        float4 cb;
-        if (!UNITZ) cb = sb[i];
+        for (int i = 0; i < n; ++i) {
+          const float4 ca = sa[i];
+          const f32x2 X = pack2(ca.x, ca.x), Y = pack2(ca.y, ca.y), Z = pack2(ca.z, ca.z), W = pack2(ca.w, ca.w);
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const float e = UNITZ ? sampson_f32_unitz(p[m], ca) : sampson_f32(p[m], ca, cb);
-          tacc[m] += fminf(e, thr);
-          if (COUNT) cnt[m] += (e < thr) ? 1 : 0;
+          for (int h = 0; h < 2; ++h) {
+            f32x2 d2, den;
+            sampson2_unitz(P2[h], X, Y, Z, W, d2, den);
+            float dl, dh;
+            unpack2(den, dl, dh);
+            const f32x2 e2 = mul2(d2, pack2(rcp_ftz(dl), rcp_ftz(dh)));
+            float el, eh;
+            unpack2(e2, el, eh);
+            tacc2[h] = add2(tacc2[h], pack2(fminf(el, thr), fminf(eh, thr)));
+            if (COUNT) {
+              cnt[2 * h] += (el < thr) ? 1 : 0;
+              cnt[2 * h + 1] += (eh < thr) ? 1 : 0;
+            }
+          }
         }
-      }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) acc[m] += tacc[m];
+        for (int h = 0; h < 2; ++h) {
+          float tl, th;
+          unpack2(tacc2[h], tl, th);
+          acc[2 * h] += tl;
+          acc[2 * h + 1] += th;
+        }
+      } else {
+        float tacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) {
+          const float4 ca = sa[i];
+          float4 cb;
+          if (!UNITZ) cb = sb[i];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const float e = UNITZ ? sampson_f32_unitz(p[m], ca) : sampson_f32(p[m], ca, cb);
+            tacc[m] += fminf(e, thr);
+            if (COUNT) cnt[m] += (e < thr) ? 1 : 0;
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) acc[m] += tacc[m];
+      }
     }
     __syncthreads();  // everyone is done with stage s before it is refilled
     if (threadIdx.x == 0 && t + kStages < ntiles) issue(t + kStages);

@@ -756,43 +756,69 @@ SSFM_HD void roots_action_matrix(const double (&G)[6][4], Cplx* xs, Cplx* ys) {
     // three non-trivial rows of (M - x I) (y^2, x, y, 1)^T = 0 in the unknowns (x, y) restore that accuracy:
     //   r0 = m00 y^2 + m01 x + m02 y + m03 - x y^2,  r1 = m10 y^2 + m11 x + m12 y + m13 - x^2,  r2 = m20 y^2 + m21 x + m22 y + m23 - x y
     Cplx px = x, py = y;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const Cplx y2 = cmul(py, py);
-      const Cplx xy = cmul(px, py);
-      Cplx r[3], jx[3], jy[3];
-      r[0] = csub(cadd(cadd(cscale(m00, y2), cscale(m01, px)), cadd(cscale(m02, py), Cplx{m03, 0.0})), cmul(px, y2));
-      r[1] = csub(cadd(cadd(cscale(m10, y2), cscale(m11, px)), cadd(cscale(m12, py), Cplx{m13, 0.0})), cmul(px, px));
-      r[2] = csub(cadd(cadd(cscale(m20, y2), cscale(m21, px)), cadd(cscale(m22, py), Cplx{m23, 0.0})), xy);
-      jx[0] = csub(Cplx{m01, 0.0}, y2);
-      jx[1] = csub(Cplx{m11, 0.0}, cscale(2.0, px));
-      jx[2] = csub(Cplx{m21, 0.0}, py);
-      jy[0] = csub(cadd(cscale(2.0 * m00, py), Cplx{m02, 0.0}), cscale(2.0, xy));
-      jy[1] = cadd(cscale(2.0 * m10, py), Cplx{m12, 0.0});
-      jy[2] = csub(cadd(cscale(2.0 * m20, py), Cplx{m22, 0.0}), px);
-      // normal equations (J^H J) d = -J^H r, 2x2 Hermitian
-      double a11 = 0.0, a22 = 0.0;
-      Cplx a12 = {0.0, 0.0}, b1 = {0.0, 0.0}, b2 = {0.0, 0.0};
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const Cplx cjx = {jx[q].re, -jx[q].im}, cjy = {jy[q].re, -jy[q].im};
-        a11 += cabs2(jx[q]);
-        a22 += cabs2(jy[q]);
-        a12 = cadd(a12, cmul(cjx, jy[q]));
-        b1 = cadd(b1, cmul(cjx, r[q]));
-        b2 = cadd(b2, cmul(cjy, r[q]));
+    if (x.im == 0.0) {
+      // real eigenvalue: real arithmetic; a second step only when the first one moved the root by more than 1e-9
+      double rx = x.re, ry = y.re;
+      for (int it = 0; it < 2; ++it) {
+        const double y2 = ry * ry, xy = rx * ry;
+        const double r0 = m00 * y2 + m01 * rx + m02 * ry + m03 - rx * y2;
+        const double r1 = m10 * y2 + m11 * rx + m12 * ry + m13 - rx * rx;
+        const double r2 = m20 * y2 + m21 * rx + m22 * ry + m23 - xy;
+        const double jx0 = m01 - y2, jx1 = m11 - 2.0 * rx, jx2 = m21 - ry;
+        const double jy0 = 2.0 * m00 * ry + m02 - 2.0 * xy, jy1 = 2.0 * m10 * ry + m12, jy2 = 2.0 * m20 * ry + m22 - rx;
+        const double a11 = jx0 * jx0 + jx1 * jx1 + jx2 * jx2, a22 = jy0 * jy0 + jy1 * jy1 + jy2 * jy2;
+        const double a12 = jx0 * jy0 + jx1 * jy1 + jx2 * jy2;
+        const double b1 = jx0 * r0 + jx1 * r1 + jx2 * r2, b2 = jy0 * r0 + jy1 * r1 + jy2 * r2;
+        const double det = a11 * a22 - a12 * a12;
+        if (!(det > 1e-30 * a11 * a22) || !isfinite(det)) break;  // (numerically) multiple root: leave it
+        const double inv = 1.0 / det;
+        const double dx = (a22 * b1 - a12 * b2) * inv, dy = (a11 * b2 - a12 * b1) * inv;
+        const double step2 = dx * dx + dy * dy, size2 = rx * rx + ry * ry + 1.0;
+        if (!isfinite(step2) || step2 > 1e-4 * size2) break;  // a polish, never a jump to another root
+        rx -= dx;
+        ry -= dy;
+        if (step2 <= 1e-18 * size2) break;
       }
-      const double det = a11 * a22 - cabs2(a12);
-      if (!(det > 1e-30 * a11 * a22) || !isfinite(det)) break;  // (numerically) multiple root: leave it
-      const Cplx ca12 = {a12.re, -a12.im};
-      const double inv = 1.0 / det;
-      Cplx dx = cscale(inv, csub(cscale(a22, b1), cmul(a12, b2)));
-      Cplx dy = cscale(inv, csub(cscale(a11, b2), cmul(ca12, b1)));
-      if (x.im == 0.0) { dx.im = 0.0; dy.im = 0.0; }  // real eigenvalue: stay on the real axis
-      const double step2 = cabs2(dx) + cabs2(dy), size2 = cabs2(px) + cabs2(py) + 1.0;
-      if (!isfinite(step2) || step2 > 1e-4 * size2) break;  // a polish, never a jump to another root
-      px = csub(px, dx);
-      py = csub(py, dy);
+      px = {rx, 0.0};
+      py = {ry, 0.0};
+    } else {
+      for (int it = 0; it < 2; ++it) {
+        const Cplx y2 = cmul(py, py);
+        const Cplx xy = cmul(px, py);
+        Cplx r[3], jx[3], jy[3];
+        r[0] = csub(cadd(cadd(cscale(m00, y2), cscale(m01, px)), cadd(cscale(m02, py), Cplx{m03, 0.0})), cmul(px, y2));
+        r[1] = csub(cadd(cadd(cscale(m10, y2), cscale(m11, px)), cadd(cscale(m12, py), Cplx{m13, 0.0})), cmul(px, px));
+        r[2] = csub(cadd(cadd(cscale(m20, y2), cscale(m21, px)), cadd(cscale(m22, py), Cplx{m23, 0.0})), xy);
+        jx[0] = csub(Cplx{m01, 0.0}, y2);
+        jx[1] = csub(Cplx{m11, 0.0}, cscale(2.0, px));
+        jx[2] = csub(Cplx{m21, 0.0}, py);
+        jy[0] = csub(cadd(cscale(2.0 * m00, py), Cplx{m02, 0.0}), cscale(2.0, xy));
+        jy[1] = cadd(cscale(2.0 * m10, py), Cplx{m12, 0.0});
+        jy[2] = csub(cadd(cscale(2.0 * m20, py), Cplx{m22, 0.0}), px);
+        // normal equations (J^H J) d = J^H r, 2x2 Hermitian
+        double a11 = 0.0, a22 = 0.0;
+        Cplx a12 = {0.0, 0.0}, b1 = {0.0, 0.0}, b2 = {0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const Cplx cjx = {jx[q].re, -jx[q].im}, cjy = {jy[q].re, -jy[q].im};
+          a11 += cabs2(jx[q]);
+          a22 += cabs2(jy[q]);
+          a12 = cadd(a12, cmul(cjx, jy[q]));
+          b1 = cadd(b1, cmul(cjx, r[q]));
+          b2 = cadd(b2, cmul(cjy, r[q]));
+        }
+        const double det = a11 * a22 - cabs2(a12);
+        if (!(det > 1e-30 * a11 * a22) || !isfinite(det)) break;
+        const Cplx ca12 = {a12.re, -a12.im};
+        const double inv = 1.0 / det;
+        const Cplx dx = cscale(inv, csub(cscale(a22, b1), cmul(a12, b2)));
+        const Cplx dy = cscale(inv, csub(cscale(a11, b2), cmul(ca12, b1)));
+        const double step2 = cabs2(dx) + cabs2(dy), size2 = cabs2(px) + cabs2(py) + 1.0;
+        if (!isfinite(step2) || step2 > 1e-4 * size2) break;
+        px = csub(px, dx);
+        py = csub(py, dy);
+        if (step2 <= 1e-18 * size2) break;
+      }
     }
     xs[k] = px;
     ys[k] = py;

@@ -453,7 +453,10 @@ def _table_vs_oracle(S, O, orc, res, flags, rays, offsets, opt):
         d = np.rad2deg(S.problems.rot_error(S.problems.so3exp(np.array(ores[p].r)), S.problems.so3exp(res["r"][p])))
         worst_deg = max(worst_deg, d)
         if same[p]:
-            worst_E = max(worst_E, model_dist(res["E"][p] / np.linalg.norm(res["E"][p]), np.array(ores[p].E) / np.linalg.norm(ores[p].E)))
+            # refined models are [t]x R at their natural scale |t| = |R e3 - e3| (tiny for tiny rotations, where normalising
+            # would turn a 1e-7 rad pose difference into 1e-4): compare them as they are
+            Ea, Eb = res["E"][p], np.array(ores[p].E)
+            worst_E = max(worst_E, min(np.abs(Ea - Eb).max(), np.abs(Ea + Eb).max()))
         else:
             assert o[p, 0] == mine[p, 0] and abs(int(o[p, 2]) - int(mine[p, 2])) <= 0.01 * N, (p, o[p], mine[p])
             print("   refit-sensitive pair %d: oracle %s engine %s, pose difference %.4f deg" % (p, o[p].tolist(), mine[p].tolist(), d))
