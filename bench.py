@@ -576,15 +576,17 @@ def main():
     # the caller-side variant: keypoints + matches + Kinv in, rays built on the device (8 B per match over PCIe)
     try:
         fpx = 600.0
+        # pair p = images (2p, 2p+1), each with its own N keypoints (independent synthetic pairs cannot share keypoints)
         kp_all = torch.empty((2 * P * N, 2), dtype=torch.float32, pin_memory=True)
         rt = torch.from_numpy(rays_np)
-        kp_all[:P * N] = (rt[:, 0:2] * fpx).to(torch.float32)
-        kp_all[P * N:] = (rt[:, 3:5] * fpx).to(torch.float32)
+        kv = kp_all.view(P, 2, N, 2)
+        kv[:, 0] = (rt[:, 0:2] * fpx).to(torch.float32).view(P, N, 2)
+        kv[:, 1] = (rt[:, 3:5] * fpx).to(torch.float32).view(P, N, 2)
         idx = torch.arange(P * N, dtype=torch.int32)
         mt_all = torch.stack([idx % N, idx % N], dim=1).contiguous()
         kp_pairs = torch.empty((P, 2), dtype=torch.int32)
-        kp_pairs[:, 0] = torch.arange(P, dtype=torch.int32)
-        kp_pairs[:, 1] = torch.arange(P, dtype=torch.int32) + P
+        kp_pairs[:, 0] = 2 * torch.arange(P, dtype=torch.int32)
+        kp_pairs[:, 1] = 2 * torch.arange(P, dtype=torch.int32) + 1
         kp_off = np.arange(2 * P + 1, dtype=np.int64) * N
         Kinv = np.array([[1 / fpx, 0, 0], [0, 1 / fpx, 0], [0, 0, 1.0]])
         mt_pin = torch.empty(mt_all.shape, dtype=torch.int32, pin_memory=True)

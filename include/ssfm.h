@@ -224,6 +224,25 @@ int ssfm_multi_get_stats(ssfm_multi_handle m, int32_t index, SsfmRunStats* stats
  * order, owned by the handle and valid until the next multi call. */
 int ssfm_multi_allgather_results(ssfm_multi_handle m, void** dev_tables, int32_t* num_pairs);
 
+/* ---- descriptor matching: the step in front of the relative-pose path ----
+ * match() (examples/spherical_sfm_tools.cpp:235-251) for every listed image pair, as match_exhaustive() (:575-600) runs it:
+ * cv::BFMatcher(NORM_L2)::knnMatch(query = features1.descs, train = features0.descs, k = 2), Lowe's ratio test
+ * `m[0].distance < ratio * m[1].distance`, `m01[trainIdx] = queryIdx` in query order.  Output = the Matches maps in their
+ * iteration order: per pair, (index in image 0, index in image 1) sorted by the first -- exactly what
+ * SsfmMatchBatch.matches takes.  Descriptors are cv::SIFT's: 128 floats holding integers 0..255 (checked; anything else is
+ * SSFM_ERR_INVALID because the fp16 tensor-core product is exact only for them); results are bit-exact with OpenCV, ties
+ * included.  match_offsets: num_pairs + 1.  matches: 2 ints per match, `capacity` matches (sum of min(n0, n1) suffices). */
+typedef struct SsfmDescriptorBatch {
+  int32_t num_images;
+  int32_t descriptor_length;    /* 128 */
+  const int64_t* desc_offsets;  /* host, num_images + 1: image i owns descriptor rows [desc_offsets[i], desc_offsets[i+1]) */
+  const float* descriptors;     /* host, rows x 128 (Features::descs, CV_32F) */
+  int32_t num_pairs;
+  const int32_t* pair_images;   /* host, 2 per pair: index0, index1 (ImageMatch) */
+  double ratio;                 /* 0.75 (spherical_sfm_tools.h:70) */
+} SsfmDescriptorBatch;
+int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* batch, int64_t* match_offsets, int32_t* matches, int64_t capacity);
+
 /* The same call split into its three stages, so inputs can stay resident in HBM:
  * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */
 int ssfm_upload(ssfm_handle h, const SsfmBatch* batch);

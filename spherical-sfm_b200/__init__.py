@@ -18,7 +18,7 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 LIB_PATH = os.environ.get("SSFM_LIB_PATH", os.path.join(_DIR, "libssfm_b200.so"))  # override: profiling builds
-_UNITS = [os.path.join(_DIR, "csrc", f) for f in ("ssfm_engine.cu", "ssfm_multi.cu")]  # translation units
+_UNITS = [os.path.join(_DIR, "csrc", f) for f in ("ssfm_engine.cu", "ssfm_multi.cu", "ssfm_match.cu")]  # translation units
 
 
 def _sources():
@@ -66,6 +66,13 @@ class SsfmMatchBatch(C.Structure):
     _fields_ = [("num_images", C.c_int32), ("keypoint_offsets", C.POINTER(C.c_int64)), ("keypoints_xy", C.POINTER(C.c_float)),
                 ("num_pairs", C.c_int32), ("pair_images", C.POINTER(C.c_int32)), ("match_offsets", C.POINTER(C.c_int64)),
                 ("matches", C.POINTER(C.c_int32)), ("Kinv", C.c_double * 9)]
+
+
+class SsfmDescriptorBatch(C.Structure):
+    """Descriptors of every image + the pair list, as match_exhaustive holds them (examples/spherical_sfm_tools.cpp:575-600)."""
+    _fields_ = [("num_images", C.c_int32), ("descriptor_length", C.c_int32), ("desc_offsets", C.POINTER(C.c_int64)),
+                ("descriptors", C.POINTER(C.c_float)), ("num_pairs", C.c_int32), ("pair_images", C.POINTER(C.c_int32)),
+                ("ratio", C.c_double)]
 
 
 class SsfmPairResult(C.Structure):
@@ -141,7 +148,7 @@ EXPORTED_SYMBOLS = [
     "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_pairs", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
     "ssfm_multi_create", "ssfm_multi_destroy", "ssfm_multi_num_devices", "ssfm_partition_pairs", "ssfm_estimate_pairs_multi",
-    "ssfm_multi_get_stats", "ssfm_multi_allgather_results",
+    "ssfm_multi_get_stats", "ssfm_multi_allgather_results", "ssfm_match_pairs",
 ]
 
 
@@ -277,6 +284,20 @@ class Engine:
         self._num_pairs = b.num_pairs
         self._num_corr = int(mo[-1])
         return res, flags
+
+    def match_pairs(self, descriptors, desc_offsets, pair_images, ratio=0.75):
+        """ssfm_match_pairs: BF 2-NN + ratio test for every pair.  descriptors (rows, 128) float32 (cv::SIFT integers),
+        desc_offsets (num_images + 1), pair_images (P, 2).  Returns (match_offsets (P + 1), matches (M, 2))."""
+        d = np.ascontiguousarray(descriptors, np.float32).reshape(-1, 128)
+        do = np.ascontiguousarray(desc_offsets, np.int64)
+        pi = np.ascontiguousarray(pair_images, np.int32).reshape(-1, 2)
+        n = np.diff(do)
+        cap = int(np.minimum(n[pi[:, 0]], n[pi[:, 1]]).sum()) if len(pi) else 0
+        b = SsfmDescriptorBatch(len(do) - 1, 128, _p(do, C.c_int64), _p(d, C.c_float), len(pi), _p(pi, C.c_int32), float(ratio))
+        offs = np.zeros(len(pi) + 1, np.int64)
+        out = np.zeros((max(cap, 1), 2), np.int32)
+        _check(lib().ssfm_match_pairs(self._h, C.byref(b), _p(offs, C.c_int64), _p(out, C.c_int32), C.c_int64(cap)))
+        return offs, out[:int(offs[-1])]
 
     def stats(self):
         s = SsfmRunStats()

@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -88,8 +89,15 @@ struct ssfm_engine {
   std::vector<long long> h_offsets;
   const double* d_rays = nullptr;  // either rays_own.p or the caller's device pointer
   DevBuf<double> rays_own;
-  DevBuf<float4> u4, v4, uv4;
+  DevBuf<float4> u4, v4, uv4;  // uv4: always; u4 / v4: only once a batch with z != 1 rays shows up (ensure_general_planes)
+  std::mutex general_mu;
   bool unit_z = false;
+  // ssfm_upload_matches: keypoints / pair table / matches / Kinv (grow-only, kept across calls)
+  DevBuf<float> m_kp;
+  DevBuf<long long> m_kpoff;
+  DevBuf<int> m_pairs, m_matches;
+  DevBuf<double> m_kinv;
+  bool matches_pending_check = false;  // a pipelined match upload whose index-range flag has not been read yet
   DevBuf<long long> offsets;
   bool resident = false;
   // pipelined upload (ssfm_estimate_pairs): one event + one unit-z flag per pass of pairs
@@ -219,6 +227,23 @@ struct RunCfg {
     }                                                                                          \
   } while (0)
 
+// The general FP32 planes (u.xyz / v.xyz) for correspondences [c0, c1): built lazily, on the stream that needs them.
+int ensure_general_planes(ssfm_engine* h, cudaStream_t st, long long c0, long long c1, std::string* err) {
+  std::lock_guard<std::mutex> lock(h->general_mu);
+  const size_t m = (size_t)std::max<long long>(h->M, 1);
+  if (h->u4.cap < m || h->v4.cap < m) {
+    // (re)allocation invalidates what was packed before: callers always pack the range they are about to read
+    cudaError_t e = h->u4.ensure(m);
+    if (e == cudaSuccess) e = h->v4.ensure(m);
+    if (e != cudaSuccess) {
+      *err = std::string("general planes: ") + cudaGetErrorString(e);
+      return e == cudaErrorMemoryAllocation ? SSFM_ERR_OOM : SSFM_ERR_CUDA;
+    }
+  }
+  if (c1 > c0) k_pack_general<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, st>>>(h->d_rays + 6 * c0, c1 - c0, h->u4.p + c0, h->v4.p + c0);
+  return SSFM_OK;
+}
+
 struct PassDesc {
   int pair0, np;
   int pipelined;  // 1: the upload is still in flight; round 0 is launched chunk by chunk as the rays arrive
@@ -255,6 +280,9 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         all_unit = all_unit && h->h_up_flags[k] == 0;
       }
       unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    }
+    if (!unit_z && (P.solver == SSFM_SOLVER_SIXPT_FOCAL || !pd.pipelined)) {
+      if (int rc = ensure_general_planes(h, w.stream, c0, c1, &w.err)) return rc;
     }
     if (P.solver == SSFM_SOLVER_SIXPT_FOCAL) {
       // Six-point shared-focal estimator under VanillaMSAC: look-ahead rounds like the 3-point path, in
@@ -416,10 +444,14 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
           SSFM_WCK(cudaEventSynchronize(h->up_ev[k]));
           const bool uz = h->h_up_flags[k] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
           all_unit = all_unit && uz;
+          if (!uz)
+            if (int rc = ensure_general_planes(h, w.stream, h->h_offsets[q0], h->h_offsets[q1], &w.err)) return rc;
           SSFM_WCK(launch_round(w.ident.p + (q0 - pair0), q1 - q0, uz, false));
           launches += 2;
         }
         unit_z = all_unit;
+        if (!unit_z)  // later rounds score the whole pass with the general kernel
+          if (int rc = ensure_general_planes(h, w.stream, c0, c1, &w.err)) return rc;
         launches -= 2;
       } else {
         SSFM_WCK(launch_round(act, count, unit_z, true));
@@ -523,6 +555,8 @@ int ssfm_abi_version(void) { return SSFM_ABI_VERSION; }
 
 const char* ssfm_last_error(void) { return g_last_error.c_str(); }
 void ssfm_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }  // for the library's other translation units
+int ssfm_internal_device(ssfm_handle h) { return h ? h->device : 0; }
+cudaStream_t ssfm_internal_stream(ssfm_handle h) { return h ? h->stream : nullptr; }
 
 void ssfm_default_options(SsfmOptions* o) {
   if (!o) return;
@@ -605,6 +639,7 @@ void ssfm_destroy(ssfm_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release();
   h->counts.release(); h->results.release(); h->flags.release();
+  h->m_kp.release(); h->m_kpoff.release(); h->m_pairs.release(); h->m_matches.release(); h->m_kinv.release();
   for (int k = 0; k < h->num_workers; ++k) {
     Worker& w = h->workers[k];
     if (w.stream) cudaStreamSynchronize(w.stream);
@@ -628,6 +663,33 @@ void ssfm_destroy(ssfm_handle h) {
   delete h;
 }
 
+// Chunked, asynchronous upload plan: graded chunk sizes (the first kernels start after a 2048-pair copy instead of a
+// 16384-pair one), one event + one unit-z flag per chunk.
+static int plan_upload_chunks(ssfm_handle h) {
+  h->up_bounds.clear();
+  int step = 2048;
+  if (const char* e = getenv("SSFM_FIRST_CHUNK")) step = std::max(256, atoi(e));
+  for (int p0 = 0; p0 < h->P;) {
+    h->up_bounds.push_back(p0);
+    p0 += std::min(step, kPipelinePassPairs);
+    if (step < kPipelinePassPairs) step *= 2;
+  }
+  h->up_bounds.push_back(h->P);
+  const int nchunks = (int)h->up_bounds.size() - 1;
+  SSFM_CK(h->up_flags.ensure(nchunks));
+  SSFM_CK(cudaMemsetAsync(h->up_flags.p, 0, sizeof(int) * nchunks, h->stream));
+  while ((int)h->up_ev.size() < nchunks) {
+    cudaEvent_t e;
+    SSFM_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->up_ev.push_back(e);
+  }
+  return SSFM_OK;
+}
+
+static bool want_pipelined_upload(ssfm_handle h) {
+  return h->P > 2 * kPipelinePassPairs && (h->P / kPipelinePassPairs) < kMaxUploadChunks - 1;
+}
+
 static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
   if (b->num_pairs < 0 || (b->num_pairs > 0 && (!b->offsets || !b->rays))) return fail(SSFM_ERR_INVALID, "bad batch");
@@ -648,8 +710,6 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   SSFM_CK(h->offsets.ensure(h->P + 1));
   SSFM_CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), sizeof(long long) * (h->P + 1), cudaMemcpyHostToDevice, h->stream));
   const size_t m = (size_t)std::max<long long>(h->M, 1);
-  SSFM_CK(h->u4.ensure(m));
-  SSFM_CK(h->v4.ensure(m));
   SSFM_CK(h->uv4.ensure(m));
   SSFM_CK(h->counts.ensure(8));
   SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), h->stream));
@@ -657,38 +717,21 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   // they wait on this event first (run_range), so a reused engine never sees the previous batch's table.
   SSFM_CK(cudaEventRecord(h->ev_tables, h->stream));
   h->up_bounds.clear();
-  if (pipelined && !b->rays_on_device && h->P > 2 * kPipelinePassPairs && (h->P / kPipelinePassPairs) < kMaxUploadChunks - 1) {
+  if (pipelined && !b->rays_on_device && want_pipelined_upload(h)) {
     // Chunked, asynchronous upload: chunk k = pairs [k*16384, (k+1)*16384); H2D + pack on the copy
     // stream, an event per chunk.  ssfm_run's passes wait on the events, so the copy of chunk k+1
     // overlaps the kernels of chunk k.  (The caller's buffer is only read until ssfm_run returns.)
     SSFM_CK(h->rays_own.ensure(m * 6));
     h->d_rays = h->rays_own.p;
-    // graded chunk sizes: the first kernels start after a 2048-pair copy instead of a 16384-pair one
-    {
-      int step = 2048;
-      if (const char* e = getenv("SSFM_FIRST_CHUNK")) step = std::max(256, atoi(e));
-      for (int p0 = 0; p0 < h->P;) {
-        h->up_bounds.push_back(p0);
-        p0 += std::min(step, kPipelinePassPairs);
-        if (step < kPipelinePassPairs) step *= 2;
-      }
-    }
-    h->up_bounds.push_back(h->P);
+    if (int rc = plan_upload_chunks(h)) return rc;
     const int nchunks = (int)h->up_bounds.size() - 1;
-    SSFM_CK(h->up_flags.ensure(nchunks));
-    SSFM_CK(cudaMemsetAsync(h->up_flags.p, 0, sizeof(int) * nchunks, h->stream));
-    while ((int)h->up_ev.size() < nchunks) {
-      cudaEvent_t e;
-      SSFM_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-      h->up_ev.push_back(e);
-    }
     for (int k = 0; k < nchunks; ++k) {
       const long long c0 = h->h_offsets[h->up_bounds[k]], c1 = h->h_offsets[h->up_bounds[k + 1]];
       if (c1 > c0) {
         SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
                                 cudaMemcpyHostToDevice, h->stream));
-        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream>>>(h->rays_own.p + 6 * c0, c1 - c0, h->u4.p + c0,
-                                                                         h->v4.p + c0, h->uv4.p + c0, h->up_flags.p + k);
+        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0,
+                                                                         h->up_flags.p + k);
         SSFM_CK(cudaGetLastError());
       }
       SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -712,13 +755,18 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (h->M > 0) {
     const int threads = 256;
     const long long blocks = (h->M + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->u4.p, h->v4.p, h->uv4.p, h->counts.p + 2);
+    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->uv4.p, h->counts.p + 2);
     SSFM_CK(cudaGetLastError());
   }
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
   SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));  // the caller's buffer may go away after we return
   h->unit_z = h->h_count[2] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  if (!h->unit_z) {
+    std::string err;
+    if (int rc = ensure_general_planes(h, h->stream, 0, h->M, &err)) return fail(rc, err);
+    SSFM_CK(cudaStreamSynchronize(h->stream));
+  }
   float ms = 0.f;
   SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
   h->stats.pack_ms = ms;
@@ -728,7 +776,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
 
 int ssfm_upload(ssfm_handle h, const SsfmBatch* b) { return upload_impl(h, b, false); }
 
-int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) {
+static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
   if (b->num_pairs < 0 || b->num_images < 0) return fail(SSFM_ERR_INVALID, "bad batch");
   if (b->num_pairs > 0 && (!b->keypoint_offsets || !b->keypoints_xy || !b->pair_images || !b->match_offsets || !b->matches))
@@ -737,63 +785,127 @@ int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) {
   const int P = b->num_pairs;
   const long long M = P > 0 ? b->match_offsets[P] : 0;
   const long long NK = b->num_images > 0 ? b->keypoint_offsets[b->num_images] : 0;
+  if (P > 0 && b->match_offsets[0] != 0) return fail(SSFM_ERR_INVALID, "match_offsets[0] must be 0");
   for (int p = 0; p < P; ++p) {
     const int i0 = b->pair_images[2 * p], i1 = b->pair_images[2 * p + 1];
     if (i0 < 0 || i1 < 0 || i0 >= b->num_images || i1 >= b->num_images) return fail(SSFM_ERR_INVALID, "pair image index out of range");
-    if (b->match_offsets[p + 1] < b->match_offsets[p]) return fail(SSFM_ERR_INVALID, "match_offsets must be non-decreasing");
+    if (b->match_offsets[p + 1] < b->match_offsets[p] || b->match_offsets[p + 1] - b->match_offsets[p] > 0x7fffffffLL)
+      return fail(SSFM_ERR_INVALID, "match_offsets must be non-decreasing (and each pair < 2^31 matches)");
   }  // (keypoint indices of the individual matches are range-checked by the kernel)
-  DevBuf<float> d_kp;
-  DevBuf<long long> d_kpoff;
-  DevBuf<int> d_pairs, d_matches;
-  DevBuf<double> d_kinv;
-  struct Guard {
-    DevBuf<float>& a; DevBuf<long long>& b; DevBuf<int>& c; DevBuf<int>& d; DevBuf<double>& e;
-    ~Guard() { a.release(); b.release(); c.release(); d.release(); e.release(); }
-  } guard{d_kp, d_kpoff, d_pairs, d_matches, d_kinv};
-  SSFM_CK(d_kp.ensure((size_t)std::max<long long>(2 * NK, 2)));
-  SSFM_CK(d_kpoff.ensure(b->num_images + 1));
-  SSFM_CK(d_pairs.ensure((size_t)std::max(2 * P, 2)));
-  SSFM_CK(d_matches.ensure((size_t)std::max<long long>(2 * M, 2)));
-  SSFM_CK(d_kinv.ensure(9));
+  h->resident = false;
+  h->have_results = false;
+  h->matches_pending_check = false;
+  h->P = P;
+  h->M = M;
+  if (P > 0) h->h_offsets.assign(b->match_offsets, b->match_offsets + P + 1);
+  else h->h_offsets.assign(1, 0);
+  h->stats = SsfmRunStats();
+  h->up_bounds.clear();
+  // persistent (grow-only) device buffers: no allocation after the first call of a given size
+  SSFM_CK(h->m_kp.ensure((size_t)std::max<long long>(2 * NK, 2)));
+  SSFM_CK(h->m_kpoff.ensure(b->num_images + 1));
+  SSFM_CK(h->m_pairs.ensure((size_t)std::max(2 * P, 2)));
+  SSFM_CK(h->m_matches.ensure((size_t)std::max<long long>(2 * M, 2)));
+  SSFM_CK(h->m_kinv.ensure(9));
   SSFM_CK(h->rays_own.ensure((size_t)std::max<long long>(6 * M, 6)));
+  SSFM_CK(h->uv4.ensure((size_t)std::max<long long>(M, 1)));
   SSFM_CK(h->offsets.ensure(P + 1));
   SSFM_CK(h->counts.ensure(8));
-  SSFM_CK(cudaMemsetAsync(h->counts.p + 3, 0, sizeof(int), h->stream));
-  if (NK > 0) SSFM_CK(cudaMemcpyAsync(d_kp.p, b->keypoints_xy, sizeof(float) * 2 * (size_t)NK, cudaMemcpyHostToDevice, h->stream));
+  h->d_rays = h->rays_own.p;
+  cudaStream_t st = h->stream;
+  SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), st));
+  const bool pipe = pipelined && want_pipelined_upload(h);
+  if (NK > 0 && !pipe) SSFM_CK(cudaMemcpyAsync(h->m_kp.p, b->keypoints_xy, sizeof(float) * 2 * (size_t)NK, cudaMemcpyHostToDevice, st));
   if (b->num_images > 0)
-    SSFM_CK(cudaMemcpyAsync(d_kpoff.p, b->keypoint_offsets, sizeof(long long) * (b->num_images + 1), cudaMemcpyHostToDevice, h->stream));
-  if (P > 0) {
-    SSFM_CK(cudaMemcpyAsync(d_pairs.p, b->pair_images, sizeof(int) * 2 * (size_t)P, cudaMemcpyHostToDevice, h->stream));
-    SSFM_CK(cudaMemcpyAsync(h->offsets.p, b->match_offsets, sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, h->stream));
-  }
-  if (M > 0) SSFM_CK(cudaMemcpyAsync(d_matches.p, b->matches, sizeof(int) * 2 * (size_t)M, cudaMemcpyHostToDevice, h->stream));
-  SSFM_CK(cudaMemcpyAsync(d_kinv.p, b->Kinv, sizeof(double) * 9, cudaMemcpyHostToDevice, h->stream));
-  if (M > 0) {
-    k_build_rays<<<(unsigned)((M + 255) / 256), 256, 0, h->stream>>>(reinterpret_cast<const float2*>(d_kp.p), d_kpoff.p, d_pairs.p,
-                                                                     h->offsets.p, P, reinterpret_cast<const int2*>(d_matches.p), M,
-                                                                     d_kinv.p, h->rays_own.p, h->counts.p + 3);
-    SSFM_CK(cudaGetLastError());
-  }
-  SSFM_CK(cudaMemcpyAsync(h->h_count + 3, h->counts.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  SSFM_CK(cudaStreamSynchronize(h->stream));
-  if (h->h_count[3] != 0) return fail(SSFM_ERR_INVALID, "match keypoint index out of range");
-  // from here on it is an ordinary batch whose rays already live in HBM
-  SsfmBatch rb;
-  rb.num_pairs = P;
-  rb.offsets = b->match_offsets;
-  rb.rays = h->rays_own.p;
-  rb.rays_on_device = 1;
-  const int rc = upload_impl(h, &rb, false);
+    SSFM_CK(cudaMemcpyAsync(h->m_kpoff.p, b->keypoint_offsets, sizeof(long long) * (b->num_images + 1), cudaMemcpyHostToDevice, st));
+  SSFM_CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), sizeof(long long) * (P + 1), cudaMemcpyHostToDevice, st));
+  if (P > 0) SSFM_CK(cudaMemcpyAsync(h->m_pairs.p, b->pair_images, sizeof(int) * 2 * (size_t)P, cudaMemcpyHostToDevice, st));
+  SSFM_CK(cudaMemcpyAsync(h->m_kinv.p, b->Kinv, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
+  SSFM_CK(cudaEventRecord(h->ev_tables, st));
   h->stats.h2d_bytes = (long long)(8 * NK + 8 * (long long)P + 8 * M + 8 * (P + 1) + 8 * (b->num_images + 1) + 72);
-  return rc;
+  auto build = [&](long long c0, long long c1, int* flag) -> cudaError_t {  // matches [c0, c1): H2D, rays + FP32 plane in one kernel
+    if (c1 <= c0) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(h->m_matches.p + 2 * c0, b->matches + 2 * c0, sizeof(int) * 2 * (size_t)(c1 - c0), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    k_build_rays<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(h->m_kp.p), h->m_kpoff.p, h->m_pairs.p,
+                                                                    h->offsets.p, P, reinterpret_cast<const int2*>(h->m_matches.p), c0,
+                                                                    c1 - c0, h->m_kinv.p, h->rays_own.p, h->uv4.p, flag, h->counts.p + 3);
+    return cudaGetLastError();
+  };
+  if (pipe) {
+    // chunk k = a range of pairs: its matches are copied and turned into rays while earlier chunks already run their
+    // first look-ahead round (same plan as the ray upload; ssfm_run waits on the chunk events).  Keypoints travel
+    // just in time: before a chunk's matches, the images it references that are not in HBM yet (image tables sorted
+    // by first use copy progressively; an exhaustive pair list references every image at once and copies them all first).
+    if (int rc = plan_upload_chunks(h)) return rc;
+    const int nchunks = (int)h->up_bounds.size() - 1;
+    int images_copied = 0;
+    for (int k = 0; k < nchunks; ++k) {
+      int need = images_copied;
+      for (int p = h->up_bounds[k]; p < h->up_bounds[k + 1]; ++p)
+        need = std::max(need, std::max(b->pair_images[2 * p], b->pair_images[2 * p + 1]) + 1);
+      if (need > images_copied) {
+        const long long k0 = b->keypoint_offsets[images_copied], k1 = b->keypoint_offsets[need];
+        if (k1 > k0)
+          SSFM_CK(cudaMemcpyAsync(h->m_kp.p + 2 * k0, b->keypoints_xy + 2 * k0, sizeof(float) * 2 * (size_t)(k1 - k0), cudaMemcpyHostToDevice, st));
+        images_copied = need;
+      }
+      SSFM_CK(build(h->h_offsets[h->up_bounds[k]], h->h_offsets[h->up_bounds[k + 1]], h->up_flags.p + k));
+      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SSFM_CK(cudaEventRecord(h->up_ev[k], st));
+    }
+    h->unit_z = false;  // decided per chunk
+    h->matches_pending_check = true;
+    h->resident = true;
+    return SSFM_OK;
+  }
+  SSFM_CK(cudaEventRecord(h->ev[4], st));
+  SSFM_CK(build(0, M, h->counts.p + 2));
+  SSFM_CK(cudaEventRecord(h->ev[5], st));
+  SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SSFM_CK(cudaStreamSynchronize(st));  // the caller's buffers may go away after we return
+  if (h->h_count[3] != 0) return fail(SSFM_ERR_INVALID, "match keypoint index out of range");
+  h->unit_z = h->h_count[2] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  if (!h->unit_z) {
+    std::string err;
+    if (int rc = ensure_general_planes(h, st, 0, M, &err)) return fail(rc, err);
+    SSFM_CK(cudaStreamSynchronize(st));
+  }
+  float ms = 0.f;
+  SSFM_CK(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+  h->stats.pack_ms = ms;
+  h->resident = true;
+  return SSFM_OK;
 }
+
+int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) { return upload_matches_impl(h, b, false); }
 
 int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch, const SsfmOptions* opt,
                                      SsfmPairResult* results, uint8_t* inlier_flags) {
   if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
   if (int rc = check_options(opt)) return rc;
-  if (int rc = ssfm_upload_matches(h, batch)) return rc;
-  if (int rc = ssfm_run(h, opt)) return rc;
+  auto abandon = [h](int rc) {  // never leave copies from the caller's buffers in flight, nor a half-uploaded batch resident
+    cudaStreamSynchronize(h->stream);
+    h->up_bounds.clear();
+    h->resident = false;
+    h->have_results = false;
+    h->matches_pending_check = false;
+    return rc;
+  };
+  if (int rc = upload_matches_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return abandon(rc);
+  if (int rc = ssfm_run(h, opt)) return abandon(rc);
+  SSFM_CK(cudaStreamSynchronize(h->stream));
+  if (h->matches_pending_check) {  // the index-range flag of a pipelined upload is complete only now
+    SSFM_CK(cudaMemcpy(h->h_count + 3, h->counts.p + 3, sizeof(int), cudaMemcpyDeviceToHost));
+    h->matches_pending_check = false;
+    if (h->h_count[3] != 0) return abandon(fail(SSFM_ERR_INVALID, "match keypoint index out of range"));
+  }
+  if (!h->up_bounds.empty()) {  // the batch is fully resident now; later ssfm_run calls use the plain plan
+    bool all_unit = true;
+    for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) all_unit = all_unit && h->h_up_flags[k] == 0;
+    h->unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    h->up_bounds.clear();
+  }
   return ssfm_download(h, results, inlier_flags);
 }
 
@@ -1209,10 +1321,11 @@ int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const doub
   SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M * num_pairs, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(doff, offsets, sizeof(long long) * ((size_t)num_pairs + 1), cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
-  if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, du, dv, duv, dflag);
+  if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, duv, dflag);
   SSFM_CK(cudaMemcpyAsync(h->h_count + 3, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
   const bool unit_z = h->h_count[3] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  if (!unit_z && n > 0) k_pack_general<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, du, dv);
   // warm-up launch (untimed), then the timed one
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[0], h->stream));

@@ -98,17 +98,24 @@ __host__ __device__ inline int lookahead(uint32_t want, int cap) {
 // ------------------------------------------------------------------------------------------
 // k_pack
 // ------------------------------------------------------------------------------------------
-__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ u4, float4* __restrict__ v4,
-                       float4* __restrict__ uv4, int* __restrict__ not_unit_z) {
+// uv4 (the unit-z plane) is always written; the general planes u4 / v4 only on request (k_pack_general), i.e. only for
+// batches that turn out to contain rays with z != 1.
+__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ uv4, int* __restrict__ not_unit_z) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const double2* src = reinterpret_cast<const double2*>(rays + 6 * i);  // 48-byte records, 16-byte aligned
   const double2 a = src[0], b = src[1], c = src[2];
-  u4[i] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
-  v4[i] = make_float4((float)b.y, (float)c.x, (float)c.y, 0.f);
   uv4[i] = make_float4((float)a.x, (float)a.y, (float)b.y, (float)c.x);
   // pipeline rays are K^-1 (x, y, 1) (examples/spherical_sfm_tools.cpp:364-373): z == 1 exactly
   if (b.x != 1.0 || c.y != 1.0) *not_unit_z = 1;
+}
+__global__ void k_pack_general(const double* __restrict__ rays, long long m, float4* __restrict__ u4, float4* __restrict__ v4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double2* src = reinterpret_cast<const double2*>(rays + 6 * i);
+  const double2 a = src[0], b = src[1], c = src[2];
+  u4[i] = make_float4((float)a.x, (float)a.y, (float)b.x, 0.f);
+  v4[i] = make_float4((float)b.y, (float)c.x, (float)c.y, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -118,10 +125,11 @@ __global__ void k_pack(const double* __restrict__ rays, long long m, float4* __r
 // ------------------------------------------------------------------------------------------
 __global__ void k_build_rays(const float2* __restrict__ kp, const long long* __restrict__ kp_off,
                              const int* __restrict__ pair_images, const long long* __restrict__ match_off, int npairs,
-                             const int2* __restrict__ matches, long long m, const double* __restrict__ Kinv,
-                             double* __restrict__ rays, int* __restrict__ bad_index) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
+                             const int2* __restrict__ matches, long long m0, long long m, const double* __restrict__ Kinv,
+                             double* __restrict__ rays, float4* __restrict__ uv4, int* __restrict__ not_unit_z,
+                             int* __restrict__ bad_index) {
+  const long long i = m0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m0 + m) return;
   int lo = 0, hi = npairs;  // last pair whose first match is <= i
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -149,6 +157,9 @@ __global__ void k_build_rays(const float2* __restrict__ kp, const long long* __r
   dst[0] = make_double2(out[0], out[1]);
   dst[1] = make_double2(out[2], out[3]);
   dst[2] = make_double2(out[4], out[5]);
+  // the FP32 plane of the scoring kernel, in the same pass (what k_pack would produce from these rays)
+  uv4[i] = make_float4((float)out[0], (float)out[1], (float)out[3], (float)out[4]);
+  if (out[2] != 1.0 || out[5] != 1.0) *not_unit_z = 1;
 }
 
 // ------------------------------------------------------------------------------------------

