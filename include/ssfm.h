@@ -242,6 +242,18 @@ typedef struct SsfmDescriptorBatch {
   double ratio;                 /* 0.75 (spherical_sfm_tools.h:70) */
 } SsfmDescriptorBatch;
 int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* batch, int64_t* match_offsets, int32_t* matches, int64_t capacity);
+/* Stage timers (CUDA events on the engine's stream) and work counts of the last ssfm_match_pairs call on this engine. */
+typedef struct SsfmMatchStats {
+  double pack_ms;    /* H2D of the descriptors + k_desc_pack */
+  double knn_ms;     /* k_match_2nn launches only (the tcgen05 kernel) */
+  double compact_ms; /* owner table -> Matches lists + D2H */
+  double total_ms;   /* whole call, host clock */
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t distance_evaluations; /* sum over pairs of n0 * n1 */
+  int64_t mma_tiles;            /* 256 x 128 x 144 tensor-core tiles executed */
+  int32_t knn_launches, ctas;
+} SsfmMatchStats;
+int ssfm_match_get_stats(ssfm_handle h, SsfmMatchStats* out);
 
 /* The same call split into its three stages, so inputs can stay resident in HBM:
  * upload (H2D + packing into float4 SoA), run (all kernels), download (D2H of the result table). */

@@ -18,7 +18,6 @@ import numpy as np
 _DIR = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_DIR)
 LIB_PATH = os.environ.get("SSFM_LIB_PATH", os.path.join(_DIR, "libssfm_b200.so"))  # override: profiling builds
-_UNITS = [os.path.join(_DIR, "csrc", f) for f in ("ssfm_engine.cu", "ssfm_multi.cu", "ssfm_match.cu")]  # translation units
 
 
 def _sources():
@@ -75,6 +74,12 @@ class SsfmDescriptorBatch(C.Structure):
                 ("ratio", C.c_double)]
 
 
+class SsfmMatchStats(C.Structure):
+    _fields_ = [("pack_ms", C.c_double), ("knn_ms", C.c_double), ("compact_ms", C.c_double), ("total_ms", C.c_double),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("distance_evaluations", C.c_int64), ("mma_tiles", C.c_int64),
+                ("knn_launches", C.c_int32), ("ctas", C.c_int32)]
+
+
 class SsfmPairResult(C.Structure):
     """Best model + RansacStatistics (ransac.h:94-101) + pose."""
     _fields_ = [
@@ -109,17 +114,13 @@ RESULT_DTYPE = np.dtype([
     ("number_lo_iterations", np.int32), ("status", np.int32), ("evals", np.int64), ("focal", np.float64)], align=True)
 assert RESULT_DTYPE.itemsize == C.sizeof(SsfmPairResult)
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-              "-Xcompiler", "-fPIC"]
-
 
 def build_extension(force=False, verbose=False):
-    """Compile csrc/ into libssfm_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    newest = max(os.path.getmtime(s) for s in _sources())
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _UNITS + ["-ldl"]
-    subprocess.check_call(cmd, cwd=_DIR)
+    """Compile csrc/ into libssfm_b200.so for sm_100a (nvcc cross-compiles without a GPU): runs the Makefile next to this
+    file -- one object per translation unit, rebuilt when it or any header changed -- which a C++ consumer can run directly."""
+    cmd = ["make", "-C", _DIR, "-j", "3", "LIB=" + LIB_PATH] + (["-B"] if force else []) + \
+          (["EXTRA_NVCCFLAGS=-Xptxas -v"] if verbose else [])
+    subprocess.check_call(cmd, stdout=None if verbose else subprocess.DEVNULL)
     return LIB_PATH
 
 
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = [
     "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_pairs", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
     "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
     "ssfm_multi_create", "ssfm_multi_destroy", "ssfm_multi_num_devices", "ssfm_partition_pairs", "ssfm_estimate_pairs_multi",
-    "ssfm_multi_get_stats", "ssfm_multi_allgather_results", "ssfm_match_pairs",
+    "ssfm_multi_get_stats", "ssfm_multi_allgather_results", "ssfm_match_pairs", "ssfm_match_get_stats",
 ]
 
 
@@ -298,6 +299,11 @@ class Engine:
         out = np.zeros((max(cap, 1), 2), np.int32)
         _check(lib().ssfm_match_pairs(self._h, C.byref(b), _p(offs, C.c_int64), _p(out, C.c_int32), C.c_int64(cap)))
         return offs, out[:int(offs[-1])]
+
+    def match_stats(self):
+        s = SsfmMatchStats()
+        _check(lib().ssfm_match_get_stats(self._h, C.byref(s)))
+        return s
 
     def stats(self):
         s = SsfmRunStats()

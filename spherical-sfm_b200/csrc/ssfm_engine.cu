@@ -114,6 +114,9 @@ struct ssfm_engine {
   bool have_results = false;
   SsfmRunStats stats = {};
   int* h_count = nullptr;  // pinned
+  // context of the descriptor-matching translation unit (ssfm_match.cu), deleted with the engine
+  void* match_ctx = nullptr;
+  void (*match_ctx_delete)(void*) = nullptr;
 };
 
 // One worker = one stream + its own scratch.  ssfm_run splits the pair list between the workers and
@@ -557,6 +560,11 @@ const char* ssfm_last_error(void) { return g_last_error.c_str(); }
 void ssfm_internal_set_error(const char* msg) { g_last_error = msg ? msg : ""; }  // for the library's other translation units
 int ssfm_internal_device(ssfm_handle h) { return h ? h->device : 0; }
 cudaStream_t ssfm_internal_stream(ssfm_handle h) { return h ? h->stream : nullptr; }
+int ssfm_internal_num_sms(ssfm_handle h) { return h ? h->num_sms : 0; }
+void** ssfm_internal_ctx_slot(ssfm_handle h, void (*deleter)(void*)) {
+  h->match_ctx_delete = deleter;
+  return &h->match_ctx;
+}
 
 void ssfm_default_options(SsfmOptions* o) {
   if (!o) return;
@@ -637,6 +645,8 @@ void ssfm_destroy(ssfm_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->match_ctx && h->match_ctx_delete) h->match_ctx_delete(h->match_ctx);
+  h->match_ctx = nullptr;
   h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release();
   h->counts.release(); h->results.release(); h->flags.release();
   h->m_kp.release(); h->m_kpoff.release(); h->m_pairs.release(); h->m_matches.release(); h->m_kinv.release();

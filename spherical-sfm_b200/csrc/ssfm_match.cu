@@ -6,18 +6,24 @@
 // `m01[trainIdx] = queryIdx` in query order (a later query overwrites an earlier one on the same train index);
 // match_exhaustive() (:575-600) runs it for every image pair under `#pragma omp parallel for`.
 //
-// B200 mapping.  For one pair the 2-NN search is S = Q T^T (n1 x n0 x 128) followed by a running top-2 per query row of
-// d^2 = |q|^2 + |t|^2 - 2 S.  SIFT descriptors are integers 0..255 stored as float (cv::SIFT), so in fp16 they are exact,
-// every product is exact in fp32 and every partial sum is an integer below 2^24: the tensor-core result is the exact
-// integer d^2 that OpenCV's float accumulation also produces, and dist = sqrtf(d^2) is the same float.  Hence bit-exact
-// index pairs, ties included (OpenCV keeps the lower train index on equal float distances: strict '<' in its insertion).
-//   k_desc_pack   float descriptors -> fp16 in the tensor-core "core matrix" order (8 rows x 16 bytes contiguous, 16 such
-//                 blocks per 8-row group), |x|^2 per row, rows of every image padded to a multiple of 256; a tile of the
-//                 packed buffer is then ONE contiguous 1-D TMA bulk copy and needs no swizzle
-//   k_match_2nn   one CTA per (pair, 128 query rows): warp 0 = TMA producer (+ TMEM alloc), warp 1 = tcgen05.mma issuer
-//                 (M=128, N=256, K=16, fp16 -> fp32 in TMEM, two accumulator buffers = all 512 TMEM columns), warps 2-5 =
-//                 epilogue (tcgen05.ld, one query row per thread, running top-2 with OpenCV's insertion rule, ratio test,
-//                 atomicMax of the query index on the winning train index = the reference's overwrite order)
+// B200 mapping.  For one pair the 2-NN search is a running top-2 per query row of d^2 = |q|^2 + |t|^2 - 2 q.t over all train
+// rows.  SIFT descriptors are integers 0..255 stored as float (cv::SIFT), so in fp16 they are exact, every product is exact
+// in fp32 and every partial sum is an integer below 2^24: the tensor-core result is the exact integer OpenCV's float
+// accumulation also produces, and dist = sqrtf(d^2) is the same float.  Hence bit-exact index pairs, ties included (OpenCV
+// keeps the lower train index on equal float distances: strict '<' in its insertion).
+//
+// The whole of |t|^2 - 2 q.t comes out of the tensor core: the contraction is K = 144 wide, 128 descriptor bins plus one
+// 16-wide block that carries |t|^2 split into three fp16-exact pieces (train side: -2 t, p0, p1, p2; query side: q, 1, 64,
+// 4096 with |t|^2 = p0 + 64 p1 + 4096 p2), so the epilogue is one compare per distance.
+//   k_desc_pack   float descriptors -> fp16 in the tensor-core "core matrix" order (8 rows x 16 bytes contiguous, 18 such
+//                 blocks per 8-row group), once in query form and once in train form, |x|^2 per row, rows of every image
+//                 padded to a multiple of 256; a tile of a packed buffer is ONE contiguous 1-D TMA bulk copy, no swizzle
+//   k_match_2nn   persistent, one CTA per SM walking (pair, 256 query rows) work items; warp 0 = TMA producer (+ TMEM alloc),
+//                 warp 1 = tcgen05.mma issuer (two M=128 halves x N=128 x K=16, fp16 -> fp32 in TMEM, accumulators double
+//                 buffered = all 512 TMEM columns), warps 2-9 = epilogue (tcgen05.ld, one query row per thread, running top-2
+//                 with OpenCV's insertion rule, ratio test, atomicMax of the query index on the winning train index = the
+//                 reference's overwrite order).  256 query rows per CTA keep the train-tile stream at 32 B/clk/SM, under the
+//                 L2 limit (128 rows would need 64 B/clk/SM against ~43 available).
 //   k_match_count / k_match_write   ordered compaction of the owner table into the Matches list (sorted by index in image 0,
 //                 the iteration order of the reference's std::map)
 // There is no CPU fallback; the entry fails with SSFM_ERR_NO_DEVICE / SSFM_ERR_CUDA like the rest of the library.
@@ -27,6 +33,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -34,21 +41,27 @@
 
 extern "C" void ssfm_internal_set_error(const char* msg);  // ssfm_engine.cu
 extern "C" int ssfm_internal_device(ssfm_handle h);
+extern "C" int ssfm_internal_num_sms(ssfm_handle h);
 extern "C" cudaStream_t ssfm_internal_stream(ssfm_handle h);
+extern "C" void** ssfm_internal_ctx_slot(ssfm_handle h, void (*deleter)(void*));  // per-engine context owned by this TU
 
 namespace {
 
 constexpr int kD = 128;            // descriptor length (SIFT)
-constexpr int kQTile = 128;        // query rows per CTA = UMMA M
-constexpr int kTTile = 256;        // train rows per MMA tile = UMMA N
-constexpr int kRowPad = 256;       // rows of every image are padded to a multiple of this in the packed buffer
-constexpr int kGroupBytes = 2048;  // one 8-row group: 16 core matrices (8 rows x 16 B) = 8 x 128 halfs
-constexpr int kStages = 2;         // train-tile ring in shared memory (and accumulator buffers in TMEM)
-constexpr int kNormBufs = 4;
-constexpr int kMatchThreads = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr uint32_t kQBytes = kQTile * kD * 2;  // 32 KB
-constexpr uint32_t kTBytes = kTTile * kD * 2;  // 64 KB
+constexpr int kKp = 144;           // contraction length: 128 bins + one 16-wide block carrying |t|^2
+constexpr int kQTile = 256;        // query rows per work item = two UMMA M=128 halves
+constexpr int kTTile = 128;        // train rows per MMA tile = UMMA N
+constexpr int kRowPad = 256;       // rows of every image are padded to a multiple of this in the packed buffers
+constexpr int kGroupBytes = (kKp / 8) * 128;  // one 8-row group: 18 core matrices (8 rows x 16 B) = 2304 bytes
+constexpr int kStages = 3;         // train-tile ring in shared memory
+constexpr int kAccBufs = 2;        // accumulator buffers in TMEM (each: 2 halves x 128 fp32 columns)
+constexpr int kEpiWarps = 8;
+constexpr int kMatchThreads = 32 * (2 + kEpiWarps);  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr uint32_t kQBytes = kQTile / 8 * kGroupBytes;  // 73 728
+constexpr uint32_t kTBytes = kTTile / 8 * kGroupBytes;  // 36 864
 constexpr uint32_t kTmemCols = 512;
+constexpr float kFarSq = 1.0e8f;   // "no neighbour yet": above any real d^2 (<= 2 * 128 * 255^2), below a padded train row's
+constexpr int kPadP2 = 60000;      // p2 of a padded train row: its d^2 - |q|^2 is 4096 * 60000 = 2.4576e8 > kFarSq
 
 int mfail(int code, const std::string& msg) {
   ssfm_internal_set_error(msg.c_str());
@@ -57,11 +70,9 @@ int mfail(int code, const std::string& msg) {
 #define MCK(call)                                                                                        \
   do {                                                                                                   \
     cudaError_t e__ = (call);                                                                            \
-    if (e__ != cudaSuccess) {                                                                            \
-      release_all();                                                                                     \
+    if (e__ != cudaSuccess)                                                                              \
       return mfail(e__ == cudaErrorMemoryAllocation ? SSFM_ERR_OOM : SSFM_ERR_CUDA,                      \
                    std::string(#call) + ": " + cudaGetErrorString(e__));                                 \
-    }                                                                                                    \
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -80,8 +91,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 // Wait for the phase with the given parity.  A pipeline bug must not hang the GPU: after ~2 s of spinning the kernel traps
 // (the launch then fails with an error instead of never returning).
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
+  long long t0 = 0;
+  for (uint32_t spins = 0;; ++spins) {
     uint32_t done;
     asm volatile(
         "{\n"
@@ -93,7 +104,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) return;
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if ((spins & 1023u) == 1023u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -118,7 +133,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 __device__ __forceinline__ void umma_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id)
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + lane id); asynchronous until tmem_wait
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -129,10 +144,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Wait for this thread's outstanding tcgen05.ld; the registers are passed through so no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 // Shared-memory matrix descriptor, K-major, no swizzle: core matrices of 8 rows x 16 bytes; the next core matrix along K
-// is 128 bytes further (leading byte offset), the next 8-row group 2048 bytes further (stride byte offset); version 1.
+// is 128 bytes further (leading byte offset), the next 8-row group kGroupBytes further (stride byte offset); version 1.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)(128u >> 4) << 16;
@@ -141,20 +165,22 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return d;
 }
 // instruction descriptor: D = F32 (bits 4-5 = 1), A = B = F16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTTile >> 3) << 17) | ((uint32_t)(kQTile >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kTTile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------------------------
-// k_desc_pack: one thread per (padded row, 8-column chunk)
+// k_desc_pack: 16 threads per padded row (one per 8-bin chunk); the first of them also writes the |t|^2 block
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_desc_pack(const float* __restrict__ desc, const long long* __restrict__ desc_off, const long long* __restrict__ prow_off,
-                            int num_images, long long total_prows, __half* __restrict__ packed, float* __restrict__ norms,
-                            int* __restrict__ not_integer) {
+                            int num_images, long long total_prows, __half* __restrict__ packed_q, __half* __restrict__ packed_t,
+                            float* __restrict__ norms, int* __restrict__ not_integer) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long prow = gid >> 4;
   const int chunk = (int)(gid & 15);
   float part = 0.f;
   bool real = false;
-  if (prow < total_prows) {
+  const bool in_range = prow < total_prows;
+  char *dq = nullptr, *dt = nullptr;
+  if (in_range) {
     int lo = 0, hi = num_images;  // image that owns this padded row
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -162,7 +188,7 @@ __global__ void k_desc_pack(const float* __restrict__ desc, const long long* __r
     }
     const long long r = prow - prow_off[lo];
     const long long n = desc_off[lo + 1] - desc_off[lo];
-    __align__(16) __half h[8];
+    __align__(16) __half hq[8], ht[8];
     if (r < n) {
       real = true;
       const float4* src = reinterpret_cast<const float4*>(desc + (desc_off[lo] + r) * kD + chunk * 8);
@@ -172,63 +198,115 @@ __global__ void k_desc_pack(const float* __restrict__ desc, const long long* __r
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         bad = bad || !(v[k] >= 0.f && v[k] <= 255.f && v[k] == rintf(v[k]));
-        h[k] = __float2half_rn(v[k]);
-        part += v[k] * v[k];  // integers < 2^24: exact
+        hq[k] = __float2half_rn(v[k]);
+        ht[k] = __float2half_rn(-2.f * v[k]);  // even integers up to 510: exact in fp16
+        part += v[k] * v[k];                    // integers < 2^24: exact
       }
       if (bad) *not_integer = 1;
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) h[k] = __float2half_rn(0.f);
+      for (int k = 0; k < 8; ++k) hq[k] = ht[k] = __float2half_rn(0.f);
     }
-    char* dst = reinterpret_cast<char*>(packed) + (prow >> 3) * kGroupBytes + chunk * 128 + (prow & 7) * 16;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
+    const size_t off = (size_t)(prow >> 3) * kGroupBytes + (size_t)(prow & 7) * 16;
+    dq = reinterpret_cast<char*>(packed_q) + off;
+    dt = reinterpret_cast<char*>(packed_t) + off;
+    *reinterpret_cast<uint4*>(dq + chunk * 128) = *reinterpret_cast<const uint4*>(hq);
+    *reinterpret_cast<uint4*>(dt + chunk * 128) = *reinterpret_cast<const uint4*>(ht);
   }
   // |x|^2 of the row: the 16 chunk threads of a row are 16 consecutive lanes
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
-  if (prow < total_prows && chunk == 0) norms[prow] = real ? part : INFINITY;  // a padded train row can never be a neighbour
+  if (in_range && chunk == 0) {
+    norms[prow] = real ? part : 0.f;
+    const int n2 = (int)part;  // <= 128 * 255^2 < 2^23
+    __align__(16) __half eq[8], et[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) eq[k] = et[k] = __float2half_rn(0.f);
+    eq[0] = __float2half_rn(1.f);
+    eq[1] = __float2half_rn(64.f);
+    eq[2] = __float2half_rn(4096.f);
+    et[0] = __float2half_rn(real ? (float)(n2 & 63) : 0.f);
+    et[1] = __float2half_rn(real ? (float)((n2 >> 6) & 63) : 0.f);
+    et[2] = __float2half_rn(real ? (float)(n2 >> 12) : (float)kPadP2);  // a padded train row can never be a neighbour
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(dq + 16 * 128) = *reinterpret_cast<const uint4*>(eq);
+    *reinterpret_cast<uint4*>(dt + 16 * 128) = *reinterpret_cast<const uint4*>(et);
+    *reinterpret_cast<uint4*>(dq + 17 * 128) = z;
+    *reinterpret_cast<uint4*>(dt + 17 * 128) = z;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // k_match_2nn
 // ---------------------------------------------------------------------------------------------------------
 struct MatchSmem {
-  unsigned long long full[kStages], empty[kStages], tfull[kStages], tempty[kStages], qfull;
+  unsigned long long full[kStages], empty[kStages], tfull[kAccBufs], tempty[kAccBufs], qfull, qempty;
   uint32_t tmem_base;
-  uint32_t pad_[13];
-  float tnorm[kNormBufs][kTTile];  // |t|^2 of the tile's train rows
 };
-constexpr size_t kMatchSmemHeader = ((sizeof(MatchSmem) + 1023) / 1024) * 1024;
+constexpr size_t kMatchSmemHeader = 1024;
+static_assert(sizeof(MatchSmem) <= kMatchSmemHeader, "header");
 constexpr size_t kMatchSmemBytes = kMatchSmemHeader + kQBytes + kStages * kTBytes;
 
+// Running two nearest neighbours of one query row, kept as exact squared distances.
+struct Top2 {
+  float b0, b1;  // d^2 of the nearest / second nearest (kFarSq: none yet)
+  int i0, i1;
+  float thr;     // b1 - |q|^2: an accumulator value below it is a candidate
+};
+// A candidate: acc = d^2 - |q|^2 < thr.  cv::batchDistance inserts with `d < dist[K-1]`, shifting while `dist[k] > d`, on
+// d = sqrtf(d^2).  sqrtf is monotone, and injective on integers below 2^22 (the gap sqrt(a+1) - sqrt(a) >= 1/(2*2048) is two
+// ulps there), so below 2^22 the float comparisons equal the integer ones (top2_insert, branch-free, the common case);
+// above -- only while the second neighbour is still far -- the floats themselves are compared (top2_insert_far).
+__device__ __forceinline__ void top2_insert(Top2& s, bool cand, float acc, float qn, int idx) {
+  const float dsq = acc + qn;
+  const bool first = dsq < s.b0;
+  s.b1 = cand ? (first ? s.b0 : dsq) : s.b1;
+  s.i1 = cand ? (first ? s.i0 : idx) : s.i1;
+  s.b0 = (cand && first) ? dsq : s.b0;
+  s.i0 = (cand && first) ? idx : s.i0;
+  s.thr = s.b1 - qn;
+}
+__device__ __noinline__ Top2 top2_insert_far(Top2 s, bool cand, float acc, float qn, int idx) {
+  const float dsq = acc + qn;
+  bool first = dsq < s.b0;
+  if (!(s.b1 < 4194304.f)) {
+    const float d = sqrtf(dsq);
+    cand = cand && d < sqrtf(s.b1);
+    first = sqrtf(s.b0) > d;
+  }
+  if (cand) {
+    if (first) { s.b1 = s.b0; s.i1 = s.i0; s.b0 = dsq; s.i0 = idx; }
+    else { s.b1 = dsq; s.i1 = idx; }
+    s.thr = s.b1 - qn;
+  }
+  return s;
+}
+
 __global__ void __launch_bounds__(kMatchThreads, 1)
-k_match_2nn(const __half* __restrict__ packed, const float* __restrict__ norms, const long long* __restrict__ prow_off,
-            const int* __restrict__ nrows, const int* __restrict__ pair_images, const int* __restrict__ work_pair,
-            const int* __restrict__ work_qblock, int pair_base, const long long* __restrict__ owner_off, int* __restrict__ owner,
-            double ratio) {
+k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ packed_t, const float* __restrict__ norms,
+            const long long* __restrict__ prow_off, const int* __restrict__ nrows, const int* __restrict__ pair_images,
+            const int* __restrict__ work_pair, const int* __restrict__ work_qblock, int num_work, int pair_base,
+            const long long* __restrict__ owner_off, int* __restrict__ owner, double ratio) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   MatchSmem* sm = reinterpret_cast<MatchSmem*>(smem_raw);
   unsigned char* sQ = smem_raw + kMatchSmemHeader;
   unsigned char* sT = sQ + kQBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = work_pair[blockIdx.x];
-  const int qb = work_qblock[blockIdx.x];
-  const int img0 = pair_images[2 * pair], img1 = pair_images[2 * pair + 1];  // train = image 0, query = image 1
-  const int n0 = nrows[img0], n1 = nrows[img1];
-  const long long t0 = prow_off[img0], q0 = prow_off[img1] + (long long)qb * kQTile;
-  const int ntiles = (n0 + kTTile - 1) / kTTile;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm->full[s], 1);
       mbar_init(&sm->empty[s], 1);
-      mbar_init(&sm->tfull[s], 1);
-      mbar_init(&sm->tempty[s], 4);  // one arrival per epilogue warp
+    }
+    for (int b = 0; b < kAccBufs; ++b) {
+      mbar_init(&sm->tfull[b], 1);
+      mbar_init(&sm->tempty[b], kEpiWarps);  // one arrival per epilogue warp
     }
     mbar_init(&sm->qfull, 1);
+    mbar_init(&sm->qempty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {  // TMEM: both accumulator buffers (2 x 256 fp32 columns x 128 lanes)
+  if (warp == 0) {  // TMEM: 2 accumulator buffers x 2 halves x 128 fp32 columns x 128 lanes
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm->tmem_base)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
@@ -239,78 +317,115 @@ k_match_2nn(const __half* __restrict__ packed, const float* __restrict__ norms, 
 
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
-      const char* base = reinterpret_cast<const char*>(packed);
-      mbar_expect_tx(&sm->qfull, kQBytes);
-      tma_load_1d(sQ, base + (q0 >> 3) * kGroupBytes, kQBytes, &sm->qfull);
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t % kStages;
-        mbar_wait(&sm->empty[s], (uint32_t)(((t / kStages) & 1) ^ 1));  // slot free (passes at once the first time round)
-        mbar_expect_tx(&sm->full[s], kTBytes + (uint32_t)sizeof(float) * kTTile);
-        tma_load_1d(sT + (size_t)s * kTBytes, base + ((t0 >> 3) + (long long)t * (kTTile / 8)) * kGroupBytes, kTBytes, &sm->full[s]);
-        tma_load_1d(sm->tnorm[t % kNormBufs], norms + t0 + (long long)t * kTTile, (uint32_t)sizeof(float) * kTTile, &sm->full[s]);
+      const char* base_q = reinterpret_cast<const char*>(packed_q);
+      const char* base_t = reinterpret_cast<const char*>(packed_t);
+      uint32_t it = 0, n = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++n) {
+        const int pair = work_pair[w], qb = work_qblock[w];
+        const int img0 = pair_images[2 * pair], img1 = pair_images[2 * pair + 1];  // train = image 0, query = image 1
+        const int ntiles = (nrows[img0] + kTTile - 1) / kTTile;
+        const long long t0 = prow_off[img0], q0 = prow_off[img1] + (long long)qb * kQTile;
+        // the first train tiles of this item are requested before its query block: they only need free ring slots, while
+        // the query buffer is free only once the previous item's last MMA has retired
+        const int qpos = ntiles < 3 ? ntiles - 1 : 2;
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          if (t == qpos) {
+            mbar_wait(&sm->qempty, (n & 1u) ^ 1u);
+            mbar_expect_tx(&sm->qfull, kQBytes);
+            tma_load_1d(sQ, base_q + (q0 >> 3) * kGroupBytes, kQBytes, &sm->qfull);
+          }
+          const uint32_t s = it % kStages;
+          mbar_wait(&sm->empty[s], ((it / kStages) & 1u) ^ 1u);  // slot free (passes at once the first time round)
+          mbar_expect_tx(&sm->full[s], kTBytes);
+          tma_load_1d(sT + (size_t)s * kTBytes, base_t + ((t0 >> 3) + (long long)t * (kTTile / 8)) * kGroupBytes, kTBytes, &sm->full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ===== MMA issuer =====
-      mbar_wait(&sm->qfull, 0u);
-      const uint64_t dq = umma_desc(smem_u32(sQ));
-      for (int t = 0; t < ntiles; ++t) {
-        const int s = t % kStages;
-        const uint32_t ph = (uint32_t)((t / kStages) & 1);
-        mbar_wait(&sm->tempty[s], ph ^ 1u);  // the epilogue has drained this accumulator buffer
-        mbar_wait(&sm->full[s], ph);         // the train tile has landed
-        tc_fence_after();
-        const uint64_t dt = umma_desc(smem_u32(sT + (size_t)s * kTBytes));
+      uint32_t it = 0, n = 0;
+      const uint64_t dq0 = umma_desc(smem_u32(sQ));
+      const uint64_t dq1 = umma_desc(smem_u32(sQ + kQBytes / 2));
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++n) {
+        const int pair = work_pair[w];
+        const int ntiles = (nrows[pair_images[2 * pair]] + kTTile - 1) / kTTile;
+        mbar_wait(&sm->qfull, n & 1u);
+        for (int t = 0; t < ntiles; ++t, ++it) {
+          const uint32_t s = it % kStages, b = it % kAccBufs;
+          mbar_wait(&sm->tempty[b], ((it / kAccBufs) & 1u) ^ 1u);  // the epilogue has drained this accumulator buffer
+          mbar_wait(&sm->full[s], (it / kStages) & 1u);            // the train tile has landed
+          tc_fence_after();
+          const uint64_t dt = umma_desc(smem_u32(sT + (size_t)s * kTBytes));
+          const uint32_t acc = tmem + b * (2 * kTTile);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k)  // K = 16 per instruction = two core matrices = 256 bytes along K
-          umma_f16(tmem + (uint32_t)s * kTTile, dq + (uint64_t)(k * 16), dt + (uint64_t)(k * 16), kIdesc, k > 0 ? 1u : 0u);
-        umma_commit(&sm->empty[s]);  // shared-memory slot reusable once these MMAs have read it
-        umma_commit(&sm->tfull[s]);  // accumulator ready for the epilogue
+          for (int k = 0; k < kKp / 16; ++k)  // K = 16 per instruction = two core matrices = 256 bytes along K
+            umma_f16(acc, dq0 + (uint64_t)(k * 16), dt + (uint64_t)(k * 16), kIdesc, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < kKp / 16; ++k)
+            umma_f16(acc + kTTile, dq1 + (uint64_t)(k * 16), dt + (uint64_t)(k * 16), kIdesc, k > 0 ? 1u : 0u);
+          umma_commit(&sm->empty[s]);   // shared-memory slot reusable once these MMAs have read it
+          umma_commit(&sm->tfull[b]);   // accumulators ready for the epilogue
+        }
+        umma_commit(&sm->qempty);       // query block reusable
       }
     }
   } else {
     // ===== epilogue: one query row per thread =====
-    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int row = quarter * 32 + lane;
-    const long long qrow = (long long)qb * kQTile + row;  // row within image 1
-    const bool live = qrow < n1;
-    const float qn = live ? norms[q0 + row] : 0.f;
-    // cv::batchDistance initialises dist = FLT_MAX, idx = -1 and inserts with `d < dist[K-1]`, shifting while `dist[k] > d`
-    float d0 = FLT_MAX, d1 = FLT_MAX;
-    int i0 = -1, i1 = -1;
-    // Exact d^2 of the two kept neighbours.  sqrtf is monotone, so a candidate with d^2 >= q1 has sqrtf(d^2) >= d1 and can
-    // never pass OpenCV's `d < dist[1]`: that is the one-compare fast path; only candidates below q1 pay for the sqrt.
-    float q0d = INFINITY, q1d = INFINITY;
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t % kStages;
-      mbar_wait(&sm->tfull[s], (uint32_t)((t / kStages) & 1));
-      tc_fence_after();
-      const float* tn = sm->tnorm[t % kNormBufs];
+    const int quarter = warp & 3;        // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int half = (warp - 2) >> 2;    // which M=128 half of the query block
+    const int row = half * 128 + quarter * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kTTile);
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int pair = work_pair[w], qb = work_qblock[w];
+      const int img0 = pair_images[2 * pair], img1 = pair_images[2 * pair + 1];
+      const int n0 = nrows[img0], n1 = nrows[img1];
+      const int ntiles = (n0 + kTTile - 1) / kTTile;
+      const long long qrow = (long long)qb * kQTile + row;  // row within image 1
+      const bool live = qrow < n1;
+      const float qn = live ? norms[prow_off[img1] + qrow] : 0.f;
+      Top2 st;
+      st.b0 = st.b1 = kFarSq;
+      st.i0 = st.i1 = -1;
+      st.thr = kFarSq - qn;
+      for (int t = 0; t < ntiles; ++t, ++it) {
+        const uint32_t b = it % kAccBufs;
+        mbar_wait(&sm->tfull[b], (it / kAccBufs) & 1u);
+        tc_fence_after();
+        const uint32_t taddr = lane_addr + b * (2 * kTTile);
 #pragma unroll 1
-      for (int c = 0; c < kTTile / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * kTTile + c * 32), v);
+        for (int c = 0; c < kTTile / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(c * 32), v);
+          tmem_wait(v);
+          const int idx0 = t * kTTile + c * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float dot = __uint_as_float(v[j]);
-          const float dsq = fmaf(-2.f, dot, tn[c * 32 + j]) + qn;  // exact integers (< 2^24); +inf for padded train rows
-          if (dsq < q1d) {
-            const float d = sqrtf(dsq);  // IEEE sqrt, the float cv::BFMatcher compares
-            if (d < d1) {
-              const int idx = t * kTTile + c * 32 + j;
-              if (d0 > d) { d1 = d0; i1 = i0; q1d = q0d; d0 = d; i0 = idx; q0d = dsq; }
-              else { d1 = d; i1 = idx; q1d = dsq; }
+          for (int g = 0; g < 4; ++g) {  // groups of eight: one min tree and one warp vote when nobody has a candidate
+            const float* x = reinterpret_cast<const float*>(v) + 8 * g;
+            const float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
+            if (__any_sync(0xffffffffu, m < st.thr)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const bool cand = x[j] < st.thr;  // |t|^2 - 2 q.t, an exact integer
+                if (__any_sync(0xffffffffu, cand)) {
+                  if (__any_sync(0xffffffffu, cand && !(st.b1 < 4194304.f))) st = top2_insert_far(st, cand, x[j], qn, idx0 + 8 * g + j);
+                  else top2_insert(st, cand, x[j], qn, idx0 + 8 * g + j);
+                }
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->tempty[b]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->tempty[s]);
+      // Lowe's ratio test in double, as `matches[i][0].distance < ratio * matches[i][1].distance` evaluates it (:246);
+      // m01[trainIdx] = queryIdx with later queries overwriting earlier ones == the maximum query index per train index
+      if (live && st.i1 >= 0) {
+        const float d0 = sqrtf(st.b0), d1 = sqrtf(st.b1);  // IEEE sqrt: the floats cv::BFMatcher returns
+        if ((double)d0 < ratio * (double)d1) atomicMax(&owner[owner_off[pair - pair_base] + st.i0], (int)qrow);
+      }
     }
-    // Lowe's ratio test in double, as `matches[i][0].distance < ratio * matches[i][1].distance` evaluates it (:246);
-    // m01[trainIdx] = queryIdx with later queries overwriting earlier ones == the maximum query index per train index
-    if (live && i1 >= 0 && (double)d0 < ratio * (double)d1) atomicMax(&owner[owner_off[pair - pair_base] + i0], (int)qrow);
   }
   tc_fence_before();
   __syncthreads();
@@ -344,14 +459,56 @@ __global__ void k_match_write(const int* __restrict__ owner, const long long* __
   }
 }
 
+// Grow-only device buffer (kept in the engine's match context across calls: no cudaMalloc in a warmed-up call).
 template <class T>
 struct Buf {
   T* p = nullptr;
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)); }
-  void release() { if (p) cudaFree(p); p = nullptr; }
+  size_t cap = 0;
+  cudaError_t need(size_t n) {
+    n = std::max<size_t>(n, 1);
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct MatchCtx {
+  Buf<float> desc, norms;
+  Buf<__half> packed_q, packed_t;
+  Buf<long long> doff, prow, ooff, moff;
+  Buf<int> nrows, pairs, wp, wq, owner, counts, flag;
+  Buf<int2> matches;
+  cudaEvent_t ev[6] = {};
+  bool attr_set = false;
+  SsfmMatchStats stats = {};
+  ~MatchCtx() {
+    desc.release(); norms.release(); packed_q.release(); packed_t.release(); doff.release(); prow.release(); ooff.release(); moff.release();
+    nrows.release(); pairs.release(); wp.release(); wq.release(); owner.release(); counts.release(); flag.release(); matches.release();
+    for (auto& e : ev)
+      if (e) cudaEventDestroy(e);
+  }
+};
+void match_ctx_delete(void* p) { delete static_cast<MatchCtx*>(p); }
+
+MatchCtx* match_ctx(ssfm_handle h) {
+  void** slot = ssfm_internal_ctx_slot(h, match_ctx_delete);
+  if (!*slot) *slot = new MatchCtx();
+  return static_cast<MatchCtx*>(*slot);
+}
+
 }  // namespace
+
+extern "C" int ssfm_match_get_stats(ssfm_handle h, SsfmMatchStats* out) {
+  if (!h || !out) return mfail(SSFM_ERR_INVALID, "ssfm_match_get_stats: NULL argument");
+  *out = match_ctx(h)->stats;
+  return SSFM_OK;
+}
 
 extern "C" int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* b, int64_t* match_offsets, int32_t* matches, int64_t capacity) {
   if (!h || !b || !match_offsets) return mfail(SSFM_ERR_INVALID, "ssfm_match_pairs: NULL argument");
@@ -364,6 +521,7 @@ extern "C" int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* b, int
   if (!b->desc_offsets || !b->descriptors || !b->pair_images || (capacity > 0 && !matches))
     return mfail(SSFM_ERR_INVALID, "ssfm_match_pairs: NULL array");
   if (b->desc_offsets[0] != 0) return mfail(SSFM_ERR_INVALID, "ssfm_match_pairs: desc_offsets[0] must be 0");
+  const auto wall0 = std::chrono::steady_clock::now();
   std::vector<long long> prow(NI + 1, 0);
   std::vector<int> nrows(std::max(NI, 1), 0);
   for (int i = 0; i < NI; ++i) {
@@ -380,46 +538,51 @@ extern "C" int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* b, int
   cudaError_t e0 = cudaSetDevice(ssfm_internal_device(h));
   if (e0 != cudaSuccess) return mfail(SSFM_ERR_CUDA, cudaGetErrorString(e0));
   cudaStream_t st = ssfm_internal_stream(h);
+  MatchCtx& c = *match_ctx(h);
+  for (auto& e : c.ev)
+    if (!e) MCK(cudaEventCreate(&e));
+  c.stats = SsfmMatchStats{};
 
-  Buf<float> d_desc, d_norms;
-  Buf<__half> d_packed;
-  Buf<long long> d_doff, d_prow, d_ooff, d_moff;
-  Buf<int> d_nrows, d_pairs, d_wp, d_wq, d_owner, d_counts, d_flag;
-  Buf<int2> d_matches;
-  auto release_all = [&]() {
-    d_desc.release(); d_norms.release(); d_packed.release(); d_doff.release(); d_prow.release(); d_ooff.release(); d_moff.release();
-    d_nrows.release(); d_pairs.release(); d_wp.release(); d_wq.release(); d_owner.release(); d_counts.release(); d_flag.release();
-    d_matches.release();
-  };
-  MCK(d_desc.alloc((size_t)rows * kD));
-  MCK(d_packed.alloc((size_t)prows * kD));
-  MCK(d_norms.alloc((size_t)prows + kTTile));
-  MCK(d_doff.alloc(NI + 1));
-  MCK(d_prow.alloc(NI + 1));
-  MCK(d_nrows.alloc(NI));
-  MCK(d_pairs.alloc((size_t)2 * P));
-  MCK(d_flag.alloc(1));
-  if (rows > 0) MCK(cudaMemcpyAsync(d_desc.p, b->descriptors, sizeof(float) * (size_t)rows * kD, cudaMemcpyHostToDevice, st));
-  MCK(cudaMemcpyAsync(d_doff.p, b->desc_offsets, sizeof(long long) * (NI + 1), cudaMemcpyHostToDevice, st));
-  MCK(cudaMemcpyAsync(d_prow.p, prow.data(), sizeof(long long) * (NI + 1), cudaMemcpyHostToDevice, st));
-  if (NI > 0) MCK(cudaMemcpyAsync(d_nrows.p, nrows.data(), sizeof(int) * NI, cudaMemcpyHostToDevice, st));
-  MCK(cudaMemcpyAsync(d_pairs.p, b->pair_images, sizeof(int) * 2 * (size_t)P, cudaMemcpyHostToDevice, st));
-  MCK(cudaMemsetAsync(d_flag.p, 0, sizeof(int), st));
+  MCK(c.desc.need((size_t)rows * kD));
+  MCK(c.packed_q.need((size_t)prows * kKp));
+  MCK(c.packed_t.need((size_t)prows * kKp));
+  MCK(c.norms.need((size_t)prows));
+  MCK(c.doff.need(NI + 1));
+  MCK(c.prow.need(NI + 1));
+  MCK(c.nrows.need(NI));
+  MCK(c.pairs.need((size_t)2 * P));
+  MCK(c.flag.need(1));
+  MCK(cudaEventRecord(c.ev[0], st));
+  if (rows > 0) MCK(cudaMemcpyAsync(c.desc.p, b->descriptors, sizeof(float) * (size_t)rows * kD, cudaMemcpyHostToDevice, st));
+  MCK(cudaMemcpyAsync(c.doff.p, b->desc_offsets, sizeof(long long) * (NI + 1), cudaMemcpyHostToDevice, st));
+  MCK(cudaMemcpyAsync(c.prow.p, prow.data(), sizeof(long long) * (NI + 1), cudaMemcpyHostToDevice, st));
+  if (NI > 0) MCK(cudaMemcpyAsync(c.nrows.p, nrows.data(), sizeof(int) * NI, cudaMemcpyHostToDevice, st));
+  MCK(cudaMemcpyAsync(c.pairs.p, b->pair_images, sizeof(int) * 2 * (size_t)P, cudaMemcpyHostToDevice, st));
+  MCK(cudaMemsetAsync(c.flag.p, 0, sizeof(int), st));
   if (prows > 0) {
     const long long threads = prows * 16;
-    k_desc_pack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_desc.p, d_doff.p, d_prow.p, NI, prows, d_packed.p, d_norms.p, d_flag.p);
+    k_desc_pack<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(c.desc.p, c.doff.p, c.prow.p, NI, prows, c.packed_q.p, c.packed_t.p,
+                                                                   c.norms.p, c.flag.p);
     MCK(cudaGetLastError());
   }
+  MCK(cudaEventRecord(c.ev[1], st));
   int bad = 0;
-  MCK(cudaMemcpyAsync(&bad, d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MCK(cudaMemcpyAsync(&bad, c.flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   MCK(cudaStreamSynchronize(st));
-  d_desc.release();
-  if (bad) {
-    release_all();
+  if (bad)
     return mfail(SSFM_ERR_INVALID, "ssfm_match_pairs: descriptors must be integers in [0, 255] stored as float (cv::SIFT); "
                                    "the exactness of the fp16 tensor-core path depends on it");
+  {
+    float ms = 0.f;
+    MCK(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+    c.stats.pack_ms = ms;
+    c.stats.h2d_bytes = (int64_t)sizeof(float) * rows * kD + (int64_t)sizeof(int) * 2 * P;
   }
-  MCK(cudaFuncSetAttribute(k_match_2nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemBytes));
+  if (!c.attr_set) {
+    MCK(cudaFuncSetAttribute(k_match_2nn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMatchSmemBytes));
+    c.attr_set = true;
+  }
+  const int num_sms = std::max(1, ssfm_internal_num_sms(h));
 
   // passes of pairs: the owner table (one int per train keypoint per pair) is bounded to 64 Mi entries
   const long long kOwnerCap = 64ll << 20;
@@ -437,52 +600,67 @@ extern "C" int ssfm_match_pairs(ssfm_handle h, const SsfmDescriptorBatch* b, int
       if (p1 > p0 && own + n0 > kOwnerCap) break;
       own += n0;
       ooff.push_back(own);
-      if (n0 >= 2)  // with fewer than two train descriptors knnMatch(k=2) has no second neighbour: no match passes the test
+      if (n0 >= 2) {  // with fewer than two train descriptors knnMatch(k=2) has no second neighbour: no match passes the test
         for (int qb = 0; qb * kQTile < n1; ++qb) { wp.push_back(p1); wq.push_back(qb); }
+        c.stats.distance_evaluations += (int64_t)n0 * n1;
+        c.stats.mma_tiles += (int64_t)((n0 + kTTile - 1) / kTTile) * ((n1 + kQTile - 1) / kQTile);
+      }
       ++p1;
     }
     const int np = p1 - p0;
-    d_owner.release(); d_ooff.release(); d_wp.release(); d_wq.release(); d_counts.release(); d_moff.release(); d_matches.release();
-    MCK(d_owner.alloc((size_t)own));
-    MCK(d_ooff.alloc(np + 1));
-    MCK(d_wp.alloc(wp.size()));
-    MCK(d_wq.alloc(wq.size()));
-    MCK(d_counts.alloc(np));
-    MCK(d_moff.alloc(np + 1));
-    MCK(cudaMemsetAsync(d_owner.p, 0xff, sizeof(int) * (size_t)std::max<long long>(own, 1), st));
-    MCK(cudaMemcpyAsync(d_ooff.p, ooff.data(), sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
+    MCK(c.owner.need((size_t)own));
+    MCK(c.ooff.need(np + 1));
+    MCK(c.wp.need(wp.size()));
+    MCK(c.wq.need(wq.size()));
+    MCK(c.counts.need(np));
+    MCK(c.moff.need(np + 1));
+    MCK(cudaMemsetAsync(c.owner.p, 0xff, sizeof(int) * (size_t)std::max<long long>(own, 1), st));
+    MCK(cudaMemcpyAsync(c.ooff.p, ooff.data(), sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
+    MCK(cudaEventRecord(c.ev[2], st));
     if (!wp.empty()) {
-      MCK(cudaMemcpyAsync(d_wp.p, wp.data(), sizeof(int) * wp.size(), cudaMemcpyHostToDevice, st));
-      MCK(cudaMemcpyAsync(d_wq.p, wq.data(), sizeof(int) * wq.size(), cudaMemcpyHostToDevice, st));
-      k_match_2nn<<<(unsigned)wp.size(), kMatchThreads, kMatchSmemBytes, st>>>(d_packed.p, d_norms.p, d_prow.p, d_nrows.p, d_pairs.p, d_wp.p,
-                                                                              d_wq.p, p0, d_ooff.p, d_owner.p, b->ratio);
+      MCK(cudaMemcpyAsync(c.wp.p, wp.data(), sizeof(int) * wp.size(), cudaMemcpyHostToDevice, st));
+      MCK(cudaMemcpyAsync(c.wq.p, wq.data(), sizeof(int) * wq.size(), cudaMemcpyHostToDevice, st));
+      const int grid = (int)std::min<size_t>(wp.size(), (size_t)num_sms);
+      MCK(cudaEventRecord(c.ev[2], st));
+      k_match_2nn<<<grid, kMatchThreads, kMatchSmemBytes, st>>>(c.packed_q.p, c.packed_t.p, c.norms.p, c.prow.p, c.nrows.p, c.pairs.p, c.wp.p,
+                                                               c.wq.p, (int)wp.size(), p0, c.ooff.p, c.owner.p, b->ratio);
       MCK(cudaGetLastError());
+      c.stats.knn_launches += 1;
+      c.stats.ctas += grid;
     }
-    k_match_count<<<(np + 3) / 4, 128, 0, st>>>(d_owner.p, d_ooff.p, np, d_counts.p);
+    MCK(cudaEventRecord(c.ev[3], st));
+    k_match_count<<<(np + 3) / 4, 128, 0, st>>>(c.owner.p, c.ooff.p, np, c.counts.p);
     MCK(cudaGetLastError());
     counts.assign(np, 0);
-    MCK(cudaMemcpyAsync(counts.data(), d_counts.p, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
+    MCK(cudaMemcpyAsync(counts.data(), c.counts.p, sizeof(int) * np, cudaMemcpyDeviceToHost, st));
     MCK(cudaStreamSynchronize(st));
     moff.assign(np + 1, 0);
     for (int k = 0; k < np; ++k) {
       moff[k + 1] = moff[k] + counts[k];
       match_offsets[p0 + k + 1] = total + moff[k + 1];
     }
-    if (total + moff[np] > capacity) {
-      release_all();
+    if (total + moff[np] > capacity)
       return mfail(SSFM_ERR_INVALID, "ssfm_match_pairs: `capacity` is too small (sum over pairs of min(n0, n1) always suffices)");
-    }
     if (moff[np] > 0) {
-      MCK(d_matches.alloc((size_t)moff[np]));
-      MCK(cudaMemcpyAsync(d_moff.p, moff.data(), sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
-      k_match_write<<<(np + 3) / 4, 128, 0, st>>>(d_owner.p, d_ooff.p, np, d_moff.p, d_matches.p);
+      MCK(c.matches.need((size_t)moff[np]));
+      MCK(cudaMemcpyAsync(c.moff.p, moff.data(), sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
+      k_match_write<<<(np + 3) / 4, 128, 0, st>>>(c.owner.p, c.ooff.p, np, c.moff.p, c.matches.p);
       MCK(cudaGetLastError());
-      MCK(cudaMemcpyAsync(matches + 2 * total, d_matches.p, sizeof(int2) * (size_t)moff[np], cudaMemcpyDeviceToHost, st));
-      MCK(cudaStreamSynchronize(st));
+      MCK(cudaMemcpyAsync(matches + 2 * total, c.matches.p, sizeof(int2) * (size_t)moff[np], cudaMemcpyDeviceToHost, st));
+    }
+    MCK(cudaEventRecord(c.ev[4], st));
+    MCK(cudaStreamSynchronize(st));
+    {
+      float ms = 0.f;
+      MCK(cudaEventElapsedTime(&ms, c.ev[2], c.ev[3]));
+      c.stats.knn_ms += ms;
+      MCK(cudaEventElapsedTime(&ms, c.ev[3], c.ev[4]));
+      c.stats.compact_ms += ms;
+      c.stats.d2h_bytes += (int64_t)sizeof(int2) * moff[np] + (int64_t)sizeof(int) * np;
     }
     total += moff[np];
     p0 = p1;
   }
-  release_all();
+  c.stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
   return SSFM_OK;
 }

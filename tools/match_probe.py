@@ -32,6 +32,10 @@ dt = time.perf_counter() - t0
 flop = 2.0 * n * n * 128 * len(pairs)
 print("pairs %d x (%d x %d): %.3f s  %.1f pairs/s  %.1f TFLOP/s (fp16 tensor)  %.3e distance evaluations/s  matches/pair %.0f" % (
     len(pairs), n, n, dt, len(pairs) / dt, flop / dt / 1e12, float(n) * n * len(pairs) / dt, mo[-1] / len(pairs)))
+ms = eng.match_stats()
+print("  stages: pack+H2D %.2f ms, k_match_2nn %.2f ms (%.1f TFLOP/s algorithmic, %.1f executed), compaction+D2H %.2f ms, call %.2f ms; tiles %d, ctas %d" % (
+    ms.pack_ms, ms.knn_ms, flop / (ms.knn_ms * 1e-3) / 1e12, ms.mma_tiles * 2.0 * 256 * 128 * 144 / (ms.knn_ms * 1e-3) / 1e12,
+    ms.compact_ms, ms.total_ms, ms.mma_tiles, ms.ctas))
 import match_oracle as MO  # noqa: E402
 t0 = time.perf_counter()
 om = MO.match(descs[pairs[0][0]], descs[pairs[0][1]])
