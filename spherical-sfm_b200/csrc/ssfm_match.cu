@@ -247,37 +247,38 @@ constexpr size_t kMatchSmemHeader = 1024;
 static_assert(sizeof(MatchSmem) <= kMatchSmemHeader, "header");
 constexpr size_t kMatchSmemBytes = kMatchSmemHeader + kQBytes + kStages * kTBytes;
 
-// Running two nearest neighbours of one query row, kept as exact squared distances.
+// Running two nearest neighbours of one query row.  Everything is kept in the accumulator's domain a = d^2 - |q|^2 (what
+// the tensor core delivers: |t|^2 - 2 q.t, an exact integer), so a clean distance costs one min and the bookkeeping is
+// min / max / select only.
 struct Top2 {
-  float b0, b1;  // d^2 of the nearest / second nearest (kFarSq: none yet)
+  float a0, a1;  // nearest / second nearest (kFarSq: none yet); a1 is the candidate threshold
   int i0, i1;
-  float thr;     // b1 - |q|^2: an accumulator value below it is a candidate
 };
-// A candidate: acc = d^2 - |q|^2 < thr.  cv::batchDistance inserts with `d < dist[K-1]`, shifting while `dist[k] > d`, on
-// d = sqrtf(d^2).  sqrtf is monotone, and injective on integers below 2^22 (the gap sqrt(a+1) - sqrt(a) >= 1/(2*2048) is two
-// ulps there), so below 2^22 the float comparisons equal the integer ones (top2_insert, branch-free, the common case);
-// above -- only while the second neighbour is still far -- the floats themselves are compared (top2_insert_far).
-__device__ __forceinline__ void top2_insert(Top2& s, bool cand, float acc, float qn, int idx) {
-  const float dsq = acc + qn;
-  const bool first = dsq < s.b0;
-  s.b1 = cand ? (first ? s.b0 : dsq) : s.b1;
-  s.i1 = cand ? (first ? s.i0 : idx) : s.i1;
-  s.b0 = (cand && first) ? dsq : s.b0;
-  s.i0 = (cand && first) ? idx : s.i0;
-  s.thr = s.b1 - qn;
-}
-__device__ __noinline__ Top2 top2_insert_far(Top2 s, bool cand, float acc, float qn, int idx) {
-  const float dsq = acc + qn;
-  bool first = dsq < s.b0;
-  if (!(s.b1 < 4194304.f)) {
-    const float d = sqrtf(dsq);
-    cand = cand && d < sqrtf(s.b1);
-    first = sqrtf(s.b0) > d;
+// cv::batchDistance inserts train index j with `d < dist[K-1]`, shifting while `dist[k] > d`, on d = sqrtf(d^2), i.e. it
+// keeps the two smallest (d, j) in lexicographic order.  sqrtf is monotone, and injective on integers below 2^22 (the gap
+// sqrt(a+1) - sqrt(a) >= 1/(2*2048) is two ulps there), so while the second neighbour is below 2^22 the float comparisons
+// equal the integer ones: eight branch-free steps (top2_group).  Above -- only while the second neighbour is still far --
+// the floats themselves are compared (top2_group_far).
+__device__ __forceinline__ void top2_group(Top2& s, const float* x, int idx) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool first = x[j] < s.a0, cand = x[j] < s.a1;
+    s.i1 = cand ? (first ? s.i0 : idx + j) : s.i1;
+    s.i0 = first ? idx + j : s.i0;
+    s.a1 = fminf(s.a1, fmaxf(s.a0, x[j]));
+    s.a0 = fminf(s.a0, x[j]);
   }
-  if (cand) {
-    if (first) { s.b1 = s.b0; s.i1 = s.i0; s.b0 = dsq; s.i0 = idx; }
-    else { s.b1 = dsq; s.i1 = idx; }
-    s.thr = s.b1 - qn;
+}
+__device__ __noinline__ Top2 top2_group_far(Top2 s, float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7,
+                                            float qn, int idx) {
+  const float x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    if (!(x[j] < s.a1)) continue;
+    const float d = sqrtf(x[j] + qn);
+    if (!(d < sqrtf(s.a1 + qn))) continue;
+    if (sqrtf(s.a0 + qn) > d) { s.a1 = s.a0; s.i1 = s.i0; s.a0 = x[j]; s.i0 = idx + j; }
+    else { s.a1 = x[j]; s.i1 = idx + j; }
   }
   return s;
 }
@@ -385,9 +386,9 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
       const bool live = qrow < n1;
       const float qn = live ? norms[prow_off[img1] + qrow] : 0.f;
       Top2 st;
-      st.b0 = st.b1 = kFarSq;
+      st.a0 = st.a1 = kFarSq;
       st.i0 = st.i1 = -1;
-      st.thr = kFarSq - qn;
+      const float far_a = 4194304.f - qn;  // second neighbour at or above it: d^2 >= 2^22, compare the floats
       for (int t = 0; t < ntiles; ++t, ++it) {
         const uint32_t b = it % kAccBufs;
         mbar_wait(&sm->tfull[b], (it / kAccBufs) & 1u);
@@ -398,20 +399,22 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)(c * 32), v);
           tmem_wait(v);
+          const float* x = reinterpret_cast<const float*>(v);
           const int idx0 = t * kTTile + c * 32;
+          float m[4];  // groups of eight: one min tree and one warp vote when nobody has a candidate
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {  // groups of eight: one min tree and one warp vote when nobody has a candidate
-            const float* x = reinterpret_cast<const float*>(v) + 8 * g;
-            const float m = fminf(fminf(fminf(x[0], x[1]), fminf(x[2], x[3])), fminf(fminf(x[4], x[5]), fminf(x[6], x[7])));
-            if (__any_sync(0xffffffffu, m < st.thr)) {
+          for (int g = 0; g < 4; ++g)
+            m[g] = fminf(fminf(fminf(x[8 * g], x[8 * g + 1]), fminf(x[8 * g + 2], x[8 * g + 3])),
+                         fminf(fminf(x[8 * g + 4], x[8 * g + 5]), fminf(x[8 * g + 6], x[8 * g + 7])));
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const bool cand = x[j] < st.thr;  // |t|^2 - 2 q.t, an exact integer
-                if (__any_sync(0xffffffffu, cand)) {
-                  if (__any_sync(0xffffffffu, cand && !(st.b1 < 4194304.f))) st = top2_insert_far(st, cand, x[j], qn, idx0 + 8 * g + j);
-                  else top2_insert(st, cand, x[j], qn, idx0 + 8 * g + j);
-                }
-              }
+          for (int g = 0; g < 4; ++g) {
+            const bool hit = m[g] < st.a1;
+            if (__any_sync(0xffffffffu, hit)) {
+              if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
+                st = top2_group_far(st, x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3], x[8 * g + 4], x[8 * g + 5], x[8 * g + 6],
+                                    x[8 * g + 7], qn, idx0 + 8 * g);
+              else
+                top2_group(st, x + 8 * g, idx0 + 8 * g);
             }
           }
         }
@@ -422,7 +425,7 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
       // Lowe's ratio test in double, as `matches[i][0].distance < ratio * matches[i][1].distance` evaluates it (:246);
       // m01[trainIdx] = queryIdx with later queries overwriting earlier ones == the maximum query index per train index
       if (live && st.i1 >= 0) {
-        const float d0 = sqrtf(st.b0), d1 = sqrtf(st.b1);  // IEEE sqrt: the floats cv::BFMatcher returns
+        const float d0 = sqrtf(st.a0 + qn), d1 = sqrtf(st.a1 + qn);  // exact d^2, IEEE sqrt: the floats cv::BFMatcher returns
         if ((double)d0 < ratio * (double)d1) atomicMax(&owner[owner_off[pair - pair_base] + st.i0], (int)qrow);
       }
     }
