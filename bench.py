@@ -304,6 +304,55 @@ def config_block(S, eng, fp32_peak, args):
     return out
 
 
+def matching_block(S, eng, args, ni=64, n=4000):
+    rng = np.random.default_rng(0)
+    base = np.minimum(rng.gamma(0.6, 30.0, (n, 128)), 255).astype(np.int32)
+    descs = []
+    for _ in range(ni):  # consecutive images share ~40 % of their descriptors (perturbed), like overlapping views
+        d = np.minimum(rng.gamma(0.6, 30.0, (n, 128)), 255).astype(np.int32)
+        keep = rng.random(n) < 0.4
+        d[keep] = np.clip(base[keep] + rng.integers(-2, 3, (int(keep.sum()), 128)), 0, 255)
+        descs.append(d.astype(np.float32))
+    allrows = np.concatenate(descs)
+    offs = (np.arange(ni + 1) * n).astype(np.int64)
+    pairs = np.array([(i, j) for i in range(ni) for j in range(i + 1, ni)], np.int32)
+    eng.match_pairs(allrows, offs, pairs[:64])
+    best, st = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        mo, mm = eng.match_pairs(allrows, offs, pairs)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, st = dt, eng.match_stats()
+    flop = 2.0 * n * n * 128 * len(pairs)
+    peak, src = None, "MEASURED_PEAKS.json absent"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak = float(json.load(f)["bf16_tflops"])
+            src = "MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone)"
+    except Exception:
+        peak, src = 2250.0, "nominal dense bf16/fp16 (MEASURED_PEAKS.json absent)"
+    tf = flop / (st.knn_ms * 1e-3) / 1e12
+    out = {"workload": "match_exhaustive: %d images x %d descriptors (128-D SIFT-like), %d pairs, ratio 0.75" % (ni, n, len(pairs)),
+           "e2e_ms": best * 1e3, "e2e_pairs_per_sec": len(pairs) / best, "matches_per_pair": float(mo[-1]) / len(pairs),
+           "stage_ms": {"h2d_pack": st.pack_ms, "k_match_2nn": st.knn_ms, "compact_d2h": st.compact_ms},
+           "distance_evals_per_sec_in_kernel": float(st.distance_evaluations) / (st.knn_ms * 1e-3),
+           "roofline": {"bound": "tensor", "kernel": "k_match_2nn", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                        "peak_source": src, "flop_convention": "2 * n0 * n1 * 128 per pair (the executed contraction is K = 144: "
+                        "%.1f TFLOP/s)" % (st.mma_tiles * 2.0 * 256 * 128 * 144 / (st.knn_ms * 1e-3) / 1e12)},
+           "h2d_bytes": int(st.h2d_bytes), "d2h_bytes": int(st.d2h_bytes)}
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import match_oracle as MO
+        t0 = time.perf_counter()
+        om = MO.match(descs[0], descs[1])
+        dc = time.perf_counter() - t0
+        a, b = int(mo[0]), int(mo[1])
+        out["cpu"] = {"pairs_per_sec": 1.0 / dc, "cores": 1, "kind": "port (numpy restatement of cv::BFMatcher::knnMatch + ratio test)",
+                      "sample": "1 pair in %.2f s" % dc, "identical_to_device": bool(len(om) == b - a and (mm[a:b] == om).all())}
+    return out
+
+
 def strong_scaling_leg(S, torch, dist, eng, args, rank, world, table_1gpu, barrier):
     """Strong scaling: ONE C3 batch (the one rank 0 processed alone in the weak leg: seed 1234) split over the ranks by
     ssfm_partition_pairs; each rank runs its shard end to end from pinned host memory (H2D inside the timed region), the
@@ -630,6 +679,12 @@ def main():
                                  "mean_iterations": float(it_t.mean())}
     except Exception as exc:
         line["retriangulate"] = {"error": str(exc)}
+    # Descriptor matching: match_exhaustive over 64 images x 4000 SIFT-like descriptors = 2016 pairs,
+    # host buffers in and out; the tcgen05 kernel's rate against the measured dense bf16/fp16 tensor peak
+    try:
+        line["matching"] = matching_block(S, eng, args)
+    except Exception as exc:
+        line["matching"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_leg(rays_np[:min(P, 32768) * N], N, args.cpu_seconds)
     print(json.dumps(line))

@@ -257,11 +257,12 @@ struct Top2 {
 // cv::batchDistance inserts train index j with `d < dist[K-1]`, shifting while `dist[k] > d`, on d = sqrtf(d^2), i.e. it
 // keeps the two smallest (d, j) in lexicographic order.  sqrtf is monotone, and injective on integers below 2^22 (the gap
 // sqrt(a+1) - sqrt(a) >= 1/(2*2048) is two ulps there), so while the second neighbour is below 2^22 the float comparisons
-// equal the integer ones: eight branch-free steps (top2_group).  Above -- only while the second neighbour is still far --
+// equal the integer ones: four branch-free steps (top2_group).  Above -- only while the second neighbour is still far --
 // the floats themselves are compared (top2_group_far).
-__device__ __forceinline__ void top2_group(Top2& s, const float* x, int idx) {
+__device__ __forceinline__ float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }  // one FMNMX3
+__device__ __forceinline__ void top2_group(Top2& s, const float* x, int idx) {  // four consecutive train rows
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     const bool first = x[j] < s.a0, cand = x[j] < s.a1;
     s.i1 = cand ? (first ? s.i0 : idx + j) : s.i1;
     s.i0 = first ? idx + j : s.i0;
@@ -269,11 +270,10 @@ __device__ __forceinline__ void top2_group(Top2& s, const float* x, int idx) {
     s.a0 = fminf(s.a0, x[j]);
   }
 }
-__device__ __noinline__ Top2 top2_group_far(Top2 s, float x0, float x1, float x2, float x3, float x4, float x5, float x6, float x7,
-                                            float qn, int idx) {
-  const float x[8] = {x0, x1, x2, x3, x4, x5, x6, x7};
+__device__ __noinline__ Top2 top2_group_far(Top2 s, float x0, float x1, float x2, float x3, float qn, int idx) {
+  const float x[4] = {x0, x1, x2, x3};
 #pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     if (!(x[j] < s.a1)) continue;
     const float d = sqrtf(x[j] + qn);
     if (!(d < sqrtf(s.a1 + qn))) continue;
@@ -401,20 +401,26 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
           tmem_wait(v);
           const float* x = reinterpret_cast<const float*>(v);
           const int idx0 = t * kTTile + c * 32;
-          float m[4];  // groups of eight: one min tree and one warp vote when nobody has a candidate
+          // groups of eight = two of four: one min tree and one warp vote per eight when nobody has a candidate; otherwise
+          // the four-groups that hold one are walked
+          float m4[8], m8[4];
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            m[g] = fminf(fminf(fminf(x[8 * g], x[8 * g + 1]), fminf(x[8 * g + 2], x[8 * g + 3])),
-                         fminf(fminf(x[8 * g + 4], x[8 * g + 5]), fminf(x[8 * g + 6], x[8 * g + 7])));
+          for (int h = 0; h < 8; ++h) m4[h] = fminf(min3f(x[4 * h], x[4 * h + 1], x[4 * h + 2]), x[4 * h + 3]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) m8[g] = fminf(m4[2 * g], m4[2 * g + 1]);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const bool hit = m[g] < st.a1;
-            if (__any_sync(0xffffffffu, hit)) {
-              if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
-                st = top2_group_far(st, x[8 * g], x[8 * g + 1], x[8 * g + 2], x[8 * g + 3], x[8 * g + 4], x[8 * g + 5], x[8 * g + 6],
-                                    x[8 * g + 7], qn, idx0 + 8 * g);
-              else
-                top2_group(st, x + 8 * g, idx0 + 8 * g);
+            if (__any_sync(0xffffffffu, m8[g] < st.a1)) {
+#pragma unroll
+              for (int h = 2 * g; h < 2 * g + 2; ++h) {
+                const bool hit = m4[h] < st.a1;
+                if (__any_sync(0xffffffffu, hit)) {
+                  if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
+                    st = top2_group_far(st, x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3], qn, idx0 + 4 * h);
+                  else
+                    top2_group(st, x + 4 * h, idx0 + 4 * h);
+                }
+              }
             }
           }
         }

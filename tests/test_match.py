@@ -84,6 +84,53 @@ def test_match_pairs_full_size_images(S, engine):
     assert mo[1] > 800
 
 
+def _far_tie_images(rng, nq=60, nt=500):
+    """Train rows at d^2 ~ 7.8e6 from every query, differing from each other by a few units: above 2^22 sqrtf maps
+    neighbouring integers to the same float, and cv::BFMatcher compares the floats (first index wins a float tie)."""
+    base_t = np.full(128, 255, np.int32)
+    base_t[120:] = 7
+    train = np.tile(base_t, (nt, 1))
+    train[:, 120:] += (rng.random((nt, 8)) < 0.3).astype(np.int32)  # d^2 = D + number of bumped bins
+    train[:, :4] -= rng.integers(0, 2, (nt, 4))
+    query = np.zeros((nq, 128), np.int32)
+    query[:, 120:] = 7
+    query[:, 4:12] += rng.integers(0, 3, (nq, 8))
+    return train.astype(np.float32), query.astype(np.float32)
+
+
+def test_far_regime_data_separates_float_from_integer_ordering():
+    """The far-regime case below has teeth: ordering by the exact integer d^2 gives a different 2-NN than ordering by
+    sqrtf(d^2) in float, which is what the restated cv::BFMatcher (and the kernel) must do."""
+    train, query = _far_tie_images(np.random.default_rng(12))
+    d2 = ((query[:, None, :].astype(np.int64) - train[None, :, :].astype(np.int64)) ** 2).sum(2)
+    assert d2.min() > 2 ** 22
+    idx, _ = MO.knn2(train, query)
+    by_integer = np.argsort(d2, axis=1, kind="stable")[:, :2]
+    assert (by_integer != idx).any(1).sum() > 10
+
+
+@pytest.mark.gpu
+def test_match_far_regime_float_ties(S, engine):
+    """Squared distances above 2^22 (see _far_tie_images), mixed with near rows so both regimes and the switch between
+    them are walked; several ratios, including > 1 so that float-tied neighbours pass the test and show up in the output."""
+    rng = np.random.default_rng(12)
+    descs, pairs = [], []
+    for k in range(12):
+        train, query = _far_tie_images(rng, nq=40 + 7 * k, nt=300 + 31 * k)
+        if k % 3 == 1:  # a few near rows in the middle of the train image: the second neighbour drops below 2^22 there
+            train[150:153] = query[:3]
+        if k % 3 == 2:  # exactly one near row: the nearest is near, the second stays far
+            train[200] = query[5]
+        descs += [train, query]
+        pairs += [(2 * k, 2 * k + 1), (2 * k + 1, 2 * k)]
+    offs = np.concatenate([[0], np.cumsum([len(d) for d in descs])]).astype(np.int64)
+    for ratio in (0.75, 1.0, 1.5):
+        mo, mm = engine.match_pairs(np.concatenate(descs), offs, np.array(pairs, np.int32), ratio)
+        oo, om = MO.match_exhaustive(descs, pairs, ratio)
+        assert mo.tolist() == oo.tolist() and (mm == om).all()
+    assert oo[-1] > 100
+
+
 @pytest.mark.gpu
 def test_match_pairs_rejects_non_integer_descriptors(S, engine):
     rng = np.random.default_rng(5)
