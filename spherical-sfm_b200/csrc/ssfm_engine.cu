@@ -136,6 +136,7 @@ struct Worker {
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned char> has;  // pre-emptive driver: hypothesis-has-a-model flags
   DevBuf<SixState> six_states;  // six-point estimator
+  DevBuf<double> six_M;         // the ten cubics of every look-ahead sample (global scratch of k_sixpt_sample_solve)
   DevBuf<LMState> lm_states;    // stragglers handed from k_refit_small to k_refit_long
   DevBuf<int> long_list;
   DevBuf<int> six_nm, pk_id, pk_count;
@@ -152,7 +153,7 @@ struct Worker {
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release(); has.release();
     lm_states.release(); long_list.release();
-    six_states.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
+    six_states.release(); six_M.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
   }
 };
 
@@ -299,6 +300,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         SSFM_WCK(w.navail.ensure(nq));
         SSFM_WCK(w.models.ensure((size_t)nq * R * kSixMaxModels * kSixRecord));
         SSFM_WCK(w.six_nm.ensure((size_t)nq * R));
+        SSFM_WCK(w.six_M.ensure(((size_t)nq * R + kSixSamplesPerBlock) * sixc::kMSize));
         SSFM_WCK(w.s32m.ensure((size_t)nq * R * kSixSlotModels));
         SSFM_WCK(w.pk_G.ensure((size_t)nq * R * kSixMaxModels * 9));
         SSFM_WCK(w.pk_id.ensure((size_t)nq * R * kSixMaxModels));
@@ -314,9 +316,10 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         while (count > 0) {
           const int cap = round == 0 ? first_cap : round_cap;
           SSFM_WCK(cudaEventRecord(evA, w.stream));
-          dim3 gs(count, (cap + 63) / 64);
-          k_sixpt_sample_solve<<<gs, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, q0, act, w.navail.p, w.six_states.p, R,
-                                                        w.models.p, w.six_nm.p, w.pk_G.p, w.pk_id.p, w.pk_count.p, w.s32m.p);
+          dim3 gs(count, (cap + kSixSamplesPerBlock - 1) / kSixSamplesPerBlock);
+          k_sixpt_sample_solve<<<gs, kSixSolveThreads, kSixSolveSmem, w.stream>>>(P, h->d_rays, h->offsets.p, q0, act, w.navail.p, w.six_states.p, R,
+                                                        w.models.p, w.six_nm.p, w.pk_G.p, w.pk_id.p, w.pk_count.p, w.s32m.p,
+                                                        w.six_M.p);
           SSFM_WCK(cudaGetLastError());
           SSFM_WCK(cudaEventRecord(evB, w.stream));
           dim3 gc(count, (cap * kSixMaxModels + 127) / 128);
@@ -1207,21 +1210,23 @@ int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t
     if (samples6[i] < 0 || samples6[i] >= n) return fail(SSFM_ERR_INVALID, "ssfm_sixpt_solve: sample index out of range");
   if (num_samples == 0) return SSFM_OK;
   SSFM_CK(cudaSetDevice(h->device));
-  DevBuf<double> d_rays, d_models;
+  DevBuf<double> d_rays, d_models, d_M;
   DevBuf<int> d_samples, d_nm;
   SSFM_CK(d_rays.ensure((size_t)n * 6));
+  SSFM_CK(d_M.ensure(((size_t)num_samples + kSixSamplesPerBlock) * sixc::kMSize));
   SSFM_CK(d_models.ensure((size_t)num_samples * kSixMaxModels * 7));
   SSFM_CK(d_samples.ensure((size_t)num_samples * 6));
   SSFM_CK(d_nm.ensure(num_samples));
   SSFM_CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(d_samples.p, samples6, sizeof(int) * 6 * num_samples, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemsetAsync(d_models.p, 0, sizeof(double) * num_samples * kSixMaxModels * 7, h->stream));
-  k_sixpt_solve_samples<<<(num_samples + 63) / 64, 64, 0, h->stream>>>(d_rays.p, d_samples.p, num_samples, d_models.p, d_nm.p);
+  k_sixpt_solve_samples<<<(num_samples + kSixSamplesPerBlock - 1) / kSixSamplesPerBlock, kSixSolveThreads, kSixSolveSmem, h->stream>>>(
+      d_rays.p, d_samples.p, num_samples, d_models.p, d_nm.p, d_M.p);
   SSFM_CK(cudaGetLastError());
   SSFM_CK(cudaMemcpyAsync(models, d_models.p, sizeof(double) * num_samples * kSixMaxModels * 7, cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaMemcpyAsync(num_models, d_nm.p, sizeof(int) * num_samples, cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
-  d_rays.release(); d_models.release(); d_samples.release(); d_nm.release();
+  d_rays.release(); d_models.release(); d_samples.release(); d_nm.release(); d_M.release();
   return SSFM_OK;
 }
 

@@ -152,16 +152,30 @@ SSFM_HD_NOINLINE void constraint_matrices(const double Fb[3][9], double M[3][10]
     }
 }
 
-constexpr int kN = 20;
+constexpr int kN = 16;  // the deflated companion matrix (see companion16)
+
+// Where a solver instance keeps its kN x kN matrix.  LocalMat: a plain array (host build, hooks).  StridedMat: element
+// (i, j) of thread t at base[(i * kN + j) * stride + t] -- shared memory of the batched kernel: every lane of a warp that
+// touches the same (i, j) hits a different bank, and the 2 KB per instance never go through local memory.
+struct LocalMat {
+  double a[kN][kN];
+  SSFM_HD double& operator()(int i, int j) { return a[i][j]; }
+};
+struct StridedMat {
+  double* base;
+  int stride;
+  SSFM_HD double& operator()(int i, int j) { return base[(size_t)(i * kN + j) * stride]; }
+};
 
 // Eigenvalue-preserving diagonal scaling (powers of two).
-SSFM_HD_NOINLINE void balance(double (*a)[kN]) {
+template <class Mat>
+SSFM_HD_NOINLINE void balance(Mat& a) {
   for (int pass = 0; pass < 20; ++pass) {
     bool done = true;
     for (int i = 0; i < kN; ++i) {
       double r = 0.0, c = 0.0;
       for (int j = 0; j < kN; ++j)
-        if (j != i) { c += fabs(a[j][i]); r += fabs(a[i][j]); }
+        if (j != i) { c += fabs(a(j, i)); r += fabs(a(i, j)); }
       if (c != 0.0 && r != 0.0) {
         double g = r * 0.5, f = 1.0;
         const double s = c + r;
@@ -171,8 +185,8 @@ SSFM_HD_NOINLINE void balance(double (*a)[kN]) {
         if ((c + r) / f < 0.95 * s) {
           done = false;
           g = 1.0 / f;
-          for (int j = 0; j < kN; ++j) a[i][j] *= g;
-          for (int j = 0; j < kN; ++j) a[j][i] *= f;
+          for (int j = 0; j < kN; ++j) a(i, j) *= g;
+          for (int j = 0; j < kN; ++j) a(j, i) *= f;
         }
       }
     }
@@ -181,24 +195,27 @@ SSFM_HD_NOINLINE void balance(double (*a)[kN]) {
 }
 
 // Reduction to upper Hessenberg form by stabilised elementary similarity transformations.
-SSFM_HD_NOINLINE void to_hessenberg(double (*a)[kN]) {
+template <class Mat>
+SSFM_HD_NOINLINE void to_hessenberg(Mat& a) {
   for (int m = 1; m < kN - 1; ++m) {
     double x = 0.0;
     int i = m;
-    for (int j = m; j < kN; ++j)
-      if (fabs(a[j][m - 1]) > fabs(x)) { x = a[j][m - 1]; i = j; }
+    for (int j = m; j < kN; ++j) {
+      const double v = a(j, m - 1);
+      if (fabs(v) > fabs(x)) { x = v; i = j; }
+    }
     if (i != m) {
-      for (int j = m - 1; j < kN; ++j) { const double t = a[i][j]; a[i][j] = a[m][j]; a[m][j] = t; }
-      for (int j = 0; j < kN; ++j) { const double t = a[j][i]; a[j][i] = a[j][m]; a[j][m] = t; }
+      for (int j = m - 1; j < kN; ++j) { const double t = a(i, j); a(i, j) = a(m, j); a(m, j) = t; }
+      for (int j = 0; j < kN; ++j) { const double t = a(j, i); a(j, i) = a(j, m); a(j, m) = t; }
     }
     if (x != 0.0) {
       for (int r = m + 1; r < kN; ++r) {
-        double y = a[r][m - 1];
+        double y = a(r, m - 1);
         if (y != 0.0) {
           y /= x;
-          a[r][m - 1] = 0.0;
-          for (int j = m; j < kN; ++j) a[r][j] -= y * a[m][j];
-          for (int j = 0; j < kN; ++j) a[j][m] += y * a[j][r];
+          a(r, m - 1) = 0.0;
+          for (int j = m; j < kN; ++j) a(r, j) -= y * a(m, j);
+          for (int j = 0; j < kN; ++j) a(j, m) += y * a(j, r);
         }
       }
     }
@@ -209,10 +226,11 @@ SSFM_HD double sign_of(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a
 
 // Eigenvalues of an upper Hessenberg matrix by the Francis double-shift QR iteration (destroys a).
 // Returns false if an eigenvalue failed to converge.
-SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double* wi) {
+template <class Mat>
+SSFM_HD_NOINLINE bool hessenberg_eigenvalues(Mat& a, double* wr, double* wi) {
   double anorm = 0.0;
   for (int i = 0; i < kN; ++i)
-    for (int j = (i > 0 ? i - 1 : 0); j < kN; ++j) anorm += fabs(a[i][j]);
+    for (int j = (i > 0 ? i - 1 : 0); j < kN; ++j) anorm += fabs(a(i, j));
   int nn = kN - 1;
   double t = 0.0;
   double p = 0.0, q = 0.0, r = 0.0;
@@ -220,17 +238,17 @@ SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double
     int its = 0, l;
     do {
       for (l = nn; l >= 1; --l) {
-        double s = fabs(a[l - 1][l - 1]) + fabs(a[l][l]);
+        double s = fabs(a(l - 1, l - 1)) + fabs(a(l, l));
         if (s == 0.0) s = anorm;
-        if (fabs(a[l][l - 1]) + s == s) { a[l][l - 1] = 0.0; break; }
+        if (fabs(a(l, l - 1)) + s == s) { a(l, l - 1) = 0.0; break; }
       }
-      double x = a[nn][nn];
+      double x = a(nn, nn);
       if (l == nn) {  // one real root
         wr[nn] = x + t;
         wi[nn--] = 0.0;
       } else {
-        double y = a[nn - 1][nn - 1];
-        double w = a[nn][nn - 1] * a[nn - 1][nn];
+        double y = a(nn - 1, nn - 1);
+        double w = a(nn, nn - 1) * a(nn - 1, nn);
         if (l == nn - 1) {  // a 2x2 block: two roots
           p = 0.5 * (y - x);
           q = p * p + w;
@@ -251,8 +269,8 @@ SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double
           if (its == 60) return false;
           if (its == 10 || its == 20 || its == 30 || its == 40) {  // exceptional shift
             t += x;
-            for (int i = 0; i <= nn; ++i) a[i][i] -= x;
-            const double s = fabs(a[nn][nn - 1]) + fabs(a[nn - 1][nn - 2]);
+            for (int i = 0; i <= nn; ++i) a(i, i) -= x;
+            const double s = fabs(a(nn, nn - 1)) + fabs(a(nn - 1, nn - 2));
             y = x = 0.75 * s;
             w = -0.4375 * s * s;
           }
@@ -260,38 +278,38 @@ SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double
           int m;
           double z;
           for (m = nn - 2; m >= l; --m) {  // look for two consecutive small sub-diagonal elements
-            z = a[m][m];
+            z = a(m, m);
             r = x - z;
             double s = y - z;
-            p = (r * s - w) / a[m + 1][m] + a[m][m + 1];
-            q = a[m + 1][m + 1] - z - r - s;
-            r = a[m + 2][m + 1];
+            p = (r * s - w) / a(m + 1, m) + a(m, m + 1);
+            q = a(m + 1, m + 1) - z - r - s;
+            r = a(m + 2, m + 1);
             s = fabs(p) + fabs(q) + fabs(r);
             p /= s; q /= s; r /= s;
             if (m == l) break;
-            const double u = fabs(a[m][m - 1]) * (fabs(q) + fabs(r));
-            const double v = fabs(p) * (fabs(a[m - 1][m - 1]) + fabs(z) + fabs(a[m + 1][m + 1]));
+            const double u = fabs(a(m, m - 1)) * (fabs(q) + fabs(r));
+            const double v = fabs(p) * (fabs(a(m - 1, m - 1)) + fabs(z) + fabs(a(m + 1, m + 1)));
             if (u + v == v) break;
           }
           for (int i = m + 2; i <= nn; ++i) {
-            a[i][i - 2] = 0.0;
-            if (i != m + 2) a[i][i - 3] = 0.0;
+            a(i, i - 2) = 0.0;
+            if (i != m + 2) a(i, i - 3) = 0.0;
           }
           for (int k = m; k <= nn - 1; ++k) {  // double QR step on rows l..nn, columns m..nn
             if (k != m) {
-              p = a[k][k - 1];
-              q = a[k + 1][k - 1];
+              p = a(k, k - 1);
+              q = a(k + 1, k - 1);
               r = 0.0;
-              if (k != nn - 1) r = a[k + 2][k - 1];
+              if (k != nn - 1) r = a(k + 2, k - 1);
               x = fabs(p) + fabs(q) + fabs(r);
               if (x != 0.0) { p /= x; q /= x; r /= x; }
             }
             const double s = sign_of(sqrt(p * p + q * q + r * r), p);
             if (s != 0.0) {
               if (k == m) {
-                if (l != m) a[k][k - 1] = -a[k][k - 1];
+                if (l != m) a(k, k - 1) = -a(k, k - 1);
               } else {
-                a[k][k - 1] = -s * x;
+                a(k, k - 1) = -s * x;
               }
               p += s;
               x = p / s;
@@ -299,24 +317,29 @@ SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double
               z = r / s;
               q /= p;
               r /= p;
+              const bool three = k != nn - 1;
               for (int j = k; j <= nn; ++j) {
-                p = a[k][j] + q * a[k + 1][j];
-                if (k != nn - 1) {
-                  p += r * a[k + 2][j];
-                  a[k + 2][j] -= p * z;
+                const double a0 = a(k, j), a1 = a(k + 1, j);
+                p = a0 + q * a1;
+                if (three) {
+                  const double a2 = a(k + 2, j);
+                  p += r * a2;
+                  a(k + 2, j) = a2 - p * z;
                 }
-                a[k + 1][j] -= p * y;
-                a[k][j] -= p * x;
+                a(k + 1, j) = a1 - p * y;
+                a(k, j) = a0 - p * x;
               }
               const int mmin = nn < k + 3 ? nn : k + 3;
               for (int i = l; i <= mmin; ++i) {
-                p = x * a[i][k] + y * a[i][k + 1];
-                if (k != nn - 1) {
-                  p += z * a[i][k + 2];
-                  a[i][k + 2] -= p * r;
+                const double a0 = a(i, k), a1 = a(i, k + 1);
+                p = x * a0 + y * a1;
+                if (three) {
+                  const double a2 = a(i, k + 2);
+                  p += z * a2;
+                  a(i, k + 2) = a2 - p * r;
                 }
-                a[i][k + 1] -= p * q;
-                a[i][k] -= p;
+                a(i, k + 1) = a1 - p * q;
+                a(i, k) = a0 - p;
               }
             }
           }
@@ -324,6 +347,103 @@ SSFM_HD_NOINLINE bool hessenberg_eigenvalues(double (*a)[kN], double* wr, double
       }
     } while (l < nn - 1);
   }
+  return true;
+}
+
+// The companion matrix of (M2 + mu M1 + mu^2 M0) m = 0 (mu = 1/w = f^2), with the four structurally zero eigenvalues
+// deflated exactly.  Every row of M2 is a multiple of the (3,3) entry F22 = a x + b y + c of F:
+//   M2[1 + 3i + j] = F22 * (2 F_i2 F_2j - F22 F_ij),  M2[0] = 0            (constraint_matrices)
+// so the row space of M2 lies in the six-dimensional span of F22 * {x^2, xy, y^2, x, y, 1}, whatever the data: M2 = C B
+// with B (6 x 10) made of a, b, c only.  With B^T = Q [R; 0] (Householder), the last four columns of Q span null(B), hence
+// (M2 Q)[:, 6..9] = 0 up to rounding, and in the coordinates m = Q m' the companion matrix
+//   [ 0, I ; -A0^-1 A2, -A0^-1 A1 ],  Ak = Mk Q
+// has four zero columns: deleting those rows and columns leaves a 16 x 16 matrix with the same non-zero eigenvalues.  Q is
+// orthogonal, so the deflation is backward stable (it perturbs M2 by rounding errors only); no rank decision is taken
+// from the data.  Layout of T: index p < 6 <-> m'_p, index 6 + i <-> (mu m')_i.
+template <class Mat>
+SSFM_HD_NOINLINE bool companion16(const double Fb[3][9], const double M[3][10][10], Mat& T) {
+  const double fa = Fb[0][8], fb = Fb[1][8], fc = Fb[2][8];
+  // B^T, 10 x 6: column p = coefficients of F22 * (p-th quadratic monomial) in the cubic monomial basis
+  double Bt[10][6];
+  for (int i = 0; i < 10; ++i)
+    for (int p = 0; p < 6; ++p) Bt[i][p] = 0.0;
+  Bt[0][0] = fa; Bt[1][0] = fb; Bt[4][0] = fc;
+  Bt[1][1] = fa; Bt[2][1] = fb; Bt[5][1] = fc;
+  Bt[2][2] = fa; Bt[3][2] = fb; Bt[6][2] = fc;
+  Bt[4][3] = fa; Bt[5][3] = fb; Bt[7][3] = fc;
+  Bt[5][4] = fa; Bt[6][4] = fb; Bt[8][4] = fc;
+  Bt[7][5] = fa; Bt[8][5] = fb; Bt[9][5] = fc;
+  double V[6][10], beta[6];  // Householder vectors (entries k..9 of V[k]) and 2 / |v|^2
+  for (int k = 0; k < 6; ++k) {
+    double nrm = 0.0;
+    for (int i = k; i < 10; ++i) nrm += Bt[i][k] * Bt[i][k];
+    nrm = sqrt(nrm);
+    if (!(nrm > 0.0)) return false;
+    const double alpha = Bt[k][k] > 0 ? -nrm : nrm;
+    for (int i = 0; i < k; ++i) V[k][i] = 0.0;
+    V[k][k] = Bt[k][k] - alpha;
+    double vn = V[k][k] * V[k][k];
+    for (int i = k + 1; i < 10; ++i) { V[k][i] = Bt[i][k]; vn += V[k][i] * V[k][i]; }
+    beta[k] = vn > 0.0 ? 2.0 / vn : 0.0;
+    for (int j = k + 1; j < 6; ++j) {
+      double d = 0.0;
+      for (int i = k; i < 10; ++i) d += V[k][i] * Bt[i][j];
+      d *= beta[k];
+      for (int i = k; i < 10; ++i) Bt[i][j] -= d * V[k][i];
+    }
+  }
+  // rows of Mk Q = ((row H0) H1) ... H5
+  double L[10][10];
+  for (int which = 0; which < 3; ++which)
+    for (int e = 0; e < 10; ++e) {
+      double row[10];
+      for (int q = 0; q < 10; ++q) row[q] = M[which][e][q];
+      for (int k = 0; k < 6; ++k) {
+        double d = 0.0;
+        for (int i = k; i < 10; ++i) d += row[i] * V[k][i];
+        d *= beta[k];
+        for (int i = k; i < 10; ++i) row[i] -= d * V[k][i];
+      }
+      if (which == 0) {
+        for (int q = 0; q < 10; ++q) L[e][q] = row[q];
+      } else if (which == 1) {
+        for (int q = 0; q < 10; ++q) T(6 + e, 6 + q) = -row[q];
+      } else {
+        for (int q = 0; q < 6; ++q) T(6 + e, q) = -row[q];  // columns 6..9 of M2 Q vanish (rounding only)
+      }
+    }
+  // rows 6..15 of T are the right-hand sides X = [-A2[:, :6] | -A1], solved in place: Gaussian elimination with partial
+  // pivoting on [A0 | X]
+  for (int k = 0; k < 10; ++k) {
+    int piv = k;
+    double best = fabs(L[k][k]);
+    for (int i = k + 1; i < 10; ++i)
+      if (fabs(L[i][k]) > best) { best = fabs(L[i][k]); piv = i; }
+    if (!(best > 1e-300)) return false;
+    if (piv != k) {
+      for (int j = 0; j < 10; ++j) { const double tt = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = tt; }
+      for (int j = 0; j < kN; ++j) { const double tt = T(6 + k, j); T(6 + k, j) = T(6 + piv, j); T(6 + piv, j) = tt; }
+    }
+    const double inv = 1.0 / L[k][k];
+    for (int i = k + 1; i < 10; ++i) {
+      const double f = L[i][k] * inv;
+      if (f != 0.0) {
+        for (int j = k + 1; j < 10; ++j) L[i][j] -= f * L[k][j];
+        for (int j = 0; j < kN; ++j) T(6 + i, j) -= f * T(6 + k, j);
+      }
+    }
+  }
+  for (int j = 0; j < kN; ++j)
+    for (int i = 9; i >= 0; --i) {
+      double v = T(6 + i, j);
+      for (int q = i + 1; q < 10; ++q) v -= L[i][q] * T(6 + q, j);
+      T(6 + i, j) = v / L[i][i];
+    }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < kN; ++j) T(i, j) = (j == 6 + i) ? 1.0 : 0.0;
+  for (int i = 6; i < kN; ++i)
+    for (int j = 0; j < kN; ++j)
+      if (!(fabs(T(i, j)) < 1e300)) return false;
   return true;
 }
 
@@ -384,8 +504,10 @@ SSFM_HD bool in_front(const double* R, const double* t, const double* a1, const 
 
 }  // namespace sixpt
 
-// rays: six correspondences, each (u.xyz, v.xyz).  Returns the number of models written (sorted by focal).
-SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out) {
+// rays: six correspondences, each (u.xyz, v.xyz).  Returns the number of models written (sorted by focal).  T: where this
+// instance keeps its kN x kN matrix (sixpt::LocalMat / sixpt::StridedMat).
+template <class Mat>
+SSFM_HD_NOINLINE int solve_sixpt_focal_in(const double (*c)[6], SixPointModel* out, Mat& T) {
   using namespace sixpt;
   double x1[6][3], x2[6][3];
   double s = 0.0;
@@ -401,46 +523,7 @@ SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out)
   if (!nullspace_6x9(x1, x2, Fb)) return 0;
   double M[3][10][10];
   constraint_matrices(Fb, M);
-  // companion matrix of (M2 + mu M1 + mu^2 M0) m = 0:  T = [0 I; -M0^-1 M2, -M0^-1 M1]
-  double T[kN][kN];
-  {
-    // rows 10..19 of T serve as the right-hand sides X = [-M2 | -M1] and are solved in place
-    double L[10][10];
-    int ok = 1;
-    for (int i = 0; i < 10; ++i)
-      for (int j = 0; j < 10; ++j) { L[i][j] = M[0][i][j]; T[10 + i][j] = -M[2][i][j]; T[10 + i][10 + j] = -M[1][i][j]; }
-    for (int k = 0; k < 10; ++k) {  // Gaussian elimination with partial pivoting on [L | X]
-      int piv = k;
-      double best = fabs(L[k][k]);
-      for (int i = k + 1; i < 10; ++i)
-        if (fabs(L[i][k]) > best) { best = fabs(L[i][k]); piv = i; }
-      if (!(best > 1e-300)) { ok = 0; break; }
-      if (piv != k) {
-        for (int j = 0; j < 10; ++j) { const double tt = L[k][j]; L[k][j] = L[piv][j]; L[piv][j] = tt; }
-        for (int j = 0; j < kN; ++j) { const double tt = T[10 + k][j]; T[10 + k][j] = T[10 + piv][j]; T[10 + piv][j] = tt; }
-      }
-      const double inv = 1.0 / L[k][k];
-      for (int i = k + 1; i < 10; ++i) {
-        const double f = L[i][k] * inv;
-        if (f != 0.0) {
-          for (int j = k + 1; j < 10; ++j) L[i][j] -= f * L[k][j];
-          for (int j = 0; j < kN; ++j) T[10 + i][j] -= f * T[10 + k][j];
-        }
-      }
-    }
-    if (!ok) return 0;
-    for (int j = 0; j < kN; ++j)
-      for (int i = 9; i >= 0; --i) {
-        double v = T[10 + i][j];
-        for (int q = i + 1; q < 10; ++q) v -= L[i][q] * T[10 + q][j];
-        T[10 + i][j] = v / L[i][i];
-      }
-    for (int i = 0; i < 10; ++i)
-      for (int j = 0; j < kN; ++j) T[i][j] = (j == 10 + i) ? 1.0 : 0.0;
-  }
-  for (int i = 0; i < kN; ++i)
-    for (int j = 0; j < kN; ++j)
-      if (!(fabs(T[i][j]) < 1e300)) return 0;
+  if (!companion16(Fb, M, T)) return 0;
   balance(T);
   to_hessenberg(T);
   double wr[kN], wi[kN];
@@ -555,6 +638,11 @@ SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out)
     }
   }
   return n_out;
+}
+
+SSFM_HD_NOINLINE int solve_sixpt_focal(const double (*c)[6], SixPointModel* out) {
+  sixpt::LocalMat T;
+  return solve_sixpt_focal_in(c, out, T);
 }
 
 // The matrix the estimator scores with.  focal_scoring == 0: E = skew3(t) so3exp(r), evaluated on the raw rays,

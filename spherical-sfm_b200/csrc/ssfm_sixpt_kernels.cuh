@@ -15,6 +15,7 @@
 #pragma once
 #include "ssfm_kernels.cuh"
 #include "ssfm_sixpt.cuh"
+#include "ssfm_sixpt_coop.cuh"
 
 namespace ssfm {
 
@@ -58,51 +59,72 @@ __global__ void k_sixpt_init(Params P, const long long* __restrict__ offsets, in
   if (a == 0) *count = npairs;
 }
 
-// grid (active pairs, ceil(cap / 64)), 64 threads
-#ifndef SSFM_SIXPT_MINBLOCKS
-#define SSFM_SIXPT_MINBLOCKS 1
-#endif
-__global__ void __launch_bounds__(64, SSFM_SIXPT_MINBLOCKS)
+// grid (active pairs, ceil(cap / kSixSamplesPerBlock)), kSixSolveThreads threads, kSixSolveSmem bytes of dynamic shared
+// memory.  Eight lanes per sample, four samples per warp (ssfm_sixpt_coop.cuh): every sample's 16 x 16 companion / Hessenberg
+// matrix and its small tables live in shared memory (3.6 KB), the ten cubics in a global scratch slot (2.4 KB, read back
+// through L2), so nothing of the solver goes through local memory except the per-candidate least-squares tableau.
+constexpr int kSixSolveThreads = 64;
+constexpr int kSixSamplesPerBlock = (kSixSolveThreads / 32) * sixc::kSixSamplesPerWarp;
+constexpr size_t kSixSolveSmem = (size_t)kSixSamplesPerBlock * sixc::kScratch * sizeof(double) +
+                                 (size_t)(kSixSolveThreads / 32) * sizeof(sixc::SixWarpScratch);
+__global__ void __launch_bounds__(kSixSolveThreads)
     k_sixpt_sample_solve(Params P, const double* __restrict__ rays, const long long* __restrict__ offsets, int pair0,
                          const int* __restrict__ active, const int* __restrict__ navail, const SixState* __restrict__ states,
                          int R, double* __restrict__ models, int* __restrict__ nmodels, float* __restrict__ pk_G,
-                         int* __restrict__ pk_id, int* __restrict__ pk_count, float* __restrict__ s32m) {
+                         int* __restrict__ pk_id, int* __restrict__ pk_count, float* __restrict__ s32m, double* __restrict__ scratch_M) {
+  extern __shared__ double six_smem[];
   const int a = active[blockIdx.x];
-  const int j = blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= navail[a]) return;
+  const int na = navail[a];
+  const int j0 = blockIdx.y * kSixSamplesPerBlock;
+  if (j0 >= na) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int j = j0 + warp * sixc::kSixSamplesPerWarp + grp;  // this group's look-ahead slot
+  const bool valid = j < na;
+  double* S = six_smem + (size_t)(warp * sixc::kSixSamplesPerWarp + grp) * sixc::kScratch;
+  sixc::SixWarpScratch* W = reinterpret_cast<sixc::SixWarpScratch*>(six_smem + (size_t)kSixSamplesPerBlock * sixc::kScratch) + warp;
+  double* Mg0 = scratch_M + ((size_t)a * R + j0 + warp * sixc::kSixSamplesPerWarp) * sixc::kMSize;
   const int pair = pair0 + a;
   const long long off = offsets[pair];
-  const int n = (int)(offsets[pair + 1] - off);
-  const uint32_t it = states[a].it + (uint32_t)j;
-  int idx[6];
-  philox_sample<6>(P.seed, P.first_pair_id + (uint32_t)pair, it, 6, n, idx);
   double c[6][6];
-  for (int s = 0; s < 6; ++s) {
-    const double2* src = reinterpret_cast<const double2*>(rays + 6 * (off + idx[s]));
-    const double2 x0 = src[0], x1 = src[1], x2 = src[2];
-    c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
+  if (valid && gl == 0) {
+    const int n = (int)(offsets[pair + 1] - off);
+    const uint32_t it = states[a].it + (uint32_t)j;
+    int idx[6];
+    philox_sample<6>(P.seed, P.first_pair_id + (uint32_t)pair, it, 6, n, idx);
+    for (int s = 0; s < 6; ++s) {
+      const double2* src = reinterpret_cast<const double2*>(rays + 6 * (off + idx[s]));
+      const double2 x0 = src[0], x1 = src[1], x2 = src[2];
+      c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
+    }
   }
-  SixPointModel out[kSixMaxModels];
-  const int nm = solve_sixpt_focal(c, out);
-  nmodels[(size_t)a * R + j] = nm;
+  const int nm = sixc::six_solve_warp(S, W, Mg0, c, valid);
+  if (!valid) return;
   float* srow = s32m + ((size_t)a * R + j) * kSixSlotModels;
-  for (int k = 0; k < kSixSlotModels; ++k) srow[k] = INFINITY;
+  srow[gl] = INFINITY;
+  srow[gl + 8] = INFINITY;
+  int base = 0;
+  if (gl == 0) {
+    nmodels[(size_t)a * R + j] = nm;
+    if (nm > 0) base = atomicAdd(&pk_count[a], nm);
+  }
   if (nm == 0) return;
-  const int base = atomicAdd(&pk_count[a], nm);
+  base = __shfl_sync(0xFFu << (8 * grp), base, 8 * grp);
+  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffT);
   double* dst = models + ((size_t)a * R + j) * kSixMaxModels * kSixRecord;
-  for (int k = 0; k < nm; ++k) {
+  for (int k = gl; k < nm; k += 8) {
+    const SixPointModel mdl = list[k];
     double G[9];
-    sixpt_scoring_matrix(out[k], P.sixpt_focal_scoring, G);
+    sixpt_scoring_matrix(mdl, P.sixpt_focal_scoring, G);
     double* d = dst + (size_t)k * kSixRecord;
     for (int q = 0; q < 9; ++q) d[q] = G[q];
-    for (int q = 0; q < 3; ++q) { d[9 + q] = out[k].t[q]; d[12 + q] = out[k].r[q]; }
-    d[15] = out[k].f;
+    for (int q = 0; q < 3; ++q) { d[9 + q] = mdl.t[q]; d[12 + q] = mdl.r[q]; }
+    d[15] = mdl.f;
     // FP32 copy, normalised (the Sampson error is invariant to the scale of G; keeps the floats in range)
     double nrm = 0.0;
     for (int q = 0; q < 9; ++q) nrm += G[q] * G[q];
     const double inv = nrm > 0.0 ? 1.0 / sqrt(nrm) : 0.0;
-    float* g = pk_G + ((size_t)a * R * kSixMaxModels + base + k) * 9;
-    for (int q = 0; q < 9; ++q) g[q] = (float)(G[q] * inv);
+    float* gq = pk_G + ((size_t)a * R * kSixMaxModels + base + k) * 9;
+    for (int q = 0; q < 9; ++q) gq[q] = (float)(G[q] * inv);
     pk_id[(size_t)a * R * kSixMaxModels + base + k] = j * kSixSlotModels + k;
   }
 }
@@ -282,21 +304,30 @@ __global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain(Params P, S
   }
 }
 
-// Hook: the minimal solver on explicit samples (6 indices each).
-__global__ void k_sixpt_solve_samples(const double* __restrict__ rays, const int* __restrict__ samples, int ns,
-                                      double* __restrict__ models /* ns x 15 x 7 */, int* __restrict__ nmodels) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= ns) return;
+// Hook: the minimal solver on explicit samples (6 indices each) -- the same warp code as the batched kernel.
+// grid ceil(ns / kSixSamplesPerBlock), kSixSolveThreads threads, kSixSolveSmem bytes.
+__global__ void __launch_bounds__(kSixSolveThreads)
+    k_sixpt_solve_samples(const double* __restrict__ rays, const int* __restrict__ samples, int ns,
+                          double* __restrict__ models /* ns x 15 x 7 */, int* __restrict__ nmodels, double* __restrict__ scratch_M) {
+  extern __shared__ double six_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const int s0 = blockIdx.x * kSixSamplesPerBlock + warp * sixc::kSixSamplesPerWarp;
+  const int s = s0 + grp;
+  const bool valid = s < ns;
+  double* S = six_smem + (size_t)(warp * sixc::kSixSamplesPerWarp + grp) * sixc::kScratch;
+  sixc::SixWarpScratch* W = reinterpret_cast<sixc::SixWarpScratch*>(six_smem + (size_t)kSixSamplesPerBlock * sixc::kScratch) + warp;
   double c[6][6];
-  for (int i = 0; i < 6; ++i)
-    for (int q = 0; q < 6; ++q) c[i][q] = rays[6 * (size_t)samples[6 * s + i] + q];
-  SixPointModel out[kSixMaxModels];
-  const int nm = solve_sixpt_focal(c, out);
-  nmodels[s] = nm;
-  for (int k = 0; k < nm; ++k) {
+  if (valid && gl == 0)
+    for (int i = 0; i < 6; ++i)
+      for (int q = 0; q < 6; ++q) c[i][q] = rays[6 * (size_t)samples[6 * s + i] + q];
+  const int nm = sixc::six_solve_warp(S, W, scratch_M + (size_t)s0 * sixc::kMSize, c, valid);
+  if (!valid) return;
+  if (gl == 0) nmodels[s] = nm;
+  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffT);
+  for (int k = gl; k < nm; k += 8) {
     double* d = models + ((size_t)s * kSixMaxModels + k) * 7;
-    for (int q = 0; q < 3; ++q) { d[q] = out[k].t[q]; d[3 + q] = out[k].r[q]; }
-    d[6] = out[k].f;
+    for (int q = 0; q < 3; ++q) { d[q] = list[k].t[q]; d[3 + q] = list[k].r[q]; }
+    d[6] = list[k].f;
   }
 }
 

@@ -9,6 +9,7 @@
 
 #include "../../spherical-sfm_b200/csrc/ssfm_chain.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_sixpt.cuh"
+#include "../../spherical-sfm_b200/csrc/ssfm_sixpt_coop.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_triangulate.cuh"
 
 using namespace ssfm;
@@ -234,7 +235,9 @@ int hs_sixpt_solve(const double* rays36, double* models /* 15 x 7: t, r, f */, d
   double c[6][6];
   for (int i = 0; i < 36; ++i) c[i / 6][i % 6] = rays36[i];
   SixPointModel out[kSixMaxModels];
-  const int n = solve_sixpt_focal(c, out);
+  // the staged solver the batched kernel runs (here with a one-lane group); focal_scoring bit 1 selects the per-thread solver
+  const int n = (focal_scoring & 2) ? solve_sixpt_focal(c, out) : sixc::solve_sixpt_focal_staged(c, out);
+  focal_scoring &= 1;
   for (int k = 0; k < n; ++k) {
     for (int d = 0; d < 3; ++d) { models[7 * k + d] = out[k].t[d]; models[7 * k + 3 + d] = out[k].r[d]; }
     models[7 * k + 6] = out[k].f;
