@@ -52,8 +52,8 @@ SSFM_HD void fma21(double c, const double* p, const double* a, double* o) {
 
 // Null space of the 6x9 epipolar system by Gauss-Jordan with complete pivoting, then modified
 // Gram-Schmidt.  Fb[k] (k<3) is a 3x3 row-major basis matrix.  Returns false if rank deficient.
-SSFM_HD_NOINLINE bool nullspace_6x9(const double (*x1)[3], const double (*x2)[3], double Fb[3][9]) {
-  double A[6][9];
+// A: 54 doubles of workspace (the batched kernel passes shared memory: with local memory this was 11 % of its time).
+SSFM_HD_NOINLINE bool nullspace_6x9_ws(const double (*x1)[3], const double (*x2)[3], double Fb[3][9], double (*A)[9]) {
   int colperm[9];
   for (int c = 0; c < 9; ++c) colperm[c] = c;
   for (int i = 0; i < 6; ++i)
@@ -99,6 +99,11 @@ SSFM_HD_NOINLINE bool nullspace_6x9(const double (*x1)[3], const double (*x2)[3]
     for (int c = 0; c < 9; ++c) Fb[q][c] = v[c] * nn;
   }
   return true;
+}
+
+SSFM_HD bool nullspace_6x9(const double (*x1)[3], const double (*x2)[3], double Fb[3][9]) {
+  double A[6][9];
+  return nullspace_6x9_ws(x1, x2, Fb, A);
 }
 
 // M[k][e][mono]: coefficient of w^k in equation e.  Equation 0 = det F, 1..9 = the trace constraint.

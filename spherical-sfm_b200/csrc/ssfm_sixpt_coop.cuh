@@ -50,6 +50,34 @@ struct LaneGroup8 {
 };
 #endif
 
+// 1 / x and 1 / sqrt(x) for the scalar part of the eigen-iteration.  Device: the hardware's approximation (2^-23) refined by
+// two Newton steps (a few DFMA instead of the ~12-instruction IEEE division sequence with its special-case branches); the
+// operands here are pivots and norms that are neither zero, infinite nor denormal (checked by the callers).  The result
+// is within an ulp or two of the exact quotient, which is all a backward-stable iteration needs.  Host: exact.
+SSFM_HD double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+SSFM_HD double fast_rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  y = fma(y, fma(-hx * y, y, 0.5), y);
+  return y;
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+
 // Per-sample scratch (doubles).  T has a row stride of 17 so that a column walk (stride 17 doubles = 34 banks) is
 // conflict-free; kScratch = 4 (mod 16) puts the four samples of a warp on different banks for the broadcast reads.
 constexpr int kTS = 17;
@@ -88,7 +116,7 @@ SSFM_HD bool six_setup(const G& g, const double (*c)[6], double* S, double* Mg) 
       x2[i][0] = c[i][3] * is; x2[i][1] = c[i][4] * is; x2[i][2] = c[i][5];
     }
     double Fb[3][9];
-    const bool ok = nullspace_6x9(x1, x2, Fb);
+    const bool ok = nullspace_6x9_ws(x1, x2, Fb, reinterpret_cast<double(*)[9]>(S + kOffT));
     S[kOffMisc] = s;
     S[kOffMisc + 1] = ok ? 1.0 : 0.0;
     for (int i = 0; i < 6; ++i)
@@ -415,15 +443,18 @@ SSFM_HD bool six_hqr(const G& g, double* S) {
             z = SIX_T(m, m);
             r = x - z;
             double s = y - z;
-            p = (r * s - w) / SIX_T(m + 1, m) + SIX_T(m, m + 1);
+            p = (r * s - w) * fast_rcp(SIX_T(m + 1, m)) + SIX_T(m, m + 1);
             q = SIX_T(m + 1, m + 1) - z - r - s;
             r = SIX_T(m + 2, m + 1);
-            s = fabs(p) + fabs(q) + fabs(r);
-            p /= s; q /= s; r /= s;
             if (m == l) break;
+            // the test is homogeneous in (p, q, r): their common scale is taken out once, after the loop
             const double u = fabs(SIX_T(m, m - 1)) * (fabs(q) + fabs(r));
             const double v = fabs(p) * (fabs(SIX_T(m - 1, m - 1)) + fabs(z) + fabs(SIX_T(m + 1, m + 1)));
             if (u + v == v) break;
+          }
+          {
+            const double s = fast_rcp(fabs(p) + fabs(q) + fabs(r));
+            p *= s; q *= s; r *= s;
           }
           g.sync();
           for (int i = m + 2 + g.lane(); i <= nn; i += G::kSize) {
@@ -438,18 +469,21 @@ SSFM_HD bool six_hqr(const G& g, double* S) {
               r = 0.0;
               if (k != nn - 1) r = SIX_T(k + 2, k - 1);
               x = fabs(p) + fabs(q) + fabs(r);
-              if (x != 0.0) { p /= x; q /= x; r /= x; }
+              if (x != 0.0) { const double ix = fast_rcp(x); p *= ix; q *= ix; r *= ix; }
             }
-            const double s = sign_of(sqrt(p * p + q * q + r * r), p);
-            if (s != 0.0) {
+            const double n2 = p * p + q * q + r * r;
+            if (n2 != 0.0) {
+              const double is = sign_of(fast_rsqrt(n2), p);  // 1 / s, s = sign(p) |(p, q, r)|
+              const double s = n2 * is;
               const double sub = (k == m) ? ((l != m) ? -SIX_T(k, k - 1) : 0.0) : -s * x;
               const bool write_sub = (k != m) || (l != m);
               p += s;
-              x = p / s;
-              y = q / s;
-              z = r / s;
-              q /= p;
-              r /= p;
+              x = p * is;
+              y = q * is;
+              z = r * is;
+              const double ip = fast_rcp(p);
+              q *= ip;
+              r *= ip;
               const bool three = k != nn - 1;
               g.sync();  // every lane has read column k-1
               if (write_sub && g.lane() == 0) SIX_T(k, k - 1) = sub;
@@ -500,37 +534,106 @@ SSFM_HD bool six_candidate(double mu, double wik, double* w) {
   return true;
 }
 
-// Least-squares start + Gauss-Newton on the ten equations in (x, y, w) + residual test.  M: the sample's M[3][10][10].
-SSFM_HD_NOINLINE bool six_polish(const double* M, double w, double* sol3) {
-  using namespace sixpt;
-  double x, y;
-  {
-    double A[10][9], b[10], sol[9];
-    for (int e = 0; e < 10; ++e) {
-      for (int q = 0; q < 9; ++q) A[e][q] = M[e * 10 + q] + w * (M[100 + e * 10 + q] + w * M[200 + e * 10 + q]);
-      b[e] = -(M[e * 10 + 9] + w * (M[100 + e * 10 + 9] + w * M[200 + e * 10 + 9]));
+// min || A x - b || for a 10 x COLS tableau in the group's scratch (rows 10 doubles apart: A[e][q] at tab[10 * e + q],
+// b[e] at tab[10 * e + COLS]), by Householder QR with the columns spread over the lanes (sixpt::least_squares10).  On return
+// the tableau holds R and Q^T b; the caller back-substitutes what it needs.  Returns false (group-uniform) on a zero column.
+template <int COLS, class G>
+SSFM_HD bool six_ls_reduce(const G& g, double* tab) {
+  for (int k = 0; k < COLS; ++k) {
+    double nrm = 0.0;
+    for (int i = k; i < 10; ++i) nrm += tab[10 * i + k] * tab[10 * i + k];
+    nrm = sqrt(nrm);
+    if (!(nrm > 0.0)) return false;
+    const double akk = tab[10 * k + k];
+    const double alpha = akk > 0 ? -nrm : nrm;
+    const double v0 = akk - alpha;
+    double vn = v0 * v0;
+    for (int i = k + 1; i < 10; ++i) vn += tab[10 * i + k] * tab[10 * i + k];
+    if (vn > 0.0) {
+      const double beta = 2.0 / vn;
+      for (int j = k + 1 + g.lane(); j <= COLS; j += G::kSize) {  // column COLS is the right-hand side
+        double d = v0 * tab[10 * k + j];
+        for (int i = k + 1; i < 10; ++i) d += tab[10 * i + k] * tab[10 * i + j];
+        d *= beta;
+        tab[10 * k + j] -= d * v0;
+        for (int i = k + 1; i < 10; ++i) tab[10 * i + j] -= d * tab[10 * i + k];
+      }
     }
-    if (!least_squares10<9>(A, b, sol)) return false;
-    x = sol[7];
-    y = sol[8];
+    g.sync();
+    if (g.lane() == 0) tab[10 * k + k] = alpha;
   }
+  g.sync();
+  return true;
+}
+
+// (x, y) at a given w: least squares for the nine non-constant monomials of the ten equations, by the group of the sample.
+// M: the sample's M[3][10][10]; tab: 100 doubles of the group's scratch.  Group-uniform.
+template <class G>
+SSFM_HD bool six_start(const G& g, const double* M, double* tab, double w, double* xy) {
+  g.sync();
+  for (int idx = g.lane(); idx < 100; idx += G::kSize) {
+    const int e = idx / 10, q = idx - 10 * e;
+    const double v = M[e * 10 + q] + w * (M[100 + e * 10 + q] + w * M[200 + e * 10 + q]);
+    tab[idx] = q < 9 ? v : -v;
+  }
+  g.sync();
+  if (!six_ls_reduce<9>(g, tab)) return false;
+  xy[1] = tab[10 * 8 + 9] / tab[10 * 8 + 8];
+  xy[0] = (tab[10 * 7 + 9] - tab[10 * 7 + 8] * xy[1]) / tab[10 * 7 + 7];
+  return true;
+}
+
+// Gauss-Newton on the ten equations in (x, y, w) + residual test: ONE LANE per candidate, everything in registers.  The
+// 10 x 3 least-squares problem of a step is reduced row by row with Givens rotations as the rows are produced (same
+// stability as the Householder form, no tableau to store).  sol3 = (x, y, w) start in, solution out.
+SSFM_HD_NOINLINE bool six_newton(const double* M, double* sol3) {
+  using namespace sixpt;
+  double x = sol3[0], y = sol3[1], w = sol3[2];
   bool ok = true, converged = false;
   for (int itn = 0; itn < 12 && ok && !converged; ++itn) {
-    double m[10], dx[10], dy[10], J[10][3], res[10], step[3];
+    double m[10], dx[10], dy[10];
     monomials(x, y, m, dx, dy);
+    double r00 = 0, r01 = 0, r02 = 0, r11 = 0, r12 = 0, r22 = 0, b0 = 0, b1 = 0, b2 = 0;
     for (int e = 0; e < 10; ++e) {
-      double r0 = 0, jx = 0, jy = 0, jw = 0;
+      double r0 = 0, a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
       for (int q = 0; q < 10; ++q) {
         const double m1 = M[100 + e * 10 + q], m2 = M[200 + e * 10 + q];
         const double mw = M[e * 10 + q] + w * (m1 + w * m2);
         r0 += mw * m[q];
-        jx += mw * dx[q];
-        jy += mw * dy[q];
-        jw += (m1 + 2.0 * w * m2) * m[q];
+        a0 += mw * dx[q];
+        a1 += mw * dy[q];
+        a2 += (m1 + 2.0 * w * m2) * m[q];
       }
-      res[e] = -r0; J[e][0] = jx; J[e][1] = jy; J[e][2] = jw;
+      double rb = -r0;
+      // rotate the row (a0, a1, a2 | rb) into the triangle
+      double h = r00 * r00 + a0 * a0;
+      if (h > 0.0) {
+        const double ih = fast_rsqrt(h), c = r00 * ih, sn = a0 * ih;
+        r00 = h * ih;
+        double t = c * r01 + sn * a1; a1 = c * a1 - sn * r01; r01 = t;
+        t = c * r02 + sn * a2; a2 = c * a2 - sn * r02; r02 = t;
+        t = c * b0 + sn * rb; rb = c * rb - sn * b0; b0 = t;
+      }
+      h = r11 * r11 + a1 * a1;
+      if (h > 0.0) {
+        const double ih = fast_rsqrt(h), c = r11 * ih, sn = a1 * ih;
+        r11 = h * ih;
+        double t = c * r12 + sn * a2; a2 = c * a2 - sn * r12; r12 = t;
+        t = c * b1 + sn * rb; rb = c * rb - sn * b1; b1 = t;
+      }
+      h = r22 * r22 + a2 * a2;
+      if (h > 0.0) {
+        const double ih = fast_rsqrt(h), c = r22 * ih, sn = a2 * ih;
+        r22 = h * ih;
+        b2 = c * b2 + sn * rb;
+      }
     }
-    if (!least_squares10<3>(J, res, step)) { ok = false; break; }
+    if (!(r00 > 0.0) || !(r11 > 0.0) || !(r22 > 0.0)) { ok = false; break; }
+    double step[3];
+    step[2] = b2 / r22;
+    step[1] = (b1 - r12 * step[2]) / r11;
+    step[0] = (b0 - r01 * step[1] - r02 * step[2]) / r00;
     x += step[0]; y += step[1]; w += step[2];
     if (!(fabs(x) < 1e300) || !(fabs(y) < 1e300) || !(fabs(w) < 1e300)) ok = false;
     // accepted only once the iteration has settled (a start that wanders is a spurious eigenvalue)
@@ -544,6 +647,7 @@ SSFM_HD_NOINLINE bool six_polish(const double* M, double w, double* sol3) {
     monomials(x, y, m, dx, dy);
     for (int e = 0; e < 10 && ok; ++e) {
       double r0 = 0, sc = 0;
+#pragma unroll
       for (int q = 0; q < 10; ++q) {
         const double mw = M[e * 10 + q] + w * (M[100 + e * 10 + q] + w * M[200 + e * 10 + q]);
         r0 += mw * m[q];
@@ -632,7 +736,9 @@ SSFM_HD_NOINLINE int solve_sixpt_focal_staged(const double (*c)[6], SixPointMode
   for (int k = 0; k < 16; ++k) {
     double w, sol[3];
     if (!six_candidate(S[kOffWr + k], S[kOffWi + k], &w)) continue;
-    if (!six_polish(M, w, sol)) continue;
+    if (!six_start(g, M, S + kOffT, w, sol)) continue;
+    sol[2] = w;
+    if (!six_newton(M, sol)) continue;
     bool dup = false;
     for (int q = 0; q < n_sol; ++q) dup = dup || six_same_solution(sols[q], sol);
     if (dup || n_sol >= kSixMaxModels) continue;
@@ -649,102 +755,75 @@ SSFM_HD_NOINLINE int solve_sixpt_focal_staged(const double (*c)[6], SixPointMode
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------------------------
-// The warp driver: 4 samples per warp, 8 lanes each.
+// The group driver: 8 lanes solve one sample from start to end (4 samples per warp, independent of each other).
 // ----------------------------------------------------------------------------------------------------------------
-struct SixWarpScratch {
-  double w[64];  // packed candidates of the warp's four samples: start value of 1 / f^2 ...
-  int id[64];    // ... and (sample in warp) * 16 + eigenvalue index
-};
 constexpr int kSixSamplesPerWarp = 4;
 
-// S: this lane's group scratch (kScratch doubles, shared memory); W: the warp's candidate list; Mg0: the global M slot of
-// the warp's first sample (sample g of the warp at + g * kMSize); c: the six correspondences (read by lane 0 of the group
-// only); valid: does this group have a sample at all.  Returns the number of models of the group's sample (group-uniform);
-// they are left sorted by focal at S + kOffT (SixPointModel records).
-__device__ __noinline__ int six_solve_warp(double* S, SixWarpScratch* W, double* Mg0, const double (*c)[6], bool valid) {
+// S: the group's scratch (kScratch doubles, shared memory); Mg: the sample's global M slot; c: the six correspondences
+// (read by lane 0 of the group only).  Returns the number of models (group-uniform); they are left sorted by focal at
+// S + kOffT (SixPointModel records).  Every collective inside names the group's own lanes.
+__device__ __noinline__ int six_solve_group(double* S, double* Mg, const double (*c)[6]) {
   const int lane = threadIdx.x & 31, grp = lane >> 3;
   const LaneGroup8 g{lane & 7, 0xFFu << (8 * grp)};
-  double* Mg = Mg0 + (size_t)grp * kMSize;
-  double* S0 = S - grp * kScratch;  // scratch of the warp's first sample
-  bool live = valid;
-  if (live) {
-    live = six_setup(g, c, S, Mg) && six_companion(g, S, Mg);
-    if (live) {
-      six_balance(g, S);
-      six_hessenberg(g, S);
-      live = six_hqr(g, S);
-    }
-  }
-  __syncwarp();
-  // candidates: every lane looks at two eigenvalues of its sample; the warp's candidates are packed in (sample, index) order
-  double w0 = 0.0, w1 = 0.0;
-  bool c0 = false, c1 = false;
-  if (live) {
-    c0 = six_candidate(S[kOffWr + g.l], S[kOffWi + g.l], &w0);
-    c1 = six_candidate(S[kOffWr + 8 + g.l], S[kOffWi + 8 + g.l], &w1);
-  }
-  S[kOffCand + 4 * g.l + 3] = 0.0;
-  S[kOffCand + 4 * (g.l + 8) + 3] = 0.0;
-  const unsigned b0 = __ballot_sync(0xffffffffu, c0), b1 = __ballot_sync(0xffffffffu, c1);
-  const unsigned below = (1u << lane) - 1u;
-  int base = 0;
-  for (int q = 0; q < grp; ++q) base += __popc(b0 & (0xFFu << (8 * q))) + __popc(b1 & (0xFFu << (8 * q)));
-  if (c0) {
-    const int pos = base + __popc(b0 & g.mask & below);
-    W->w[pos] = w0;
-    W->id[pos] = grp * 16 + g.l;
-  }
-  if (c1) {
-    const int pos = base + __popc(b0 & g.mask) + __popc(b1 & g.mask & below);
-    W->w[pos] = w1;
-    W->id[pos] = grp * 16 + 8 + g.l;
-  }
-  const int total = __popc(b0) + __popc(b1);
-  __syncwarp();
-  // polish: one lane per candidate
-  for (int ci = lane; ci < total; ci += 32) {
-    const int id = W->id[ci], gq = id >> 4, k = id & 15;
-    double sol[3];
-    if (six_polish(Mg0 + (size_t)gq * kMSize, W->w[ci], sol)) {
-      double* dst = S0 + gq * kScratch + kOffCand + 4 * k;
-      dst[0] = sol[0]; dst[1] = sol[1]; dst[2] = sol[2]; dst[3] = 1.0;
-    }
-  }
-  __syncwarp();
-  if (live) {
-    if (g.l == 0) {  // duplicates: a solution equal to an earlier accepted one is dropped (in eigenvalue order)
-      int n_sol = 0;
-      for (int k = 0; k < 16; ++k) {
-        if (S[kOffCand + 4 * k + 3] != 1.0) continue;
-        bool dup = false;
-        for (int q = 0; q < k; ++q)
-          if (S[kOffCand + 4 * q + 3] == 2.0) dup = dup || six_same_solution(S + kOffCand + 4 * q, S + kOffCand + 4 * k);
-        if (dup || n_sol >= kSixMaxModels) continue;
-        S[kOffCand + 4 * k + 3] = 2.0;
-        ++n_sol;
-      }
-      S[kOffMisc + 1] = 0.0;  // number of models in the list
-    }
+  if (!six_setup(g, c, S, Mg) || !six_companion(g, S, Mg)) return 0;
+  six_balance(g, S);
+  six_hessenberg(g, S);
+  if (!six_hqr(g, S)) return 0;
+  // candidates in eigenvalue order: least-squares start by the whole group, one after the other ...
+  for (int k = 0; k < 16; ++k) {
+    double w, xy[2];
+    bool keep = six_candidate(S[kOffWr + k], S[kOffWi + k], &w);
+    if (keep) keep = six_start(g, Mg, S + kOffT, w, xy);
     g.sync();
-    // decomposition: one lane per accepted solution; the models enter the focal-sorted list in eigenvalue order
-    SixPointModel* list = reinterpret_cast<SixPointModel*>(S + kOffT);
-    for (int r = 0; r < 2; ++r) {
-      const int k = g.l + 8 * r;
-      SixPointModel four[4];
-      int n4 = 0;
-      if (S[kOffCand + 4 * k + 3] == 2.0) n4 = six_decompose(S, S + kOffCand + 4 * k, four);
-      for (int kk = 0; kk < 8; ++kk) {
-        if (g.l == kk && n4 > 0) {
-          int n_out = (int)S[kOffMisc + 1];
-          for (int i = 0; i < n4; ++i) n_out = six_insert_sorted(list, n_out, four[i]);
-          S[kOffMisc + 1] = (double)n_out;
-        }
-        g.sync();
-      }
+    if (g.l == 0) {
+      double* dst = S + kOffCand + 4 * k;
+      dst[3] = keep ? 1.0 : 0.0;
+      if (keep) { dst[0] = xy[0]; dst[1] = xy[1]; dst[2] = w; }
     }
   }
-  __syncwarp();
-  return live ? (int)S[kOffMisc + 1] : 0;
+  g.sync();
+  // ... Gauss-Newton with one lane per candidate ...
+  for (int r = 0; r < 2; ++r) {
+    double* cand = S + kOffCand + 4 * (g.l + 8 * r);
+    if (cand[3] == 1.0) {
+      double sol[3] = {cand[0], cand[1], cand[2]};
+      if (six_newton(Mg, sol)) { cand[0] = sol[0]; cand[1] = sol[1]; cand[2] = sol[2]; }
+      else cand[3] = 0.0;
+    }
+  }
+  g.sync();
+  if (g.l == 0) {  // ... and a solution equal to an earlier accepted one is dropped
+    int n_sol = 0;
+    for (int k = 0; k < 16; ++k) {
+      if (S[kOffCand + 4 * k + 3] != 1.0) continue;
+      bool dup = false;
+      for (int q = 0; q < k; ++q)
+        if (S[kOffCand + 4 * q + 3] == 2.0) dup = dup || six_same_solution(S + kOffCand + 4 * q, S + kOffCand + 4 * k);
+      if (dup || n_sol >= kSixMaxModels) continue;
+      S[kOffCand + 4 * k + 3] = 2.0;
+      ++n_sol;
+    }
+  }
+  g.sync();
+  if (g.l == 0) S[kOffMisc + 1] = 0.0;  // number of models in the list
+  g.sync();
+  // decomposition: one lane per accepted solution; the models enter the focal-sorted list in eigenvalue order
+  SixPointModel* list = reinterpret_cast<SixPointModel*>(S + kOffT);
+  for (int r = 0; r < 2; ++r) {
+    const int k = g.l + 8 * r;
+    SixPointModel four[4];
+    int n4 = 0;
+    if (S[kOffCand + 4 * k + 3] == 2.0) n4 = six_decompose(S, S + kOffCand + 4 * k, four);
+    for (int kk = 0; kk < 8; ++kk) {
+      if (g.l == kk && n4 > 0) {
+        int n_out = (int)S[kOffMisc + 1];
+        for (int i = 0; i < n4; ++i) n_out = six_insert_sorted(list, n_out, four[i]);
+        S[kOffMisc + 1] = (double)n_out;
+      }
+      g.sync();
+    }
+  }
+  return (int)S[kOffMisc + 1];
 }
 #endif  // __CUDACC__
 

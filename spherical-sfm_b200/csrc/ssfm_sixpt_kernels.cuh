@@ -65,9 +65,11 @@ __global__ void k_sixpt_init(Params P, const long long* __restrict__ offsets, in
 // through L2), so nothing of the solver goes through local memory except the per-candidate least-squares tableau.
 constexpr int kSixSolveThreads = 64;
 constexpr int kSixSamplesPerBlock = (kSixSolveThreads / 32) * sixc::kSixSamplesPerWarp;
-constexpr size_t kSixSolveSmem = (size_t)kSixSamplesPerBlock * sixc::kScratch * sizeof(double) +
-                                 (size_t)(kSixSolveThreads / 32) * sizeof(sixc::SixWarpScratch);
-__global__ void __launch_bounds__(kSixSolveThreads)
+constexpr size_t kSixSolveSmem = (size_t)kSixSamplesPerBlock * sixc::kScratch * sizeof(double);
+#ifndef SSFM_SIXPT_MINBLOCKS
+#define SSFM_SIXPT_MINBLOCKS 7  // shared memory allows 7 blocks (14 warps) per SM: keep the registers under 146
+#endif
+__global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
     k_sixpt_sample_solve(Params P, const double* __restrict__ rays, const long long* __restrict__ offsets, int pair0,
                          const int* __restrict__ active, const int* __restrict__ navail, const SixState* __restrict__ states,
                          int R, double* __restrict__ models, int* __restrict__ nmodels, float* __restrict__ pk_G,
@@ -81,8 +83,7 @@ __global__ void __launch_bounds__(kSixSolveThreads)
   const int j = j0 + warp * sixc::kSixSamplesPerWarp + grp;  // this group's look-ahead slot
   const bool valid = j < na;
   double* S = six_smem + (size_t)(warp * sixc::kSixSamplesPerWarp + grp) * sixc::kScratch;
-  sixc::SixWarpScratch* W = reinterpret_cast<sixc::SixWarpScratch*>(six_smem + (size_t)kSixSamplesPerBlock * sixc::kScratch) + warp;
-  double* Mg0 = scratch_M + ((size_t)a * R + j0 + warp * sixc::kSixSamplesPerWarp) * sixc::kMSize;
+  double* Mg = scratch_M + ((size_t)a * R + j) * sixc::kMSize;
   const int pair = pair0 + a;
   const long long off = offsets[pair];
   double c[6][6];
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kSixSolveThreads)
       c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
     }
   }
-  const int nm = sixc::six_solve_warp(S, W, Mg0, c, valid);
-  if (!valid) return;
+  if (!valid) return;  // the whole group leaves: the other groups of the warp never wait for it
+  const int nm = sixc::six_solve_group(S, Mg, c);
   float* srow = s32m + ((size_t)a * R + j) * kSixSlotModels;
   srow[gl] = INFINITY;
   srow[gl + 8] = INFINITY;
@@ -315,13 +316,12 @@ __global__ void __launch_bounds__(kSixSolveThreads)
   const int s = s0 + grp;
   const bool valid = s < ns;
   double* S = six_smem + (size_t)(warp * sixc::kSixSamplesPerWarp + grp) * sixc::kScratch;
-  sixc::SixWarpScratch* W = reinterpret_cast<sixc::SixWarpScratch*>(six_smem + (size_t)kSixSamplesPerBlock * sixc::kScratch) + warp;
   double c[6][6];
-  if (valid && gl == 0)
+  if (!valid) return;
+  if (gl == 0)
     for (int i = 0; i < 6; ++i)
       for (int q = 0; q < 6; ++q) c[i][q] = rays[6 * (size_t)samples[6 * s + i] + q];
-  const int nm = sixc::six_solve_warp(S, W, scratch_M + (size_t)s0 * sixc::kMSize, c, valid);
-  if (!valid) return;
+  const int nm = sixc::six_solve_group(S, scratch_M + (size_t)s * sixc::kMSize, c);
   if (gl == 0) nmodels[s] = nm;
   const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffT);
   for (int k = gl; k < nm; k += 8) {
