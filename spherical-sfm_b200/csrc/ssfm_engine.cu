@@ -313,6 +313,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         int* act = w.active0.p;
         int* act_next = w.active1.p;
         int round = 0;
+        SSFM_WCK(cudaFuncSetAttribute(k_sixpt_sample_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSixSolveSmem));
         while (count > 0) {
           const int cap = round == 0 ? first_cap : round_cap;
           SSFM_WCK(cudaEventRecord(evA, w.stream));
@@ -1220,6 +1221,7 @@ int ssfm_sixpt_solve(ssfm_handle h, const double* rays, int32_t n, const int32_t
   SSFM_CK(cudaMemcpyAsync(d_rays.p, rays, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(d_samples.p, samples6, sizeof(int) * 6 * num_samples, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemsetAsync(d_models.p, 0, sizeof(double) * num_samples * kSixMaxModels * 7, h->stream));
+  SSFM_CK(cudaFuncSetAttribute(k_sixpt_solve_samples, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSixSolveSmem));
   k_sixpt_solve_samples<<<(num_samples + kSixSamplesPerBlock - 1) / kSixSamplesPerBlock, kSixSolveThreads, kSixSolveSmem, h->stream>>>(
       d_rays.p, d_samples.p, num_samples, d_models.p, d_nm.p, d_M.p);
   SSFM_CK(cudaGetLastError());

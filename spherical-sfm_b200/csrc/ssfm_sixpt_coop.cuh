@@ -79,17 +79,20 @@ SSFM_HD double fast_rsqrt(double x) {
 }
 
 // Per-sample scratch (doubles).  T has a row stride of 17 so that a column walk (stride 17 doubles = 34 banks) is
-// conflict-free; kScratch = 4 (mod 16) puts the four samples of a warp on different banks for the broadcast reads.
+// conflict-free; kScratch = 4 (mod 16) puts the four samples of a warp on different banks for the broadcast reads; 436
+// doubles = 3.4 KB let two blocks of 32 samples share one SM.
 constexpr int kTS = 17;
-constexpr int kOffT = 0;                 // 16 x 17
-constexpr int kOffX = 16 * kTS;          // 112: L (10 x 11) while the companion matrix is built; then wr, wi, candidates
-constexpr int kOffFb = kOffX + 112;      // 27
+constexpr int kOffT = 0;                 // 16 x 17; after the eigenvalues: least-squares tableau (0..99), model list (140..244)
+constexpr int kOffX = 16 * kTS;          // 100: L (10 x 10) while the companion matrix is built; then wr, wi, candidates
+constexpr int kOffFb = kOffX + 100;      // 27
 constexpr int kOffPts = kOffFb + 27;     // 36: the normalised sample (x1[6][3], x2[6][3])
-constexpr int kOffMisc = kOffPts + 36;   // scale, ok flag
-constexpr int kScratch = 452;
-static_assert(kOffMisc + 2 <= kScratch && kScratch % 16 == 4, "scratch layout");
-constexpr int kLS = 11;                  // row stride of L
+constexpr int kScratch = 436;
+constexpr int kOffMisc = kOffT + 14 * kTS + 16;  // two doubles in the unused 17th column of T's rows 14 and 15: scale | flag
+constexpr int kMiscStride = kTS;
+static_assert(kOffPts + 36 <= kScratch && kScratch % 16 == 4, "scratch layout");
+constexpr int kLS = 10;                  // row stride of L
 constexpr int kOffWr = kOffX, kOffWi = kOffX + 16, kOffCand = kOffX + 32;  // candidates: 16 x (x, y, w, state)
+constexpr int kOffList = kOffT + 140;    // SixPointModel[15]
 constexpr int kMSize = 300;              // M[3][10][10] in the global scratch slot of a sample
 
 #define SIX_T(i, j) S[kOffT + (i) * kTS + (j)]
@@ -118,7 +121,7 @@ SSFM_HD bool six_setup(const G& g, const double (*c)[6], double* S, double* Mg) 
     double Fb[3][9];
     const bool ok = nullspace_6x9_ws(x1, x2, Fb, reinterpret_cast<double(*)[9]>(S + kOffT));
     S[kOffMisc] = s;
-    S[kOffMisc + 1] = ok ? 1.0 : 0.0;
+    S[kOffMisc + kMiscStride] = ok ? 1.0 : 0.0;
     for (int i = 0; i < 6; ++i)
       for (int d = 0; d < 3; ++d) { S[kOffPts + 3 * i + d] = x1[i][d]; S[kOffPts + 18 + 3 * i + d] = x2[i][d]; }
     if (ok) {
@@ -129,7 +132,7 @@ SSFM_HD bool six_setup(const G& g, const double (*c)[6], double* S, double* Mg) 
       for (int e = 0; e < 9; ++e) { F[e][0] = Fb[0][e]; F[e][1] = Fb[1][e]; F[e][2] = Fb[2][e]; }
       double* G0 = S + kOffX;        // 6 x 6
       double* G1 = S + kOffX + 36;   // 6 x 6
-      double* tr = S + kOffX + 72;   // 3 x 6
+      double* tr = S + kOffX + 72;   // 3 x 6 (90 of the 100 doubles of X)
       for (int i = 0; i < 3; ++i)
         for (int j = i; j < 3; ++j) {
           double a[6], b[6];
@@ -147,7 +150,7 @@ SSFM_HD bool six_setup(const G& g, const double (*c)[6], double* S, double* Mg) 
     }
   }
   g.sync();
-  if (S[kOffMisc + 1] == 0.0) return false;
+  if (S[kOffMisc + kMiscStride] == 0.0) return false;
   // the ten cubics, one per lane: equation 0 = det F, 1 + 3 i + j = (2 H F - tr(H) F)_ij with H = F Q F^T Q, Q = diag(1,1,w)
   for (int e = g.lane(); e < 10; e += G::kSize) {
     double o0[10], o1[10], o2[10];
@@ -230,10 +233,10 @@ SSFM_HD bool six_companion(const G& g, double* S, const double* Mg) {
         for (int i = k; i < 10; ++i) Bt[i][j] -= d * V[10 * k + i];
       }
     }
-    S[kOffMisc + 1] = ok ? 1.0 : 0.0;
+    S[kOffMisc + kMiscStride] = ok ? 1.0 : 0.0;
   }
   g.sync();
-  if (S[kOffMisc + 1] == 0.0) return false;
+  if (S[kOffMisc + kMiscStride] == 0.0) return false;
   // rows of Mk Q = ((row H0) H1) ... H5: 30 rows over the lanes
   for (int r = g.lane(); r < 30; r += G::kSize) {
     const int which = r / 10, e = r - 10 * which;
@@ -761,37 +764,54 @@ constexpr int kSixSamplesPerWarp = 4;
 
 // S: the group's scratch (kScratch doubles, shared memory); Mg: the sample's global M slot; c: the six correspondences
 // (read by lane 0 of the group only).  Returns the number of models (group-uniform); they are left sorted by focal at
-// S + kOffT (SixPointModel records).  Every collective inside names the group's own lanes.
-__device__ __noinline__ int six_solve_group(double* S, double* Mg, const double (*c)[6]) {
+// S + kOffT (SixPointModel records).  Every warp-level collective inside names the group's own lanes.
+// kBlockSync: every warp of the block walks the stages together (__syncthreads between them), so that all warps of an SM
+// execute the same few KB of code at a time: the solver is ~200 KB of instructions, and with every block in a stage of
+// its own the kernel spent more than half of its cycles waiting for instruction fetches (ncu: stall_no_instruction 7.8
+// per issue).  A group without a sample (valid == false) only takes part in the block barriers.
+template <bool kBlockSync>
+__device__ __forceinline__ int six_solve_group(double* S, double* Mg, const double (*c)[6], bool valid) {
   const int lane = threadIdx.x & 31, grp = lane >> 3;
   const LaneGroup8 g{lane & 7, 0xFFu << (8 * grp)};
-  if (!six_setup(g, c, S, Mg) || !six_companion(g, S, Mg)) return 0;
-  six_balance(g, S);
-  six_hessenberg(g, S);
-  if (!six_hqr(g, S)) return 0;
-  // candidates in eigenvalue order: least-squares start by the whole group, one after the other ...
-  for (int k = 0; k < 16; ++k) {
-    double w, xy[2];
-    bool keep = six_candidate(S[kOffWr + k], S[kOffWi + k], &w);
-    if (keep) keep = six_start(g, Mg, S + kOffT, w, xy);
+  bool live = valid;
+  if (live) live = six_setup(g, c, S, Mg) && six_companion(g, S, Mg);
+  if (live) {
+    six_balance(g, S);
+    six_hessenberg(g, S);
+  }
+  if (kBlockSync) __syncthreads();
+  if (live) live = six_hqr(g, S);
+  if (kBlockSync) __syncthreads();
+  if (live) {
+    // candidates in eigenvalue order: least-squares start by the whole group, one after the other ...
+    for (int k = 0; k < 16; ++k) {
+      double w, xy[2];
+      bool keep = six_candidate(S[kOffWr + k], S[kOffWi + k], &w);
+      if (keep) keep = six_start(g, Mg, S + kOffT, w, xy);
+      g.sync();
+      if (g.l == 0) {
+        double* dst = S + kOffCand + 4 * k;
+        dst[3] = keep ? 1.0 : 0.0;
+        if (keep) { dst[0] = xy[0]; dst[1] = xy[1]; dst[2] = w; }
+      }
+    }
     g.sync();
-    if (g.l == 0) {
-      double* dst = S + kOffCand + 4 * k;
-      dst[3] = keep ? 1.0 : 0.0;
-      if (keep) { dst[0] = xy[0]; dst[1] = xy[1]; dst[2] = w; }
-    }
   }
-  g.sync();
-  // ... Gauss-Newton with one lane per candidate ...
-  for (int r = 0; r < 2; ++r) {
-    double* cand = S + kOffCand + 4 * (g.l + 8 * r);
-    if (cand[3] == 1.0) {
-      double sol[3] = {cand[0], cand[1], cand[2]};
-      if (six_newton(Mg, sol)) { cand[0] = sol[0]; cand[1] = sol[1]; cand[2] = sol[2]; }
-      else cand[3] = 0.0;
+  if (kBlockSync) __syncthreads();
+  if (live) {
+    // ... Gauss-Newton with one lane per candidate ...
+    for (int r = 0; r < 2; ++r) {
+      double* cand = S + kOffCand + 4 * (g.l + 8 * r);
+      if (cand[3] == 1.0) {
+        double sol[3] = {cand[0], cand[1], cand[2]};
+        if (six_newton(Mg, sol)) { cand[0] = sol[0]; cand[1] = sol[1]; cand[2] = sol[2]; }
+        else cand[3] = 0.0;
+      }
     }
+    g.sync();
   }
-  g.sync();
+  if (kBlockSync) __syncthreads();
+  if (!live) return 0;
   if (g.l == 0) {  // ... and a solution equal to an earlier accepted one is dropped
     int n_sol = 0;
     for (int k = 0; k < 16; ++k) {
@@ -803,12 +823,11 @@ __device__ __noinline__ int six_solve_group(double* S, double* Mg, const double 
       S[kOffCand + 4 * k + 3] = 2.0;
       ++n_sol;
     }
+    S[kOffMisc + kMiscStride] = 0.0;  // number of models in the list
   }
   g.sync();
-  if (g.l == 0) S[kOffMisc + 1] = 0.0;  // number of models in the list
-  g.sync();
   // decomposition: one lane per accepted solution; the models enter the focal-sorted list in eigenvalue order
-  SixPointModel* list = reinterpret_cast<SixPointModel*>(S + kOffT);
+  SixPointModel* list = reinterpret_cast<SixPointModel*>(S + kOffList);
   for (int r = 0; r < 2; ++r) {
     const int k = g.l + 8 * r;
     SixPointModel four[4];
@@ -816,14 +835,14 @@ __device__ __noinline__ int six_solve_group(double* S, double* Mg, const double 
     if (S[kOffCand + 4 * k + 3] == 2.0) n4 = six_decompose(S, S + kOffCand + 4 * k, four);
     for (int kk = 0; kk < 8; ++kk) {
       if (g.l == kk && n4 > 0) {
-        int n_out = (int)S[kOffMisc + 1];
+        int n_out = (int)S[kOffMisc + kMiscStride];
         for (int i = 0; i < n4; ++i) n_out = six_insert_sorted(list, n_out, four[i]);
-        S[kOffMisc + 1] = (double)n_out;
+        S[kOffMisc + kMiscStride] = (double)n_out;
       }
       g.sync();
     }
   }
-  return (int)S[kOffMisc + 1];
+  return (int)S[kOffMisc + kMiscStride];
 }
 #endif  // __CUDACC__
 

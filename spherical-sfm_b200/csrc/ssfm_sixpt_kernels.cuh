@@ -63,11 +63,14 @@ __global__ void k_sixpt_init(Params P, const long long* __restrict__ offsets, in
 // memory.  Eight lanes per sample, four samples per warp (ssfm_sixpt_coop.cuh): every sample's 16 x 16 companion / Hessenberg
 // matrix and its small tables live in shared memory (3.6 KB), the ten cubics in a global scratch slot (2.4 KB, read back
 // through L2), so nothing of the solver goes through local memory except the per-candidate least-squares tableau.
-constexpr int kSixSolveThreads = 64;
+#ifndef SSFM_SIXPT_THREADS
+#define SSFM_SIXPT_THREADS 256  // 8 warps = 32 samples per block (divides the 256 look-ahead slots), two blocks per SM
+#endif
+constexpr int kSixSolveThreads = SSFM_SIXPT_THREADS;
 constexpr int kSixSamplesPerBlock = (kSixSolveThreads / 32) * sixc::kSixSamplesPerWarp;
 constexpr size_t kSixSolveSmem = (size_t)kSixSamplesPerBlock * sixc::kScratch * sizeof(double);
 #ifndef SSFM_SIXPT_MINBLOCKS
-#define SSFM_SIXPT_MINBLOCKS 7  // shared memory allows 7 blocks (14 warps) per SM: keep the registers under 146
+#define SSFM_SIXPT_MINBLOCKS 2  // x 256 threads: registers capped at 128
 #endif
 __global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
     k_sixpt_sample_solve(Params P, const double* __restrict__ rays, const long long* __restrict__ offsets, int pair0,
@@ -98,8 +101,8 @@ __global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
       c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
     }
   }
-  if (!valid) return;  // the whole group leaves: the other groups of the warp never wait for it
-  const int nm = sixc::six_solve_group(S, Mg, c);
+  const int nm = sixc::six_solve_group<true>(S, Mg, c, valid);
+  if (!valid) return;
   float* srow = s32m + ((size_t)a * R + j) * kSixSlotModels;
   srow[gl] = INFINITY;
   srow[gl + 8] = INFINITY;
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
   }
   if (nm == 0) return;
   base = __shfl_sync(0xFFu << (8 * grp), base, 8 * grp);
-  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffT);
+  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffList);
   double* dst = models + ((size_t)a * R + j) * kSixMaxModels * kSixRecord;
   for (int k = gl; k < nm; k += 8) {
     const SixPointModel mdl = list[k];
@@ -317,13 +320,13 @@ __global__ void __launch_bounds__(kSixSolveThreads)
   const bool valid = s < ns;
   double* S = six_smem + (size_t)(warp * sixc::kSixSamplesPerWarp + grp) * sixc::kScratch;
   double c[6][6];
-  if (!valid) return;
-  if (gl == 0)
+  if (valid && gl == 0)
     for (int i = 0; i < 6; ++i)
       for (int q = 0; q < 6; ++q) c[i][q] = rays[6 * (size_t)samples[6 * s + i] + q];
-  const int nm = sixc::six_solve_group(S, scratch_M + (size_t)s * sixc::kMSize, c);
+  const int nm = sixc::six_solve_group<true>(S, scratch_M + (size_t)s * sixc::kMSize, c, valid);
+  if (!valid) return;
   if (gl == 0) nmodels[s] = nm;
-  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffT);
+  const SixPointModel* list = reinterpret_cast<const SixPointModel*>(S + sixc::kOffList);
   for (int k = gl; k < nm; k += 8) {
     double* d = models + ((size_t)s * kSixMaxModels + k) * 7;
     for (int q = 0; q < 3; ++q) { d[q] = list[k].t[q]; d[3 + q] = list[k].r[q]; }
