@@ -99,6 +99,27 @@ SSFM_HD void load6(const double* p, double (&c)[6]) {
 #endif
 }
 
+// What the full passes over a pair read.  Pipeline rays are K^-1 (x, y, 1): z == 1 exactly, so the passes only need the
+// four doubles (u.x, u.y, v.x, v.y) of a correspondence -- 32 bytes instead of 48 from HBM, and k_chain is HBM-bound
+// (ncu: 4.6 TB/s).  `stream` is either the 48-byte records themselves or the compact plane with bit 0 of the address set
+// (records are 16-byte aligned); load_stream rebuilds the same six doubles either way, so the arithmetic is unchanged.
+SSFM_HD const double* compact_stream(const double* xy4) { return reinterpret_cast<const double*>(reinterpret_cast<uintptr_t>(xy4) | 1u); }
+SSFM_HD void load_stream(const double* stream, size_t i, double (&c)[6]) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(stream);
+  if (a & 1u) {
+    const double* p = reinterpret_cast<const double*>(a - 1u) + 4 * i;
+#if defined(__CUDA_ARCH__)
+    const double2 u = reinterpret_cast<const double2*>(p)[0];
+    const double2 v = reinterpret_cast<const double2*>(p)[1];
+    c[0] = u.x; c[1] = u.y; c[2] = 1.0; c[3] = v.x; c[4] = v.y; c[5] = 1.0;
+#else
+    c[0] = p[0]; c[1] = p[1]; c[2] = 1.0; c[3] = p[2]; c[4] = p[3]; c[5] = 1.0;
+#endif
+  } else {
+    load6(stream + 6 * i, c);
+  }
+}
+
 // ScoreModel (ransac.h:295-303) fused with the inlier count GetInliers would return for the same
 // model and threshold (:311-336): one pass yields both, so the reference's "GetInliers(best_model)"
 // refresh needs no second pass over the data.
@@ -110,7 +131,7 @@ SSFM_HD_NOINLINE double msac_score_exact(const Ctx& cx, const double* E, const d
 #pragma unroll 2
   for (int i = cx.lane(); i < n; i += cx.width()) {
     double ry[6];
-    load6(rays + 6 * (size_t)i, ry);
+    load_stream(rays, (size_t)i, ry);
     const double e = sampson_exact(E, ry, ry + 3);
     s += (thr < e) ? thr : e;  // std::min(e, thr) incl. its NaN behaviour (ransac.h:306-309)
     c += (e < thr) ? 1 : 0;
@@ -131,7 +152,7 @@ SSFM_HD_NOINLINE int collect_inliers(const Ctx& cx, const double* E, const doubl
     bool in = false;
     if (i < n) {
       double ry[6];
-      load6(rays + 6 * (size_t)i, ry);
+      load_stream(rays, (size_t)i, ry);
       const double e = sampson_exact(E, ry, ry + 3);
       in = inclusive ? (e <= thr) : (e < thr);
       if (flags) flags[i] = in ? 1 : 0;
@@ -442,8 +463,9 @@ struct Scratch {
 enum { PH_SCAN = 8, PH_RESCORE, PH_LO_COLLECT, PH_LO_SHUFFLE, PH_LO_LM, PH_LO_SCORE, PH_FINAL_LM, PH_FINAL_REST, PH_TOTAL };
 
 struct PairView {
-  const double* rays;  // 6 doubles per correspondence
+  const double* rays;    // 6 doubles per correspondence
   int n;
+  const double* stream;  // what msac_score_exact / collect_inliers read: rays, or compact_stream(xy plane) (load_stream)
 };
 
 template <class Ctx>
@@ -451,7 +473,7 @@ SSFM_HD_NOINLINE void lsq_fit(const Ctx& cx, const Params& P, const PairView& pv
                      long long* evals) {  // LeastSquaresFit, ransac.h:409-420
   const int cap = P.min_sample_mult * 3;
   int n;
-  { SSFM_TIC n = collect_inliers(cx, E, pv.rays, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
+  { SSFM_TIC n = collect_inliers(cx, E, pv.stream, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
   if (n < 3) return;
   { SSFM_TIC shuffle_and_resize(cx, sc.mt, sc.list_a, n, n < cap ? n : cap); SSFM_TOC(sc, PH_LO_SHUFFLE) }
   { SSFM_TIC least_squares(cx, pv.rays, sc.list_a, n < cap ? n : cap, P.inward != 0, E); SSFM_TOC(sc, PH_LO_LM) }
@@ -539,10 +561,10 @@ SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const P
   lsq_fit(cx, P, pv, sc, thr * mult, m_init, evals);
   int cnt = 0;
   double score;
-  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.rays, pv.n, thr, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
+  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.stream, pv.n, thr, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
   keep_better(score, m_init, cnt, score_best, E_best, cnt_best);
   if (P.num_lo_steps <= 0) return;  // inliers_base is only used by the steps below
-  const int nbase = collect_inliers(cx, m_init, pv.rays, pv.n, thr * mult, false, sc.list_b, (unsigned char*)0, evals);
+  const int nbase = collect_inliers(cx, m_init, pv.stream, pv.n, thr * mult, false, sc.list_b, (unsigned char*)0, evals);
   int non_min = 3 * P.non_min_mult;
   if (nbase / 2 < non_min) non_min = nbase / 2;
   if (non_min < 4) non_min = 4;
@@ -560,14 +582,14 @@ SSFM_HD_NOINLINE void local_optimization(const Ctx& cx, const Params& P, const P
     }
     double m[9];
     if (!non_minimal_solver(cx, pv, sc.list_a, ns, m, P.skip_complex != 0)) continue;
-    score = msac_score_exact(cx, m, pv.rays, pv.n, thr, &cnt, evals);
+    score = msac_score_exact(cx, m, pv.stream, pv.n, thr, &cnt, evals);
     keep_better(score, m, cnt, score_best, E_best, cnt_best);
     lsq_fit(cx, P, pv, sc, thr, m, evals);
     double th = mult * thr;
     const double dth = (mult - 1.0) * thr / (double)(int)(P.num_lsq_iters - 1);
     for (int i = 0; i < P.num_lsq_iters; ++i) {
       lsq_fit(cx, P, pv, sc, th, m, evals);
-      score = msac_score_exact(cx, m, pv.rays, pv.n, thr, &cnt, evals);
+      score = msac_score_exact(cx, m, pv.stream, pv.n, thr, &cnt, evals);
       keep_better(score, m, cnt, score_best, E_best, cnt_best);
       th -= dth;
     }
@@ -583,7 +605,7 @@ SSFM_HD_NOINLINE int lo_begin(const Ctx& cx, const Params& P, const PairView& pv
   if (4 > pv.n) return -1;
   const int cap = P.min_sample_mult * 3;
   int n;
-  { SSFM_TIC n = collect_inliers(cx, E, pv.rays, pv.n, P.thr2 * P.thr_mult, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
+  { SSFM_TIC n = collect_inliers(cx, E, pv.stream, pv.n, P.thr2 * P.thr_mult, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
   if (n < 3) return 0;
   { SSFM_TIC shuffle_and_resize(cx, sc.mt, sc.list_a, n, n < cap ? n : cap); SSFM_TOC(sc, PH_LO_SHUFFLE) }
   return n < cap ? n : cap;
@@ -594,7 +616,7 @@ SSFM_HD_NOINLINE void lo_end(const Ctx& cx, const Params& P, const PairView& pv,
                              double* E_target, double* score_target, int* cnt_target, long long* evals) {
   int cnt = 0;
   double score;
-  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.rays, pv.n, P.thr2, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
+  { SSFM_TIC score = msac_score_exact(cx, m_init, pv.stream, pv.n, P.thr2, &cnt, evals); SSFM_TOC(sc, PH_LO_SCORE) }
   keep_better(score, m_init, cnt, score_target, E_target, cnt_target);
 }
 
@@ -765,7 +787,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
       double Em[9];
       E_from_p(p, Em);
       int cnt = 0;
-      const double s = msac_score_exact(cx, Em, pv.rays, pv.n, P.thr2, &cnt, &st.evals_exact);
+      const double s = msac_score_exact(cx, Em, pv.stream, pv.n, P.thr2, &cnt, &st.evals_exact);
       if (legacy) {
         if (s < st.best_min_score && s < local_best) { local_best = s; local_id = m; local_cnt = cnt; }
       } else if (s < local_best) {
@@ -787,7 +809,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
         st.best_min_score = local_best;
         st.best_model_score = local_best;
         for (int i = 0; i < 9; ++i) st.E_best[i] = Em[i];
-        st.best_num_inliers = collect_inliers(cx, Em, pv.rays, pv.n, P.thr2, true, (int*)0, (unsigned char*)0, &st.evals_exact);
+        st.best_num_inliers = collect_inliers(cx, Em, pv.stream, pv.n, P.thr2, true, (int*)0, (unsigned char*)0, &st.evals_exact);
         st.inlier_ratio = (double)st.best_num_inliers / (double)pv.n;
         const double outlier_ratio = (pv.n - st.best_num_inliers) / (double)pv.n;
         if (outlier_ratio < 1.0) {  // msac.h:119-126
@@ -883,7 +905,7 @@ SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairVie
       // LeastSquares on ALL current inliers of best_model (stats.inlier_indices)
       double refined[9];
       if (stage < 2) {
-        const int ni = collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, &st.evals_exact);
+        const int ni = collect_inliers(cx, st.E_best, pv.stream, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, &st.evals_exact);
         if (DEFER) {
           if (cx.lane() == 0)
             for (int i = 0; i < 9; ++i) sc.lm_E[i] = st.E_best[i];
@@ -897,7 +919,7 @@ SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairVie
         for (int i = 0; i < 9; ++i) refined[i] = sc.lm_E[i];
       }
       int cnt = 0;
-      const double score = msac_score_exact(cx, refined, pv.rays, pv.n, P.thr2, &cnt, &st.evals_exact);
+      const double score = msac_score_exact(cx, refined, pv.stream, pv.n, P.thr2, &cnt, &st.evals_exact);
       if (score < st.best_model_score) {
         st.best_model_score = score;
         st.cnt_best = cnt;
@@ -913,7 +935,7 @@ SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairVie
       for (int i = cx.lane(); i < pv.n; i += cx.width()) flags[i] = 0;
     return 2;
   }
-  if (flags) collect_inliers(cx, st.E_best, pv.rays, pv.n, P.thr2, P.driver == 2, (int*)0, flags, &st.evals_exact);
+  if (flags) collect_inliers(cx, st.E_best, pv.stream, pv.n, P.thr2, P.driver == 2, (int*)0, flags, &st.evals_exact);
   decompose_spherical_E(st.E_best, P.inward != 0, r, t);
   return 0;
 }

@@ -90,6 +90,7 @@ struct ssfm_engine {
   const double* d_rays = nullptr;  // either rays_own.p or the caller's device pointer
   DevBuf<double> rays_own;
   DevBuf<float4> u4, v4, uv4;  // uv4: always; u4 / v4: only once a batch with z != 1 rays shows up (ensure_general_planes)
+  DevBuf<double> xy64;         // (u.x, u.y, v.x, v.y) in float64: what the chain's exact passes stream when every z == 1
   std::mutex general_mu;
   bool unit_z = false;
   // ssfm_upload_matches: keypoints / pair table / matches / Kinv (grow-only, kept across calls)
@@ -470,6 +471,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
       {
         ChainArgs A;
         A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = pair0;
+        A.xy64 = (unit_z && getenv("SSFM_NO_XY64") == nullptr) ? h->xy64.p : nullptr;
         A.navail = w.navail.p; A.states = w.states.p; A.R = R; A.models = w.models.p; A.s32 = w.s32.p; A.s32m = w.s32m.p;
         A.list_a = w.list_a.p; A.list_b = w.list_b.p; A.mt = w.mt.p; A.lm_E = w.lm_E.p; A.list_base = c0;
         A.flags = h->flags.p + c0; A.results = h->results.p + pair0; A.next_active = act_next; A.next_count = w.counts.p + 1;
@@ -651,7 +653,7 @@ void ssfm_destroy(ssfm_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->match_ctx && h->match_ctx_delete) h->match_ctx_delete(h->match_ctx);
   h->match_ctx = nullptr;
-  h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->offsets.release();
+  h->rays_own.release(); h->u4.release(); h->v4.release(); h->uv4.release(); h->xy64.release(); h->offsets.release();
   h->counts.release(); h->results.release(); h->flags.release();
   h->m_kp.release(); h->m_kpoff.release(); h->m_pairs.release(); h->m_matches.release(); h->m_kinv.release();
   for (int k = 0; k < h->num_workers; ++k) {
@@ -725,6 +727,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   SSFM_CK(cudaMemcpyAsync(h->offsets.p, h->h_offsets.data(), sizeof(long long) * (h->P + 1), cudaMemcpyHostToDevice, h->stream));
   const size_t m = (size_t)std::max<long long>(h->M, 1);
   SSFM_CK(h->uv4.ensure(m));
+  SSFM_CK(h->xy64.ensure(4 * m));
   SSFM_CK(h->counts.ensure(8));
   SSFM_CK(cudaMemsetAsync(h->counts.p, 0, 8 * sizeof(int), h->stream));
   // Worker streams are non-blocking and start reading `offsets` before any chunk event in the pipelined plan:
@@ -745,7 +748,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
         SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
                                 cudaMemcpyHostToDevice, h->stream));
         k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0,
-                                                                         h->up_flags.p + k);
+                                                                         h->xy64.p + 4 * c0, h->up_flags.p + k);
         SSFM_CK(cudaGetLastError());
       }
       SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -769,7 +772,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (h->M > 0) {
     const int threads = 256;
     const long long blocks = (h->M + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->uv4.p, h->counts.p + 2);
+    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->uv4.p, h->xy64.p, h->counts.p + 2);
     SSFM_CK(cudaGetLastError());
   }
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
@@ -823,6 +826,7 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
   SSFM_CK(h->m_kinv.ensure(9));
   SSFM_CK(h->rays_own.ensure((size_t)std::max<long long>(6 * M, 6)));
   SSFM_CK(h->uv4.ensure((size_t)std::max<long long>(M, 1)));
+  SSFM_CK(h->xy64.ensure((size_t)std::max<long long>(4 * M, 4)));
   SSFM_CK(h->offsets.ensure(P + 1));
   SSFM_CK(h->counts.ensure(8));
   h->d_rays = h->rays_own.p;
@@ -843,7 +847,7 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
     if (e != cudaSuccess) return e;
     k_build_rays<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(h->m_kp.p), h->m_kpoff.p, h->m_pairs.p,
                                                                     h->offsets.p, P, reinterpret_cast<const int2*>(h->m_matches.p), c0,
-                                                                    c1 - c0, h->m_kinv.p, h->rays_own.p, h->uv4.p, flag, h->counts.p + 3);
+                                                                    c1 - c0, h->m_kinv.p, h->rays_own.p, h->uv4.p, h->xy64.p, flag, h->counts.p + 3);
     return cudaGetLastError();
   };
   if (pipe) {
@@ -1338,7 +1342,7 @@ int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const doub
   SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M * num_pairs, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(doff, offsets, sizeof(long long) * ((size_t)num_pairs + 1), cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemsetAsync(dflag, 0, sizeof(int), h->stream));
-  if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, duv, dflag);
+  if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, duv, (double*)nullptr, dflag);
   SSFM_CK(cudaMemcpyAsync(h->h_count + 3, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
   const bool unit_z = h->h_count[3] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;

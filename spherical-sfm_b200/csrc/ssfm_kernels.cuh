@@ -100,12 +100,19 @@ __host__ __device__ inline int lookahead(uint32_t want, int cap) {
 // ------------------------------------------------------------------------------------------
 // uv4 (the unit-z plane) is always written; the general planes u4 / v4 only on request (k_pack_general), i.e. only for
 // batches that turn out to contain rays with z != 1.
-__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ uv4, int* __restrict__ not_unit_z) {
+// xy64: the same four numbers in float64 (32 bytes per correspondence), what the chain's exact passes stream for a unit-z batch.
+__global__ void k_pack(const double* __restrict__ rays, long long m, float4* __restrict__ uv4, double* __restrict__ xy64,
+                       int* __restrict__ not_unit_z) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const double2* src = reinterpret_cast<const double2*>(rays + 6 * i);  // 48-byte records, 16-byte aligned
   const double2 a = src[0], b = src[1], c = src[2];
   uv4[i] = make_float4((float)a.x, (float)a.y, (float)b.y, (float)c.x);
+  if (xy64) {
+    double2* d = reinterpret_cast<double2*>(xy64 + 4 * i);
+    d[0] = a;
+    d[1] = make_double2(b.y, c.x);
+  }
   // pipeline rays are K^-1 (x, y, 1) (examples/spherical_sfm_tools.cpp:364-373): z == 1 exactly
   if (b.x != 1.0 || c.y != 1.0) *not_unit_z = 1;
 }
@@ -126,8 +133,8 @@ __global__ void k_pack_general(const double* __restrict__ rays, long long m, flo
 __global__ void k_build_rays(const float2* __restrict__ kp, const long long* __restrict__ kp_off,
                              const int* __restrict__ pair_images, const long long* __restrict__ match_off, int npairs,
                              const int2* __restrict__ matches, long long m0, long long m, const double* __restrict__ Kinv,
-                             double* __restrict__ rays, float4* __restrict__ uv4, int* __restrict__ not_unit_z,
-                             int* __restrict__ bad_index) {
+                             double* __restrict__ rays, float4* __restrict__ uv4, double* __restrict__ xy64,
+                             int* __restrict__ not_unit_z, int* __restrict__ bad_index) {
   const long long i = m0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m0 + m) return;
   int lo = 0, hi = npairs;  // last pair whose first match is <= i
@@ -159,6 +166,11 @@ __global__ void k_build_rays(const float2* __restrict__ kp, const long long* __r
   dst[2] = make_double2(out[4], out[5]);
   // the FP32 plane of the scoring kernel, in the same pass (what k_pack would produce from these rays)
   uv4[i] = make_float4((float)out[0], (float)out[1], (float)out[3], (float)out[4]);
+  if (xy64) {
+    double2* d = reinterpret_cast<double2*>(xy64 + 4 * i);
+    d[0] = make_double2(out[0], out[1]);
+    d[1] = make_double2(out[3], out[4]);
+  }
   if (out[2] != 1.0 || out[5] != 1.0) *not_unit_z = 1;
 }
 
@@ -536,6 +548,7 @@ constexpr int kSmallRefit = 32;  // refits with at most this many residuals get 
 
 struct ChainArgs {
   const double* rays;
+  const double* xy64;  // compact float64 plane (u.x, u.y, v.x, v.y) of a unit-z batch, or NULL
   const long long* offsets;
   int pair0;
   const int* list;
@@ -574,7 +587,7 @@ __global__ void __launch_bounds__(kChainWarps * 32, DEFER ? SSFM_CHAIN_MINBLOCKS
   const int pair = A.pair0 + a;
   const long long off = A.offsets[pair];
   const int n = (int)(A.offsets[pair + 1] - off);
-  PairView pv{A.rays + 6 * off, n};
+  PairView pv{A.rays + 6 * off, n, A.xy64 ? compact_stream(A.xy64 + 4 * off) : A.rays + 6 * off};
   Scratch sc{A.list_a + (off - A.list_base), A.list_b + (off - A.list_base), A.mt + (size_t)a * 625, A.counters,
              A.lm_E + (size_t)a * 9};
 #if defined(SSFM_PROFILE_CHAIN)
@@ -892,7 +905,7 @@ __global__ void k_non_minimal(const double* __restrict__ rays, int n, const int*
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= nprob) return;
   WarpCtx cx{(int)(threadIdx.x & 31)};
-  PairView pv{rays, n};
+  PairView pv{rays, n, rays};
   double E[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool good = non_minimal_solver(cx, pv, idx + sample_offsets[w], sample_offsets[w + 1] - sample_offsets[w], E);
   if (cx.lane() == 0) {

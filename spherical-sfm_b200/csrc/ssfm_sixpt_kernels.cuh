@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain(Params P, S
   const int pair = A.pair0 + a;
   const long long off = A.offsets[pair];
   const int n = (int)(A.offsets[pair + 1] - off);
-  PairView pv{A.rays + 6 * off, n};
+  PairView pv{A.rays + 6 * off, n, A.rays + 6 * off};
   SixState st = A.states[a];
   const int na = A.navail[a];
   const double* mbase = A.models + (size_t)a * A.R * kSixMaxModels * kSixRecord;

@@ -142,7 +142,7 @@ void hs_estimate_pair(const double* rays, int n, const HsParams* hp, uint32_t pa
   double lmE[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   Scratch sc{la.data(), lb.data(), mt.data(), nullptr, lmE};
   const bool defer = hp->defer != 0 && P.num_lo_steps == 0;
-  PairView pv{rays, n};
+  PairView pv{rays, n, rays};
   SerialCtx cx;
   int rounds = 0, candidates = 0;
   std::vector<double> models;
