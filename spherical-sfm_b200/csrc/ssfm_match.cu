@@ -283,6 +283,35 @@ __device__ __noinline__ Top2 top2_group_far(Top2 s, float x0, float x1, float x2
   return s;
 }
 
+// 32 consecutive train rows against the running top-2 of this thread's query row.  Groups of eight = two of four: one min
+// tree per eight and ONE round of warp votes per 32 (against the threshold at the start: it only decreases, so a stale
+// one lets a few more groups through, never fewer); the four-groups that hold a candidate are walked.
+__device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, float qn, float far_a) {
+  float m4[8], m8[4];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) m4[h] = fminf(min3f(x[4 * h], x[4 * h + 1], x[4 * h + 2]), x[4 * h + 3]);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) m8[g] = fminf(m4[2 * g], m4[2 * g + 1]);
+  bool gate[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) gate[g] = __any_sync(0xffffffffu, m8[g] < st.a1);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (gate[g]) {
+#pragma unroll
+      for (int h = 2 * g; h < 2 * g + 2; ++h) {
+        const bool hit = m4[h] < st.a1;
+        if (__any_sync(0xffffffffu, hit)) {
+          if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
+            st = top2_group_far(st, x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3], qn, idx0 + 4 * h);
+          else
+            top2_group(st, x + 4 * h, idx0 + 4 * h);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ packed_t, const float* __restrict__ norms,
             const long long* __restrict__ prow_off, const int* __restrict__ nrows, const int* __restrict__ pair_images,
@@ -394,35 +423,18 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
         mbar_wait(&sm->tfull[b], (it / kAccBufs) & 1u);
         tc_fence_after();
         const uint32_t taddr = lane_addr + b * (2 * kTTile);
+        // two register buffers: the next 32 columns are in flight while the current ones are scanned
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_wait(va);
 #pragma unroll 1
-        for (int c = 0; c < kTTile / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(c * 32), v);
-          tmem_wait(v);
-          const float* x = reinterpret_cast<const float*>(v);
-          const int idx0 = t * kTTile + c * 32;
-          // groups of eight = two of four: one min tree and one warp vote per eight when nobody has a candidate; otherwise
-          // the four-groups that hold one are walked
-          float m4[8], m8[4];
-#pragma unroll
-          for (int h = 0; h < 8; ++h) m4[h] = fminf(min3f(x[4 * h], x[4 * h + 1], x[4 * h + 2]), x[4 * h + 3]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) m8[g] = fminf(m4[2 * g], m4[2 * g + 1]);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (__any_sync(0xffffffffu, m8[g] < st.a1)) {
-#pragma unroll
-              for (int h = 2 * g; h < 2 * g + 2; ++h) {
-                const bool hit = m4[h] < st.a1;
-                if (__any_sync(0xffffffffu, hit)) {
-                  if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
-                    st = top2_group_far(st, x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3], qn, idx0 + 4 * h);
-                  else
-                    top2_group(st, x + 4 * h, idx0 + 4 * h);
-                }
-              }
-            }
-          }
+        for (int c = 0; c < kTTile / 32; c += 2) {
+          tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
+          top2_scan32(st, reinterpret_cast<const float*>(va), t * kTTile + c * 32, qn, far_a);
+          tmem_wait(vb);
+          if (c + 2 < kTTile / 32) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
+          top2_scan32(st, reinterpret_cast<const float*>(vb), t * kTTile + (c + 1) * 32, qn, far_a);
+          if (c + 2 < kTTile / 32) tmem_wait(va);
         }
         tc_fence_before();
         __syncwarp();

