@@ -677,6 +677,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
   // s32[j] = min over the four roots of the FP32 cost, s32m[m * mstride + j] = the four costs.
   const bool lo_driver = P.driver == 0;
   const bool legacy = P.driver == 2;
+  const float abs_slack = (float)pv.n * (float)P.thr2 * 2.4e-7f;
   int j = 0;
   bool skip_top = false;
   if (DEFER && st.phase == PHASE_LO_START) {  // the refit of the LO at lo_start came back (ransac.h:166-177)
@@ -713,7 +714,9 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
         const int jj = base + cx.slane();
         const float s = jj < navail ? s32[jj] : INFINITY;
         const float before = cx.prefix_min_excl(s, run);
-        const bool cand = s < INFINITY && s <= before * (1.0f + P.cand_margin);
+        // relative slack + an absolute one for scores near zero (noise-free data), where FP32 rounding noise of the sum
+        // (<= n * thr * 2^-22) is all that separates the iterations
+        const bool cand = s < INFINITY && s <= before * (1.0f + P.cand_margin) + abs_slack;
         const bool special = lo_driver && jj < navail && (st.it + (uint32_t)(jj - j)) == P.lo_start;
         const unsigned m = cx.ballot(cand || special);
         if (m) {
@@ -783,7 +786,7 @@ SSFM_HD_NOINLINE void process_round(const Ctx& cx, const Params& P, const PairVi
       if (p[0] != p[0]) continue;  // absent (or NaN) model: can never win a '<'
       ++nvalid;
       const float sm = s32m[(size_t)m * mstride + j];
-      if (!(sm <= smin * (1.0f + P.cand_margin))) continue;
+      if (!(sm <= smin * (1.0f + P.cand_margin) + abs_slack)) continue;
       double Em[9];
       E_from_p(p, Em);
       int cnt = 0;

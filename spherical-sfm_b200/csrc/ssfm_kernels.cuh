@@ -359,6 +359,15 @@ __device__ __forceinline__ void sampson2_unitz(const f32x2 (&P)[7], f32x2 X, f32
 // cost (and optionally the inlier count) of the calling thread's four models.  Warps whose lanes
 // are all idle (`active` false) only take part in the barriers.  Partial sums are folded per tile
 // so the FP32 accumulation error stays ~(kTile + ntiles) ulp.
+// min(e, thr) that PROPAGATES a NaN residual (FMNMX.NAN, same cost as fminf): the reference's std::min(e, thr) returns the NaN
+// and such a model never wins; with fminf it would count as thr, get a finite FP32 score and could lower the running
+// minimum of the pre-filter.  A NaN FP32 score is never a candidate and never enters the running minimum.
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
 template <bool UNITZ, bool COUNT>
 __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4* __restrict__ pa, const float4* __restrict__ pb,
                                              long long c0, long long c1, const float (&p)[4][6], float thr, bool active,
@@ -410,7 +419,7 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
             const f32x2 e2 = mul2(d2, pack2(rcp_ftz(dl), rcp_ftz(dh)));
             float el, eh;
             unpack2(e2, el, eh);
-            tacc2[h] = add2(tacc2[h], pack2(fminf(el, thr), fminf(eh, thr)));
+            tacc2[h] = add2(tacc2[h], pack2(min_nan(el, thr), min_nan(eh, thr)));
             if (COUNT) {
               cnt[2 * h] += (el < thr) ? 1 : 0;
               cnt[2 * h + 1] += (eh < thr) ? 1 : 0;
@@ -434,7 +443,7 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             const float e = UNITZ ? sampson_f32_unitz(p[m], ca) : sampson_f32(p[m], ca, cb);
-            tacc[m] += fminf(e, thr);
+            tacc[m] += min_nan(e, thr);
             if (COUNT) cnt[m] += (e < thr) ? 1 : 0;
           }
         }

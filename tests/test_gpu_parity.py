@@ -144,6 +144,36 @@ def test_config_c3_slice(S, O, engine, orc, ref):
     _compare_batch(S, O, engine, ref if ref is not None else orc, S.pipeline_options(THR2), 16, 1500, 0.7, 77)
 
 
+def test_near_noise_free_pairs_scores_near_zero(S, O, engine, orc, ref):
+    """Almost noise-free data (0.001 px), with and without outliers: the MSAC cost of a good model is ~1e-15 in float64 -
+    still well defined, different minimal samples give distinguishable costs - while its FP32 copy is pure rounding noise
+    (the epipolar product cancels to ~1e-7 absolute), so a purely relative FP32 pre-filter would skip iterations the
+    reference loop acts on.  The pre-filter's absolute slack must keep the trajectory identical: iteration / LO
+    counts, inlier counts and flags.  Exactly noise-free data is run too, but there even the float64 costs (~1e-28) are
+    rounding noise of the minimal solver, so which of the perfect models 'wins' an iteration is not defined by the
+    reference either: only the outcome (status, every true correspondence an inlier, pose) is asserted."""
+    impl = ref if ref is not None else orc
+    for seed, outl, noise in ((21, 0.0, 1e-3 / 600), (22, 0.3, 1e-3 / 600), (23, 0.0, 0.0), (24, 0.3, 0.0)):
+        P, N = 12, 400
+        rays, offsets, probs = S.problems.make_batch(seed, P, N, noise=noise, outlier_frac=outl, max_angle_deg=20.0)
+        opt = S.pipeline_options(THR2)
+        res, flags = engine.estimate_pairs(rays, offsets, opt)
+        oopt = to_oracle_options(O, opt)
+        for p in range(P):
+            r, inl = impl.estimate_pair(rays[offsets[p]:offsets[p + 1]], oopt, p)
+            fl = np.zeros(N, np.uint8)
+            fl[inl] = 1
+            assert int(res["status"][p]) == r.status
+            assert np.rad2deg(S.problems.rot_error(probs[p].R, S.problems.so3exp(res["r"][p]))) < 0.01
+            if noise == 0.0:
+                assert int(res["best_num_inliers"][p]) >= int(round(N * (1 - outl))), (seed, p)
+                continue
+            assert int(res["num_iterations"][p]) == r.num_iterations, (seed, p)
+            assert int(res["number_lo_iterations"][p]) == r.number_lo_iterations, (seed, p)
+            assert int(res["best_num_inliers"][p]) == r.best_num_inliers, (seed, p)
+            assert (flags[offsets[p]:offsets[p + 1]] == fl).all(), (seed, p)
+
+
 def test_default_lo_options(S, O, engine, orc, ref):
     """RansacLib's default LO schedule (10 LO steps x 4 LSQ iterations, NonMinimalSolver)."""
     _compare_batch(S, O, engine, ref if ref is not None else orc, S.default_options(squared_inlier_threshold=THR2), 8, 600, 0.5, 5)

@@ -4,6 +4,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
@@ -25,7 +26,7 @@ with open(out, "w") as f:
     f.write("# %s\n\nSource: `%s` (ncu --set full --clock-control none --import-source on). One column per captured launch.\n\n" % (title, rep))
     f.write("| metric | unit | " + " | ".join("launch %d" % i for i in range(len(data))) + " |\n|---|---|" + "---|" * len(data) + "\n")
     f.write("| kernel | | " + " | ".join(r[hdr.index("Kernel Name")][:40] for r in data) + " |\n")
-    for k in KEYS:
+    for k in KEYS + [h for h in hdr if ("tensor" in h or "tmem" in h) and h not in KEYS][:12]:
         if k in hdr:
             i = hdr.index(k)
             f.write("| %s | %s | %s |\n" % (k, units[i], " | ".join(r[i] for r in data)))
