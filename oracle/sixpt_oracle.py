@@ -303,6 +303,175 @@ def vanilla_msac(rays, sampler, thr2, min_iters=100, max_iters=10000, prob=0.999
     return st
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# LocallyOptimizedMSAC (include/RansacLib/ransac.h:119-430) around the six-point estimator: the driver the estimator's
+# NonMinimalSolver (examples/six_point_estimator.cpp:121-144) and LeastSquares (:146-192) exist for.
+# ---------------------------------------------------------------------------------------------------------------
+class Mt19937:
+    """std::mt19937 seeded with rng.seed(seed) (ransac.h:143-144): numpy's legacy seeding is the same init_genrand."""
+
+    def __init__(self, seed):
+        self._bg = np.random.RandomState(int(seed) & 0xFFFFFFFF)._bit_generator
+
+    def __call__(self):
+        return int(self._bg.random_raw())
+
+
+def _uniform_int(rng, lo, hi):
+    """std::uniform_int_distribution<int>(lo, hi)(mt19937), libstdc++ >= 11 (Lemire's nearly divisionless method)"""
+    rng_range = hi - lo + 1
+    prod = rng() * rng_range
+    low = prod & 0xFFFFFFFF
+    if low < rng_range:
+        threshold = ((1 << 32) - rng_range) % rng_range
+        while low < threshold:
+            prod = rng() * rng_range
+            low = prod & 0xFFFFFFFF
+    return lo + (prod >> 32)
+
+
+def shuffle_and_resize(v, target, rng):
+    """utils::RandomShuffleAndResize (include/RansacLib/utils.h:34-73); std::vector::resize pads with zeros"""
+    v = list(v)
+    n = len(v)
+    for i in range(n - 1):
+        j = _uniform_int(rng, i, n - 1)
+        v[i], v[j] = v[j], v[i]
+    return v[:target] + [0] * max(0, target - n)
+
+
+def lo_msac(rays, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.9999, num_lo_steps=10,
+            threshold_multiplier=np.sqrt(2.0), num_lsq_iterations=4, min_sample_multiplicator=7, non_min_sample_multiplier=3,
+            lo_starting_iterations=50, final_least_squares=False, focal_scoring=False, solve=None):
+    """LocallyOptimizedMSAC::EstimateModel with SixPointEstimator (min_sample_size 6, non_minimal_sample_size 7).
+    sampler(iteration) -> 6 indices (the product's Philox stream); solve(rays6) substitutes the minimal solver."""
+    solve = solve or minimal_solver
+    n = len(rays)
+    BIG = np.finfo(float).max
+    st = dict(num_iterations=0, best_num_inliers=0, best_model_score=BIG, inlier_ratio=0.0, inliers=np.zeros(0, int),
+              model=None, number_lo_iterations=0, status=1 if n < 6 else 2, lm_calls=0)
+    if n < 6:
+        return st
+    rng = Mt19937(seed)
+
+    def G_of(m):
+        return scoring_matrix(m, focal_scoring)
+
+    def score_model(m):  # ScoreModel :295-303 (sequential sum)
+        e = np.minimum(sampson(G_of(m), rays), thr2)
+        s = 0.0
+        for x in e:
+            s += x
+        return s
+
+    def get_inliers(m, thr):
+        return np.nonzero(sampson(G_of(m), rays) < thr)[0]
+
+    def lsq(m, sample):
+        st["lm_calls"] += 1
+        return least_squares(rays, sample, m)[0]
+
+    def least_squares_fit(thresh, m):  # :409-420
+        inl = get_inliers(m, thresh)
+        if len(inl) < 6:
+            return m
+        k = min(min_sample_multiplicator * 6, len(inl))
+        return lsq(m, shuffle_and_resize(inl, k, rng))
+
+    def non_minimal_solver(sample):  # six_point_estimator.cpp:121-144: the first six of the sample, summed error over all
+        sols = solve(rays[sample[:6]])
+        if not sols:
+            return None
+        best, best_score = 0, np.inf
+        for i, m in enumerate(sols):
+            e = sampson(G_of(m), rays[sample])
+            s = 0.0
+            for x in e:
+                s += x
+            if s < best_score:
+                best_score, best = s, i
+        return sols[best]
+
+    def local_optimization(m_best, score_best):  # :341-407
+        if 7 > n:
+            return m_best, score_best
+        m_init = least_squares_fit(thr2 * threshold_multiplier, m_best)
+        score = score_model(m_init)
+        if score < score_best:
+            score_best, m_best = score, m_init
+        base = get_inliers(m_init, thr2 * threshold_multiplier)
+        non_min = max(7, min(6 * non_min_sample_multiplier, len(base) // 2))
+        for _ in range(num_lo_steps):
+            sample = shuffle_and_resize(base, non_min, rng)
+            m = non_minimal_solver(np.asarray(sample, int))
+            if m is None:
+                continue
+            score = score_model(m)
+            if score < score_best:
+                score_best, m_best = score, m
+            m = least_squares_fit(thr2, m)
+            th = threshold_multiplier * thr2
+            with np.errstate(all="ignore"):
+                dth = np.float64((threshold_multiplier - 1.0) * thr2) / np.float64(int(num_lsq_iterations - 1))
+            for _i in range(num_lsq_iterations):
+                m = least_squares_fit(th, m)
+                score = score_model(m)
+                if score < score_best:
+                    score_best, m_best = score, m
+                th -= dth
+        return m_best, score_best
+
+    def refresh(update_max):
+        nonlocal limit
+        st["inliers"] = get_inliers(st["model"], thr2)
+        st["best_num_inliers"] = len(st["inliers"])
+        st["inlier_ratio"] = st["best_num_inliers"] / n
+        if update_max:
+            limit = required_iterations(st["inlier_ratio"], 1.0 - prob, 6, min_iters, max_iters)
+
+    limit = max(max_iters, min_iters)
+    best_min, best_min_score = None, BIG
+    it = 0
+    while it < limit:
+        if it == lo_starting_iterations and best_min_score < BIG:  # :166-177
+            st["number_lo_iterations"] += 1
+            st["model"], st["best_model_score"] = local_optimization(st["model"], st["best_model_score"])
+            refresh(True)
+        models = solve(rays[sampler(it)])
+        if models:
+            scores = [score_model(m) for m in models]
+            k = int(np.argmin(scores))  # first minimum, like the strict '<' scan (:278-293); NaN scores never win there
+            local = scores[k] if scores[k] == scores[k] else BIG
+            if local < best_min_score or it == lo_starting_iterations:
+                better = local < best_min_score
+                if better:
+                    best_min_score, best_min = local, models[k]
+                    if best_min_score < st["best_model_score"]:
+                        st["best_model_score"], st["model"] = best_min_score, best_min
+                    st["status"] = 0
+                run_lo = it >= lo_starting_iterations and best_min_score < BIG
+                if better or run_lo:
+                    if run_lo:
+                        st["number_lo_iterations"] += 1
+                        best_min, score = local_optimization(best_min, best_min_score)
+                        if score < st["best_model_score"]:
+                            st["best_model_score"], st["model"] = score, best_min
+                    refresh(True)
+        it += 1
+    st["num_iterations"] = it
+    if it <= lo_starting_iterations and st["best_model_score"] < BIG:  # :246-257
+        st["number_lo_iterations"] += 1
+        st["model"], st["best_model_score"] = local_optimization(st["model"], st["best_model_score"])
+        refresh(False)
+    if final_least_squares and st["model"] is not None:  # :259-275
+        refined = lsq(st["model"], st["inliers"])
+        score = score_model(refined)
+        if score < st["best_model_score"]:
+            st["best_model_score"], st["model"] = score, refined
+            refresh(False)
+    return st
+
+
 def make_problem(rng, n, focal, outlier_frac=0.0, noise_px=0.0, max_angle_deg=20.0):
     """synthetic shared-focal pair in pixel units about the principal point (config C4)"""
     ax = rng.normal(size=3)
@@ -329,12 +498,18 @@ def make_problem(rng, n, focal, outlier_frac=0.0, noise_px=0.0, max_angle_deg=20
 # trust-region LM with Solver::Options defaults, the autodiff'd SampsonError functor (:25-76) and
 # ceres::SphereManifold<3> (Plus / PlusJacobian in Householder form) are restated from Ceres' documentation.
 # ---------------------------------------------------------------------------------------------------------------
+def _col(a):
+    """broadcast a value part against a (..., 7) partials part"""
+    return a[..., None] if isinstance(a, np.ndarray) and a.ndim else a
+
+
 class _Dual:
-    """forward-mode scalar with a 7-vector of partials (r1, t1, focal) -- the role of ceres::Jet<double, 7>"""
+    """forward-mode scalar with a 7-vector of partials (r1, t1, focal) -- the role of ceres::Jet<double, 7>.  The value may
+    be an array (one entry per residual, partials (n, 7)): the same elementwise operations, evaluated for all residuals at once."""
     __slots__ = ("a", "v")
 
     def __init__(self, a, v=None):
-        self.a = float(a)
+        self.a = a if isinstance(a, np.ndarray) else float(a)
         self.v = np.zeros(7) if v is None else v
 
     @staticmethod
@@ -363,13 +538,13 @@ class _Dual:
 
     def __mul__(self, o):
         o = self._c(o)
-        return _Dual(self.a * o.a, self.a * o.v + self.v * o.a)
+        return _Dual(self.a * o.a, _col(self.a) * o.v + self.v * _col(o.a))
     __rmul__ = __mul__
 
     def __truediv__(self, o):
         o = self._c(o)
         q = self.a / o.a
-        return _Dual(q, (self.v - q * o.v) / o.a)
+        return _Dual(q, (self.v - _col(q) * o.v) / _col(o.a))
 
 
 def _dsqrt(x):
@@ -434,20 +609,26 @@ def least_squares(rays, sample, model, max_iters=200):
     """returns (refined model, iterations, initial cost, final cost)"""
     t, r, f = model
     x = np.concatenate([np.asarray(r, float), np.asarray(t, float), [float(f)]])
-    pts = [(rays[i, :3], rays[i, 3:]) for i in sample]
+    pts = np.asarray(sample, int)
+    U = np.ascontiguousarray(rays[pts, :3].T)  # all residuals at once: the functor's arithmetic is elementwise
+    V = np.ascontiguousarray(rays[pts, 3:].T)
 
     def eval_full(xx):
         X = [_Dual.var(xx[k], k) for k in range(7)]
-        res = [_sampson_functor(X, u, v) for u, v in pts]
-        rv = np.array([q.a for q in res])
-        Ja = np.array([q.v for q in res]).reshape(-1, 7)
+        if len(pts) == 0:
+            return np.zeros(0), np.zeros((0, 6))
+        res = _sampson_functor(X, U, V)
+        rv = np.array(res.a, float).reshape(-1)
+        Ja = np.broadcast_to(res.v, (len(pts), 7))
         Pt = sphere_plus_jacobian(xx[3:6])
         Jl = np.concatenate([Ja[:, :3], Ja[:, 3:6] @ Pt, Ja[:, 6:7]], axis=1)
         return rv, Jl
 
     def eval_cost(xx):
         X = [_Dual(xx[k]) for k in range(7)]
-        rv = np.array([_sampson_functor(X, u, v).a for u, v in pts])
+        if len(pts) == 0:
+            return 0.0
+        rv = np.array(_sampson_functor(X, U, V).a, float).reshape(-1)
         return 0.5 * float(rv @ rv)
 
     res, J = eval_full(x)

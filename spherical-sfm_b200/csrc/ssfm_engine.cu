@@ -137,6 +137,8 @@ struct Worker {
   DevBuf<unsigned long long> counters;
   DevBuf<unsigned char> has;  // pre-emptive driver: hypothesis-has-a-model flags
   DevBuf<SixState> six_states;  // six-point estimator
+  DevBuf<SixLoState> six_lo_states;  // ... under LO-MSAC
+  DevBuf<uint32_t> six_it;           // iteration number of every pair's look-ahead slot 0
   DevBuf<double> six_M;         // the ten cubics of every look-ahead sample (global scratch of k_sixpt_sample_solve)
   DevBuf<LMState> lm_states;    // stragglers handed from k_refit_small to k_refit_long
   DevBuf<int> long_list;
@@ -154,7 +156,7 @@ struct Worker {
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release(); has.release();
     lm_states.release(); long_list.release();
-    six_states.release(); six_M.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
+    six_states.release(); six_lo_states.release(); six_it.release(); six_M.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
   }
 };
 
@@ -194,8 +196,8 @@ Params make_params(const SsfmOptions& o) {
 int check_options(const SsfmOptions* o) {
   if (!o) return fail(SSFM_ERR_INVALID, "options is NULL");
   if (o->solver < 0 || o->solver > 3) return fail(SSFM_ERR_INVALID, "unknown solver kind");
-  if (o->solver == SSFM_SOLVER_SIXPT_FOCAL && o->driver != SSFM_DRIVER_VANILLA_MSAC)
-    return fail(SSFM_ERR_INVALID, "the batched six-point shared-focal path runs SSFM_DRIVER_VANILLA_MSAC (config C4); for LO-MSAC drive GpuSixPointEstimator through the hooks");
+  if (o->solver == SSFM_SOLVER_SIXPT_FOCAL && o->driver != SSFM_DRIVER_VANILLA_MSAC && o->driver != SSFM_DRIVER_LO_MSAC)
+    return fail(SSFM_ERR_INVALID, "the batched six-point shared-focal path runs SSFM_DRIVER_VANILLA_MSAC (config C4) or SSFM_DRIVER_LO_MSAC");
   if (o->driver < 0 || o->driver > 3) return fail(SSFM_ERR_INVALID, "unknown driver kind");
   if (o->complex_root_models != SSFM_COMPLEX_CANONICAL && o->complex_root_models != SSFM_COMPLEX_SKIP)
     return fail(SSFM_ERR_INVALID, "unknown complex_root_models");
@@ -209,8 +211,8 @@ int check_options(const SsfmOptions* o) {
 
 template <int KIND>
 void launch_solve(ssfm_engine* h, Worker& w, const Params& P, int pair0, const int* active, int count, int cap, int R) {
-  dim3 grid(count, (cap + 63) / 64);
-  k_sample_solve<KIND><<<grid, 64, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, active, w.navail.p, w.states.p, R,
+  dim3 grid(count, (cap + kSolveThreads - 1) / kSolveThreads);
+  k_sample_solve<KIND><<<grid, kSolveThreads, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, active, w.navail.p, w.states.p, R,
                                                   w.models.p);
 }
 
@@ -290,12 +292,22 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
       if (int rc = ensure_general_planes(h, w.stream, c0, c1, &w.err)) return rc;
     }
     if (P.solver == SSFM_SOLVER_SIXPT_FOCAL) {
-      // Six-point shared-focal estimator under VanillaMSAC: look-ahead rounds like the 3-point path, in
-      // sub-passes bounded by the model table (15 models x 16 doubles per look-ahead slot).
+      // Six-point shared-focal estimator under VanillaMSAC (config C4) or LO-MSAC: look-ahead rounds like the 3-point
+      // path, in sub-passes bounded by the model table (15 models x 16 doubles per look-ahead slot).
+      const bool six_lo = P.driver == SSFM_DRIVER_LO_MSAC;
       const int kSub = 2048;
+      if (six_lo) {
+        SSFM_WCK(w.list_a.ensure(mpass + 16));
+        SSFM_WCK(w.list_b.ensure(mpass + 16));
+        SSFM_WCK(w.mt.ensure((size_t)std::min(np, kSub) * 625));
+        SSFM_WCK(w.parked0.ensure(std::min(np, kSub)));
+        SSFM_WCK(w.parked1.ensure(std::min(np, kSub)));
+      }
       for (int s0 = 0; s0 < np; s0 += kSub) {
         const int q0 = pair0 + s0, nq = std::min(kSub, np - s0);
-        SSFM_WCK(w.six_states.ensure(nq));
+        if (six_lo) SSFM_WCK(w.six_lo_states.ensure(nq));
+        else SSFM_WCK(w.six_states.ensure(nq));
+        SSFM_WCK(w.six_it.ensure(nq));
         SSFM_WCK(w.active0.ensure(nq));
         SSFM_WCK(w.active1.ensure(nq));
         SSFM_WCK(w.navail.ensure(nq));
@@ -307,8 +319,16 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         SSFM_WCK(w.pk_id.ensure((size_t)nq * R * kSixMaxModels));
         SSFM_WCK(w.pk_count.ensure(nq));
         SSFM_WCK(cudaMemsetAsync(w.pk_count.p, 0, sizeof(int) * nq, w.stream));
-        k_sixpt_init<<<(nq + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, q0, nq, w.six_states.p, w.active0.p, w.navail.p,
-                                                             first_cap, w.counts.p);
+        if (six_lo) {
+          k_sixpt_lo_init<<<(nq + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, q0, nq, w.six_lo_states.p, w.mt.p, w.active0.p,
+                                                                  w.navail.p, first_cap, w.counts.p, w.six_it.p);
+          k_sixpt_lo_trivial<<<(nq + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, q0, nq, w.six_lo_states.p, h->results.p + q0,
+                                                                     h->flags.p);
+          launches += 1;
+        } else {
+          k_sixpt_init<<<(nq + 127) / 128, 128, 0, w.stream>>>(P, h->offsets.p, q0, nq, w.six_states.p, w.active0.p, w.navail.p,
+                                                               first_cap, w.counts.p, w.six_it.p);
+        }
         launches += 1;
         int count = nq;
         int* act = w.active0.p;
@@ -319,7 +339,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
           const int cap = round == 0 ? first_cap : round_cap;
           SSFM_WCK(cudaEventRecord(evA, w.stream));
           dim3 gs(count, (cap + kSixSamplesPerBlock - 1) / kSixSamplesPerBlock);
-          k_sixpt_sample_solve<<<gs, kSixSolveThreads, kSixSolveSmem, w.stream>>>(P, h->d_rays, h->offsets.p, q0, act, w.navail.p, w.six_states.p, R,
+          k_sixpt_sample_solve<<<gs, kSixSolveThreads, kSixSolveSmem, w.stream>>>(P, h->d_rays, h->offsets.p, q0, act, w.navail.p, w.six_it.p, R,
                                                         w.models.p, w.six_nm.p, w.pk_G.p, w.pk_id.p, w.pk_count.p, w.s32m.p,
                                                         w.six_M.p);
           SSFM_WCK(cudaGetLastError());
@@ -338,9 +358,37 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
           A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = q0; A.list = act; A.nlist = count; A.navail = w.navail.p;
           A.states = w.six_states.p; A.R = R; A.models = w.models.p; A.nmodels = w.six_nm.p; A.s32m = w.s32m.p;
           A.flags = h->flags.p; A.results = h->results.p + q0; A.next_active = act_next; A.next_count = w.counts.p + 1;
-          A.next_cap = round_cap; A.pk_count = w.pk_count.p; A.counters = w.counters.p;
-          k_sixpt_chain<<<(count + kSixChainWarps - 1) / kSixChainWarps, kSixChainWarps * 32, 0, w.stream>>>(P, A);
-          SSFM_WCK(cudaGetLastError());
+          A.next_cap = round_cap; A.pk_count = w.pk_count.p; A.counters = w.counters.p; A.round_it = w.six_it.p;
+          A.lo_states = w.six_lo_states.p; A.parked = w.parked0.p; A.parked_count = w.counts.p + 2;
+          A.list_a = w.list_a.p; A.list_b = w.list_b.p; A.list_base = c0; A.mt = w.mt.p;
+          if (!six_lo) {
+            k_sixpt_chain<<<(count + kSixChainWarps - 1) / kSixChainWarps, kSixChainWarps * 32, 0, w.stream>>>(P, A);
+            SSFM_WCK(cudaGetLastError());
+            launches += 3;
+          } else {
+            // waves: walk -> (parked pairs) LocalOptimization -> walk the parked pairs on -> ... until nobody is parked
+            int nlist = count;
+            launches += 2;
+            for (;;) {
+              SSFM_WCK(cudaMemsetAsync(w.counts.p + 2, 0, sizeof(int), w.stream));
+              A.nlist = nlist;
+              k_sixpt_chain_lo<<<(nlist + kSixChainWarps - 1) / kSixChainWarps, kSixChainWarps * 32, 0, w.stream>>>(P, A);
+              SSFM_WCK(cudaGetLastError());
+              SSFM_WCK(cudaMemcpyAsync(w.h_count + 1, w.counts.p + 2, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
+              SSFM_WCK(cudaStreamSynchronize(w.stream));
+              const int nparked = w.h_count[1];
+              launches += 1;
+              if (nparked == 0) break;
+              k_sixpt_lo<<<(nparked + 63) / 64, 64, 0, w.stream>>>(P, A, nparked);
+              SSFM_WCK(cudaGetLastError());
+              launches += 1;
+              w.refit_waves += 1;
+              // the next walk reads this wave's parked list while it appends the next one: hand it a copy
+              SSFM_WCK(cudaMemcpyAsync(w.parked1.p, w.parked0.p, sizeof(int) * nparked, cudaMemcpyDeviceToDevice, w.stream));
+              A.list = w.parked1.p;
+              nlist = nparked;
+            }
+          }
           SSFM_WCK(cudaEventRecord(evD, w.stream));
           SSFM_WCK(cudaMemcpyAsync(w.h_count, w.counts.p + 1, sizeof(int), cudaMemcpyDeviceToHost, w.stream));
           SSFM_WCK(cudaStreamSynchronize(w.stream));
@@ -352,7 +400,6 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
           w.score_ms += t2;
           w.chain_ms += t3;
           w.score_launches += 1;
-          launches += 3;
           count = w.h_count[0];
           std::swap(act, act_next);
           ++round;

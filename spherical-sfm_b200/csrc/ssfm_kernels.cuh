@@ -202,15 +202,37 @@ __global__ void k_init_pairs(Params P, const long long* __restrict__ offsets, in
 #ifndef SSFM_SOLVE_MINBLOCKS
 #define SSFM_SOLVE_MINBLOCKS 4
 #endif
+#ifndef SSFM_SOLVE_THREADS
+#define SSFM_SOLVE_THREADS 64
+#endif
+#ifndef SSFM_SOLVE_SYNC
+#define SSFM_SOLVE_SYNC 0  // 1: block barriers between the solver's stages (action-matrix solver only)
+#endif
+constexpr int kSolveThreads = SSFM_SOLVE_THREADS;
+struct BlockStageSync {
+  __host__ __device__ void operator()() const {
+#if defined(__CUDA_ARCH__)
+    __syncthreads();
+#endif
+  }
+};
 template <int KIND>
-__global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Params P, const double* __restrict__ rays,
+__global__ void __launch_bounds__(kSolveThreads, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Params P, const double* __restrict__ rays,
                                                      const long long* __restrict__ offsets, int pair0,
                                                      const int* __restrict__ active, const int* __restrict__ navail,
                                                      const PairState* __restrict__ states, int R,
                                                      double* __restrict__ models) {
   const int a = active[blockIdx.x];
-  const int j = blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= navail[a]) return;
+  const int na = navail[a];
+  int j = blockIdx.y * blockDim.x + threadIdx.x;
+  constexpr bool kSync = SSFM_SOLVE_SYNC != 0 && KIND == 0;
+  if (kSync) {
+    if ((int)(blockIdx.y * blockDim.x) >= na) return;  // the whole block is past the look-ahead (uniform)
+  } else if (j >= na) {
+    return;
+  }
+  const bool valid = j < na;
+  if (!valid) j = na - 1;  // barrier variant: surplus threads solve the last slot again and store nothing
   const int pair = pair0 + a;
   const long long off = offsets[pair];
   const int n = (int)(offsets[pair + 1] - off);
@@ -228,7 +250,11 @@ __global__ void __launch_bounds__(64, SSFM_SOLVE_MINBLOCKS) k_sample_solve(Param
     c[s][0] = x0.x; c[s][1] = x0.y; c[s][2] = x1.x; c[s][3] = x1.y; c[s][4] = x2.x; c[s][5] = x2.y;
   }
   double m[4][6];
-  solve_minimal<KIND>(c[0], c[0] + 3, c[1], c[1] + 3, c[2], c[2] + 3, m, P.skip_complex != 0);
+  if (kSync)
+    solve_minimal<KIND, BlockStageSync>(c[0], c[0] + 3, c[1], c[1] + 3, c[2], c[2] + 3, m, P.skip_complex != 0);
+  else
+    solve_minimal<KIND>(c[0], c[0] + 3, c[1], c[1] + 3, c[2], c[2] + 3, m, P.skip_complex != 0);
+  if (!valid) return;
   double* dst = models + (size_t)a * 24 * R + j;
 #pragma unroll
   for (int k = 0; k < 4; ++k)

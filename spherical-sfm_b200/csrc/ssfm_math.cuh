@@ -831,9 +831,14 @@ SSFM_HD void roots_action_matrix(const double (&G)[6][4], Cplx* xs, Cplx* ys) {
 // -- upstream's own commented-out filter (src/spherical_solvers.cpp:294).  Otherwise they are the canonical
 // representative (model_from_b): the reference's Re(eigenvector) has a phase fixed by rounding noise in Eigen's QR
 // sweeps, which no second implementation can reproduce.
-template <int KIND>
+// `stage()` is called between the solver's stages: a no-op by default; the batched kernel passes a block barrier so that all
+// warps of a CTA run the same stage at the same time and share its instructions in the instruction cache.
+struct NoStageSync {
+  SSFM_HD void operator()() const {}
+};
+template <int KIND, class StageSync = NoStageSync>
 SSFM_HD_NOINLINE int solve_minimal(const double* u0, const double* v0, const double* u1, const double* v1, const double* u2,
-                          const double* v2, double (&models)[4][6], bool skip_complex = false) {
+                          const double* v2, double (&models)[4][6], bool skip_complex = false, StageSync stage = StageSync()) {
   double m[6][3];
   {
     double a[6];
@@ -849,18 +854,22 @@ SSFM_HD_NOINLINE int solve_minimal(const double* u0, const double* v0, const dou
   }
   double B[6][3];
   nullspace_colpiv<3>(m, B);
+  stage();
   double C[6][10], G[6][4];
   build_constraints<KIND>(B, C);
+  stage();
   const double nanv = nan("");
   if (KIND == 0) {
     const bool ok = eliminate_G<2>(C, G);
+    stage();
+    Cplx xs[4], ys[4];
+    if (ok) roots_action_matrix(G, xs, ys);
+    stage();
     if (!ok) {
       for (int k = 0; k < 4; ++k)
         for (int i = 0; i < 6; ++i) models[k][i] = nanv;
       return 4;
     }
-    Cplx xs[4], ys[4];
-    roots_action_matrix(G, xs, ys);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       model_from_b(B, xs[k], ys[k], Cplx{1.0, 0.0}, models[k]);

@@ -16,6 +16,7 @@
 #include "ssfm_kernels.cuh"
 #include "ssfm_sixpt.cuh"
 #include "ssfm_sixpt_coop.cuh"
+#include "ssfm_sixpt_lo.cuh"
 
 namespace ssfm {
 
@@ -36,9 +37,10 @@ constexpr int kSixRecord = 16;                     // doubles per stored model: 
 constexpr float kSixCandMargin = 5e-3f;            // FP32 pre-filter slack (pixel-unit rays: larger dynamic range)
 
 __global__ void k_sixpt_init(Params P, const long long* __restrict__ offsets, int pair0, int npairs, SixState* states,
-                             int* active, int* navail, int first_cap, int* count) {
+                             int* active, int* navail, int first_cap, int* count, uint32_t* round_it) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= npairs) return;
+  round_it[a] = 0;
   const int pair = pair0 + a;
   const int n = (int)(offsets[pair + 1] - offsets[pair]);
   SixState st;
@@ -74,7 +76,7 @@ constexpr size_t kSixSolveSmem = (size_t)kSixSamplesPerBlock * sixc::kScratch * 
 #endif
 __global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
     k_sixpt_sample_solve(Params P, const double* __restrict__ rays, const long long* __restrict__ offsets, int pair0,
-                         const int* __restrict__ active, const int* __restrict__ navail, const SixState* __restrict__ states,
+                         const int* __restrict__ active, const int* __restrict__ navail, const uint32_t* __restrict__ round_it,
                          int R, double* __restrict__ models, int* __restrict__ nmodels, float* __restrict__ pk_G,
                          int* __restrict__ pk_id, int* __restrict__ pk_count, float* __restrict__ s32m, double* __restrict__ scratch_M) {
   extern __shared__ double six_smem[];
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(kSixSolveThreads, SSFM_SIXPT_MINBLOCKS)
   double c[6][6];
   if (valid && gl == 0) {
     const int n = (int)(offsets[pair + 1] - off);
-    const uint32_t it = states[a].it + (uint32_t)j;
+    const uint32_t it = round_it[a] + (uint32_t)j;  // iteration number of look-ahead slot j
     int idx[6];
     philox_sample<6>(P.seed, P.first_pair_id + (uint32_t)pair, it, 6, n, idx);
     for (int s = 0; s < 6; ++s) {
@@ -216,6 +218,15 @@ struct SixChainArgs {
   int next_cap;
   int* pk_count;
   unsigned long long* counters;
+  uint32_t* round_it;  // iteration number of look-ahead slot 0 of the pair's next round
+  // LO-MSAC variant only
+  SixLoState* lo_states;
+  int* parked;        // pairs waiting for k_sixpt_lo
+  int* parked_count;
+  int* list_a;        // CSR-aligned scratch lists (list_base = first correspondence of the pass)
+  int* list_b;
+  long long list_base;
+  uint32_t* mt;       // 625 words per pair
 };
 
 constexpr int kSixChainWarps = 4;
@@ -297,6 +308,7 @@ __global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain(Params P, S
   if (cx.lane() == 0) {
     A.states[a] = st;
     A.pk_count[a] = 0;
+    A.round_it[a] = st.it;
     if (!st.done) {
       A.navail[a] = lookahead(st.max_iters - st.it, A.next_cap);
       const int pos = atomicAdd(A.next_count, 1);
@@ -306,6 +318,183 @@ __global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain(Params P, S
     }
     atomicAdd(&A.counters[1], (unsigned long long)exact);
   }
+}
+
+// ---- LO-MSAC around the six-point estimator (ssfm_sixpt_lo.cuh) ----------------------------------------------
+
+__global__ void k_sixpt_lo_init(Params P, const long long* __restrict__ offsets, int pair0, int npairs, SixLoState* states,
+                                uint32_t* mt, int* active, int* navail, int first_cap, int* count, uint32_t* round_it) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= npairs) return;
+  const int pair = pair0 + a;
+  const int n = (int)(offsets[pair + 1] - offsets[pair]);
+  SixLoState st;
+  six_lo_init(P, n, st);
+  if (st.max_iters == 0) st.phase = st.done ? SIX_PH_NONE : SIX_PH_FINAL;  // empty loop: straight to :243
+  states[a] = st;
+  round_it[a] = 0;
+  mt19937_seed(mt + (size_t)a * 625, P.seed);  // rng.seed(options.random_seed_), ransac.h:143-144
+  navail[a] = st.done ? 0 : lookahead(st.max_iters, first_cap);
+  active[a] = a;
+  if (a == 0) *count = npairs;
+}
+
+// One warp per listed pair: walks the round's look-ahead slots from st.resume_j exactly like EstimateModel's loop
+// (ransac.h:160-241) until the round is used up, the loop ends, or a LocalOptimization is due -- then the pair is
+// appended to `parked` for k_sixpt_lo and the walk resumes (same slot or the next one) in the following wave.
+__global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain_lo(Params P, SixChainArgs A) {
+  const int wid = blockIdx.x * kSixChainWarps + (threadIdx.x >> 5);
+  if (wid >= A.nlist) return;
+  WarpCtx cx{(int)(threadIdx.x & 31)};
+  const int a = A.list[wid];
+  SixLoState st = A.lo_states[a];
+  if (st.done) return;  // finished by k_sixpt_lo in the previous wave
+  const int pair = A.pair0 + a;
+  const long long off = A.offsets[pair];
+  const int n = (int)(A.offsets[pair + 1] - off);
+  PairView pv{A.rays + 6 * off, n, A.rays + 6 * off};
+  const int na = A.navail[a];
+  const double* mbase = A.models + (size_t)a * A.R * kSixMaxModels * kSixRecord;
+  const float* sbase = A.s32m + (size_t)a * A.R * kSixSlotModels;
+  long long exact = 0;
+  bool park = st.phase == SIX_PH_FINAL;  // (max_num_iterations == 0)
+  int j = st.resume_j;
+  for (; !park && j < na; ++j) {
+    if (st.phase == SIX_PH_RESUME_BODY) {
+      st.phase = SIX_PH_NONE;  // back from the LO at lo_starting_iterations_: the iteration's body continues
+    } else {
+      if (st.it >= st.max_iters) break;
+      if (st.it == P.lo_start && st.best_min_score < kDblMax && !st.lo_start_done) {  // :166-177
+        st.phase = SIX_PH_LO_START;
+        st.resume_j = j;
+        park = true;
+        break;
+      }
+    }
+    const int nm = A.nmodels[(size_t)a * A.R + j];
+    if (nm <= 0) { st.it += 1; continue; }  // :184
+    st.evals += (long long)nm * n;
+    const bool force = st.it == P.lo_start;  // :194, the LO branch is entered whatever the score
+    const float mine = cx.lane() < nm ? sbase[j * kSixSlotModels + cx.lane()] : INFINITY;
+    const float smin = cx.min_f(mine);
+    const bool nan_any = __any_sync(0xffffffffu, mine != mine);
+    const bool cand = nan_any || smin <= st.runmin32 * (1.0f + kSixCandMargin);
+    if (!cand && !force) { st.it += 1; continue; }
+    double local_best = kDblMax;
+    int local_id = 0, local_cnt = 0;
+    if (cand) {
+      if (smin < st.runmin32) st.runmin32 = smin;
+      for (int k = 0; k < nm; ++k) {
+        const float sk = __shfl_sync(0xffffffffu, mine, k);
+        if (!(sk != sk) && !(sk <= smin * (1.0f + kSixCandMargin))) continue;
+        const double* rec = mbase + ((size_t)j * kSixMaxModels + k) * kSixRecord;
+        double G[9];
+        for (int q = 0; q < 9; ++q) G[q] = rec[q];
+        int cnt = 0;
+        const double s = msac_score_exact(cx, G, pv.rays, pv.n, P.thr2, &cnt, &exact);
+        if (s < local_best) { local_best = s; local_id = k; local_cnt = cnt; }  // GetBestEstimatedModelId, :278-293
+      }
+    }
+    const bool better = local_best < st.best_min_score;  // kBestMinModel, :196
+    if (better) {
+      st.best_min_score = local_best;
+      const double* rec = mbase + ((size_t)j * kSixMaxModels + local_id) * kSixRecord;
+      for (int q = 0; q < 9; ++q) st.bestmin.G[q] = rec[q];
+      for (int q = 0; q < 3; ++q) { st.bestmin.m.t[q] = rec[9 + q]; st.bestmin.m.r[q] = rec[12 + q]; }
+      st.bestmin.m.f = rec[15];
+      st.bestmin.score = local_best;
+      st.bestmin.cnt = local_cnt;
+      six_keep_better(local_best, local_cnt, st.bestmin.m, st.bestmin.G, st.best);  // :204-206
+    }
+    const bool run_lo = st.it >= P.lo_start && st.best_min_score < kDblMax;  // :209-211
+    st.it += 1;
+    if (!better && !force) continue;   // :193-194
+    if (!better && !run_lo) continue;  // :213
+    if (run_lo) {  // :219-227 and the refresh after it happen in k_sixpt_lo
+      st.phase = SIX_PH_LO_BEST;
+      st.resume_j = j + 1;
+      park = true;
+      break;
+    }
+    six_refresh(P, n, st, true);  // :231-238
+  }
+  if (!park && st.it >= st.max_iters) {  // the loop has ended: :243-275 run in k_sixpt_lo
+    st.phase = SIX_PH_FINAL;
+    park = true;
+  }
+  if (cx.lane() == 0) {
+    if (park) {
+      const int pos = atomicAdd(A.parked_count, 1);
+      A.parked[pos] = a;
+    } else {  // look-ahead used up: next round
+      st.resume_j = 0;
+      A.pk_count[a] = 0;
+      A.round_it[a] = st.it;
+      A.navail[a] = lookahead(st.max_iters - st.it, A.next_cap);
+      const int pos = atomicAdd(A.next_count, 1);
+      A.next_active[pos] = a;
+    }
+    A.lo_states[a] = st;
+    atomicAdd(&A.counters[1], (unsigned long long)exact);
+  }
+}
+
+// One THREAD per parked pair: the LocalOptimization (or the loop's epilogue) the pair is waiting for, start to finish.
+__global__ void __launch_bounds__(64) k_sixpt_lo(Params P, SixChainArgs A, int nparked) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nparked) return;
+  const int a = A.parked[q];
+  const int pair = A.pair0 + a;
+  const long long off = A.offsets[pair];
+  const int n = (int)(A.offsets[pair + 1] - off);
+  PairView pv{A.rays + 6 * off, n, A.rays + 6 * off};
+  SixScratch sc{A.list_a + (off - A.list_base), A.list_b + (off - A.list_base), A.mt + (size_t)a * 625};
+  SixLoState st = A.lo_states[a];
+  SerialCtx cx;
+  long long exact = 0;
+  const bool finished = six_lo_phase(cx, P, pv, sc, st, A.flags ? A.flags + off : (unsigned char*)0, &exact);
+  if (finished) {
+    const bool have = st.best.score < kDblMax;
+    SsfmPairResult& o = A.results[a];
+    for (int i = 0; i < 9; ++i) o.E[i] = st.best.G[i];
+    for (int i = 0; i < 3; ++i) { o.r[i] = st.best.m.r[i]; o.t[i] = st.best.m.t[i]; }
+    o.best_model_score = st.best.score;
+    o.inlier_ratio = st.inlier_ratio;
+    o.num_iterations = st.it;
+    o.best_num_inliers = st.best_num_inliers;
+    o.number_lo_iterations = st.num_lo;
+    o.status = have ? SSFM_PAIR_OK : SSFM_PAIR_NO_MODEL;
+    o.evals = st.evals;
+    o.focal = st.best.m.f;
+    A.navail[a] = 0;
+  }
+  A.lo_states[a] = st;
+  atomicAdd(&A.counters[1], (unsigned long long)exact);
+}
+
+// Pairs that never enter the loop (fewer than 6 correspondences, or below the caller's min_num_points).
+__global__ void k_sixpt_lo_trivial(Params P, const long long* __restrict__ offsets, int pair0, int npairs, const SixLoState* states,
+                                   SsfmPairResult* results, unsigned char* flags) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= npairs) return;
+  const int pair = pair0 + a;
+  const long long off = offsets[pair];
+  const int n = (int)(offsets[pair + 1] - off);
+  if (!(n < 6 || n < P.min_points)) return;
+  SsfmPairResult& o = results[a];
+  for (int i = 0; i < 9; ++i) o.E[i] = 0.0;
+  for (int i = 0; i < 3; ++i) { o.r[i] = 0.0; o.t[i] = 0.0; }
+  o.best_model_score = kDblMax;
+  o.inlier_ratio = 0.0;
+  o.num_iterations = 0;
+  o.best_num_inliers = 0;
+  o.number_lo_iterations = 0;
+  o.status = n < 6 ? SSFM_PAIR_TOO_FEW_POINTS : SSFM_PAIR_SKIPPED;
+  o.evals = 0;
+  o.focal = 0.0;
+  if (flags)
+    for (int i = 0; i < n; ++i) flags[off + i] = 0;
+  (void)states;
 }
 
 // Hook: the minimal solver on explicit samples (6 indices each) -- the same warp code as the batched kernel.

@@ -10,6 +10,7 @@
 #include "../../spherical-sfm_b200/csrc/ssfm_chain.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_sixpt.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_sixpt_coop.cuh"
+#include "../../spherical-sfm_b200/csrc/ssfm_sixpt_lo.cuh"
 #include "../../spherical-sfm_b200/csrc/ssfm_triangulate.cuh"
 
 using namespace ssfm;
@@ -257,6 +258,87 @@ int hs_sixpt_least_squares(const double* rays, const int* sample, int n, double*
   costs2[0] = s.initial_cost;
   costs2[1] = s.final_cost;
   return s.iterations;
+}
+
+// LO-MSAC around the six-point estimator on the host (tests only): the walk of k_sixpt_chain_lo, serially and without the
+// FP32 pre-filter (every model of every iteration is scored in float64), around the very functions k_sixpt_lo runs
+// (six_lo_phase / six_local_optimization, csrc/ssfm_sixpt_lo.cuh).  out7 = t, r, f.
+int hs_sixpt_lo_msac(const double* rays, int n, const HsParams* hp, uint32_t pair_id, int focal_scoring, double* out7,
+                     double* best_score, uint32_t* iterations, int* num_lo, unsigned char* flags) {
+  Params P{};
+  P.min_points = 0;
+  P.min_iters = hp->min_iters; P.max_iters = hp->max_iters;
+  P.eta = 1.0 - hp->success_probability; P.thr2 = hp->thr2; P.seed = hp->seed;
+  P.num_lo_steps = hp->num_lo_steps; P.thr_mult = hp->thr_mult; P.num_lsq_iters = hp->num_lsq_iters;
+  P.min_sample_mult = hp->min_sample_mult; P.non_min_mult = hp->non_min_mult; P.lo_start = hp->lo_start;
+  P.final_lsq = hp->final_lsq; P.first_pair_id = 0; P.sixpt_focal_scoring = focal_scoring;
+  SerialCtx cx;
+  PairView pv{rays, n, rays};
+  std::vector<int> la(n + 16), lb(n + 16);
+  std::vector<uint32_t> mt(625);
+  mt19937_seed(mt.data(), P.seed);
+  SixScratch sc{la.data(), lb.data(), mt.data()};
+  SixLoState st;
+  six_lo_init(P, n, st);
+  long long ev = 0;
+  if (!st.done) {
+    for (;;) {
+      if (st.phase == SIX_PH_RESUME_BODY) {
+        st.phase = SIX_PH_NONE;
+      } else {
+        if (st.it >= st.max_iters) break;
+        if (st.it == P.lo_start && st.best_min_score < kDblMax && !st.lo_start_done) {
+          st.phase = SIX_PH_LO_START;
+          six_lo_phase(cx, P, pv, sc, st, (unsigned char*)0, &ev);
+          continue;
+        }
+      }
+      int idx[6];
+      philox_sample<6>(P.seed, pair_id, st.it, 6, n, idx);
+      double c[6][6];
+      for (int i = 0; i < 6; ++i)
+        for (int q = 0; q < 6; ++q) c[i][q] = rays[6 * (size_t)idx[i] + q];
+      SixPointModel sol[kSixMaxModels];
+      const int nm = sixc::solve_sixpt_focal_staged(c, sol);
+      if (nm <= 0) { st.it += 1; continue; }
+      double local_best = kDblMax;
+      int local_id = 0, local_cnt = 0;
+      double Gs[kSixMaxModels][9];
+      for (int k = 0; k < nm; ++k) {
+        sixpt_scoring_matrix(sol[k], focal_scoring, Gs[k]);
+        int cnt = 0;
+        const double s = msac_score_exact(cx, Gs[k], pv.stream, n, P.thr2, &cnt, &ev);
+        if (s < local_best) { local_best = s; local_id = k; local_cnt = cnt; }
+      }
+      const bool better = local_best < st.best_min_score;
+      if (better) {
+        st.best_min_score = local_best;
+        st.bestmin.m = sol[local_id];
+        for (int q = 0; q < 9; ++q) st.bestmin.G[q] = Gs[local_id][q];
+        st.bestmin.score = local_best;
+        st.bestmin.cnt = local_cnt;
+        six_keep_better(local_best, local_cnt, st.bestmin.m, st.bestmin.G, st.best);
+      }
+      const bool enter = better || st.it == P.lo_start;  // ransac.h:193-194
+      const bool run_lo = st.it >= P.lo_start && st.best_min_score < kDblMax;
+      st.it += 1;
+      if (!enter || (!better && !run_lo)) continue;
+      if (run_lo) {
+        st.phase = SIX_PH_LO_BEST;
+        six_lo_phase(cx, P, pv, sc, st, (unsigned char*)0, &ev);
+        continue;
+      }
+      six_refresh(P, n, st, true);
+    }
+    st.phase = SIX_PH_FINAL;
+    six_lo_phase(cx, P, pv, sc, st, flags, &ev);
+  }
+  for (int d = 0; d < 3; ++d) { out7[d] = st.best.m.t[d]; out7[3 + d] = st.best.m.r[d]; }
+  out7[6] = st.best.m.f;
+  *best_score = st.best.score;
+  *iterations = st.it;
+  *num_lo = st.num_lo;
+  return st.best_num_inliers;
 }
 
 }  // extern "C"

@@ -72,6 +72,62 @@ def _host_ls(shim_lib, rays, sample, model):
     return m, it, costs
 
 
+def _host_lo_msac(shim, rays, kw, focal_scoring, thr2, seed, pair_id=0):
+    from conftest import HsParams
+    rays = np.ascontiguousarray(rays, np.float64)
+    n = len(rays)
+    hp = HsParams(min_iters=kw.get("min_num_iterations", 100), max_iters=kw.get("max_num_iterations", 10000),
+                  success_probability=0.9999, thr2=thr2, seed=seed, num_lo_steps=kw.get("num_lo_steps", 10), thr_mult=2 ** 0.5,
+                  num_lsq_iters=kw.get("num_lsq_iterations", 4), min_sample_mult=7, non_min_mult=3,
+                  lo_start=kw.get("lo_starting_iterations", 50), final_lsq=kw.get("final_least_squares", 0))
+    out7, flags = np.zeros(7), np.zeros(max(n, 1), np.uint8)
+    sc, it, nlo = C.c_double(), C.c_uint32(), C.c_int()
+    dp = C.POINTER(C.c_double)
+    shim.lib.hs_sixpt_lo_msac.restype = C.c_int
+    ninl = shim.lib.hs_sixpt_lo_msac(rays.ctypes.data_as(dp), n, C.byref(hp), C.c_uint32(pair_id), focal_scoring,
+                                     out7.ctypes.data_as(dp), C.byref(sc), C.byref(it), C.byref(nlo),
+                                     flags.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return dict(model=out7, score=sc.value, num_iterations=it.value, number_lo_iterations=nlo.value, best_num_inliers=ninl,
+                flags=flags[:n])
+
+
+def _oracle_lo_msac(sampler, rays, kw, focal_scoring, thr2, seed):
+    return X.lo_msac(rays, sampler, thr2, seed=seed, min_iters=kw.get("min_num_iterations", 100),
+                     max_iters=kw.get("max_num_iterations", 10000), num_lo_steps=kw.get("num_lo_steps", 10),
+                     num_lsq_iterations=kw.get("num_lsq_iterations", 4), lo_starting_iterations=kw.get("lo_starting_iterations", 50),
+                     final_least_squares=bool(kw.get("final_least_squares", 0)), focal_scoring=bool(focal_scoring))
+
+
+LO_CASES = [  # (seed, N, outliers, options)
+    (1, 300, 0.4, dict(num_lo_steps=2, num_lsq_iterations=2, lo_starting_iterations=20, final_least_squares=1,
+                       min_num_iterations=50, max_num_iterations=400)),
+    (2, 300, 0.3, dict()),  # RansacLib defaults: 10 LO steps x 4 LSQ iterations, LO from iteration 50
+    (3, 150, 0.2, dict(num_lo_steps=1, num_lsq_iterations=2, lo_starting_iterations=200, min_num_iterations=60,
+                       max_num_iterations=60, final_least_squares=1)),  # the loop ends before lo_start: LO after the loop (:246-257)
+]
+
+
+def test_lo_msac_product_on_host_matches_oracle(shim, S):
+    """LocallyOptimizedMSAC around SixPointEstimator (NonMinimalSolver / LeastSquares, six_point_estimator.cpp:121-192):
+    csrc/ssfm_sixpt_lo.cuh compiled for the host -- the functions k_sixpt_lo runs per parked pair -- against the numpy
+    restatement of ransac.h: same iteration and LO counts, same inlier set, same model."""
+    for seed, N, outl, kw in LO_CASES:
+        rays, offs, f, R, t = S.problems.make_sixpt_batch(seed, 1, N, outlier_frac=outl)
+        got = _host_lo_msac(shim, rays, kw, 1, 4.0, 7)
+
+        def sampler(i):
+            idx = np.zeros(6, np.int32)
+            shim.lib.hs_sample(C.c_uint32(7), C.c_uint32(0), C.c_uint32(i), 6, N, idx.ctypes.data_as(C.POINTER(C.c_int)))
+            return idx
+        st = _oracle_lo_msac(sampler, rays, kw, 1, 4.0, 7)
+        assert got["num_iterations"] == st["num_iterations"], seed
+        assert got["number_lo_iterations"] == st["number_lo_iterations"] and st["number_lo_iterations"] >= 1, seed
+        assert got["best_num_inliers"] == st["best_num_inliers"], seed
+        assert np.nonzero(got["flags"])[0].tolist() == st["inliers"].tolist(), seed
+        assert _model_diff(got["model"], st["model"]) < 1e-7, seed
+        assert abs(got["score"] - st["best_model_score"]) <= 1e-8 * st["best_model_score"], seed
+
+
 def _refit_cases(n_cases, seed):
     rng = np.random.default_rng(seed)
     out = []
@@ -212,6 +268,52 @@ def test_six_point_edge_cases_and_driver_check(S, engine):
     assert list(res["status"][:2]) == [1, 1]
     assert res["status"][3] == 0 and res["best_num_inliers"][3] >= 30 and 350 < res["focal"][3] < 1400
     assert res["num_iterations"][2] == 10000 or res["status"][2] == 0  # six points: every sample is the same set
-    opt.driver = S.DRIVER_LO_MSAC
+    opt.driver = S.DRIVER_LO_MSAC  # the same edge cases under LO-MSAC
+    res2, flags2 = engine.estimate_pairs(rays, offsets, opt)
+    assert list(res2["status"][:2]) == [1, 1]
+    assert res2["status"][3] == 0 and res2["best_num_inliers"][3] >= 30 and 350 < res2["focal"][3] < 1400
+    opt.driver = S.DRIVER_MSAC_FIXED
     with pytest.raises(S.SsfmError):
         engine.estimate_pairs(rays, offsets, opt)
+
+
+@pytest.mark.gpu
+def test_six_point_lo_msac_batched_matches_oracle(S, engine, orc):
+    """LO-MSAC around the six-point estimator, batched on the device (k_sixpt_chain_lo walks, k_sixpt_lo runs the parked
+    LocalOptimizations): per pair the same iteration count, LO count, inlier mask and model as the numpy restatement of
+    ransac.h:127-276 with SixPointEstimator::NonMinimalSolver / LeastSquares."""
+    for seed, N, outl, kw in LO_CASES:
+        P = 3
+        rays, offsets, f, R, t = S.problems.make_sixpt_batch(seed, P, N, outlier_frac=outl)
+        opt = S.default_options(squared_inlier_threshold=4.0, driver=S.DRIVER_LO_MSAC, solver=S.SOLVER_SIXPT_FOCAL,
+                                sixpt_focal_scoring=1, random_seed=7, first_pair_id=5, **kw)
+        res, flags = engine.estimate_pairs(rays, offsets, opt)
+        for p in range(P if not kw else 2):
+            pr = rays[offsets[p]:offsets[p + 1]]
+            st = _oracle_lo_msac(lambda it: orc.philox_sample(7, 5 + p, it, 6, N), pr, kw, 1, 4.0, 7)
+            assert int(res["status"][p]) == st["status"] == 0
+            assert int(res["num_iterations"][p]) == st["num_iterations"], (seed, p)
+            assert int(res["number_lo_iterations"][p]) == st["number_lo_iterations"], (seed, p)
+            assert int(res["best_num_inliers"][p]) == st["best_num_inliers"], (seed, p)
+            assert np.nonzero(flags[offsets[p]:offsets[p + 1]])[0].tolist() == st["inliers"].tolist(), (seed, p)
+            tt, r, ff = st["model"]
+            assert max(np.abs(res["t"][p] - tt).max(), np.abs(res["r"][p] - r).max(), abs(res["focal"][p] - ff) / ff) < 1e-7
+            assert abs(res["best_model_score"][p] - st["best_model_score"]) <= 1e-8 * st["best_model_score"]
+
+
+@pytest.mark.gpu
+def test_six_point_lo_msac_improves_on_vanilla_at_scale(S, engine):
+    """2 500 pairs (more than one sub-pass of 2 048): every pair finishes, LO-MSAC never ends with a worse MSAC cost than
+    the VanillaMSAC run on the same samples would at the same iteration budget, and its refits pull the focal in."""
+    P, N = 2500, 400
+    rays, offsets, f, R, t = S.problems.make_sixpt_batch(4, P, N, outlier_frac=0.4)
+    kw = dict(squared_inlier_threshold=4.0, solver=S.SOLVER_SIXPT_FOCAL, sixpt_focal_scoring=1, random_seed=3,
+              min_num_iterations=200, max_num_iterations=200)
+    lo, _ = engine.estimate_pairs(rays, offsets, S.default_options(driver=S.DRIVER_LO_MSAC, num_lo_steps=2, num_lsq_iterations=2, **kw))
+    va, _ = engine.estimate_pairs(rays, offsets, S.default_options(driver=S.DRIVER_VANILLA_MSAC, **kw))
+    assert (lo["status"] == 0).all() and (va["status"] == 0).all()
+    assert (lo["num_iterations"] == 200).all() and (lo["number_lo_iterations"] >= 1).all()
+    assert (lo["best_model_score"] <= va["best_model_score"] * (1 + 1e-12)).all()
+    err_lo = np.abs(lo["focal"] / f - 1)
+    err_va = np.abs(va["focal"] / f - 1)
+    assert np.median(err_lo) < np.median(err_va)
