@@ -677,6 +677,26 @@ def main():
         line["retriangulate"] = {"points": int(len(offs_t) - 1), "observations": int(offs_t[-1]), "ms": ms_t,
                                  "points_per_sec": (len(offs_t) - 1) / (ms_t * 1e-3), "ok_fraction": float((st_t == 0).mean()),
                                  "mean_iterations": float(it_t.mean())}
+        if world == 1 and not args.no_cpu:
+            # the same points through the oracle (triangulation_estimator.cpp + RansacLib restated in C++), all host cores,
+            # bounded sample; ctypes releases the GIL, so a thread pool scales
+            from concurrent.futures import ThreadPoolExecutor
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as O
+            orc_t = O.load()
+            oopt_t = O.default_options(squared_inlier_threshold=4.0, final_least_squares=1)
+            cores_t = os.cpu_count() or 1
+            n_cpu = 30000
+
+            def one(pid):
+                a, b = offs_t[pid], offs_t[pid + 1]
+                orc_t.triangulate(cam_t[oc_t[a:b]], oxy_t[a:b], f_t, oopt_t, pid)
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores_t) as pool:
+                list(pool.map(one, range(n_cpu), chunksize=50))
+            sec_t = time.perf_counter() - t0
+            line["retriangulate"]["cpu"] = {"points_per_sec": n_cpu / sec_t, "cores": cores_t, "kind": "port",
+                                            "sample": "%d points in %.1f s" % (n_cpu, sec_t)}
     except Exception as exc:
         line["retriangulate"] = {"error": str(exc)}
     # Descriptor matching: match_exhaustive over 64 images x 4000 SIFT-like descriptors = 2016 pairs,

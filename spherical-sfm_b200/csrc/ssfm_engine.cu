@@ -379,7 +379,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
               const int nparked = w.h_count[1];
               launches += 1;
               if (nparked == 0) break;
-              k_sixpt_lo<<<(nparked + 63) / 64, 64, 0, w.stream>>>(P, A, nparked);
+              k_sixpt_lo<<<(nparked + kSixLoWarps - 1) / kSixLoWarps, kSixLoWarps * 32, 0, w.stream>>>(P, A, nparked);
               SSFM_WCK(cudaGetLastError());
               launches += 1;
               w.refit_waves += 1;

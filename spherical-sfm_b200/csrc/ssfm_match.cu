@@ -55,8 +55,17 @@ constexpr int kRowPad = 256;       // rows of every image are padded to a multip
 constexpr int kGroupBytes = (kKp / 8) * 128;  // one 8-row group: 18 core matrices (8 rows x 16 B) = 2304 bytes
 constexpr int kStages = 3;         // train-tile ring in shared memory
 constexpr int kAccBufs = 2;        // accumulator buffers in TMEM (each: 2 halves x 128 fp32 columns)
-constexpr int kEpiWarps = 8;
-constexpr int kMatchThreads = 32 * (2 + kEpiWarps);  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+#ifndef SSFM_MATCH_COLSPLIT
+#define SSFM_MATCH_COLSPLIT 2
+#endif
+constexpr int kColSplit = SSFM_MATCH_COLSPLIT;  // epilogue threads per query row: each scans kTTile / kColSplit columns of every tile
+constexpr int kEpiWarps = 8 * kColSplit;        // (two epilogue warps per scheduler cannot hide the TMEM-load and ALU latencies)
+constexpr int kMatchThreads = 32 * (2 + kEpiWarps);  // warp 0 producer, warp 1 MMA, the rest epilogue
+constexpr int kEpiChunks = kTTile / 32 / kColSplit;  // 32-column TMEM loads per tile and thread
+static_assert(kColSplit == 1 || kColSplit == 2, "column split");
+#ifndef SSFM_MATCH_DOUBLEBUF
+#define SSFM_MATCH_DOUBLEBUF 1
+#endif
 constexpr uint32_t kQBytes = kQTile / 8 * kGroupBytes;  // 73 728
 constexpr uint32_t kTBytes = kTTile / 8 * kGroupBytes;  // 36 864
 constexpr uint32_t kTmemCols = 512;
@@ -245,7 +254,9 @@ struct MatchSmem {
 };
 constexpr size_t kMatchSmemHeader = 1024;
 static_assert(sizeof(MatchSmem) <= kMatchSmemHeader, "header");
-constexpr size_t kMatchSmemBytes = kMatchSmemHeader + kQBytes + kStages * kTBytes;
+struct MergeSlot { float a0, a1; int i0, i1; };  // top-2 of the upper column half of a query row, handed to its partner thread
+constexpr size_t kMergeBytes = kColSplit > 1 ? 2 * kQTile * sizeof(MergeSlot) : 0;  // double buffered over work items
+constexpr size_t kMatchSmemBytes = kMatchSmemHeader + kQBytes + kStages * kTBytes + kMergeBytes;
 
 // Running two nearest neighbours of one query row.  Everything is kept in the accumulator's domain a = d^2 - |q|^2 (what
 // the tensor core delivers: |t|^2 - 2 q.t, an exact integer), so a clean distance costs one min and the bookkeeping is
@@ -312,6 +323,18 @@ __device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, 
   }
 }
 
+// The two smallest (sqrtf(d^2), train index) pairs of two disjoint column sets = the two smallest of their four candidates:
+// the comparison cv::batchDistance makes, on the floats it makes it on (exact in the near and in the far regime alike).
+__device__ __forceinline__ void top2_insert(Top2& s, float a, int i, float qn) {
+  const float d = sqrtf(a + qn), d0 = sqrtf(s.a0 + qn), d1 = sqrtf(s.a1 + qn);
+  if (d < d0 || (d == d0 && (unsigned)i < (unsigned)s.i0)) {
+    s.a1 = s.a0; s.i1 = s.i0; s.a0 = a; s.i0 = i;
+  } else if (d < d1 || (d == d1 && (unsigned)i < (unsigned)s.i1)) {
+    s.a1 = a; s.i1 = i;
+  }
+}
+
+// 18 warps are allocated as 20 (granularity of four): 65536 / (20 x 32) = 102 -> 96 registers per thread with the column split
 __global__ void __launch_bounds__(kMatchThreads, 1)
 k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ packed_t, const float* __restrict__ norms,
             const long long* __restrict__ prow_off, const int* __restrict__ nrows, const int* __restrict__ pair_images,
@@ -401,12 +424,15 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
     }
   } else {
     // ===== epilogue: one query row per thread =====
-    const int quarter = warp & 3;        // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
-    const int half = (warp - 2) >> 2;    // which M=128 half of the query block
+    const int quarter = warp & 3;               // a warp may only touch TMEM lanes [32 * (warp % 4), +32)
+    const int half = ((warp - 2) >> 2) & 1;     // which M=128 half of the query block
+    const int colpart = (warp - 2) >> 3;        // which kTTile / kColSplit columns of every tile
+    const int col0 = colpart * (kTTile / kColSplit);
     const int row = half * 128 + quarter * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kTTile);
-    uint32_t it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const uint32_t lane_addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * kTTile + col0);
+    MergeSlot* merge = reinterpret_cast<MergeSlot*>(sT + (size_t)kStages * kTBytes);
+    uint32_t it = 0, item = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++item) {
       const int pair = work_pair[w], qb = work_qblock[w];
       const int img0 = pair_images[2 * pair], img1 = pair_images[2 * pair + 1];
       const int n0 = nrows[img0], n1 = nrows[img1];
@@ -423,26 +449,47 @@ k_match_2nn(const __half* __restrict__ packed_q, const __half* __restrict__ pack
         mbar_wait(&sm->tfull[b], (it / kAccBufs) & 1u);
         tc_fence_after();
         const uint32_t taddr = lane_addr + b * (2 * kTTile);
+#if SSFM_MATCH_DOUBLEBUF
         // two register buffers: the next 32 columns are in flight while the current ones are scanned
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
         tmem_wait(va);
 #pragma unroll 1
-        for (int c = 0; c < kTTile / 32; c += 2) {
+        for (int c = 0; c < kEpiChunks; c += 2) {
           tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
-          top2_scan32(st, reinterpret_cast<const float*>(va), t * kTTile + c * 32, qn, far_a);
+          top2_scan32(st, reinterpret_cast<const float*>(va), t * kTTile + col0 + c * 32, qn, far_a);
           tmem_wait(vb);
-          if (c + 2 < kTTile / 32) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
-          top2_scan32(st, reinterpret_cast<const float*>(vb), t * kTTile + (c + 1) * 32, qn, far_a);
-          if (c + 2 < kTTile / 32) tmem_wait(va);
+          if (c + 2 < kEpiChunks) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
+          top2_scan32(st, reinterpret_cast<const float*>(vb), t * kTTile + col0 + (c + 1) * 32, qn, far_a);
+          if (c + 2 < kEpiChunks) tmem_wait(va);
         }
+#else
+        // one register buffer: with four epilogue warps per scheduler the other warps cover the TMEM-load latency
+        uint32_t va[32];
+#pragma unroll 1
+        for (int c = 0; c < kEpiChunks; ++c) {
+          tmem_ld32(taddr + (uint32_t)(c * 32), va);
+          tmem_wait(va);
+          top2_scan32(st, reinterpret_cast<const float*>(va), t * kTTile + col0 + c * 32, qn, far_a);
+        }
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->tempty[b]);
       }
       // Lowe's ratio test in double, as `matches[i][0].distance < ratio * matches[i][1].distance` evaluates it (:246);
       // m01[trainIdx] = queryIdx with later queries overwriting earlier ones == the maximum query index per train index
-      if (live && st.i1 >= 0) {
+      if (kColSplit > 1) {  // the upper column half hands its two candidates to the thread that owns the lower half
+        MergeSlot* slot = merge + (size_t)(item & 1u) * kQTile + row;
+        if (colpart) *slot = MergeSlot{st.a0, st.a1, st.i0, st.i1};
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // epilogue warps only
+        if (colpart == 0) {
+          const MergeSlot o = *slot;
+          top2_insert(st, o.a0, o.i0, qn);
+          top2_insert(st, o.a1, o.i1, qn);
+        }
+      }
+      if (colpart == 0 && live && st.i1 >= 0) {
         const float d0 = sqrtf(st.a0 + qn), d1 = sqrtf(st.a1 + qn);  // exact d^2, IEEE sqrt: the floats cv::BFMatcher returns
         if ((double)d0 < ratio * (double)d1) atomicMax(&owner[owner_off[pair - pair_base] + st.i0], (int)qrow);
       }

@@ -716,8 +716,20 @@ struct SixLmSummary {
   double initial_cost, final_cost;
 };
 
-// rays: the estimator's correspondences (6 doubles each); sample: indices of the residuals.
-SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const double* rays, const int* sample, int n, SixPointModel& model) {
+// One-lane execution context (the interface of SerialCtx / WarpCtx, ssfm_chain.cuh, as far as this file needs it).
+struct SixOneLane {
+  SSFM_HD int lane() const { return 0; }
+  SSFM_HD int width() const { return 1; }
+  SSFM_HD double sum(double x) const { return x; }
+  template <int K>
+  SSFM_HD void sum_vec(double (&v)[K]) const { (void)v; }
+};
+
+// rays: the estimator's correspondences (6 doubles each); sample: indices of the residuals.  With a multi-lane context the
+// residuals (and their contributions to the normal equations) are spread over the lanes and reduced; everything else is
+// computed redundantly by every lane from identical inputs, so control flow stays uniform.
+template <class Ctx>
+SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const Ctx& cx, const double* rays, const int* sample, int n, SixPointModel& model) {
   using namespace sixpt;
   double x[7] = {model.r[0], model.r[1], model.r[2], model.t[0], model.t[1], model.t[2], model.f};
   double H[21], g[6], scale[6], diagonal[6] = {0, 0, 0, 0, 0, 0}, gmax = 0.0;
@@ -743,7 +755,7 @@ SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const double* rays, const int*
     const double S[9] = {1, 1, f, 1, 1, f, f, f, f * f}, dS[9] = {0, 0, 1, 0, 0, 1, 1, 1, 2 * f};
     double F[9];
     for (int q = 0; q < 9; ++q) F[q] = Ej[q].a * S[q];
-    for (int k = 0; k < n; ++k) {
+    for (int k = cx.lane(); k < n; k += cx.width()) {
       const double* u = rays + 6 * (size_t)sample[k];
       const double* v = u + 3;
       const double Fu0 = F[0] * u[0] + F[1] * u[1] + F[2] * u[2];
@@ -782,7 +794,10 @@ SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const double* rays, const int*
         for (int b = 0; b <= a; ++b) H[hk++] += jl[a] * jl[b];
       }
     }
+    c = cx.sum(c);
     if (with_jac) {
+      cx.sum_vec(H);
+      cx.sum_vec(g);
       gmax = 0.0;
       for (int a = 0; a < 6; ++a) gmax = fmax(gmax, fabs(g[a]));  // gradient of the unscaled problem
       if (!have_scale) {
@@ -872,6 +887,9 @@ SSFM_HD_NOINLINE SixLmSummary sixpt_least_squares(const double* rays, const int*
   for (int i = 0; i < 3; ++i) { model.r[i] = x[i]; model.t[i] = x[3 + i]; }
   model.f = x[6];
   return sum;
+}
+SSFM_HD SixLmSummary sixpt_least_squares(const double* rays, const int* sample, int n, SixPointModel& model) {
+  return sixpt_least_squares(SixOneLane(), rays, sample, n, model);
 }
 
 }  // namespace ssfm

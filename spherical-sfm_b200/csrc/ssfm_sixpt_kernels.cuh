@@ -439,10 +439,12 @@ __global__ void __launch_bounds__(kSixChainWarps * 32) k_sixpt_chain_lo(Params P
   }
 }
 
-// One THREAD per parked pair: the LocalOptimization (or the loop's epilogue) the pair is waiting for, start to finish.
-__global__ void __launch_bounds__(64) k_sixpt_lo(Params P, SixChainArgs A, int nparked) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per parked pair: the LocalOptimization (or the loop's epilogue) the pair is waiting for, start to finish.
+constexpr int kSixLoWarps = 2;
+__global__ void __launch_bounds__(kSixLoWarps * 32) k_sixpt_lo(Params P, SixChainArgs A, int nparked) {
+  const int q = blockIdx.x * kSixLoWarps + (threadIdx.x >> 5);
   if (q >= nparked) return;
+  WarpCtx cx{(int)(threadIdx.x & 31)};
   const int a = A.parked[q];
   const int pair = A.pair0 + a;
   const long long off = A.offsets[pair];
@@ -450,9 +452,9 @@ __global__ void __launch_bounds__(64) k_sixpt_lo(Params P, SixChainArgs A, int n
   PairView pv{A.rays + 6 * off, n, A.rays + 6 * off};
   SixScratch sc{A.list_a + (off - A.list_base), A.list_b + (off - A.list_base), A.mt + (size_t)a * 625};
   SixLoState st = A.lo_states[a];
-  SerialCtx cx;
   long long exact = 0;
   const bool finished = six_lo_phase(cx, P, pv, sc, st, A.flags ? A.flags + off : (unsigned char*)0, &exact);
+  if (cx.lane() != 0) return;
   if (finished) {
     const bool have = st.best.score < kDblMax;
     SsfmPairResult& o = A.results[a];

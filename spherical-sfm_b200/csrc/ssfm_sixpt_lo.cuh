@@ -5,12 +5,14 @@
 // "estimator concept is complete" row of SURVEY section 8, not a benchmark configuration.
 //
 // Split of the work.  The walk over a round's look-ahead iterations (FP32 pre-filter, FP64 certification, best-minimal /
-// best-model bookkeeping) stays one warp per pair (k_sixpt_chain_lo).  Everything a LocalOptimization call does -- up to
+// best-model bookkeeping) is one warp per pair (k_sixpt_chain_lo).  A pair that reaches a LocalOptimization call -- up to
 // 1 + num_lo_steps * (2 + num_lsq_iterations) Ceres refits of <= 42 residuals, one six-point solve per LO step, ~100
-// passes over the pair's correspondences -- is sequential by construction (one mt19937 stream, each step depends on the
-// previous one), so a pair that reaches an LO is PARKED and all parked pairs run their LO together, one THREAD per pair
-// (k_sixpt_lo): thousands of independent sequential jobs fill the machine where one warp per pair would idle 31 lanes
-// during the refits.  The same functions compile for the host (tests/hostshim) with SerialCtx.
+// passes over the pair's correspondences, all sequential by construction (one mt19937 stream, each step depends on the
+// previous one) -- is PARKED, and all parked pairs run their LO together in k_sixpt_lo, one WARP per pair: the passes and
+// the refits' residual loops are spread over the lanes, the scalar parts (6 x 6 Cholesky, the six-point solve of an LO
+// step) run redundantly on every lane from identical inputs.  (First cut: one thread per pair -- measured 490 pairs/s on
+// 2000 x 1000 correspondences: a sub-pass holds at most 2048 pairs, i.e. 14 threads per SM.)  The same functions compile
+// for the host (tests/hostshim) with SerialCtx.
 #pragma once
 #include "ssfm_chain.cuh"
 #include "ssfm_sixpt.cuh"
@@ -52,7 +54,7 @@ SSFM_HD_NOINLINE void six_lsq_fit(const Ctx& cx, const Params& P, const PairView
   if (n < 6) return;
   const int k = n < cap ? n : cap;
   shuffle_and_resize(cx, sc.mt, sc.list_a, n, k);
-  sixpt_least_squares(pv.rays, sc.list_a, k, m);
+  sixpt_least_squares(cx, pv.rays, sc.list_a, k, m);
   sixpt_scoring_matrix(m, P.sixpt_focal_scoring, G);
 }
 
@@ -207,7 +209,7 @@ SSFM_HD_NOINLINE bool six_lo_phase(const Ctx& cx, const Params& P, const PairVie
     const int ni = collect_inliers(cx, st.best.G, pv.stream, pv.n, P.thr2, false, sc.list_a, (unsigned char*)0, evals);
     SixPointModel m = st.best.m;
     double G[9];
-    sixpt_least_squares(pv.rays, sc.list_a, ni, m);
+    sixpt_least_squares(cx, pv.rays, sc.list_a, ni, m);
     sixpt_scoring_matrix(m, P.sixpt_focal_scoring, G);
     int cnt = 0;
     const double score = msac_score_exact(cx, G, pv.stream, pv.n, P.thr2, &cnt, evals);
