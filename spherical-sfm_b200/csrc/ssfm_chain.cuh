@@ -35,6 +35,12 @@ struct Params {
   int sixpt_focal_scoring;  // six-point estimator: score with Kinv E Kinv instead of E
   float cand_margin;  // relative slack of the FP32 pre-filter (see process_round)
   int skip_complex;   // action-matrix solver: leave out the models of complex eigenvalues (SsfmOptions.complex_root_models)
+  // Small batches run the LocalOptimization refits inline (no parked waves, no host round trips) but with the arithmetic
+  // of the deferred path, so a pair's result does not depend on the size of the batch it is in: refits of at most
+  // inline_small_max residuals run as ONE lane would run them (every lane redundantly: uniform) and switch to the
+  // lane-parallel sums after inline_handover iterations -- exactly k_refit_small -> k_refit_long.  0: off.
+  int inline_small_max;
+  int inline_handover;
 };
 
 // Per-pair RANSAC state carried across rounds (RansacStatistics + the loop's locals).
@@ -444,6 +450,24 @@ SSFM_HD_NOINLINE void least_squares(const Ctx& cx, const double* rays, const int
   lm_finish(S, inward, E);
 }
 
+// The deferred path's small refit (k_refit_small, then k_refit_long after `handover` iterations), inline.
+template <class Ctx>
+SSFM_HD_NOINLINE void least_squares_as_deferred(const Ctx& cx, const double* rays, const int* sample, int n, bool inward, double* E,
+                                                int handover) {
+  SerialCtx one;
+  LMState S;
+  lm_init(one, rays, sample, n, inward, E, S);
+  bool done = false;
+  for (;;) {
+    if (lm_step(one, rays, sample, n, S)) { done = true; break; }
+    if (handover > 0 && S.iteration >= handover) break;
+  }
+  if (!done)
+    while (!lm_step(cx, rays, sample, n, S)) {
+    }
+  lm_finish(S, inward, E);
+}
+
 struct Scratch {
   int* list_a;   // n ints
   int* list_b;   // n ints
@@ -476,7 +500,11 @@ SSFM_HD_NOINLINE void lsq_fit(const Ctx& cx, const Params& P, const PairView& pv
   { SSFM_TIC n = collect_inliers(cx, E, pv.stream, pv.n, thresh, false, sc.list_a, (unsigned char*)0, evals); SSFM_TOC(sc, PH_LO_COLLECT) }
   if (n < 3) return;
   { SSFM_TIC shuffle_and_resize(cx, sc.mt, sc.list_a, n, n < cap ? n : cap); SSFM_TOC(sc, PH_LO_SHUFFLE) }
-  { SSFM_TIC least_squares(cx, pv.rays, sc.list_a, n < cap ? n : cap, P.inward != 0, E); SSFM_TOC(sc, PH_LO_LM) }
+  const int nr = n < cap ? n : cap;
+  SSFM_TIC
+  if (P.inline_small_max > 0 && nr <= P.inline_small_max) least_squares_as_deferred(cx, pv.rays, sc.list_a, nr, P.inward != 0, E, P.inline_handover);
+  else least_squares(cx, pv.rays, sc.list_a, nr, P.inward != 0, E);
+  SSFM_TOC(sc, PH_LO_LM)
 }
 
 SSFM_HD void keep_better(double s, const double* m, int c, double* sb, double* mb, int* cb) {  // UpdateBestModel :422-428
@@ -917,7 +945,12 @@ SSFM_HD_NOINLINE int finalize_pair(const Ctx& cx, const Params& P, const PairVie
           return -1;
         }
         for (int i = 0; i < 9; ++i) refined[i] = st.E_best[i];
-        { SSFM_TIC least_squares(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined); SSFM_TOC(sc, PH_FINAL_LM) }
+        SSFM_TIC
+        if (P.inline_small_max > 0 && ni <= P.inline_small_max)  // the deferred path solves a refit this small on one lane
+          least_squares_as_deferred(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined, P.inline_handover);
+        else
+          least_squares(cx, pv.rays, sc.list_a, ni, P.inward != 0, refined);
+        SSFM_TOC(sc, PH_FINAL_LM)
       } else {
         for (int i = 0; i < 9; ++i) refined[i] = sc.lm_E[i];
       }

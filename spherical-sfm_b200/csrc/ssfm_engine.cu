@@ -53,6 +53,7 @@ constexpr int kMaxPassPairs = 131072;
 constexpr int kPipelinePassPairs = 16384;  // pass size when the upload is pipelined with the compute
 constexpr int kMaxUploadChunks = 4096;
 constexpr int kRoundCap = 256;
+constexpr int kDeferMinPairs = 4096;  // batches below this run the LO refits inline (measured crossover)
 
 template <class T>
 struct DevBuf {
@@ -190,6 +191,8 @@ Params make_params(const SsfmOptions& o) {
   P.skip_complex = o.complex_root_models == SSFM_COMPLEX_SKIP;
   P.cand_margin = 2e-4f;
   if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
+  P.inline_small_max = 0;
+  P.inline_handover = 0;
   return P;
 }
 
@@ -295,7 +298,15 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
       // Six-point shared-focal estimator under VanillaMSAC (config C4) or LO-MSAC: look-ahead rounds like the 3-point
       // path, in sub-passes bounded by the model table (15 models x 16 doubles per look-ahead slot).
       const bool six_lo = P.driver == SSFM_DRIVER_LO_MSAC;
-      const int kSub = 2048;
+      // LO-MSAC: the LocalOptimization waves are one warp per parked pair, so they want many pairs in flight; a shorter
+      // look-ahead (down to 64 slots instead of 256, when the pass has more than 2048 pairs) lets up to four times as many pairs share the
+      // same 1 GB model table.
+      int r_lo = cfg.R;
+      while (six_lo && r_lo > 64 && (long long)np * r_lo > 2048LL * cfg.R) r_lo >>= 1;  // only when the pass has the pairs to fill it
+      if (const char* e = getenv("SSFM_SIXPT_LO_R")) r_lo = std::max(32, std::min(cfg.R, atoi(e) & ~31));
+      const int R = six_lo ? r_lo : cfg.R;
+      const int first_cap = std::min(cfg.first_cap, R), round_cap = std::min(cfg.round_cap, R);
+      const int kSub = 2048 * (cfg.R / R);
       if (six_lo) {
         SSFM_WCK(w.list_a.ensure(mpass + 16));
         SSFM_WCK(w.list_b.ensure(mpass + 16));
@@ -979,7 +990,7 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (int rc = check_options(opt)) return rc;
   if (!h->resident) return fail(SSFM_ERR_INVALID, "ssfm_run without a resident batch (call ssfm_upload first)");
   SSFM_CK(cudaSetDevice(h->device));
-  const Params P = make_params(*opt);
+  Params P = make_params(*opt);
   const double pack_ms = h->stats.pack_ms;
   const long long h2d = h->stats.h2d_bytes;
   h->stats = SsfmRunStats();
@@ -1001,10 +1012,22 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   if (const char* e = getenv("SSFM_FIRST_CAP")) cfg.first_cap = (std::max(32, atoi(e)) + 31) & ~31;
   cfg.R = std::max(cfg.first_cap, cfg.round_cap);
   cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
-  cfg.thr32 = (float)P.thr2;
   cfg.handover = getenv("SSFM_NO_HANDOVER") == nullptr;
   cfg.handover_at = kHandover;
   if (const char* e = getenv("SSFM_HANDOVER")) cfg.handover_at = std::max(1, atoi(e));
+  if (cfg.defer) {
+    // Parking refits pays when a wave holds thousands of them; below that a wave is a host round trip for a handful of
+    // threads (one C1-sized pair: five waves = 1.0 of its 1.27 ms).  Small batches run the same refits inline, with the
+    // deferred path's arithmetic (Params::inline_small_max), so the table does not depend on the batch size.
+    int defer_min = kDeferMinPairs;
+    if (const char* e = getenv("SSFM_DEFER_MIN_PAIRS")) defer_min = atoi(e);
+    if (h->P < defer_min) {
+      cfg.defer = false;
+      P.inline_small_max = kSmallRefit;
+      P.inline_handover = cfg.handover ? cfg.handover_at : 0;
+    }
+  }
+  cfg.thr32 = (float)P.thr2;
   // 0: every small refit is solved one thread per problem.  (A warp-per-refit path for thin waves has lower
   // latency but sums in a different order, which would make results depend on how many pairs share a wave.)
   cfg.small_refit_threads_min = 0;

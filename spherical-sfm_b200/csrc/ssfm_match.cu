@@ -297,7 +297,14 @@ __device__ __noinline__ Top2 top2_group_far(Top2 s, float x0, float x1, float x2
 // 32 consecutive train rows against the running top-2 of this thread's query row.  Groups of eight = two of four: one min
 // tree per eight and ONE round of warp votes per 32 (against the threshold at the start: it only decreases, so a stale
 // one lets a few more groups through, never fewer); the four-groups that hold a candidate are walked.
+#ifndef SSFM_MATCH_DIAG
+#define SSFM_MATCH_DIAG 0  // timing diagnostics only (WRONG results): 1 = clean scan without the exact insertions, 2 = no scan at all
+#endif
 __device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, float qn, float far_a) {
+#if SSFM_MATCH_DIAG == 2
+  st.a0 = fminf(st.a0, x[0]);
+  return;
+#endif
   float m4[8], m8[4];
 #pragma unroll
   for (int h = 0; h < 8; ++h) m4[h] = fminf(min3f(x[4 * h], x[4 * h + 1], x[4 * h + 2]), x[4 * h + 3]);
@@ -306,6 +313,11 @@ __device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, 
   bool gate[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) gate[g] = __any_sync(0xffffffffu, m8[g] < st.a1);
+#if SSFM_MATCH_DIAG == 1
+#pragma unroll
+  for (int g = 0; g < 4; ++g) st.a1 = fminf(st.a1, gate[g] ? m8[g] : st.a1);
+  return;
+#endif
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     if (gate[g]) {

@@ -174,6 +174,24 @@ def test_near_noise_free_pairs_scores_near_zero(S, O, engine, orc, ref):
             assert (flags[offsets[p]:offsets[p + 1]] == fl).all(), (seed, p)
 
 
+def test_small_batch_inline_refits_equal_deferred_results(S, engine):
+    """Batches below 4096 pairs run the LocalOptimization refits inline (no parked waves: a single pair is 1.0 ms instead of
+    1.3 ms), larger ones park them and solve them one thread each.  Both use the same arithmetic (one-lane refit, lane-
+    parallel continuation after 24 iterations), so a pair's record must not depend on the size of its batch: the first 24
+    pairs of a 4200-pair batch, run again on their own, give byte-identical records and flags."""
+    P, N = 4200, 300
+    rays, offsets, _ = S.problems.make_batch(31, P, N, noise=1.0 / 600, outlier_frac=0.5, max_angle_deg=20.0)
+    opt = S.pipeline_options(THR2)
+    big, big_flags = engine.estimate_pairs(rays, offsets, opt)
+    assert engine.stats().refit_waves > 0  # the large batch did go through the deferred path
+    k = 24
+    small, small_flags = engine.estimate_pairs(rays[:offsets[k]], offsets[:k + 1], opt)
+    assert engine.stats().refit_waves == 0
+    assert (small["number_lo_iterations"] >= 1).all()
+    assert small.tobytes() == big[:k].tobytes()
+    assert (small_flags == big_flags[:offsets[k]]).all()
+
+
 def test_default_lo_options(S, O, engine, orc, ref):
     """RansacLib's default LO schedule (10 LO steps x 4 LSQ iterations, NonMinimalSolver)."""
     _compare_batch(S, O, engine, ref if ref is not None else orc, S.default_options(squared_inlier_threshold=THR2), 8, 600, 0.5, 5)

@@ -41,4 +41,4 @@ t0 = time.perf_counter()
 om = MO.match(descs[pairs[0][0]], descs[pairs[0][1]])
 dc = time.perf_counter() - t0
 a, b = mo[0], mo[1]
-print("oracle (numpy, 1 core) one pair: %.2f s; identical: %s" % (dc, bool((mm[a:b] == om).all() and len(om) == b - a)))
+print("oracle (numpy, 1 core) one pair: %.2f s; identical: %s" % (dc, bool(len(om) == b - a and (mm[a:b] == om).all())))
