@@ -104,6 +104,9 @@ struct ssfm_engine {
   bool resident = false;
   // pipelined upload (ssfm_estimate_pairs): one event + one unit-z flag per pass of pairs
   std::vector<cudaEvent_t> up_ev;
+  std::vector<cudaEvent_t> copy_ev;   // chunk k has landed in HBM (recorded on `stream`, waited on by `stream_pack`)
+  cudaStream_t stream_pack = nullptr;  // high priority: the per-chunk pack / ray-build kernels.  On the copy stream they
+                                       // would hold the NEXT chunk's H2D back until SMs free up under the workers' kernels.
   std::vector<int> up_bounds;  // pair bounds of the upload chunks (empty: not pipelined)
   DevBuf<int> up_flags;
   int* h_up_flags = nullptr;  // pinned
@@ -687,6 +690,11 @@ int ssfm_create(int device, ssfm_handle* out) {
 
 static int create_resources(ssfm_engine* h) {
   SSFM_CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    SSFM_CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SSFM_CK(cudaStreamCreateWithPriority(&h->stream_pack, cudaStreamNonBlocking, prio_hi));
+  }
   for (auto& ev : h->ev) SSFM_CK(cudaEventCreate(&ev));
   SSFM_CK(cudaEventCreateWithFlags(&h->ev_tables, cudaEventDisableTiming));
   SSFM_CK(cudaMallocHost(&h->h_count, 64));
@@ -732,6 +740,8 @@ void ssfm_destroy(ssfm_handle h) {
   if (h->h_count) cudaFreeHost(h->h_count);
   if (h->h_up_flags) cudaFreeHost(h->h_up_flags);
   for (auto& e : h->up_ev) cudaEventDestroy(e);
+  for (auto& e : h->copy_ev) cudaEventDestroy(e);
+  if (h->stream_pack) cudaStreamDestroy(h->stream_pack);
   h->up_flags.release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -756,6 +766,11 @@ static int plan_upload_chunks(ssfm_handle h) {
     cudaEvent_t e;
     SSFM_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->up_ev.push_back(e);
+  }
+  while ((int)h->copy_ev.size() < nchunks) {
+    cudaEvent_t e;
+    SSFM_CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->copy_ev.push_back(e);
   }
   return SSFM_OK;
 }
@@ -802,16 +817,22 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
     const int nchunks = (int)h->up_bounds.size() - 1;
     for (int k = 0; k < nchunks; ++k) {
       const long long c0 = h->h_offsets[h->up_bounds[k]], c1 = h->h_offsets[h->up_bounds[k + 1]];
-      if (c1 > c0) {
+      // the copies queue back to back on the copy stream; each chunk's pack kernel runs on the high-priority stream as
+      // soon as the chunk has landed
+      if (c1 > c0)
         SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
                                 cudaMemcpyHostToDevice, h->stream));
-        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0,
-                                                                         h->xy64.p + 4 * c0, h->up_flags.p + k);
+      SSFM_CK(cudaEventRecord(h->copy_ev[k], h->stream));
+      SSFM_CK(cudaStreamWaitEvent(h->stream_pack, h->copy_ev[k], 0));
+      if (c1 > c0) {
+        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream_pack>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0,
+                                                                              h->xy64.p + 4 * c0, h->up_flags.p + k);
         SSFM_CK(cudaGetLastError());
       }
-      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      SSFM_CK(cudaEventRecord(h->up_ev[k], h->stream));
+      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream_pack));
+      SSFM_CK(cudaEventRecord(h->up_ev[k], h->stream_pack));
     }
+    if (nchunks > 0) SSFM_CK(cudaStreamWaitEvent(h->stream, h->up_ev[nchunks - 1], 0));  // a sync of `stream` covers the packs
     h->stats.h2d_bytes = (long long)(sizeof(double) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
     h->unit_z = false;  // decided per chunk
     h->resident = true;
@@ -899,11 +920,15 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
   SSFM_CK(cudaMemcpyAsync(h->m_kinv.p, b->Kinv, sizeof(double) * 9, cudaMemcpyHostToDevice, st));
   SSFM_CK(cudaEventRecord(h->ev_tables, st));
   h->stats.h2d_bytes = (long long)(8 * NK + 8 * (long long)P + 8 * M + 8 * (P + 1) + 8 * (b->num_images + 1) + 72);
-  auto build = [&](long long c0, long long c1, int* flag) -> cudaError_t {  // matches [c0, c1): H2D, rays + FP32 plane in one kernel
+  auto build = [&](long long c0, long long c1, int* flag, cudaStream_t kst, cudaEvent_t landed) -> cudaError_t {  // matches [c0, c1): H2D, rays + FP32 plane in one kernel
     if (c1 <= c0) return cudaSuccess;
     cudaError_t e = cudaMemcpyAsync(h->m_matches.p + 2 * c0, b->matches + 2 * c0, sizeof(int) * 2 * (size_t)(c1 - c0), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    k_build_rays<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float2*>(h->m_kp.p), h->m_kpoff.p, h->m_pairs.p,
+    if (kst != st) {  // pipelined: the kernel runs on the high-priority stream once the chunk has landed
+      if ((e = cudaEventRecord(landed, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(kst, landed, 0)) != cudaSuccess) return e;
+    }
+    k_build_rays<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, kst>>>(reinterpret_cast<const float2*>(h->m_kp.p), h->m_kpoff.p, h->m_pairs.p,
                                                                     h->offsets.p, P, reinterpret_cast<const int2*>(h->m_matches.p), c0,
                                                                     c1 - c0, h->m_kinv.p, h->rays_own.p, h->uv4.p, h->xy64.p, flag, h->counts.p + 3);
     return cudaGetLastError();
@@ -926,17 +951,23 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
           SSFM_CK(cudaMemcpyAsync(h->m_kp.p + 2 * k0, b->keypoints_xy + 2 * k0, sizeof(float) * 2 * (size_t)(k1 - k0), cudaMemcpyHostToDevice, st));
         images_copied = need;
       }
-      SSFM_CK(build(h->h_offsets[h->up_bounds[k]], h->h_offsets[h->up_bounds[k + 1]], h->up_flags.p + k));
-      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, st));
-      SSFM_CK(cudaEventRecord(h->up_ev[k], st));
+      const long long c0 = h->h_offsets[h->up_bounds[k]], c1 = h->h_offsets[h->up_bounds[k + 1]];
+      if (c1 <= c0) {  // empty chunk: still order the flag read after whatever precedes it
+        SSFM_CK(cudaEventRecord(h->copy_ev[k], st));
+        SSFM_CK(cudaStreamWaitEvent(h->stream_pack, h->copy_ev[k], 0));
+      }
+      SSFM_CK(build(c0, c1, h->up_flags.p + k, h->stream_pack, h->copy_ev[k]));
+      SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream_pack));
+      SSFM_CK(cudaEventRecord(h->up_ev[k], h->stream_pack));
     }
+    if (nchunks > 0) SSFM_CK(cudaStreamWaitEvent(st, h->up_ev[nchunks - 1], 0));  // a sync of `stream` covers the kernels
     h->unit_z = false;  // decided per chunk
     h->matches_pending_check = true;
     h->resident = true;
     return SSFM_OK;
   }
   SSFM_CK(cudaEventRecord(h->ev[4], st));
-  SSFM_CK(build(0, M, h->counts.p + 2));
+  SSFM_CK(build(0, M, h->counts.p + 2, st, nullptr));
   SSFM_CK(cudaEventRecord(h->ev[5], st));
   SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   SSFM_CK(cudaStreamSynchronize(st));  // the caller's buffers may go away after we return
