@@ -234,9 +234,16 @@ def config_block(S, eng, fp32_peak, args):
     ms2 = (time.perf_counter() - t0) * 1e3 / 3
     st2 = eng.stats()
     r2, _ = eng.download(want_flags=False)
-    t0 = time.perf_counter()
-    eng.estimate_pairs(rays2, offs2, opt2)
-    ms2e = (time.perf_counter() - t0) * 1e3
+    # end to end with pinned host buffers in and out, like the headline e2e (pageable memory would time the staging copy)
+    import torch
+    rays2_t = torch.from_numpy(rays2).pin_memory()
+    res2_t = torch.empty(P2 * S.RESULT_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    flags2_t = torch.empty(P2 * N2, dtype=torch.uint8, pin_memory=True)
+    ms2e = 1e30
+    for _ in range(4):
+        t0 = time.perf_counter()
+        eng.estimate_pairs(rays2_t.numpy(), offs2, opt2, out_results=res2_t.numpy().view(S.RESULT_DTYPE), out_flags=flags2_t.numpy())
+        ms2e = min(ms2e, (time.perf_counter() - t0) * 1e3)
     oo = O.default_options(squared_inlier_threshold=THR2, driver=2, solver_kind=2, legacy_budget=512)
     nc = P2
     _, secs = orc.estimate_batch(rays2[:nc * N2], offs2[:nc + 1], oo, 0, cores)
