@@ -662,6 +662,24 @@ def main():
         del kp_all, mt_all, mt_pin, rt
     except Exception as exc:
         line["e2e_from_matches"] = {"error": str(exc)}
+    # the packed-float input (SSFM_RAYS_F32): the same call with 24 instead of 48 bytes per correspondence over PCIe
+    try:
+        r32_t = torch.empty((P * N, 6), dtype=torch.float32, pin_memory=True)
+        r32_t.copy_(torch.from_numpy(rays_np))
+        eng.estimate_pairs(r32_t.numpy(), offsets, opt, out_results=out_res, out_flags=out_flags)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rf, _ = eng.estimate_pairs(r32_t.numpy(), offsets, opt, out_results=out_res, out_flags=out_flags)
+        torch.cuda.synchronize()
+        ms_f = (time.perf_counter() - t0) * 1e3 / args.steps
+        stf = eng.stats()
+        line["e2e_float32_rays"] = {"value": float(rf["evals"].sum()) * world / (ms_f * 1e-3), "unit": "evals/s", "ms_per_step": ms_f,
+                                    "pairs_per_sec": world * P / (ms_f * 1e-3), "h2d_bytes_per_step": int(stf.h2d_bytes),
+                                    "note": "rays rounded to float32 on the host, widened on the device: the result equals the float64 call on those values"}
+        del r32_t
+    except Exception as exc:
+        line["e2e_float32_rays"] = {"error": str(exc)}
     # BASELINE.json configs other than the headline one: C1, C2, full C4, C5 as specified -- each with a CPU figure beside it
     try:
         line["configs"] = config_block(S, eng, fp32_peak, args)

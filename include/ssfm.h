@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define SSFM_ABI_VERSION 2
+#define SSFM_ABI_VERSION 3
 
 typedef struct ssfm_engine* ssfm_handle;
 
@@ -112,7 +112,12 @@ typedef struct SsfmBatch {
   const int64_t* offsets; /* host, num_pairs + 1 entries */
   const double* rays;     /* host pointer, or device pointer (16-byte aligned) if rays_on_device != 0 */
   int32_t rays_on_device;
+  int32_t ray_format;     /* SSFM_RAYS_F64 (0): 6 doubles per correspondence, the RayPair memory.  SSFM_RAYS_F32 (1): `rays`
+                             points at 6 FLOATS per correspondence (u.xyz, v.xyz) -- half the bytes over PCIe (SURVEY 8b's
+                             packed-float input); they are widened to double on the device, so the result is exactly the
+                             SSFM_RAYS_F64 result for the same values.  (ABI 3; the field occupies former padding: zero it.) */
 } SsfmBatch;
+enum { SSFM_RAYS_F64 = 0, SSFM_RAYS_F32 = 1 };
 
 /* Per-pair output: the best model + RansacStatistics (include/RansacLib/ransac.h:94-101) + the
  * pose the callers extract afterwards with decompose_spherical_essential_matrix

@@ -271,6 +271,7 @@ int estimate_one(int driver, const Options& options, const Solver& solver, Model
   b.offsets = offsets;
   b.rays = solver.rays();
   b.rays_on_device = 0;
+  b.ray_format = SSFM_RAYS_F64;
   SsfmPairResult r;
   std::vector<uint8_t> flags(n > 0 ? n : 1);
   check(ssfm_estimate_pairs(solver.handle(), &b, &o, &r, flags.data()));
@@ -437,6 +438,7 @@ int legacy_compute(const Engine& eng, SsfmOptions o, It begin, It end, std::vect
   b.offsets = offsets;
   b.rays = n > 0 ? reinterpret_cast<const double*>(&*begin) : nullptr;
   b.rays_on_device = 0;
+  b.ray_format = SSFM_RAYS_F64;
   SsfmPairResult res;
   std::vector<uint8_t> flags(n > 0 ? n : 1);
   check(ssfm_estimate_pairs(eng.get(), &b, &o, &res, flags.data()));
@@ -544,6 +546,7 @@ inline void detail::estimate_pairs_impl(const Options& options, const std::vecto
   b.offsets = offsets.data();
   b.rays = rays.data();
   b.rays_on_device = 0;
+  b.ray_format = SSFM_RAYS_F64;
   results->resize(pair_lists.size());
   if (inlier_flags) inlier_flags->assign((size_t)offsets.back(), 0);
   check(call(&b, &o, results->data(), inlier_flags ? inlier_flags->data() : nullptr));

@@ -57,7 +57,17 @@ class SsfmOptions(C.Structure):
 
 class SsfmBatch(C.Structure):
     _fields_ = [("num_pairs", C.c_int32), ("offsets", C.POINTER(C.c_int64)), ("rays", C.c_void_p),
-                ("rays_on_device", C.c_int32)]
+                ("rays_on_device", C.c_int32), ("ray_format", C.c_int32)]
+
+
+RAYS_F64, RAYS_F32 = 0, 1
+
+
+def _ray_array(rays):
+    """(contiguous array, ray_format): float32 input stays float32 (SSFM_RAYS_F32, half the bytes), anything else is float64."""
+    if isinstance(rays, np.ndarray) and rays.dtype == np.float32:
+        return np.ascontiguousarray(rays), RAYS_F32
+    return np.ascontiguousarray(rays, np.float64), RAYS_F64
 
 
 class SsfmMatchBatch(C.Structure):
@@ -216,8 +226,9 @@ class Engine:
             pass
 
     # ---- the batched entry point --------------------------------------------------------
-    def upload(self, rays, offsets, device_ptr=None):
-        """rays: (M, 6) float64 host array (RayPair memory), or device_ptr=int for rays already in HBM."""
+    def upload(self, rays, offsets, device_ptr=None, device_format=RAYS_F64):
+        """rays: (M, 6) float64 host array (RayPair memory) or float32 (SSFM_RAYS_F32), or device_ptr=int for rays already
+        in HBM (device_format says which of the two layouts they are in)."""
         offsets = np.ascontiguousarray(offsets, np.int64)
         b = SsfmBatch()
         b.num_pairs = len(offsets) - 1
@@ -225,8 +236,9 @@ class Engine:
         if device_ptr is not None:
             b.rays = C.c_void_p(int(device_ptr))
             b.rays_on_device = 1
+            b.ray_format = device_format
         else:
-            rays = np.ascontiguousarray(rays, np.float64)
+            rays, b.ray_format = _ray_array(rays)
             assert rays.size == 6 * int(offsets[-1])
             self._keep = rays
             b.rays = C.c_void_p(rays.ctypes.data)
@@ -249,9 +261,9 @@ class Engine:
     def estimate_pairs(self, rays, offsets, opt, want_flags=True, out_results=None, out_flags=None):
         """ssfm_estimate_pairs: upload + run + download in one call (host buffers in, host buffers out).
         out_results / out_flags: optional preallocated (e.g. pinned) output arrays."""
-        rays = np.ascontiguousarray(rays, np.float64)
+        rays, fmt = _ray_array(rays)
         offsets = np.ascontiguousarray(offsets, np.int64)
-        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0)
+        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0, fmt)
         res = out_results if out_results is not None else np.zeros(b.num_pairs, RESULT_DTYPE)
         assert res.dtype == RESULT_DTYPE and len(res) == b.num_pairs
         flags = (out_flags if out_flags is not None else np.zeros(int(offsets[-1]), np.uint8)) if want_flags else None
@@ -484,9 +496,9 @@ class MultiEngine:
             pass
 
     def estimate_pairs(self, rays, offsets, opt, want_flags=True, out_results=None, out_flags=None):
-        rays = np.ascontiguousarray(rays, np.float64)
+        rays, fmt = _ray_array(rays)
         offsets = np.ascontiguousarray(offsets, np.int64)
-        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0)
+        b = SsfmBatch(len(offsets) - 1, _p(offsets, C.c_int64), C.c_void_p(rays.ctypes.data), 0, fmt)
         res = out_results if out_results is not None else np.zeros(b.num_pairs, RESULT_DTYPE)
         flags = (out_flags if out_flags is not None else np.zeros(int(offsets[-1]), np.uint8)) if want_flags else None
         _check(lib().ssfm_estimate_pairs_multi(self._h, C.byref(b), C.byref(opt), C.c_void_p(res.ctypes.data),

@@ -101,6 +101,7 @@ struct ssfm_engine {
   DevBuf<double> m_kinv;
   bool matches_pending_check = false;  // a pipelined match upload whose index-range flag has not been read yet
   DevBuf<long long> offsets;
+  DevBuf<float> rays_f32;  // staging for SSFM_RAYS_F32 host input (24 bytes per correspondence)
   bool resident = false;
   // pipelined upload (ssfm_estimate_pairs): one event + one unit-z flag per pass of pairs
   std::vector<cudaEvent_t> up_ev;
@@ -782,8 +783,10 @@ static bool want_pipelined_upload(ssfm_handle h) {
 static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
   if (b->num_pairs < 0 || (b->num_pairs > 0 && (!b->offsets || !b->rays))) return fail(SSFM_ERR_INVALID, "bad batch");
-  if (b->rays_on_device && (reinterpret_cast<uintptr_t>(b->rays) & 15u) != 0)
-    return fail(SSFM_ERR_INVALID, "device rays must be 16-byte aligned (they are read as double2)");
+  if (b->ray_format != SSFM_RAYS_F64 && b->ray_format != SSFM_RAYS_F32) return fail(SSFM_ERR_INVALID, "unknown ray_format");
+  const bool f32 = b->ray_format == SSFM_RAYS_F32;
+  if (b->rays_on_device && (reinterpret_cast<uintptr_t>(b->rays) & (f32 ? 7u : 15u)) != 0)
+    return fail(SSFM_ERR_INVALID, "device rays must be 16-byte aligned (8-byte for SSFM_RAYS_F32): they are read as double2 / float2");
   SSFM_CK(cudaSetDevice(h->device));
   h->resident = false;
   h->have_results = false;
@@ -812,6 +815,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
     // stream, an event per chunk.  ssfm_run's passes wait on the events, so the copy of chunk k+1
     // overlaps the kernels of chunk k.  (The caller's buffer is only read until ssfm_run returns.)
     SSFM_CK(h->rays_own.ensure(m * 6));
+    if (f32) SSFM_CK(h->rays_f32.ensure(m * 6));
     h->d_rays = h->rays_own.p;
     if (int rc = plan_upload_chunks(h)) return rc;
     const int nchunks = (int)h->up_bounds.size() - 1;
@@ -819,27 +823,50 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
       const long long c0 = h->h_offsets[h->up_bounds[k]], c1 = h->h_offsets[h->up_bounds[k + 1]];
       // the copies queue back to back on the copy stream; each chunk's pack kernel runs on the high-priority stream as
       // soon as the chunk has landed
-      if (c1 > c0)
-        SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
-                                cudaMemcpyHostToDevice, h->stream));
+      if (c1 > c0) {
+        if (f32)
+          SSFM_CK(cudaMemcpyAsync(h->rays_f32.p + 6 * c0, reinterpret_cast<const float*>(b->rays) + 6 * c0,
+                                  sizeof(float) * 6 * (size_t)(c1 - c0), cudaMemcpyHostToDevice, h->stream));
+        else
+          SSFM_CK(cudaMemcpyAsync(h->rays_own.p + 6 * c0, b->rays + 6 * c0, sizeof(double) * 6 * (size_t)(c1 - c0),
+                                  cudaMemcpyHostToDevice, h->stream));
+      }
       SSFM_CK(cudaEventRecord(h->copy_ev[k], h->stream));
       SSFM_CK(cudaStreamWaitEvent(h->stream_pack, h->copy_ev[k], 0));
       if (c1 > c0) {
-        k_pack<<<(unsigned)((c1 - c0 + 255) / 256), 256, 0, h->stream_pack>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0,
-                                                                              h->xy64.p + 4 * c0, h->up_flags.p + k);
+        const unsigned nb = (unsigned)((c1 - c0 + 255) / 256);
+        if (f32)
+          k_pack_f32<<<nb, 256, 0, h->stream_pack>>>(h->rays_f32.p + 6 * c0, c1 - c0, h->rays_own.p + 6 * c0, h->uv4.p + c0,
+                                                     h->xy64.p + 4 * c0, h->up_flags.p + k);
+        else
+          k_pack<<<nb, 256, 0, h->stream_pack>>>(h->rays_own.p + 6 * c0, c1 - c0, h->uv4.p + c0, h->xy64.p + 4 * c0,
+                                                 h->up_flags.p + k);
         SSFM_CK(cudaGetLastError());
       }
       SSFM_CK(cudaMemcpyAsync(h->h_up_flags + k, h->up_flags.p + k, sizeof(int), cudaMemcpyDeviceToHost, h->stream_pack));
       SSFM_CK(cudaEventRecord(h->up_ev[k], h->stream_pack));
     }
     if (nchunks > 0) SSFM_CK(cudaStreamWaitEvent(h->stream, h->up_ev[nchunks - 1], 0));  // a sync of `stream` covers the packs
-    h->stats.h2d_bytes = (long long)(sizeof(double) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
+    h->stats.h2d_bytes = (long long)((f32 ? sizeof(float) : sizeof(double)) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
     h->unit_z = false;  // decided per chunk
     h->resident = true;
     return SSFM_OK;
   }
   SSFM_CK(cudaEventRecord(h->ev[4], h->stream));
-  if (b->rays_on_device) {
+  const float* src32 = nullptr;
+  if (f32) {  // the float64 records the exact passes read are always the engine's own copy
+    SSFM_CK(h->rays_own.ensure(m * 6));
+    if (b->rays_on_device) {
+      src32 = reinterpret_cast<const float*>(b->rays);
+    } else {
+      SSFM_CK(h->rays_f32.ensure(m * 6));
+      if (h->M > 0)
+        SSFM_CK(cudaMemcpyAsync(h->rays_f32.p, b->rays, sizeof(float) * 6 * (size_t)h->M, cudaMemcpyHostToDevice, h->stream));
+      src32 = h->rays_f32.p;
+      h->stats.h2d_bytes = (long long)(sizeof(float) * 6 * (size_t)h->M + sizeof(long long) * (h->P + 1));
+    }
+    h->d_rays = h->rays_own.p;
+  } else if (b->rays_on_device) {
     h->d_rays = b->rays;
   } else {
     SSFM_CK(h->rays_own.ensure(m * 6));
@@ -851,7 +878,10 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   if (h->M > 0) {
     const int threads = 256;
     const long long blocks = (h->M + threads - 1) / threads;
-    k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->uv4.p, h->xy64.p, h->counts.p + 2);
+    if (f32)
+      k_pack_f32<<<(unsigned)blocks, threads, 0, h->stream>>>(src32, h->M, h->rays_own.p, h->uv4.p, h->xy64.p, h->counts.p + 2);
+    else
+      k_pack<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_rays, h->M, h->uv4.p, h->xy64.p, h->counts.p + 2);
     SSFM_CK(cudaGetLastError());
   }
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));

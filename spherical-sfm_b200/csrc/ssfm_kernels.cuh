@@ -116,6 +116,26 @@ __global__ void k_pack(const double* __restrict__ rays, long long m, float4* __r
   // pipeline rays are K^-1 (x, y, 1) (examples/spherical_sfm_tools.cpp:364-373): z == 1 exactly
   if (b.x != 1.0 || c.y != 1.0) *not_unit_z = 1;
 }
+// SSFM_RAYS_F32 input: 6 floats per correspondence -> the float64 records the exact passes read (widening is exact) + the
+// same planes as k_pack.
+__global__ void k_pack_f32(const float* __restrict__ rays32, long long m, double* __restrict__ rays64, float4* __restrict__ uv4,
+                           double* __restrict__ xy64, int* __restrict__ not_unit_z) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const float2* src = reinterpret_cast<const float2*>(rays32 + 6 * i);  // 24-byte records, 8-byte aligned
+  const float2 a = src[0], b = src[1], c = src[2];
+  double2* dst = reinterpret_cast<double2*>(rays64 + 6 * i);
+  dst[0] = make_double2((double)a.x, (double)a.y);
+  dst[1] = make_double2((double)b.x, (double)b.y);
+  dst[2] = make_double2((double)c.x, (double)c.y);
+  uv4[i] = make_float4(a.x, a.y, b.y, c.x);
+  if (xy64) {
+    double2* d = reinterpret_cast<double2*>(xy64 + 4 * i);
+    d[0] = make_double2((double)a.x, (double)a.y);
+    d[1] = make_double2((double)b.y, (double)c.x);
+  }
+  if (b.x != 1.0f || c.y != 1.0f) *not_unit_z = 1;
+}
 __global__ void k_pack_general(const double* __restrict__ rays, long long m, float4* __restrict__ u4, float4* __restrict__ v4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;

@@ -170,8 +170,10 @@ int ssfm_estimate_pairs_multi(ssfm_multi_handle m, const SsfmBatch* batch, const
     SsfmBatch b;
     b.num_pairs = p1 - p0;
     b.offsets = offs.data();
-    b.rays = batch->rays ? batch->rays + 6 * c0 : nullptr;
+    const size_t elem = batch->ray_format == SSFM_RAYS_F32 ? sizeof(float) : sizeof(double);
+    b.rays = batch->rays ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(batch->rays) + elem * 6 * (size_t)c0) : nullptr;
     b.rays_on_device = 0;
+    b.ray_format = batch->ray_format;
     SsfmOptions o = *opt;
     o.first_pair_id = opt->first_pair_id + (uint32_t)p0;  // pair p keeps its Philox key wherever it runs
     m->rc[i] = ssfm_estimate_pairs(m->engines[i], &b, &o, results + p0, inlier_flags ? inlier_flags + c0 : nullptr);

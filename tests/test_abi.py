@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol(S):
     for n in names:
         assert hasattr(L, n), n
     assert sorted(S.EXPORTED_SYMBOLS) == names
-    assert L.ssfm_abi_version() == 2
+    assert L.ssfm_abi_version() == 3
 
 
 def test_built_for_sm_100a_with_tma(S):

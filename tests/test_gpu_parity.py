@@ -192,6 +192,37 @@ def test_small_batch_inline_refits_equal_deferred_results(S, engine):
     assert (small_flags == big_flags[:offsets[k]]).all()
 
 
+def test_float32_ray_input_equals_float64_input_of_the_same_values(S, engine):
+    """SSFM_RAYS_F32 (SURVEY 8b's packed-float input: 24 instead of 48 bytes per correspondence over PCIe): the floats are
+    widened on the device, so the record table and the flags are byte-identical to the float64 call on the same values --
+    through the plain upload, the chunk-pipelined one (P > 32 768) and the resident (upload + run) path."""
+    for P, N in ((300, 200), (40000, 24)):
+        rays, offsets, _ = S.problems.make_batch(41, P, N, noise=1.0 / 600, outlier_frac=0.4, max_angle_deg=20.0)
+        r32 = rays.astype(np.float32)
+        r64 = r32.astype(np.float64)
+        assert (r64[:, 2] == 1.0).all() and (r64[:, 5] == 1.0).all()
+        opt = S.pipeline_options(THR2)
+        a, fa = engine.estimate_pairs(r64, offsets, opt)
+        b, fb = engine.estimate_pairs(r32, offsets, opt)
+        assert a.tobytes() == b.tobytes() and (fa == fb).all()
+        assert engine.stats().h2d_bytes < 0.55 * (r64.nbytes + offsets.nbytes)
+        engine.upload(r32, offsets)
+        engine.run(opt)
+        c, fc = engine.download()
+        assert a.tobytes() == c.tobytes() and (fa == fc).all()
+        assert (a["status"] == 0).mean() > 0.99
+    # general rays (z != 1) take the general planes
+    rng = np.random.default_rng(3)
+    rays, offsets, _ = S.problems.make_batch(42, 64, 300, noise=1.0 / 600, outlier_frac=0.3, max_angle_deg=20.0)
+    scale = rng.uniform(0.5, 2.0, (len(rays), 2))
+    rays[:, :3] *= scale[:, :1]
+    rays[:, 3:] *= scale[:, 1:]
+    r32 = rays.astype(np.float32)
+    a, fa = engine.estimate_pairs(r32.astype(np.float64), offsets, S.pipeline_options(THR2))
+    b, fb = engine.estimate_pairs(r32, offsets, S.pipeline_options(THR2))
+    assert a.tobytes() == b.tobytes() and (fa == fb).all() and (a["status"] == 0).mean() > 0.9
+
+
 def test_default_lo_options(S, O, engine, orc, ref):
     """RansacLib's default LO schedule (10 LO steps x 4 LSQ iterations, NonMinimalSolver)."""
     _compare_batch(S, O, engine, ref if ref is not None else orc, S.default_options(squared_inlier_threshold=THR2), 8, 600, 0.5, 5)
