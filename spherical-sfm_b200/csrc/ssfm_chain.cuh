@@ -306,7 +306,7 @@ SSFM_HD double lm_eval_jac(const Ctx& cx, const double* rays, const int* sample,
   for (int a = 0; a < 28; ++a) acc[a] = 0.0;
   for (int i = cx.lane(); i < n; i += cx.width()) {
     double ry[6];
-    load6(rays + 6 * (size_t)sample[i], ry);
+    load6(rays + 6 * (size_t)(sample ? sample[i] : i), ry);  // sample == NULL: the residuals are rays[0..n) themselves
     double r, jr[6];
     sampson_value_grad(Ej, ry, ry + 3, r, jr);
     acc[27] += r * r;
@@ -342,7 +342,7 @@ SSFM_HD double lm_eval_cost(const Ctx& cx, const double* rays, const int* sample
   double c = 0.0;
   for (int i = cx.lane(); i < n; i += cx.width()) {
     double ry[6];
-    load6(rays + 6 * (size_t)sample[i], ry);
+    load6(rays + 6 * (size_t)(sample ? sample[i] : i), ry);  // sample == NULL: the residuals are rays[0..n) themselves
     const double r = sampson_value(Ev, ry, ry + 3);
     c += r * r;
   }

@@ -278,6 +278,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
   SSFM_WCK(cudaStreamWaitEvent(w.stream_hi, h->ev_tables, 0));
   SSFM_WCK(cudaMemsetAsync(w.counters.p, 0, 32 * sizeof(unsigned long long), w.stream));
   cudaEvent_t evA = w.ev[0], evB = w.ev[1], evC = w.ev[2], evD = w.ev[3];
+  SSFM_WCK(cudaFuncSetAttribute(k_refit_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRefitBigSmem));
   int launches = 0;
   for (const PassDesc& pd : passes) {
     const int pair0 = pd.pair0, np = pd.np;
@@ -578,12 +579,12 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
               }
             } else if (ns > 0) {
               // too few to fill the machine one thread each: one warp per refit (lower latency; this is tail)
-              k_refit_big<<<(ns + 3) / 4, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, ns, 1, w.states.p,
+              k_refit_big<<<(ns + 3) / 4, 128, kRefitBigSmem, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, ns, 1, w.states.p,
                                                         w.list_a.p, c0, w.lm_E.p);
               launches += 1;
             }
             if (nb > 0) {
-              k_refit_big<<<(nb + 3) / 4, 128, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, nb, 0, w.states.p,
+              k_refit_big<<<(nb + 3) / 4, 128, kRefitBigSmem, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, np, nb, 0, w.states.p,
                                                         w.list_a.p, c0, w.lm_E.p);
               launches += 1;
             }
