@@ -145,6 +145,7 @@ struct Worker {
   DevBuf<SixLoState> six_lo_states;  // ... under LO-MSAC
   DevBuf<uint32_t> six_it;           // iteration number of every pair's look-ahead slot 0
   DevBuf<double> six_M;         // the ten cubics of every look-ahead sample (global scratch of k_sixpt_sample_solve)
+  DevBuf<double> small_stage;   // k_refit_small: each lane's contiguous copy of its refit's correspondences
   DevBuf<LMState> lm_states;    // stragglers handed from k_refit_small to k_refit_long
   DevBuf<int> long_list;
   DevBuf<int> six_nm, pk_id, pk_count;
@@ -160,7 +161,7 @@ struct Worker {
     states.release(); mt.release(); active0.release(); active1.release(); ident.release(); navail.release(); list_a.release();
     list_b.release(); counts.release(); parked0.release(); parked1.release(); models.release(); lm_E.release();
     s32.release(); s32m.release(); counters.release(); has.release();
-    lm_states.release(); long_list.release();
+    lm_states.release(); long_list.release(); small_stage.release();
     six_states.release(); six_lo_states.release(); six_it.release(); six_M.release(); six_nm.release(); pk_id.release(); pk_count.release(); pk_G.release();
   }
 };
@@ -566,10 +567,12 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
               // persistent lanes pulling from a queue: enough warps to fill the machine, not one per task
               SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, 2 * sizeof(int), hs));  // task queue head, straggler count
               const int blocks = std::min((ns + 63) / 64, h->num_sms * 8);
+              SSFM_WCK(w.small_stage.ensure((size_t)h->num_sms * 8 * 64 * kSmallRefit * 6));
               const bool handover = cfg.handover;
               k_refit_small<<<blocks, 64, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, w.counts.p + 6, w.states.p,
                                                    w.list_a.p, c0, w.lm_E.p, w.lm_states.p, handover ? w.long_list.p : nullptr,
-                                                   w.counts.p + 7, cfg.handover_at);
+                                                   w.counts.p + 7, cfg.handover_at,
+                                                   getenv("SSFM_NO_SMALL_STAGE") ? nullptr : w.small_stage.p);
               launches += 1;
               if (handover) {
                 SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, sizeof(int), hs));

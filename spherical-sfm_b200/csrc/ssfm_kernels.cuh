@@ -717,8 +717,12 @@ __global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params
                                                     const int* __restrict__ parked, int ntasks, int* queue_head,
                                                     const PairState* __restrict__ states, const int* __restrict__ list_a,
                                                     long long list_base, double* lm_E, LMState* __restrict__ lm_states,
-                                                    int* __restrict__ long_list, int* long_count, int handover_at) {
+                                                    int* __restrict__ long_list, int* long_count, int handover_at,
+                                                    double* __restrict__ stage /* kSmallRefit * 6 doubles per thread, or NULL */) {
   SerialCtx cx;
+  // The lane's own copy of its refit's correspondences, contiguous (L1-resident across the ~30 passes of a refit) instead of
+  // up to 32 scattered 48-byte records re-gathered through L2 on every pass.  Same values, same order: results unchanged.
+  double* mine = stage ? stage + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (kSmallRefit * 6) : (double*)0;
   const bool inward = P.inward != 0;
   int task = ntasks, a = 0, n = 0;
   bool have = false;
@@ -734,6 +738,18 @@ __global__ void __launch_bounds__(64, SSFM_REFIT_MINBLOCKS) k_refit_small(Params
         ry = rays + 6 * off;
         smp = list_a + (off - list_base);
         n = states[a].lm_n;
+        if (mine && n <= kSmallRefit) {
+          for (int i = 0; i < n; ++i) {
+            double c[6];
+            load6(ry + 6 * (size_t)smp[i], c);
+            double2* d = reinterpret_cast<double2*>(mine + 6 * i);
+            d[0] = make_double2(c[0], c[1]);
+            d[1] = make_double2(c[2], c[3]);
+            d[2] = make_double2(c[4], c[5]);
+          }
+          ry = mine;
+          smp = (const int*)0;
+        }
         double E[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) E[i] = lm_E[(size_t)a * 9 + i];
