@@ -77,8 +77,58 @@ struct DevBuf {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// Environment knobs.  They exist for measurements and tests (A/B runs of tools/gpu_*.sh, the pre-filter margin test), not
+// for users: every one of them is read in ONE place, read_knobs(), once per public call (refresh_knobs), and the rest of
+// the engine only sees this struct.
+// ---------------------------------------------------------------------------------------------------------
+struct Knobs {
+  float cand_margin = 2e-4f;   // SSFM_CAND_MARGIN      relative slack of the FP32 pre-filter
+  bool no_unitz = false;       // SSFM_NO_UNITZ         always use the general (z != 1) scoring planes
+  bool no_xy64 = false;        // SSFM_NO_XY64          exact passes stream the 48-byte records instead of the compact plane
+  bool no_small_stage = false; // SSFM_NO_SMALL_STAGE   k_refit_small gathers through L2 on every pass
+  bool no_pipeline = false;    // SSFM_NO_PIPELINE      blocking upload instead of the chunk-pipelined one
+  bool no_defer = false;       // SSFM_NO_DEFER         run the LO refits inline whatever the batch size
+  bool no_handover = false;    // SSFM_NO_HANDOVER      stragglers stay on their thread
+  int handover_at = 0;         // SSFM_HANDOVER         iterations before a small refit moves to a warp (0: kHandover)
+  int defer_min_pairs = -1;    // SSFM_DEFER_MIN_PAIRS  batches below this run the LO refits inline (-1: kDeferMinPairs)
+  int refit_threads_min = 0;   // SSFM_REFIT_THREADS_MIN
+  int sixpt_lo_r = 0;          // SSFM_SIXPT_LO_R       look-ahead of the six-point LO-MSAC path (0: adaptive)
+  int first_chunk = 2048;      // SSFM_FIRST_CHUNK      pairs in the first upload chunk
+  int round_cap = 0;           // SSFM_ROUND_CAP        look-ahead of rounds >= 1 (0: kRoundCap)
+  int first_cap = 0;           // SSFM_FIRST_CAP        look-ahead of round 0 (0: round_up32(min_num_iterations))
+  int workers = 0;             // SSFM_WORKERS          streams over the pair list (0: automatic)
+  int e2e_workers = 0;         // SSFM_E2E_WORKERS      ... while an upload is in flight
+  int e2e_parts = 0;           // SSFM_E2E_PARTS        parts dealt to those workers (0: 3 per worker)
+};
+
+static Knobs read_knobs() {
+  Knobs k;
+  auto flag = [](const char* name) { return getenv(name) != nullptr; };
+  auto num = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  if (const char* e = getenv("SSFM_CAND_MARGIN")) k.cand_margin = (float)atof(e);
+  k.no_unitz = flag("SSFM_NO_UNITZ");
+  k.no_xy64 = flag("SSFM_NO_XY64");
+  k.no_small_stage = flag("SSFM_NO_SMALL_STAGE");
+  k.no_pipeline = flag("SSFM_NO_PIPELINE");
+  k.no_defer = flag("SSFM_NO_DEFER");
+  k.no_handover = flag("SSFM_NO_HANDOVER");
+  k.handover_at = num("SSFM_HANDOVER", 0);
+  k.defer_min_pairs = num("SSFM_DEFER_MIN_PAIRS", -1);
+  k.refit_threads_min = num("SSFM_REFIT_THREADS_MIN", 0);
+  k.sixpt_lo_r = num("SSFM_SIXPT_LO_R", 0);
+  k.first_chunk = std::max(256, num("SSFM_FIRST_CHUNK", 2048));
+  k.round_cap = num("SSFM_ROUND_CAP", 0);
+  k.first_cap = num("SSFM_FIRST_CAP", 0);
+  k.workers = num("SSFM_WORKERS", 0);
+  k.e2e_workers = num("SSFM_E2E_WORKERS", 0);
+  k.e2e_parts = num("SSFM_E2E_PARTS", 0);
+  return k;
+}
+
 struct Worker;
 struct ssfm_engine {
+  Knobs knobs;  // refreshed at the top of every public call (refresh_knobs)
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
@@ -170,7 +220,11 @@ namespace {
 
 constexpr int kMaxWorkers = 4;
 
-Params make_params(const SsfmOptions& o) {
+static void refresh_knobs(ssfm_engine* h) {
+  if (h) h->knobs = read_knobs();
+}
+
+Params make_params(const SsfmOptions& o, const Knobs& knobs) {
   Params P;
   P.min_iters = o.min_num_iterations;
   P.max_iters = o.max_num_iterations;
@@ -194,8 +248,7 @@ Params make_params(const SsfmOptions& o) {
   P.preempt_block = o.preemptive_block;
   P.sixpt_focal_scoring = o.sixpt_focal_scoring;
   P.skip_complex = o.complex_root_models == SSFM_COMPLEX_SKIP;
-  P.cand_margin = 2e-4f;
-  if (const char* e = getenv("SSFM_CAND_MARGIN")) P.cand_margin = (float)atof(e);
+  P.cand_margin = knobs.cand_margin;
   P.inline_small_max = 0;
   P.inline_handover = 0;
   return P;
@@ -295,7 +348,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
         SSFM_WCK(cudaEventSynchronize(h->up_ev[k]));
         all_unit = all_unit && h->h_up_flags[k] == 0;
       }
-      unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+      unit_z = all_unit && !h->knobs.no_unitz;
     }
     if (!unit_z && (P.solver == SSFM_SOLVER_SIXPT_FOCAL || !pd.pipelined)) {
       if (int rc = ensure_general_planes(h, w.stream, c0, c1, &w.err)) return rc;
@@ -309,7 +362,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
       // same 1 GB model table.
       int r_lo = cfg.R;
       while (six_lo && r_lo > 64 && (long long)np * r_lo > 2048LL * cfg.R) r_lo >>= 1;  // only when the pass has the pairs to fill it
-      if (const char* e = getenv("SSFM_SIXPT_LO_R")) r_lo = std::max(32, std::min(cfg.R, atoi(e) & ~31));
+      if (h->knobs.sixpt_lo_r > 0) r_lo = std::max(32, std::min(cfg.R, h->knobs.sixpt_lo_r & ~31));
       const int R = six_lo ? r_lo : cfg.R;
       const int first_cap = std::min(cfg.first_cap, R), round_cap = std::min(cfg.round_cap, R);
       const int kSub = 2048 * (cfg.R / R);
@@ -514,7 +567,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
           const int q0 = std::max(h->up_bounds[k], pair0), q1 = std::min(h->up_bounds[k + 1], pair0 + np);
           if (q1 <= q0) continue;
           SSFM_WCK(cudaEventSynchronize(h->up_ev[k]));
-          const bool uz = h->h_up_flags[k] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+          const bool uz = h->h_up_flags[k] == 0 && !h->knobs.no_unitz;
           all_unit = all_unit && uz;
           if (!uz)
             if (int rc = ensure_general_planes(h, w.stream, h->h_offsets[q0], h->h_offsets[q1], &w.err)) return rc;
@@ -535,7 +588,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
       {
         ChainArgs A;
         A.rays = h->d_rays; A.offsets = h->offsets.p; A.pair0 = pair0;
-        A.xy64 = (unit_z && getenv("SSFM_NO_XY64") == nullptr) ? h->xy64.p : nullptr;
+        A.xy64 = (unit_z && !h->knobs.no_xy64) ? h->xy64.p : nullptr;
         A.navail = w.navail.p; A.states = w.states.p; A.R = R; A.models = w.models.p; A.s32 = w.s32.p; A.s32m = w.s32m.p;
         A.list_a = w.list_a.p; A.list_b = w.list_b.p; A.mt = w.mt.p; A.lm_E = w.lm_E.p; A.list_base = c0;
         A.flags = h->flags.p + c0; A.results = h->results.p + pair0; A.next_active = act_next; A.next_count = w.counts.p + 1;
@@ -572,7 +625,7 @@ int run_range(ssfm_engine* h, Worker& w, const Params& P, const RunCfg& cfg, con
               k_refit_small<<<blocks, 64, 0, hs>>>(P, h->d_rays, h->offsets.p, pair0, out, ns, w.counts.p + 6, w.states.p,
                                                    w.list_a.p, c0, w.lm_E.p, w.lm_states.p, handover ? w.long_list.p : nullptr,
                                                    w.counts.p + 7, cfg.handover_at,
-                                                   getenv("SSFM_NO_SMALL_STAGE") ? nullptr : w.small_stage.p);
+                                                   h->knobs.no_small_stage ? nullptr : w.small_stage.p);
               launches += 1;
               if (handover) {
                 SSFM_WCK(cudaMemsetAsync(w.counts.p + 6, 0, sizeof(int), hs));
@@ -756,8 +809,7 @@ void ssfm_destroy(ssfm_handle h) {
 // 16384-pair one), one event + one unit-z flag per chunk.
 static int plan_upload_chunks(ssfm_handle h) {
   h->up_bounds.clear();
-  int step = 2048;
-  if (const char* e = getenv("SSFM_FIRST_CHUNK")) step = std::max(256, atoi(e));
+  int step = h->knobs.first_chunk;
   for (int p0 = 0; p0 < h->P;) {
     h->up_bounds.push_back(p0);
     p0 += std::min(step, kPipelinePassPairs);
@@ -891,7 +943,7 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   SSFM_CK(cudaEventRecord(h->ev[5], h->stream));
   SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));  // the caller's buffer may go away after we return
-  h->unit_z = h->h_count[2] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  h->unit_z = h->h_count[2] == 0 && !h->knobs.no_unitz;
   if (!h->unit_z) {
     std::string err;
     if (int rc = ensure_general_planes(h, h->stream, 0, h->M, &err)) return fail(rc, err);
@@ -904,7 +956,10 @@ static int upload_impl(ssfm_handle h, const SsfmBatch* b, bool pipelined) {
   return SSFM_OK;
 }
 
-int ssfm_upload(ssfm_handle h, const SsfmBatch* b) { return upload_impl(h, b, false); }
+int ssfm_upload(ssfm_handle h, const SsfmBatch* b) {
+  refresh_knobs(h);
+  return upload_impl(h, b, false);
+}
 
 static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipelined) {
   if (!h || !b) return fail(SSFM_ERR_INVALID, "NULL handle or batch");
@@ -1006,7 +1061,7 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
   SSFM_CK(cudaMemcpyAsync(h->h_count + 2, h->counts.p + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   SSFM_CK(cudaStreamSynchronize(st));  // the caller's buffers may go away after we return
   if (h->h_count[3] != 0) return fail(SSFM_ERR_INVALID, "match keypoint index out of range");
-  h->unit_z = h->h_count[2] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  h->unit_z = h->h_count[2] == 0 && !h->knobs.no_unitz;
   if (!h->unit_z) {
     std::string err;
     if (int rc = ensure_general_planes(h, st, 0, M, &err)) return fail(rc, err);
@@ -1019,10 +1074,14 @@ static int upload_matches_impl(ssfm_handle h, const SsfmMatchBatch* b, bool pipe
   return SSFM_OK;
 }
 
-int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) { return upload_matches_impl(h, b, false); }
+int ssfm_upload_matches(ssfm_handle h, const SsfmMatchBatch* b) {
+  refresh_knobs(h);
+  return upload_matches_impl(h, b, false);
+}
 
 int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch, const SsfmOptions* opt,
                                      SsfmPairResult* results, uint8_t* inlier_flags) {
+  refresh_knobs(h);
   if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
   if (int rc = check_options(opt)) return rc;
   auto abandon = [h](int rc) {  // never leave copies from the caller's buffers in flight, nor a half-uploaded batch resident
@@ -1033,7 +1092,7 @@ int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch,
     h->matches_pending_check = false;
     return rc;
   };
-  if (int rc = upload_matches_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return abandon(rc);
+  if (int rc = upload_matches_impl(h, batch, !h->knobs.no_pipeline)) return abandon(rc);
   if (int rc = ssfm_run(h, opt)) return abandon(rc);
   SSFM_CK(cudaStreamSynchronize(h->stream));
   if (h->matches_pending_check) {  // the index-range flag of a pipelined upload is complete only now
@@ -1044,18 +1103,19 @@ int ssfm_estimate_pairs_from_matches(ssfm_handle h, const SsfmMatchBatch* batch,
   if (!h->up_bounds.empty()) {  // the batch is fully resident now; later ssfm_run calls use the plain plan
     bool all_unit = true;
     for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) all_unit = all_unit && h->h_up_flags[k] == 0;
-    h->unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    h->unit_z = all_unit && !h->knobs.no_unitz;
     h->up_bounds.clear();
   }
   return ssfm_download(h, results, inlier_flags);
 }
 
 int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
+  refresh_knobs(h);
   if (!h) return fail(SSFM_ERR_INVALID, "NULL handle");
   if (int rc = check_options(opt)) return rc;
   if (!h->resident) return fail(SSFM_ERR_INVALID, "ssfm_run without a resident batch (call ssfm_upload first)");
   SSFM_CK(cudaSetDevice(h->device));
-  Params P = make_params(*opt);
+  Params P = make_params(*opt, h->knobs);
   const double pack_ms = h->stats.pack_ms;
   const long long h2d = h->stats.h2d_bytes;
   h->stats = SsfmRunStats();
@@ -1073,19 +1133,19 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     cfg.first_cap = (int)std::min<uint32_t>((std::max<uint32_t>(P.min_iters, 32u) + 31u) & ~31u, 1024u);
     cfg.round_cap = kRoundCap;
   }
-  if (const char* e = getenv("SSFM_ROUND_CAP")) cfg.round_cap = (std::max(32, atoi(e)) + 31) & ~31;
-  if (const char* e = getenv("SSFM_FIRST_CAP")) cfg.first_cap = (std::max(32, atoi(e)) + 31) & ~31;
+  if (h->knobs.round_cap > 0) cfg.round_cap = (std::max(32, h->knobs.round_cap) + 31) & ~31;
+  if (h->knobs.first_cap > 0) cfg.first_cap = (std::max(32, h->knobs.first_cap) + 31) & ~31;
   cfg.R = std::max(cfg.first_cap, cfg.round_cap);
-  cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && getenv("SSFM_NO_DEFER") == nullptr;
-  cfg.handover = getenv("SSFM_NO_HANDOVER") == nullptr;
+  cfg.defer = P.driver == SSFM_DRIVER_LO_MSAC && P.num_lo_steps <= 0 && !h->knobs.no_defer;
+  cfg.handover = !h->knobs.no_handover;
   cfg.handover_at = kHandover;
-  if (const char* e = getenv("SSFM_HANDOVER")) cfg.handover_at = std::max(1, atoi(e));
+  if (h->knobs.handover_at > 0) cfg.handover_at = h->knobs.handover_at;
   if (cfg.defer) {
     // Parking refits pays when a wave holds thousands of them; below that a wave is a host round trip for a handful of
     // threads (one C1-sized pair: five waves = 1.0 of its 1.27 ms).  Small batches run the same refits inline, with the
     // deferred path's arithmetic (Params::inline_small_max), so the table does not depend on the batch size.
     int defer_min = kDeferMinPairs;
-    if (const char* e = getenv("SSFM_DEFER_MIN_PAIRS")) defer_min = atoi(e);
+    if (h->knobs.defer_min_pairs >= 0) defer_min = h->knobs.defer_min_pairs;
     if (h->P < defer_min) {
       cfg.defer = false;
       P.inline_small_max = kSmallRefit;
@@ -1096,15 +1156,15 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
   // 0: every small refit is solved one thread per problem.  (A warp-per-refit path for thin waves has lower
   // latency but sums in a different order, which would make results depend on how many pairs share a wave.)
   cfg.small_refit_threads_min = 0;
-  if (const char* e = getenv("SSFM_REFIT_THREADS_MIN")) cfg.small_refit_threads_min = atoi(e);
+  cfg.small_refit_threads_min = h->knobs.refit_threads_min;
 
   // Pass lists per worker: contiguous ranges balanced by correspondence count.
   // Resident batch: one stream (a second one gains ~1 %).  While the upload is still streaming in
   // (ssfm_estimate_pairs), three streams over six interleaved parts (measured: 456 -> 440 ms end to end).
   int nw = (!h->up_bounds.empty() && h->P >= 4096) ? 3 : 1;
-  if (const char* e = getenv("SSFM_WORKERS")) nw = std::max(1, std::min(kMaxWorkers, atoi(e)));
+  if (h->knobs.workers > 0) nw = std::min(kMaxWorkers, h->knobs.workers);
   if (!h->up_bounds.empty())
-    if (const char* e = getenv("SSFM_E2E_WORKERS")) nw = std::max(1, std::min(kMaxWorkers, atoi(e)));
+    if (h->knobs.e2e_workers > 0) nw = std::min(kMaxWorkers, h->knobs.e2e_workers);
   nw = std::max(1, std::min(nw, std::max(h->P, 1)));
   std::vector<std::vector<PassDesc>> plan(nw);
   {
@@ -1115,7 +1175,7 @@ int ssfm_run(ssfm_handle h, const SsfmOptions* opt) {
     int nparts = nw;
     if (pipelined && nw > 1) {
       nparts = 3 * nw;
-      if (const char* e = getenv("SSFM_E2E_PARTS")) nparts = std::max(nw, atoi(e));
+      if (h->knobs.e2e_parts > 0) nparts = std::max(nw, h->knobs.e2e_parts);
     }
     std::vector<int> bounds(nparts + 1, 0);
     bounds[nparts] = h->P;
@@ -1207,6 +1267,7 @@ int ssfm_device_results(ssfm_handle h, void** dev_ptr, int32_t* num_pairs) {
 
 int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions* opt, SsfmPairResult* results,
                         uint8_t* inlier_flags) {
+  refresh_knobs(h);
   if (!results) return fail(SSFM_ERR_INVALID, "results is NULL");
   if (int rc = check_options(opt)) return rc;
   auto abandon = [h](int rc) {  // never leave copies from the caller's buffer in flight, nor a half-uploaded batch resident
@@ -1216,13 +1277,13 @@ int ssfm_estimate_pairs(ssfm_handle h, const SsfmBatch* batch, const SsfmOptions
     h->have_results = false;
     return rc;
   };
-  if (int rc = upload_impl(h, batch, getenv("SSFM_NO_PIPELINE") == nullptr)) return abandon(rc);
+  if (int rc = upload_impl(h, batch, !h->knobs.no_pipeline)) return abandon(rc);
   if (int rc = ssfm_run(h, opt)) return abandon(rc);
   SSFM_CK(cudaStreamSynchronize(h->stream));
   if (!h->up_bounds.empty()) {  // the batch is fully resident now; later ssfm_run calls use the plain plan
     bool all_unit = true;
     for (size_t k = 0; k + 1 < h->up_bounds.size(); ++k) all_unit = all_unit && h->h_up_flags[k] == 0;
-    h->unit_z = all_unit && getenv("SSFM_NO_UNITZ") == nullptr;
+    h->unit_z = all_unit && !h->knobs.no_unitz;
     h->up_bounds.clear();
   }
   if (int rc = ssfm_download(h, results, inlier_flags)) return rc;
@@ -1253,7 +1314,7 @@ int ssfm_retriangulate(ssfm_handle h, const SsfmTrackBatch* b, const SsfmOptions
   for (long long i = 0; i < M; ++i)
     if (b->obs_camera[i] < 0 || b->obs_camera[i] >= b->num_cameras) return fail(SSFM_ERR_INVALID, "ssfm_retriangulate: camera index out of range");
   SSFM_CK(cudaSetDevice(h->device));
-  Params P = make_params(*opt);
+  Params P = make_params(*opt, h->knobs);
   DevBuf<tri::Cam> cams;
   DevBuf<double> d_tr, d_xy, d_pts;
   DevBuf<long long> d_off;
@@ -1441,6 +1502,7 @@ int ssfm_score(ssfm_handle h, const double* models6, int32_t M, const double* ra
 int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const double* rays, const int64_t* offsets, int32_t num_pairs,
                      double thr2, float* scores, int32_t* counts, float* kernel_ms) {
   if (!h || !models6 || !rays || !offsets || !scores || !counts || M < 0 || num_pairs < 0) return fail(SSFM_ERR_INVALID, "bad argument");
+  refresh_knobs(h);
   if (M == 0 || num_pairs == 0) return SSFM_OK;
   if (offsets[0] != 0) return fail(SSFM_ERR_INVALID, "offsets[0] must be 0");
   long long nmax = 0;
@@ -1480,7 +1542,7 @@ int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const doub
   if (n > 0) k_pack<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, duv, (double*)nullptr, dflag);
   SSFM_CK(cudaMemcpyAsync(h->h_count + 3, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   SSFM_CK(cudaStreamSynchronize(h->stream));
-  const bool unit_z = h->h_count[3] == 0 && getenv("SSFM_NO_UNITZ") == nullptr;
+  const bool unit_z = h->h_count[3] == 0 && !h->knobs.no_unitz;
   if (!unit_z && n > 0) k_pack_general<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, du, dv);
   // warm-up launch (untimed), then the timed one
   for (int rep = 0; rep < 2; ++rep) {
