@@ -313,6 +313,9 @@ __device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, 
   bool gate[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) gate[g] = __any_sync(0xffffffffu, m8[g] < st.a1);
+  // the threshold only decreases: once every row of the warp is in the near regime (second neighbour below 2^22) it stays
+  // there, and the per-group far-regime vote below is not needed any more
+  const bool all_near = __all_sync(0xffffffffu, st.a1 < far_a);
 #if SSFM_MATCH_DIAG == 1
 #pragma unroll
   for (int g = 0; g < 4; ++g) st.a1 = fminf(st.a1, gate[g] ? m8[g] : st.a1);
@@ -325,7 +328,7 @@ __device__ __forceinline__ void top2_scan32(Top2& st, const float* x, int idx0, 
       for (int h = 2 * g; h < 2 * g + 2; ++h) {
         const bool hit = m4[h] < st.a1;
         if (__any_sync(0xffffffffu, hit)) {
-          if (__any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
+          if (!all_near && __any_sync(0xffffffffu, hit && !(st.a1 < far_a)))
             st = top2_group_far(st, x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3], qn, idx0 + 4 * h);
           else
             top2_group(st, x + 4 * h, idx0 + 4 * h);
