@@ -223,6 +223,32 @@ def test_float32_ray_input_equals_float64_input_of_the_same_values(S, engine):
     assert a.tobytes() == b.tobytes() and (fa == fb).all() and (a["status"] == 0).mean() > 0.9
 
 
+def test_device_resident_rays_both_formats(S, engine):
+    """SsfmBatch.rays_on_device: rays already in HBM (float64 records, or float32 with SSFM_RAYS_F32) give the table of the
+    host call byte for byte; a device pointer that is not aligned for the vector loads is refused, not dereferenced."""
+    import torch
+    P, N = 500, 160
+    rays, offsets, _ = S.problems.make_batch(43, P, N, noise=1.0 / 600, outlier_frac=0.4, max_angle_deg=20.0)
+    r32 = rays.astype(np.float32)
+    r64 = r32.astype(np.float64)
+    opt = S.pipeline_options(THR2)
+    want, want_flags = engine.estimate_pairs(r64, offsets, opt)
+    d64 = torch.from_numpy(r64).cuda()
+    engine.upload(None, offsets, device_ptr=d64.data_ptr())
+    engine.run(opt)
+    got, got_flags = engine.download()
+    assert got.tobytes() == want.tobytes() and (got_flags == want_flags).all()
+    d32 = torch.from_numpy(r32).cuda()
+    engine.upload(None, offsets, device_ptr=d32.data_ptr(), device_format=S.RAYS_F32)
+    engine.run(opt)
+    got, got_flags = engine.download()
+    assert got.tobytes() == want.tobytes() and (got_flags == want_flags).all()
+    pad = torch.zeros(r64.size + 1, dtype=torch.float64, device="cuda")
+    pad[1:] = d64.reshape(-1)
+    with pytest.raises(S.SsfmError):
+        engine.upload(None, offsets, device_ptr=pad.data_ptr() + 8)  # 8-byte aligned only: the records are read as double2
+
+
 def test_default_lo_options(S, O, engine, orc, ref):
     """RansacLib's default LO schedule (10 LO steps x 4 LSQ iterations, NonMinimalSolver)."""
     _compare_batch(S, O, engine, ref if ref is not None else orc, S.default_options(squared_inlier_threshold=THR2), 8, 600, 0.5, 5)
