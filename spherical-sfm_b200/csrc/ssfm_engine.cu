@@ -1523,18 +1523,6 @@ int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const doub
   SSFM_TMP(int, b_flag, 1) SSFM_KEEP(g, b_flag)
   SSFM_TMP(long long, b_off, (size_t)num_pairs + 1) SSFM_KEEP(g, b_off)
   float4* duv = (float4*)g.ptrs[4]; int* dflag = (int*)g.ptrs[5]; long long* doff = (long long*)g.ptrs[6];
-  // correspondences of every pair are split into chunks (multiples of the tile) so that the grid fills the machine
-  const int gx = (M + 4 * kScoreThreads - 1) / (4 * kScoreThreads);
-  const int max_chunks = (int)std::max<long long>(1, (nmax + kTile - 1) / kTile);
-  int nchunks = std::min(max_chunks, std::max(1, (4 * h->num_sms * 2 + gx * num_pairs - 1) / (gx * num_pairs)));
-  int chunk = (int)(((nmax + nchunks - 1) / nchunks + kTile - 1) / kTile * kTile);
-  if (chunk <= 0) chunk = kTile;
-  nchunks = (int)std::max<long long>(1, (nmax + chunk - 1) / chunk);
-  SSFM_TMP(float, b_ps, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_ps)
-  SSFM_TMP(int, b_pc, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_pc)
-  SSFM_TMP(float, b_s, (size_t)num_pairs * M) SSFM_KEEP(g, b_s)
-  SSFM_TMP(int, b_c, (size_t)num_pairs * M) SSFM_KEEP(g, b_c)
-  float* ps = (float*)g.ptrs[7]; int* pc = (int*)g.ptrs[8]; float* ds = (float*)g.ptrs[9]; int* dc = (int*)g.ptrs[10];
   if (n > 0) SSFM_CK(cudaMemcpyAsync(dr, rays, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(dm, models6, sizeof(double) * 6 * (size_t)M * num_pairs, cudaMemcpyHostToDevice, h->stream));
   SSFM_CK(cudaMemcpyAsync(doff, offsets, sizeof(long long) * ((size_t)num_pairs + 1), cudaMemcpyHostToDevice, h->stream));
@@ -1544,6 +1532,26 @@ int ssfm_score_pairs(ssfm_handle h, const double* models6, int32_t M, const doub
   SSFM_CK(cudaStreamSynchronize(h->stream));
   const bool unit_z = h->h_count[3] == 0 && !h->knobs.no_unitz;
   if (!unit_z && n > 0) k_pack_general<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(dr, n, du, dv);
+  // Correspondences of every pair are split into chunks (multiples of the tile) so that the grid is ONE full wave of CTAs:
+  // gx * num_pairs CTAs per chunk layer, as many layers as fit the resident-CTA slots (rounded DOWN: a 19th layer on 18.5
+  // layers' worth of slots would run as a second, almost empty wave and double the launch's duration).
+  const int gx = (M + 4 * kScoreThreads - 1) / (4 * kScoreThreads);
+  const int max_chunks = (int)std::max<long long>(1, (nmax + kTile - 1) / kTile);
+  int per_sm = 8;
+  if (unit_z) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_models<true>, kScoreThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_score_models<false>, kScoreThreads, 0);
+  const long long slots = (long long)std::max(per_sm, 1) * h->num_sms, layer = (long long)gx * num_pairs;
+  int nchunks = (int)std::min<long long>(max_chunks, std::max<long long>(1, slots / layer));
+  // chunk starts only need the 16-byte alignment of the bulk copies (one float4 per correspondence): a multiple of 64 keeps
+  // the split even for small pairs, where whole 512-correspondence tiles would leave half the machine idle
+  int chunk = (int)(((nmax + nchunks - 1) / nchunks + 63) / 64 * 64);
+  if (chunk <= 0) chunk = 64;
+  nchunks = (int)std::max<long long>(1, (nmax + chunk - 1) / chunk);
+  SSFM_TMP(float, b_ps, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_ps)
+  SSFM_TMP(int, b_pc, (size_t)num_pairs * nchunks * M) SSFM_KEEP(g, b_pc)
+  SSFM_TMP(float, b_s, (size_t)num_pairs * M) SSFM_KEEP(g, b_s)
+  SSFM_TMP(int, b_c, (size_t)num_pairs * M) SSFM_KEEP(g, b_c)
+  float* ps = (float*)g.ptrs[7]; int* pc = (int*)g.ptrs[8]; float* ds = (float*)g.ptrs[9]; int* dc = (int*)g.ptrs[10];
   // warm-up launch (untimed), then the timed one
   for (int rep = 0; rep < 2; ++rep) {
     if (rep == 1) SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
