@@ -272,8 +272,11 @@ int check_options(const SsfmOptions* o) {
 
 template <int KIND>
 void launch_solve(ssfm_engine* h, Worker& w, const Params& P, int pair0, const int* active, int count, int cap, int R) {
-  dim3 grid(count, (cap + kSolveThreads - 1) / kSolveThreads);
-  k_sample_solve<KIND><<<grid, kSolveThreads, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, active, w.navail.p, w.states.p, R,
+  // a 32-slot round (the fixed-budget legacy driver) would leave half of every 64-thread block idle and, with the block count
+  // fixed by the pair count, cost extra waves: one warp per block there
+  const int threads = (cap <= 32 && SSFM_SOLVE_SYNC == 0) ? 32 : kSolveThreads;
+  dim3 grid(count, (cap + threads - 1) / threads);
+  k_sample_solve<KIND><<<grid, threads, 0, w.stream>>>(P, h->d_rays, h->offsets.p, pair0, active, w.navail.p, w.states.p, R,
                                                   w.models.p);
 }
 
