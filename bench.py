@@ -320,7 +320,9 @@ def matching_block(S, eng, args, ni=64, n=4000):
         keep = rng.random(n) < 0.4
         d[keep] = np.clip(base[keep] + rng.integers(-2, 3, (int(keep.sum()), 128)), 0, 255)
         descs.append(d.astype(np.float32))
-    allrows = np.concatenate(descs)
+    import torch
+    allrows_t = torch.from_numpy(np.concatenate(descs)).pin_memory()  # host buffers are pinned, as for the headline e2e
+    allrows = allrows_t.numpy()
     offs = (np.arange(ni + 1) * n).astype(np.int64)
     pairs = np.array([(i, j) for i in range(ni) for j in range(i + 1, ni)], np.int32)
     eng.match_pairs(allrows, offs, pairs[:64])

@@ -308,7 +308,7 @@ class Engine:
         cap = int(np.minimum(n[pi[:, 0]], n[pi[:, 1]]).sum()) if len(pi) else 0
         b = SsfmDescriptorBatch(len(do) - 1, 128, _p(do, C.c_int64), _p(d, C.c_float), len(pi), _p(pi, C.c_int32), float(ratio))
         offs = np.zeros(len(pi) + 1, np.int64)
-        out = np.zeros((max(cap, 1), 2), np.int32)
+        out = np.empty((max(cap, 1), 2), np.int32)  # capacity, not content: only the first offs[-1] rows are written and returned
         _check(lib().ssfm_match_pairs(self._h, C.byref(b), _p(offs, C.c_int64), _p(out, C.c_int32), C.c_int64(cap)))
         return offs, out[:int(offs[-1])]
 
