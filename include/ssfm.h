@@ -48,8 +48,9 @@ enum {
   SSFM_SOLVER_FAST_STURM = 2,    /* SphericalFastEstimator::compute, src/spherical_fast_estimator.cpp:44-257 */
   SSFM_SOLVER_SIXPT_FOCAL = 3    /* SixPointEstimator (examples/six_point_estimator.{h,cpp}): six-point shared-focal
                                     relative pose, <= 15 models {t, r, focal} per sample, min_sample_size 6.  Rays are
-                                    (x - cx, y - cy, 1) in pixel units.  Batched driver: SSFM_DRIVER_VANILLA_MSAC (config C4);
-                                    the whole estimator concept is exposed through the hooks ssfm_sixpt_solve,
+                                    (x - cx, y - cy, 1) in pixel units.  Batched drivers: SSFM_DRIVER_VANILLA_MSAC (config C4) and
+                                    SSFM_DRIVER_LO_MSAC (LocallyOptimizedMSAC with the estimator's NonMinimalSolver :121-144 and
+                                    LeastSquares :146-192); the whole estimator concept is also exposed through the hooks ssfm_sixpt_solve,
                                     ssfm_score_exact and ssfm_sixpt_least_squares.
                                     SsfmPairResult.E is the matrix the estimator scores with, r/t/focal the model. */
 };
