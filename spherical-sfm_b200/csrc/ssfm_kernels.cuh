@@ -401,6 +401,26 @@ __device__ __forceinline__ void sampson2_unitz(const f32x2 (&P)[7], f32x2 X, f32
   d2 = mul2(d, d);
 }
 
+// The same, with the v-side half of the denominator expanded: for E = [p0 p1 p2; p1 -p0 p3; p4 p5 0]
+//   (E^T v)_0^2 + (E^T v)_1^2 = (p0^2 + p1^2)(z^2 + w^2) + 2 (p0 p4 + p1 p5) z + 2 (p1 p4 - p0 p5) w + (p4^2 + p5^2),
+// four per-model constants Q (computed once per thread) and one per-correspondence z^2 + w^2 shared by the thread's four
+// models: 3 FMA for that half instead of 6 (the two products themselves are not needed by anything else), 16 FMA-pipe
+// instructions per evaluation pair instead of 19.  The u-side half stays a sum of squares because d needs E u anyway.
+// This is the FP32 pre-filter (and config C5's FP32 score): the float64 certification is untouched.
+#ifndef SSFM_SCORE_EXPANDED
+#define SSFM_SCORE_EXPANDED 1
+#endif
+__device__ __forceinline__ void sampson2_unitz_expanded(const f32x2 (&P)[7], const f32x2 (&Q)[4], f32x2 X, f32x2 Y, f32x2 Z, f32x2 W,
+                                                        f32x2 T, f32x2& d2, f32x2& den) {
+  const f32x2 Eu0 = fma2(P[1], Y, fma2(P[0], X, P[2]));
+  const f32x2 Eu1 = fma2(P[6], Y, fma2(P[1], X, P[3]));
+  const f32x2 Eu2 = fma2(P[5], Y, mul2(P[4], X));
+  const f32x2 d = fma2(W, Eu1, fma2(Z, Eu0, Eu2));
+  const f32x2 denT = fma2(Q[0], T, fma2(Q[1], Z, fma2(Q[2], W, Q[3])));
+  den = fma2(Eu1, Eu1, fma2(Eu0, Eu0, denT));
+  d2 = mul2(d, d);
+}
+
 // Streams correspondences [c0, c1) of one pair through shared memory and accumulates the MSAC
 // cost (and optionally the inlier count) of the calling thread's four models.  Warps whose lanes
 // are all idle (`active` false) only take part in the barriers.  Partial sums are folded per tile
@@ -425,6 +445,23 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
 #pragma unroll
     for (int i = 0; i < 6; ++i) P2[h][i] = pack2(p[2 * h][i], p[2 * h + 1][i]);
     P2[h][6] = pack2(-p[2 * h][0], -p[2 * h + 1][0]);
+  }
+  f32x2 Q2[2][4];
+  if (UNITZ && kPackedScoring && SSFM_SCORE_EXPANDED) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float q[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float* m = p[2 * h + k];
+        q[k][0] = m[0] * m[0] + m[1] * m[1];
+        q[k][1] = 2.f * (m[0] * m[4] + m[1] * m[5]);
+        q[k][2] = 2.f * (m[1] * m[4] - m[0] * m[5]);
+        q[k][3] = m[4] * m[4] + m[5] * m[5];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) Q2[h][i] = pack2(q[0][i], q[1][i]);
+    }
   }
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -456,10 +493,18 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
         for (int i = 0; i < n; ++i) {
           const float4 ca = sa[i];
           const f32x2 X = pack2(ca.x, ca.x), Y = pack2(ca.y, ca.y), Z = pack2(ca.z, ca.z), W = pack2(ca.w, ca.w);
+#if SSFM_SCORE_EXPANDED
+          const float tt = fmaf(ca.w, ca.w, ca.z * ca.z);
+          const f32x2 T = pack2(tt, tt);
+#endif
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             f32x2 d2, den;
+#if SSFM_SCORE_EXPANDED
+            sampson2_unitz_expanded(P2[h], Q2[h], X, Y, Z, W, T, d2, den);
+#else
             sampson2_unitz(P2[h], X, Y, Z, W, d2, den);
+#endif
             float dl, dh;
             unpack2(den, dl, dh);
             const f32x2 e2 = mul2(d2, pack2(rcp_ftz(dl), rcp_ftz(dh)));

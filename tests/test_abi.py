@@ -161,5 +161,8 @@ def test_bench_product_arm_contract_small():
     assert line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1 and line["gpu_launches"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and 0 < line["e2e"]["value"] < line["value"] * 1.05
     rf = line["roofline"]
-    assert rf["bound"] == "fp32" and 0.3 < rf["frac"] < 1.0 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    # `frac` is ALGORITHMIC flops (42 per evaluation) over peak and may pass 1 because the kernel executes fewer;
+    # what the FMA pipe really does is in `executed` and can never pass 1
+    assert rf["bound"] == "fp32" and 0.3 < rf["frac"] < 1.25 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 0.2 < rf["executed"]["fma_pipe_frac"] < 1.0 and rf["executed"]["flop_per_eval"] < rf["flop_per_eval"]
     assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
