@@ -35,10 +35,11 @@ sys.path.insert(0, ROOT)
 THR2 = (2.0 / 600.0) ** 2
 FLOP_PER_EVAL = 42.0  # generic 3x3 E Sampson evaluation
 # what k_score_rounds<unit-z> executes on the FMA pipe per evaluation (profiles/r02_score_kernel.sass): per PAIR of evaluations
-# 12 FFMA2 (4 flop) + 3 FMUL2 + 1 FADD2 (2 flop) = 56 flop, + (FMUL + FFMA) once per correspondence for the thread's 4 models
-EXEC_FLOP_PER_EVAL = 56.0 / 2 + 3.0 / 4
-# FMA-pipe issue slots in scalar-FMA equivalents (a packed instruction occupies the pipe for two): 16 packed x 2 / 2 + 2 / 4
-EXEC_FMA_SLOTS_PER_EVAL = 16.0 + 0.5
+# 10 FFMA2 (4 flop) + 3 FMUL2 + 1 FADD2 (2 flop) = 48 flop; the model-independent products of a correspondence (7 flop) are
+# computed once per 128-thread block, i.e. 7 / 512 per evaluation
+EXEC_FLOP_PER_EVAL = 48.0 / 2 + 7.0 / 512
+# FMA-pipe issue slots in scalar-FMA equivalents (a packed instruction occupies the pipe for two): 14 packed x 2 / 2
+EXEC_FMA_SLOTS_PER_EVAL = 14.0 + 7.0 / 512
 C3_PAIRS, C3_CORR, C3_OUTLIERS = 124750, 1500, 0.7
 
 
@@ -631,9 +632,9 @@ def main():
                      "evals_per_sec_in_kernel": evals_per_launch / (score_ms_per_launch * 1e-3),
                      # `achieved` / `frac` follow the contract: ALGORITHMIC flops (SURVEY 8(d)'s 42 per evaluation of a generic 3x3
                      # E) over the measured duration.  The kernel executes fewer: the spherical E has 6 free parameters, z == 1, and
-                     # half of the Sampson denominator is expanded into per-model constants, so `frac` can
+                     # the bilinear forms are expanded over per-model constants and per-correspondence products, so `frac` can
                      # exceed 1.  The executed figures below are what the FMA pipe actually does (from the SASS under profiles/:
-                     # 12 FFMA2 + 3 FMUL2 + 1 FADD2 per pair of evaluations, + z^2 + w^2 once per correspondence and thread).
+                     # 10 FFMA2 + 3 FMUL2 + 1 FADD2 per pair of evaluations; the per-correspondence products once per block).
                      "executed": {"flop_per_eval": EXEC_FLOP_PER_EVAL,
                                   "tflops": evals_per_launch * EXEC_FLOP_PER_EVAL / (score_ms_per_launch * 1e-3) / 1e12,
                                   "fma_pipe_slots_per_eval": EXEC_FMA_SLOTS_PER_EVAL,

@@ -296,10 +296,15 @@ constexpr bool kPackedScoring = SSFM_PACKED_SCORING != 0;  // unit-z scoring loo
 // UNITZ = every ray of the batch has z == 1 exactly (the pipeline's K^-1 (x,y,1) rays and the
 // reference's generator): one float4 (u0,u1,v0,v1) per correspondence and 19 FMA-pipe ops per
 // evaluation; otherwise two float4 (u.xyz, v.xyz) and 24.
+#ifndef SSFM_SCORE_EXPANDED
+#define SSFM_SCORE_EXPANDED 2  // unit-z packed loop: 0 = plain, 1 = v-side denominator expanded, 2 = d and the whole denominator
+#endif                         // expanded over per-correspondence products computed once per tile (score_stream)
+constexpr bool kScoreDerived = SSFM_SCORE_EXPANDED == 2 && kPackedScoring;
 template <bool UNITZ>
 struct ScoreSmem {
   float4 a[kStages][kTile];
-  float4 b[UNITZ ? 1 : kStages][UNITZ ? 1 : kTile];
+  // general rays: the v plane.  Unit-z with kScoreDerived: the tile's derived plane (zx - wy, zy + wx, x^2+y^2+z^2+w^2, -)
+  float4 b[(UNITZ && !kScoreDerived) ? 1 : kStages][(UNITZ && !kScoreDerived) ? 1 : kTile];
   unsigned long long bar[kStages];
 };
 
@@ -407,9 +412,6 @@ __device__ __forceinline__ void sampson2_unitz(const f32x2 (&P)[7], f32x2 X, f32
 // models: 3 FMA for that half instead of 6 (the two products themselves are not needed by anything else), 16 FMA-pipe
 // instructions per evaluation pair instead of 19.  The u-side half stays a sum of squares because d needs E u anyway.
 // This is the FP32 pre-filter (and config C5's FP32 score): the float64 certification is untouched.
-#ifndef SSFM_SCORE_EXPANDED
-#define SSFM_SCORE_EXPANDED 1
-#endif
 __device__ __forceinline__ void sampson2_unitz_expanded(const f32x2 (&P)[7], const f32x2 (&Q)[4], f32x2 X, f32x2 Y, f32x2 Z, f32x2 W,
                                                         f32x2 T, f32x2& d2, f32x2& den) {
   const f32x2 Eu0 = fma2(P[1], Y, fma2(P[0], X, P[2]));
@@ -418,6 +420,21 @@ __device__ __forceinline__ void sampson2_unitz_expanded(const f32x2 (&P)[7], con
   const f32x2 d = fma2(W, Eu1, fma2(Z, Eu0, Eu2));
   const f32x2 denT = fma2(Q[0], T, fma2(Q[1], Z, fma2(Q[2], W, Q[3])));
   den = fma2(Eu1, Eu1, fma2(Eu0, Eu0, denT));
+  d2 = mul2(d, d);
+}
+
+// Everything bilinear expanded.  With u = (x, y, 1), v = (z, w, 1) and E as above
+//   d   = v^T E u = p0 (zx - wy) + p1 (zy + wx) + p2 z + p3 w + p4 x + p5 y
+//   den = (p0^2 + p1^2)(x^2 + y^2 + z^2 + w^2) + 2 (p0 p2 + p1 p3) x + 2 (p1 p2 - p0 p3) y + 2 (p0 p4 + p1 p5) z
+//         + 2 (p1 p4 - p0 p5) w + (p2^2 + p3^2 + p4^2 + p5^2)
+// The three per-correspondence products (zx - wy, zy + wx, x^2 + y^2 + z^2 + w^2) do not depend on the model: they are computed
+// ONCE per tile by the block (four correspondences per thread) into a second shared-memory plane, so an evaluation pair is
+// 10 FFMA2 + 3 FMUL2 + 1 FADD2 = 14 FMA-pipe instructions (19 for the plain form, 16 with only the v side expanded).
+// Q = (A, Bu, Cu, Bt, Ct, D) per model pair.
+__device__ __forceinline__ void sampson2_unitz_bilinear(const f32x2 (&P)[7], const f32x2 (&Q)[6], f32x2 X, f32x2 Y, f32x2 Z, f32x2 W,
+                                                        f32x2 ZXWY, f32x2 ZYWX, f32x2 ST, f32x2& d2, f32x2& den) {
+  const f32x2 d = fma2(P[0], ZXWY, fma2(P[1], ZYWX, fma2(P[2], Z, fma2(P[3], W, fma2(P[4], X, mul2(P[5], Y))))));
+  den = fma2(Q[0], ST, fma2(Q[1], X, fma2(Q[2], Y, fma2(Q[3], Z, fma2(Q[4], W, Q[5])))));
   d2 = mul2(d, d);
 }
 
@@ -446,21 +463,30 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
     for (int i = 0; i < 6; ++i) P2[h][i] = pack2(p[2 * h][i], p[2 * h + 1][i]);
     P2[h][6] = pack2(-p[2 * h][0], -p[2 * h + 1][0]);
   }
-  f32x2 Q2[2][4];
+  f32x2 Q2[2][6];
   if (UNITZ && kPackedScoring && SSFM_SCORE_EXPANDED) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float q[2][4];
+      float q[2][6];
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const float* m = p[2 * h + k];
-        q[k][0] = m[0] * m[0] + m[1] * m[1];
-        q[k][1] = 2.f * (m[0] * m[4] + m[1] * m[5]);
-        q[k][2] = 2.f * (m[1] * m[4] - m[0] * m[5]);
-        q[k][3] = m[4] * m[4] + m[5] * m[5];
+        const float A = m[0] * m[0] + m[1] * m[1];
+        const float Bt = 2.f * (m[0] * m[4] + m[1] * m[5]), Ct = 2.f * (m[1] * m[4] - m[0] * m[5]);
+        const float Dt = m[4] * m[4] + m[5] * m[5];
+        if (SSFM_SCORE_EXPANDED == 2) {
+          q[k][0] = A;
+          q[k][1] = 2.f * (m[0] * m[2] + m[1] * m[3]);
+          q[k][2] = 2.f * (m[1] * m[2] - m[0] * m[3]);
+          q[k][3] = Bt;
+          q[k][4] = Ct;
+          q[k][5] = (m[2] * m[2] + m[3] * m[3]) + Dt;
+        } else {
+          q[k][0] = A; q[k][1] = Bt; q[k][2] = Ct; q[k][3] = Dt; q[k][4] = 0.f; q[k][5] = 0.f;
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) Q2[h][i] = pack2(q[0][i], q[1][i]);
+      for (int i = 0; i < 6; ++i) Q2[h][i] = pack2(q[0][i], q[1][i]);
     }
   }
   if (threadIdx.x == 0) {
@@ -482,26 +508,44 @@ __device__ __forceinline__ void score_stream(ScoreSmem<UNITZ>& sm, const float4*
   for (int t = 0; t < ntiles; ++t) {
     const int s = t % kStages;
     mbar_wait(&sm.bar[s], (uint32_t)((t / kStages) & 1));
+    if (UNITZ && kScoreDerived) {  // the tile's model-independent products, once per block (every warp takes part)
+      const long long b0 = c0 + (long long)t * kTile;
+      const int nt = (int)((c1 - b0) < kTile ? (c1 - b0) : kTile);
+      for (int i = threadIdx.x; i < nt; i += kScoreThreads) {
+        const float4 ca = sm.a[s][i];
+        sm.b[s][i] = make_float4(fmaf(ca.z, ca.x, -ca.w * ca.y), fmaf(ca.z, ca.y, ca.w * ca.x),
+                                 fmaf(ca.w, ca.w, fmaf(ca.z, ca.z, fmaf(ca.y, ca.y, ca.x * ca.x))), 0.f);
+      }
+      __syncthreads();
+    }
     if (active) {
       const long long b = c0 + (long long)t * kTile;
       const int n = (int)((c1 - b) < kTile ? (c1 - b) : kTile);
       const float4* sa = sm.a[s];
-      const float4* sb = sm.b[UNITZ ? 0 : s];
+      const float4* sb = sm.b[(UNITZ && !kScoreDerived) ? 0 : s];
       if (UNITZ && kPackedScoring) {
         f32x2 tacc2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
 #pragma unroll 8
         for (int i = 0; i < n; ++i) {
           const float4 ca = sa[i];
           const f32x2 X = pack2(ca.x, ca.x), Y = pack2(ca.y, ca.y), Z = pack2(ca.z, ca.z), W = pack2(ca.w, ca.w);
-#if SSFM_SCORE_EXPANDED
+#if SSFM_SCORE_EXPANDED == 2
+          const float4 cd = sb[i];
+          const f32x2 ZXWY = pack2(cd.x, cd.x), ZYWX = pack2(cd.y, cd.y), ST = pack2(cd.z, cd.z);
+#elif SSFM_SCORE_EXPANDED == 1
           const float tt = fmaf(ca.w, ca.w, ca.z * ca.z);
           const f32x2 T = pack2(tt, tt);
 #endif
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             f32x2 d2, den;
-#if SSFM_SCORE_EXPANDED
-            sampson2_unitz_expanded(P2[h], Q2[h], X, Y, Z, W, T, d2, den);
+#if SSFM_SCORE_EXPANDED == 2
+            sampson2_unitz_bilinear(P2[h], Q2[h], X, Y, Z, W, ZXWY, ZYWX, ST, d2, den);
+#elif SSFM_SCORE_EXPANDED == 1
+            {
+              const f32x2 Q4[4] = {Q2[h][0], Q2[h][1], Q2[h][2], Q2[h][3]};
+              sampson2_unitz_expanded(P2[h], Q4, X, Y, Z, W, T, d2, den);
+            }
 #else
             sampson2_unitz(P2[h], X, Y, Z, W, d2, den);
 #endif
