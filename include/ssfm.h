@@ -342,7 +342,9 @@ int ssfm_sixpt_least_squares(ssfm_handle h, const double* rays, int32_t n, const
 int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t* sizes, const int32_t* targets,
                     int32_t* out);
 
-/* Peak-FP32 microbenchmark (FFMA chains on every SM) used as the roofline denominator. */
+/* Peak-FP32 microbenchmarks used as the roofline denominator: independent FFMA chains on every SM, once with the scalar
+ * instruction and once with the packed one (fma.rn.f32x2 -> FFMA2).  ssfm_measure_fp32_peak returns the higher of the two. */
+int ssfm_measure_fp32_peaks(ssfm_handle h, double* scalar_tflops, double* packed_tflops);
 int ssfm_measure_fp32_peak(ssfm_handle h, double* tflops);
 
 #ifdef __cplusplus

@@ -157,7 +157,7 @@ EXPORTED_SYMBOLS = [
     "ssfm_abi_version", "ssfm_last_error", "ssfm_default_options", "ssfm_create", "ssfm_destroy",
     "ssfm_estimate_pairs", "ssfm_upload_matches", "ssfm_estimate_pairs_from_matches", "ssfm_upload", "ssfm_run", "ssfm_download", "ssfm_get_stats", "ssfm_device_results",
     "ssfm_sample", "ssfm_selection_sample", "ssfm_sixpt_solve", "ssfm_sixpt_least_squares", "ssfm_retriangulate", "ssfm_minimal_solve", "ssfm_minimal_solve_opt", "ssfm_score", "ssfm_score_pairs", "ssfm_score_exact", "ssfm_least_squares", "ssfm_non_minimal_solve", "ssfm_decompose", "ssfm_decompose_rescaled",
-    "ssfm_lo_shuffle", "ssfm_measure_fp32_peak",
+    "ssfm_lo_shuffle", "ssfm_measure_fp32_peak", "ssfm_measure_fp32_peaks",
     "ssfm_multi_create", "ssfm_multi_destroy", "ssfm_multi_num_devices", "ssfm_partition_pairs", "ssfm_estimate_pairs_multi",
     "ssfm_multi_get_stats", "ssfm_multi_allgather_results", "ssfm_match_pairs", "ssfm_match_get_stats",
 ]
@@ -465,6 +465,12 @@ class Engine:
         t = C.c_double()
         _check(lib().ssfm_measure_fp32_peak(self._h, C.byref(t)))
         return t.value
+
+    def measure_fp32_peaks(self):
+        """(scalar FFMA chain, packed FFMA2 chain) in TFLOP/s"""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().ssfm_measure_fp32_peaks(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
 
 def partition_pairs(offsets, num_shards):

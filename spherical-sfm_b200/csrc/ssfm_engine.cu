@@ -1733,26 +1733,38 @@ int ssfm_lo_shuffle(ssfm_handle h, uint32_t seed, int32_t ncalls, const int32_t*
   return SSFM_OK;
 }
 
-int ssfm_measure_fp32_peak(ssfm_handle h, double* tflops) {
-  if (!h || !tflops) return fail(SSFM_ERR_INVALID, "bad argument");
+int ssfm_measure_fp32_peaks(ssfm_handle h, double* scalar_tflops, double* packed_tflops) {
+  if (!h || !scalar_tflops || !packed_tflops) return fail(SSFM_ERR_INVALID, "bad argument");
   SSFM_CK(cudaSetDevice(h->device));
   const int threads = 256, blocks = h->num_sms * 8, iters = 4096;
   TmpGuard g;
   SSFM_TMP(float, b_o, (size_t)threads * blocks) SSFM_KEEP(g, b_o)
   float* d = (float*)g.ptrs[0];
-  double best = 0.0;
-  for (int rep = 0; rep < 5; ++rep) {
-    SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
-    k_fma_peak<<<blocks, threads, 0, h->stream>>>(d, iters, 1.000001f, 1e-7f);
-    SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
-    SSFM_CK(cudaStreamSynchronize(h->stream));
-    float ms = 0.f;
-    SSFM_CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
-    const double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
-    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
-  }
+  double best[2] = {0.0, 0.0};
+  for (int packed = 0; packed < 2; ++packed)
+    for (int rep = 0; rep < 5; ++rep) {
+      SSFM_CK(cudaEventRecord(h->ev[0], h->stream));
+      if (packed) k_fma2_peak<<<blocks, threads, 0, h->stream>>>(d, iters, 1.000001f, 1e-7f);
+      else k_fma_peak<<<blocks, threads, 0, h->stream>>>(d, iters, 1.000001f, 1e-7f);
+      SSFM_CK(cudaEventRecord(h->ev[1], h->stream));
+      SSFM_CK(cudaStreamSynchronize(h->stream));
+      float ms = 0.f;
+      SSFM_CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+      // 64 FMA per iteration and thread (scalar) or 64 packed FMA = 128 FMA (packed), 2 flop each
+      const double flops = 2.0 * 64.0 * (packed ? 2.0 : 1.0) * (double)iters * threads * blocks;
+      if (rep > 0) best[packed] = std::max(best[packed], flops / (ms * 1e-3) / 1e12);
+    }
   SSFM_CK(cudaGetLastError());
-  *tflops = best;
+  *scalar_tflops = best[0];
+  *packed_tflops = best[1];
+  return SSFM_OK;
+}
+
+int ssfm_measure_fp32_peak(ssfm_handle h, double* tflops) {  // the roofline denominator: the higher of the two
+  if (!tflops) return fail(SSFM_ERR_INVALID, "bad argument");
+  double a = 0.0, b = 0.0;
+  if (int rc = ssfm_measure_fp32_peaks(h, &a, &b)) return rc;
+  *tflops = std::max(a, b);
   return SSFM_OK;
 }
 

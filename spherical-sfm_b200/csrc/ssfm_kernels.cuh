@@ -1164,4 +1164,27 @@ __global__ void k_fma_peak(float* out, int iters, float a, float b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// The same probe on the packed instruction (fma.rn.f32x2 -> FFMA2): 8 independent chains of two floats per thread.
+__global__ void k_fma2_peak(float* out, int iters, float a, float b) {
+  const f32x2 A = pack2(a, a), B = pack2(b, b);
+  f32x2 x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = pack2((float)threadIdx.x + k, (float)threadIdx.x - k);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) x[k] = fma2(x[k], A, B);
+    }
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float lo, hi;
+    unpack2(x[k], lo, hi);
+    acc += lo + hi;
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace ssfm
