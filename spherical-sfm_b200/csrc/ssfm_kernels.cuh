@@ -294,8 +294,8 @@ constexpr int kStages = 2;
 constexpr bool kPackedScoring = SSFM_PACKED_SCORING != 0;  // unit-z scoring loop on FFMA2 (0: the scalar FFMA loop)
 
 // UNITZ = every ray of the batch has z == 1 exactly (the pipeline's K^-1 (x,y,1) rays and the
-// reference's generator): one float4 (u0,u1,v0,v1) per correspondence and 19 FMA-pipe ops per
-// evaluation; otherwise two float4 (u.xyz, v.xyz) and 24.
+// reference's generator): one float4 (u0,u1,v0,v1) per correspondence and 14 FMA-pipe instructions per PAIR of
+// evaluations in the packed loop (score_stream); otherwise two float4 (u.xyz, v.xyz) and 24 per evaluation.
 #ifndef SSFM_SCORE_EXPANDED
 #define SSFM_SCORE_EXPANDED 2  // unit-z packed loop: 0 = plain, 1 = v-side denominator expanded, 2 = d and the whole denominator
 #endif                         // expanded over per-correspondence products computed once per tile (score_stream)
