@@ -105,6 +105,18 @@ void hs_least_squares(const double* rays, const int* sample, int n, int inward, 
   least_squares(cx, rays, sample, n, inward != 0, E);
 }
 
+// What k_refit_big / k_refit_small / k_refit_long do since round 2: gather the refit's correspondences once into a
+// contiguous copy and run the same minimiser on it with sample == NULL (identity).  mode 1: plain; mode 2: the
+// deferred path's arithmetic (one lane, lane-parallel after `handover` iterations -- with one lane both are the same sums).
+void hs_least_squares_staged(const double* rays, const int* sample, int n, int inward, double* E, int mode, int handover) {
+  SerialCtx cx;
+  std::vector<double> staged((size_t)(n > 0 ? n : 1) * 6);
+  for (int i = 0; i < n; ++i)
+    for (int q = 0; q < 6; ++q) staged[6 * (size_t)i + q] = rays[6 * (size_t)sample[i] + q];
+  if (mode == 2) least_squares_as_deferred(cx, staged.data(), (const int*)0, n, inward != 0, E, handover);
+  else least_squares(cx, staged.data(), (const int*)0, n, inward != 0, E);
+}
+
 void hs_lo_shuffle(uint32_t seed, int ncalls, const int* sizes, const int* targets, int* out) {
   std::vector<uint32_t> mt(625);
   mt19937_seed(mt.data(), seed);

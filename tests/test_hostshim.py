@@ -98,6 +98,28 @@ def test_device_decompose_and_refit(S, orc, shim):
     assert worst_d < 1e-9 and worst_l < 1e-8
 
 
+def test_staged_refit_is_bit_identical(S, shim):
+    """The refit kernels gather a refit's correspondences once into a contiguous copy (shared memory / an L1-resident slot)
+    and minimise over that copy with an identity sample list: same values, same order, so the refined model must be
+    bit-identical to the gathered-on-every-pass version -- also through the small-batch inline path's entry
+    (least_squares_as_deferred), whatever the hand-over iteration."""
+    for tr in range(12):
+        rng = S.problems.make_rng(17, tr)
+        inward = bool(tr % 2)
+        pr = S.problems.make_problem(rng, 300, inward, None, 1 / 600, 90, 20.0)
+        inl = np.nonzero(pr.inlier_mask)[0].astype(np.int32)
+        if tr % 3 == 0:
+            inl = inl[:21]  # the size of an LO refit
+        E0 = np.ascontiguousarray((pr.E / np.linalg.norm(pr.E)).reshape(9))
+        E0 = E0 + 1e-3 * rng.standard_normal(9)
+        want = E0.copy()
+        shim.lib.hs_least_squares(shim.dp(pr.rays), shim.ip(inl), len(inl), int(inward), shim.dp(want))
+        for mode, handover in ((1, 0), (2, 0), (2, 3), (2, 24)):
+            got = E0.copy()
+            shim.lib.hs_least_squares_staged(shim.dp(pr.rays), shim.ip(inl), len(inl), int(inward), shim.dp(got), mode, handover)
+            assert got.tobytes() == want.tobytes(), (tr, mode, handover)
+
+
 def test_required_iterations(shim):
     import math
     for w in (0.0, 1.0, 0.05, 0.3, 0.31234, 0.9, 0.999999, 1e-9):
