@@ -4,7 +4,10 @@ Follows examples/six_point_estimator.{h,cpp} of the reference:
   MinimalSolver          six_point_estimator.cpp:93-119  (poselib::relpose_6pt_shared_focal, :104)
   EvaluateModelOnPoint   :78-91   (E = skew3(t) * so3exp(r); the focal is NOT used, as upstream)
   SampsonError functor   :25-76   (F = Kinv E Kinv, Kinv = diag(1,1,focal)) -> `focal_scoring=True`
-and evaluation/vanilla_ransac.h:23-99 for the driver (config C4 runs VanillaMSAC).
+and evaluation/vanilla_ransac.h:23-99 for the driver (config C4 runs VanillaMSAC);
+  NonMinimalSolver       :121-144, LeastSquares :146-192 and include/RansacLib/ransac.h:127-276, 341-420 for the LO-MSAC
+                         driver around the same estimator (`lo_msac`; its mt19937 / uniform_int replay is checked against the
+                         C++ oracle's, its control flow is a restatement: same status as the rest of this file).
 
 PARITY UNPINNED: the arithmetic of the minimal solver lives in PoseLib (vlarsson/PoseLib, cloned at an
 unpinned HEAD by docker/Dockerfile:58-62, absent from /root/reference and from this image); the reference has
