@@ -267,6 +267,12 @@ def build(ref=True, force=False):
             subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-pthread"] + inc +
                                   ["-o", out3, os.path.join(_DIR, "ref_tri.cpp")] +
                                   [os.path.join(refroot, "src", f) for f in ("triangulation_estimator.cpp", "sfm_types.cpp", "so3.cpp")])
+        # the reference's LocallyOptimizedMSAC header around a toy line estimator: pins sixpt_oracle.lo_msac_generic
+        out7 = os.path.join(_DIR, "_ref", "libssfm_reftoy.so")
+        toy = os.path.join(_DIR, "ref_toy.cpp")
+        if force or not os.path.exists(out7) or os.path.getmtime(out7) < os.path.getmtime(toy):
+            subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + os.path.join(refroot, "include"),
+                                   "-o", out7, toy])
 
 
 _cache = {}

@@ -6,8 +6,9 @@ Follows examples/six_point_estimator.{h,cpp} of the reference:
   SampsonError functor   :25-76   (F = Kinv E Kinv, Kinv = diag(1,1,focal)) -> `focal_scoring=True`
 and evaluation/vanilla_ransac.h:23-99 for the driver (config C4 runs VanillaMSAC);
   NonMinimalSolver       :121-144, LeastSquares :146-192 and include/RansacLib/ransac.h:127-276, 341-420 for the LO-MSAC
-                         driver around the same estimator (`lo_msac`; its mt19937 / uniform_int replay is checked against the
-                         C++ oracle's, its control flow is a restatement: same status as the rest of this file).
+                         driver around the same estimator (`lo_msac` = `lo_msac_generic` + `SixPointEstimator`).  The DRIVER is pinned:
+                         the reference's header compiled around a toy estimator (oracle/ref_toy.cpp) gives the same
+                         trajectories as lo_msac_generic; the estimator's arithmetic stays unpinned as below.
 
 PARITY UNPINNED: the arithmetic of the minimal solver lives in PoseLib (vlarsson/PoseLib, cloned at an
 unpinned HEAD by docker/Dockerfile:58-62, absent from /root/reference and from this image); the reference has
@@ -343,70 +344,57 @@ def shuffle_and_resize(v, target, rng):
     return v[:target] + [0] * max(0, target - n)
 
 
-def lo_msac(rays, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.9999, num_lo_steps=10,
-            threshold_multiplier=np.sqrt(2.0), num_lsq_iterations=4, min_sample_multiplicator=7, non_min_sample_multiplier=3,
-            lo_starting_iterations=50, final_least_squares=False, focal_scoring=False, solve=None):
-    """LocallyOptimizedMSAC::EstimateModel with SixPointEstimator (min_sample_size 6, non_minimal_sample_size 7).
-    sampler(iteration) -> 6 indices (the product's Philox stream); solve(rays6) substitutes the minimal solver."""
-    solve = solve or minimal_solver
-    n = len(rays)
+def lo_msac_generic(est, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.9999, num_lo_steps=10,
+                    threshold_multiplier=np.sqrt(2.0), num_lsq_iterations=4, min_sample_multiplicator=7,
+                    non_min_sample_multiplier=3, lo_starting_iterations=50, final_least_squares=False):
+    """LocallyOptimizedMSAC::EstimateModel (include/RansacLib/ransac.h:127-276) with LocalOptimization (:341-407) and
+    LeastSquaresFit (:409-420), for any estimator object with
+        n, min_sample_size, non_minimal_sample_size,
+        minimal_solver(sample) -> list of models, non_minimal_solver(sample) -> model or None,
+        least_squares(sample, model) -> model, errors(model) -> squared error of every data point.
+    sampler(iteration) -> minimal sample.  Pinned against the header itself on a toy estimator both sides can compute
+    (oracle/ref_toy.cpp, tests/test_sixpt.py::test_restated_lo_msac_driver_equals_reference_header)."""
+    n, k_min, k_nonmin = est.n, est.min_sample_size, est.non_minimal_sample_size
     BIG = np.finfo(float).max
     st = dict(num_iterations=0, best_num_inliers=0, best_model_score=BIG, inlier_ratio=0.0, inliers=np.zeros(0, int),
-              model=None, number_lo_iterations=0, status=1 if n < 6 else 2, lm_calls=0)
-    if n < 6:
+              model=None, number_lo_iterations=0, status=1 if n < k_min else 2, lm_calls=0)
+    if n < k_min:
         return st
     rng = Mt19937(seed)
 
-    def G_of(m):
-        return scoring_matrix(m, focal_scoring)
-
     def score_model(m):  # ScoreModel :295-303 (sequential sum)
-        e = np.minimum(sampson(G_of(m), rays), thr2)
+        e = np.minimum(est.errors(m), thr2)
         s = 0.0
         for x in e:
             s += x
         return s
 
     def get_inliers(m, thr):
-        return np.nonzero(sampson(G_of(m), rays) < thr)[0]
+        return np.nonzero(est.errors(m) < thr)[0]
 
     def lsq(m, sample):
         st["lm_calls"] += 1
-        return least_squares(rays, sample, m)[0]
+        return est.least_squares(sample, m)
 
     def least_squares_fit(thresh, m):  # :409-420
         inl = get_inliers(m, thresh)
-        if len(inl) < 6:
+        if len(inl) < k_min:
             return m
-        k = min(min_sample_multiplicator * 6, len(inl))
+        k = min(min_sample_multiplicator * k_min, len(inl))
         return lsq(m, shuffle_and_resize(inl, k, rng))
 
-    def non_minimal_solver(sample):  # six_point_estimator.cpp:121-144: the first six of the sample, summed error over all
-        sols = solve(rays[sample[:6]])
-        if not sols:
-            return None
-        best, best_score = 0, np.inf
-        for i, m in enumerate(sols):
-            e = sampson(G_of(m), rays[sample])
-            s = 0.0
-            for x in e:
-                s += x
-            if s < best_score:
-                best_score, best = s, i
-        return sols[best]
-
     def local_optimization(m_best, score_best):  # :341-407
-        if 7 > n:
+        if k_nonmin > n:
             return m_best, score_best
         m_init = least_squares_fit(thr2 * threshold_multiplier, m_best)
         score = score_model(m_init)
         if score < score_best:
             score_best, m_best = score, m_init
         base = get_inliers(m_init, thr2 * threshold_multiplier)
-        non_min = max(7, min(6 * non_min_sample_multiplier, len(base) // 2))
+        non_min = max(k_nonmin, min(k_min * non_min_sample_multiplier, len(base) // 2))
         for _ in range(num_lo_steps):
             sample = shuffle_and_resize(base, non_min, rng)
-            m = non_minimal_solver(np.asarray(sample, int))
+            m = est.non_minimal_solver(np.asarray(sample, int))
             if m is None:
                 continue
             score = score_model(m)
@@ -430,7 +418,7 @@ def lo_msac(rays, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.
         st["best_num_inliers"] = len(st["inliers"])
         st["inlier_ratio"] = st["best_num_inliers"] / n
         if update_max:
-            limit = required_iterations(st["inlier_ratio"], 1.0 - prob, 6, min_iters, max_iters)
+            limit = required_iterations(st["inlier_ratio"], 1.0 - prob, k_min, min_iters, max_iters)
 
     limit = max(max_iters, min_iters)
     best_min, best_min_score = None, BIG
@@ -440,7 +428,7 @@ def lo_msac(rays, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.
             st["number_lo_iterations"] += 1
             st["model"], st["best_model_score"] = local_optimization(st["model"], st["best_model_score"])
             refresh(True)
-        models = solve(rays[sampler(it)])
+        models = est.minimal_solver(sampler(it))
         if models:
             scores = [score_model(m) for m in models]
             k = int(np.argmin(scores))  # first minimum, like the strict '<' scan (:278-293); NaN scores never win there
@@ -473,6 +461,43 @@ def lo_msac(rays, sampler, thr2, seed=0, min_iters=100, max_iters=10000, prob=0.
             st["best_model_score"], st["model"] = score, refined
             refresh(False)
     return st
+
+
+class SixPointEstimator:
+    """examples/six_point_estimator.{h,cpp} as an estimator object for lo_msac_generic: min_sample_size 6,
+    non_minimal_sample_size 7 (six_point_estimator.h:21-23)."""
+    min_sample_size, non_minimal_sample_size = 6, 7
+
+    def __init__(self, rays, focal_scoring=False, solve=None):
+        self.rays, self.n, self.focal_scoring, self.solve = rays, len(rays), focal_scoring, solve or minimal_solver
+
+    def errors(self, m):
+        return sampson(scoring_matrix(m, self.focal_scoring), self.rays)
+
+    def minimal_solver(self, sample):  # :93-119: the first six entries of the sample
+        return self.solve(self.rays[np.asarray(sample, int)[:6]])
+
+    def non_minimal_solver(self, sample):  # :121-144: MinimalSolver on the sample, summed error over the sample decides
+        sols = self.minimal_solver(sample)
+        if not sols:
+            return None
+        best, best_score = 0, np.inf
+        for i, m in enumerate(sols):
+            s = 0.0
+            for x in sampson(scoring_matrix(m, self.focal_scoring), self.rays[sample]):
+                s += x
+            if s < best_score:
+                best_score, best = s, i
+        return sols[best]
+
+    def least_squares(self, sample, m):  # :146-192
+        return least_squares(self.rays, sample, m)[0]
+
+
+def lo_msac(rays, sampler, thr2, focal_scoring=False, solve=None, **options):
+    """LocallyOptimizedMSAC around SixPointEstimator.  sampler(iteration) -> 6 indices (the product's Philox stream);
+    solve(rays6) substitutes the minimal solver; options as lo_msac_generic."""
+    return lo_msac_generic(SixPointEstimator(rays, focal_scoring, solve), sampler, thr2, **options)
 
 
 def make_problem(rng, n, focal, outlier_frac=0.0, noise_px=0.0, max_angle_deg=20.0):

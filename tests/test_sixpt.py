@@ -128,6 +128,113 @@ def test_lo_msac_product_on_host_matches_oracle(shim, S):
         assert abs(got["score"] - st["best_model_score"]) <= 1e-8 * st["best_model_score"], seed
 
 
+class _ToyLine:
+    """The toy estimator of oracle/ref_toy.cpp (a 2-D line: minimal = through two points (+ a second, shifted hypothesis),
+    non-minimal and LeastSquares = closed-form total least squares with sequential sums), restated for lo_msac_generic."""
+    min_sample_size, non_minimal_sample_size = 2, 3
+
+    def __init__(self, xy):
+        self.xy, self.n = xy, len(xy)
+
+    def errors(self, m):
+        d = m[0] * self.xy[:, 0] + m[1] * self.xy[:, 1] + m[2]
+        return d * d
+
+    def minimal_solver(self, sample):
+        import math
+        (x0, y0), (x1, y1) = self.xy[sample[0]], self.xy[sample[1]]
+        dx, dy = x1 - x0, y1 - y0
+        nrm = math.sqrt(dx * dx + dy * dy)
+        if not nrm > 0:
+            return []
+        a, b = dy / nrm, -dx / nrm
+        c = -(a * x0 + b * y0)
+        return [(a, b, c), (a, b, c + 0.25)]
+
+    def _fit(self, sample):
+        import math
+        m = len(sample)
+        if m < 2:
+            return None
+        mx = my = 0.0
+        for i in sample:
+            mx += self.xy[i, 0]
+            my += self.xy[i, 1]
+        mx /= m
+        my /= m
+        sxx = sxy = syy = 0.0
+        for i in sample:
+            dx, dy = self.xy[i, 0] - mx, self.xy[i, 1] - my
+            sxx += dx * dx
+            sxy += dx * dy
+            syy += dy * dy
+        if sxx + syy <= 0:
+            return None
+        th = 0.5 * math.atan2(2 * sxy, sxx - syy)
+        a, b = -math.sin(th), math.cos(th)
+        return (a, b, -(a * mx + b * my))
+
+    def non_minimal_solver(self, sample):
+        return self._fit([int(i) for i in sample])
+
+    def least_squares(self, sample, m):
+        r = self._fit([int(i) for i in sample])
+        return m if r is None else r
+
+
+def test_restated_lo_msac_driver_equals_reference_header():
+    """The Python restatement of LocallyOptimizedMSAC that drives the six-point oracle (sixpt_oracle.lo_msac_generic) against the
+    reference's own include/RansacLib/ransac.h, compiled unmodified around the same toy estimator (oracle/_ref/libssfm_reftoy.so):
+    identical iteration counts, LO counts, inlier lists, scores and models over option sets that reach every branch -- the LO at
+    lo_starting_iterations_ (:166-177), the LO after a loop that ends before it (:246-257), final_least_squares_ (:259-275),
+    num_lo_steps 0, samples that resize beyond the inlier list, and the shared mt19937 / uniform_int stream throughout."""
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libssfm_reftoy.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libssfm_reftoy.so not built (needs the reference tree)")
+    lib = C.CDLL(lib_path)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    cases = [  # (n, outlier fraction, noise, options)
+        (200, 0.4, 0.01, dict()),
+        (200, 0.6, 0.02, dict(num_lo_steps=3, num_lsq_iterations=2, lo_starting_iterations=10, final_least_squares=True)),
+        (60, 0.3, 0.01, dict(num_lo_steps=2, num_lsq_iterations=3, lo_starting_iterations=500, min_iters=40, max_iters=40,
+                             final_least_squares=True)),
+        (120, 0.5, 0.02, dict(num_lo_steps=0, num_lsq_iterations=0, final_least_squares=True)),
+        (12, 0.2, 0.005, dict(num_lo_steps=4, lo_starting_iterations=5, min_iters=30, max_iters=200)),
+    ]
+    for ci, (n, outl, noise, kw) in enumerate(cases):
+        for seed in range(4):
+            rng = np.random.default_rng(1000 * ci + seed)
+            t = rng.uniform(-1, 1, n)
+            ang = rng.uniform(0, np.pi)
+            xy = np.stack([t * np.cos(ang) + 0.3, t * np.sin(ang) - 0.2], 1) + noise * rng.standard_normal((n, 2))
+            out = rng.random(n) < outl
+            xy[out] = rng.uniform(-1.5, 1.5, (int(out.sum()), 2))
+            xy = np.ascontiguousarray(xy)
+            thr2 = (3 * noise) ** 2
+            o = dict(num_lo_steps=10, num_lsq_iterations=4, min_sample_multiplicator=7, non_min_sample_multiplier=3,
+                     lo_starting_iterations=50, final_least_squares=False, min_iters=100, max_iters=10000)
+            o.update(kw)
+            model, score, stats, inl = np.zeros(3), C.c_double(), np.zeros(3, np.int32), np.zeros(n, np.int32)
+            lib.ref_toy_lomsac.restype = C.c_int
+            ninl = lib.ref_toy_lomsac(xy.ctypes.data_as(dp), n, C.c_double(thr2), C.c_uint(7 + seed), o["num_lo_steps"],
+                                      o["num_lsq_iterations"], o["min_sample_multiplicator"], o["non_min_sample_multiplier"],
+                                      C.c_uint(o["lo_starting_iterations"]), int(o["final_least_squares"]), C.c_uint(o["min_iters"]),
+                                      C.c_uint(o["max_iters"]), model.ctypes.data_as(dp), C.byref(score), stats.ctypes.data_as(ip),
+                                      inl.ctypes.data_as(ip))
+
+            def sampler(it):
+                first = (7 * it) % n
+                return [first, (first + 1 + (13 * it) % (n - 1)) % n]
+            st = X.lo_msac_generic(_ToyLine(xy), sampler, thr2, seed=7 + seed, **o)
+            tag = (ci, seed)
+            assert st["num_iterations"] == stats[0], tag
+            assert st["number_lo_iterations"] == stats[1], tag
+            assert st["best_num_inliers"] == stats[2] == ninl, tag
+            assert st["inliers"].tolist() == inl[:ninl].tolist(), tag
+            assert abs(st["best_model_score"] - score.value) <= 1e-12 * max(score.value, 1e-300), tag
+            assert np.abs(np.array(st["model"]) - model).max() < 1e-12, tag
+
+
 def _refit_cases(n_cases, seed):
     rng = np.random.default_rng(seed)
     out = []
