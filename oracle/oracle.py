@@ -272,7 +272,7 @@ def build(ref=True, force=False):
         toy = os.path.join(_DIR, "ref_toy.cpp")
         if force or not os.path.exists(out7) or os.path.getmtime(out7) < os.path.getmtime(toy):
             subprocess.check_call([_compiler(), "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I" + os.path.join(refroot, "include"),
-                                   "-o", out7, toy])
+                                   "-I" + os.path.join(refroot, "evaluation"), "-o", out7, toy])
 
 
 _cache = {}

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <RansacLib/ransac.h>
+#include <vanilla_ransac.h>  // evaluation/vanilla_ransac.h: the driver of config C4
 
 namespace {
 
@@ -92,6 +93,23 @@ extern "C" int ref_toy_lomsac(const double* xy, int n, double thr2, unsigned see
   o.lo_starting_iterations_ = lo_start; o.final_least_squares_ = final_lsq != 0;
   LineEstimator est(xy, n);
   ransac_lib::LocallyOptimizedMSAC<Line, std::vector<Line>, LineEstimator, ToySampler<LineEstimator>> ransac;
+  ransac_lib::RansacStatistics st;
+  Line best;
+  const int ninl = ransac.EstimateModel(o, est, &best, &st);
+  model3[0] = best.a; model3[1] = best.b; model3[2] = best.c;
+  *score = st.best_model_score;
+  stats3[0] = (int)st.num_iterations; stats3[1] = st.number_lo_iterations; stats3[2] = st.best_num_inliers;
+  for (size_t i = 0; i < st.inlier_indices.size(); ++i) inliers[i] = st.inlier_indices[i];
+  return ninl;
+}
+
+// evaluation/vanilla_ransac.h:23-99 (the driver config C4 runs around the six-point estimator), same toy estimator.
+extern "C" int ref_toy_vanilla(const double* xy, int n, double thr2, unsigned seed, unsigned min_iters, unsigned max_iters,
+                               double* model3, double* score, int* stats3, int* inliers) {
+  ransac_lib::RansacOptions o;
+  o.min_num_iterations_ = min_iters; o.max_num_iterations_ = max_iters; o.squared_inlier_threshold_ = thr2; o.random_seed_ = seed;
+  LineEstimator est(xy, n);
+  ransac_lib::VanillaMSAC<Line, std::vector<Line>, LineEstimator, ToySampler<LineEstimator>> ransac;
   ransac_lib::RansacStatistics st;
   Line best;
   const int ninl = ransac.EstimateModel(o, est, &best, &st);

@@ -269,42 +269,47 @@ def required_iterations(w, eta, k, lo, hi):  # include/RansacLib/utils.h:110-140
     return max(lo, min(int(n), hi))
 
 
-def vanilla_msac(rays, sampler, thr2, min_iters=100, max_iters=10000, prob=0.9999, focal_scoring=False,
-                 scoring_of=None):
-    """evaluation/vanilla_ransac.h:23-99 with the six-point estimator.  sampler(iteration) -> 6 indices.
-    scoring_of(model) -> 3x3 lets a test substitute the product's scoring matrix for its own."""
-    n = len(rays)
+def vanilla_msac_generic(est, sampler, thr2, min_iters=100, max_iters=10000, prob=0.9999):
+    """evaluation/vanilla_ransac.h:23-99 for any estimator object (see lo_msac_generic for the interface).  Pinned against the
+    header itself on a toy estimator (oracle/ref_toy.cpp, test_restated_vanilla_msac_driver_equals_reference_header)."""
+    n, k_min = est.n, est.min_sample_size
     st = dict(num_iterations=0, best_num_inliers=0, best_model_score=np.finfo(float).max, inlier_ratio=0.0,
-              inliers=np.zeros(0, int), model=None, evals=0, status=1 if n < 6 else 2)
-    if n < 6:
+              inliers=np.zeros(0, int), model=None, evals=0, status=1 if n < k_min else 2)
+    if n < k_min:
         return st
     limit = max(max_iters, min_iters)
     best_min = np.finfo(float).max
     it = 0
     while it < limit:
-        models = minimal_solver(rays[sampler(it)])
+        models = est.minimal_solver(sampler(it))
         if models:
             st["evals"] += len(models) * n
-            scores = []
-            for m in models:
-                E = scoring_of(m) if scoring_of else scoring_matrix(m, focal_scoring)
-                scores.append(np.minimum(sampson(E, rays), thr2).sum())  # NaN-propagating like std::min(err, thr)
+            scores = [np.minimum(est.errors(m), thr2).sum() for m in models]  # NaN-propagating like std::min(err, thr)
             k = int(np.argmin(scores))  # first minimum wins, like the strict '<' scan (ransac.h:278-293)
             if scores[k] < best_min:
                 best_min = scores[k]
                 st["best_model_score"] = scores[k]
                 st["model"] = models[k]
-                E = scoring_of(models[k]) if scoring_of else scoring_matrix(models[k], focal_scoring)
-                err = sampson(E, rays)
+                err = est.errors(models[k])
                 st["errors"] = err
                 st["inliers"] = np.nonzero(err < thr2)[0]
                 st["best_num_inliers"] = len(st["inliers"])
                 st["inlier_ratio"] = st["best_num_inliers"] / n
-                limit = required_iterations(st["inlier_ratio"], 1.0 - prob, 6, min_iters, max_iters)
+                limit = required_iterations(st["inlier_ratio"], 1.0 - prob, k_min, min_iters, max_iters)
                 st["status"] = 0
         it += 1
     st["num_iterations"] = it
     return st
+
+
+def vanilla_msac(rays, sampler, thr2, min_iters=100, max_iters=10000, prob=0.9999, focal_scoring=False,
+                 scoring_of=None):
+    """evaluation/vanilla_ransac.h:23-99 with the six-point estimator.  sampler(iteration) -> 6 indices.
+    scoring_of(model) -> 3x3 lets a test substitute the product's scoring matrix for its own."""
+    est = SixPointEstimator(rays, focal_scoring)
+    if scoring_of is not None:
+        est.errors = lambda m: sampson(scoring_of(m), rays)
+    return vanilla_msac_generic(est, sampler, thr2, min_iters, max_iters, prob)
 
 
 # ---------------------------------------------------------------------------------------------------------------

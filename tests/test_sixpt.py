@@ -235,6 +235,42 @@ def test_restated_lo_msac_driver_equals_reference_header():
             assert np.abs(np.array(st["model"]) - model).max() < 1e-12, tag
 
 
+def test_restated_vanilla_msac_driver_equals_reference_header():
+    """The driver of config C4: evaluation/vanilla_ransac.h compiled unmodified around the toy estimator against its Python
+    restatement (sixpt_oracle.vanilla_msac_generic, what the six-point oracle and the device tests run): identical iteration
+    counts, inlier lists, scores and models, including runs that stop at min / max iterations and a 12-point problem."""
+    lib_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libssfm_reftoy.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("oracle/_ref/libssfm_reftoy.so not built (needs the reference tree)")
+    lib = C.CDLL(lib_path)
+    lib.ref_toy_vanilla.restype = C.c_int
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    for ci, (n, outl, noise, min_it, max_it) in enumerate([(200, 0.4, 0.01, 100, 10000), (300, 0.7, 0.02, 100, 10000),
+                                                           (80, 0.5, 0.01, 30, 60), (12, 0.2, 0.005, 20, 500)]):
+        for seed in range(4):
+            rng = np.random.default_rng(2000 * ci + seed)
+            t = rng.uniform(-1, 1, n)
+            ang = rng.uniform(0, np.pi)
+            xy = np.stack([t * np.cos(ang) + 0.3, t * np.sin(ang) - 0.2], 1) + noise * rng.standard_normal((n, 2))
+            out = rng.random(n) < outl
+            xy[out] = rng.uniform(-1.5, 1.5, (int(out.sum()), 2))
+            xy = np.ascontiguousarray(xy)
+            thr2 = (3 * noise) ** 2
+            model, score, stats, inl = np.zeros(3), C.c_double(), np.zeros(3, np.int32), np.zeros(n, np.int32)
+            ninl = lib.ref_toy_vanilla(xy.ctypes.data_as(dp), n, C.c_double(thr2), C.c_uint(seed), C.c_uint(min_it), C.c_uint(max_it),
+                                       model.ctypes.data_as(dp), C.byref(score), stats.ctypes.data_as(ip), inl.ctypes.data_as(ip))
+
+            def sampler(it):
+                first = (7 * it) % n
+                return [first, (first + 1 + (13 * it) % (n - 1)) % n]
+            st = X.vanilla_msac_generic(_ToyLine(xy), sampler, thr2, min_iters=min_it, max_iters=max_it)
+            tag = (ci, seed)
+            assert st["num_iterations"] == stats[0] and st["best_num_inliers"] == stats[2] == ninl, tag
+            assert st["inliers"].tolist() == inl[:ninl].tolist(), tag
+            assert abs(st["best_model_score"] - score.value) <= 1e-12 * max(score.value, 1e-300), tag
+            assert np.abs(np.array(st["model"]) - model).max() < 1e-12, tag
+
+
 def _refit_cases(n_cases, seed):
     rng = np.random.default_rng(seed)
     out = []
